@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE — ctypes bindings for the CPU oracle and the reference harness.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import this
+package; the product (``pgrc_b200``) never does.
+
+* :func:`oracle_map_reads`  -> ``oracle/libpgrc_oracle.so`` (plain-C restatement, pgrc_oracle.c)
+* :func:`ref_map_reads`     -> ``oracle/_ref/libpgrc_ref.so`` (the reference's own classes
+  behind oracle/ref_harness.cpp; present only if it was built where /root/reference exists)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "libpgrc_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libpgrc_ref.so")
+
+NOT_MATCHED_POSITION = np.uint64(0xFFFFFFFFFFFFFFFF)
+NOT_MATCHED_COUNT = 255
+
+
+def build(ref: bool = True) -> None:
+    """Compile the C restatement and, where /root/reference exists, the reference harness."""
+    subprocess.run(["make", "-s", "-C", _HERE, "oracle"], check=True)
+    if ref and os.path.isdir("/root/reference/matching"):
+        subprocess.run(["make", "-s", "-j8", "-C", _HERE, "ref"], check=True)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [("matched", ctypes.c_uint64), ("better", ctypes.c_uint64),
+                ("false_matches", ctypes.c_uint64), ("per_mm", ctypes.c_uint64 * 256),
+                ("n_patterns", ctypes.c_uint64), ("n_events", ctypes.c_uint64),
+                ("n_verified", ctypes.c_uint64), ("n_cross_strand_skips", ctypes.c_uint64)]
+
+
+@dataclass
+class MatchResult:
+    pos: np.ndarray          # uint64, NOT_MATCHED_POSITION when unmatched
+    rc: np.ndarray           # uint8 0/1
+    mm: np.ndarray           # uint8, 255 when unmatched
+    matched: int = 0
+    better: int = 0
+    false_matches: int = 0
+    per_mm: np.ndarray = field(default_factory=lambda: np.zeros(256, np.uint64))
+    seconds: float = 0.0
+    extra: dict = field(default_factory=dict)
+
+
+_oracle_lib = None
+_ref_lib = None
+
+
+def _oracle():
+    global _oracle_lib
+    if _oracle_lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        lib = ctypes.CDLL(ORACLE_SO)
+        lib.pgo_pack_reads.restype = ctypes.c_int
+        lib.pgo_pack_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+        lib.pgo_map_reads.restype = ctypes.c_int
+        lib.pgo_map_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint32,
+                                      ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                      ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char, ctypes.c_char, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _oracle_lib = lib
+    return _oracle_lib
+
+
+def _ref():
+    global _ref_lib
+    if _ref_lib is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libpgrc_ref.so not built (needs /root/reference)")
+        lib = ctypes.CDLL(REF_SO)
+        lib.pgref_map_reads.restype = ctypes.c_int
+        lib.pgref_map_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint32,
+                                        ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                        ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char, ctypes.c_char,
+                                        ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p]
+        lib.pgref_pack_reads.restype = ctypes.c_int
+        lib.pgref_pack_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+        _ref_lib = lib
+    return _ref_lib
+
+
+def _ascii2d(reads, read_len: int) -> np.ndarray:
+    a = np.ascontiguousarray(reads, dtype=np.uint8)
+    if a.size == 0:
+        return a.reshape(0, read_len)
+    return a.reshape(-1, read_len)
+
+
+def pack_reads(reads_ascii: np.ndarray, read_len: int, with_n: bool, use_ref: bool = False) -> np.ndarray:
+    """ASCII reads (n x L uint8) -> packed reads with the reference's layout."""
+    a = _ascii2d(reads_ascii, read_len)
+    n = a.shape[0]
+    spe = 3 if with_n else 4
+    packed_len = (read_len + spe - 1) // spe
+    out = np.zeros((n, packed_len), np.uint8)
+    if n:
+        fn = _ref().pgref_pack_reads if use_ref else _oracle().pgo_pack_reads
+        r = fn(a.ctypes.data, n, read_len, int(with_n), out.ctypes.data)
+        if r != packed_len:
+            raise ValueError(f"pack_reads failed ({r})")
+    return out
+
+
+def _mode(c: str) -> bytes:
+    return c.encode("ascii")[:1]
+
+
+def oracle_map_reads(text: np.ndarray, lq_packed: np.ndarray, n_packed: np.ndarray | None, read_len: int,
+                     seed: int = 38, min_chars_per_mismatch: int = 3, mode: str = "d",
+                     pre_seed: int = 0, pre_mode: str = "d", rev_compl: bool = True) -> MatchResult:
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    lq = np.ascontiguousarray(lq_packed, dtype=np.uint8)
+    n_lq = lq.shape[0] if lq.size else 0
+    nn = np.ascontiguousarray(n_packed, dtype=np.uint8) if n_packed is not None and len(n_packed) else np.zeros((0, 1), np.uint8)
+    n_n = nn.shape[0] if nn.size else 0
+    n = n_lq + n_n
+    pos = np.empty(n, np.uint64); rc = np.empty(n, np.uint8); mm = np.empty(n, np.uint8)
+    st = _Stats()
+    r = _oracle().pgo_map_reads(text.ctypes.data, text.size, lq.ctypes.data, n_lq, nn.ctypes.data, n_n,
+                                read_len, pre_seed, seed, min_chars_per_mismatch, _mode(pre_mode), _mode(mode),
+                                int(rev_compl), pos.ctypes.data, rc.ctypes.data, mm.ctypes.data, ctypes.byref(st))
+    if r != 0:
+        raise RuntimeError(f"pgo_map_reads failed ({r})")
+    return MatchResult(pos, rc, mm, st.matched, st.better, st.false_matches,
+                       np.frombuffer(bytes(st.per_mm), np.uint64).copy(),
+                       extra={"n_patterns": st.n_patterns, "n_events": st.n_events, "n_verified": st.n_verified,
+                              "n_cross_strand_skips": st.n_cross_strand_skips})
+
+
+def ref_map_reads(text: np.ndarray, lq_ascii: np.ndarray, n_ascii: np.ndarray | None, read_len: int,
+                  seed: int = 38, min_chars_per_mismatch: int = 3, mode: str = "d",
+                  pre_seed: int = 0, pre_mode: str = "d", rev_compl: bool = True, threads: int = 0) -> MatchResult:
+    """Runs the reference's own matcher classes (ASCII reads in, as addRead takes them)."""
+    # one extra readable byte: the reference reads txt[len] once (HashMatcher.h:62)
+    buf = np.zeros(np.asarray(text).size + 1, np.uint8)
+    buf[:-1] = np.asarray(text, dtype=np.uint8)
+    lq = _ascii2d(lq_ascii, read_len)
+    nn = _ascii2d(n_ascii, read_len) if n_ascii is not None and len(n_ascii) else np.zeros((0, read_len), np.uint8)
+    n = lq.shape[0] + nn.shape[0]
+    pos = np.empty(n, np.uint64); rc = np.empty(n, np.uint8); mm = np.empty(n, np.uint8)
+    st = np.zeros(259, np.uint64)
+    secs = ctypes.c_double(0.0)
+    r = _ref().pgref_map_reads(buf.ctypes.data, buf.size - 1, lq.ctypes.data, lq.shape[0], nn.ctypes.data, nn.shape[0],
+                               read_len, pre_seed, seed, min_chars_per_mismatch, _mode(pre_mode), _mode(mode),
+                               int(rev_compl), threads, pos.ctypes.data, rc.ctypes.data, mm.ctypes.data,
+                               st.ctypes.data, ctypes.byref(secs))
+    if r != 0:
+        raise RuntimeError(f"pgref_map_reads failed ({r})")
+    if not np.array_equal(buf[:-1], np.asarray(text, dtype=np.uint8)):
+        raise RuntimeError("reference left the text modified")
+    return MatchResult(pos, rc, mm, int(st[0]), int(st[1]), int(st[2]), st[3:].copy(), seconds=secs.value)

@@ -1,0 +1,441 @@
+/* TEST INFRASTRUCTURE — CPU oracle (see pgrc_oracle.h for scope and parity status).
+ *
+ * Sequential restatement of PgRC's stage-4 read-vs-pseudogenome matching:
+ *   pattern table     ConstantLengthPatternsOnTextHashMatcher.cpp:23-42  (addReadsSetOfPatterns)
+ *   text iteration    ConstantLengthPatternsOnTextHashMatcher.h:42-68    (iterateOver / moveNext)
+ *   rolling hash      rollinghash/cyclichash.h:29-35,100-123             (CyclicHash<uint32>(n, 32))
+ *   exact matcher     ReadsMatchers.cpp:190-230
+ *   approx matcher    ReadsMatchers.cpp:276-341
+ *   pass structure    ReadsMatchers.cpp:162-184
+ *   driver            ReadsMatchers.cpp:693-783 (mapReadsIntoPg, modes 'd'/'D')
+ *   read layout       SymbolsPackingFacility.cpp:147-185, PackedConstantLengthReadsSet.h:40-46
+ *   mismatch count    SymbolsPackingFacility.cpp:344-374 (contract: exact count if <= limit, else 255)
+ *   reverse compl.    utils/helper.cpp:383-393
+ *
+ * Two deliberate differences from a literal transcription, both result-neutral:
+ *  (1) The reference's CharacterHash table is seeded from time()/clock()
+ *      (mersennetwister.cpp:151-175), so only the table-INDEPENDENT collisions are
+ *      reproducible: with word size 32 the symbol at window offset k is rotated by
+ *      (n-1-k) mod 32, hence for n > 32 offsets k and k+32 share a rotation and the hash
+ *      only sees the per-rotation-class symbol parity.  The oracle hashes
+ *      with the same rotate-xor construction on two fixed tables (64-bit key) and then
+ *      confirms every hit by comparing that canonical form explicitly, so its candidate set
+ *      is exactly "Buzhash-equivalent seeds" and does not depend on the oracle's tables.
+ *  (2) std::unordered_multimap is replaced by a sorted array; equal_range order is
+ *      reproduced as reverse insertion order (larger pattern index first), which is what
+ *      libstdc++ does.
+ */
+#include "pgrc_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ read layout (a11) */
+
+static int sym_code4(char c) { /* ACGT order, DividedPCLReadsSets.cpp:6 */
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; }
+    return -1;
+}
+static int sym_code5(char c) { /* ACGNT order, DividedPCLReadsSets.cpp:8 */
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'N': return 3; case 'T': return 4; }
+    return -1;
+}
+static const char SYMS4[4] = {'A', 'C', 'G', 'T'};
+static const char SYMS5[5] = {'A', 'C', 'G', 'N', 'T'};
+
+int pgo_pack_reads(const char *ascii, uint32_t n, uint32_t read_len, int with_n, uint8_t *out) {
+    const uint32_t spe = with_n ? 3 : 4, sigma = with_n ? 5 : 4;
+    const uint32_t packed_len = (read_len + spe - 1) / spe;
+    for (uint32_t i = 0; i < n; i++) {
+        const char *r = ascii + (size_t)i * read_len;
+        uint8_t *o = out + (size_t)i * packed_len;
+        for (uint32_t b = 0; b < packed_len; b++) {
+            /* packSymbols / packSuffixSymbols: value = ((s0*σ + s1)*σ + ...), missing tail = 0 */
+            uint32_t v = 0;
+            for (uint32_t j = 0; j < spe; j++) {
+                uint32_t p = b * spe + j;
+                v *= sigma;
+                if (p < read_len) {
+                    int c = with_n ? sym_code5(r[p]) : sym_code4(r[p]);
+                    if (c < 0) return -1;
+                    v += (uint32_t)c;
+                }
+            }
+            o[b] = (uint8_t)v;
+        }
+    }
+    return (int)packed_len;
+}
+
+/* reverseValue(sequence, pos): symbol at position pos of a packed read */
+static char packed_symbol(const uint8_t *packed, uint32_t pos, int with_n) {
+    if (!with_n) {
+        uint8_t v = packed[pos >> 2];
+        return SYMS4[(v >> (2 * (3 - (pos & 3)))) & 3];
+    } else {
+        uint8_t v = packed[pos / 3];
+        uint32_t j = pos % 3;
+        uint32_t d = j == 0 ? v / 25 : (j == 1 ? (v / 5) % 5 : v % 5);
+        return SYMS5[d];
+    }
+}
+
+void pgo_unpack_read(const uint8_t *packed, uint32_t read_len, int with_n, char *out) {
+    for (uint32_t p = 0; p < read_len; p++) out[p] = packed_symbol(packed, p, with_n);
+}
+
+/* SumOfConstantLengthReadsSets view: LQ set (ACGT) then N set (ACGNT) */
+typedef struct {
+    const uint8_t *lq; uint32_t n_lq, lq_stride;
+    const uint8_t *nn; uint32_t n_n, nn_stride;
+    uint32_t read_len;
+} reads_view;
+
+static char read_symbol(const reads_view *rs, uint32_t i, uint32_t pos) {
+    if (i < rs->n_lq) return packed_symbol(rs->lq + (size_t)i * rs->lq_stride, pos, 0);
+    return packed_symbol(rs->nn + (size_t)(i - rs->n_lq) * rs->nn_stride, pos, 1);
+}
+
+static void get_read(const reads_view *rs, uint32_t i, char *out) {
+    for (uint32_t p = 0; p < rs->read_len; p++) out[p] = read_symbol(rs, i, p);
+}
+
+/* countSequenceMismatchesVsUnpacked contract on an unpacked read: Hamming distance with
+ * early exit; returns the exact count if <= limit, else 255. */
+static uint8_t count_mismatches(const char *read, const char *txt, uint32_t len, uint8_t limit) {
+    uint8_t res = 0;
+    for (uint32_t k = 0; k < len; k++)
+        if (read[k] != txt[k])
+            if (res++ >= limit) return PGO_NOT_MATCHED_COUNT;
+    return res;
+}
+
+/* ------------------------------------------------------------------ rolling hash (a1, a2) */
+
+static uint64_t splitmix64(uint64_t *s) {
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+typedef struct {
+    uint32_t t1[256], t2[256]; /* two independent CharacterHash tables */
+    uint32_t n, myr;           /* window length, n % 32 (cyclichash.h:33) */
+    uint32_t h1, h2;
+} buzhash;
+
+static uint32_t rotl32(uint32_t x, uint32_t r) { r &= 31; return r ? (x << r) | (x >> (32 - r)) : x; }
+
+static void buz_init(buzhash *b, uint32_t n) {
+    uint64_t s = 0x5047524342323030ULL; /* fixed seed: results must not depend on it */
+    for (int k = 0; k < 256; k++) { uint64_t z = splitmix64(&s); b->t1[k] = (uint32_t)z; b->t2[k] = (uint32_t)(z >> 32); }
+    b->n = n; b->myr = n % 32; b->h1 = b->h2 = 0;
+}
+static void buz_reset(buzhash *b) { b->h1 = b->h2 = 0; }
+static void buz_eat(buzhash *b, unsigned char c) { /* cyclichash.h:120-123 */
+    b->h1 = rotl32(b->h1, 1) ^ b->t1[c];
+    b->h2 = rotl32(b->h2, 1) ^ b->t2[c];
+}
+static void buz_update(buzhash *b, unsigned char out, unsigned char in) { /* cyclichash.h:100-107 */
+    b->h1 = rotl32(b->h1, 1) ^ rotl32(b->t1[out], b->myr) ^ b->t1[in];
+    b->h2 = rotl32(b->h2, 1) ^ rotl32(b->t2[out], b->myr) ^ b->t2[in];
+}
+static uint64_t buz_value(const buzhash *b) { return ((uint64_t)b->h2 << 32) | b->h1; }
+
+/* Canonical form of a window under CyclicHash(n, 32): for every rotation class
+ * (n-1-k) mod 32 the parity mask of the symbols occurring in it. */
+static void canonical_form(const char *w, uint32_t n, uint8_t form[32]) {
+    memset(form, 0, 32);
+    for (uint32_t k = 0; k < n; k++) {
+        uint8_t bit;
+        switch (w[k]) { case 'A': bit = 1; break; case 'C': bit = 2; break; case 'G': bit = 4; break;
+                        case 'T': bit = 8; break; case 'N': bit = 16; break; default: bit = 32; }
+        form[(n - 1 - k) & 31] ^= bit;
+    }
+}
+
+/* ------------------------------------------------------------------ pattern table (a3, a4) */
+
+typedef struct { uint64_t key; uint32_t idx; } pat_entry;
+
+typedef struct {
+    pat_entry *e; uint64_t n;      /* sorted by (key asc, idx desc) */
+    uint32_t *dir; uint64_t dir_mask; /* open addressing: first index of each key run, or UINT32_MAX */
+    uint32_t pattern_len, parts;
+    buzhash hf;
+} pat_table;
+
+static int cmp_pat(const void *a, const void *b) {
+    const pat_entry *x = (const pat_entry *)a, *y = (const pat_entry *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    if (x->idx != y->idx) return x->idx > y->idx ? -1 : 1; /* LIFO: larger pattern index first */
+    return 0;
+}
+
+static uint64_t dir_slot(uint64_t key, uint64_t mask) {
+    key ^= key >> 33; key *= 0xff51afd7ed558ccdULL; key ^= key >> 33;
+    return key & mask;
+}
+
+static void table_free(pat_table *t) { free(t->e); free(t->dir); t->e = NULL; t->dir = NULL; }
+
+/* addReadsSetOfPatterns(readsSet, partsCount, matchedReadsBitmap) */
+static int table_build(pat_table *t, const reads_view *rs, uint32_t n_reads, uint32_t pattern_len,
+                       uint32_t parts, const uint8_t *skip_bitmap) {
+    memset(t, 0, sizeof(*t));
+    t->pattern_len = pattern_len; t->parts = parts;
+    buz_init(&t->hf, pattern_len);
+    uint64_t cap = (uint64_t)n_reads * parts;
+    t->e = (pat_entry *)malloc((cap ? cap : 1) * sizeof(pat_entry));
+    if (!t->e) return -2;
+    uint64_t m = 0;
+    for (uint32_t i = 0; i < n_reads; i++) {
+        if (skip_bitmap && skip_bitmap[i]) continue;
+        uint32_t offset = 0;
+        for (uint32_t j = 0; j < parts; j++, offset += pattern_len) {
+            buz_reset(&t->hf);
+            for (uint32_t k = 0; k < pattern_len; k++)
+                buz_eat(&t->hf, (unsigned char)read_symbol(rs, i, offset + k));
+            t->e[m].key = buz_value(&t->hf);
+            t->e[m].idx = i * parts + j;
+            m++;
+        }
+    }
+    t->n = m;
+    qsort(t->e, m, sizeof(pat_entry), cmp_pat);
+    uint64_t dsz = 16;
+    while (dsz < 2 * m + 1) dsz <<= 1;
+    t->dir = (uint32_t *)malloc(dsz * sizeof(uint32_t));
+    if (!t->dir) { table_free(t); return -2; }
+    memset(t->dir, 0xFF, dsz * sizeof(uint32_t));
+    t->dir_mask = dsz - 1;
+    for (uint64_t k = 0; k < m; k++) {
+        if (k > 0 && t->e[k].key == t->e[k - 1].key) continue;
+        uint64_t s = dir_slot(t->e[k].key, t->dir_mask);
+        while (t->dir[s] != UINT32_MAX) s = (s + 1) & t->dir_mask;
+        t->dir[s] = (uint32_t)k;
+    }
+    return 0;
+}
+
+/* equal_range(hash): returns first index and count of the run with this key */
+static uint64_t table_lookup(const pat_table *t, uint64_t key, uint64_t *first) {
+    if (t->n == 0) return 0;
+    uint64_t s = dir_slot(key, t->dir_mask);
+    while (t->dir[s] != UINT32_MAX) {
+        uint64_t k = t->dir[s];
+        if (t->e[k].key == key) {
+            uint64_t c = 1;
+            while (k + c < t->n && t->e[k + c].key == key) c++;
+            *first = k;
+            return c;
+        }
+        s = (s + 1) & t->dir_mask;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ matcher state (a5) */
+
+typedef struct {
+    const char *pg; uint64_t pg_len; int rev_compl;
+    const reads_view *rs; uint32_t n_reads, read_len, matching_len;
+    uint64_t *pos; uint8_t *rc; uint8_t *mm; /* readMatchPos, readMatchRC, readMismatchesCount */
+    pgo_stats *st;
+    /* approx parameters */
+    uint32_t part_len, parts; uint8_t max_mm, min_mm;
+    char *cur_read, *seed_buf;
+} matcher;
+
+/* true iff the hash hit is a table-independent (structural) one */
+static int seed_equivalent(const matcher *m, uint32_t read_idx, uint32_t offset, uint32_t n, const char *window) {
+    uint8_t f1[32], f2[32];
+    for (uint32_t k = 0; k < n; k++) m->seed_buf[k] = read_symbol(m->rs, read_idx, offset + k);
+    canonical_form(m->seed_buf, n, f1);
+    canonical_form(window, n, f2);
+    return memcmp(f1, f2, 32) == 0;
+}
+
+/* DefaultReadsExactMatcher::executeMatching (ReadsMatchers.cpp:198-230) */
+static void exact_pass(matcher *m, pat_table *t, const char *txt, int rev_mode) {
+    const uint64_t L = t->pattern_len;
+    if (m->pg_len < L) return;
+    buzhash *hf = &t->hf;
+    buz_reset(hf);
+    for (uint64_t i = 0; i < L; i++) buz_eat(hf, (unsigned char)txt[i]);
+    for (uint64_t p = 0; p + L <= m->pg_len; p++) {
+        uint64_t first, cnt = table_lookup(t, buz_value(hf), &first);
+        unsigned char in = p + L < m->pg_len ? (unsigned char)txt[p + L] : 0; /* txt[len] is the NUL */
+        buz_update(hf, (unsigned char)txt[p], in);
+        for (uint64_t q = 0; q < cnt; q++) {
+            uint32_t r = t->e[first + q].idx;
+            m->st->n_events++;
+            if (!seed_equivalent(m, r, 0, (uint32_t)L, txt + p)) continue; /* accidental: not reproducible */
+            get_read(m->rs, r, m->cur_read);
+            m->st->n_verified++;
+            int equal = memcmp(m->cur_read, txt + p, m->read_len) == 0; /* compareReadWithPattern == 0 */
+            if (equal) {
+                if (m->pos[r] == PGO_NOT_MATCHED_POSITION) {
+                    m->pos[r] = rev_mode ? m->pg_len - (p + m->matching_len) : p;
+                    if (rev_mode) m->rc[r] = 1;
+                    m->st->matched++;
+                } else
+                    m->st->better++;
+            } else
+                m->st->false_matches++;
+        }
+    }
+}
+
+/* DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:297-341) */
+static void approx_pass(matcher *m, pat_table *t, const char *txt, int rev_mode) {
+    const uint64_t L = t->pattern_len;
+    if (m->pg_len < L) return;
+    buzhash *hf = &t->hf;
+    buz_reset(hf);
+    for (uint64_t i = 0; i < L; i++) buz_eat(hf, (unsigned char)txt[i]);
+    for (uint64_t p = 0; p + L <= m->pg_len; p++) {
+        uint64_t first, cnt = table_lookup(t, buz_value(hf), &first);
+        unsigned char in = p + L < m->pg_len ? (unsigned char)txt[p + L] : 0;
+        buz_update(hf, (unsigned char)txt[p], in);
+        for (uint64_t q = 0; q < cnt; q++) {
+            const uint32_t pat = t->e[first + q].idx;
+            const uint32_t r = pat / m->parts;
+            m->st->n_events++;
+            if (!seed_equivalent(m, r, (pat % m->parts) * m->part_len, (uint32_t)L, txt + p)) continue;
+            if (m->mm[r] <= m->min_mm) continue;
+            uint64_t match_pos = p;
+            const uint32_t shift = (pat % m->parts) * m->part_len;
+            if (shift > match_pos) continue;
+            match_pos -= shift;
+            if (match_pos + m->read_len > m->pg_len) continue;
+            const uint64_t rep = rev_mode ? m->pg_len - (match_pos + m->matching_len) : match_pos;
+            if (m->pos[r] == rep) { /* coordinate-only compare */
+                if (m->rc[r] != (uint8_t)(rev_mode ? 1 : 0)) m->st->n_cross_strand_skips++;
+                continue;
+            }
+            const uint8_t limit = m->mm[r] == PGO_NOT_MATCHED_COUNT ? m->max_mm : (uint8_t)(m->mm[r] - 1);
+            get_read(m->rs, r, m->cur_read);
+            m->st->n_verified++;
+            const uint8_t c = count_mismatches(m->cur_read, txt + match_pos, m->matching_len, limit);
+            if (c < m->mm[r]) {
+                if (m->mm[r] == PGO_NOT_MATCHED_COUNT) m->st->matched++;
+                else m->st->better++;
+                m->st->per_mm[m->mm[r]]--;
+                m->st->per_mm[c]++;
+                m->pos[r] = rep;
+                m->rc[r] = (uint8_t)(rev_mode ? 1 : 0);
+                m->mm[r] = c;
+            } else
+                m->st->false_matches++;
+        }
+    }
+}
+
+/* reverseComplementInPlace semantics on a copy (helper.cpp:383-393) */
+static char *reverse_complement(const char *s, uint64_t n) {
+    char *o = (char *)malloc(n + 1);
+    if (!o) return NULL;
+    for (uint64_t i = 0; i < n; i++) {
+        char c = s[n - 1 - i];
+        o[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;
+    }
+    o[n] = 0;
+    return o;
+}
+
+/* matchConstantLengthReads / continueMatchingConstantLengthReads pass structure */
+static int run_passes(matcher *m, pat_table *t, int exact) {
+    if (exact) exact_pass(m, t, m->pg, 0); else approx_pass(m, t, m->pg, 0);
+    if (m->rev_compl) {
+        char *rcpg = reverse_complement(m->pg, m->pg_len);
+        if (!rcpg) return -2;
+        if (exact) exact_pass(m, t, rcpg, 1); else approx_pass(m, t, rcpg, 1);
+        free(rcpg);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ driver (a12, a13) */
+
+static int is_upper_mode(char c) { return c >= 'A' && c <= 'Z'; }
+static char lower_mode(char c) { return is_upper_mode(c) ? (char)(c - 'A' + 'a') : c; }
+
+int pgo_map_reads(const char *text, uint64_t text_len,
+                  const uint8_t *lq_packed, uint32_t n_lq,
+                  const uint8_t *n_packed, uint32_t n_n,
+                  uint32_t read_len, uint32_t pre_seed, uint32_t seed,
+                  uint32_t min_chars_per_mismatch, char pre_mode, char mode, int rev_compl,
+                  uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgo_stats *stats) {
+    if (!text || read_len == 0 || read_len > 255 || seed == 0 || min_chars_per_mismatch == 0) return -1;
+    if (lower_mode(mode) != 'd' || (pre_seed && lower_mode(pre_mode) != 'd')) return -1;
+    pgo_stats local;
+    if (!stats) stats = &local;
+    memset(stats, 0, sizeof(*stats));
+
+    reads_view rs = { lq_packed, n_lq, (read_len + 3) / 4, n_packed, n_n, (read_len + 2) / 3, read_len };
+    const uint32_t n = n_lq + n_n;
+
+    /* ReadsMatchers.cpp:699-713 */
+    const uint8_t max_mm = (uint8_t)(read_len / min_chars_per_mismatch);
+    uint32_t reads_exact = seed > read_len ? read_len : seed;
+    uint32_t pre_exact = pre_seed > read_len ? read_len : pre_seed;
+    uint32_t cur_exact = reads_exact;
+    char cur_mode = mode;
+    if (pre_exact > 0) { cur_exact = pre_exact; cur_mode = pre_mode; }
+    const uint8_t cur_min_mm = is_upper_mode(cur_mode) ? max_mm : 0;
+    const uint8_t target_mm = (uint8_t)(read_len / cur_exact - 1);
+
+    matcher m;
+    memset(&m, 0, sizeof(m));
+    m.pg = text; m.pg_len = text_len; m.rev_compl = rev_compl;
+    m.rs = &rs; m.n_reads = n; m.read_len = read_len; m.matching_len = read_len; /* DISABLED_PREFIX_MODE */
+    m.pos = out_pos; m.rc = out_rc; m.mm = out_mm; m.st = stats;
+    m.cur_read = (char *)malloc(read_len + 1);
+    m.seed_buf = (char *)malloc(read_len + 1);
+    if (!m.cur_read || !m.seed_buf) { free(m.cur_read); free(m.seed_buf); return -2; }
+
+    /* DefaultReadsMatcher::initMatching (ReadsMatchers.cpp:97-105) */
+    for (uint32_t i = 0; i < n; i++) { out_pos[i] = PGO_NOT_MATCHED_POSITION; out_rc[i] = 0; out_mm[i] = PGO_NOT_MATCHED_COUNT; }
+
+    int rcode = 0;
+    pat_table t;
+    const int first_exact = (read_len == cur_exact);
+    if (first_exact) {
+        /* DefaultReadsExactMatcher::initMatching: whole reads as patterns (parts = 1) */
+        rcode = table_build(&t, &rs, n, m.matching_len, 1, NULL);
+        if (rcode == 0) { stats->n_patterns = t.n; rcode = run_passes(&m, &t, 1); table_free(&t); }
+        /* DefaultReadsExactMatcher::transferMatchingResults (ReadsMatchers.cpp:127-133) */
+        for (uint32_t i = 0; i < n; i++) out_mm[i] = out_pos[i] == PGO_NOT_MATCHED_POSITION ? PGO_NOT_MATCHED_COUNT : 0;
+        stats->per_mm[0] = stats->matched;
+        stats->per_mm[PGO_NOT_MATCHED_COUNT] = n - stats->matched;
+    } else {
+        /* AbstractReadsApproxMatcher ctor + DefaultReadsApproxMatcher::initMatching */
+        m.part_len = cur_exact; m.parts = (uint32_t)target_mm + 1; m.max_mm = max_mm; m.min_mm = cur_min_mm;
+        stats->per_mm[PGO_NOT_MATCHED_COUNT] = n;
+        rcode = table_build(&t, &rs, n, m.part_len, m.parts, NULL);
+        if (rcode == 0) { stats->n_patterns = t.n; rcode = run_passes(&m, &t, 0); table_free(&t); }
+    }
+
+    if (rcode == 0 && pre_exact > 0) {
+        /* 2nd phase (ReadsMatchers.cpp:749-779): minMismatches uses the FIRST phase's targetMismatches */
+        const uint8_t min_mm2 = is_upper_mode(mode) ? max_mm : (uint8_t)(target_mm + 1);
+        m.part_len = reads_exact;
+        m.parts = read_len / reads_exact; /* targetMismatches + 1 of the new matcher */
+        m.max_mm = max_mm; m.min_mm = min_mm2;
+        /* initMatchingContinuation: getMatchedReadsBitmap(minMismatches) of the previous matcher:
+         * exact matcher ignores the argument (:677-683), approx matcher uses mm <= arg (:685-691) */
+        uint8_t *skip = (uint8_t *)malloc(n ? n : 1);
+        if (!skip) rcode = -2;
+        else {
+            for (uint32_t i = 0; i < n; i++)
+                skip[i] = first_exact ? (out_pos[i] != PGO_NOT_MATCHED_POSITION) : (out_mm[i] <= min_mm2);
+            rcode = table_build(&t, &rs, n, m.part_len, m.parts, skip);
+            free(skip);
+            if (rcode == 0) { stats->n_patterns = t.n; rcode = run_passes(&m, &t, 0); table_free(&t); }
+        }
+    }
+    free(m.cur_read); free(m.seed_buf);
+    return rcode;
+}

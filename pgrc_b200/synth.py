@@ -1,0 +1,217 @@
+"""Synthetic matcher-level inputs (there is no network; BASELINE.md §3 / SURVEY.md §8(d)).
+
+Everything here is host-side numpy: genomes, pseudogenome-like texts, error-containing
+reads, and the reference's packed-read layout.  The shapes follow the
+BASELINE configs; the matcher inputs are generated directly (text + the error-containing
+subset of reads) because the full PgRC chain cannot produce them on the bench host.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+_A, _C, _G, _T, _N = (ord(c) for c in "ACGTN")
+_CODE2ASCII = np.array([_A, _C, _G, _T], np.uint8)
+_COMP = np.arange(256, dtype=np.uint8)
+_COMP[_A], _COMP[_C], _COMP[_G], _COMP[_T] = _T, _G, _C, _A
+_ASCII2CODE4 = np.full(256, 255, np.uint8)
+_ASCII2CODE4[[_A, _C, _G, _T]] = [0, 1, 2, 3]
+_ASCII2CODE5 = np.full(256, 255, np.uint8)
+_ASCII2CODE5[[_A, _C, _G, _N, _T]] = [0, 1, 2, 3, 4]
+
+
+def random_genome(length: int, rng: np.random.Generator) -> np.ndarray:
+    """i.i.d. uniform ACGT, ASCII uint8."""
+    return _CODE2ASCII[rng.integers(0, 4, size=length, dtype=np.uint8)]
+
+
+def revcomp(a: np.ndarray) -> np.ndarray:
+    """Reverse complement along the last axis (N stays N)."""
+    return _COMP[a[..., ::-1]]
+
+
+def make_pseudogenome(genome: np.ndarray, rng: np.random.Generator, copies: float = 2.8,
+                      mean_contig: int = 4000) -> np.ndarray:
+    """Pseudogenome-like text: the genome cut into contigs, each emitted in a random
+    orientation, repeated until the text is ``copies`` x the genome (the reference's HQ
+    pseudogenome is 2.0-2.9 x the genome, both strands mixed)."""
+    G = genome.size
+    out = []
+    remaining = copies
+    while remaining > 1e-9:
+        frac = min(1.0, remaining)
+        span = max(1, int(G * frac))
+        lo = 0 if span >= G else int(rng.integers(0, G - span + 1))
+        ncut = max(0, span // max(1, mean_contig) - 1)
+        cuts = np.unique(rng.integers(lo + 1, lo + span, size=ncut)) if ncut and span > 1 else np.empty(0, np.int64)
+        bounds = np.concatenate(([lo], cuts, [lo + span])).astype(np.int64)
+        flips = rng.random(bounds.size - 1) < 0.5
+        for b, e, f in zip(bounds[:-1], bounds[1:], flips):
+            seg = genome[b:e]
+            out.append(revcomp(seg) if f else seg)
+        remaining -= frac
+    return np.ascontiguousarray(np.concatenate(out))
+
+
+def sample_reads(genome: np.ndarray, n: int, read_len: int, err: float, rng: np.random.Generator,
+                 require_error: bool = True, chunk: int = 1 << 20) -> np.ndarray:
+    """n reads (n x L ASCII): uniform start, 50 % reverse-complemented, i.i.d. substitutions
+    with probability ``err``.  With ``require_error`` every read carries >= 1 substitution —
+    the matcher only sees the error-containing (LQ) subset."""
+    G = genome.size
+    out = np.empty((n, read_len), np.uint8)
+    ar = np.arange(read_len, dtype=np.int64)
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        start = rng.integers(0, G - read_len + 1, size=m, dtype=np.int64)
+        r = genome[start[:, None] + ar[None, :]]
+        flip = rng.random(m) < 0.5
+        r[flip] = revcomp(r[flip])
+        mask = rng.random((m, read_len)) < err
+        if require_error:
+            none = ~mask.any(axis=1)
+            mask[np.nonzero(none)[0], rng.integers(0, read_len, size=int(none.sum()))] = True
+        codes = _ASCII2CODE4[r]
+        shift = rng.integers(1, 4, size=(m, read_len), dtype=np.uint8)
+        codes = np.where(mask, (codes + shift) & 3, codes)
+        out[s:s + m] = _CODE2ASCII[codes]
+    return out
+
+
+def inject_n(reads: np.ndarray, rng: np.random.Generator, max_n: int = 3) -> np.ndarray:
+    """Replaces 1..max_n random bases of every read by 'N' (reads destined for the ACGNT set)."""
+    r = reads.copy()
+    n, L = r.shape
+    for _ in range(max_n):
+        sel = rng.random(n) < (1.0 if _ == 0 else 0.5)
+        r[np.nonzero(sel)[0], rng.integers(0, L, size=int(sel.sum()))] = _N
+    return r
+
+
+def pack_reads(reads: np.ndarray, with_n: bool = False) -> np.ndarray:
+    """The reference's packed-read layout (SymbolsPackingFacility.cpp:147-185): ACGT -> 4
+    bases/byte, first base in the most significant digit, tail padded with A; ACGNT -> 3
+    bases/byte, base 5, codes A0 C1 G2 N3 T4."""
+    reads = np.ascontiguousarray(reads, np.uint8)
+    n, L = reads.shape
+    spe, sigma, lut = (3, 5, _ASCII2CODE5) if with_n else (4, 4, _ASCII2CODE4)
+    plen = (L + spe - 1) // spe
+    codes = lut[reads]
+    if codes.size and codes.max() == 255:
+        raise ValueError("symbol outside the alphabet")
+    pad = plen * spe - L
+    if pad:
+        codes = np.concatenate([codes, np.zeros((n, pad), np.uint8)], axis=1)
+    w = np.array([sigma ** (spe - 1 - j) for j in range(spe)], np.uint16)
+    return (codes.reshape(n, plen, spe).astype(np.uint16) * w).sum(axis=2).astype(np.uint8)
+
+
+@dataclass
+class MatcherInputs:
+    """What PgRCEncoder::runMappingLQReadsOnHQPg hands to mapReadsIntoPg (pgrc-encoder.cpp:342-366)."""
+    text: np.ndarray            # ASCII pseudogenome
+    lq_reads: np.ndarray        # n_lq x L ASCII (ACGT)
+    n_reads: np.ndarray         # n_n x L ASCII (ACGNT), may be empty
+    read_len: int
+    name: str = ""
+
+    @property
+    def lq_packed(self) -> np.ndarray:
+        return pack_reads(self.lq_reads, False)
+
+    @property
+    def n_packed(self) -> np.ndarray:
+        return pack_reads(self.n_reads, True) if len(self.n_reads) else np.zeros((0, (self.read_len + 2) // 3), np.uint8)
+
+
+def workload(genome_len: int, n_reads: int, read_len: int, err: float, seed: int,
+             copies: float = 2.8, n_frac: float = 0.0, name: str = "") -> MatcherInputs:
+    """Matcher-level workload of a BASELINE config shape (scaled by the caller)."""
+    rng = np.random.default_rng(seed)
+    genome = random_genome(genome_len, rng)
+    text = make_pseudogenome(genome, rng, copies=copies)
+    n_n = int(round(n_reads * n_frac))
+    lq = sample_reads(genome, n_reads - n_n, read_len, err, rng)
+    nn = inject_n(sample_reads(genome, n_n, read_len, err, rng), rng) if n_n else np.zeros((0, read_len), np.uint8)
+    return MatcherInputs(text, lq, nn, read_len, name)
+
+
+def adversarial(seed: int, read_len: int = 100, n_reads: int = 3000, text_len: int = 40000,
+                with_n: bool = True) -> MatcherInputs:
+    """Small adversarial case modelled on the survey's validation harness:
+    diverged repeats, reverse-complement copies, near-reverse-palindromes (which trigger the
+    coordinate-only skip of ReadsMatchers.cpp:313), low-complexity tracts, a tail shorter than
+    a read, reads with 0..L/3+ substitutions, and N reads including N pairs 32 apart (they
+    cancel in the 32-bit rotate-xor hash when the seed is longer than 32)."""
+    rng = np.random.default_rng(seed)
+    L = read_len
+    parts = []
+    base = random_genome(text_len // 2, rng)
+    parts.append(base)
+    # diverged repeats of random windows
+    for _ in range(12):
+        s = int(rng.integers(0, base.size - 3 * L))
+        seg = base[s:s + int(rng.integers(L, 3 * L))].copy()
+        k = int(rng.integers(0, 6))
+        idx = rng.integers(0, seg.size, size=k)
+        seg[idx] = _CODE2ASCII[rng.integers(0, 4, size=k)]
+        parts.append(seg)
+    # reverse-complement copies
+    for _ in range(8):
+        s = int(rng.integers(0, base.size - 3 * L))
+        parts.append(revcomp(base[s:s + int(rng.integers(L, 3 * L))]))
+    # near-reverse-palindromes: X + few-diffs + revcomp(X)
+    pals = []
+    for _ in range(24):
+        half = random_genome(int(rng.integers(L // 2 + 5, L + 20)), rng)
+        other = revcomp(half).copy()
+        k = int(rng.integers(0, 5))
+        idx = rng.integers(0, other.size, size=k)
+        other[idx] = _CODE2ASCII[rng.integers(0, 4, size=k)]
+        pals.append(np.concatenate([half, other]))
+    parts.extend(pals)
+    # low-complexity tracts
+    for unit in ("A", "AC", "AT", "ACG", "T"):
+        u = np.frombuffer(unit.encode(), np.uint8)
+        parts.append(np.tile(u, (2 * L + 30) // u.size + 1)[:2 * L + 30])
+    parts.append(random_genome(text_len // 4, rng))
+    parts.append(random_genome(L - 7, rng))            # tail shorter than a read
+    order = rng.permutation(len(parts) - 1)
+    text = np.ascontiguousarray(np.concatenate([parts[i] for i in order] + [parts[-1]]))
+
+    # reads: windows of the text (either strand) with 0..many substitutions
+    n_n = n_reads // 5 if with_n else 0
+    n_lq = n_reads - n_n
+
+    def draw(m):
+        start = rng.integers(0, text.size - L + 1, size=m)
+        r = text[start[:, None] + np.arange(L)[None, :]].copy()
+        # every 4th read sits on a near-palindrome, half of those exactly centred on it: the
+        # forward and the RC alignment then report the SAME coordinate (ReadsMatchers.cpp:313)
+        for i in range(0, m, 4):
+            pal = pals[int(rng.integers(0, len(pals)))]
+            c = pal.size // 2
+            s0 = c - L // 2 if (i // 4) % 2 == 0 else int(rng.integers(max(0, c - L + 8), min(c - 8, pal.size - L) + 1))
+            r[i] = pal[s0:s0 + L]
+        flip = rng.random(m) < 0.5
+        r[flip] = revcomp(r[flip])
+        nsub = rng.choice([0, 1, 2, 3, 5, 8, 12, 20, L // 3, L // 3 + 1, L // 2], size=m)
+        for i in range(m):
+            if nsub[i]:
+                idx = rng.choice(L, size=int(nsub[i]), replace=False)
+                r[i, idx] = _CODE2ASCII[(_ASCII2CODE4[r[i, idx]] + rng.integers(1, 4, size=idx.size)) & 3]
+        return r
+
+    lq = draw(n_lq)
+    nn = draw(n_n)
+    for i in range(n_n):
+        mode = i % 3
+        if mode == 0:       # N pair 32 apart inside seed 0: cancels in the hash for seeds > 32
+            k = int(rng.integers(0, 6))
+            nn[i, [k, k + 32]] = _N
+        elif mode == 1:     # single N
+            nn[i, int(rng.integers(0, L))] = _N
+        else:               # 2-3 random N
+            nn[i, rng.choice(L, size=int(rng.integers(2, 4)), replace=False)] = _N
+    return MatcherInputs(text, lq, nn, L, f"adversarial(seed={seed},L={L})")
