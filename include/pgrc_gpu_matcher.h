@@ -1,0 +1,165 @@
+/* pgrc_gpu_matcher.h — C ABI of the B200-native read-vs-pseudogenome matcher for PgRC.
+ *
+ * Drop-in boundary for PgRC's stage 4 (reads -> HQ pseudogenome mapping).  Every entry point
+ * names the reference interface it replaces (file:line relative to kowallus/PgRC).  The
+ * reference has no FFI: the boundary is the virtual-class interface of
+ * PgTools::DefaultReadsMatcher (matching/ReadsMatchers.h:24-83).  INTEGRATION.md shows the
+ * C++ subclass a maintainer adds to ReadsMatchers.cpp to call these functions.
+ *
+ * Conventions
+ *  - plain C types only; all buffers are owned by the caller.  Input and output pointers may
+ *    be host memory (pageable or pinned) or device memory of the context's GPU; the library
+ *    detects which and never writes to an input.
+ *  - every function returns PGM_OK (0) or a negative pgm_status; pgm_last_error() gives the
+ *    message.  There is NO CPU fallback: without a usable sm_100 device pgm_create fails.
+ *  - a context is bound to one GPU and one stream and is not thread-safe (the reference
+ *    calls the matcher once, from the main thread: pgrc-encoder.cpp:359).
+ *  - multi-GPU: one context per GPU (one process per GPU).  Each context scans its own text
+ *    range (pgm_set_text_shard); between pgm_scan_pass and pgm_resolve_pass the caller merges
+ *    the per-read accumulators across GPUs (pgm_get_accumulators: MIN / SUM reductions over
+ *    NCCL).  With a single GPU, pgm_map_reads does everything.
+ */
+#ifndef PGRC_GPU_MATCHER_H
+#define PGRC_GPU_MATCHER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGM_ABI_VERSION 1
+
+typedef enum pgm_status {
+    PGM_OK = 0,
+    PGM_ERR_INVALID_ARG = -1,  /* bad pointer / size / parameter combination            */
+    PGM_ERR_NO_DEVICE = -2,    /* no CUDA device, or not compute capability 10.x        */
+    PGM_ERR_CUDA = -3,         /* a CUDA runtime call failed (message has the detail)   */
+    PGM_ERR_OOM = -4,          /* device memory exhausted                               */
+    PGM_ERR_BAD_SYMBOL = -5,   /* text contains a symbol outside ACGT                   */
+    PGM_ERR_UNSUPPORTED = -6,  /* feature of the reference not covered (see message)    */
+    PGM_ERR_STATE = -7         /* call order violated (e.g. scan before match_begin)    */
+} pgm_status;
+
+#define PGM_NOT_MATCHED_POSITION UINT64_MAX /* DefaultReadsMatcher::NOT_MATCHED_POSITION, ReadsMatchers.cpp:69 */
+#define PGM_NOT_MATCHED_COUNT 255           /* PgTools::NOT_MATCHED_COUNT, ReadsMatchers.h:17                  */
+#define PGM_DISABLED_PREFIX_MODE 0xFFFFu    /* DefaultReadsMatcher::DISABLED_PREFIX_MODE, ReadsMatchers.cpp:68 */
+
+typedef struct pgm_ctx pgm_ctx;
+
+/* Result counters.  matched / per_mm reproduce the reference's matchedReadsCount
+ * (ReadsMatchers.h:35) and matchedCountPerMismatches (ReadsMatchers.h:116) exactly.
+ * betterMatchCount / falseMatchCount (ReadsMatchers.h:42-43) are printed by the reference
+ * but never reach the archive and depend on its sequential event order; they are NOT
+ * reproduced.  The remaining fields describe the work done (used for the roofline). */
+typedef struct pgm_stats {
+    uint64_t matched;            /* reads with a match                                   */
+    uint64_t per_mm[256];        /* per_mm[k] = reads matched with k mismatches; [255] = unmatched */
+    uint64_t patterns_inserted;  /* seeds inserted into the last pattern table           */
+    uint64_t table_slots;        /* slots of the last pattern table                      */
+    uint64_t candidates;         /* seed hits forwarded to verification (all passes)     */
+    uint64_t verified;           /* candidates whose read was actually compared          */
+    uint64_t accepted;           /* verified candidates within the mismatch limit        */
+    uint64_t queue_overflows;    /* candidates verified inline because a CTA queue was full */
+} pgm_stats;
+
+/* Device pointers of the per-read accumulators of the current pass, for the cross-GPU
+ * merge between pgm_scan_pass and pgm_resolve_pass (n_reads elements each):
+ *   best_key  int64  MIN   first_other_order int64 MIN
+ *   same_pos_mask int32 SUM (bits are disjoint across text shards)   same_pos_mm uint8 MIN
+ * `touched` points to one int32 that is non-zero iff this GPU wrote first_other_order /
+ * same_pos_* in this pass (MAX-reduce it first; if 0 everywhere only best_key needs merging). */
+typedef struct pgm_accumulators {
+    void *best_key;
+    void *first_other_order;
+    void *same_pos_mask;
+    void *same_pos_mm;
+    void *touched;
+    uint64_t n_reads;
+} pgm_accumulators;
+
+/* ---- life cycle ------------------------------------------------------------------------
+ * replaces: new/delete of the matcher object in mapReadsIntoPg (ReadsMatchers.cpp:714-794)
+ * and the hash matcher it owns (ReadsMatchers.cpp:83-95). */
+int pgm_abi_version(void);
+int pgm_create(int device, pgm_ctx **out);
+void pgm_destroy(pgm_ctx *ctx);
+const char *pgm_last_error(const pgm_ctx *ctx); /* ctx may be NULL: last pgm_create error */
+/* Use an existing CUDA stream (cudaStream_t) for all work of this context; NULL = own stream. */
+int pgm_set_stream(pgm_ctx *ctx, void *cuda_stream);
+/* Blocks until all work queued by this context has finished. */
+int pgm_synchronize(pgm_ctx *ctx);
+
+/* ---- inputs ----------------------------------------------------------------------------
+ * pgm_set_text replaces the (char* pgPtr, uint_pg_len_max pgLength) constructor arguments
+ * (ReadsMatchers.h:59-60; text = SeparatedPseudoGenome::getPgSequence(), 1 byte per base,
+ * alphabet ACGT).  The text is packed on the device into two bit planes per strand; the
+ * caller's buffer is only read (the reference reverse-complements it in place and restores
+ * it, ReadsMatchers.cpp:167-171 — not needed here). */
+int pgm_set_text(pgm_ctx *ctx, const char *text, uint64_t pg_len);
+/* Text shard for one GPU of several: `slice` holds text[slice_begin, slice_begin+slice_len);
+ * this context owns the seed-window start positions [own_begin, own_end).  The slice must
+ * extend PGM_SHARD_HALO bases beyond the owned range on both sides (clipped to the text). */
+#define PGM_SHARD_HALO 512
+int pgm_set_text_shard(pgm_ctx *ctx, const char *slice, uint64_t slice_begin, uint64_t slice_len,
+                       uint64_t pg_len, uint64_t own_begin, uint64_t own_end);
+/* Even split of [0, pg_len) over `world` GPUs, with halos; outputs feed pgm_set_text_shard. */
+int pgm_shard_plan(uint64_t pg_len, int rank, int world, uint64_t *slice_begin, uint64_t *slice_len,
+                   uint64_t *own_begin, uint64_t *own_end);
+
+/* pgm_set_reads replaces the ConstantLengthReadsSetInterface* constructor argument
+ * (ReadsMatchers.h:59-60).  lq_packed: n_lq reads of the ACGT set, ceil(read_len/4) bytes
+ * each, exactly PackedConstantLengthReadsSet::getPackedRead's layout
+ * (PackedConstantLengthReadsSet.h:40, SymbolsPackingFacility.cpp:147-185); n_packed: n_n
+ * reads of the ACGNT set, ceil(read_len/3) bytes each.  Global read index = LQ reads first,
+ * then N reads (SumOfConstantLengthReadsSets, ReadsSetInterface.h:45-89).  read_len <= 255. */
+int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq,
+                  const uint8_t *n_packed, uint32_t n_n, uint32_t read_len);
+
+/* ---- one matcher object's work, step by step ----------------------------------------------
+ * pgm_match_begin replaces initMatching() / initMatchingContinuation()
+ * (ReadsMatchers.cpp:97-105,190-196,276-295): builds the seed table in HBM for
+ * `parts` seeds of `seed_len` per read.  seed_len == read_len && parts == 1 && max_mm == 0 is
+ * the exact path (DefaultReadsExactMatcher).  continuation = 0 resets the per-read state;
+ * continuation = 1 keeps it and leaves out reads already matched with <= min_mm mismatches
+ * (getMatchedReadsBitmap(minMismatches), ReadsMatchers.cpp:287-295,677-691). */
+int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm,
+                    uint32_t min_mm, int continuation);
+/* pgm_scan_pass replaces executeMatching(revCompMode) (ReadsMatchers.cpp:198-230,297-341)
+ * up to, but excluding, the per-read decision: scan of the (reverse-complemented, if
+ * rev_mode) text, table probes, XOR/popcount verification, per-read accumulators. */
+int pgm_scan_pass(pgm_ctx *ctx, int rev_mode);
+int pgm_get_accumulators(pgm_ctx *ctx, pgm_accumulators *out);
+/* pgm_resolve_pass applies the reference's accept/tie-break rule of that pass to the
+ * (merged) accumulators: strict improvement, scan order, LIFO among equal-hash patterns,
+ * the coordinate-only "already stored" skip of ReadsMatchers.cpp:313, minMismatches stop. */
+int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode);
+/* pgm_get_results replaces reading readMatchPos / readMatchRC / readMismatchesCount
+ * (ReadsMatchers.h:32-33,115) and getMatchedReadsBitmap.  n_reads entries each;
+ * stats may be NULL.  Synchronizes the context's stream. */
+int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats);
+
+/* ---- the whole stage on one GPU ---------------------------------------------------------
+ * pgm_map_reads replaces the matching part of PgTools::mapReadsIntoPg
+ * (ReadsMatchers.cpp:693-783) for matching modes 'd'/'D': parameter derivation
+ * (:699-713), first matcher (:714-747), optional second phase (:749-779), same argument
+ * meaning as the reference (pre_seed = preReadsExactMatchingChars, seed =
+ * readsExactMatchingChars, min_chars_per_mismatch = minCharsPerMismatch, upper-case mode
+ * letter = shortcut mode).  match_prefix_length must be PGM_DISABLED_PREFIX_MODE (what
+ * pgrc-encoder.cpp:360 passes) or >= read_len.  Requires pgm_set_text and pgm_set_reads. */
+int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed, uint32_t seed,
+                  uint32_t min_chars_per_mismatch, char pre_mode, char mode, int rev_compl,
+                  uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats);
+
+/* ---- introspection (bench / tests) -------------------------------------------------------*/
+/* Number of kernels this context has launched so far. */
+uint64_t pgm_kernel_launches(const pgm_ctx *ctx);
+/* Tuning knobs; call before pgm_match_begin.  filter_log2_bits = 0 disables the L2-resident
+ * pre-filter; slots_per_pattern sets the table size (>= 2). */
+int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGRC_GPU_MATCHER_H */

@@ -1,0 +1,81 @@
+"""ctypes binding of the C ABI declared in include/pgrc_gpu_matcher.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There
+is no fallback: if it is missing, importing the product fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgrc_gpu.so")
+
+PGM_OK = 0
+PGM_DISABLED_PREFIX_MODE = 0xFFFF
+PGM_SHARD_HALO = 512
+
+STATUS_NAMES = {0: "PGM_OK", -1: "PGM_ERR_INVALID_ARG", -2: "PGM_ERR_NO_DEVICE", -3: "PGM_ERR_CUDA",
+                -4: "PGM_ERR_OOM", -5: "PGM_ERR_BAD_SYMBOL", -6: "PGM_ERR_UNSUPPORTED", -7: "PGM_ERR_STATE"}
+
+# every symbol include/pgrc_gpu_matcher.h declares
+EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pgm_set_stream", "pgm_synchronize",
+           "pgm_set_text", "pgm_set_text_shard", "pgm_shard_plan", "pgm_set_reads", "pgm_match_begin",
+           "pgm_scan_pass", "pgm_get_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_map_reads",
+           "pgm_kernel_launches", "pgm_set_tuning"]
+
+
+class PgmStats(ctypes.Structure):
+    _fields_ = [("matched", ctypes.c_uint64), ("per_mm", ctypes.c_uint64 * 256),
+                ("patterns_inserted", ctypes.c_uint64), ("table_slots", ctypes.c_uint64),
+                ("candidates", ctypes.c_uint64), ("verified", ctypes.c_uint64),
+                ("accepted", ctypes.c_uint64), ("queue_overflows", ctypes.c_uint64)]
+
+
+class PgmAccumulators(ctypes.Structure):
+    _fields_ = [("best_key", ctypes.c_void_p), ("first_other_order", ctypes.c_void_p),
+                ("same_pos_mask", ctypes.c_void_p), ("same_pos_mm", ctypes.c_void_p),
+                ("touched", ctypes.c_void_p), ("n_reads", ctypes.c_uint64)]
+
+
+class PgmError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). pgrc_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u64, u32, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+    lib.pgm_abi_version.restype = ci
+    lib.pgm_create.restype = ci; lib.pgm_create.argtypes = [ci, ctypes.POINTER(vp)]
+    lib.pgm_destroy.restype = None; lib.pgm_destroy.argtypes = [vp]
+    lib.pgm_last_error.restype = ctypes.c_char_p; lib.pgm_last_error.argtypes = [vp]
+    lib.pgm_set_stream.restype = ci; lib.pgm_set_stream.argtypes = [vp, vp]
+    lib.pgm_synchronize.restype = ci; lib.pgm_synchronize.argtypes = [vp]
+    lib.pgm_set_text.restype = ci; lib.pgm_set_text.argtypes = [vp, vp, u64]
+    lib.pgm_set_text_shard.restype = ci; lib.pgm_set_text_shard.argtypes = [vp, vp, u64, u64, u64, u64, u64]
+    lib.pgm_shard_plan.restype = ci
+    lib.pgm_shard_plan.argtypes = [u64, ci, ci] + [ctypes.POINTER(u64)] * 4
+    lib.pgm_set_reads.restype = ci; lib.pgm_set_reads.argtypes = [vp, vp, u32, vp, u32, u32]
+    lib.pgm_match_begin.restype = ci; lib.pgm_match_begin.argtypes = [vp, u32, u32, u32, u32, ci]
+    lib.pgm_scan_pass.restype = ci; lib.pgm_scan_pass.argtypes = [vp, ci]
+    lib.pgm_get_accumulators.restype = ci; lib.pgm_get_accumulators.argtypes = [vp, ctypes.POINTER(PgmAccumulators)]
+    lib.pgm_resolve_pass.restype = ci; lib.pgm_resolve_pass.argtypes = [vp, ci]
+    lib.pgm_get_results.restype = ci; lib.pgm_get_results.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PgmStats)]
+    lib.pgm_map_reads.restype = ci
+    lib.pgm_map_reads.argtypes = [vp, u32, u32, u32, u32, ctypes.c_char, ctypes.c_char, ci, vp, vp, vp,
+                                  ctypes.POINTER(PgmStats)]
+    lib.pgm_kernel_launches.restype = u64; lib.pgm_kernel_launches.argtypes = [vp]
+    lib.pgm_set_tuning.restype = ci; lib.pgm_set_tuning.argtypes = [vp, ci, ci, ci]
+    _lib = lib
+    return lib

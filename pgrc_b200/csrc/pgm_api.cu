@@ -1,0 +1,556 @@
+// pgm_api.cu — C ABI (include/pgrc_gpu_matcher.h) over the kernels in pgm_kernels.cuh.
+// Host-side plumbing only: device buffers, stream-ordered launches, parameter derivation
+// restated from PgTools::mapReadsIntoPg (matching/ReadsMatchers.cpp:693-783).
+#include "../../include/pgrc_gpu_matcher.h"
+#include "pgm_kernels.cuh"
+
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+constexpr uint64_t TEXT_CHUNK_BASES = 64ull << 20; // ASCII staging chunk (multiple of 32)
+
+} // namespace
+
+struct pgm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+
+    // tuning
+    int filter_log2_bits = -1; // -1 = auto
+    int slots_per_pattern = 3;
+    int ctas_per_sm = 4;
+
+    // text
+    DevBuf f_lo, f_hi, r_lo, r_hi, ascii_stage;
+    uint64_t pg_len = 0, slice_begin = 0, slice_len = 0, own_begin = 0, own_end = 0;
+    bool has_text = false;
+
+    // reads
+    DevBuf packed_stage, lq_planes, n_planes;
+    uint32_t n_lq = 0, n_n = 0, read_len = 0, W = 0, lq_stride = 0, n_stride = 0;
+    bool has_reads = false;
+
+    // per read
+    DevBuf state, best_key, first_order, same_mask, same_mm, touched;
+
+    // table
+    DevBuf slots, next, filter;
+    uint64_t n_slots = 0;
+    int filter_word_bits = 0;
+
+    // phase
+    uint32_t seed_len = 0, parts = 0, max_mm = 0, min_mm = 0;
+    bool phase_active = false;
+
+    // misc device scalars: counters[0..3] scan, [4] inserted, [5] tile counter (low 32 bits)
+    DevBuf counters, hist, err_flag;
+    DevBuf out_pos, out_rc, out_mm;
+
+    uint32_t n_reads() const { return n_lq + n_n; }
+};
+
+namespace {
+
+int fail(pgm_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+int cuda_fail(pgm_ctx *c, cudaError_t e, const char *what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    return fail(c, e == cudaErrorMemoryAllocation ? PGM_ERR_OOM : PGM_ERR_CUDA, buf);
+}
+
+#define CU(call)                                                         \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);         \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                               \
+    do {                                                                 \
+        ctx->launches++;                                                 \
+        cudaError_t _e = cudaGetLastError();                             \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, name);          \
+    } while (0)
+
+int ensure(pgm_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return PGM_OK;
+    if (b.p) { CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = std::max<size_t>(bytes, 256);
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return PGM_OK;
+}
+
+void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+inline unsigned int grid_for(uint64_t n, unsigned int block) { return (unsigned int)((n + block - 1) / block); }
+
+uint64_t plane_words(uint64_t slice_len) { return (slice_len + 31) / 32; }
+size_t plane_bytes(uint64_t slice_len) { return (PGM_PAD_WORDS + plane_words(slice_len) + PGM_TAIL_WORDS) * sizeof(uint32_t); }
+
+pgm::PerRead per_read(pgm_ctx *c) {
+    pgm::PerRead pr;
+    pr.state = c->state.as<unsigned long long>();
+    pr.best_key = c->best_key.as<long long>();
+    pr.first_other_order = c->first_order.as<long long>();
+    pr.same_pos_mask = c->same_mask.as<int>();
+    pr.same_pos_mm = c->same_mm.as<uint8_t>();
+    pr.touched = c->touched.as<int>();
+    return pr;
+}
+
+pgm::ReadsView reads_view(pgm_ctx *c) {
+    pgm::ReadsView rv;
+    rv.lq_planes = c->lq_planes.as<uint32_t>();
+    rv.n_planes = c->n_planes.as<uint32_t>();
+    rv.n_lq = c->n_lq; rv.n_n = c->n_n;
+    rv.lq_stride = c->lq_stride; rv.n_stride = c->n_stride;
+    rv.read_len = c->read_len; rv.W = c->W;
+    return rv;
+}
+
+pgm::TableView table_view(pgm_ctx *c) {
+    pgm::TableView tv;
+    tv.slots = c->slots.as<unsigned long long>();
+    tv.next = c->next.as<uint32_t>();
+    tv.filter = c->filter_word_bits ? c->filter.as<uint32_t>() : nullptr;
+    tv.bucket_mask = (uint32_t)(c->n_slots / 4 - 1);
+    tv.filter_word_bits = c->filter_word_bits;
+    return tv;
+}
+
+int ceil_log2(uint64_t v) { int b = 0; while ((1ull << b) < v) b++; return b; }
+
+template <int NCH>
+void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s) {
+    pgm::scan_kernel<NCH><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+}
+
+} // namespace
+
+extern "C" {
+
+int pgm_abi_version(void) { return PGM_ABI_VERSION; }
+
+const char *pgm_last_error(const pgm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int pgm_create(int device, pgm_ctx **out) {
+    pgm_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, PGM_ERR_INVALID_ARG, "pgm_create: out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PGM_ERR_NO_DEVICE,
+                    std::string("pgm_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, PGM_ERR_INVALID_ARG, "pgm_create: device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, PGM_ERR_NO_DEVICE,
+                    std::string("pgm_create: device '") + prop.name + "' is not compute capability 10.x; kernels are built for sm_100a only");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    ctx = new pgm_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
+    ctx->own_stream = true;
+    int rc;
+    if ((rc = ensure(ctx, ctx->counters, 16 * sizeof(unsigned long long))) != PGM_OK ||
+        (rc = ensure(ctx, ctx->hist, 257 * sizeof(unsigned long long))) != PGM_OK ||
+        (rc = ensure(ctx, ctx->err_flag, sizeof(int))) != PGM_OK ||
+        (rc = ensure(ctx, ctx->touched, sizeof(int))) != PGM_OK) {
+        g_create_error = ctx->err;
+        pgm_destroy(ctx);
+        return rc;
+    }
+    cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream);
+    cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), ctx->stream);
+    cudaMemsetAsync(ctx->touched.p, 0, sizeof(int), ctx->stream);
+    *out = ctx;
+    return PGM_OK;
+}
+
+void pgm_destroy(pgm_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->f_lo, &ctx->f_hi, &ctx->r_lo, &ctx->r_hi, &ctx->ascii_stage, &ctx->packed_stage,
+                      &ctx->lq_planes, &ctx->n_planes, &ctx->state, &ctx->best_key, &ctx->first_order,
+                      &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->slots, &ctx->next, &ctx->filter,
+                      &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
+    for (DevBuf *b : bufs) release(*b);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int pgm_set_stream(pgm_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    if (cuda_stream) ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    return PGM_OK;
+}
+
+int pgm_synchronize(pgm_ctx *ctx) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PGM_OK;
+}
+
+int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (filter_log2_bits > 32 || (filter_log2_bits > 0 && filter_log2_bits < 10))
+        return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_tuning: filter_log2_bits must be 0 (off), <0 (auto) or 10..32");
+    if (slots_per_pattern < 2 || slots_per_pattern > 64) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_tuning: slots_per_pattern must be 2..64");
+    if (ctas_per_sm < 1 || ctas_per_sm > 8) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_tuning: ctas_per_sm must be 1..8");
+    ctx->filter_log2_bits = filter_log2_bits;
+    ctx->slots_per_pattern = slots_per_pattern;
+    ctx->ctas_per_sm = ctas_per_sm;
+    return PGM_OK;
+}
+
+uint64_t pgm_kernel_launches(const pgm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pgm_shard_plan(uint64_t pg_len, int rank, int world, uint64_t *slice_begin, uint64_t *slice_len,
+                   uint64_t *own_begin, uint64_t *own_end) {
+    if (world < 1 || rank < 0 || rank >= world || !slice_begin || !slice_len || !own_begin || !own_end) return PGM_ERR_INVALID_ARG;
+    auto cut = [&](int k) -> uint64_t {
+        if (k >= world) return pg_len;
+        unsigned __int128 v = (unsigned __int128)pg_len * (unsigned)k / (unsigned)world;
+        return ((uint64_t)v / 128) * 128; // keep tile copies 16-byte aligned relative to the slice
+    };
+    const uint64_t ob = cut(rank), oe = cut(rank + 1);
+    uint64_t sb = ob > PGM_SHARD_HALO ? ob - PGM_SHARD_HALO : 0;
+    sb = (sb / 128) * 128;
+    const uint64_t se = std::min(pg_len, oe + PGM_SHARD_HALO);
+    *own_begin = ob; *own_end = oe; *slice_begin = sb; *slice_len = se - sb;
+    return PGM_OK;
+}
+
+int pgm_set_text_shard(pgm_ctx *ctx, const char *slice, uint64_t slice_begin, uint64_t slice_len,
+                       uint64_t pg_len, uint64_t own_begin, uint64_t own_end) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!slice && slice_len) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_text: text is null");
+    if (pg_len >= PGM_POS_MASK) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_set_text: pseudogenome longer than 2^40-2 bases");
+    if (slice_begin + slice_len > pg_len || own_begin > own_end || own_end > pg_len ||
+        own_begin < slice_begin || own_end > slice_begin + slice_len)
+        return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_text_shard: inconsistent slice / owned range");
+    if (slice_begin % 32 != 0) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_text_shard: slice_begin must be a multiple of 32");
+    if ((own_begin != 0 && own_begin - slice_begin < PGM_SHARD_HALO && slice_begin != 0) ||
+        (own_end != pg_len && slice_begin + slice_len - own_end < PGM_SHARD_HALO && slice_begin + slice_len != pg_len))
+        return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_text_shard: slice must extend PGM_SHARD_HALO bases beyond the owned range");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const size_t pb = plane_bytes(slice_len);
+    if ((rc = ensure(ctx, ctx->f_lo, pb)) || (rc = ensure(ctx, ctx->f_hi, pb)) ||
+        (rc = ensure(ctx, ctx->r_lo, pb)) || (rc = ensure(ctx, ctx->r_hi, pb))) return rc;
+    CU(cudaMemsetAsync(ctx->f_lo.p, 0, pb, ctx->stream));
+    CU(cudaMemsetAsync(ctx->f_hi.p, 0, pb, ctx->stream));
+    CU(cudaMemsetAsync(ctx->r_lo.p, 0, pb, ctx->stream));
+    CU(cudaMemsetAsync(ctx->r_hi.p, 0, pb, ctx->stream));
+    uint32_t *flo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS, *fhi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
+    uint32_t *rlo = ctx->r_lo.as<uint32_t>() + PGM_PAD_WORDS, *rhi = ctx->r_hi.as<uint32_t>() + PGM_PAD_WORDS;
+    const bool on_device = slice_len && is_device_ptr(slice);
+    if (!on_device && slice_len)
+        if ((rc = ensure(ctx, ctx->ascii_stage, (size_t)std::min<uint64_t>(slice_len, TEXT_CHUNK_BASES)))) return rc;
+    for (uint64_t off = 0; off < slice_len; off += TEXT_CHUNK_BASES) {
+        const uint64_t n = std::min<uint64_t>(TEXT_CHUNK_BASES, slice_len - off);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(slice) + off;
+        if (!on_device) {
+            CU(cudaMemcpyAsync(ctx->ascii_stage.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
+            src = ctx->ascii_stage.as<uint8_t>();
+        }
+        pgm::pack_text_kernel<<<grid_for((n + 31) / 32, 256), 256, 0, ctx->stream>>>(src, n, flo, fhi, off / 32, ctx->err_flag.as<int>());
+        LAUNCH_CHECK("pack_text_kernel");
+    }
+    if (slice_len) {
+        pgm::rc_text_kernel<<<grid_for(plane_words(slice_len), 256), 256, 0, ctx->stream>>>(flo, fhi, slice_len, rlo, rhi);
+        LAUNCH_CHECK("rc_text_kernel");
+    }
+    ctx->pg_len = pg_len; ctx->slice_begin = slice_begin; ctx->slice_len = slice_len;
+    ctx->own_begin = own_begin; ctx->own_end = own_end;
+    ctx->has_text = true;
+    return PGM_OK;
+}
+
+int pgm_set_text(pgm_ctx *ctx, const char *text, uint64_t pg_len) {
+    return pgm_set_text_shard(ctx, text, 0, pg_len, pg_len, 0, pg_len);
+}
+
+int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq, const uint8_t *n_packed, uint32_t n_n,
+                  uint32_t read_len) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (read_len == 0 || read_len > 255) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_reads: read_len must be 1..255 (PgRC limit)");
+    if ((n_lq && !lq_packed) || (n_n && !n_packed)) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_reads: null reads pointer");
+    if ((uint64_t)n_lq + n_n >= 0xFFFFFFFFull) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_reads: too many reads");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t W = (read_len + 31) / 32;
+    const uint32_t lq_stride = (2 * W + 3) & ~3u, n_stride = (3 * W + 3) & ~3u;
+    const uint32_t lq_plen = (read_len + 3) / 4, n_plen = (read_len + 2) / 3;
+    int rc;
+    if ((rc = ensure(ctx, ctx->lq_planes, (size_t)std::max<uint32_t>(n_lq, 1) * lq_stride * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->n_planes, (size_t)std::max<uint32_t>(n_n, 1) * n_stride * 4))) return rc;
+    const uint32_t n = n_lq + n_n;
+    if ((rc = ensure(ctx, ctx->state, (size_t)std::max<uint32_t>(n, 1) * 8)) || (rc = ensure(ctx, ctx->best_key, (size_t)std::max<uint32_t>(n, 1) * 8)) ||
+        (rc = ensure(ctx, ctx->first_order, (size_t)std::max<uint32_t>(n, 1) * 8)) || (rc = ensure(ctx, ctx->same_mask, (size_t)std::max<uint32_t>(n, 1) * 4)) ||
+        (rc = ensure(ctx, ctx->same_mm, std::max<uint32_t>(n, 1))) || (rc = ensure(ctx, ctx->out_pos, (size_t)std::max<uint32_t>(n, 1) * 8)) ||
+        (rc = ensure(ctx, ctx->out_rc, std::max<uint32_t>(n, 1))) || (rc = ensure(ctx, ctx->out_mm, std::max<uint32_t>(n, 1)))) return rc;
+    struct Part { const uint8_t *src; uint32_t cnt, plen, stride; int with_n; uint32_t *dst; };
+    Part partsv[2] = {{lq_packed, n_lq, lq_plen, lq_stride, 0, ctx->lq_planes.as<uint32_t>()},
+                      {n_packed, n_n, n_plen, n_stride, 1, ctx->n_planes.as<uint32_t>()}};
+    for (const Part &pt : partsv) {
+        if (!pt.cnt) continue;
+        const size_t bytes = (size_t)pt.cnt * pt.plen;
+        const uint8_t *src = pt.src;
+        if (!is_device_ptr(src)) {
+            // staged after any kernel that still reads the staging buffer (same stream)
+            if ((rc = ensure(ctx, ctx->packed_stage, bytes))) return rc;
+            CU(cudaMemcpyAsync(ctx->packed_stage.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            src = ctx->packed_stage.as<uint8_t>();
+        }
+        pgm::unpack_reads_kernel<<<grid_for(pt.cnt, 128), 128, 0, ctx->stream>>>(src, pt.cnt, read_len, pt.plen, pt.with_n, pt.dst, pt.stride, W);
+        LAUNCH_CHECK("unpack_reads_kernel");
+        if (src == ctx->packed_stage.as<uint8_t>() && pt.with_n == 0 && n_n) {
+            // the N set reuses the staging buffer: a second ensure() may reallocate it while the
+            // LQ unpack is still running, so wait for it
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    ctx->n_lq = n_lq; ctx->n_n = n_n; ctx->read_len = read_len; ctx->W = W;
+    ctx->lq_stride = lq_stride; ctx->n_stride = n_stride;
+    ctx->has_reads = true;
+    ctx->phase_active = false;
+    return PGM_OK;
+}
+
+int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm, int continuation) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_match_begin: pgm_set_reads has not been called");
+    if (seed_len == 0 || parts == 0 || (uint64_t)seed_len * parts > ctx->read_len)
+        return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_match_begin: need seed_len >= 1 and seed_len * parts <= read_len");
+    if (max_mm > 127 || min_mm > 127) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_match_begin: mismatch limits must be <= 127");
+    const uint64_t n_patterns = (uint64_t)ctx->n_reads() * parts;
+    if (n_patterns >= 0xFFFFFFFFull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin: pattern index exceeds 32 bits (reference limit, HashMatcher.cpp:39)");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->n_reads();
+    // table geometry
+    uint64_t want = std::max<uint64_t>(4096, n_patterns * (uint64_t)ctx->slots_per_pattern);
+    uint64_t n_slots = 1ull << ceil_log2(want);
+    if (n_slots / 4 > 0x80000000ull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin: table too large");
+    int rc;
+    if ((rc = ensure(ctx, ctx->slots, n_slots * 8)) || (rc = ensure(ctx, ctx->next, std::max<uint64_t>(n_patterns, 1) * 4))) return rc;
+    ctx->n_slots = n_slots;
+    CU(cudaMemsetAsync(ctx->slots.p, 0xFF, n_slots * 8, ctx->stream));
+    int fbits = ctx->filter_log2_bits;
+    if (fbits < 0) fbits = std::min(28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 16)));
+    if (fbits > 0) {
+        ctx->filter_word_bits = fbits - 5;
+        const size_t fbytes = (size_t)1 << (fbits - 3);
+        if ((rc = ensure(ctx, ctx->filter, fbytes))) return rc;
+        CU(cudaMemsetAsync(ctx->filter.p, 0, fbytes, ctx->stream));
+    } else {
+        ctx->filter_word_bits = 0;
+    }
+    if (!continuation) CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    else CU(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 4, 0, sizeof(unsigned long long), ctx->stream));
+    if (n) {
+        pgm::init_state_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(per_read(ctx), n, continuation ? 0 : 1);
+        LAUNCH_CHECK("init_state_kernel");
+    }
+    ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
+    if (n_patterns) {
+        const uint32_t tail = seed_len % 32 ? (1u << (seed_len % 32)) - 1u : 0xFFFFFFFFu;
+        pgm::build_table_kernel<<<grid_for(n_patterns, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), ctx->state.as<unsigned long long>(), table_view(ctx), seed_len, parts, min_mm,
+            continuation ? 1 : 0, tail, ctx->counters.as<unsigned long long>() + 4);
+        LAUNCH_CHECK("build_table_kernel");
+    }
+    ctx->phase_active = true;
+    return PGM_OK;
+}
+
+int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_scan_pass: pgm_match_begin has not been called");
+    if (!ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_scan_pass: pgm_set_text has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->seed_len, pg = ctx->pg_len;
+    if (pg < n || ctx->n_reads() == 0) return PGM_OK;
+    // owned window starts of this pass (global coordinates of the pass's text)
+    uint64_t fb = ctx->own_begin, fe = std::min<uint64_t>(ctx->own_end, pg - n + 1);
+    if (fb >= fe) return PGM_OK;
+    pgm::ScanParams sp;
+    memset(&sp, 0, sizeof sp);
+    if (!rev_mode) {
+        sp.tlo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS; sp.thi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
+        sp.slice_origin = ctx->slice_begin;
+        sp.own_begin = fb; sp.own_end = fe;
+    } else {
+        // the window starting at forward p is the window starting at q = pg - n - p of the RC text
+        sp.tlo = ctx->r_lo.as<uint32_t>() + PGM_PAD_WORDS; sp.thi = ctx->r_hi.as<uint32_t>() + PGM_PAD_WORDS;
+        sp.slice_origin = pg - (ctx->slice_begin + ctx->slice_len);
+        sp.own_begin = pg - n - (fe - 1); sp.own_end = pg - n - fb + 1;
+    }
+    sp.pg_len = pg;
+    const uint64_t lb = sp.own_begin - sp.slice_origin, le = sp.own_end - sp.slice_origin;
+    sp.first_word = (uint32_t)((lb / 32) & ~3ull);
+    sp.n_tiles = (uint32_t)((le - (uint64_t)sp.first_word * 32 + PGM_TILE_POS - 1) / PGM_TILE_POS);
+    sp.seed_len = ctx->seed_len; sp.parts = ctx->parts; sp.max_mm = ctx->max_mm; sp.min_mm = ctx->min_mm;
+    sp.tail_mask = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
+    sp.rev_mode = rev_mode ? 1 : 0;
+    sp.tab = table_view(ctx);
+    sp.reads = reads_view(ctx);
+    sp.pr = per_read(ctx);
+    sp.tile_counter = reinterpret_cast<unsigned int *>(ctx->counters.as<unsigned long long>() + 5);
+    sp.counters = ctx->counters.as<unsigned long long>();
+    CU(cudaMemsetAsync(sp.tile_counter, 0, sizeof(unsigned int), ctx->stream));
+    const unsigned int grid = (unsigned int)std::min<uint64_t>(sp.n_tiles, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
+    const int nch = (int)((ctx->seed_len + 31) / 32);
+    switch (nch) {
+        case 1: launch_scan<1>(sp, grid, ctx->stream); break;
+        case 2: launch_scan<2>(sp, grid, ctx->stream); break;
+        case 3: launch_scan<3>(sp, grid, ctx->stream); break;
+        case 4: launch_scan<4>(sp, grid, ctx->stream); break;
+        case 5: launch_scan<5>(sp, grid, ctx->stream); break;
+        case 6: launch_scan<6>(sp, grid, ctx->stream); break;
+        case 7: launch_scan<7>(sp, grid, ctx->stream); break;
+        default: launch_scan<8>(sp, grid, ctx->stream); break;
+    }
+    LAUNCH_CHECK("scan_kernel");
+    return PGM_OK;
+}
+
+int pgm_get_accumulators(pgm_ctx *ctx, pgm_accumulators *out) {
+    if (!ctx || !out) return PGM_ERR_INVALID_ARG;
+    if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_get_accumulators: no reads");
+    out->best_key = ctx->best_key.p; out->first_other_order = ctx->first_order.p;
+    out->same_pos_mask = ctx->same_mask.p; out->same_pos_mm = ctx->same_mm.p;
+    out->touched = ctx->touched.p; out->n_reads = ctx->n_reads();
+    return PGM_OK;
+}
+
+int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_resolve_pass: pgm_match_begin has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->n_reads();
+    if (!n) return PGM_OK;
+    pgm::resolve_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(per_read(ctx), n, ctx->pg_len, ctx->read_len, ctx->seed_len,
+                                                                  ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0);
+    LAUNCH_CHECK("resolve_kernel");
+    return PGM_OK;
+}
+
+int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_get_results: no reads");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->n_reads();
+    CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
+    if (n) {
+        pgm::finalize_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->state.as<unsigned long long>(), n,
+                                                                       ctx->out_pos.as<unsigned long long>(),
+                                                                       ctx->out_rc.as<uint8_t>(), ctx->out_mm.as<uint8_t>(),
+                                                                       ctx->hist.as<unsigned long long>());
+        LAUNCH_CHECK("finalize_kernel");
+        if (out_pos) CU(cudaMemcpyAsync(out_pos, ctx->out_pos.p, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+        if (out_rc) CU(cudaMemcpyAsync(out_rc, ctx->out_rc.p, n, cudaMemcpyDefault, ctx->stream));
+        if (out_mm) CU(cudaMemcpyAsync(out_mm, ctx->out_mm.p, n, cudaMemcpyDefault, ctx->stream));
+    }
+    unsigned long long h[257], cnt[16];
+    int bad = 0;
+    CU(cudaMemcpyAsync(h, ctx->hist.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(cnt, ctx->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&bad, ctx->err_flag.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (bad) return fail(ctx, PGM_ERR_BAD_SYMBOL, "pseudogenome text contains a symbol outside ACGT (2-bit text planes cannot hold it)");
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int k = 0; k < 256; k++) stats->per_mm[k] = h[k];
+        stats->matched = (uint64_t)n - h[255];
+        stats->patterns_inserted = cnt[4];
+        stats->table_slots = ctx->n_slots;
+        stats->candidates = cnt[0]; stats->verified = cnt[1]; stats->accepted = cnt[2]; stats->queue_overflows = cnt[3];
+    }
+    return PGM_OK;
+}
+
+int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed, uint32_t seed,
+                  uint32_t min_chars_per_mismatch, char pre_mode, char mode, int rev_compl,
+                  uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->has_text || !ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_map_reads: set the text and the reads first");
+    const uint32_t L = ctx->read_len;
+    if (match_prefix_length != PGM_DISABLED_PREFIX_MODE && match_prefix_length < L)
+        return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_map_reads: prefix matching (matchPrefixLength < readLength) is not used by pgrc-encoder and not supported");
+    if (seed == 0 || min_chars_per_mismatch == 0) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_map_reads: seed and min_chars_per_mismatch must be > 0");
+    if (std::tolower(mode) != 'd' || (pre_seed && std::tolower(pre_mode) != 'd')) {
+        // error convention of the reference: "Unknown matching mode" + exit (ReadsMatchers.cpp:737-739); here a status
+        return fail(ctx, PGM_ERR_UNSUPPORTED, std::string("pgm_map_reads: matching mode '") + mode + "' is not the hash-matcher path ('d'/'D')");
+    }
+    // ReadsMatchers.cpp:699-713
+    const uint32_t max_mm = L / min_chars_per_mismatch;
+    if (max_mm > 127) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_map_reads: min_chars_per_mismatch must be >= 2 (PgRC limit)");
+    const uint32_t reads_exact = std::min(seed, L), pre_exact = std::min(pre_seed, L);
+    uint32_t cur_exact = reads_exact;
+    char cur_mode = mode;
+    if (pre_exact > 0) { cur_exact = pre_exact; cur_mode = pre_mode; }
+    const uint32_t cur_min = std::isupper((unsigned char)cur_mode) ? max_mm : 0;
+    const uint32_t target_mm = L / cur_exact - 1;
+    int rc;
+    auto run_passes = [&]() -> int {
+        int r;
+        if ((r = pgm_scan_pass(ctx, 0)) || (r = pgm_resolve_pass(ctx, 0))) return r;
+        if (rev_compl && ((r = pgm_scan_pass(ctx, 1)) || (r = pgm_resolve_pass(ctx, 1)))) return r;
+        return PGM_OK;
+    };
+    if (L == cur_exact) rc = pgm_match_begin(ctx, L, 1, 0, 0, 0);                    // DefaultReadsExactMatcher (:718-722)
+    else rc = pgm_match_begin(ctx, cur_exact, target_mm + 1, max_mm, cur_min, 0);     // DefaultReadsApproxMatcher (:724-727)
+    if (rc || (rc = run_passes())) return rc;
+    if (pre_exact > 0) {
+        // second phase (:749-779); minMismatches comes from the FIRST phase's targetMismatches (:755)
+        const uint32_t min2 = std::isupper((unsigned char)mode) ? max_mm : target_mm + 1;
+        if ((rc = pgm_match_begin(ctx, reads_exact, L / reads_exact, max_mm, min2, 1)) || (rc = run_passes())) return rc;
+    }
+    return pgm_get_results(ctx, out_pos, out_rc, out_mm, stats);
+}
+
+} // extern "C"

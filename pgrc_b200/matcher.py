@@ -1,0 +1,309 @@
+"""Host-side mirror of the reference's matcher interface for the GPU path.
+
+``map_reads_into_pg`` mirrors ``PgTools::mapReadsIntoPg`` (matching/ReadsMatchers.cpp:693-783):
+same parameter names and meaning, same selection of the exact / approximate matcher and of the
+optional second phase; it returns what the reference's matcher object holds afterwards
+(``readMatchPos``, ``readMatchRC``, ``readMismatchesCount``, ``matchedReadsCount``,
+``matchedCountPerMismatches``; ReadsMatchers.h:32-35,115-116).  ``GpuReadsMatcher`` wraps one
+``pgm_ctx`` of the C ABI (include/pgrc_gpu_matcher.h) — one GPU, one stream — and exposes the
+per-pass steps so that several ranks (one process per GPU) can merge their per-read
+accumulators with ``torch.distributed`` between the scan and the decision
+(``map_reads_into_pg_sharded``).
+
+Everything here is plumbing; the work happens in the CUDA kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import PGM_DISABLED_PREFIX_MODE, PgmAccumulators, PgmError, PgmStats
+
+NOT_MATCHED_POSITION = np.uint64(0xFFFFFFFFFFFFFFFF)   # DefaultReadsMatcher::NOT_MATCHED_POSITION
+NOT_MATCHED_COUNT = 255                                 # PgTools::NOT_MATCHED_COUNT
+DISABLED_PREFIX_MODE = PGM_DISABLED_PREFIX_MODE         # DefaultReadsMatcher::DISABLED_PREFIX_MODE
+
+
+@dataclass
+class MatchResult:
+    pos: "np.ndarray"       # readMatchPos   (uint64)
+    rc: "np.ndarray"        # readMatchRC    (uint8 0/1)
+    mm: "np.ndarray"        # readMismatchesCount (uint8, 255 = unmatched)
+    matched: int = 0        # matchedReadsCount
+    per_mm: "np.ndarray" = field(default_factory=lambda: np.zeros(256, np.uint64))  # matchedCountPerMismatches
+    stats: dict = field(default_factory=dict)
+
+    def matched_reads_bitmap(self, max_mismatches: int = NOT_MATCHED_COUNT - 1) -> np.ndarray:
+        """AbstractReadsApproxMatcher::getMatchedReadsBitmap (ReadsMatchers.cpp:685-691)."""
+        return np.asarray(self.mm) <= max_mismatches
+
+
+def _ptr(a):
+    """Address of a numpy array or a torch tensor (host or CUDA); keeps no reference."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return a.data_ptr()
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+def _rows(a, row_bytes: int) -> int:
+    if a is None:
+        return 0
+    n = a.numel() if hasattr(a, "numel") else a.size
+    if n % row_bytes:
+        raise ValueError("packed reads buffer is not a multiple of the packed read length")
+    return n // row_bytes
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+        self._owner = owner
+
+
+class GpuReadsMatcher:
+    """One matcher context on one GPU (wraps ``pgm_ctx``)."""
+
+    def __init__(self, device: int = 0, use_torch_stream: bool = False):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.pgm_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise PgmError(rc, self._lib.pgm_last_error(None).decode())
+        self._h = h
+        self.device = device
+        self._keep = []
+        self.n_reads = 0
+        self.read_len = 0
+        if use_torch_stream:
+            import torch
+            self._check(self._lib.pgm_set_stream(self._h, ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PgmError(rc, self._lib.pgm_last_error(self._h).decode())
+
+    # -- inputs
+    def set_tuning(self, filter_log2_bits: int = -1, slots_per_pattern: int = 3, ctas_per_sm: int = 3):
+        self._check(self._lib.pgm_set_tuning(self._h, filter_log2_bits, slots_per_pattern, ctas_per_sm))
+
+    def set_text(self, text):
+        """text: ASCII pseudogenome (numpy uint8 / torch uint8, host or device)."""
+        n = text.numel() if hasattr(text, "numel") else text.size
+        self._keep = [k for k in self._keep if k[0] != "text"] + [("text", text)]
+        self._check(self._lib.pgm_set_text(self._h, _ptr(text), n))
+        self.pg_len = n
+
+    def set_text_shard(self, text_slice, slice_begin: int, pg_len: int, own_begin: int, own_end: int):
+        n = text_slice.numel() if hasattr(text_slice, "numel") else text_slice.size
+        self._keep = [k for k in self._keep if k[0] != "text"] + [("text", text_slice)]
+        self._check(self._lib.pgm_set_text_shard(self._h, _ptr(text_slice), slice_begin, n, pg_len, own_begin, own_end))
+        self.pg_len = pg_len
+
+    def set_reads(self, lq_packed, n_packed, read_len: int):
+        """Packed reads exactly as PackedConstantLengthReadsSet stores them (LQ: 4 bases/byte,
+        N set: 3 bases/byte); global read index = LQ first, then N."""
+        n_lq = _rows(lq_packed, (read_len + 3) // 4)
+        n_n = _rows(n_packed, (read_len + 2) // 3)
+        self._keep = [k for k in self._keep if k[0] != "reads"] + [("reads", lq_packed, n_packed)]
+        self._check(self._lib.pgm_set_reads(self._h, _ptr(lq_packed) if n_lq else None, n_lq,
+                                            _ptr(n_packed) if n_n else None, n_n, read_len))
+        self.n_reads = n_lq + n_n
+        self.read_len = read_len
+
+    # -- per-pass steps (initMatching / executeMatching split at the cross-GPU merge point)
+    def match_begin(self, seed_len: int, parts: int, max_mm: int, min_mm: int, continuation: bool = False):
+        self._check(self._lib.pgm_match_begin(self._h, seed_len, parts, max_mm, min_mm, int(continuation)))
+
+    def scan_pass(self, rev_mode: bool):
+        self._check(self._lib.pgm_scan_pass(self._h, int(rev_mode)))
+
+    def resolve_pass(self, rev_mode: bool):
+        self._check(self._lib.pgm_resolve_pass(self._h, int(rev_mode)))
+
+    def accumulators(self):
+        """torch views (no copy) of the per-read accumulators of the current pass."""
+        import torch
+        acc = PgmAccumulators()
+        self._check(self._lib.pgm_get_accumulators(self._h, ctypes.byref(acc)))
+        n = int(acc.n_reads)
+        dev = f"cuda:{self.device}"
+        mk = lambda p, cnt, ts: torch.as_tensor(_DevArray(p, cnt, ts, self), device=dev)
+        return {"best_key": mk(acc.best_key, n, "<i8"), "first_other_order": mk(acc.first_other_order, n, "<i8"),
+                "same_pos_mask": mk(acc.same_pos_mask, n, "<i4"), "same_pos_mm": mk(acc.same_pos_mm, n, "|u1"),
+                "touched": mk(acc.touched, 1, "<i4")}
+
+    def synchronize(self):
+        self._check(self._lib.pgm_synchronize(self._h))
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.pgm_kernel_launches(self._h))
+
+    def _alloc_out(self, out):
+        if out is not None:
+            return out
+        n = self.n_reads
+        return (np.empty(n, np.uint64), np.empty(n, np.uint8), np.empty(n, np.uint8))
+
+    @staticmethod
+    def _result(out, st: PgmStats) -> MatchResult:
+        per = np.frombuffer(bytes(st.per_mm), np.uint64).copy()
+        stats = {k: int(getattr(st, k)) for k in ("patterns_inserted", "table_slots", "candidates", "verified",
+                                                  "accepted", "queue_overflows")}
+        return MatchResult(out[0], out[1], out[2], int(st.matched), per, stats)
+
+    def get_results(self, out=None) -> MatchResult:
+        out = self._alloc_out(out)
+        st = PgmStats()
+        self._check(self._lib.pgm_get_results(self._h, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), ctypes.byref(st)))
+        return self._result(out, st)
+
+    # -- the whole stage on this GPU
+    def map_reads(self, seed: int = 38, min_chars_per_mismatch: int = 3, mode: str = "d", pre_seed: int = 0,
+                  pre_mode: str = "d", rev_compl: bool = True, match_prefix_length: int = DISABLED_PREFIX_MODE,
+                  out=None) -> MatchResult:
+        out = self._alloc_out(out)
+        st = PgmStats()
+        self._check(self._lib.pgm_map_reads(self._h, match_prefix_length, pre_seed, seed, min_chars_per_mismatch,
+                                            pre_mode.encode()[:1], mode.encode()[:1], int(rev_compl),
+                                            _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), ctypes.byref(st)))
+        return self._result(out, st)
+
+
+@dataclass
+class MatchPlan:
+    """Parameter derivation of mapReadsIntoPg (ReadsMatchers.cpp:699-713,749-756): a list of
+    matcher phases, each (seed_len, parts, max_mm, min_mm, continuation)."""
+    phases: list
+
+    @staticmethod
+    def derive(read_len: int, seed: int, min_chars_per_mismatch: int, mode: str, pre_seed: int = 0,
+               pre_mode: str = "d") -> "MatchPlan":
+        if mode.lower() != "d" or (pre_seed and pre_mode.lower() != "d"):
+            raise PgmError(-6, f"matching mode '{mode}' is not the hash-matcher path ('d'/'D')")
+        if seed <= 0 or min_chars_per_mismatch <= 0:
+            raise PgmError(-1, "seed and min_chars_per_mismatch must be > 0")
+        L = read_len
+        max_mm = L // min_chars_per_mismatch
+        reads_exact, pre_exact = min(seed, L), min(pre_seed, L)
+        cur_exact, cur_mode = (pre_exact, pre_mode) if pre_exact > 0 else (reads_exact, mode)
+        cur_min = max_mm if cur_mode.isupper() else 0
+        target_mm = L // cur_exact - 1
+        phases = [(L, 1, 0, 0, False)] if L == cur_exact else [(cur_exact, target_mm + 1, max_mm, cur_min, False)]
+        if pre_exact > 0:
+            min2 = max_mm if mode.isupper() else target_mm + 1
+            phases.append((reads_exact, L // reads_exact, max_mm, min2, True))
+        return MatchPlan(phases)
+
+
+def map_reads_into_pg(text, lq_packed, n_packed, read_len: int, *, rev_compl_pg: bool = True,
+                      match_prefix_length: int = DISABLED_PREFIX_MODE, pre_reads_exact_matching_chars: int = 0,
+                      reads_exact_matching_chars: int = 38, min_chars_per_mismatch: int = 3,
+                      pre_matching_mode: str = "d", matching_mode: str = "d", device: int = 0,
+                      matcher: GpuReadsMatcher | None = None) -> MatchResult:
+    """Single-GPU mirror of ``PgTools::mapReadsIntoPg`` (matching part only; the archive export,
+    ReadsMatchers.cpp:785-792, stays on the host side of PgRC)."""
+    own = matcher is None
+    m = matcher or GpuReadsMatcher(device)
+    try:
+        m.set_text(text)
+        m.set_reads(lq_packed, n_packed, read_len)
+        return m.map_reads(reads_exact_matching_chars, min_chars_per_mismatch, matching_mode,
+                           pre_reads_exact_matching_chars, pre_matching_mode, rev_compl_pg, match_prefix_length)
+    finally:
+        if own:
+            m.close()
+
+
+def shard_plan(pg_len: int, rank: int, world: int):
+    """(slice_begin, slice_len, own_begin, own_end) of one rank: contiguous ranges of seed-window
+    starts with PGM_SHARD_HALO bases of text on either side."""
+    lib = _lib.load()
+    v = [ctypes.c_uint64() for _ in range(4)]
+    rc = lib.pgm_shard_plan(pg_len, rank, world, *[ctypes.byref(x) for x in v])
+    if rc != 0:
+        raise PgmError(rc, "pgm_shard_plan")
+    return tuple(int(x.value) for x in v)
+
+
+def merge_accumulators(m: GpuReadsMatcher, group=None):
+    """The one exchange step of the sharded path: per-read MIN / SUM all-reduce of the pass
+    accumulators over NCCL (NVLink / NVSwitch).  The rarely used ones are merged only when some
+    rank touched them."""
+    import torch
+    import torch.distributed as dist
+    acc = m.accumulators()
+    dist.all_reduce(acc["best_key"], op=dist.ReduceOp.MIN, group=group)
+    flag = acc["touched"].clone()
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()):
+        dist.all_reduce(acc["first_other_order"], op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(acc["same_pos_mask"], op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(acc["same_pos_mm"], op=dist.ReduceOp.MIN, group=group)
+    return acc
+
+
+def run_plan_sharded(m: GpuReadsMatcher, plan: MatchPlan, rev_compl_pg: bool = True, group=None, merge=merge_accumulators):
+    """Runs the matcher phases on a context that holds one text shard; after every scan the
+    per-read accumulators are merged across ranks, then every rank applies the decision, so the
+    per-read state stays replicated."""
+    for seed_len, parts, max_mm, min_mm, cont in plan.phases:
+        m.match_begin(seed_len, parts, max_mm, min_mm, cont)
+        for rev in ((False, True) if rev_compl_pg else (False,)):
+            m.scan_pass(rev)
+            merge(m, group)
+            m.resolve_pass(rev)
+
+
+def map_reads_into_pg_sharded(text, lq_packed, n_packed, read_len: int, *, rank: int, world: int, device: int,
+                              rev_compl_pg: bool = True, pre_reads_exact_matching_chars: int = 0,
+                              reads_exact_matching_chars: int = 38, min_chars_per_mismatch: int = 3,
+                              pre_matching_mode: str = "d", matching_mode: str = "d", group=None,
+                              matcher: GpuReadsMatcher | None = None) -> MatchResult:
+    """Multi-GPU mirror of mapReadsIntoPg: the pseudogenome is sharded into contiguous ranges
+    (one per rank, halos of PGM_SHARD_HALO bases), the reads and the seed table are replicated,
+    and per-read best matches are merged with an NCCL all-reduce after every pass."""
+    pg_len = text.numel() if hasattr(text, "numel") else text.size
+    sb, sl, ob, oe = shard_plan(pg_len, rank, world)
+    own = matcher is None
+    m = matcher or GpuReadsMatcher(device, use_torch_stream=True)
+    try:
+        m.set_text_shard(text[sb:sb + sl], sb, pg_len, ob, oe)
+        m.set_reads(lq_packed, n_packed, read_len)
+        plan = MatchPlan.derive(read_len, reads_exact_matching_chars, min_chars_per_mismatch, matching_mode,
+                                pre_reads_exact_matching_chars, pre_matching_mode)
+        run_plan_sharded(m, plan, rev_compl_pg, group)
+        return m.get_results()
+    finally:
+        if own:
+            m.close()

@@ -1,0 +1,137 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle
+(oracle/pgrc_oracle.c, pinned against the reference's own classes) on the same seeded inputs.
+Bar: bit-exact positions, strands, mismatch counts, matched count and histogram."""
+import numpy as np
+import pytest
+
+import oracle
+from pgrc_b200 import matcher, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(inp, **kw):
+    okw = dict(seed=kw.get("reads_exact_matching_chars", 38), min_chars_per_mismatch=kw.get("min_chars_per_mismatch", 3),
+               mode=kw.get("matching_mode", "d"), pre_seed=kw.get("pre_reads_exact_matching_chars", 0),
+               pre_mode=kw.get("pre_matching_mode", "d"), rev_compl=kw.get("rev_compl_pg", True))
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **okw)
+    got = matcher.map_reads_into_pg(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+    bad = np.nonzero((got.pos != want.pos) | (got.rc != want.rc) | (got.mm != want.mm))[0]
+    assert bad.size == 0, (f"{inp.name} {kw}: {bad.size} reads differ, first {bad[:5]}: "
+                           f"gpu pos/rc/mm {got.pos[bad[:5]]} {got.rc[bad[:5]]} {got.mm[bad[:5]]} "
+                           f"oracle {want.pos[bad[:5]]} {want.rc[bad[:5]]} {want.mm[bad[:5]]}")
+    assert got.matched == want.matched
+    if not (inp.read_len == okw["seed"] and okw["pre_seed"] == 0):
+        assert np.array_equal(got.per_mm, want.per_mm)
+    return got, want
+
+
+@pytest.mark.parametrize("seed,L", [(1, 100), (2, 100), (3, 150), (4, 120), (5, 64), (6, 255)])
+def test_adversarial_default_params(seed, L):
+    got, want = _check(synth.adversarial(seed, L))
+    if L <= 150:
+        assert want.extra["n_cross_strand_skips"] > 0  # the ":313" quirk is exercised
+
+
+@pytest.mark.parametrize("kw", [
+    dict(reads_exact_matching_chars=30),
+    dict(reads_exact_matching_chars=32),
+    dict(reads_exact_matching_chars=33),
+    dict(reads_exact_matching_chars=45),
+    dict(reads_exact_matching_chars=100),                      # exact path
+    dict(reads_exact_matching_chars=200),                      # clamped to read length: exact path
+    dict(matching_mode="D"),                                   # shortcut mode
+    dict(pre_reads_exact_matching_chars=100),                  # exact pre-phase + continuation
+    dict(pre_reads_exact_matching_chars=50, reads_exact_matching_chars=38),
+    dict(pre_reads_exact_matching_chars=50, matching_mode="D"),
+    dict(pre_reads_exact_matching_chars=100, pre_matching_mode="D", matching_mode="D"),
+    dict(min_chars_per_mismatch=2),
+    dict(min_chars_per_mismatch=10),
+    dict(rev_compl_pg=False),
+])
+def test_adversarial_parameter_matrix(kw):
+    for s in (11, 12):
+        _check(synth.adversarial(s, 100), **kw)
+
+
+def test_config1_shape_scaled():
+    # BASELINE config 1 shape / 20: SE, 100 bp, 0.1 % substitutions
+    _check(synth.workload(250_000, 20_000, 100, 0.001, seed=101, name="c1/20"))
+
+
+def test_config2_shape_scaled():
+    # BASELINE config 2 shape / 100: 150 bp, 0.5 %, 3 seeds per read
+    _check(synth.workload(500_000, 100_000, 150, 0.005, seed=102, n_frac=0.02, name="c2/100"))
+
+
+def test_config4_shape_scaled_high_error():
+    _check(synth.workload(400_000, 60_000, 100, 0.01, seed=104, name="c4 scaled"))
+
+
+def test_edge_cases():
+    rng = np.random.default_rng(5)
+    g = synth.random_genome(5000, rng)
+    reads = synth.sample_reads(g, 300, 100, 0.01, rng)
+    # text shorter than a read, than a seed, empty reads sets, single read
+    for text in (g[:99], g[:37], g[:38], g[:100], g[:101], g):
+        inp = synth.MatcherInputs(np.ascontiguousarray(text), reads, np.zeros((0, 100), np.uint8), 100, f"text{len(text)}")
+        _check(inp)
+    inp = synth.MatcherInputs(g, reads[:1], np.zeros((0, 100), np.uint8), 100, "one read")
+    _check(inp)
+    inp = synth.MatcherInputs(g, np.zeros((0, 100), np.uint8), synth.inject_n(reads[:50], rng), 100, "only N reads")
+    _check(inp)
+    # duplicated reads and low-complexity text: long chains of identical seeds
+    dup = np.repeat(reads[:10], 40, axis=0)
+    polya = np.full(3000, ord("A"), np.uint8)
+    text = np.concatenate([g[:1500], polya, g[1500:3000]])
+    areads = np.full((200, 100), ord("A"), np.uint8)
+    inp = synth.MatcherInputs(np.ascontiguousarray(text), np.concatenate([dup, areads]), np.zeros((0, 100), np.uint8), 100, "dups")
+    _check(inp)
+
+
+def test_bad_symbol_is_an_error():
+    rng = np.random.default_rng(6)
+    g = synth.random_genome(4000, rng)
+    g[1234] = ord("N")
+    reads = synth.sample_reads(synth.random_genome(4000, rng), 10, 100, 0.01, rng)
+    with pytest.raises(matcher.PgmError) as e:
+        matcher.map_reads_into_pg(g, synth.pack_reads(reads), None, 100)
+    assert e.value.status == -5
+
+
+def test_unsupported_modes_fail_loudly():
+    rng = np.random.default_rng(7)
+    g = synth.random_genome(4000, rng)
+    reads = synth.sample_reads(g, 10, 100, 0.01, rng)
+    for kw in (dict(matching_mode="c"), dict(matching_mode="i"), dict(match_prefix_length=50)):
+        with pytest.raises(matcher.PgmError) as e:
+            matcher.map_reads_into_pg(g, synth.pack_reads(reads), None, 100, **kw)
+        assert e.value.status == -6
+
+
+def test_text_left_untouched_and_device_inputs():
+    import torch
+    inp = synth.adversarial(21, 100)
+    before = inp.text.copy()
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, 100)
+    t = torch.from_numpy(inp.text).cuda()
+    lq = torch.from_numpy(inp.lq_packed).cuda()
+    nn = torch.from_numpy(inp.n_packed).cuda()
+    got = matcher.map_reads_into_pg(t, lq, nn, 100)
+    assert np.array_equal(inp.text, before) and np.array_equal(t.cpu().numpy(), before)
+    assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)
+
+
+def test_context_reuse_and_filter_off():
+    inp = synth.adversarial(22, 100)
+    inp2 = synth.adversarial(23, 150)
+    w1 = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, 100)
+    w2 = oracle.oracle_map_reads(inp2.text, inp2.lq_packed, inp2.n_packed, 150)
+    with matcher.GpuReadsMatcher(0) as m:
+        for fb in (-1, 0, 12):
+            m.set_tuning(filter_log2_bits=fb)
+            g1 = matcher.map_reads_into_pg(inp.text, inp.lq_packed, inp.n_packed, 100, matcher=m)
+            g2 = matcher.map_reads_into_pg(inp2.text, inp2.lq_packed, inp2.n_packed, 150, matcher=m)
+            assert np.array_equal(g1.pos, w1.pos) and np.array_equal(g1.mm, w1.mm) and np.array_equal(g1.rc, w1.rc)
+            assert np.array_equal(g2.pos, w2.pos) and np.array_equal(g2.mm, w2.mm) and np.array_equal(g2.rc, w2.rc)
+        assert m.kernel_launches() > 0
