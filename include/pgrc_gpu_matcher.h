@@ -155,6 +155,18 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
 /* ---- introspection (bench / tests) -------------------------------------------------------*/
 /* Number of kernels this context has launched so far. */
 uint64_t pgm_kernel_launches(const pgm_ctx *ctx);
+/* Per-kernel device times, for the roofline in bench.py.  With profiling on, every kernel
+ * launch of this context is bracketed by CUDA events on the context's stream; pgm_get_timings
+ * synchronizes, adds up the event durations per kernel since the last call and resets them.
+ * launches[] counts the launches behind each sum. */
+enum { PGM_K_PACK_TEXT = 0, PGM_K_RC_TEXT, PGM_K_UNPACK_READS, PGM_K_INIT_STATE, PGM_K_BUILD_TABLE,
+       PGM_K_SCAN, PGM_K_RESOLVE, PGM_K_FINALIZE, PGM_K_COUNT };
+typedef struct pgm_timings {
+    double ms[PGM_K_COUNT];
+    uint64_t launches[PGM_K_COUNT];
+} pgm_timings;
+int pgm_set_profiling(pgm_ctx *ctx, int on);
+int pgm_get_timings(pgm_ctx *ctx, pgm_timings *out);
 /* Tuning knobs; call before pgm_match_begin.  filter_log2_bits = 0 disables the L2-resident
  * pre-filter; slots_per_pattern sets the table size (>= 2). */
 int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm);

@@ -22,7 +22,9 @@ STATUS_NAMES = {0: "PGM_OK", -1: "PGM_ERR_INVALID_ARG", -2: "PGM_ERR_NO_DEVICE",
 EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pgm_set_stream", "pgm_synchronize",
            "pgm_set_text", "pgm_set_text_shard", "pgm_shard_plan", "pgm_set_reads", "pgm_match_begin",
            "pgm_scan_pass", "pgm_get_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_map_reads",
-           "pgm_kernel_launches", "pgm_set_tuning"]
+           "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings"]
+
+KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize"]
 
 
 class PgmStats(ctypes.Structure):
@@ -30,6 +32,10 @@ class PgmStats(ctypes.Structure):
                 ("patterns_inserted", ctypes.c_uint64), ("table_slots", ctypes.c_uint64),
                 ("candidates", ctypes.c_uint64), ("verified", ctypes.c_uint64),
                 ("accepted", ctypes.c_uint64), ("queue_overflows", ctypes.c_uint64)]
+
+
+class PgmTimings(ctypes.Structure):
+    _fields_ = [("ms", ctypes.c_double * len(KERNEL_NAMES)), ("launches", ctypes.c_uint64 * len(KERNEL_NAMES))]
 
 
 class PgmAccumulators(ctypes.Structure):
@@ -77,5 +83,7 @@ def load() -> ctypes.CDLL:
                                   ctypes.POINTER(PgmStats)]
     lib.pgm_kernel_launches.restype = u64; lib.pgm_kernel_launches.argtypes = [vp]
     lib.pgm_set_tuning.restype = ci; lib.pgm_set_tuning.argtypes = [vp, ci, ci, ci]
+    lib.pgm_set_profiling.restype = ci; lib.pgm_set_profiling.argtypes = [vp, ci]
+    lib.pgm_get_timings.restype = ci; lib.pgm_get_timings.argtypes = [vp, ctypes.POINTER(PgmTimings)]
     _lib = lib
     return lib

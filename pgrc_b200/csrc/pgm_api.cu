@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -31,6 +32,12 @@ struct pgm_ctx {
     bool own_stream = false;
     std::string err;
     uint64_t launches = 0;
+
+    // per-kernel event timing (pgm_set_profiling)
+    struct EvPair { int kind; cudaEvent_t a, b; };
+    bool profiling = false;
+    std::vector<EvPair> ev_used;
+    std::vector<cudaEvent_t> ev_free;
 
     // tuning
     int filter_log2_bits = -1; // -1 = auto
@@ -90,6 +97,23 @@ int cuda_fail(pgm_ctx *c, cudaError_t e, const char *what) {
         ctx->launches++;                                                 \
         cudaError_t _e = cudaGetLastError();                             \
         if (_e != cudaSuccess) return cuda_fail(ctx, _e, name);          \
+    } while (0)
+
+cudaEvent_t ev_get(pgm_ctx *c) {
+    if (!c->ev_free.empty()) { cudaEvent_t e = c->ev_free.back(); c->ev_free.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Launch wrapper: counts the launch, checks it, and (profiling on) brackets it with events.
+#define KLAUNCH(kind, name, ...)                                         \
+    do {                                                                 \
+        cudaEvent_t _a = nullptr, _b = nullptr;                          \
+        if (ctx->profiling) { _a = ev_get(ctx); _b = ev_get(ctx); cudaEventRecord(_a, ctx->stream); } \
+        __VA_ARGS__;                                                     \
+        if (ctx->profiling) { cudaEventRecord(_b, ctx->stream); ctx->ev_used.push_back({kind, _a, _b}); } \
+        LAUNCH_CHECK(name);                                              \
     } while (0)
 
 int ensure(pgm_ctx *ctx, DevBuf &b, size_t bytes) {
@@ -214,6 +238,8 @@ void pgm_destroy(pgm_ctx *ctx) {
                       &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->slots, &ctx->next, &ctx->filter,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
+    for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (cudaEvent_t e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -248,6 +274,29 @@ int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, in
 }
 
 uint64_t pgm_kernel_launches(const pgm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pgm_set_profiling(pgm_ctx *ctx, int on) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    ctx->profiling = on != 0;
+    return PGM_OK;
+}
+
+int pgm_get_timings(pgm_ctx *ctx, pgm_timings *out) {
+    if (!ctx || !out) return PGM_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memset(out, 0, sizeof *out);
+    for (const pgm_ctx::EvPair &e : ctx->ev_used) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e.a, e.b));
+        out->ms[e.kind] += ms;
+        out->launches[e.kind]++;
+        ctx->ev_free.push_back(e.a);
+        ctx->ev_free.push_back(e.b);
+    }
+    ctx->ev_used.clear();
+    return PGM_OK;
+}
 
 int pgm_shard_plan(uint64_t pg_len, int rank, int world, uint64_t *slice_begin, uint64_t *slice_len,
                    uint64_t *own_begin, uint64_t *own_end) {
@@ -298,12 +347,10 @@ int pgm_set_text_shard(pgm_ctx *ctx, const char *slice, uint64_t slice_begin, ui
             CU(cudaMemcpyAsync(ctx->ascii_stage.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
             src = ctx->ascii_stage.as<uint8_t>();
         }
-        pgm::pack_text_kernel<<<grid_for((n + 31) / 32, 256), 256, 0, ctx->stream>>>(src, n, flo, fhi, off / 32, ctx->err_flag.as<int>());
-        LAUNCH_CHECK("pack_text_kernel");
+        KLAUNCH(PGM_K_PACK_TEXT, "pack_text_kernel", pgm::pack_text_kernel<<<grid_for((n + 31) / 32, 256), 256, 0, ctx->stream>>>(src, n, flo, fhi, off / 32, ctx->err_flag.as<int>()));
     }
     if (slice_len) {
-        pgm::rc_text_kernel<<<grid_for(plane_words(slice_len), 256), 256, 0, ctx->stream>>>(flo, fhi, slice_len, rlo, rhi);
-        LAUNCH_CHECK("rc_text_kernel");
+        KLAUNCH(PGM_K_RC_TEXT, "rc_text_kernel", pgm::rc_text_kernel<<<grid_for(plane_words(slice_len), 256), 256, 0, ctx->stream>>>(flo, fhi, slice_len, rlo, rhi));
     }
     ctx->pg_len = pg_len; ctx->slice_begin = slice_begin; ctx->slice_len = slice_len;
     ctx->own_begin = own_begin; ctx->own_end = own_end;
@@ -346,8 +393,7 @@ int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq, const u
             CU(cudaMemcpyAsync(ctx->packed_stage.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
             src = ctx->packed_stage.as<uint8_t>();
         }
-        pgm::unpack_reads_kernel<<<grid_for(pt.cnt, 128), 128, 0, ctx->stream>>>(src, pt.cnt, read_len, pt.plen, pt.with_n, pt.dst, pt.stride, W);
-        LAUNCH_CHECK("unpack_reads_kernel");
+        KLAUNCH(PGM_K_UNPACK_READS, "unpack_reads_kernel", pgm::unpack_reads_kernel<<<grid_for(pt.cnt, 128), 128, 0, ctx->stream>>>(src, pt.cnt, read_len, pt.plen, pt.with_n, pt.dst, pt.stride, W));
         if (src == ctx->packed_stage.as<uint8_t>() && pt.with_n == 0 && n_n) {
             // the N set reuses the staging buffer: a second ensure() may reallocate it while the
             // LQ unpack is still running, so wait for it
@@ -392,16 +438,14 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     if (!continuation) CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
     else CU(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 4, 0, sizeof(unsigned long long), ctx->stream));
     if (n) {
-        pgm::init_state_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(per_read(ctx), n, continuation ? 0 : 1);
-        LAUNCH_CHECK("init_state_kernel");
+        KLAUNCH(PGM_K_INIT_STATE, "init_state_kernel", pgm::init_state_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(per_read(ctx), n, continuation ? 0 : 1));
     }
     ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
     if (n_patterns) {
         const uint32_t tail = seed_len % 32 ? (1u << (seed_len % 32)) - 1u : 0xFFFFFFFFu;
-        pgm::build_table_kernel<<<grid_for(n_patterns, 256), 256, 0, ctx->stream>>>(
+        KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid_for(n_patterns, 256), 256, 0, ctx->stream>>>(
             reads_view(ctx), ctx->state.as<unsigned long long>(), table_view(ctx), seed_len, parts, min_mm,
-            continuation ? 1 : 0, tail, ctx->counters.as<unsigned long long>() + 4);
-        LAUNCH_CHECK("build_table_kernel");
+            continuation ? 1 : 0, tail, ctx->counters.as<unsigned long long>() + 4));
     }
     ctx->phase_active = true;
     return PGM_OK;
@@ -444,7 +488,7 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
     CU(cudaMemsetAsync(sp.tile_counter, 0, sizeof(unsigned int), ctx->stream));
     const unsigned int grid = (unsigned int)std::min<uint64_t>(sp.n_tiles, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
     const int nch = (int)((ctx->seed_len + 31) / 32);
-    switch (nch) {
+    KLAUNCH(PGM_K_SCAN, "scan_kernel", switch (nch) {
         case 1: launch_scan<1>(sp, grid, ctx->stream); break;
         case 2: launch_scan<2>(sp, grid, ctx->stream); break;
         case 3: launch_scan<3>(sp, grid, ctx->stream); break;
@@ -453,8 +497,7 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
         case 6: launch_scan<6>(sp, grid, ctx->stream); break;
         case 7: launch_scan<7>(sp, grid, ctx->stream); break;
         default: launch_scan<8>(sp, grid, ctx->stream); break;
-    }
-    LAUNCH_CHECK("scan_kernel");
+    });
     return PGM_OK;
 }
 
@@ -473,9 +516,8 @@ int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode) {
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->n_reads();
     if (!n) return PGM_OK;
-    pgm::resolve_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(per_read(ctx), n, ctx->pg_len, ctx->read_len, ctx->seed_len,
-                                                                  ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0);
-    LAUNCH_CHECK("resolve_kernel");
+    KLAUNCH(PGM_K_RESOLVE, "resolve_kernel", pgm::resolve_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(per_read(ctx), n, ctx->pg_len, ctx->read_len, ctx->seed_len,
+                                                                  ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0));
     return PGM_OK;
 }
 
@@ -486,11 +528,10 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
     const uint32_t n = ctx->n_reads();
     CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
     if (n) {
-        pgm::finalize_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->state.as<unsigned long long>(), n,
+        KLAUNCH(PGM_K_FINALIZE, "finalize_kernel", pgm::finalize_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->state.as<unsigned long long>(), n,
                                                                        ctx->out_pos.as<unsigned long long>(),
                                                                        ctx->out_rc.as<uint8_t>(), ctx->out_mm.as<uint8_t>(),
-                                                                       ctx->hist.as<unsigned long long>());
-        LAUNCH_CHECK("finalize_kernel");
+                                                                       ctx->hist.as<unsigned long long>()));
         if (out_pos) CU(cudaMemcpyAsync(out_pos, ctx->out_pos.p, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
         if (out_rc) CU(cudaMemcpyAsync(out_rc, ctx->out_rc.p, n, cudaMemcpyDefault, ctx->stream));
         if (out_mm) CU(cudaMemcpyAsync(out_mm, ctx->out_mm.p, n, cudaMemcpyDefault, ctx->stream));

@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import PGM_DISABLED_PREFIX_MODE, PgmAccumulators, PgmError, PgmStats
+from ._lib import KERNEL_NAMES, PGM_DISABLED_PREFIX_MODE, PgmAccumulators, PgmError, PgmStats, PgmTimings
 
 NOT_MATCHED_POSITION = np.uint64(0xFFFFFFFFFFFFFFFF)   # DefaultReadsMatcher::NOT_MATCHED_POSITION
 NOT_MATCHED_COUNT = 255                                 # PgTools::NOT_MATCHED_COUNT
@@ -168,6 +168,15 @@ class GpuReadsMatcher:
 
     def kernel_launches(self) -> int:
         return int(self._lib.pgm_kernel_launches(self._h))
+
+    def set_profiling(self, on: bool = True):
+        self._check(self._lib.pgm_set_profiling(self._h, int(on)))
+
+    def timings(self) -> dict:
+        """Per-kernel device time (ms) and launch count since the last call: {name: (ms, launches)}."""
+        t = PgmTimings()
+        self._check(self._lib.pgm_get_timings(self._h, ctypes.byref(t)))
+        return {k: (float(t.ms[i]), int(t.launches[i])) for i, k in enumerate(KERNEL_NAMES)}
 
     def _alloc_out(self, out):
         if out is not None:

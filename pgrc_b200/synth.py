@@ -215,3 +215,90 @@ def adversarial(seed: int, read_len: int = 100, n_reads: int = 3000, text_len: i
         else:               # 2-3 random N
             nn[i, rng.choice(L, size=int(rng.integers(2, 4)), replace=False)] = _N
     return MatcherInputs(text, lq, nn, L, f"adversarial(seed={seed},L={L})")
+
+
+# ---------------------------------------------------------------------------------------------
+# Device-side generator for the full-size bench workloads (same shapes as `workload`, built with
+# torch on the GPU because numpy needs minutes for 10^7 reads).  torch is plumbing here.
+
+# BASELINE.json configs at matcher level: genome length, LQ reads handed to the
+# matcher, read length, substitution rate, pseudogenome length / genome length.
+# C1 and C2 sizes are the reference's own (probed) matcher inputs; C3-C5 are the survey's estimates.
+CONFIGS = {
+    "c1": dict(genome_len=5_000_000, n_reads=384_497, read_len=100, err=0.001, copies=2.0687),
+    "c2": dict(genome_len=50_000_000, n_reads=10_447_991, read_len=150, err=0.005, copies=2.8126),
+    "c3": dict(genome_len=100_000_000, n_reads=32_000_000, read_len=150, err=0.005, copies=2.5),
+    "c4": dict(genome_len=1_000_000_000, n_reads=126_000_000, read_len=100, err=0.01, copies=2.5),
+    "c5": dict(genome_len=3_000_000_000, n_reads=330_000_000, read_len=150, err=0.005, copies=2.5),
+}
+
+
+def scaled_config(name: str, scale: float = 1.0) -> dict:
+    c = dict(CONFIGS[name])
+    c["genome_len"] = max(2000, int(c["genome_len"] * scale))
+    c["n_reads"] = max(1, int(c["n_reads"] * scale))
+    return c
+
+
+def workload_device(genome_len: int, n_reads: int, read_len: int, err: float, copies: float, seed: int,
+                    device, mean_contig: int = 4000, chunk: int = 1 << 20):
+    """Returns (text_ascii uint8[pg_len], lq_packed uint8[n_reads, ceil(L/4)]) as torch tensors on
+    `device`: uniform-random genome, contigs in random orientation repeated `copies` times, reads
+    from uniform positions, 50 % reverse-complemented, i.i.d. substitutions with probability `err`
+    and at least one per read (the matcher only sees error-containing reads)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    G, L = genome_len, read_len
+    genome = torch.randint(0, 4, (G,), dtype=torch.uint8, device=device, generator=g)
+    pieces = []
+    remaining = copies
+    while remaining > 1e-9:
+        frac = min(1.0, remaining)
+        span = max(1, int(G * frac))
+        lo = 0 if span >= G else int(torch.randint(0, G - span + 1, (1,), device=device, generator=g).item())
+        ncut = max(0, span // max(1, mean_contig) - 1)
+        cuts = torch.unique(torch.randint(lo + 1, lo + span, (ncut,), device=device, generator=g)) if ncut and span > 1 \
+            else torch.empty(0, dtype=torch.int64, device=device)
+        bounds = torch.cat([torch.tensor([lo], device=device), cuts, torch.tensor([lo + span], device=device)])
+        flips = torch.rand(bounds.numel() - 1, device=device, generator=g) < 0.5
+        for s in range(lo, lo + span, 1 << 26):
+            pos = torch.arange(s, min(lo + span, s + (1 << 26)), device=device)
+            seg = torch.searchsorted(bounds, pos, right=True) - 1
+            f = flips[seg]
+            src = torch.where(f, bounds[seg] + bounds[seg + 1] - 1 - pos, pos)
+            piece = genome[src]
+            pieces.append(torch.where(f, 3 - piece, piece))
+        remaining -= frac
+    text_codes = torch.cat(pieces)
+    lut = torch.tensor([ord(c) for c in "ACGT"], dtype=torch.uint8, device=device)
+    text = lut[text_codes.long()]
+    del text_codes, pieces
+    plen = (L + 3) // 4
+    packed = torch.empty((n_reads, plen), dtype=torch.uint8, device=device)
+    ar = torch.arange(L, device=device)
+    for s in range(0, n_reads, chunk):
+        m = min(chunk, n_reads - s)
+        start = torch.randint(0, G - L + 1, (m,), device=device, generator=g)
+        flip = torch.rand(m, device=device, generator=g) < 0.5
+        idx = torch.where(flip[:, None], start[:, None] + (L - 1 - ar)[None, :], start[:, None] + ar[None, :])
+        r = genome[idx]
+        r = torch.where(flip[:, None], 3 - r, r)
+        mask = torch.rand((m, L), device=device, generator=g) < err
+        none = ~mask.any(dim=1)
+        forced = torch.randint(0, L, (m,), device=device, generator=g)
+        mask |= none[:, None] & (ar[None, :] == forced[:, None])
+        shift = torch.randint(1, 4, (m, L), dtype=torch.uint8, device=device, generator=g)
+        r = torch.where(mask, (r + shift) & 3, r)
+        if plen * 4 != L:
+            r = torch.cat([r, torch.zeros((m, plen * 4 - L), dtype=torch.uint8, device=device)], dim=1)
+        r = r.view(m, plen, 4)
+        packed[s:s + m] = (r[:, :, 0] << 6) | (r[:, :, 1] << 4) | (r[:, :, 2] << 2) | r[:, :, 3]
+    return text, packed
+
+
+def unpack_reads_ascii(packed: np.ndarray, read_len: int) -> np.ndarray:
+    """Inverse of pack_reads for the ACGT set (n x L ASCII)."""
+    p = np.ascontiguousarray(packed, np.uint8)
+    codes = np.stack([(p >> 6) & 3, (p >> 4) & 3, (p >> 2) & 3, p & 3], axis=2).reshape(p.shape[0], -1)[:, :read_len]
+    return _CODE2ASCII[codes]

@@ -1,0 +1,51 @@
+"""CPU, live: the plain-C oracle against the reference's own classes (oracle/_ref, built from
+/root/reference by oracle/Makefile) on fresh seeded inputs.  Skipped where oracle/_ref is absent
+(the committed golden vectors in tests/test_oracle_golden.py cover that case)."""
+import numpy as np
+import pytest
+
+import oracle
+from pgrc_b200 import synth
+
+pytestmark = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def _cmp(inp, **kw):
+    r = oracle.ref_map_reads(inp.text, inp.lq_reads, inp.n_reads, inp.read_len, **kw)
+    o = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+    assert np.array_equal(o.pos, r.pos) and np.array_equal(o.rc, r.rc) and np.array_equal(o.mm, r.mm), inp.name
+    assert (o.matched, o.better) == (r.matched, r.better)
+    # falseMatchCount: the reference adds table-dependent collisions in some runs (time-seeded table), never fewer
+    assert r.false_matches >= o.false_matches
+    return o
+
+
+@pytest.mark.parametrize("seed,L", [(31, 100), (32, 150), (33, 120), (34, 70), (35, 200)])
+def test_adversarial(seed, L):
+    o = _cmp(synth.adversarial(seed, L, n_reads=1500, text_len=30000))
+    if L <= 150:
+        assert o.extra["n_cross_strand_skips"] > 0
+
+
+@pytest.mark.parametrize("kw", [dict(seed=30), dict(seed=33), dict(seed=50), dict(seed=100), dict(mode="D"),
+                                dict(pre_seed=100), dict(pre_seed=50, mode="D"), dict(min_chars_per_mismatch=2),
+                                dict(min_chars_per_mismatch=7), dict(rev_compl=False)])
+def test_parameter_matrix(kw):
+    _cmp(synth.adversarial(41, 100, n_reads=1200, text_len=24000), **kw)
+
+
+def test_workload_shapes():
+    _cmp(synth.workload(100_000, 8_000, 100, 0.001, seed=51))
+    _cmp(synth.workload(100_000, 12_000, 150, 0.005, seed=52, n_frac=0.02))
+
+
+def test_device_generator_shape():
+    # the bench generator (torch) produces inputs the reference accepts and mostly matches
+    c = synth.scaled_config("c2", 0.001)
+    text, packed = synth.workload_device(**c, seed=5, device="cpu")
+    text, packed = text.numpy(), packed.numpy()
+    asc = synth.unpack_reads_ascii(packed, c["read_len"])
+    r = oracle.ref_map_reads(text, asc, None, c["read_len"])
+    o = oracle.oracle_map_reads(text, packed, None, c["read_len"])
+    assert np.array_equal(o.pos, r.pos) and np.array_equal(o.mm, r.mm) and np.array_equal(o.rc, r.rc)
+    assert r.matched > 0.95 * len(r.pos)
