@@ -1,0 +1,74 @@
+"""CPU, world_size 2, gloo: the host logic of the text-sharded path (shard_plan -> per-rank scan ->
+merge_accumulators over torch.distributed -> per-pass decision on every rank) reproduces the oracle.
+The per-rank kernels are replaced by the plain-Python model in tests/cpu_shard_model.py; the merge, the
+shard plan and the phase plan are the product's own code."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, kw, ret_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from cpu_shard_model import CpuShardMatcher
+    from pgrc_b200 import matcher, synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inp = synth.adversarial(case["seed"], case["L"], n_reads=case["n_reads"], text_len=case["text_len"])
+    m = CpuShardMatcher()
+    pg_len = inp.text.size
+    sb, sl, ob, oe = matcher.shard_plan(pg_len, rank, world)
+    m.set_text_shard(inp.text[sb:sb + sl], sb, pg_len, ob, oe)
+    m.set_reads(inp.lq_reads, inp.n_reads, inp.read_len)
+    plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), kw.get("min_chars_per_mismatch", 3), kw.get("mode", "d"),
+                                    kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
+    matcher.run_plan_sharded(m, plan, kw.get("rev_compl", True))
+    res = m.get_results()
+    np.savez(os.path.join(ret_dir, f"rank{rank}.npz"), pos=res.pos, rc=res.rc, mm=res.mm)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(pre_seed=100), dict(mode="D"), dict(seed=45, rev_compl=False)])
+def test_text_sharded_two_ranks_gloo(tmp_path, kw):
+    import oracle
+    from pgrc_b200 import synth
+    case = dict(seed=77, L=100, n_reads=240, text_len=5000)
+    mp.spawn(_worker, args=(2, _free_port(), case, kw, str(tmp_path)), nprocs=2, join=True)
+    inp = synth.adversarial(case["seed"], case["L"], n_reads=case["n_reads"], text_len=case["text_len"])
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+    assert want.matched > 20
+    for rank in range(2):
+        got = np.load(tmp_path / f"rank{rank}.npz")
+        assert np.array_equal(got["pos"], want.pos), f"rank {rank}"
+        assert np.array_equal(got["rc"], want.rc) and np.array_equal(got["mm"], want.mm)
+
+
+def test_match_plan_mirrors_reference_parameter_derivation():
+    from pgrc_b200.matcher import MatchPlan, PgmError
+    # (ReadsMatchers.cpp:699-713,749-756)
+    assert MatchPlan.derive(100, 38, 3, "d").phases == [(38, 2, 33, 0, False)]
+    assert MatchPlan.derive(150, 38, 3, "d").phases == [(38, 3, 50, 0, False)]
+    assert MatchPlan.derive(100, 38, 3, "D").phases == [(38, 2, 33, 33, False)]
+    assert MatchPlan.derive(100, 100, 3, "d").phases == [(100, 1, 0, 0, False)]
+    assert MatchPlan.derive(100, 250, 3, "d").phases == [(100, 1, 0, 0, False)]
+    assert MatchPlan.derive(100, 38, 3, "d", pre_seed=100).phases == [(100, 1, 0, 0, False), (38, 2, 33, 1, True)]
+    assert MatchPlan.derive(100, 38, 3, "d", pre_seed=50).phases == [(50, 2, 33, 0, False), (38, 2, 33, 2, True)]
+    assert MatchPlan.derive(100, 38, 3, "D", pre_seed=50).phases == [(50, 2, 33, 0, False), (38, 2, 33, 33, True)]
+    for bad in ("c", "i", "x"):
+        with pytest.raises(PgmError):
+            MatchPlan.derive(100, 38, 3, bad)
