@@ -50,6 +50,11 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=float, default=0.05, help="fraction of the workload shape timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    # kernel tuning knobs (pgm_set_tuning); defaults = the library's
+    ap.add_argument("--filter-bits", type=int, default=-1)
+    ap.add_argument("--slots-per-pattern", type=int, default=2)
+    ap.add_argument("--ctas-per-sm", type=int, default=4)
+    ap.add_argument("--l2-hints", type=int, default=1)
     return ap.parse_args()
 
 
@@ -238,6 +243,7 @@ def ours(args):
     torch.cuda.synchronize()
 
     m = matcher.GpuReadsMatcher(local, use_torch_stream=True)
+    m.set_tuning(args.filter_bits, args.slots_per_pattern, args.ctas_per_sm, bool(args.l2_hints))
     plan = matcher.MatchPlan.derive(L, MATCH_KW["seed"], MATCH_KW["min_chars_per_mismatch"], MATCH_KW["mode"])
 
     # shard (N > 1)
@@ -352,7 +358,10 @@ def ours(args):
                            "matched": res.matched if (world == 1 or args.shard == "text") else None,
                            "parallelism": "single GPU" if world == 1 else f"{args.shard}-sharded x{world}",
                            "l2": "inputs (text + reads + seed table) exceed the 126 MB L2; no flush between steps",
-                           "candidates_per_step": st["candidates"], "table_slots": st["table_slots"]},
+                           "candidates_per_step": st["candidates"], "filter_positives_per_step": st["filter_positives"],
+                           "table_slots": st["table_slots"],
+                           "tuning": {"filter_bits": args.filter_bits, "slots_per_pattern": args.slots_per_pattern,
+                                      "ctas_per_sm": args.ctas_per_sm, "l2_hints": args.l2_hints}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
         if e2e:
             line["e2e"] = e2e

@@ -61,7 +61,7 @@ typedef struct pgm_stats {
     uint64_t candidates;         /* seed hits forwarded to verification (all passes)     */
     uint64_t verified;           /* candidates whose read was actually compared          */
     uint64_t accepted;           /* verified candidates within the mismatch limit        */
-    uint64_t queue_overflows;    /* candidates verified inline because a CTA queue was full */
+    uint64_t filter_positives;   /* text windows that passed the L2-resident pre-filter (all passes) */
 } pgm_stats;
 
 /* Device pointers of the per-read accumulators of the current pass, for the cross-GPU
@@ -131,6 +131,10 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
  * rev_mode) text, table probes, XOR/popcount verification, per-read accumulators. */
 int pgm_scan_pass(pgm_ctx *ctx, int rev_mode);
 int pgm_get_accumulators(pgm_ctx *ctx, pgm_accumulators *out);
+/* The per-read keys live inside the read records in HBM: pgm_get_accumulators copies them into a
+ * contiguous array (the best_key pointer it returns); after the cross-GPU reduction
+ * pgm_put_accumulators copies the merged keys back, then pgm_resolve_pass decides. */
+int pgm_put_accumulators(pgm_ctx *ctx);
 /* pgm_resolve_pass applies the reference's accept/tie-break rule of that pass to the
  * (merged) accumulators: strict improvement, scan order, LIFO among equal-hash patterns,
  * the coordinate-only "already stored" skip of ReadsMatchers.cpp:313, minMismatches stop. */
@@ -160,7 +164,7 @@ uint64_t pgm_kernel_launches(const pgm_ctx *ctx);
  * synchronizes, adds up the event durations per kernel since the last call and resets them.
  * launches[] counts the launches behind each sum. */
 enum { PGM_K_PACK_TEXT = 0, PGM_K_RC_TEXT, PGM_K_UNPACK_READS, PGM_K_INIT_STATE, PGM_K_BUILD_TABLE,
-       PGM_K_SCAN, PGM_K_RESOLVE, PGM_K_FINALIZE, PGM_K_COUNT };
+       PGM_K_SCAN, PGM_K_RESOLVE, PGM_K_FINALIZE, PGM_K_ACCUM, PGM_K_COUNT };
 typedef struct pgm_timings {
     double ms[PGM_K_COUNT];
     uint64_t launches[PGM_K_COUNT];
@@ -168,8 +172,9 @@ typedef struct pgm_timings {
 int pgm_set_profiling(pgm_ctx *ctx, int on);
 int pgm_get_timings(pgm_ctx *ctx, pgm_timings *out);
 /* Tuning knobs; call before pgm_match_begin.  filter_log2_bits = 0 disables the L2-resident
- * pre-filter; slots_per_pattern sets the table size (>= 2). */
-int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm);
+ * pre-filter (< 0 = auto); slots_per_pattern sets the table size (>= 2); l2_hints = 1 loads the
+ * filter with an L2 evict_last policy and table buckets / read records with evict_first. */
+int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm, int l2_hints);
 
 #ifdef __cplusplus
 }

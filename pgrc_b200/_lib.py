@@ -21,17 +21,17 @@ STATUS_NAMES = {0: "PGM_OK", -1: "PGM_ERR_INVALID_ARG", -2: "PGM_ERR_NO_DEVICE",
 # every symbol include/pgrc_gpu_matcher.h declares
 EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pgm_set_stream", "pgm_synchronize",
            "pgm_set_text", "pgm_set_text_shard", "pgm_shard_plan", "pgm_set_reads", "pgm_match_begin",
-           "pgm_scan_pass", "pgm_get_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_map_reads",
+           "pgm_scan_pass", "pgm_get_accumulators", "pgm_put_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_map_reads",
            "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings"]
 
-KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize"]
+KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators"]
 
 
 class PgmStats(ctypes.Structure):
     _fields_ = [("matched", ctypes.c_uint64), ("per_mm", ctypes.c_uint64 * 256),
                 ("patterns_inserted", ctypes.c_uint64), ("table_slots", ctypes.c_uint64),
                 ("candidates", ctypes.c_uint64), ("verified", ctypes.c_uint64),
-                ("accepted", ctypes.c_uint64), ("queue_overflows", ctypes.c_uint64)]
+                ("accepted", ctypes.c_uint64), ("filter_positives", ctypes.c_uint64)]
 
 
 class PgmTimings(ctypes.Structure):
@@ -76,13 +76,14 @@ def load() -> ctypes.CDLL:
     lib.pgm_match_begin.restype = ci; lib.pgm_match_begin.argtypes = [vp, u32, u32, u32, u32, ci]
     lib.pgm_scan_pass.restype = ci; lib.pgm_scan_pass.argtypes = [vp, ci]
     lib.pgm_get_accumulators.restype = ci; lib.pgm_get_accumulators.argtypes = [vp, ctypes.POINTER(PgmAccumulators)]
+    lib.pgm_put_accumulators.restype = ci; lib.pgm_put_accumulators.argtypes = [vp]
     lib.pgm_resolve_pass.restype = ci; lib.pgm_resolve_pass.argtypes = [vp, ci]
     lib.pgm_get_results.restype = ci; lib.pgm_get_results.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PgmStats)]
     lib.pgm_map_reads.restype = ci
     lib.pgm_map_reads.argtypes = [vp, u32, u32, u32, u32, ctypes.c_char, ctypes.c_char, ci, vp, vp, vp,
                                   ctypes.POINTER(PgmStats)]
     lib.pgm_kernel_launches.restype = u64; lib.pgm_kernel_launches.argtypes = [vp]
-    lib.pgm_set_tuning.restype = ci; lib.pgm_set_tuning.argtypes = [vp, ci, ci, ci]
+    lib.pgm_set_tuning.restype = ci; lib.pgm_set_tuning.argtypes = [vp, ci, ci, ci, ci]
     lib.pgm_set_profiling.restype = ci; lib.pgm_set_profiling.argtypes = [vp, ci]
     lib.pgm_get_timings.restype = ci; lib.pgm_get_timings.argtypes = [vp, ctypes.POINTER(PgmTimings)]
     _lib = lib

@@ -41,26 +41,30 @@ struct pgm_ctx {
 
     // tuning
     int filter_log2_bits = -1; // -1 = auto
-    int slots_per_pattern = 3;
+    int slots_per_pattern = 2;
     int ctas_per_sm = 4;
+    int l2_hints = 1;
 
     // text
     DevBuf f_lo, f_hi, r_lo, r_hi, ascii_stage;
     uint64_t pg_len = 0, slice_begin = 0, slice_len = 0, own_begin = 0, own_end = 0;
     bool has_text = false;
 
-    // reads
-    DevBuf packed_stage, lq_planes, n_planes;
-    uint32_t n_lq = 0, n_n = 0, read_len = 0, W = 0, lq_stride = 0, n_stride = 0;
+    // reads: one record per read (header {state, key} + bit planes), see pgm_kernels.cuh
+    DevBuf packed_stage, lq_recs, n_recs;
+    uint32_t n_lq = 0, n_n = 0, read_len = 0, W = 0, lq_stride16 = 0, n_stride16 = 0;
     bool has_reads = false;
+    bool state_fresh = false;   // record headers are {unmatched, no key} (just unpacked)
+    bool aux_clean = false;     // first_order / same_mask / same_mm hold their neutral values
 
-    // per read
-    DevBuf state, best_key, first_order, same_mask, same_mm, touched;
+    // per read (outside the records: rarely touched)
+    DevBuf first_order, same_mask, same_mm, touched, keys;
 
     // table
-    DevBuf slots, next, filter;
+    DevBuf buckets, next, filter;
     uint64_t n_slots = 0;
-    int filter_word_bits = 0;
+    uint32_t n_buckets = 0;
+    uint32_t filter_words = 0;  // 0 = no filter
 
     // phase
     uint32_t seed_len = 0, parts = 0, max_mm = 0, min_mm = 0;
@@ -143,8 +147,6 @@ size_t plane_bytes(uint64_t slice_len) { return (PGM_PAD_WORDS + plane_words(sli
 
 pgm::PerRead per_read(pgm_ctx *c) {
     pgm::PerRead pr;
-    pr.state = c->state.as<unsigned long long>();
-    pr.best_key = c->best_key.as<long long>();
     pr.first_other_order = c->first_order.as<long long>();
     pr.same_pos_mask = c->same_mask.as<int>();
     pr.same_pos_mm = c->same_mm.as<uint8_t>();
@@ -154,25 +156,36 @@ pgm::PerRead per_read(pgm_ctx *c) {
 
 pgm::ReadsView reads_view(pgm_ctx *c) {
     pgm::ReadsView rv;
-    rv.lq_planes = c->lq_planes.as<uint32_t>();
-    rv.n_planes = c->n_planes.as<uint32_t>();
+    rv.lq = c->lq_recs.as<uint4>();
+    rv.nn = c->n_recs.as<uint4>();
     rv.n_lq = c->n_lq; rv.n_n = c->n_n;
-    rv.lq_stride = c->lq_stride; rv.n_stride = c->n_stride;
+    rv.lq_stride16 = c->lq_stride16; rv.n_stride16 = c->n_stride16;
     rv.read_len = c->read_len; rv.W = c->W;
     return rv;
 }
 
 pgm::TableView table_view(pgm_ctx *c) {
     pgm::TableView tv;
-    tv.slots = c->slots.as<unsigned long long>();
+    tv.buckets = c->buckets.as<uint4>();
     tv.next = c->next.as<uint32_t>();
-    tv.filter = c->filter_word_bits ? c->filter.as<uint32_t>() : nullptr;
-    tv.bucket_mask = (uint32_t)(c->n_slots / 4 - 1);
-    tv.filter_word_bits = c->filter_word_bits;
+    tv.filter = c->filter_words ? c->filter.as<uint32_t>() : nullptr;
+    tv.n_buckets = c->n_buckets;
+    tv.filter_mask = c->filter_words ? c->filter_words - 1 : 0;
     return tv;
 }
 
 int ceil_log2(uint64_t v) { int b = 0; while ((1ull << b) < v) b++; return b; }
+
+uint32_t next_prime(uint64_t v) {
+    if (v < 3) return 2;
+    if (!(v & 1)) v++;
+    for (;; v += 2) {
+        bool prime = true;
+        for (uint64_t d = 3; d * d <= v; d += 2)
+            if (v % d == 0) { prime = false; break; }
+        if (prime) return (uint32_t)v;
+    }
+}
 
 template <int NCH>
 void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s) {
@@ -234,8 +247,8 @@ void pgm_destroy(pgm_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->f_lo, &ctx->f_hi, &ctx->r_lo, &ctx->r_hi, &ctx->ascii_stage, &ctx->packed_stage,
-                      &ctx->lq_planes, &ctx->n_planes, &ctx->state, &ctx->best_key, &ctx->first_order,
-                      &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->slots, &ctx->next, &ctx->filter,
+                      &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
+                      &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
     for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -261,7 +274,7 @@ int pgm_synchronize(pgm_ctx *ctx) {
     return PGM_OK;
 }
 
-int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm) {
+int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm, int l2_hints) {
     if (!ctx) return PGM_ERR_INVALID_ARG;
     if (filter_log2_bits > 32 || (filter_log2_bits > 0 && filter_log2_bits < 10))
         return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_tuning: filter_log2_bits must be 0 (off), <0 (auto) or 10..32");
@@ -270,6 +283,7 @@ int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, in
     ctx->filter_log2_bits = filter_log2_bits;
     ctx->slots_per_pattern = slots_per_pattern;
     ctx->ctas_per_sm = ctas_per_sm;
+    ctx->l2_hints = l2_hints ? 1 : 0;
     return PGM_OK;
 }
 
@@ -370,39 +384,45 @@ int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq, const u
     if ((uint64_t)n_lq + n_n >= 0xFFFFFFFFull) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_set_reads: too many reads");
     CU(cudaSetDevice(ctx->device));
     const uint32_t W = (read_len + 31) / 32;
-    const uint32_t lq_stride = (2 * W + 3) & ~3u, n_stride = (3 * W + 3) & ~3u;
+    // record = header uint4 + planes, rounded up to whole 64-byte requests
+    const uint32_t lq_stride16 = (1 + (W + 1) / 2 + 3) & ~3u, n_stride16 = (1 + W + 3) & ~3u;
     const uint32_t lq_plen = (read_len + 3) / 4, n_plen = (read_len + 2) / 3;
     int rc;
-    if ((rc = ensure(ctx, ctx->lq_planes, (size_t)std::max<uint32_t>(n_lq, 1) * lq_stride * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->n_planes, (size_t)std::max<uint32_t>(n_n, 1) * n_stride * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->lq_recs, (size_t)std::max<uint32_t>(n_lq, 1) * lq_stride16 * 16))) return rc;
+    if ((rc = ensure(ctx, ctx->n_recs, (size_t)std::max<uint32_t>(n_n, 1) * n_stride16 * 16))) return rc;
     const uint32_t n = n_lq + n_n;
-    if ((rc = ensure(ctx, ctx->state, (size_t)std::max<uint32_t>(n, 1) * 8)) || (rc = ensure(ctx, ctx->best_key, (size_t)std::max<uint32_t>(n, 1) * 8)) ||
-        (rc = ensure(ctx, ctx->first_order, (size_t)std::max<uint32_t>(n, 1) * 8)) || (rc = ensure(ctx, ctx->same_mask, (size_t)std::max<uint32_t>(n, 1) * 4)) ||
-        (rc = ensure(ctx, ctx->same_mm, std::max<uint32_t>(n, 1))) || (rc = ensure(ctx, ctx->out_pos, (size_t)std::max<uint32_t>(n, 1) * 8)) ||
-        (rc = ensure(ctx, ctx->out_rc, std::max<uint32_t>(n, 1))) || (rc = ensure(ctx, ctx->out_mm, std::max<uint32_t>(n, 1)))) return rc;
-    struct Part { const uint8_t *src; uint32_t cnt, plen, stride; int with_n; uint32_t *dst; };
-    Part partsv[2] = {{lq_packed, n_lq, lq_plen, lq_stride, 0, ctx->lq_planes.as<uint32_t>()},
-                      {n_packed, n_n, n_plen, n_stride, 1, ctx->n_planes.as<uint32_t>()}};
-    for (const Part &pt : partsv) {
+    const size_t n1 = std::max<uint32_t>(n, 1);
+    if (ctx->first_order.cap < n1 * 8 || ctx->same_mask.cap < n1 * 4 || ctx->same_mm.cap < n1) ctx->aux_clean = false;
+    if ((rc = ensure(ctx, ctx->first_order, n1 * 8)) || (rc = ensure(ctx, ctx->same_mask, n1 * 4)) ||
+        (rc = ensure(ctx, ctx->same_mm, n1)) || (rc = ensure(ctx, ctx->out_pos, n1 * 8)) ||
+        (rc = ensure(ctx, ctx->out_rc, n1)) || (rc = ensure(ctx, ctx->out_mm, n1))) return rc;
+    struct Part { const uint8_t *src; uint32_t cnt, plen, stride16; int with_n; uint4 *dst; };
+    Part partsv[2] = {{lq_packed, n_lq, lq_plen, lq_stride16, 0, ctx->lq_recs.as<uint4>()},
+                      {n_packed, n_n, n_plen, n_stride16, 1, ctx->n_recs.as<uint4>()}};
+    // both sets share one staging buffer (LQ first, 16-byte aligned start for the N set)
+    const size_t lq_bytes = (size_t)n_lq * lq_plen, n_bytes = (size_t)n_n * n_plen;
+    const size_t n_off = (lq_bytes + 15) & ~(size_t)15;
+    const bool stage_lq = n_lq && !is_device_ptr(lq_packed), stage_n = n_n && !is_device_ptr(n_packed);
+    if (stage_lq || stage_n)
+        if ((rc = ensure(ctx, ctx->packed_stage, n_off + n_bytes + 16))) return rc;
+    for (int k = 0; k < 2; k++) {
+        const Part &pt = partsv[k];
         if (!pt.cnt) continue;
         const size_t bytes = (size_t)pt.cnt * pt.plen;
         const uint8_t *src = pt.src;
-        if (!is_device_ptr(src)) {
-            // staged after any kernel that still reads the staging buffer (same stream)
-            if ((rc = ensure(ctx, ctx->packed_stage, bytes))) return rc;
-            CU(cudaMemcpyAsync(ctx->packed_stage.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-            src = ctx->packed_stage.as<uint8_t>();
+        if (k == 0 ? stage_lq : stage_n) {
+            uint8_t *st = ctx->packed_stage.as<uint8_t>() + (k == 0 ? 0 : n_off);
+            CU(cudaMemcpyAsync(st, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            src = st;
         }
-        KLAUNCH(PGM_K_UNPACK_READS, "unpack_reads_kernel", pgm::unpack_reads_kernel<<<grid_for(pt.cnt, 128), 128, 0, ctx->stream>>>(src, pt.cnt, read_len, pt.plen, pt.with_n, pt.dst, pt.stride, W));
-        if (src == ctx->packed_stage.as<uint8_t>() && pt.with_n == 0 && n_n) {
-            // the N set reuses the staging buffer: a second ensure() may reallocate it while the
-            // LQ unpack is still running, so wait for it
-            CU(cudaStreamSynchronize(ctx->stream));
-        }
+        const unsigned int threads = 128;
+        KLAUNCH(PGM_K_UNPACK_READS, "unpack_reads_kernel", pgm::unpack_reads_kernel<<<grid_for(pt.cnt, threads), threads, threads * pt.plen, ctx->stream>>>(
+            src, pt.cnt, read_len, pt.plen, pt.with_n, pt.dst, pt.stride16, W));
     }
     ctx->n_lq = n_lq; ctx->n_n = n_n; ctx->read_len = read_len; ctx->W = W;
-    ctx->lq_stride = lq_stride; ctx->n_stride = n_stride;
+    ctx->lq_stride16 = lq_stride16; ctx->n_stride16 = n_stride16;
     ctx->has_reads = true;
+    ctx->state_fresh = true;
     ctx->phase_active = false;
     return PGM_OK;
 }
@@ -417,35 +437,39 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     if (n_patterns >= 0xFFFFFFFFull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin: pattern index exceeds 32 bits (reference limit, HashMatcher.cpp:39)");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->n_reads();
-    // table geometry
-    uint64_t want = std::max<uint64_t>(4096, n_patterns * (uint64_t)ctx->slots_per_pattern);
-    uint64_t n_slots = 1ull << ceil_log2(want);
-    if (n_slots / 4 > 0x80000000ull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin: table too large");
+    // table geometry: a prime number of 8-slot buckets, slots_per_pattern slots per pattern
+    const uint64_t want_slots = std::max<uint64_t>(512, n_patterns * (uint64_t)ctx->slots_per_pattern);
+    const uint64_t nb64 = next_prime((want_slots + 7) / 8);
+    if (nb64 >= 0x7FFFFFFFull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin: table too large");
     int rc;
-    if ((rc = ensure(ctx, ctx->slots, n_slots * 8)) || (rc = ensure(ctx, ctx->next, std::max<uint64_t>(n_patterns, 1) * 4))) return rc;
-    ctx->n_slots = n_slots;
-    CU(cudaMemsetAsync(ctx->slots.p, 0xFF, n_slots * 8, ctx->stream));
+    if ((rc = ensure(ctx, ctx->buckets, nb64 * 64)) || (rc = ensure(ctx, ctx->next, std::max<uint64_t>(n_patterns, 1) * 4))) return rc;
+    ctx->n_buckets = (uint32_t)nb64;
+    ctx->n_slots = nb64 * 8;
+    CU(cudaMemsetAsync(ctx->buckets.p, 0xFF, nb64 * 64, ctx->stream));
+    CU(cudaMemsetAsync(ctx->next.p, 0xFF, std::max<uint64_t>(n_patterns, 1) * 4, ctx->stream));
     int fbits = ctx->filter_log2_bits;
-    if (fbits < 0) fbits = std::min(28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 16)));
+    if (fbits < 0) fbits = std::min(28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 8)));
     if (fbits > 0) {
-        ctx->filter_word_bits = fbits - 5;
+        ctx->filter_words = 1u << (fbits - 5);
         const size_t fbytes = (size_t)1 << (fbits - 3);
         if ((rc = ensure(ctx, ctx->filter, fbytes))) return rc;
         CU(cudaMemsetAsync(ctx->filter.p, 0, fbytes, ctx->stream));
     } else {
-        ctx->filter_word_bits = 0;
+        ctx->filter_words = 0;
     }
     if (!continuation) CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
     else CU(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 4, 0, sizeof(unsigned long long), ctx->stream));
-    if (n) {
-        KLAUNCH(PGM_K_INIT_STATE, "init_state_kernel", pgm::init_state_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(per_read(ctx), n, continuation ? 0 : 1));
+    if (n && ((!continuation && !ctx->state_fresh) || !ctx->aux_clean)) {
+        KLAUNCH(PGM_K_INIT_STATE, "reset_state_kernel", pgm::reset_state_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), per_read(ctx), n, continuation ? 0 : 1));
+        CU(cudaMemsetAsync(ctx->touched.p, 0, sizeof(int), ctx->stream));
+        ctx->aux_clean = true;
     }
     ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
     if (n_patterns) {
-        const uint32_t tail = seed_len % 32 ? (1u << (seed_len % 32)) - 1u : 0xFFFFFFFFu;
-        KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid_for(n_patterns, 256), 256, 0, ctx->stream>>>(
-            reads_view(ctx), ctx->state.as<unsigned long long>(), table_view(ctx), seed_len, parts, min_mm,
-            continuation ? 1 : 0, tail, ctx->counters.as<unsigned long long>() + 4));
+        KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid_for(n_patterns * 4, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), table_view(ctx), seed_len, parts, min_mm, continuation ? 1 : 0,
+            ctx->counters.as<unsigned long long>() + 4));
     }
     ctx->phase_active = true;
     return PGM_OK;
@@ -480,6 +504,7 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
     sp.seed_len = ctx->seed_len; sp.parts = ctx->parts; sp.max_mm = ctx->max_mm; sp.min_mm = ctx->min_mm;
     sp.tail_mask = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
     sp.rev_mode = rev_mode ? 1 : 0;
+    sp.l2_hints = ctx->l2_hints;
     sp.tab = table_view(ctx);
     sp.reads = reads_view(ctx);
     sp.pr = per_read(ctx);
@@ -488,6 +513,8 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
     CU(cudaMemsetAsync(sp.tile_counter, 0, sizeof(unsigned int), ctx->stream));
     const unsigned int grid = (unsigned int)std::min<uint64_t>(sp.n_tiles, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
     const int nch = (int)((ctx->seed_len + 31) / 32);
+    ctx->state_fresh = false;
+    ctx->aux_clean = false;
     KLAUNCH(PGM_K_SCAN, "scan_kernel", switch (nch) {
         case 1: launch_scan<1>(sp, grid, ctx->stream); break;
         case 2: launch_scan<2>(sp, grid, ctx->stream); break;
@@ -504,9 +531,29 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
 int pgm_get_accumulators(pgm_ctx *ctx, pgm_accumulators *out) {
     if (!ctx || !out) return PGM_ERR_INVALID_ARG;
     if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_get_accumulators: no reads");
-    out->best_key = ctx->best_key.p; out->first_other_order = ctx->first_order.p;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->n_reads();
+    int rc;
+    if ((rc = ensure(ctx, ctx->keys, (size_t)std::max<uint32_t>(n, 1) * 8))) return rc;
+    if (n) {
+        KLAUNCH(PGM_K_ACCUM, "export_keys_kernel", pgm::export_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), n, ctx->keys.as<long long>()));
+    }
+    out->best_key = ctx->keys.p; out->first_other_order = ctx->first_order.p;
     out->same_pos_mask = ctx->same_mask.p; out->same_pos_mm = ctx->same_mm.p;
-    out->touched = ctx->touched.p; out->n_reads = ctx->n_reads();
+    out->touched = ctx->touched.p; out->n_reads = n;
+    return PGM_OK;
+}
+
+int pgm_put_accumulators(pgm_ctx *ctx) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->has_reads || !ctx->keys.p) return fail(ctx, PGM_ERR_STATE, "pgm_put_accumulators: pgm_get_accumulators has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->n_reads();
+    if (n) {
+        KLAUNCH(PGM_K_ACCUM, "import_keys_kernel", pgm::import_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), n, ctx->keys.as<long long>()));
+    }
     return PGM_OK;
 }
 
@@ -516,8 +563,10 @@ int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode) {
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->n_reads();
     if (!n) return PGM_OK;
-    KLAUNCH(PGM_K_RESOLVE, "resolve_kernel", pgm::resolve_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(per_read(ctx), n, ctx->pg_len, ctx->read_len, ctx->seed_len,
-                                                                  ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0));
+    KLAUNCH(PGM_K_RESOLVE, "resolve_kernel", pgm::resolve_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+        reads_view(ctx), per_read(ctx), n, ctx->pg_len, ctx->seed_len, ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0));
+    CU(cudaMemsetAsync(ctx->touched.p, 0, sizeof(int), ctx->stream));
+    ctx->aux_clean = true;
     return PGM_OK;
 }
 
@@ -528,10 +577,9 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
     const uint32_t n = ctx->n_reads();
     CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
     if (n) {
-        KLAUNCH(PGM_K_FINALIZE, "finalize_kernel", pgm::finalize_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->state.as<unsigned long long>(), n,
-                                                                       ctx->out_pos.as<unsigned long long>(),
-                                                                       ctx->out_rc.as<uint8_t>(), ctx->out_mm.as<uint8_t>(),
-                                                                       ctx->hist.as<unsigned long long>()));
+        KLAUNCH(PGM_K_FINALIZE, "finalize_kernel", pgm::finalize_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), n, ctx->out_pos.as<unsigned long long>(), ctx->out_rc.as<uint8_t>(), ctx->out_mm.as<uint8_t>(),
+            ctx->hist.as<unsigned long long>()));
         if (out_pos) CU(cudaMemcpyAsync(out_pos, ctx->out_pos.p, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
         if (out_rc) CU(cudaMemcpyAsync(out_rc, ctx->out_rc.p, n, cudaMemcpyDefault, ctx->stream));
         if (out_mm) CU(cudaMemcpyAsync(out_mm, ctx->out_mm.p, n, cudaMemcpyDefault, ctx->stream));
@@ -549,7 +597,7 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
         stats->matched = (uint64_t)n - h[255];
         stats->patterns_inserted = cnt[4];
         stats->table_slots = ctx->n_slots;
-        stats->candidates = cnt[0]; stats->verified = cnt[1]; stats->accepted = cnt[2]; stats->queue_overflows = cnt[3];
+        stats->candidates = cnt[0]; stats->verified = cnt[1]; stats->accepted = cnt[2]; stats->filter_positives = cnt[3];
     }
     return PGM_OK;
 }

@@ -5,13 +5,19 @@
 //               per uint32 word, base p at bit (p & 31) of word (p >> 5); PGM_PAD_WORDS zero
 //               words in front of the origin, a zero tail behind it.  The reverse-complement
 //               strand is materialised once (rc = ~bitreverse) so both passes run one kernel.
-//   reads       per read, interleaved per 32 bases: {lo, hi} (ACGT set) or {lo, hi, nmask} (ACGNT
-//               set), W = ceil(L/32) groups, stride rounded to 16 bytes: fetched with uint4 loads.
-//   seed table  open addressing, 32-byte buckets of four 8-byte slots {head:32 | flag:1 tag:31};
-//               one slot per distinct seed key, duplicates chained through next[pattern].
+//   read record one per read, 64-byte multiples, fetched as ONE DRAM request by a lane quad:
+//               uint4 #0 = {state64, best_key64}; ACGT set: uint4 #(1+g/2) = {lo,hi} of the 32-base
+//               groups g, g+1; ACGNT set: uint4 #(1+g) = {lo, hi, nmask, 0} of group g (lo = hi = 0
+//               under an N).  state64 = mm:8 | rc:1 | pos:40 ; best_key64 = cls:8 | txtPos:40 |
+//               (parts-1-j):8 | mm:8 (MIN-mergeable accumulator of the current pass).
+//   seed table  multimap, 64-byte buckets of eight 8-byte slots {tag:31 chain:1 | pattern:32}, double
+//               hashing over a prime number of buckets.  Every pattern owns a slot of the first
+//               bucket of its probe sequence that has room (so a lookup stops at the first bucket with
+//               an empty slot); only when PGM_WALK_CAP buckets in a row are full of the same key (hot
+//               seeds: poly-A, satellites) a pattern is chained behind a slot through next[].
 //   filter      2^f-bit blocked Bloom filter (2 bits in one word), sized to stay L2-resident.
-//   per read    state64 = mm:8 | rc:1 | pos:40 ; accumulators best_key / first_other_order
-//               (int64, MIN-mergeable), same_pos_mask (int32), same_pos_mm (uint8).
+//   per read    first_other_order (int64 MIN), same_pos_mask (int32 OR), same_pos_mm (uint8): only
+//               touched when a read that already has a match meets a better candidate (rule a-R).
 //
 // Seed key.  The reference hashes a seed with CyclicHash<uint32>(n, 32)
 // (rollinghash/cyclichash.h:29-35,100-123): symbol k is rotated by (n-1-k) mod 32, so two
@@ -19,85 +25,79 @@
 // symbol with the same parity.  That equivalence is reproduced exactly by
 // XOR-folding the window's bit planes into 32-bit words: P = fold(lo), Q = fold(hi),
 // R = fold(lo & hi) determine the four parity vectors.  key = mix(P, Q, R).
+//
+// Memory-system facts the kernels are shaped by (tools/ubench.cu, profiles/ubench_r01.txt): a fully
+// divergent 4-byte gather costs one L1 wavefront per lane (285 G lookups/s chip-wide); DRAM serves
+// about 42 G random requests/s whether they carry 32 or 64 bytes, provided ONE instruction asks for
+// the whole 64 bytes (four lanes x 16 bytes); one lane issuing 4 x 16 bytes gets 18 G/s.  So every
+// random access here is a 64-byte item fetched by a lane quad.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define PGM_TILE_WORDS 256                 // text words per tile == threads per scan CTA
-#define PGM_TILE_POS (PGM_TILE_WORDS * 32) // 8192 text positions per tile
+#define PGM_TILE_WORDS 128                 // text words per tile
+#define PGM_TILE_POS (PGM_TILE_WORDS * 32) // 4096 text positions per tile
 #define PGM_HALO_L 12                      // words staged left of a tile  (alignments reach back (parts-1)*n <= 255 bases)
 #define PGM_HALO_R 20                      // words staged right of a tile (window + read tail <= 255 + 255 bases)
 #define PGM_BUF_WORDS (PGM_HALO_L + PGM_TILE_WORDS + PGM_HALO_R)
 #define PGM_PAD_WORDS 64                   // zero words in front of every plane
 #define PGM_TAIL_WORDS (PGM_TILE_WORDS + 64)
-#define PGM_QCAP 2048                      // per-CTA candidate queue entries
-#define PGM_SCAN_THREADS PGM_TILE_WORDS
+#define PGM_SCAN_THREADS 256
+#define PGM_SCAN_WARPS (PGM_SCAN_THREADS / 32)
+#define PGM_WORDS_PER_WARP (PGM_TILE_WORDS / PGM_SCAN_WARPS)
+#define PGM_G 2                            // 64-byte requests in flight per lane quad
+#define PGM_WQ_CAP 384                     // per-warp candidate queue entries
+#define PGM_WQ_ROUND (64 * PGM_G)          // most entries one probe round can add (8 quads x 8 slots x G)
+#define PGM_WALK_CAP 4                     // full buckets walked before a duplicate key is chained
 
 #define PGM_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define PGM_NIL 0xFFFFFFFFu
 #define PGM_KEY_INF 0x7FFFFFFFFFFFFFFFll
 #define PGM_POS_MASK 0xFFFFFFFFFFull       // 40-bit positions
 #define PGM_STATE_UNMATCHED ((255ull << 56) | PGM_POS_MASK)
+#define PGM_FULL 0xFFFFFFFFu
 
 namespace pgm {
 
 // ------------------------------------------------------------------------------------------ hashing
-__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
-
-__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
-    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
-    return h;
+// 96-bit canonical seed form -> 64 well-mixed bits (splitmix64 finaliser).
+__host__ __device__ __forceinline__ uint64_t seed_hash64(uint32_t P, uint32_t Q, uint32_t R) {
+    uint64_t v = (((uint64_t)Q << 32) | P) ^ ((uint64_t)R * 0x9E3779B97F4A7C15ull);
+    v ^= v >> 30; v *= 0xBF58476D1CE4E5B9ull;
+    v ^= v >> 27; v *= 0x94D049BB133111EBull;
+    v ^= v >> 31;
+    return v;
 }
-
-// 96-bit canonical seed form -> two independent 32-bit hashes (murmur3-style, shared scrambles).
-__host__ __device__ __forceinline__ void seed_hash(uint32_t P, uint32_t Q, uint32_t R, uint32_t &h1, uint32_t &h2) {
-    const uint32_t k1 = rotl32(P * 0xcc9e2d51u, 15) * 0x1b873593u;
-    const uint32_t k2 = rotl32(Q * 0xcc9e2d51u, 15) * 0x1b873593u;
-    const uint32_t k3 = rotl32(R * 0xcc9e2d51u, 15) * 0x1b873593u;
-    uint32_t a = 0x9747b28cu, b = 0x3c6ef372u;
-    a ^= k1; a = rotl32(a, 13) * 5u + 0xe6546b64u;  b ^= k2; b = rotl32(b, 13) * 5u + 0xe6546b64u;
-    a ^= k2; a = rotl32(a, 13) * 5u + 0xe6546b64u;  b ^= k3; b = rotl32(b, 13) * 5u + 0xe6546b64u;
-    a ^= k3; a = rotl32(a, 13) * 5u + 0xe6546b64u;  b ^= k1; b = rotl32(b, 13) * 5u + 0xe6546b64u;
-    h1 = fmix32(a ^ 12u);
-    h2 = fmix32(b ^ 12u);
-}
-
 __host__ __device__ __forceinline__ uint32_t seed_tag(uint32_t h2) {
-    uint32_t t = h2 & 0x7FFFFFFFu;
-    return t == 0x7FFFFFFFu ? 0x7FFFFFFEu : t; // 0x7FFFFFFF is what an empty slot shows
+    const uint32_t t = h2 & 0x7FFFFFFFu;
+    return t == 0x7FFFFFFFu ? 0x7FFFFFFEu : t;   // 0x7FFFFFFF is what an empty slot shows
 }
-
-__host__ __device__ __forceinline__ uint32_t filter_word(uint32_t h1, uint32_t h2, int word_bits) {
-    return ((h1 ^ rotl32(h2, 15)) * 0x9E3779B1u) >> (32 - word_bits);
-}
-__host__ __device__ __forceinline__ uint32_t filter_mask(uint32_t h1, uint32_t h2) {
-    return (1u << (h1 >> 27)) | (1u << (h2 >> 27));
+__host__ __device__ __forceinline__ uint32_t filter_bits(uint32_t h2) {
+    return (1u << (h2 >> 27)) | (1u << ((h2 >> 22) & 31u));
 }
 
 // ------------------------------------------------------------------------------------------ parameters
 struct TableView {
-    unsigned long long *slots;  // 4 slots per bucket
-    uint32_t *next;             // chain of patterns sharing a key
+    uint4 *buckets;             // 4 uint4 = 8 slots per bucket; slot = {pattern, chain:1 | tag:31}
+    uint32_t *next;             // chains of hot keys
     uint32_t *filter;           // may be null
-    uint32_t bucket_mask;
-    int filter_word_bits;       // log2(#filter words); 0 = no filter
+    uint32_t n_buckets;         // prime
+    uint32_t filter_mask;       // #filter words - 1
 };
 
 struct ReadsView {
-    const uint32_t *lq_planes;  // n_lq * lq_stride words
-    const uint32_t *n_planes;   // n_n * n_stride words
+    uint4 *lq;                  // n_lq records of lq_stride16 uint4
+    uint4 *nn;                  // n_n records of n_stride16 uint4
     uint32_t n_lq, n_n;
-    uint32_t lq_stride, n_stride; // words per read
+    uint32_t lq_stride16, n_stride16;
     uint32_t read_len, W;
 };
 
 struct PerRead {
-    unsigned long long *state;      // mm:8 | rc:1 | pos:40
-    long long *best_key;            // cls:8 | txtPos:40 | (parts-1-j):8 | mm:8   (events with rep != stored pos)
-    long long *first_other_order;   // txtPos:40 | (parts-1-j):8                 (earliest such event)
+    long long *first_other_order;   // txtPos:40 | (parts-1-j):8  (earliest accepted event reporting a position != stored)
     int *same_pos_mask;             // bit j: seed j hit the alignment that reports the stored pos
     uint8_t *same_pos_mm;           // its mismatch count
-    int *touched;
+    int *touched;                   // set when any of the three above was written in this pass
 };
 
 struct ScanParams {
@@ -110,11 +110,12 @@ struct ScanParams {
     uint32_t seed_len, parts, max_mm, min_mm;
     uint32_t tail_mask;             // valid bits of the last 32-base chunk of a seed
     int rev_mode;
+    int l2_hints;                   // 1: filter loads evict_last, bucket/record loads evict_first
     TableView tab;
     ReadsView reads;
     PerRead pr;
     unsigned int *tile_counter;
-    unsigned long long *counters;   // [0] candidates [1] verified [2] accepted [3] queue overflows
+    unsigned long long *counters;   // [0] candidates [1] verified [2] accepted [3] filter positives
 };
 
 // ------------------------------------------------------------------------------------------ small helpers
@@ -143,12 +144,48 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// 32 bits starting at bit position `bit` of a plane whose word k lives at w[k * stride]
-__device__ __forceinline__ uint32_t extract32(const uint32_t *w, uint32_t nwords, uint32_t stride, uint32_t bit) {
-    const uint32_t k = bit >> 5;
-    const uint32_t a = k < nwords ? w[k * stride] : 0u;
-    const uint32_t b = k + 1 < nwords ? w[(k + 1) * stride] : 0u;
-    return __funnelshift_r(a, b, bit & 31);
+// L2 eviction policies (createpolicy): the filter is the one structure worth keeping in L2; table buckets and
+// read records are one-shot random traffic.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ld_u32_hint(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_u4_hint(const uint4 *p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, uint32_t r) { return __funnelshift_r(x, x, r); }
+
+__device__ __forceinline__ uint32_t quad_xor(uint32_t v) {
+    v ^= __shfl_xor_sync(PGM_FULL, v, 1);
+    v ^= __shfl_xor_sync(PGM_FULL, v, 2);
+    return v;
+}
+__device__ __forceinline__ int quad_sum(int v) {
+    v += __shfl_xor_sync(PGM_FULL, v, 1);
+    v += __shfl_xor_sync(PGM_FULL, v, 2);
+    return v;
+}
+
+// record of global read r: pointer, stride (uint4), ACGNT?
+__device__ __forceinline__ uint4 *record_of(const ReadsView &rv, uint32_t r, uint32_t &stride16, bool &is_n) {
+    is_n = r >= rv.n_lq;
+    stride16 = is_n ? rv.n_stride16 : rv.lq_stride16;
+    return is_n ? rv.nn + (size_t)(r - rv.n_lq) * rv.n_stride16 : rv.lq + (size_t)r * rv.lq_stride16;
 }
 
 // ------------------------------------------------------------------------------------------ text packing
@@ -226,386 +263,532 @@ __global__ void rc_text_kernel(const uint32_t *__restrict__ flo, const uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------ reads
-// Packed reads (reference layout, SymbolsPackingFacility.cpp:147-185) -> interleaved bit planes:
-// ACGT set: word 2i = lo bits of bases 32i..32i+31, word 2i+1 = hi bits; ACGNT set: words 3i, 3i+1,
-// 3i+2 = lo, hi, N mask (lo = hi = 0 under an N).  One thread per read.
+// Packed reads (reference layout, SymbolsPackingFacility.cpp:147-185) -> read records (layout above) with a
+// fresh header {unmatched, no key}.  A block stages its reads' packed bytes in shared memory with
+// coalesced loads; then one thread builds one record.
 __global__ void unpack_reads_kernel(const uint8_t *__restrict__ packed, uint32_t n_reads, uint32_t read_len,
-                                    uint32_t packed_len, int with_n, uint32_t *__restrict__ planes, uint32_t stride,
+                                    uint32_t packed_len, int with_n, uint4 *__restrict__ recs, uint32_t stride16,
                                     uint32_t W) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const uint8_t *src = packed + (size_t)r * packed_len;
-    uint32_t *dst = planes + (size_t)r * stride;
-    uint32_t lo = 0, hi = 0, nm = 0, wi = 0, bitpos = 0;
-    if (!with_n) {
-        for (uint32_t b = 0; b < packed_len; b++) {
-            const uint32_t v = src[b];
-            // bases 4b..4b+3, first base in the two most significant bits; the tail of the last byte is 'A' = 0
-            const uint32_t l4 = ((v >> 6) & 1) | (((v >> 4) & 1) << 1) | (((v >> 2) & 1) << 2) | ((v & 1) << 3);
-            const uint32_t h4 = ((v >> 7) & 1) | (((v >> 5) & 1) << 1) | (((v >> 3) & 1) << 2) | (((v >> 1) & 1) << 3);
-            lo |= l4 << bitpos; hi |= h4 << bitpos;
-            bitpos += 4;
-            if (bitpos == 32) { dst[2 * wi] = lo; dst[2 * wi + 1] = hi; wi++; lo = hi = 0; bitpos = 0; }
+    extern __shared__ __align__(16) uint8_t sbuf[];
+    const uint32_t r0 = blockIdx.x * blockDim.x;
+    const uint32_t nb = min(blockDim.x, n_reads - r0);
+    const size_t g0 = (size_t)r0 * packed_len;
+    const uint32_t bytes = nb * packed_len;
+    {   // head bytes up to 16-byte alignment, 16-byte body, tail bytes
+        const uint8_t *src = packed + g0;
+        const uint32_t head = min(bytes, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15));
+        const uint32_t body = (bytes - head) & ~15u;
+        for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) sbuf[i] = src[i];
+        for (uint32_t i = threadIdx.x * 16; i < body; i += blockDim.x * 16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + head + i));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) sbuf[head + i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
         }
-        if (bitpos && wi < W) { dst[2 * wi] = lo; dst[2 * wi + 1] = hi; wi++; }
-        for (uint32_t k = 2 * wi; k < stride; k++) dst[k] = 0;
+        for (uint32_t i = head + body + threadIdx.x; i < bytes; i += blockDim.x) sbuf[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x >= nb) return;
+    const uint8_t *src = sbuf + threadIdx.x * packed_len;
+    uint4 *dst = recs + (size_t)(r0 + threadIdx.x) * stride16;
+    dst[0] = make_uint4(0xFFFFFFFFu, 0xFF0000FFu, 0xFFFFFFFFu, 0x7FFFFFFFu);   // PGM_STATE_UNMATCHED, PGM_KEY_INF
+    if (!with_n) {
+        // bases 4b..4b+3 of byte b, first base in the two most significant bits; the tail of the last byte is 'A' = 0
+        for (uint32_t u = 1; u < stride16; u++) {
+            uint32_t w4[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint32_t g = 2 * (u - 1) + half;
+                if (g < W) {
+                    uint32_t lo = 0, hi = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const uint32_t bi = g * 8 + b;
+                        const uint32_t v = bi < packed_len ? src[bi] : 0u;
+                        const uint32_t l4 = ((v >> 6) & 1) | (((v >> 4) & 1) << 1) | (((v >> 2) & 1) << 2) | ((v & 1) << 3);
+                        const uint32_t h4 = ((v >> 7) & 1) | (((v >> 5) & 1) << 1) | (((v >> 3) & 1) << 2) | (((v >> 1) & 1) << 3);
+                        lo |= l4 << (4 * b); hi |= h4 << (4 * b);
+                    }
+                    const uint32_t rem = read_len - 32 * g;
+                    if (rem < 32) { lo &= (1u << rem) - 1u; hi &= (1u << rem) - 1u; }
+                    w4[2 * half] = lo; w4[2 * half + 1] = hi;
+                }
+            }
+            dst[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
     } else {
-        uint32_t p = 0;
+        uint32_t lo = 0, hi = 0, nm = 0, g = 0, bitpos = 0, p = 0;
         for (uint32_t b = 0; b < packed_len; b++) {
             const uint32_t v = src[b];
             const uint32_t s[3] = {v / 25u, (v / 5u) % 5u, v % 5u};
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
+            for (int k = 0; k < 3; k++) {
                 if (p < read_len) {
-                    const uint32_t sym = s[j];
+                    const uint32_t sym = s[k];
                     const uint32_t isn = sym == 3u ? 1u : 0u;
                     const uint32_t code = sym == 4u ? 3u : (isn ? 0u : sym);
                     lo |= (code & 1u) << bitpos; hi |= (code >> 1) << bitpos; nm |= isn << bitpos;
                     p++; bitpos++;
-                    if (bitpos == 32) {
-                        dst[3 * wi] = lo; dst[3 * wi + 1] = hi; dst[3 * wi + 2] = nm;
-                        wi++; lo = hi = nm = 0; bitpos = 0;
-                    }
+                    if (bitpos == 32) { dst[1 + g] = make_uint4(lo, hi, nm, 0); g++; lo = hi = nm = 0; bitpos = 0; }
                 }
             }
         }
-        if (bitpos && wi < W) { dst[3 * wi] = lo; dst[3 * wi + 1] = hi; dst[3 * wi + 2] = nm; wi++; }
-        for (uint32_t k = 3 * wi; k < stride; k++) dst[k] = 0;
+        if (bitpos) { dst[1 + g] = make_uint4(lo, hi, nm, 0); g++; }
+        for (uint32_t u = 1 + g; u < stride16; u++) dst[u] = make_uint4(0, 0, 0, 0);
     }
 }
 
 // ------------------------------------------------------------------------------------------ per-read state
-__global__ void init_state_kernel(PerRead pr, uint32_t n_reads, int reset_state) {
+__global__ void reset_state_kernel(ReadsView reads, PerRead pr, uint32_t n_reads, int reset_state) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
-    if (reset_state) pr.state[r] = PGM_STATE_UNMATCHED;
-    pr.best_key[r] = PGM_KEY_INF;
+    uint32_t stride16; bool is_n;
+    uint4 *rec = record_of(reads, r, stride16, is_n);
+    uint4 h = rec[0];
+    if (reset_state) { h.x = 0xFFFFFFFFu; h.y = 0xFF0000FFu; }
+    h.z = 0xFFFFFFFFu; h.w = 0x7FFFFFFFu;
+    rec[0] = h;
     pr.first_other_order[r] = PGM_KEY_INF;
     pr.same_pos_mask[r] = 0;
     pr.same_pos_mm[r] = 255;
-    if (r == 0) *pr.touched = 0;
+}
+
+// ------------------------------------------------------------------------------------------ seed form of a read
+// Folded canonical form of seed j (read bases [j*n, (j+1)*n)) from the quad-distributed record: lane q of the quad
+// holds uint4 #q (#q+4, ... are fetched here when the record is longer than 64 bytes).  A base at read position x
+// lands on bit (x - j*n) mod 32, i.e. each 32-base group contributes rotr(group & range, (j*n) mod 32).
+__device__ __forceinline__ void fold_groups(uint32_t u, bool is_n, uint4 v, uint32_t W, uint32_t b0, uint32_t b1,
+                                            uint32_t &P, uint32_t &Q, uint32_t &R, uint32_t &FN) {
+    if (u == 0) return;
+    const uint32_t s = b0 & 31u;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        if (is_n && half) break;
+        const uint32_t g = is_n ? u - 1 : 2 * (u - 1) + half;
+        if (g >= W) break;
+        const int lo_bit = max((int)b0 - (int)(32 * g), 0), hi_bit = min((int)b1 - (int)(32 * g), 32);
+        if (hi_bit <= lo_bit) continue;
+        uint32_t m = hi_bit == 32 ? 0xFFFFFFFFu : (1u << hi_bit) - 1u;
+        m &= ~((1u << lo_bit) - 1u);
+        const uint32_t l = (half ? v.z : v.x) & m, h = (half ? v.w : v.y) & m;
+        P ^= rotr32(l, s); Q ^= rotr32(h, s); R ^= rotr32(l & h, s);
+        if (is_n) FN ^= rotr32(v.z & m, s);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ table build
-// One thread per pattern (read r, seed j): canonical key of read bases [j*n, (j+1)*n), insert into the
-// open-addressing table.  Restates addReadsSetOfPatterns (ConstantLengthPatternsOnTextHashMatcher.cpp:23-42);
-// pattern index = r * parts + j (:39).  Reads already matched with <= min_mm mismatches are left out when
-// `continuation` (the matchedReadsBitmap argument, ReadsMatchers.cpp:290-291).
-__global__ void build_table_kernel(ReadsView reads, const unsigned long long *__restrict__ state, TableView tab,
-                                   uint32_t seed_len, uint32_t parts, uint32_t min_mm, int continuation,
-                                   uint32_t tail_mask, unsigned long long *inserted) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One lane quad per pattern (read r, seed j): fetch the record (one 64-byte request), fold the seed, insert into
+// the first bucket of the probe sequence with room.  Restates addReadsSetOfPatterns
+// (ConstantLengthPatternsOnTextHashMatcher.cpp:23-42); pattern index = r * parts + j (:39).  Reads already
+// matched with <= min_mm mismatches are left out when `continuation` (the matchedReadsBitmap argument,
+// ReadsMatchers.cpp:290-291).
+__global__ void __launch_bounds__(256) build_table_kernel(ReadsView reads, TableView tab, uint32_t seed_len, uint32_t parts,
+                                                          uint32_t min_mm, int continuation, unsigned long long *inserted) {
+    const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t p = gt >> 2;
+    const uint32_t lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3u;
     const uint64_t n_patterns = (uint64_t)(reads.n_lq + reads.n_n) * parts;
     bool active = p < n_patterns;
-    uint32_t r = 0, j = 0;
+    uint32_t r = 0, j = 0, stride16 = 4;
+    bool is_n = false;
+    uint4 *rec = reads.lq;
+    uint4 v = make_uint4(0, 0, 0, 0);
     if (active) {
         r = (uint32_t)(p / parts);
         j = (uint32_t)(p - (uint64_t)r * parts);
-        if (continuation && (uint32_t)(state[r] >> 56) <= min_mm) active = false;
+        rec = record_of(reads, r, stride16, is_n);
+        v = __ldg(rec + q);
     }
+    const uint32_t st_hi = __shfl_sync(PGM_FULL, v.y, qb);
+    if (continuation && (st_hi >> 24) <= min_mm) active = false;
+    uint32_t P = 0, Q = 0, R = 0, FN = 0;
     if (active) {
-        const bool is_n = r >= reads.n_lq;
-        const uint32_t *pl = is_n ? reads.n_planes + (size_t)(r - reads.n_lq) * reads.n_stride
-                                  : reads.lq_planes + (size_t)r * reads.lq_stride;
-        const uint32_t il = is_n ? 3u : 2u; // interleave factor
-        const uint32_t W = reads.W;
-        const uint32_t nch = (seed_len + 31) >> 5;
-        uint32_t P = 0, Q = 0, R = 0, FN = 0;
-        for (uint32_t i = 0; i < nch; i++) {
-            const uint32_t bit = j * seed_len + 32 * i;
-            const uint32_t m = (i == nch - 1) ? tail_mask : 0xFFFFFFFFu;
-            const uint32_t l = extract32(pl, W, il, bit) & m;
-            const uint32_t h = extract32(pl + 1, W, il, bit) & m;
-            P ^= l; Q ^= h; R ^= (l & h);
-            if (is_n) FN ^= extract32(pl + 2, W, il, bit) & m;
+        const uint32_t b0 = j * seed_len, b1 = b0 + seed_len;
+        fold_groups(q, is_n, v, reads.W, b0, b1, P, Q, R, FN);
+        for (uint32_t u = q + 4; u < stride16; u += 4) fold_groups(u, is_n, __ldg(rec + u), reads.W, b0, b1, P, Q, R, FN);
+    }
+    P = quad_xor(P); Q = quad_xor(Q); R = quad_xor(R); FN = quad_xor(FN);
+    // a seed whose N parity is odd in some rotation class can never collide with an ACGT window
+    if (FN != 0) active = false;
+    const uint64_t hv = seed_hash64(P, Q, R);
+    const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
+    const uint32_t tag = seed_tag(h2);
+    const uint32_t pat = (uint32_t)p;
+    if (active && q == 0 && tab.filter) atomicOr(tab.filter + (h1 & tab.filter_mask), filter_bits(h2));
+    uint32_t b = __umulhi(h1, tab.n_buckets);
+    const uint32_t step = 1u + __umulhi(h2 * 0x9E3779B1u, tab.n_buckets - 1u);
+    const unsigned long long mine = ((unsigned long long)tag << 32) | pat;
+    bool pending = active;
+    uint32_t walked = 0;
+    unsigned long long *same_slot = nullptr;
+    while (__ballot_sync(PGM_FULL, pending)) {
+        uint4 s = make_uint4(0, 0, 0, 0);
+        uint4 *bp = tab.buckets + (size_t)b * 4 + q;
+        if (pending) s = __ldcg(bp);
+        const bool e0 = pending && s.y == 0xFFFFFFFFu, e1 = pending && s.w == 0xFFFFFFFFu;
+        const bool t0 = pending && (s.y & 0x7FFFFFFFu) == tag, t1 = pending && (s.w & 0x7FFFFFFFu) == tag;
+        const uint32_t qe = (__ballot_sync(PGM_FULL, e0 || e1) >> qb) & 0xFu;
+        const uint32_t qt = (__ballot_sync(PGM_FULL, t0 || t1) >> qb) & 0xFu;
+        // all shuffles are executed by the whole warp; only their results are used conditionally
+        const uint32_t ql_t = qt ? __ffs(qt) - 1 : 0u, ql_e = qe ? __ffs(qe) - 1 : 0u;
+        const uint32_t first_t = __shfl_sync(PGM_FULL, t0 ? 0u : 1u, qb + ql_t);
+        if (pending && same_slot == nullptr && qt)   // remember one slot that already holds this key
+            same_slot = reinterpret_cast<unsigned long long *>(tab.buckets + (size_t)b * 4 + ql_t) + first_t;
+        int ok = 0;
+        if (pending && qe && q == ql_e) {
+            unsigned long long *sl = reinterpret_cast<unsigned long long *>(bp) + (e0 ? 0 : 1);
+            ok = atomicCAS(sl, PGM_EMPTY64, mine) == PGM_EMPTY64;
         }
-        // a seed whose N parity is odd in some rotation class can never collide with an ACGT window
-        if (FN != 0) active = false;
-        if (active) {
-            uint32_t h1, h2;
-            seed_hash(P, Q, R, h1, h2);
-            const uint32_t tag = seed_tag(h2);
-            const uint32_t pat = (uint32_t)p;
-            tab.next[pat] = PGM_NIL;
-            uint32_t b = h1 & tab.bucket_mask, s = 0;
-            const unsigned long long mine = ((unsigned long long)tag << 32) | pat;
-            for (;;) {
-                unsigned long long *sl = tab.slots + (size_t)b * 4 + s;
-                unsigned long long old = atomicCAS(sl, PGM_EMPTY64, mine);
-                if (old == PGM_EMPTY64) break;
-                if ((uint32_t)((old >> 32) & 0x7FFFFFFFu) == tag) {
-                    // same key already present: become the head of its chain and set the chain flag
+        ok = __shfl_sync(PGM_FULL, ok, qb + ql_e);
+        bool done = false;
+        if (pending && qe) {
+            done = ok != 0;   // lost the race: look at the same bucket again
+        } else if (pending) {
+            walked++;
+            if (walked >= PGM_WALK_CAP && same_slot != nullptr) {
+                // hot key: chain this pattern behind a slot that already holds the key
+                if (q == 0) {
+                    unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(same_slot);
                     for (;;) {
-                        const unsigned long long nw = (((old >> 32) | 0x80000000ull) << 32) | pat;
                         tab.next[pat] = (uint32_t)old;
-                        const unsigned long long prev = atomicCAS(sl, old, nw);
+                        const unsigned long long nw = (((old >> 32) | 0x80000000ull) << 32) | pat;
+                        const unsigned long long prev = atomicCAS(same_slot, old, nw);
                         if (prev == old) break;
                         old = prev;
                     }
-                    break;
                 }
-                if (++s == 4) { s = 0; b = (b + 1) & tab.bucket_mask; }
+                done = true;
+            } else {
+                b += step;
+                if (b >= tab.n_buckets) b -= tab.n_buckets;
             }
-            if (tab.filter) atomicOr(tab.filter + filter_word(h1, h2, tab.filter_word_bits), filter_mask(h1, h2));
         }
+        if (done) pending = false;
     }
-    const unsigned int cnt = __popc(__ballot_sync(0xFFFFFFFFu, active));
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(inserted, (unsigned long long)cnt);
+    const unsigned int cnt = __popc(__ballot_sync(PGM_FULL, active && q == 0));
+    if (lane == 0 && cnt) atomicAdd(inserted, (unsigned long long)cnt);
 }
 
-// ------------------------------------------------------------------------------------------ verification
+// ------------------------------------------------------------------------------------------ the scan
 struct ScanShared {
-    uint32_t lo[PGM_BUF_WORDS];
-    uint32_t hi[PGM_BUF_WORDS];
-    uint2 queue[PGM_QCAP];       // {pos_in_tile | chain flag << 31, head pattern}
-    uint64_t bar;
-    unsigned int q_count;
-    unsigned int tile;
+    uint32_t lo[2][PGM_BUF_WORDS];
+    uint32_t hi[2][PGM_BUF_WORDS];
+    uint2 wq[PGM_SCAN_WARPS][PGM_WQ_CAP];   // per-warp candidate queues {pos_in_tile | chain << 31, pattern}
+    uint16_t q1[PGM_TILE_POS];              // filter-positive positions of the tile
+    uint64_t bar[2];
+    unsigned int q1_count[2], q1_cursor[2], tile[2];
 };
 
-// Hamming distance between a read (interleaved planes in registers) and the staged text at bit offset boff.
-template <int IL>
-__device__ __forceinline__ int count_mismatches(const uint32_t *rw, const ScanShared &sm, uint32_t boff, uint32_t W,
-                                                uint32_t L) {
-    const uint32_t tw = boff >> 5, ts = boff & 31;
+// canonical form + hash of the seed window starting at tile position `pos` (text staged in shared memory)
+template <int NCH>
+__device__ __forceinline__ uint64_t window_hash(const uint32_t *slo, const uint32_t *shi, uint32_t pos, uint32_t tail_mask) {
+    const uint32_t wi = pos >> 5, s = pos & 31u;
+    uint32_t P = 0, Q = 0, R = 0;
+    uint32_t la = slo[wi], ha = shi[wi];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+        const uint32_t lb = slo[wi + i + 1], hb = shi[wi + i + 1];
+        uint32_t l = __funnelshift_r(la, lb, s), h = __funnelshift_r(ha, hb, s);
+        if (i == NCH - 1) { l &= tail_mask; h &= tail_mask; }
+        P ^= l; Q ^= h; R ^= (l & h);
+        la = lb; ha = hb;
+    }
+    return seed_hash64(P, Q, R);
+}
+
+// Mismatches of this lane's share of a read record (uint4 #u) against the staged text at bit offset boff.
+__device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, const uint32_t *blo, const uint32_t *bhi,
+                                            uint32_t boff, uint32_t W, uint32_t L) {
+    if (u == 0) return 0;
+    const uint32_t tw = boff >> 5, ts = boff & 31u;
     int c = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        if ((uint32_t)i < W) {
-            const uint32_t tl = __funnelshift_r(sm.lo[tw + i], sm.lo[tw + i + 1], ts);
-            const uint32_t th = __funnelshift_r(sm.hi[tw + i], sm.hi[tw + i + 1], ts);
-            uint32_t diff = (rw[IL * i] ^ tl) | (rw[IL * i + 1] ^ th);
-            if (IL == 3) diff |= rw[IL * i + 2];   // an N never equals a text symbol
-            const uint32_t rem = L - 32 * i;
-            if (rem < 32) diff &= (1u << rem) - 1u;
-            c += __popc(diff);
-        }
+    for (int half = 0; half < 2; half++) {
+        if (is_n && half) break;
+        const uint32_t g = is_n ? u - 1 : 2 * (u - 1) + half;
+        if (g >= W) break;
+        const uint32_t tl = __funnelshift_r(blo[tw + g], blo[tw + g + 1], ts);
+        const uint32_t th = __funnelshift_r(bhi[tw + g], bhi[tw + g + 1], ts);
+        uint32_t diff = ((half ? v.z : v.x) ^ tl) | ((half ? v.w : v.y) ^ th);
+        if (is_n) diff |= v.z;                              // an N never equals a text symbol
+        const uint32_t rem = L - 32 * g;
+        if (rem < 32) diff &= (1u << rem) - 1u;
+        c += __popc(diff);
     }
     return c;
 }
 
-// Verifies one pattern hit at global text position g (this pass's coordinates).  Restates the body of
-// DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:301-331) up to the decision, which is
-// deferred to resolve_kernel so that it does not depend on scan order.
-// Returns verified | accepted << 1.
-__device__ __forceinline__ uint32_t verify_pattern(const ScanParams &p, const ScanShared &sm, int64_t tile_bit0,
-                                                   uint64_t g, uint32_t pat) {
-    const uint32_t r = pat / p.parts;
-    const uint32_t j = pat - r * p.parts;
-    const unsigned long long st = __ldg(p.pr.state + r);
-    const uint32_t c_in = (uint32_t)(st >> 56);
-    if (c_in <= p.min_mm) return 0;                                 // :304
-    const uint32_t shift = j * p.seed_len;
-    if (shift > g) return 0;                                        // :308
-    const uint64_t a = g - shift;
-    const uint32_t L = p.reads.read_len;
-    if (a + L > p.pg_len) return 0;                                 // :311
-    const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;       // :313,:326 (matchingLength == readLength)
-    const bool has_pos = c_in != 255u;
-    const bool same_pos = has_pos && ((st & PGM_POS_MASK) == rep);  // coordinate-only compare, :313
-    int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;            // :315
-    const unsigned long long order = (g << 8) | (unsigned long long)(p.parts - 1 - j);
-    if (!has_pos) {
-        // nothing stored yet: only the minimum key matters, so an event that cannot beat the current
-        // minimum need not be verified (a stale read is safe: the key only ever decreases)
-        const long long k = *(volatile long long *)(p.pr.best_key + r);
-        if (k != PGM_KEY_INF) {
-            const int kcls = (int)(k >> 56);
-            const unsigned long long korder = ((unsigned long long)k >> 8) & 0xFFFFFFFFFFFFull;
-            const int T = kcls - (order >= korder ? 1 : 0);
-            if (T < 0) return 0;
-            limit = min(limit, max(T, (int)p.min_mm));
-        }
-    }
-    if (limit < 0) return 0;
-    const uint32_t boff = (uint32_t)((int64_t)(a - p.slice_origin) - tile_bit0);
-    const uint32_t W = p.reads.W;
-    int c;
-    if (r < p.reads.n_lq) {
-        const uint4 *pl4 = reinterpret_cast<const uint4 *>(p.reads.lq_planes + (size_t)r * p.reads.lq_stride);
-        const uint32_t nvec = p.reads.lq_stride >> 2;
-        uint32_t rw[16];
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if ((uint32_t)v < nvec) q = __ldg(pl4 + v);
-            rw[4 * v] = q.x; rw[4 * v + 1] = q.y; rw[4 * v + 2] = q.z; rw[4 * v + 3] = q.w;
-        }
-        c = count_mismatches<2>(rw, sm, boff, W, L);
-    } else {
-        const uint4 *pl4 = reinterpret_cast<const uint4 *>(p.reads.n_planes + (size_t)(r - p.reads.n_lq) * p.reads.n_stride);
-        const uint32_t nvec = p.reads.n_stride >> 2;
-        uint32_t rw[24];
-#pragma unroll
-        for (int v = 0; v < 6; v++) {
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if ((uint32_t)v < nvec) q = __ldg(pl4 + v);
-            rw[4 * v] = q.x; rw[4 * v + 1] = q.y; rw[4 * v + 2] = q.z; rw[4 * v + 3] = q.w;
-        }
-        c = count_mismatches<3>(rw, sm, boff, W, L);
-    }
-    if (c > limit) return 1;
-    if (!same_pos) {
-        const unsigned long long cls = (uint32_t)c <= p.min_mm ? 0ull : (unsigned long long)c;
-        const long long key = (long long)((cls << 56) | (order << 8) | (unsigned long long)c);
-        atomicMin(p.pr.best_key + r, key);
-        if (has_pos) {
-            atomicMin(p.pr.first_other_order + r, (long long)order);
-            *p.pr.touched = 1;
-        }
-    } else {
-        atomicOr(p.pr.same_pos_mask + r, 1 << j);
-        p.pr.same_pos_mm[r] = (uint8_t)c;
-        *p.pr.touched = 1;
-    }
-    return 3;
-}
-
-// One queue entry = one table slot hit; walks the chain of patterns sharing the key.
-// Returns candidates | verified << 10 | accepted << 20 (saturating is irrelevant: summed in 64 bits by the caller).
-__device__ __noinline__ uint3 verify_entry(const ScanParams &p, const ScanShared &sm, int64_t tile_bit0,
-                                           uint64_t tile_g0, uint2 e) {
-    const uint64_t g = tile_g0 + (e.x & 0x7FFFFFFFu);
-    uint32_t pat = e.y;
-    const bool chained = (e.x >> 31) != 0;
-    uint3 cnt = make_uint3(0, 0, 0);
-    for (;;) {
-        const uint32_t v = verify_pattern(p, sm, tile_bit0, g, pat);
-        cnt.x++; cnt.y += v & 1; cnt.z += v >> 1;
-        if (!chained) break;
-        pat = __ldg(p.tab.next + pat);
-        if (pat == PGM_NIL) break;
-    }
-    return cnt;
-}
-
-// ------------------------------------------------------------------------------------------ the scan
-// Persistent CTAs pull 8192-position tiles of the 2-bit text.  Per tile: (1) one elected thread stages
-// the two planes (+halos) into shared memory with TMA bulk copies; (2) every thread owns one 32-base word
-// and derives, for its 32 window starts, the folded canonical seed form with funnel shifts, hashes it,
-// tests the L2-resident filter and probes one 32-byte table bucket; hits go to a shared queue;
-// (3) the queue is drained one candidate per thread: XOR/popcount of the read planes against the staged
-// text, then atomicMin on the read's key.  Restates iterateOver/moveNext (HashMatcher.h:42-68) +
-// executeMatching (ReadsMatchers.cpp:297-341) without their sequential order.
+// Persistent CTAs pull 4096-position tiles of the 2-bit text; the next tile's planes (+halos) are staged into the
+// other shared-memory buffer with TMA bulk copies while the current one is processed.  Per tile:
+//  A1  lane <-> text position: every warp derives, for 32 consecutive window starts at a time, the folded
+//      canonical seed form (funnel shifts of broadcast shared-memory words), hashes it and tests the L2-resident
+//      filter (one 4-byte gather per position: the L1 wavefront rate bounds this stage); positives are
+//      ballot-compacted into a shared list.
+//  A2  lane quads pull positives from the list, rehash and fetch the 64-byte table bucket as one request (16
+//      bytes per lane); tag hits are ballot-compacted into the warp's candidate queue; a bucket without an empty
+//      slot sends the quad on along its double-hashing sequence.
+//  B   when the warp's queue runs full (and at the end) its quads verify one candidate each: one 64-byte request
+//      for the read record, XOR/popcount against the staged text per lane, quad shuffle-reduce, then atomicMin on the
+//      record's key.  Restates iterateOver/moveNext (HashMatcher.h:42-68) + executeMatching
+//      (ReadsMatchers.cpp:297-341) without their sequential order; the decision is deferred to resolve_kernel.
 template <int NCH>
-__global__ void __launch_bounds__(PGM_SCAN_THREADS, 3) scan_kernel(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_constant__ ScanParams p) {
     __shared__ __align__(128) ScanShared sm;
-    const uint32_t t = threadIdx.x;
-    unsigned long long n_cand = 0, n_ver = 0, n_acc = 0, n_ovf = 0;
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u, quad = lane >> 2, q = lane & 3u, qb = lane & ~3u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned long long n_cand = 0, n_ver = 0, n_acc = 0, n_pos = 0;
+    const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    const bool hints = p.l2_hints != 0;
+
+    auto issue_tile = [&](unsigned int tile, int b) {
+        const int64_t w0 = (int64_t)p.first_word + (int64_t)tile * PGM_TILE_WORDS - PGM_HALO_L;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&sm.bar[b], 2 * PGM_BUF_WORDS * 4);
+        bulk_g2s(sm.lo[b], p.tlo + w0, PGM_BUF_WORDS * 4, &sm.bar[b]);
+        bulk_g2s(sm.hi[b], p.thi + w0, PGM_BUF_WORDS * 4, &sm.bar[b]);
+    };
     if (t == 0) {
-        mbar_init(&sm.bar, 1);
-        sm.q_count = 0;
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned int tile = atomicAdd(p.tile_counter, 1u);
+        sm.tile[0] = tile;
+        sm.q1_count[0] = 0; sm.q1_cursor[0] = 0;
+        if (tile < p.n_tiles) issue_tile(tile, 0);
     }
     __syncthreads();
-    uint32_t parity = 0;
-    const uint4 *slots4 = reinterpret_cast<const uint4 *>(p.tab.slots);
+    uint32_t parity[2] = {0, 0};
+    int buf = 0;
+    uint2 *wq = sm.wq[warp];
 
     for (;;) {
-        if (t == 0) {
-            const unsigned int tile = atomicAdd(p.tile_counter, 1u);
-            sm.tile = tile;
-            if (tile < p.n_tiles) {
-                const int64_t w0 = (int64_t)p.first_word + (int64_t)tile * PGM_TILE_WORDS - PGM_HALO_L;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&sm.bar, 2 * PGM_BUF_WORDS * 4);
-                bulk_g2s(sm.lo, p.tlo + w0, PGM_BUF_WORDS * 4, &sm.bar);
-                bulk_g2s(sm.hi, p.thi + w0, PGM_BUF_WORDS * 4, &sm.bar);
-            }
-        }
-        __syncthreads();
-        const unsigned int tile = sm.tile;
+        const unsigned int tile = sm.tile[buf];
         if (tile >= p.n_tiles) break;
-        mbar_wait(&sm.bar, parity);
-        parity ^= 1;
+        if (t == 0) {
+            const unsigned int nxt = atomicAdd(p.tile_counter, 1u);
+            sm.tile[buf ^ 1] = nxt;
+            sm.q1_count[buf ^ 1] = 0; sm.q1_cursor[buf ^ 1] = 0;
+            if (nxt < p.n_tiles) issue_tile(nxt, buf ^ 1);
+        }
+        mbar_wait(&sm.bar[buf], parity[buf]);
+        parity[buf] ^= 1;
 
         const int64_t tile_word0 = (int64_t)p.first_word + (int64_t)tile * PGM_TILE_WORDS;
         const uint64_t tile_g0 = p.slice_origin + (uint64_t)tile_word0 * 32;   // global position of the tile's first base
-        const int64_t tile_bit0 = (tile_word0 - PGM_HALO_L) * 32;              // local position of sm.lo[0] bit 0
+        const int64_t buf_bit0 = (tile_word0 - PGM_HALO_L) * 32;               // local position of buffer word 0, bit 0
+        const uint32_t *blo = sm.lo[buf], *bhi = sm.hi[buf];
+        const uint32_t *slo = blo + PGM_HALO_L, *shi = bhi + PGM_HALO_L;       // tile position 0
 
-        // ---- stage A: hash + filter + probe, 32 window starts per thread
-        const uint64_t base = tile_g0 + (uint64_t)t * 32;
-        uint32_t vmask = 0;
-        if (base + 32 > p.own_begin && base < p.own_end) {
-            vmask = 0xFFFFFFFFu;
-            if (base < p.own_begin) vmask &= 0xFFFFFFFFu << (uint32_t)(p.own_begin - base);
-            if (base + 32 > p.own_end) vmask &= 0xFFFFFFFFu >> (uint32_t)(base + 32 - p.own_end);
-        }
-        if (vmask) {
-            uint32_t wl[NCH + 1], wh[NCH + 1];
-#pragma unroll
-            for (int i = 0; i <= NCH; i++) { wl[i] = sm.lo[PGM_HALO_L + t + i]; wh[i] = sm.hi[PGM_HALO_L + t + i]; }
+        // ---- A1: hash + filter, lane <-> position
+        const int64_t vb64 = (int64_t)p.own_begin - (int64_t)tile_g0, ve64 = (int64_t)p.own_end - (int64_t)tile_g0;
+        const uint32_t vb = (uint32_t)max((int64_t)0, min(vb64, (int64_t)PGM_TILE_POS));
+        const uint32_t ve = (uint32_t)max((int64_t)0, min(ve64, (int64_t)PGM_TILE_POS));
+        {
             constexpr int U = 4;
+            const uint32_t w_first = warp * PGM_WORDS_PER_WARP;
 #pragma unroll 1
-            for (int s0 = 0; s0 < 32; s0 += U) {
-                uint32_t h1[U], h2[U], fw[U];
+            for (uint32_t it0 = 0; it0 < PGM_WORDS_PER_WARP; it0 += U) {
+                const uint32_t pos0 = (w_first + it0) * 32;
+                if (pos0 >= ve || pos0 + 32 * U <= vb) continue;
+                uint32_t fm[U], fi[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const int s = s0 + u;
-                    uint32_t P = 0, Q = 0, R = 0;
-#pragma unroll
-                    for (int i = 0; i < NCH; i++) {
-                        uint32_t l = __funnelshift_r(wl[i], wl[i + 1], s);
-                        uint32_t h = __funnelshift_r(wh[i], wh[i + 1], s);
-                        if (i == NCH - 1) { l &= p.tail_mask; h &= p.tail_mask; }
-                        P ^= l; Q ^= h; R ^= (l & h);
-                    }
-                    seed_hash(P, Q, R, h1[u], h2[u]);
+                    const uint64_t hv = window_hash<NCH>(slo, shi, pos0 + 32 * u + lane, p.tail_mask);
+                    fi[u] = (uint32_t)hv & p.tab.filter_mask;
+                    fm[u] = filter_bits((uint32_t)(hv >> 32));
                 }
+                uint32_t fw[U];
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    fw[u] = p.tab.filter ? __ldg(p.tab.filter + filter_word(h1[u], h2[u], p.tab.filter_word_bits)) : 0xFFFFFFFFu;
+                    fw[u] = !p.tab.filter ? 0xFFFFFFFFu : hints ? ld_u32_hint(p.tab.filter + fi[u], pol_keep) : __ldg(p.tab.filter + fi[u]);
+                uint32_t bal[U], tot = 0;
+                bool hit[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const int s = s0 + u;
-                    const uint32_t fm = filter_mask(h1[u], h2[u]);
-                    if (((vmask >> s) & 1u) && (fw[u] & fm) == fm) {
-                        const uint32_t tag = seed_tag(h2[u]);
-                        uint32_t b = h1[u] & p.tab.bucket_mask;
-                        for (;;) {
-                            const uint4 q0 = __ldg(slots4 + (size_t)b * 2);
-                            const uint4 q1 = __ldg(slots4 + (size_t)b * 2 + 1);
-                            const uint32_t heads[4] = {q0.x, q0.z, q1.x, q1.z};
-                            const uint32_t tags[4] = {q0.y, q0.w, q1.y, q1.w};
-                            bool empty = false;
+                    const uint32_t pos = pos0 + 32 * u + lane;
+                    hit[u] = pos >= vb && pos < ve && (fw[u] & fm[u]) == fm[u];
+                    bal[u] = __ballot_sync(PGM_FULL, hit[u]);
+                    tot += __popc(bal[u]);
+                }
+                if (tot) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.q1_count[buf], tot);
+                    base = __shfl_sync(PGM_FULL, base, 0);
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                if ((tags[k] & 0x7FFFFFFFu) == tag) {
-                                    const uint2 e = make_uint2((t * 32 + s) | (tags[k] & 0x80000000u), heads[k]);
-                                    const unsigned int qi = atomicAdd(&sm.q_count, 1u);
-                                    if (qi < PGM_QCAP) sm.queue[qi] = e;
-                                    else {
-                                        const uint3 cn = verify_entry(p, sm, tile_bit0, tile_g0, e);
-                                        n_cand += cn.x; n_ver += cn.y; n_acc += cn.z; n_ovf++;
-                                    }
-                                }
-                                empty |= tags[k] == 0xFFFFFFFFu;
-                            }
-                            if (empty) break;
-                            b = (b + 1) & p.tab.bucket_mask;
-                        }
+                    for (int u = 0; u < U; u++) {
+                        if (hit[u]) sm.q1[base + __popc(bal[u] & lt_mask)] = (uint16_t)(pos0 + 32 * u + lane);
+                        base += __popc(bal[u]);
                     }
+                    if (lane == 0) n_pos += tot;
                 }
             }
         }
         __syncthreads();
-        // ---- stage B: drain the candidate queue, one candidate per thread
-        const unsigned int total = min(sm.q_count, (unsigned int)PGM_QCAP);
-        for (unsigned int i = t; i < total; i += PGM_SCAN_THREADS) {
-            const uint3 cn = verify_entry(p, sm, tile_bit0, tile_g0, sm.queue[i]);
-            n_cand += cn.x; n_ver += cn.y; n_acc += cn.z;
+
+        // ---- A2 + B, warp-autonomous
+        const uint32_t q1n = sm.q1_count[buf];
+        uint32_t wcount = 0;
+        bool exhausted = false;
+        bool act[PGM_G];
+        uint32_t ppos[PGM_G], ptag[PGM_G], pb[PGM_G], pstep[PGM_G];
+#pragma unroll
+        for (int g = 0; g < PGM_G; g++) { act[g] = false; ppos[g] = ptag[g] = pb[g] = pstep[g] = 0; }
+        for (;;) {
+            // produce: probe rounds until the queue is nearly full or the positives are used up
+            while (wcount + PGM_WQ_ROUND <= PGM_WQ_CAP) {
+                bool any = false;
+#pragma unroll
+                for (int g = 0; g < PGM_G; g++) any |= act[g];
+                if (!__ballot_sync(PGM_FULL, any)) {
+                    if (exhausted) break;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.q1_cursor[buf], 8u * PGM_G);
+                    base = __shfl_sync(PGM_FULL, base, 0);
+                    if (base >= q1n) { exhausted = true; break; }
+#pragma unroll
+                    for (int g = 0; g < PGM_G; g++) {
+                        const uint32_t idx = base + g * 8 + quad;
+                        act[g] = idx < q1n;
+                        ppos[g] = act[g] ? sm.q1[idx] : 0u;
+                        const uint64_t hv = window_hash<NCH>(slo, shi, ppos[g], p.tail_mask);
+                        const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
+                        ptag[g] = seed_tag(h2);
+                        pb[g] = __umulhi(h1, p.tab.n_buckets);
+                        pstep[g] = 1u + __umulhi(h2 * 0x9E3779B1u, p.tab.n_buckets - 1u);
+                    }
+                }
+                uint4 s[PGM_G];
+#pragma unroll
+                for (int g = 0; g < PGM_G; g++) {
+                    s[g] = make_uint4(0, 0, 0, 0);
+                    if (act[g]) {
+                        const uint4 *bp = p.tab.buckets + (size_t)pb[g] * 4 + q;
+                        s[g] = hints ? ld_u4_hint(bp, pol_stream) : __ldg(bp);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < PGM_G; g++) {
+                    const bool m0 = act[g] && (s[g].y & 0x7FFFFFFFu) == ptag[g];
+                    const bool m1 = act[g] && (s[g].w & 0x7FFFFFFFu) == ptag[g];
+                    const bool em = act[g] && (s[g].y == 0xFFFFFFFFu || s[g].w == 0xFFFFFFFFu);
+                    const uint32_t b0 = __ballot_sync(PGM_FULL, m0), b1 = __ballot_sync(PGM_FULL, m1);
+                    const uint32_t be = __ballot_sync(PGM_FULL, em);
+                    if (b0 | b1) {
+                        uint32_t off = wcount + __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
+                        if (m0) wq[off++] = make_uint2(ppos[g] | (s[g].y & 0x80000000u), s[g].x);
+                        if (m1) wq[off] = make_uint2(ppos[g] | (s[g].w & 0x80000000u), s[g].z);
+                        wcount += __popc(b0) + __popc(b1);
+                    }
+                    if ((be >> qb) & 0xFu) act[g] = false;       // a bucket with an empty slot ends the probe sequence
+                    else if (act[g]) { pb[g] += pstep[g]; if (pb[g] >= p.tab.n_buckets) pb[g] -= p.tab.n_buckets; }
+                }
+            }
+            __syncwarp();
+            // consume: verify the queued candidates, one per quad, PGM_G in flight
+            for (uint32_t i0 = 0; i0 < wcount; i0 += 8 * PGM_G) {
+                bool on[PGM_G], isn[PGM_G], chain[PGM_G];
+                uint32_t cpos[PGM_G], cpat[PGM_G], cr[PGM_G], cj[PGM_G], cs16[PGM_G];
+                uint4 *crec[PGM_G];
+                uint4 v[PGM_G];
+#pragma unroll
+                for (int g = 0; g < PGM_G; g++) {
+                    const uint32_t i = i0 + g * 8 + quad;
+                    on[g] = i < wcount;
+                    const uint2 e = on[g] ? wq[i] : make_uint2(0, 0);
+                    cpos[g] = e.x & 0x7FFFFFFFu; chain[g] = (e.x >> 31) != 0; cpat[g] = e.y;
+                }
+                bool again;
+                do {
+#pragma unroll
+                    for (int g = 0; g < PGM_G; g++) {
+                        cr[g] = cpat[g] / p.parts;
+                        cj[g] = cpat[g] - cr[g] * p.parts;
+                        crec[g] = record_of(p.reads, cr[g], cs16[g], isn[g]);
+                        v[g] = make_uint4(0, 0, 0, 0);
+                        if (on[g]) v[g] = hints ? ld_u4_hint(crec[g] + q, pol_stream) : __ldcg(crec[g] + q);
+                    }
+#pragma unroll
+                    for (int g = 0; g < PGM_G; g++) {
+                        // header of the record (lane 0 of the quad holds it)
+                        const uint32_t st_lo = __shfl_sync(PGM_FULL, v[g].x, qb), st_hi = __shfl_sync(PGM_FULL, v[g].y, qb);
+                        const uint32_t bk_lo = __shfl_sync(PGM_FULL, v[g].z, qb), bk_hi = __shfl_sync(PGM_FULL, v[g].w, qb);
+                        // body of DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:301-331) up to the decision
+                        const uint32_t c_in = st_hi >> 24;
+                        const uint64_t gpos = tile_g0 + cpos[g];
+                        const uint32_t shift = cj[g] * p.seed_len;
+                        const uint32_t L = p.reads.read_len;
+                        bool ok = on[g] && c_in > p.min_mm && (uint64_t)shift <= gpos;             // :304, :308
+                        const uint64_t a = ok ? gpos - shift : tile_g0;
+                        ok = ok && a + L <= p.pg_len;                                              // :311
+                        const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;                 // :313,:326 (matchingLength == readLength)
+                        const bool has_pos = c_in != 255u;
+                        const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
+                        const bool same_pos = has_pos && st_pos == rep;                            // coordinate-only compare, :313
+                        const int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;                 // :315
+                        const uint32_t boff = ok ? (uint32_t)((int64_t)(a - p.slice_origin) - buf_bit0) : 0u;
+                        int c = count_groups(q, isn[g], v[g], blo, bhi, boff, p.reads.W, L);
+                        for (uint32_t u = q + 4; u < cs16[g]; u += 4) {
+                            uint4 x = make_uint4(0, 0, 0, 0);
+                            if (ok) x = __ldcg(crec[g] + u);
+                            c += count_groups(u, isn[g], x, blo, bhi, boff, p.reads.W, L);
+                        }
+                        c = quad_sum(c);
+                        if (q == 0 && on[g]) {
+                            n_cand++;
+                            if (ok) {
+                                n_ver++;
+                                if (c <= limit) {
+                                    n_acc++;
+                                    const unsigned long long order = (gpos << 8) | (unsigned long long)(p.parts - 1 - cj[g]);
+                                    if (!same_pos) {
+                                        const unsigned long long cls = (uint32_t)c <= p.min_mm ? 0ull : (unsigned long long)c;
+                                        const long long key = (long long)((cls << 56) | (order << 8) | (unsigned long long)c);
+                                        const long long seen = (long long)(((uint64_t)bk_hi << 32) | bk_lo);   // never below the live value
+                                        if (key < seen) atomicMin(reinterpret_cast<long long *>(crec[g]) + 1, key);
+                                        if (has_pos) {
+                                            atomicMin(p.pr.first_other_order + cr[g], (long long)order);
+                                            *p.pr.touched = 1;
+                                        }
+                                    } else {
+                                        atomicOr(p.pr.same_pos_mask + cr[g], 1 << cj[g]);
+                                        p.pr.same_pos_mm[cr[g]] = (uint8_t)c;
+                                        *p.pr.touched = 1;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    // hot keys: walk the chain behind the slot
+                    again = false;
+#pragma unroll
+                    for (int g = 0; g < PGM_G; g++) {
+                        if (on[g] && chain[g]) {
+                            cpat[g] = __ldg(p.tab.next + cpat[g]);
+                            on[g] = cpat[g] != PGM_NIL;
+                        } else on[g] = false;
+                        again |= on[g];
+                    }
+                    again = __ballot_sync(PGM_FULL, again) != 0;
+                } while (again);
+            }
+            __syncwarp();
+            wcount = 0;
+            bool any = false;
+#pragma unroll
+            for (int g = 0; g < PGM_G; g++) any |= act[g];
+            if (exhausted && !__ballot_sync(PGM_FULL, any)) break;
         }
         __syncthreads();
-        if (t == 0) sm.q_count = 0;
+        buf ^= 1;
     }
 
     // counters: warp reduce, one atomic per warp
-    unsigned long long v[4] = {n_cand, n_ver, n_acc, n_ovf};
+    unsigned long long cv[4] = {n_cand, n_ver, n_acc, n_pos};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
-        if ((t & 31) == 0 && v[k]) atomicAdd(p.counters + k, v[k]);
+        for (int o = 16; o > 0; o >>= 1) cv[k] += __shfl_xor_sync(PGM_FULL, cv[k], o);
+        if (lane == 0 && cv[k]) atomicAdd(p.counters + k, cv[k]);
     }
 }
 
@@ -616,56 +799,67 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 3) scan_kernel(const __grid_
 // only after the earliest of those — by the events of the alignment that reports X itself
 // (ReadsMatchers.cpp:313 skips them while X is still stored).  class = 0 for c <= minMismatches (the
 // reference stops updating a read there, :304), else c.
-__global__ void resolve_kernel(PerRead pr, uint32_t n_reads, uint64_t pg_len, uint32_t read_len, uint32_t seed_len,
+__global__ void resolve_kernel(ReadsView reads, PerRead pr, uint32_t n_reads, uint64_t pg_len, uint32_t seed_len,
                                uint32_t parts, uint32_t max_mm, uint32_t min_mm, int rev_mode) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
-    const unsigned long long st = pr.state[r];
-    long long best = pr.best_key[r];
-    const long long o1 = pr.first_other_order[r];
-    const int mask = pr.same_pos_mask[r];
-    const uint32_t cx = pr.same_pos_mm[r];
-    pr.best_key[r] = PGM_KEY_INF;
-    pr.first_other_order[r] = PGM_KEY_INF;
-    pr.same_pos_mask[r] = 0;
-    pr.same_pos_mm[r] = 255;
-    if (r == 0) *pr.touched = 0;
+    const uint32_t read_len = reads.read_len;
+    uint32_t stride16; bool is_n;
+    uint4 *rec = record_of(reads, r, stride16, is_n);
+    const uint4 h = __ldcg(rec);
+    const unsigned long long st = ((unsigned long long)h.y << 32) | h.x;
+    long long best = (long long)(((unsigned long long)h.w << 32) | h.z);
+    const int touched = *pr.touched;       // reset by the host after this kernel
+    long long o1 = PGM_KEY_INF;
+    int mask = 0;
+    uint32_t cx = 255;
+    if (touched) {
+        o1 = pr.first_other_order[r]; mask = pr.same_pos_mask[r]; cx = pr.same_pos_mm[r];
+        if (o1 != PGM_KEY_INF) pr.first_other_order[r] = PGM_KEY_INF;
+        if (mask) { pr.same_pos_mask[r] = 0; pr.same_pos_mm[r] = 255; }
+    }
+    if (best == PGM_KEY_INF && mask == 0) return;
+    unsigned long long new_st = st;
     const uint32_t c_in = (uint32_t)(st >> 56);
-    if (c_in <= min_mm) return;
-    const int limit = c_in != 255u ? (int)c_in - 1 : (int)max_mm;
-    if (mask != 0 && (int)cx <= limit && o1 != PGM_KEY_INF) {
-        const uint64_t X = st & PGM_POS_MASK;
-        const uint64_t aX = rev_mode ? pg_len - X - read_len : X;   // that alignment in this pass's coordinates
-        for (uint32_t j = 0; j < parts; j++) {
-            if (!((mask >> j) & 1)) continue;
-            const unsigned long long order = ((aX + (uint64_t)j * seed_len) << 8) | (unsigned long long)(parts - 1 - j);
-            if ((long long)order > o1) {
-                const unsigned long long cls = cx <= min_mm ? 0ull : (unsigned long long)cx;
-                const long long key = (long long)((cls << 56) | (order << 8) | cx);
-                best = min(best, key);
-                break;
+    if (c_in > min_mm) {
+        const int limit = c_in != 255u ? (int)c_in - 1 : (int)max_mm;
+        if (mask != 0 && (int)cx <= limit && o1 != PGM_KEY_INF) {
+            const uint64_t X = st & PGM_POS_MASK;
+            const uint64_t aX = rev_mode ? pg_len - X - read_len : X;   // that alignment in this pass's coordinates
+            for (uint32_t j = 0; j < parts; j++) {
+                if (!((mask >> j) & 1)) continue;
+                const unsigned long long order = ((aX + (uint64_t)j * seed_len) << 8) | (unsigned long long)(parts - 1 - j);
+                if ((long long)order > o1) {
+                    const unsigned long long cls = cx <= min_mm ? 0ull : (unsigned long long)cx;
+                    const long long key = (long long)((cls << 56) | (order << 8) | cx);
+                    best = min(best, key);
+                    break;
+                }
             }
         }
+        if (best != PGM_KEY_INF) {
+            const uint32_t c = (uint32_t)(best & 0xFF);
+            const uint32_t jj = (uint32_t)((best >> 8) & 0xFF);
+            const uint64_t g = ((unsigned long long)best >> 16) & PGM_POS_MASK;
+            const uint64_t a = g - (uint64_t)(parts - 1 - jj) * seed_len;
+            const uint64_t rep = rev_mode ? pg_len - (a + read_len) : a;
+            new_st = ((unsigned long long)c << 56) | ((unsigned long long)(rev_mode ? 1 : 0) << 55) | rep;
+        }
     }
-    if (best == PGM_KEY_INF) return;
-    const uint32_t c = (uint32_t)(best & 0xFF);
-    const uint32_t jj = (uint32_t)((best >> 8) & 0xFF);
-    const uint64_t g = ((unsigned long long)best >> 16) & PGM_POS_MASK;
-    const uint64_t a = g - (uint64_t)(parts - 1 - jj) * seed_len;
-    const uint64_t rep = rev_mode ? pg_len - (a + read_len) : a;
-    pr.state[r] = ((unsigned long long)c << 56) | ((unsigned long long)(rev_mode ? 1 : 0) << 55) | rep;
+    rec[0] = make_uint4((uint32_t)new_st, (uint32_t)(new_st >> 32), 0xFFFFFFFFu, 0x7FFFFFFFu);
 }
 
 // state -> the three archive-visible arrays (+ matched count and per-mismatch histogram)
-__global__ void finalize_kernel(const unsigned long long *__restrict__ state, uint32_t n_reads,
-                                unsigned long long *__restrict__ out_pos, uint8_t *__restrict__ out_rc,
-                                uint8_t *__restrict__ out_mm, unsigned long long *hist /*[257]*/) {
+__global__ void finalize_kernel(ReadsView reads, uint32_t n_reads, unsigned long long *__restrict__ out_pos,
+                                uint8_t *__restrict__ out_rc, uint8_t *__restrict__ out_mm, unsigned long long *hist /*[257]*/) {
     __shared__ unsigned int sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n_reads) {
-        const unsigned long long st = state[r];
+        uint32_t stride16; bool is_n;
+        const uint2 h = __ldcg(reinterpret_cast<const uint2 *>(record_of(reads, r, stride16, is_n)));
+        const unsigned long long st = ((unsigned long long)h.y << 32) | h.x;
         const uint32_t c = (uint32_t)(st >> 56);
         out_pos[r] = c == 255u ? 0xFFFFFFFFFFFFFFFFull : (st & PGM_POS_MASK);
         out_rc[r] = (uint8_t)((st >> 55) & 1);
@@ -674,6 +868,24 @@ __global__ void finalize_kernel(const unsigned long long *__restrict__ state, ui
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
+}
+
+// Multi-GPU exchange: the per-read keys live inside the records; these two kernels copy them to / from a
+// contiguous array that the caller all-reduces (MIN) across the text shards.
+__global__ void export_keys_kernel(ReadsView reads, uint32_t n_reads, long long *__restrict__ keys) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    uint32_t stride16; bool is_n;
+    const uint4 h = __ldcg(record_of(reads, r, stride16, is_n));
+    keys[r] = (long long)(((unsigned long long)h.w << 32) | h.z);
+}
+__global__ void import_keys_kernel(ReadsView reads, uint32_t n_reads, const long long *__restrict__ keys) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    uint32_t stride16; bool is_n;
+    long long *k = reinterpret_cast<long long *>(record_of(reads, r, stride16, is_n)) + 1;
+    const long long v = keys[r];
+    if (*k != v) *k = v;
 }
 
 } // namespace pgm

@@ -114,8 +114,8 @@ class GpuReadsMatcher:
             raise PgmError(rc, self._lib.pgm_last_error(self._h).decode())
 
     # -- inputs
-    def set_tuning(self, filter_log2_bits: int = -1, slots_per_pattern: int = 3, ctas_per_sm: int = 3):
-        self._check(self._lib.pgm_set_tuning(self._h, filter_log2_bits, slots_per_pattern, ctas_per_sm))
+    def set_tuning(self, filter_log2_bits: int = -1, slots_per_pattern: int = 2, ctas_per_sm: int = 4, l2_hints: bool = True):
+        self._check(self._lib.pgm_set_tuning(self._h, filter_log2_bits, slots_per_pattern, ctas_per_sm, int(l2_hints)))
 
     def set_text(self, text):
         """text: ASCII pseudogenome (numpy uint8 / torch uint8, host or device)."""
@@ -163,6 +163,10 @@ class GpuReadsMatcher:
                 "same_pos_mask": mk(acc.same_pos_mask, n, "<i4"), "same_pos_mm": mk(acc.same_pos_mm, n, "|u1"),
                 "touched": mk(acc.touched, 1, "<i4")}
 
+    def put_accumulators(self):
+        """Copies the (merged) contiguous keys back into the read records (pgm_put_accumulators)."""
+        self._check(self._lib.pgm_put_accumulators(self._h))
+
     def synchronize(self):
         self._check(self._lib.pgm_synchronize(self._h))
 
@@ -188,7 +192,7 @@ class GpuReadsMatcher:
     def _result(out, st: PgmStats) -> MatchResult:
         per = np.frombuffer(bytes(st.per_mm), np.uint64).copy()
         stats = {k: int(getattr(st, k)) for k in ("patterns_inserted", "table_slots", "candidates", "verified",
-                                                  "accepted", "queue_overflows")}
+                                                  "accepted", "filter_positives")}
         return MatchResult(out[0], out[1], out[2], int(st.matched), per, stats)
 
     def get_results(self, out=None) -> MatchResult:
@@ -279,6 +283,7 @@ def merge_accumulators(m: GpuReadsMatcher, group=None):
         dist.all_reduce(acc["first_other_order"], op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(acc["same_pos_mask"], op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(acc["same_pos_mm"], op=dist.ReduceOp.MIN, group=group)
+    m.put_accumulators()
     return acc
 
 

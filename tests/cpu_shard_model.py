@@ -57,6 +57,9 @@ class CpuShardMatcher:
     def accumulators(self):
         return self.acc
 
+    def put_accumulators(self):
+        """The model keeps its keys in the contiguous arrays themselves (the CUDA path copies them back into the read records)."""
+
     def scan_pass(self, rev):
         n, L, pg = self.seed_len, self.read_len, self.pg_len
         if pg < n or not self.n_reads:

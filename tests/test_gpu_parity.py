@@ -135,3 +135,25 @@ def test_context_reuse_and_filter_off():
             assert np.array_equal(g1.pos, w1.pos) and np.array_equal(g1.mm, w1.mm) and np.array_equal(g1.rc, w1.rc)
             assert np.array_equal(g2.pos, w2.pos) and np.array_equal(g2.mm, w2.mm) and np.array_equal(g2.rc, w2.rc)
         assert m.kernel_launches() > 0
+
+
+def test_hot_seeds_duplicate_reads_and_homopolymers():
+    """Hundreds of reads sharing one seed (duplicates, poly-A): exercises the full-bucket walk and the
+    chains behind a slot of the seed table, and the per-warp candidate queues running full."""
+    rng = np.random.default_rng(9)
+    g = synth.random_genome(30_000, rng)
+    text = np.concatenate([g[:10_000], np.full(400, ord("A"), np.uint8), g[10_000:20_000], np.full(300, ord("T"), np.uint8),
+                           np.tile(np.frombuffer(b"AC", np.uint8), 200), g[20_000:]])
+    base = synth.sample_reads(g, 40, 100, 0.02, rng)
+    dup = np.repeat(base, 60, axis=0)                                     # 60 copies of each of 40 reads
+    polya = np.full((300, 100), ord("A"), np.uint8)
+    polya[np.arange(300), rng.integers(0, 100, 300)] = ord("C")           # one substitution each
+    acac = np.tile(np.frombuffer(b"AC", np.uint8), (150, 50))
+    reads = np.concatenate([dup, polya, acac, synth.sample_reads(g, 500, 100, 0.01, rng)])
+    reads = reads[rng.permutation(len(reads))]
+    nn = synth.inject_n(np.repeat(base[:5], 40, axis=0), rng)
+    inp = synth.MatcherInputs(np.ascontiguousarray(text), np.ascontiguousarray(reads), nn, 100, "hot seeds")
+    got, want = _check(inp)
+    assert got.stats["candidates"] > 100_000
+    _check(inp, matching_mode="D")
+    _check(inp, reads_exact_matching_chars=100)
