@@ -67,7 +67,7 @@ struct pgm_ctx {
     uint32_t filter_words = 0;  // 0 = no filter
 
     // phase
-    uint32_t seed_len = 0, parts = 0, max_mm = 0, min_mm = 0;
+    uint32_t seed_len = 0, parts = 0, max_mm = 0, min_mm = 0, part_bits = 0;
     bool phase_active = false;
 
     // misc device scalars: counters[0..3] scan, [4] inserted, [5] tile counter (low 32 bits)
@@ -161,12 +161,13 @@ pgm::ReadsView reads_view(pgm_ctx *c) {
     rv.n_lq = c->n_lq; rv.n_n = c->n_n;
     rv.lq_stride16 = c->lq_stride16; rv.n_stride16 = c->n_stride16;
     rv.read_len = c->read_len; rv.W = c->W;
+    rv.part_bits = c->part_bits;
     return rv;
 }
 
 pgm::TableView table_view(pgm_ctx *c) {
     pgm::TableView tv;
-    tv.buckets = c->buckets.as<uint4>();
+    tv.buckets = c->buckets.as<pgm::u32x8>();
     tv.next = c->next.as<uint32_t>();
     tv.filter = c->filter_words ? c->filter.as<uint32_t>() : nullptr;
     tv.n_buckets = c->n_buckets;
@@ -434,19 +435,23 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
         return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_match_begin: need seed_len >= 1 and seed_len * parts <= read_len");
     if (max_mm > 127 || min_mm > 127) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_match_begin: mismatch limits must be <= 127");
     const uint64_t n_patterns = (uint64_t)ctx->n_reads() * parts;
-    if (n_patterns >= 0xFFFFFFFFull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin: pattern index exceeds 32 bits (reference limit, HashMatcher.cpp:39)");
+    // pattern id = read << part_bits | seed; the reference's limit is n_reads * parts < 2^32 (HashMatcher.cpp:39)
+    const uint32_t part_bits = (uint32_t)ceil_log2(parts);
+    const uint64_t n_ids = (uint64_t)ctx->n_reads() << part_bits;
+    if (n_ids >= 0xFFFFFFFFull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin: pattern index exceeds 32 bits (reads << ceil(log2(parts)))");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->n_reads();
-    // table geometry: a prime number of 8-slot buckets, slots_per_pattern slots per pattern
+    // table geometry: a prime number of 4-slot buckets, slots_per_pattern slots per pattern
     const uint64_t want_slots = std::max<uint64_t>(512, n_patterns * (uint64_t)ctx->slots_per_pattern);
-    const uint64_t nb64 = next_prime((want_slots + 7) / 8);
+    const uint64_t nb64 = next_prime((want_slots + 3) / 4);
     if (nb64 >= 0x7FFFFFFFull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin: table too large");
     int rc;
-    if ((rc = ensure(ctx, ctx->buckets, nb64 * 64)) || (rc = ensure(ctx, ctx->next, std::max<uint64_t>(n_patterns, 1) * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->buckets, nb64 * 32)) || (rc = ensure(ctx, ctx->next, std::max<uint64_t>(n_ids, 1) * 4))) return rc;
     ctx->n_buckets = (uint32_t)nb64;
-    ctx->n_slots = nb64 * 8;
-    CU(cudaMemsetAsync(ctx->buckets.p, 0xFF, nb64 * 64, ctx->stream));
-    CU(cudaMemsetAsync(ctx->next.p, 0xFF, std::max<uint64_t>(n_patterns, 1) * 4, ctx->stream));
+    ctx->n_slots = nb64 * 4;
+    ctx->part_bits = part_bits;
+    CU(cudaMemsetAsync(ctx->buckets.p, 0xFF, nb64 * 32, ctx->stream));
+    CU(cudaMemsetAsync(ctx->next.p, 0xFF, std::max<uint64_t>(n_ids, 1) * 4, ctx->stream));
     int fbits = ctx->filter_log2_bits;
     if (fbits < 0) fbits = std::min(28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 8)));
     if (fbits > 0) {
@@ -467,8 +472,10 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     }
     ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
     if (n_patterns) {
-        KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid_for(n_patterns * 4, 256), 256, 0, ctx->stream>>>(
-            reads_view(ctx), table_view(ctx), seed_len, parts, min_mm, continuation ? 1 : 0,
+        const uint32_t tail = seed_len % 32 ? (1u << (seed_len % 32)) - 1u : 0xFFFFFFFFu;
+        const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(n, 256), (uint64_t)ctx->sm_count * 8);
+        KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid, 256, 0, ctx->stream>>>(
+            reads_view(ctx), table_view(ctx), seed_len, parts, min_mm, continuation ? 1 : 0, tail,
             ctx->counters.as<unsigned long long>() + 4));
     }
     ctx->phase_active = true;

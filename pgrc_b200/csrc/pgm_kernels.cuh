@@ -5,13 +5,14 @@
 //               per uint32 word, base p at bit (p & 31) of word (p >> 5); PGM_PAD_WORDS zero
 //               words in front of the origin, a zero tail behind it.  The reverse-complement
 //               strand is materialised once (rc = ~bitreverse) so both passes run one kernel.
-//   read record one per read, 64-byte multiples, fetched as ONE DRAM request by a lane quad:
+//   read record one per read, 64-byte multiples, fetched as ONE DRAM request by a lane pair (2 x 32 bytes):
 //               uint4 #0 = {state64, best_key64}; ACGT set: uint4 #(1+g/2) = {lo,hi} of the 32-base
 //               groups g, g+1; ACGNT set: uint4 #(1+g) = {lo, hi, nmask, 0} of group g (lo = hi = 0
 //               under an N).  state64 = mm:8 | rc:1 | pos:40 ; best_key64 = cls:8 | txtPos:40 |
 //               (parts-1-j):8 | mm:8 (MIN-mergeable accumulator of the current pass).
-//   seed table  multimap, 64-byte buckets of eight 8-byte slots {tag:31 chain:1 | pattern:32}, double
-//               hashing over a prime number of buckets.  Every pattern owns a slot of the first
+//   seed table  multimap, 32-byte buckets of four 8-byte slots {tag:31 chain:1 | pattern:32} (one 256-bit load
+//               per probe), double hashing over a prime number of buckets; pattern = read << part_bits | seed.
+//               Every pattern owns a slot of the first
 //               bucket of its probe sequence that has room (so a lookup stops at the first bucket with
 //               an empty slot); only when PGM_WALK_CAP buckets in a row are full of the same key (hot
 //               seeds: poly-A, satellites) a pattern is chained behind a slot through next[].
@@ -29,8 +30,10 @@
 // Memory-system facts the kernels are shaped by (tools/ubench.cu, profiles/ubench_r01.txt): a fully
 // divergent 4-byte gather costs one L1 wavefront per lane (285 G lookups/s chip-wide); DRAM serves
 // about 42 G random requests/s whether they carry 32 or 64 bytes, provided ONE instruction asks for
-// the whole 64 bytes (four lanes x 16 bytes); one lane issuing 4 x 16 bytes gets 18 G/s.  So every
-// random access here is a 64-byte item fetched by a lane quad.
+// the whole item (one lane x 32 bytes, or adjacent lanes covering 64 bytes); one lane issuing 2 x 32 or
+// 4 x 16 bytes gets about half of that.  So a table probe is one 256-bit load by one lane and a read
+// record is fetched by a lane pair.  A first version with lane quads everywhere was instruction-issue
+// bound (profiles/scan_lines_r01d.txt): control flow replicated on four lanes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -45,10 +48,9 @@
 #define PGM_SCAN_THREADS 256
 #define PGM_SCAN_WARPS (PGM_SCAN_THREADS / 32)
 #define PGM_WORDS_PER_WARP (PGM_TILE_WORDS / PGM_SCAN_WARPS)
-#define PGM_G 2                            // 64-byte requests in flight per lane quad
-#define PGM_WQ_CAP 384                     // per-warp candidate queue entries
-#define PGM_WQ_ROUND (64 * PGM_G)          // most entries one probe round can add (8 quads x 8 slots x G)
-#define PGM_WALK_CAP 4                     // full buckets walked before a duplicate key is chained
+#define PGM_WQ_CAP 320                     // per-warp candidate queue entries
+#define PGM_WQ_ROUND 128                   // most entries one probe round can add (32 lanes x 4 slots)
+#define PGM_WALK_CAP 6                     // full buckets walked before a duplicate key is chained
 
 #define PGM_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define PGM_NIL 0xFFFFFFFFu
@@ -77,8 +79,10 @@ __host__ __device__ __forceinline__ uint32_t filter_bits(uint32_t h2) {
 }
 
 // ------------------------------------------------------------------------------------------ parameters
+struct __align__(32) u32x8 { uint32_t v[8]; };
+
 struct TableView {
-    uint4 *buckets;             // 4 uint4 = 8 slots per bucket; slot = {pattern, chain:1 | tag:31}
+    u32x8 *buckets;             // 4 slots per bucket; slot = {pattern, chain:1 | tag:31}
     uint32_t *next;             // chains of hot keys
     uint32_t *filter;           // may be null
     uint32_t n_buckets;         // prime
@@ -91,6 +95,7 @@ struct ReadsView {
     uint32_t n_lq, n_n;
     uint32_t lq_stride16, n_stride16;
     uint32_t read_len, W;
+    uint32_t part_bits;         // pattern id = read << part_bits | seed index
 };
 
 struct PerRead {
@@ -168,18 +173,28 @@ __device__ __forceinline__ uint4 ld_u4_hint(const uint4 *p, uint64_t pol) {
     return v;
 }
 
+// 256-bit loads (LDG.256, new on sm_100): one request for a whole 32-byte sector
+__device__ __forceinline__ u32x8 ld256_stream(const void *p) {
+    u32x8 r;
+    asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ u32x8 ld256_stream_hint(const void *p, uint64_t pol) {
+    u32x8 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ u32x8 ld256_cg(const void *p) {
+    u32x8 r;
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, uint32_t r) { return __funnelshift_r(x, x, r); }
 
-__device__ __forceinline__ uint32_t quad_xor(uint32_t v) {
-    v ^= __shfl_xor_sync(PGM_FULL, v, 1);
-    v ^= __shfl_xor_sync(PGM_FULL, v, 2);
-    return v;
-}
-__device__ __forceinline__ int quad_sum(int v) {
-    v += __shfl_xor_sync(PGM_FULL, v, 1);
-    v += __shfl_xor_sync(PGM_FULL, v, 2);
-    return v;
-}
 
 // record of global read r: pointer, stride (uint4), ACGNT?
 __device__ __forceinline__ uint4 *record_of(const ReadsView &rv, uint32_t r, uint32_t &stride16, bool &is_n) {
@@ -353,101 +368,73 @@ __global__ void reset_state_kernel(ReadsView reads, PerRead pr, uint32_t n_reads
     pr.same_pos_mm[r] = 255;
 }
 
-// ------------------------------------------------------------------------------------------ seed form of a read
-// Folded canonical form of seed j (read bases [j*n, (j+1)*n)) from the quad-distributed record: lane q of the quad
-// holds uint4 #q (#q+4, ... are fetched here when the record is longer than 64 bytes).  A base at read position x
-// lands on bit (x - j*n) mod 32, i.e. each 32-base group contributes rotr(group & range, (j*n) mod 32).
-__device__ __forceinline__ void fold_groups(uint32_t u, bool is_n, uint4 v, uint32_t W, uint32_t b0, uint32_t b1,
-                                            uint32_t &P, uint32_t &Q, uint32_t &R, uint32_t &FN) {
-    if (u == 0) return;
-    const uint32_t s = b0 & 31u;
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        if (is_n && half) break;
-        const uint32_t g = is_n ? u - 1 : 2 * (u - 1) + half;
-        if (g >= W) break;
-        const int lo_bit = max((int)b0 - (int)(32 * g), 0), hi_bit = min((int)b1 - (int)(32 * g), 32);
-        if (hi_bit <= lo_bit) continue;
-        uint32_t m = hi_bit == 32 ? 0xFFFFFFFFu : (1u << hi_bit) - 1u;
-        m &= ~((1u << lo_bit) - 1u);
-        const uint32_t l = (half ? v.z : v.x) & m, h = (half ? v.w : v.y) & m;
-        P ^= rotr32(l, s); Q ^= rotr32(h, s); R ^= rotr32(l & h, s);
-        if (is_n) FN ^= rotr32(v.z & m, s);
-    }
+// ------------------------------------------------------------------------------------------ table build
+// 32 bits of a record's plane starting at read position `bit` (plane words sit `stride` words apart)
+__device__ __forceinline__ uint32_t extract32(const uint32_t *w, uint32_t nwords, uint32_t stride, uint32_t bit) {
+    const uint32_t k = bit >> 5;
+    const uint32_t a = k < nwords ? __ldg(w + k * stride) : 0u;
+    const uint32_t b = k + 1 < nwords ? __ldg(w + (k + 1) * stride) : 0u;
+    return __funnelshift_r(a, b, bit & 31);
 }
 
-// ------------------------------------------------------------------------------------------ table build
-// One lane quad per pattern (read r, seed j): fetch the record (one 64-byte request), fold the seed, insert into
-// the first bucket of the probe sequence with room.  Restates addReadsSetOfPatterns
-// (ConstantLengthPatternsOnTextHashMatcher.cpp:23-42); pattern index = r * parts + j (:39).  Reads already
-// matched with <= min_mm mismatches are left out when `continuation` (the matchedReadsBitmap argument,
-// ReadsMatchers.cpp:290-291).
+// One thread per read: for each of its `parts` seeds, fold read bases [j*n, (j+1)*n) into the canonical form
+// (the record's plane words come through L1: adjacent lanes read adjacent records), set the filter bits and
+// insert the pattern into the first bucket of its probe sequence with room.  Restates addReadsSetOfPatterns
+// (ConstantLengthPatternsOnTextHashMatcher.cpp:23-42); the reference's pattern index r * parts + j (:39) is
+// kept as (r << part_bits) | j.  Reads already matched with <= min_mm mismatches are left out when
+// `continuation` (the matchedReadsBitmap argument, ReadsMatchers.cpp:290-291).
 __global__ void __launch_bounds__(256) build_table_kernel(ReadsView reads, TableView tab, uint32_t seed_len, uint32_t parts,
-                                                          uint32_t min_mm, int continuation, unsigned long long *inserted) {
-    const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t p = gt >> 2;
-    const uint32_t lane = threadIdx.x & 31, q = lane & 3, qb = lane & ~3u;
-    const uint64_t n_patterns = (uint64_t)(reads.n_lq + reads.n_n) * parts;
-    bool active = p < n_patterns;
-    uint32_t r = 0, j = 0, stride16 = 4;
-    bool is_n = false;
-    uint4 *rec = reads.lq;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (active) {
-        r = (uint32_t)(p / parts);
-        j = (uint32_t)(p - (uint64_t)r * parts);
-        rec = record_of(reads, r, stride16, is_n);
-        v = __ldg(rec + q);
-    }
-    const uint32_t st_hi = __shfl_sync(PGM_FULL, v.y, qb);
-    if (continuation && (st_hi >> 24) <= min_mm) active = false;
-    uint32_t P = 0, Q = 0, R = 0, FN = 0;
-    if (active) {
-        const uint32_t b0 = j * seed_len, b1 = b0 + seed_len;
-        fold_groups(q, is_n, v, reads.W, b0, b1, P, Q, R, FN);
-        for (uint32_t u = q + 4; u < stride16; u += 4) fold_groups(u, is_n, __ldg(rec + u), reads.W, b0, b1, P, Q, R, FN);
-    }
-    P = quad_xor(P); Q = quad_xor(Q); R = quad_xor(R); FN = quad_xor(FN);
-    // a seed whose N parity is odd in some rotation class can never collide with an ACGT window
-    if (FN != 0) active = false;
-    const uint64_t hv = seed_hash64(P, Q, R);
-    const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
-    const uint32_t tag = seed_tag(h2);
-    const uint32_t pat = (uint32_t)p;
-    if (active && q == 0 && tab.filter) atomicOr(tab.filter + (h1 & tab.filter_mask), filter_bits(h2));
-    uint32_t b = __umulhi(h1, tab.n_buckets);
-    const uint32_t step = 1u + __umulhi(h2 * 0x9E3779B1u, tab.n_buckets - 1u);
-    const unsigned long long mine = ((unsigned long long)tag << 32) | pat;
-    bool pending = active;
-    uint32_t walked = 0;
-    unsigned long long *same_slot = nullptr;
-    while (__ballot_sync(PGM_FULL, pending)) {
-        uint4 s = make_uint4(0, 0, 0, 0);
-        uint4 *bp = tab.buckets + (size_t)b * 4 + q;
-        if (pending) s = __ldcg(bp);
-        const bool e0 = pending && s.y == 0xFFFFFFFFu, e1 = pending && s.w == 0xFFFFFFFFu;
-        const bool t0 = pending && (s.y & 0x7FFFFFFFu) == tag, t1 = pending && (s.w & 0x7FFFFFFFu) == tag;
-        const uint32_t qe = (__ballot_sync(PGM_FULL, e0 || e1) >> qb) & 0xFu;
-        const uint32_t qt = (__ballot_sync(PGM_FULL, t0 || t1) >> qb) & 0xFu;
-        // all shuffles are executed by the whole warp; only their results are used conditionally
-        const uint32_t ql_t = qt ? __ffs(qt) - 1 : 0u, ql_e = qe ? __ffs(qe) - 1 : 0u;
-        const uint32_t first_t = __shfl_sync(PGM_FULL, t0 ? 0u : 1u, qb + ql_t);
-        if (pending && same_slot == nullptr && qt)   // remember one slot that already holds this key
-            same_slot = reinterpret_cast<unsigned long long *>(tab.buckets + (size_t)b * 4 + ql_t) + first_t;
-        int ok = 0;
-        if (pending && qe && q == ql_e) {
-            unsigned long long *sl = reinterpret_cast<unsigned long long *>(bp) + (e0 ? 0 : 1);
-            ok = atomicCAS(sl, PGM_EMPTY64, mine) == PGM_EMPTY64;
-        }
-        ok = __shfl_sync(PGM_FULL, ok, qb + ql_e);
-        bool done = false;
-        if (pending && qe) {
-            done = ok != 0;   // lost the race: look at the same bucket again
-        } else if (pending) {
-            walked++;
-            if (walked >= PGM_WALK_CAP && same_slot != nullptr) {
-                // hot key: chain this pattern behind a slot that already holds the key
-                if (q == 0) {
+                                                          uint32_t min_mm, int continuation, uint32_t tail_mask,
+                                                          unsigned long long *inserted) {
+    const uint32_t n_reads = reads.n_lq + reads.n_n;
+    unsigned int n_ins = 0;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
+        uint32_t stride16; bool is_n;
+        const uint4 *rec = record_of(reads, r, stride16, is_n);
+        if (continuation && (__ldg(reinterpret_cast<const uint32_t *>(rec) + 1) >> 24) <= min_mm) continue;
+        const uint32_t *pl = reinterpret_cast<const uint32_t *>(rec) + 4;   // ACGT: lo,hi pairs; ACGNT: lo,hi,nm,0 quadruples
+        const uint32_t il = is_n ? 4u : 2u;
+        const uint32_t nch = (seed_len + 31) >> 5;
+        for (uint32_t j = 0; j < parts; j++) {
+            uint32_t P = 0, Q = 0, R = 0, FN = 0;
+            for (uint32_t i = 0; i < nch; i++) {
+                const uint32_t bit = j * seed_len + 32 * i;
+                const uint32_t m = (i == nch - 1) ? tail_mask : 0xFFFFFFFFu;
+                const uint32_t l = extract32(pl, reads.W, il, bit) & m;
+                const uint32_t h = extract32(pl + 1, reads.W, il, bit) & m;
+                P ^= l; Q ^= h; R ^= (l & h);
+                if (is_n) FN ^= extract32(pl + 2, reads.W, il, bit) & m;
+            }
+            // a seed whose N parity is odd in some rotation class can never collide with an ACGT window
+            if (FN != 0) continue;
+            const uint64_t hv = seed_hash64(P, Q, R);
+            const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
+            const uint32_t tag = seed_tag(h2);
+            const uint32_t pat = (r << reads.part_bits) | j;
+            if (tab.filter) atomicOr(tab.filter + (h1 & tab.filter_mask), filter_bits(h2));
+            uint32_t b = __umulhi(h1, tab.n_buckets);
+            const uint32_t step = 1u + __umulhi(h2 * 0x9E3779B1u, tab.n_buckets - 1u);
+            const unsigned long long mine = ((unsigned long long)tag << 32) | pat;
+            unsigned long long *same_slot = nullptr;
+            uint32_t walked = 0;
+            for (;;) {
+                unsigned long long *bp = reinterpret_cast<unsigned long long *>(tab.buckets + b);
+                const u32x8 s = ld256_cg(bp);
+                bool done = false, saw_empty = false;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (done) break;
+                    if (s.v[2 * k + 1] == 0xFFFFFFFFu) {
+                        saw_empty = true;
+                        done = atomicCAS(bp + k, PGM_EMPTY64, mine) == PGM_EMPTY64;   // lost the race: try the next empty slot
+                    } else if (same_slot == nullptr && (s.v[2 * k + 1] & 0x7FFFFFFFu) == tag) {
+                        same_slot = bp + k;   // a slot that already holds this key
+                    }
+                }
+                if (done) break;
+                if (saw_empty) continue;      // every empty slot seen was taken meanwhile: look at the bucket again
+                if (++walked >= PGM_WALK_CAP && same_slot != nullptr) {
+                    // hot key: chain this pattern behind a slot that already holds the key
                     unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(same_slot);
                     for (;;) {
                         tab.next[pat] = (uint32_t)old;
@@ -456,17 +443,23 @@ __global__ void __launch_bounds__(256) build_table_kernel(ReadsView reads, Table
                         if (prev == old) break;
                         old = prev;
                     }
+                    break;
                 }
-                done = true;
-            } else {
                 b += step;
                 if (b >= tab.n_buckets) b -= tab.n_buckets;
             }
+            n_ins++;
         }
-        if (done) pending = false;
     }
-    const unsigned int cnt = __popc(__ballot_sync(PGM_FULL, active && q == 0));
-    if (lane == 0 && cnt) atomicAdd(inserted, (unsigned long long)cnt);
+    // one counter update per block
+    __shared__ unsigned int blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_ins += __shfl_xor_sync(PGM_FULL, n_ins, o);
+    if ((threadIdx.x & 31) == 0 && n_ins) atomicAdd(&blk, n_ins);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk) atomicAdd(inserted, (unsigned long long)blk);
 }
 
 // ------------------------------------------------------------------------------------------ the scan
@@ -524,17 +517,19 @@ __device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, cons
 //      canonical seed form (funnel shifts of broadcast shared-memory words), hashes it and tests the L2-resident
 //      filter (one 4-byte gather per position: the L1 wavefront rate bounds this stage); positives are
 //      ballot-compacted into a shared list.
-//  A2  lane quads pull positives from the list, rehash and fetch the 64-byte table bucket as one request (16
-//      bytes per lane); tag hits are ballot-compacted into the warp's candidate queue; a bucket without an empty
-//      slot sends the quad on along its double-hashing sequence.
-//  B   when the warp's queue runs full (and at the end) its quads verify one candidate each: one 64-byte request
-//      for the read record, XOR/popcount against the staged text per lane, quad shuffle-reduce, then atomicMin on the
-//      record's key.  Restates iterateOver/moveNext (HashMatcher.h:42-68) + executeMatching
-//      (ReadsMatchers.cpp:297-341) without their sequential order; the decision is deferred to resolve_kernel.
+//  A2  every lane pulls one positive from the list, rehashes it and fetches its 32-byte table bucket with one
+//      256-bit load; tag hits are ballot-compacted into the warp's candidate queue; a bucket without an empty
+//      slot sends the lane on along its double-hashing sequence.
+//  B   when the warp's queue runs full (and at the end) lane pairs verify one candidate each: the two lanes fetch
+//      the two 32-byte halves of the read record (one 64-byte DRAM request), XOR/popcount their 32-base groups
+//      against the staged text, add up with one shuffle, and the even lane applies the accept test and
+//      atomicMin's the key inside the record.  Restates iterateOver/moveNext (HashMatcher.h:42-68) +
+//      executeMatching (ReadsMatchers.cpp:297-341) without their sequential order; the decision is deferred to
+//      resolve_kernel.
 template <int NCH>
 __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_constant__ ScanParams p) {
     __shared__ __align__(128) ScanShared sm;
-    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u, quad = lane >> 2, q = lane & 3u, qb = lane & ~3u;
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     unsigned long long n_cand = 0, n_ver = 0, n_acc = 0, n_pos = 0;
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
@@ -575,7 +570,6 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
 
         const int64_t tile_word0 = (int64_t)p.first_word + (int64_t)tile * PGM_TILE_WORDS;
         const uint64_t tile_g0 = p.slice_origin + (uint64_t)tile_word0 * 32;   // global position of the tile's first base
-        const int64_t buf_bit0 = (tile_word0 - PGM_HALO_L) * 32;               // local position of buffer word 0, bit 0
         const uint32_t *blo = sm.lo[buf], *bhi = sm.hi[buf];
         const uint32_t *slo = blo + PGM_HALO_L, *shi = bhi + PGM_HALO_L;       // tile position 0
 
@@ -627,131 +621,112 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
 
         // ---- A2 + B, warp-autonomous
         const uint32_t q1n = sm.q1_count[buf];
+        const uint32_t pmask = (1u << p.reads.part_bits) - 1u;
         uint32_t wcount = 0;
-        bool exhausted = false;
-        bool act[PGM_G];
-        uint32_t ppos[PGM_G], ptag[PGM_G], pb[PGM_G], pstep[PGM_G];
-#pragma unroll
-        for (int g = 0; g < PGM_G; g++) { act[g] = false; ppos[g] = ptag[g] = pb[g] = pstep[g] = 0; }
+        bool exhausted = false, act = false;
+        uint32_t ppos = 0, ptag = 0, pb = 0, pstep = 0;
         for (;;) {
-            // produce: probe rounds until the queue is nearly full or the positives are used up
+            // produce: one lane per filter-positive position, one 256-bit load per probed bucket
             while (wcount + PGM_WQ_ROUND <= PGM_WQ_CAP) {
-                bool any = false;
-#pragma unroll
-                for (int g = 0; g < PGM_G; g++) any |= act[g];
-                if (!__ballot_sync(PGM_FULL, any)) {
+                if (!__ballot_sync(PGM_FULL, act)) {
                     if (exhausted) break;
                     uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&sm.q1_cursor[buf], 8u * PGM_G);
+                    if (lane == 0) base = atomicAdd(&sm.q1_cursor[buf], 32u);
                     base = __shfl_sync(PGM_FULL, base, 0);
                     if (base >= q1n) { exhausted = true; break; }
-#pragma unroll
-                    for (int g = 0; g < PGM_G; g++) {
-                        const uint32_t idx = base + g * 8 + quad;
-                        act[g] = idx < q1n;
-                        ppos[g] = act[g] ? sm.q1[idx] : 0u;
-                        const uint64_t hv = window_hash<NCH>(slo, shi, ppos[g], p.tail_mask);
-                        const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
-                        ptag[g] = seed_tag(h2);
-                        pb[g] = __umulhi(h1, p.tab.n_buckets);
-                        pstep[g] = 1u + __umulhi(h2 * 0x9E3779B1u, p.tab.n_buckets - 1u);
-                    }
+                    act = base + lane < q1n;
+                    ppos = act ? sm.q1[base + lane] : 0u;
+                    const uint64_t hv = window_hash<NCH>(slo, shi, ppos, p.tail_mask);
+                    const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
+                    ptag = seed_tag(h2);
+                    pb = __umulhi(h1, p.tab.n_buckets);
+                    pstep = 1u + __umulhi(h2 * 0x9E3779B1u, p.tab.n_buckets - 1u);
                 }
-                uint4 s[PGM_G];
+                u32x8 s;
 #pragma unroll
-                for (int g = 0; g < PGM_G; g++) {
-                    s[g] = make_uint4(0, 0, 0, 0);
-                    if (act[g]) {
-                        const uint4 *bp = p.tab.buckets + (size_t)pb[g] * 4 + q;
-                        s[g] = hints ? ld_u4_hint(bp, pol_stream) : __ldg(bp);
-                    }
-                }
+                for (int k = 0; k < 8; k++) s.v[k] = 0;
+                if (act) s = hints ? ld256_stream_hint(p.tab.buckets + pb, pol_stream) : ld256_stream(p.tab.buckets + pb);
+                bool m[4], em = false;
+                uint32_t bal[4], mine = 0, tot = 0;
 #pragma unroll
-                for (int g = 0; g < PGM_G; g++) {
-                    const bool m0 = act[g] && (s[g].y & 0x7FFFFFFFu) == ptag[g];
-                    const bool m1 = act[g] && (s[g].w & 0x7FFFFFFFu) == ptag[g];
-                    const bool em = act[g] && (s[g].y == 0xFFFFFFFFu || s[g].w == 0xFFFFFFFFu);
-                    const uint32_t b0 = __ballot_sync(PGM_FULL, m0), b1 = __ballot_sync(PGM_FULL, m1);
-                    const uint32_t be = __ballot_sync(PGM_FULL, em);
-                    if (b0 | b1) {
-                        uint32_t off = wcount + __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
-                        if (m0) wq[off++] = make_uint2(ppos[g] | (s[g].y & 0x80000000u), s[g].x);
-                        if (m1) wq[off] = make_uint2(ppos[g] | (s[g].w & 0x80000000u), s[g].z);
-                        wcount += __popc(b0) + __popc(b1);
-                    }
-                    if ((be >> qb) & 0xFu) act[g] = false;       // a bucket with an empty slot ends the probe sequence
-                    else if (act[g]) { pb[g] += pstep[g]; if (pb[g] >= p.tab.n_buckets) pb[g] -= p.tab.n_buckets; }
+                for (int k = 0; k < 4; k++) {
+                    m[k] = act && (s.v[2 * k + 1] & 0x7FFFFFFFu) == ptag;
+                    em |= s.v[2 * k + 1] == 0xFFFFFFFFu;
+                    bal[k] = __ballot_sync(PGM_FULL, m[k]);
+                    mine += __popc(bal[k] & lt_mask);
+                    tot += __popc(bal[k]);
                 }
+                if (tot) {
+                    uint32_t off = wcount + mine;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (m[k]) wq[off++] = make_uint2(ppos | (s.v[2 * k + 1] & 0x80000000u), s.v[2 * k]);
+                    wcount += tot;
+                }
+                if (em) act = false;                     // a bucket with an empty slot ends the probe sequence
+                else if (act) { pb += pstep; if (pb >= p.tab.n_buckets) pb -= p.tab.n_buckets; }
             }
             __syncwarp();
-            // consume: verify the queued candidates, one per quad, PGM_G in flight
-            for (uint32_t i0 = 0; i0 < wcount; i0 += 8 * PGM_G) {
-                bool on[PGM_G], isn[PGM_G], chain[PGM_G];
-                uint32_t cpos[PGM_G], cpat[PGM_G], cr[PGM_G], cj[PGM_G], cs16[PGM_G];
-                uint4 *crec[PGM_G];
-                uint4 v[PGM_G];
-#pragma unroll
-                for (int g = 0; g < PGM_G; g++) {
-                    const uint32_t i = i0 + g * 8 + quad;
-                    on[g] = i < wcount;
-                    const uint2 e = on[g] ? wq[i] : make_uint2(0, 0);
-                    cpos[g] = e.x & 0x7FFFFFFFu; chain[g] = (e.x >> 31) != 0; cpat[g] = e.y;
-                }
+            // consume: one lane pair per candidate; each lane fetches one 32-byte half of the 64-byte record
+            const uint32_t half = lane & 1u;
+            for (uint32_t i0 = 0; i0 < wcount; i0 += 16) {
+                const uint32_t i = i0 + (lane >> 1);
+                bool on = i < wcount;
+                const uint2 e = on ? wq[i] : make_uint2(0, 0);
+                const uint32_t cpos = e.x & 0x7FFFFFFFu;
+                const bool chain = (e.x >> 31) != 0;
+                uint32_t cpat = e.y;
                 bool again;
                 do {
+                    const uint32_t cr = cpat >> p.reads.part_bits, cj = cpat & pmask;
+                    uint32_t cs16; bool isn;
+                    uint4 *crec = record_of(p.reads, cr, cs16, isn);
+                    u32x8 v;
 #pragma unroll
-                    for (int g = 0; g < PGM_G; g++) {
-                        cr[g] = cpat[g] / p.parts;
-                        cj[g] = cpat[g] - cr[g] * p.parts;
-                        crec[g] = record_of(p.reads, cr[g], cs16[g], isn[g]);
-                        v[g] = make_uint4(0, 0, 0, 0);
-                        if (on[g]) v[g] = hints ? ld_u4_hint(crec[g] + q, pol_stream) : __ldcg(crec[g] + q);
+                    for (int k = 0; k < 8; k++) v.v[k] = 0;
+                    if (on) v = hints ? ld256_stream_hint(reinterpret_cast<const u32x8 *>(crec) + half, pol_stream)
+                                      : ld256_cg(reinterpret_cast<const u32x8 *>(crec) + half);
+                    // tile-relative alignment: always inside the staged buffer, so the count needs no validity checks
+                    const uint32_t shift = cj * p.seed_len;
+                    const uint32_t boff = PGM_HALO_L * 32 + cpos - (on ? shift : 0u);
+                    const uint32_t L = p.reads.read_len, W = p.reads.W;
+                    int c = count_groups(2 * half, isn, make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]), blo, bhi, boff, W, L)
+                          + count_groups(2 * half + 1, isn, make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]), blo, bhi, boff, W, L);
+                    for (uint32_t u = 4 + 2 * half; u < cs16; u += 4) {      // records longer than 64 bytes
+                        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+                        if (on) { x0 = __ldcg(crec + u); x1 = __ldcg(crec + u + 1); }
+                        c += count_groups(u, isn, x0, blo, bhi, boff, W, L) + count_groups(u + 1, isn, x1, blo, bhi, boff, W, L);
                     }
-#pragma unroll
-                    for (int g = 0; g < PGM_G; g++) {
-                        // header of the record (lane 0 of the quad holds it)
-                        const uint32_t st_lo = __shfl_sync(PGM_FULL, v[g].x, qb), st_hi = __shfl_sync(PGM_FULL, v[g].y, qb);
-                        const uint32_t bk_lo = __shfl_sync(PGM_FULL, v[g].z, qb), bk_hi = __shfl_sync(PGM_FULL, v[g].w, qb);
+                    c += __shfl_xor_sync(PGM_FULL, c, 1);
+                    if (half == 0 && on) {
                         // body of DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:301-331) up to the decision
+                        n_cand++;
+                        const uint32_t st_lo = v.v[0], st_hi = v.v[1];
                         const uint32_t c_in = st_hi >> 24;
-                        const uint64_t gpos = tile_g0 + cpos[g];
-                        const uint32_t shift = cj[g] * p.seed_len;
-                        const uint32_t L = p.reads.read_len;
-                        bool ok = on[g] && c_in > p.min_mm && (uint64_t)shift <= gpos;             // :304, :308
-                        const uint64_t a = ok ? gpos - shift : tile_g0;
-                        ok = ok && a + L <= p.pg_len;                                              // :311
-                        const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;                 // :313,:326 (matchingLength == readLength)
-                        const bool has_pos = c_in != 255u;
-                        const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
-                        const bool same_pos = has_pos && st_pos == rep;                            // coordinate-only compare, :313
-                        const int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;                 // :315
-                        const uint32_t boff = ok ? (uint32_t)((int64_t)(a - p.slice_origin) - buf_bit0) : 0u;
-                        int c = count_groups(q, isn[g], v[g], blo, bhi, boff, p.reads.W, L);
-                        for (uint32_t u = q + 4; u < cs16[g]; u += 4) {
-                            uint4 x = make_uint4(0, 0, 0, 0);
-                            if (ok) x = __ldcg(crec[g] + u);
-                            c += count_groups(u, isn[g], x, blo, bhi, boff, p.reads.W, L);
-                        }
-                        c = quad_sum(c);
-                        if (q == 0 && on[g]) {
-                            n_cand++;
-                            if (ok) {
+                        const uint64_t gpos = tile_g0 + cpos;
+                        if (c_in > p.min_mm && (uint64_t)shift <= gpos) {                              // :304, :308
+                            const uint64_t a = gpos - shift;
+                            if (a + L <= p.pg_len) {                                                   // :311
                                 n_ver++;
+                                const bool has_pos = c_in != 255u;
+                                const int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;             // :315
                                 if (c <= limit) {
                                     n_acc++;
-                                    const unsigned long long order = (gpos << 8) | (unsigned long long)(p.parts - 1 - cj[g]);
-                                    if (!same_pos) {
+                                    const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;         // :313,:326 (matchingLength == readLength)
+                                    const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
+                                    const unsigned long long order = (gpos << 8) | (unsigned long long)(p.parts - 1 - cj);
+                                    if (!(has_pos && st_pos == rep)) {                                 // coordinate-only compare, :313
                                         const unsigned long long cls = (uint32_t)c <= p.min_mm ? 0ull : (unsigned long long)c;
                                         const long long key = (long long)((cls << 56) | (order << 8) | (unsigned long long)c);
-                                        const long long seen = (long long)(((uint64_t)bk_hi << 32) | bk_lo);   // never below the live value
-                                        if (key < seen) atomicMin(reinterpret_cast<long long *>(crec[g]) + 1, key);
+                                        const long long seen = (long long)(((uint64_t)v.v[3] << 32) | v.v[2]);   // never below the live value
+                                        if (key < seen) atomicMin(reinterpret_cast<long long *>(crec) + 1, key);
                                         if (has_pos) {
-                                            atomicMin(p.pr.first_other_order + cr[g], (long long)order);
+                                            atomicMin(p.pr.first_other_order + cr, (long long)order);
                                             *p.pr.touched = 1;
                                         }
                                     } else {
-                                        atomicOr(p.pr.same_pos_mask + cr[g], 1 << cj[g]);
-                                        p.pr.same_pos_mm[cr[g]] = (uint8_t)c;
+                                        atomicOr(p.pr.same_pos_mask + cr, 1 << cj);
+                                        p.pr.same_pos_mm[cr] = (uint8_t)c;
                                         *p.pr.touched = 1;
                                     }
                                 }
@@ -759,24 +734,16 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
                         }
                     }
                     // hot keys: walk the chain behind the slot
-                    again = false;
-#pragma unroll
-                    for (int g = 0; g < PGM_G; g++) {
-                        if (on[g] && chain[g]) {
-                            cpat[g] = __ldg(p.tab.next + cpat[g]);
-                            on[g] = cpat[g] != PGM_NIL;
-                        } else on[g] = false;
-                        again |= on[g];
-                    }
-                    again = __ballot_sync(PGM_FULL, again) != 0;
+                    if (on && chain) {
+                        cpat = __ldg(p.tab.next + cpat);
+                        on = cpat != PGM_NIL;
+                    } else on = false;
+                    again = __ballot_sync(PGM_FULL, on) != 0;
                 } while (again);
             }
             __syncwarp();
             wcount = 0;
-            bool any = false;
-#pragma unroll
-            for (int g = 0; g < PGM_G; g++) any |= act[g];
-            if (exhausted && !__ballot_sync(PGM_FULL, any)) break;
+            if (exhausted && !__ballot_sync(PGM_FULL, act)) break;
         }
         __syncthreads();
         buf ^= 1;
