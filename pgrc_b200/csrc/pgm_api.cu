@@ -190,7 +190,9 @@ uint32_t next_prime(uint64_t v) {
 
 template <int NCH>
 void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s) {
-    pgm::scan_kernel<NCH><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    // FAST: only ACGT reads, records of exactly 64 bytes (read length <= 192)
+    if (sp.reads.n_n == 0 && sp.reads.lq_stride16 == 4) pgm::scan_kernel<NCH, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    else pgm::scan_kernel<NCH, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
 }
 
 } // namespace

@@ -526,7 +526,7 @@ __device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, cons
 //      atomicMin's the key inside the record.  Restates iterateOver/moveNext (HashMatcher.h:42-68) +
 //      executeMatching (ReadsMatchers.cpp:297-341) without their sequential order; the decision is deferred to
 //      resolve_kernel.
-template <int NCH>
+template <int NCH, bool FAST>
 __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_constant__ ScanParams p) {
     __shared__ __align__(128) ScanShared sm;
     const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
@@ -667,79 +667,180 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
                 else if (act) { pb += pstep; if (pb >= p.tab.n_buckets) pb -= p.tab.n_buckets; }
             }
             __syncwarp();
-            // consume: one lane pair per candidate; each lane fetches one 32-byte half of the 64-byte record
             const uint32_t half = lane & 1u;
-            for (uint32_t i0 = 0; i0 < wcount; i0 += 16) {
-                const uint32_t i = i0 + (lane >> 1);
-                bool on = i < wcount;
-                const uint2 e = on ? wq[i] : make_uint2(0, 0);
-                const uint32_t cpos = e.x & 0x7FFFFFFFu;
-                const bool chain = (e.x >> 31) != 0;
-                uint32_t cpat = e.y;
-                bool again;
-                do {
-                    const uint32_t cr = cpat >> p.reads.part_bits, cj = cpat & pmask;
-                    uint32_t cs16; bool isn;
-                    uint4 *crec = record_of(p.reads, cr, cs16, isn);
-                    u32x8 v;
+            if constexpr (FAST) {
+                // consume (ACGT set, 64-byte records): every lane owns one candidate; the two lanes of a pair fetch the
+                // even lane's record together (one instruction = one 64-byte request), then the odd lane's, and swap
+                // the halves they fetched for each other.
+                for (uint32_t i0 = 0; i0 < wcount; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    bool on = i < wcount;
+                    const uint2 e = on ? wq[i] : make_uint2(0, 0);
+                    const uint32_t cpos = e.x & 0x7FFFFFFFu;
+                    const bool chain = (e.x >> 31) != 0;
+                    uint32_t cpat = e.y;
+                    const uint32_t pat_o = __shfl_xor_sync(PGM_FULL, cpat, 1);
+                    const bool on_o = __shfl_xor_sync(PGM_FULL, (int)on, 1) != 0;
+                    const uint32_t patA = half ? pat_o : cpat, patB = half ? cpat : pat_o;
+                    const bool onA = half ? on_o : on, onB = half ? on : on_o;
+                    const u32x8 *recA = reinterpret_cast<const u32x8 *>(p.reads.lq) + (size_t)(patA >> p.reads.part_bits) * 2 + half;
+                    const u32x8 *recB = reinterpret_cast<const u32x8 *>(p.reads.lq) + (size_t)(patB >> p.reads.part_bits) * 2 + half;
+                    u32x8 rA, rB;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v.v[k] = 0;
-                    if (on) v = hints ? ld256_stream_hint(reinterpret_cast<const u32x8 *>(crec) + half, pol_stream)
-                                      : ld256_cg(reinterpret_cast<const u32x8 *>(crec) + half);
-                    // tile-relative alignment: always inside the staged buffer, so the count needs no validity checks
-                    const uint32_t shift = cj * p.seed_len;
-                    const uint32_t boff = PGM_HALO_L * 32 + cpos - (on ? shift : 0u);
-                    const uint32_t L = p.reads.read_len, W = p.reads.W;
-                    int c = count_groups(2 * half, isn, make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]), blo, bhi, boff, W, L)
-                          + count_groups(2 * half + 1, isn, make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]), blo, bhi, boff, W, L);
-                    for (uint32_t u = 4 + 2 * half; u < cs16; u += 4) {      // records longer than 64 bytes
-                        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
-                        if (on) { x0 = __ldcg(crec + u); x1 = __ldcg(crec + u + 1); }
-                        c += count_groups(u, isn, x0, blo, bhi, boff, W, L) + count_groups(u + 1, isn, x1, blo, bhi, boff, W, L);
+                    for (int k = 0; k < 8; k++) { rA.v[k] = 0; rB.v[k] = 0; }
+                    if (onA) rA = hints ? ld256_stream_hint(recA, pol_stream) : ld256_cg(recA);
+                    if (onB) rB = hints ? ld256_stream_hint(recB, pol_stream) : ld256_cg(recB);
+                    uint32_t s0[8], s1[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t got = __shfl_xor_sync(PGM_FULL, half ? rA.v[k] : rB.v[k], 1);
+                        s0[k] = half ? got : rA.v[k];      // first 32 bytes of this lane's record: header, groups 0-1
+                        s1[k] = half ? rB.v[k] : got;      // second 32 bytes: groups 2-5
                     }
-                    c += __shfl_xor_sync(PGM_FULL, c, 1);
-                    if (half == 0 && on) {
-                        // body of DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:301-331) up to the decision
-                        n_cand++;
-                        const uint32_t st_lo = v.v[0], st_hi = v.v[1];
-                        const uint32_t c_in = st_hi >> 24;
-                        const uint64_t gpos = tile_g0 + cpos;
-                        if (c_in > p.min_mm && (uint64_t)shift <= gpos) {                              // :304, :308
-                            const uint64_t a = gpos - shift;
-                            if (a + L <= p.pg_len) {                                                   // :311
-                                n_ver++;
-                                const bool has_pos = c_in != 255u;
-                                const int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;             // :315
-                                if (c <= limit) {
-                                    n_acc++;
-                                    const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;         // :313,:326 (matchingLength == readLength)
-                                    const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
-                                    const unsigned long long order = (gpos << 8) | (unsigned long long)(p.parts - 1 - cj);
-                                    if (!(has_pos && st_pos == rep)) {                                 // coordinate-only compare, :313
-                                        const unsigned long long cls = (uint32_t)c <= p.min_mm ? 0ull : (unsigned long long)c;
-                                        const long long key = (long long)((cls << 56) | (order << 8) | (unsigned long long)c);
-                                        const long long seen = (long long)(((uint64_t)v.v[3] << 32) | v.v[2]);   // never below the live value
-                                        if (key < seen) atomicMin(reinterpret_cast<long long *>(crec) + 1, key);
-                                        if (has_pos) {
-                                            atomicMin(p.pr.first_other_order + cr, (long long)order);
+                    uint32_t cr = cpat >> p.reads.part_bits, cj = cpat & pmask;
+                    for (;;) {
+                        const uint32_t L = p.reads.read_len;
+                        const uint32_t shift = on ? cj * p.seed_len : 0u;
+                        // tile-relative alignment: always inside the staged buffer, so the count needs no validity checks
+                        const uint32_t boff = PGM_HALO_L * 32 + cpos - shift;
+                        const uint32_t tw = boff >> 5, ts = boff & 31u;
+                        int c = 0;
+#pragma unroll
+                        for (int g = 0; g < 6; g++) {
+                            if ((uint32_t)g < p.reads.W) {
+                                const uint32_t rl = g < 2 ? s0[4 + 2 * g] : s1[2 * (g - 2)], rh = g < 2 ? s0[5 + 2 * g] : s1[2 * (g - 2) + 1];
+                                const uint32_t tl = __funnelshift_r(blo[tw + g], blo[tw + g + 1], ts);
+                                const uint32_t th = __funnelshift_r(bhi[tw + g], bhi[tw + g + 1], ts);
+                                uint32_t diff = (rl ^ tl) | (rh ^ th);
+                                const uint32_t rem = L - 32 * g;
+                                if (rem < 32) diff &= (1u << rem) - 1u;
+                                c += __popc(diff);
+                            }
+                        }
+                        if (on) {
+                            // body of DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:301-331) up to the decision
+                            n_cand++;
+                            const uint32_t st_lo = s0[0], st_hi = s0[1];
+                            const uint32_t c_in = st_hi >> 24;
+                            const uint64_t gpos = tile_g0 + cpos;
+                            if (c_in > p.min_mm && (uint64_t)shift <= gpos) {                              // :304, :308
+                                const uint64_t a = gpos - shift;
+                                if (a + L <= p.pg_len) {                                                   // :311
+                                    n_ver++;
+                                    const bool has_pos = c_in != 255u;
+                                    const int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;             // :315
+                                    if (c <= limit) {
+                                        n_acc++;
+                                        const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;         // :313,:326 (matchingLength == readLength)
+                                        const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
+                                        const unsigned long long order = (gpos << 8) | (unsigned long long)(p.parts - 1 - cj);
+                                        if (!(has_pos && st_pos == rep)) {                                 // coordinate-only compare, :313
+                                            const unsigned long long cls = (uint32_t)c <= p.min_mm ? 0ull : (unsigned long long)c;
+                                            const long long key = (long long)((cls << 56) | (order << 8) | (unsigned long long)c);
+                                            const long long seen = (long long)(((uint64_t)s0[3] << 32) | s0[2]);   // never below the live value
+                                            if (key < seen) atomicMin(reinterpret_cast<long long *>(p.reads.lq + (size_t)cr * 4) + 1, key);
+                                            if (has_pos) {
+                                                atomicMin(p.pr.first_other_order + cr, (long long)order);
+                                                *p.pr.touched = 1;
+                                            }
+                                        } else {
+                                            atomicOr(p.pr.same_pos_mask + cr, 1 << cj);
+                                            p.pr.same_pos_mm[cr] = (uint8_t)c;
                                             *p.pr.touched = 1;
                                         }
-                                    } else {
-                                        atomicOr(p.pr.same_pos_mask + cr, 1 << cj);
-                                        p.pr.same_pos_mm[cr] = (uint8_t)c;
-                                        *p.pr.touched = 1;
                                     }
                                 }
                             }
                         }
+                        // hot keys: walk the chain behind the slot (this lane alone fetches the next record)
+                        if (on && chain) {
+                            cpat = __ldg(p.tab.next + cpat);
+                            on = cpat != PGM_NIL;
+                        } else on = false;
+                        if (!__ballot_sync(PGM_FULL, on)) break;
+                        cr = cpat >> p.reads.part_bits; cj = cpat & pmask;
+                        if (on) {
+                            const u32x8 *rec = reinterpret_cast<const u32x8 *>(p.reads.lq) + (size_t)cr * 2;
+                            const u32x8 x0 = ld256_cg(rec), x1 = ld256_cg(rec + 1);
+#pragma unroll
+                            for (int k = 0; k < 8; k++) { s0[k] = x0.v[k]; s1[k] = x1.v[k]; }
+                        }
                     }
-                    // hot keys: walk the chain behind the slot
-                    if (on && chain) {
-                        cpat = __ldg(p.tab.next + cpat);
-                        on = cpat != PGM_NIL;
-                    } else on = false;
-                    again = __ballot_sync(PGM_FULL, on) != 0;
-                } while (again);
+                }
+            } else {
+                // consume: one lane pair per candidate; each lane fetches one 32-byte half of the 64-byte record
+                    for (uint32_t i0 = 0; i0 < wcount; i0 += 16) {
+                    const uint32_t i = i0 + (lane >> 1);
+                    bool on = i < wcount;
+                    const uint2 e = on ? wq[i] : make_uint2(0, 0);
+                    const uint32_t cpos = e.x & 0x7FFFFFFFu;
+                    const bool chain = (e.x >> 31) != 0;
+                    uint32_t cpat = e.y;
+                    bool again;
+                    do {
+                        const uint32_t cr = cpat >> p.reads.part_bits, cj = cpat & pmask;
+                        uint32_t cs16; bool isn;
+                        uint4 *crec = record_of(p.reads, cr, cs16, isn);
+                        u32x8 v;
+    #pragma unroll
+                        for (int k = 0; k < 8; k++) v.v[k] = 0;
+                        if (on) v = hints ? ld256_stream_hint(reinterpret_cast<const u32x8 *>(crec) + half, pol_stream)
+                                          : ld256_cg(reinterpret_cast<const u32x8 *>(crec) + half);
+                        // tile-relative alignment: always inside the staged buffer, so the count needs no validity checks
+                        const uint32_t shift = cj * p.seed_len;
+                        const uint32_t boff = PGM_HALO_L * 32 + cpos - (on ? shift : 0u);
+                        const uint32_t L = p.reads.read_len, W = p.reads.W;
+                        int c = count_groups(2 * half, isn, make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]), blo, bhi, boff, W, L)
+                              + count_groups(2 * half + 1, isn, make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]), blo, bhi, boff, W, L);
+                        for (uint32_t u = 4 + 2 * half; u < cs16; u += 4) {      // records longer than 64 bytes
+                            uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+                            if (on) { x0 = __ldcg(crec + u); x1 = __ldcg(crec + u + 1); }
+                            c += count_groups(u, isn, x0, blo, bhi, boff, W, L) + count_groups(u + 1, isn, x1, blo, bhi, boff, W, L);
+                        }
+                        c += __shfl_xor_sync(PGM_FULL, c, 1);
+                        if (half == 0 && on) {
+                            // body of DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:301-331) up to the decision
+                            n_cand++;
+                            const uint32_t st_lo = v.v[0], st_hi = v.v[1];
+                            const uint32_t c_in = st_hi >> 24;
+                            const uint64_t gpos = tile_g0 + cpos;
+                            if (c_in > p.min_mm && (uint64_t)shift <= gpos) {                              // :304, :308
+                                const uint64_t a = gpos - shift;
+                                if (a + L <= p.pg_len) {                                                   // :311
+                                    n_ver++;
+                                    const bool has_pos = c_in != 255u;
+                                    const int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;             // :315
+                                    if (c <= limit) {
+                                        n_acc++;
+                                        const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;         // :313,:326 (matchingLength == readLength)
+                                        const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
+                                        const unsigned long long order = (gpos << 8) | (unsigned long long)(p.parts - 1 - cj);
+                                        if (!(has_pos && st_pos == rep)) {                                 // coordinate-only compare, :313
+                                            const unsigned long long cls = (uint32_t)c <= p.min_mm ? 0ull : (unsigned long long)c;
+                                            const long long key = (long long)((cls << 56) | (order << 8) | (unsigned long long)c);
+                                            const long long seen = (long long)(((uint64_t)v.v[3] << 32) | v.v[2]);   // never below the live value
+                                            if (key < seen) atomicMin(reinterpret_cast<long long *>(crec) + 1, key);
+                                            if (has_pos) {
+                                                atomicMin(p.pr.first_other_order + cr, (long long)order);
+                                                *p.pr.touched = 1;
+                                            }
+                                        } else {
+                                            atomicOr(p.pr.same_pos_mask + cr, 1 << cj);
+                                            p.pr.same_pos_mm[cr] = (uint8_t)c;
+                                            *p.pr.touched = 1;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        // hot keys: walk the chain behind the slot
+                        if (on && chain) {
+                            cpat = __ldg(p.tab.next + cpat);
+                            on = cpat != PGM_NIL;
+                        } else on = false;
+                        again = __ballot_sync(PGM_FULL, on) != 0;
+                    } while (again);
+                }
             }
             __syncwarp();
             wcount = 0;

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Per-region instruction counts of a kernel from an ncu report (source page, needs -lineinfo):
-    python tools/ncu_lines.py report.ncu-rep [top_n]"""
+    python tools/ncu_lines.py report.ncu-rep [top_n] [kernel regex]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kern = sys.argv[3] if len(sys.argv) > 3 else "scan_kernel"
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:" + kern, "-c", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 his = [i for i, r in enumerate(rows) if r and r[0] == 'Line No']
 hi = his[0]; end = his[1] if len(his) > 1 else len(rows)
