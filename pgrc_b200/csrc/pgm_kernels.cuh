@@ -628,20 +628,28 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
         for (;;) {
             // produce: one lane per filter-positive position, one 256-bit load per probed bucket
             while (wcount + PGM_WQ_ROUND <= PGM_WQ_CAP) {
-                if (!__ballot_sync(PGM_FULL, act)) {
-                    if (exhausted) break;
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&sm.q1_cursor[buf], 32u);
-                    base = __shfl_sync(PGM_FULL, base, 0);
-                    if (base >= q1n) { exhausted = true; break; }
-                    act = base + lane < q1n;
-                    ppos = act ? sm.q1[base + lane] : 0u;
-                    const uint64_t hv = window_hash<NCH>(slo, shi, ppos, p.tail_mask);
-                    const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
-                    ptag = seed_tag(h2);
-                    pb = __umulhi(h1, p.tab.n_buckets);
-                    pstep = 1u + __umulhi(h2 * 0x9E3779B1u, p.tab.n_buckets - 1u);
+                // idle lanes (probe sequence finished) take the next positives from the list
+                if (!exhausted) {
+                    const uint32_t idle = __ballot_sync(PGM_FULL, !act);
+                    if (idle) {
+                        const uint32_t n_idle = __popc(idle);
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&sm.q1_cursor[buf], n_idle);
+                        base = __shfl_sync(PGM_FULL, base, 0);
+                        const uint32_t mine = base + __popc(idle & lt_mask);
+                        if (!act && mine < q1n) {
+                            act = true;
+                            ppos = sm.q1[mine];
+                            const uint64_t hv = window_hash<NCH>(slo, shi, ppos, p.tail_mask);
+                            const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
+                            ptag = seed_tag(h2);
+                            pb = __umulhi(h1, p.tab.n_buckets);
+                            pstep = 1u + __umulhi(h2 * 0x9E3779B1u, p.tab.n_buckets - 1u);
+                        }
+                        if (base + n_idle >= q1n) exhausted = true;
+                    }
                 }
+                if (!__ballot_sync(PGM_FULL, act)) break;
                 u32x8 s;
 #pragma unroll
                 for (int k = 0; k < 8; k++) s.v[k] = 0;

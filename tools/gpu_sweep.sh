@@ -1,0 +1,28 @@
+#!/bin/bash
+# Tuning sweep on the full C2 workload: prints per-kernel ms for each setting.
+TAG=${1:-sweep}
+OUT=gpurun_out
+mkdir -p $OUT
+run() {
+  timeout 300 python bench.py --no-cpu-baseline --no-e2e --steps 5 --warmup 2 "$@" > $OUT/tmp_sweep.json 2>> $OUT/sweep_$TAG.err
+  python - "$@" <<PY
+import json,sys
+try:
+    d=json.load(open("$OUT/tmp_sweep.json"))
+    k=d["roofline"]["kernel_ms_per_step"]
+    print(" ".join(sys.argv[1:]), "| ms/step", d["ms_per_step"], "scan", k["scan"], "build", k["build_table"], "pos", d["config"]["filter_positives_per_step"], "cand", d["config"]["candidates_per_step"])
+except Exception as e:
+    print(" ".join(sys.argv[1:]), "FAILED", e)
+PY
+}
+run
+run --l2-hints 0
+run --filter-bits 29
+run --filter-bits 27
+run --filter-bits 29 --l2-hints 0
+run --slots-per-pattern 3
+run --slots-per-pattern 4
+run --ctas-per-sm 3
+run --ctas-per-sm 5
+run --ctas-per-sm 6
+run --ctas-per-sm 8

@@ -21,7 +21,7 @@ src = open('/root/repo/pgrc_b200/csrc/pgm_kernels.cuh').read().split('\n')
 marks = {}
 pats = [('seed_hash64', 'uint64_t seed_hash64('), ('helpers', 'small helpers'), ('record_of', 'uint4 *record_of('), ('text kernels', 'text packing'),
         ('window_hash', 'uint64_t window_hash('), ('count_groups', 'int count_groups('), ('scan prologue', 'scan_kernel(const __grid_constant__'),
-        ('A1', '// ---- A1'), ('A2 produce', '// ---- A2 + B'), ('B consume', '// consume: verify'), ('chain', '// hot keys: walk'), ('epilogue', '// counters: warp reduce')]
+        ('A1', '// ---- A1'), ('A2 produce', '// ---- A2 + B'), ('B consume', 'const uint32_t half = lane & 1u;'), ('chain', '// hot keys: walk'), ('epilogue', '// counters: warp reduce')]
 for i, l in enumerate(src, 1):
     for name, pat in pats:
         if pat in l and name not in marks: marks[name] = i
