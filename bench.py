@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     # kernel tuning knobs (pgm_set_tuning); defaults = the library's
     ap.add_argument("--filter-bits", type=int, default=-1)
-    ap.add_argument("--slots-per-pattern", type=int, default=2)
+    ap.add_argument("--slots-per-pattern", type=int, default=3)
     ap.add_argument("--ctas-per-sm", type=int, default=4)
     ap.add_argument("--l2-hints", type=int, default=1)
     return ap.parse_args()

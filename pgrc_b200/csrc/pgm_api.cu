@@ -41,7 +41,7 @@ struct pgm_ctx {
 
     // tuning
     int filter_log2_bits = -1; // -1 = auto
-    int slots_per_pattern = 2;
+    int slots_per_pattern = 3;
     int ctas_per_sm = 4;
     int l2_hints = 1;
 
@@ -56,6 +56,7 @@ struct pgm_ctx {
     bool has_reads = false;
     bool state_fresh = false;   // record headers are {unmatched, no key} (just unpacked)
     bool aux_clean = false;     // first_order / same_mask / same_mm hold their neutral values
+    bool outputs_valid = false; // out_pos / out_rc / out_mm / hist reflect the current record states
 
     // per read (outside the records: rarely touched)
     DevBuf first_order, same_mask, same_mm, touched, keys;
@@ -419,13 +420,14 @@ int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq, const u
             src = st;
         }
         const unsigned int threads = 128;
-        KLAUNCH(PGM_K_UNPACK_READS, "unpack_reads_kernel", pgm::unpack_reads_kernel<<<grid_for(pt.cnt, threads), threads, threads * pt.plen, ctx->stream>>>(
+        KLAUNCH(PGM_K_UNPACK_READS, "unpack_reads_kernel", pgm::unpack_reads_kernel<<<grid_for(pt.cnt, threads), threads, ((threads * pt.plen + 15) & ~15u) + threads * pt.stride16 * 16, ctx->stream>>>(
             src, pt.cnt, read_len, pt.plen, pt.with_n, pt.dst, pt.stride16, W));
     }
     ctx->n_lq = n_lq; ctx->n_n = n_n; ctx->read_len = read_len; ctx->W = W;
     ctx->lq_stride16 = lq_stride16; ctx->n_stride16 = n_stride16;
     ctx->has_reads = true;
     ctx->state_fresh = true;
+    ctx->outputs_valid = false;
     ctx->phase_active = false;
     return PGM_OK;
 }
@@ -473,6 +475,7 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
         ctx->aux_clean = true;
     }
     ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
+    ctx->outputs_valid = false;
     if (n_patterns) {
         const uint32_t tail = seed_len % 32 ? (1u << (seed_len % 32)) - 1u : 0xFFFFFFFFu;
         const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(n, 256), (uint64_t)ctx->sm_count * 8);
@@ -524,6 +527,7 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
     const int nch = (int)((ctx->seed_len + 31) / 32);
     ctx->state_fresh = false;
     ctx->aux_clean = false;
+    ctx->outputs_valid = false;
     KLAUNCH(PGM_K_SCAN, "scan_kernel", switch (nch) {
         case 1: launch_scan<1>(sp, grid, ctx->stream); break;
         case 2: launch_scan<2>(sp, grid, ctx->stream); break;
@@ -566,17 +570,37 @@ int pgm_put_accumulators(pgm_ctx *ctx) {
     return PGM_OK;
 }
 
-int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode) {
-    if (!ctx) return PGM_ERR_INVALID_ARG;
+} // extern "C"
+
+namespace {
+// resolve (+ outputs and histogram when `fin`: the last pass of pgm_map_reads)
+int resolve_impl(pgm_ctx *ctx, int rev_mode, bool fin) {
     if (!ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_resolve_pass: pgm_match_begin has not been called");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->n_reads();
     if (!n) return PGM_OK;
-    KLAUNCH(PGM_K_RESOLVE, "resolve_kernel", pgm::resolve_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
-        reads_view(ctx), per_read(ctx), n, ctx->pg_len, ctx->seed_len, ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0));
+    if (fin) {
+        CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
+        KLAUNCH(PGM_K_RESOLVE, "resolve_kernel", pgm::resolve_kernel<true><<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), per_read(ctx), n, ctx->pg_len, ctx->seed_len, ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0,
+            ctx->out_pos.as<unsigned long long>(), ctx->out_rc.as<uint8_t>(), ctx->out_mm.as<uint8_t>(), ctx->hist.as<unsigned long long>()));
+        ctx->outputs_valid = true;
+    } else {
+        KLAUNCH(PGM_K_RESOLVE, "resolve_kernel", pgm::resolve_kernel<false><<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), per_read(ctx), n, ctx->pg_len, ctx->seed_len, ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0,
+            nullptr, nullptr, nullptr, nullptr));
+    }
     CU(cudaMemsetAsync(ctx->touched.p, 0, sizeof(int), ctx->stream));
     ctx->aux_clean = true;
     return PGM_OK;
+}
+} // namespace
+
+extern "C" {
+
+int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    return resolve_impl(ctx, rev_mode, false);
 }
 
 int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats) {
@@ -584,14 +608,19 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
     if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_get_results: no reads");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->n_reads();
-    CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
     if (n) {
-        KLAUNCH(PGM_K_FINALIZE, "finalize_kernel", pgm::finalize_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
-            reads_view(ctx), n, ctx->out_pos.as<unsigned long long>(), ctx->out_rc.as<uint8_t>(), ctx->out_mm.as<uint8_t>(),
-            ctx->hist.as<unsigned long long>()));
+        if (!ctx->outputs_valid) {
+            CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
+            KLAUNCH(PGM_K_FINALIZE, "finalize_kernel", pgm::finalize_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+                reads_view(ctx), n, ctx->out_pos.as<unsigned long long>(), ctx->out_rc.as<uint8_t>(), ctx->out_mm.as<uint8_t>(),
+                ctx->hist.as<unsigned long long>()));
+            ctx->outputs_valid = true;
+        }
         if (out_pos) CU(cudaMemcpyAsync(out_pos, ctx->out_pos.p, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
         if (out_rc) CU(cudaMemcpyAsync(out_rc, ctx->out_rc.p, n, cudaMemcpyDefault, ctx->stream));
         if (out_mm) CU(cudaMemcpyAsync(out_mm, ctx->out_mm.p, n, cudaMemcpyDefault, ctx->stream));
+    } else {
+        CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
     }
     unsigned long long h[257], cnt[16];
     int bad = 0;
@@ -634,19 +663,19 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
     const uint32_t cur_min = std::isupper((unsigned char)cur_mode) ? max_mm : 0;
     const uint32_t target_mm = L / cur_exact - 1;
     int rc;
-    auto run_passes = [&]() -> int {
+    auto run_passes = [&](bool last_phase) -> int {
         int r;
-        if ((r = pgm_scan_pass(ctx, 0)) || (r = pgm_resolve_pass(ctx, 0))) return r;
-        if (rev_compl && ((r = pgm_scan_pass(ctx, 1)) || (r = pgm_resolve_pass(ctx, 1)))) return r;
+        if ((r = pgm_scan_pass(ctx, 0)) || (r = resolve_impl(ctx, 0, last_phase && !rev_compl))) return r;
+        if (rev_compl && ((r = pgm_scan_pass(ctx, 1)) || (r = resolve_impl(ctx, 1, last_phase)))) return r;
         return PGM_OK;
     };
     if (L == cur_exact) rc = pgm_match_begin(ctx, L, 1, 0, 0, 0);                    // DefaultReadsExactMatcher (:718-722)
     else rc = pgm_match_begin(ctx, cur_exact, target_mm + 1, max_mm, cur_min, 0);     // DefaultReadsApproxMatcher (:724-727)
-    if (rc || (rc = run_passes())) return rc;
+    if (rc || (rc = run_passes(pre_exact == 0))) return rc;
     if (pre_exact > 0) {
         // second phase (:749-779); minMismatches comes from the FIRST phase's targetMismatches (:755)
         const uint32_t min2 = std::isupper((unsigned char)mode) ? max_mm : target_mm + 1;
-        if ((rc = pgm_match_begin(ctx, reads_exact, L / reads_exact, max_mm, min2, 1)) || (rc = run_passes())) return rc;
+        if ((rc = pgm_match_begin(ctx, reads_exact, L / reads_exact, max_mm, min2, 1)) || (rc = run_passes(true))) return rc;
     }
     return pgm_get_results(ctx, out_pos, out_rc, out_mm, stats);
 }

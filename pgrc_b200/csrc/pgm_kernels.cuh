@@ -74,8 +74,18 @@ __host__ __device__ __forceinline__ uint32_t seed_tag(uint32_t h2) {
     const uint32_t t = h2 & 0x7FFFFFFFu;
     return t == 0x7FFFFFFFu ? 0x7FFFFFFEu : t;   // 0x7FFFFFFF is what an empty slot shows
 }
-__host__ __device__ __forceinline__ uint32_t filter_bits(uint32_t h2) {
-    return (1u << (h2 >> 27)) | (1u << ((h2 >> 22) & 31u));
+// The pre-filter has its own, cheaper 32-bit hash of the canonical form (it is evaluated for EVERY text window; the
+// 64-bit key only for the windows that pass).  A weaker hash here can only cost extra table probes, never a result.
+__host__ __device__ __forceinline__ uint32_t filter_hash(uint32_t P, uint32_t Q, uint32_t R) {
+    const uint32_t q = Q * 0x85EBCA77u, r = R * 0xC2B2AE3Du;
+    uint32_t x = (P * 0x9E3779B1u) ^ ((q << 13) | (q >> 19)) ^ ((r << 7) | (r >> 25));
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t filter_bits(uint32_t f) {
+    return (1u << (f >> 27)) | (1u << ((f >> 22) & 31u));
 }
 
 // ------------------------------------------------------------------------------------------ parameters
@@ -279,8 +289,8 @@ __global__ void rc_text_kernel(const uint32_t *__restrict__ flo, const uint32_t 
 
 // ------------------------------------------------------------------------------------------ reads
 // Packed reads (reference layout, SymbolsPackingFacility.cpp:147-185) -> read records (layout above) with a
-// fresh header {unmatched, no key}.  A block stages its reads' packed bytes in shared memory with
-// coalesced loads; then one thread builds one record.
+// fresh header {unmatched, no key}.  A block stages its reads' packed bytes in shared memory with coalesced
+// loads, one thread builds one record in shared memory, and the block writes the records out coalesced.
 __global__ void unpack_reads_kernel(const uint8_t *__restrict__ packed, uint32_t n_reads, uint32_t read_len,
                                     uint32_t packed_len, int with_n, uint4 *__restrict__ recs, uint32_t stride16,
                                     uint32_t W) {
@@ -289,68 +299,78 @@ __global__ void unpack_reads_kernel(const uint8_t *__restrict__ packed, uint32_t
     const uint32_t nb = min(blockDim.x, n_reads - r0);
     const size_t g0 = (size_t)r0 * packed_len;
     const uint32_t bytes = nb * packed_len;
+    uint4 *sout = reinterpret_cast<uint4 *>(sbuf + ((blockDim.x * packed_len + 15) & ~15u));
     {   // head bytes up to 16-byte alignment, 16-byte body, tail bytes
         const uint8_t *src = packed + g0;
         const uint32_t head = min(bytes, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15));
         const uint32_t body = (bytes - head) & ~15u;
         for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) sbuf[i] = src[i];
-        for (uint32_t i = threadIdx.x * 16; i < body; i += blockDim.x * 16) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + head + i));
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if (head == 0) {
+            for (uint32_t i = threadIdx.x * 16; i < body; i += blockDim.x * 16)
+                *reinterpret_cast<uint4 *>(sbuf + i) = __ldg(reinterpret_cast<const uint4 *>(src + i));
+        } else {
+            for (uint32_t i = threadIdx.x * 16; i < body; i += blockDim.x * 16) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + head + i));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int k = 0; k < 16; k++) sbuf[head + i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+                for (int k = 0; k < 16; k++) sbuf[head + i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+            }
         }
         for (uint32_t i = head + body + threadIdx.x; i < bytes; i += blockDim.x) sbuf[i] = src[i];
     }
     __syncthreads();
-    if (threadIdx.x >= nb) return;
-    const uint8_t *src = sbuf + threadIdx.x * packed_len;
-    uint4 *dst = recs + (size_t)(r0 + threadIdx.x) * stride16;
-    dst[0] = make_uint4(0xFFFFFFFFu, 0xFF0000FFu, 0xFFFFFFFFu, 0x7FFFFFFFu);   // PGM_STATE_UNMATCHED, PGM_KEY_INF
-    if (!with_n) {
-        // bases 4b..4b+3 of byte b, first base in the two most significant bits; the tail of the last byte is 'A' = 0
-        for (uint32_t u = 1; u < stride16; u++) {
-            uint32_t w4[4] = {0, 0, 0, 0};
+    if (threadIdx.x < nb) {
+        const uint8_t *src = sbuf + threadIdx.x * packed_len;
+        uint4 *dst = sout + (size_t)threadIdx.x * stride16;
+        dst[0] = make_uint4(0xFFFFFFFFu, 0xFF0000FFu, 0xFFFFFFFFu, 0x7FFFFFFFu);   // PGM_STATE_UNMATCHED, PGM_KEY_INF
+        if (!with_n) {
+            // bases 4b..4b+3 of byte b, first base in the two most significant bits; the tail of the last byte is 'A' = 0
+            for (uint32_t u = 1; u < stride16; u++) {
+                uint32_t w4[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const uint32_t g = 2 * (u - 1) + half;
-                if (g < W) {
-                    uint32_t lo = 0, hi = 0;
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t g = 2 * (u - 1) + half;
+                    if (g < W) {
+                        uint32_t lo = 0, hi = 0;
 #pragma unroll
-                    for (int b = 0; b < 8; b++) {
-                        const uint32_t bi = g * 8 + b;
-                        const uint32_t v = bi < packed_len ? src[bi] : 0u;
-                        const uint32_t l4 = ((v >> 6) & 1) | (((v >> 4) & 1) << 1) | (((v >> 2) & 1) << 2) | ((v & 1) << 3);
-                        const uint32_t h4 = ((v >> 7) & 1) | (((v >> 5) & 1) << 1) | (((v >> 3) & 1) << 2) | (((v >> 1) & 1) << 3);
-                        lo |= l4 << (4 * b); hi |= h4 << (4 * b);
+                        for (int b = 0; b < 8; b++) {
+                            const uint32_t bi = g * 8 + b;
+                            const uint32_t v = bi < packed_len ? src[bi] : 0u;
+                            const uint32_t l4 = ((v >> 6) & 1) | (((v >> 4) & 1) << 1) | (((v >> 2) & 1) << 2) | ((v & 1) << 3);
+                            const uint32_t h4 = ((v >> 7) & 1) | (((v >> 5) & 1) << 1) | (((v >> 3) & 1) << 2) | (((v >> 1) & 1) << 3);
+                            lo |= l4 << (4 * b); hi |= h4 << (4 * b);
+                        }
+                        const uint32_t rem = read_len - 32 * g;
+                        if (rem < 32) { lo &= (1u << rem) - 1u; hi &= (1u << rem) - 1u; }
+                        w4[2 * half] = lo; w4[2 * half + 1] = hi;
                     }
-                    const uint32_t rem = read_len - 32 * g;
-                    if (rem < 32) { lo &= (1u << rem) - 1u; hi &= (1u << rem) - 1u; }
-                    w4[2 * half] = lo; w4[2 * half + 1] = hi;
                 }
+                dst[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
-            dst[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        }
-    } else {
-        uint32_t lo = 0, hi = 0, nm = 0, g = 0, bitpos = 0, p = 0;
-        for (uint32_t b = 0; b < packed_len; b++) {
-            const uint32_t v = src[b];
-            const uint32_t s[3] = {v / 25u, (v / 5u) % 5u, v % 5u};
+        } else {
+            uint32_t lo = 0, hi = 0, nm = 0, g = 0, bitpos = 0, p = 0;
+            for (uint32_t b = 0; b < packed_len; b++) {
+                const uint32_t v = src[b];
+                const uint32_t sy[3] = {v / 25u, (v / 5u) % 5u, v % 5u};
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                if (p < read_len) {
-                    const uint32_t sym = s[k];
-                    const uint32_t isn = sym == 3u ? 1u : 0u;
-                    const uint32_t code = sym == 4u ? 3u : (isn ? 0u : sym);
-                    lo |= (code & 1u) << bitpos; hi |= (code >> 1) << bitpos; nm |= isn << bitpos;
-                    p++; bitpos++;
-                    if (bitpos == 32) { dst[1 + g] = make_uint4(lo, hi, nm, 0); g++; lo = hi = nm = 0; bitpos = 0; }
+                for (int k = 0; k < 3; k++) {
+                    if (p < read_len) {
+                        const uint32_t sym = sy[k];
+                        const uint32_t isn = sym == 3u ? 1u : 0u;
+                        const uint32_t code = sym == 4u ? 3u : (isn ? 0u : sym);
+                        lo |= (code & 1u) << bitpos; hi |= (code >> 1) << bitpos; nm |= isn << bitpos;
+                        p++; bitpos++;
+                        if (bitpos == 32) { dst[1 + g] = make_uint4(lo, hi, nm, 0); g++; lo = hi = nm = 0; bitpos = 0; }
+                    }
                 }
             }
+            if (bitpos) { dst[1 + g] = make_uint4(lo, hi, nm, 0); g++; }
+            for (uint32_t u = 1 + g; u < stride16; u++) dst[u] = make_uint4(0, 0, 0, 0);
         }
-        if (bitpos) { dst[1 + g] = make_uint4(lo, hi, nm, 0); g++; }
-        for (uint32_t u = 1 + g; u < stride16; u++) dst[u] = make_uint4(0, 0, 0, 0);
     }
+    __syncthreads();
+    uint4 *out = recs + (size_t)r0 * stride16;
+    for (uint32_t i = threadIdx.x; i < nb * stride16; i += blockDim.x) out[i] = sout[i];
 }
 
 // ------------------------------------------------------------------------------------------ per-read state
@@ -411,7 +431,10 @@ __global__ void __launch_bounds__(256) build_table_kernel(ReadsView reads, Table
             const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
             const uint32_t tag = seed_tag(h2);
             const uint32_t pat = (r << reads.part_bits) | j;
-            if (tab.filter) atomicOr(tab.filter + (h1 & tab.filter_mask), filter_bits(h2));
+            if (tab.filter) {
+                const uint32_t f = filter_hash(P, Q, R);
+                atomicOr(tab.filter + (f & tab.filter_mask), filter_bits(f));
+            }
             uint32_t b = __umulhi(h1, tab.n_buckets);
             const uint32_t step = 1u + __umulhi(h2 * 0x9E3779B1u, tab.n_buckets - 1u);
             const unsigned long long mine = ((unsigned long long)tag << 32) | pat;
@@ -472,11 +495,12 @@ struct ScanShared {
     unsigned int q1_count[2], q1_cursor[2], tile[2];
 };
 
-// canonical form + hash of the seed window starting at tile position `pos` (text staged in shared memory)
+// canonical form of the seed window starting at tile position `pos` (text staged in shared memory)
 template <int NCH>
-__device__ __forceinline__ uint64_t window_hash(const uint32_t *slo, const uint32_t *shi, uint32_t pos, uint32_t tail_mask) {
+__device__ __forceinline__ void window_form(const uint32_t *slo, const uint32_t *shi, uint32_t pos, uint32_t tail_mask,
+                                            uint32_t &P, uint32_t &Q, uint32_t &R) {
     const uint32_t wi = pos >> 5, s = pos & 31u;
-    uint32_t P = 0, Q = 0, R = 0;
+    P = 0; Q = 0; R = 0;
     uint32_t la = slo[wi], ha = shi[wi];
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
@@ -486,6 +510,11 @@ __device__ __forceinline__ uint64_t window_hash(const uint32_t *slo, const uint3
         P ^= l; Q ^= h; R ^= (l & h);
         la = lb; ha = hb;
     }
+}
+template <int NCH>
+__device__ __forceinline__ uint64_t window_hash(const uint32_t *slo, const uint32_t *shi, uint32_t pos, uint32_t tail_mask) {
+    uint32_t P, Q, R;
+    window_form<NCH>(slo, shi, pos, tail_mask, P, Q, R);
     return seed_hash64(P, Q, R);
 }
 
@@ -529,7 +558,8 @@ __device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, cons
 template <int NCH, bool FAST>
 __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_constant__ ScanParams p) {
     __shared__ __align__(128) ScanShared sm;
-    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    // the warp index through a shuffle: lets the compiler treat it (and every branch on it) as warp-uniform
+    const uint32_t t = threadIdx.x, warp = __shfl_sync(PGM_FULL, t >> 5, 0), lane = t & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     unsigned long long n_cand = 0, n_ver = 0, n_acc = 0, n_pos = 0;
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
@@ -583,13 +613,14 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
 #pragma unroll 1
             for (uint32_t it0 = 0; it0 < PGM_WORDS_PER_WARP; it0 += U) {
                 const uint32_t pos0 = (w_first + it0) * 32;
-                if (pos0 >= ve || pos0 + 32 * U <= vb) continue;
                 uint32_t fm[U], fi[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const uint64_t hv = window_hash<NCH>(slo, shi, pos0 + 32 * u + lane, p.tail_mask);
-                    fi[u] = (uint32_t)hv & p.tab.filter_mask;
-                    fm[u] = filter_bits((uint32_t)(hv >> 32));
+                    uint32_t P, Q, R;
+                    window_form<NCH>(slo, shi, pos0 + 32 * u + lane, p.tail_mask, P, Q, R);
+                    const uint32_t f = filter_hash(P, Q, R);
+                    fi[u] = f & p.tab.filter_mask;
+                    fm[u] = filter_bits(f);
                 }
                 uint32_t fw[U];
 #pragma unroll
@@ -875,54 +906,77 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
 // only after the earliest of those — by the events of the alignment that reports X itself
 // (ReadsMatchers.cpp:313 skips them while X is still stored).  class = 0 for c <= minMismatches (the
 // reference stops updating a read there, :304), else c.
+// FIN: the last pass of a matcher call also writes the three archive-visible arrays and the histogram
+// (what finalize_kernel does), saving one sweep over the records.
+template <bool FIN>
 __global__ void resolve_kernel(ReadsView reads, PerRead pr, uint32_t n_reads, uint64_t pg_len, uint32_t seed_len,
-                               uint32_t parts, uint32_t max_mm, uint32_t min_mm, int rev_mode) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const uint32_t read_len = reads.read_len;
-    uint32_t stride16; bool is_n;
-    uint4 *rec = record_of(reads, r, stride16, is_n);
-    const uint4 h = __ldcg(rec);
-    const unsigned long long st = ((unsigned long long)h.y << 32) | h.x;
-    long long best = (long long)(((unsigned long long)h.w << 32) | h.z);
-    const int touched = *pr.touched;       // reset by the host after this kernel
-    long long o1 = PGM_KEY_INF;
-    int mask = 0;
-    uint32_t cx = 255;
-    if (touched) {
-        o1 = pr.first_other_order[r]; mask = pr.same_pos_mask[r]; cx = pr.same_pos_mm[r];
-        if (o1 != PGM_KEY_INF) pr.first_other_order[r] = PGM_KEY_INF;
-        if (mask) { pr.same_pos_mask[r] = 0; pr.same_pos_mm[r] = 255; }
+                               uint32_t parts, uint32_t max_mm, uint32_t min_mm, int rev_mode,
+                               unsigned long long *__restrict__ out_pos, uint8_t *__restrict__ out_rc,
+                               uint8_t *__restrict__ out_mm, unsigned long long *hist /*[257]*/) {
+    __shared__ unsigned int sh[256];
+    if (FIN) {
+        sh[threadIdx.x] = 0;
+        __syncthreads();
     }
-    if (best == PGM_KEY_INF && mask == 0) return;
-    unsigned long long new_st = st;
-    const uint32_t c_in = (uint32_t)(st >> 56);
-    if (c_in > min_mm) {
-        const int limit = c_in != 255u ? (int)c_in - 1 : (int)max_mm;
-        if (mask != 0 && (int)cx <= limit && o1 != PGM_KEY_INF) {
-            const uint64_t X = st & PGM_POS_MASK;
-            const uint64_t aX = rev_mode ? pg_len - X - read_len : X;   // that alignment in this pass's coordinates
-            for (uint32_t j = 0; j < parts; j++) {
-                if (!((mask >> j) & 1)) continue;
-                const unsigned long long order = ((aX + (uint64_t)j * seed_len) << 8) | (unsigned long long)(parts - 1 - j);
-                if ((long long)order > o1) {
-                    const unsigned long long cls = cx <= min_mm ? 0ull : (unsigned long long)cx;
-                    const long long key = (long long)((cls << 56) | (order << 8) | cx);
-                    best = min(best, key);
-                    break;
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_reads) {
+        const uint32_t read_len = reads.read_len;
+        uint32_t stride16; bool is_n;
+        uint4 *rec = record_of(reads, r, stride16, is_n);
+        const uint4 h = __ldcg(rec);
+        const unsigned long long st = ((unsigned long long)h.y << 32) | h.x;
+        long long best = (long long)(((unsigned long long)h.w << 32) | h.z);
+        const int touched = *pr.touched;       // reset by the host after this kernel
+        long long o1 = PGM_KEY_INF;
+        int mask = 0;
+        uint32_t cx = 255;
+        if (touched) {
+            o1 = pr.first_other_order[r]; mask = pr.same_pos_mask[r]; cx = pr.same_pos_mm[r];
+            if (o1 != PGM_KEY_INF) pr.first_other_order[r] = PGM_KEY_INF;
+            if (mask) { pr.same_pos_mask[r] = 0; pr.same_pos_mm[r] = 255; }
+        }
+        unsigned long long new_st = st;
+        if (best != PGM_KEY_INF || mask != 0) {
+            const uint32_t c_in = (uint32_t)(st >> 56);
+            if (c_in > min_mm) {
+                const int limit = c_in != 255u ? (int)c_in - 1 : (int)max_mm;
+                if (mask != 0 && (int)cx <= limit && o1 != PGM_KEY_INF) {
+                    const uint64_t X = st & PGM_POS_MASK;
+                    const uint64_t aX = rev_mode ? pg_len - X - read_len : X;   // that alignment in this pass's coordinates
+                    for (uint32_t j = 0; j < parts; j++) {
+                        if (!((mask >> j) & 1)) continue;
+                        const unsigned long long order = ((aX + (uint64_t)j * seed_len) << 8) | (unsigned long long)(parts - 1 - j);
+                        if ((long long)order > o1) {
+                            const unsigned long long cls = cx <= min_mm ? 0ull : (unsigned long long)cx;
+                            const long long key = (long long)((cls << 56) | (order << 8) | cx);
+                            best = min(best, key);
+                            break;
+                        }
+                    }
+                }
+                if (best != PGM_KEY_INF) {
+                    const uint32_t c = (uint32_t)(best & 0xFF);
+                    const uint32_t jj = (uint32_t)((best >> 8) & 0xFF);
+                    const uint64_t g = ((unsigned long long)best >> 16) & PGM_POS_MASK;
+                    const uint64_t a = g - (uint64_t)(parts - 1 - jj) * seed_len;
+                    const uint64_t rep = rev_mode ? pg_len - (a + read_len) : a;
+                    new_st = ((unsigned long long)c << 56) | ((unsigned long long)(rev_mode ? 1 : 0) << 55) | rep;
                 }
             }
+            rec[0] = make_uint4((uint32_t)new_st, (uint32_t)(new_st >> 32), 0xFFFFFFFFu, 0x7FFFFFFFu);
         }
-        if (best != PGM_KEY_INF) {
-            const uint32_t c = (uint32_t)(best & 0xFF);
-            const uint32_t jj = (uint32_t)((best >> 8) & 0xFF);
-            const uint64_t g = ((unsigned long long)best >> 16) & PGM_POS_MASK;
-            const uint64_t a = g - (uint64_t)(parts - 1 - jj) * seed_len;
-            const uint64_t rep = rev_mode ? pg_len - (a + read_len) : a;
-            new_st = ((unsigned long long)c << 56) | ((unsigned long long)(rev_mode ? 1 : 0) << 55) | rep;
+        if (FIN) {
+            const uint32_t c = (uint32_t)(new_st >> 56);
+            out_pos[r] = c == 255u ? 0xFFFFFFFFFFFFFFFFull : (new_st & PGM_POS_MASK);
+            out_rc[r] = (uint8_t)((new_st >> 55) & 1);
+            out_mm[r] = (uint8_t)c;
+            atomicAdd(&sh[c], 1u);
         }
     }
-    rec[0] = make_uint4((uint32_t)new_st, (uint32_t)(new_st >> 32), 0xFFFFFFFFu, 0x7FFFFFFFu);
+    if (FIN) {
+        __syncthreads();
+        if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
+    }
 }
 
 // state -> the three archive-visible arrays (+ matched count and per-mismatch histogram)
