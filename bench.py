@@ -243,7 +243,7 @@ def ours(args):
     torch.cuda.synchronize()
 
     m = matcher.GpuReadsMatcher(local, use_torch_stream=True)
-    m.set_tuning(args.filter_bits, args.slots_per_pattern, args.ctas_per_sm, bool(args.l2_hints))
+    m.set_tuning(args.filter_bits, args.slots_per_pattern, args.ctas_per_sm, args.l2_hints)
     plan = matcher.MatchPlan.derive(L, MATCH_KW["seed"], MATCH_KW["min_chars_per_mismatch"], MATCH_KW["mode"])
 
     # shard (N > 1)

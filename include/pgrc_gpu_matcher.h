@@ -172,8 +172,9 @@ typedef struct pgm_timings {
 int pgm_set_profiling(pgm_ctx *ctx, int on);
 int pgm_get_timings(pgm_ctx *ctx, pgm_timings *out);
 /* Tuning knobs; call before pgm_match_begin.  filter_log2_bits = 0 disables the L2-resident
- * pre-filter (< 0 = auto); slots_per_pattern sets the table size (>= 2); l2_hints = 1 loads the
- * filter with an L2 evict_last policy and table buckets / read records with evict_first. */
+ * pre-filter (< 0 = auto); slots_per_pattern sets the table size (>= 2); l2_hints: 0 = none, 1 = the
+ * filter is loaded with an L2 evict_last policy and table buckets / read records with evict_first,
+ * 2 = evict_first on buckets / records plus a persisting L2 access-policy window over the filter. */
 int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm, int l2_hints);
 
 #ifdef __cplusplus

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -21,7 +22,8 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-constexpr uint64_t TEXT_CHUNK_BASES = 64ull << 20; // ASCII staging chunk (multiple of 32)
+constexpr uint64_t TEXT_CHUNK_BASES = 16ull << 20; // H2D / pack chunk of the ASCII text (multiple of the tile size)
+constexpr uint32_t READS_CHUNK = 1u << 20;          // reads per H2D / unpack / table-build chunk
 
 } // namespace
 
@@ -43,12 +45,23 @@ struct pgm_ctx {
     int filter_log2_bits = -1; // -1 = auto
     int slots_per_pattern = 3;
     int ctas_per_sm = 4;
-    int l2_hints = 1;
+    int l2_hints = 1;           // 0 none, 1 per-load eviction hints, 2 hints + persisting access-policy window on the filter
+    size_t persist_max = 0, window_max = 0, persist_set = 0;
 
     // text
     DevBuf f_lo, f_hi, r_lo, r_hi, ascii_stage;
     uint64_t pg_len = 0, slice_begin = 0, slice_len = 0, own_begin = 0, own_end = 0;
     bool has_text = false;
+
+    // host inputs are uploaded lazily, in chunks on a copy stream, so that the H2D copies overlap the unpack /
+    // table-build / forward-scan kernels of the chunks that have already arrived (pgm_match_begin, pgm_scan_pass)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t fence_ev = nullptr;
+    std::vector<cudaEvent_t> text_ev, reads_ev;
+    const uint8_t *h_text = nullptr;
+    bool text_pending = false, text_copies_enqueued = false;
+    const uint8_t *h_lq = nullptr, *h_n = nullptr;
+    bool reads_pending = false;
 
     // reads: one record per read (header {state, key} + bit planes), see pgm_kernels.cuh
     DevBuf packed_stage, lq_recs, n_recs;
@@ -189,6 +202,157 @@ uint32_t next_prime(uint64_t v) {
     }
 }
 
+cudaEvent_t chunk_event(std::vector<cudaEvent_t> &pool, size_t i) {
+    while (pool.size() <= i) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        pool.push_back(e);
+    }
+    return pool[i];
+}
+
+// The copy stream may overwrite the staging buffers only after everything queued so far on the main stream
+// (the kernels of the previous call that read them) has finished.
+int fence_copy_stream(pgm_ctx *ctx) {
+    CU(cudaEventRecord(ctx->fence_ev, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->fence_ev, 0));
+    return PGM_OK;
+}
+
+uint64_t text_chunks(const pgm_ctx *ctx) { return (ctx->slice_len + TEXT_CHUNK_BASES - 1) / TEXT_CHUNK_BASES; }
+
+// Queue the H2D copies of a pending host text, chunk by chunk, on the copy stream.
+int enqueue_text_copies(pgm_ctx *ctx, bool fence) {
+    if (!ctx->text_pending || ctx->text_copies_enqueued) return PGM_OK;
+    if (fence) { int rc = fence_copy_stream(ctx); if (rc) return rc; }
+    for (uint64_t c = 0, off = 0; off < ctx->slice_len; c++, off += TEXT_CHUNK_BASES) {
+        const uint64_t n = std::min<uint64_t>(TEXT_CHUNK_BASES, ctx->slice_len - off);
+        CU(cudaMemcpyAsync(ctx->ascii_stage.as<uint8_t>() + off, ctx->h_text + off, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(chunk_event(ctx->text_ev, c), ctx->copy_stream));
+    }
+    ctx->text_copies_enqueued = true;
+    return PGM_OK;
+}
+
+// Pack chunk c of the text (device-resident source, or the staged copy of a pending host text) into the planes.
+int pack_text_chunk(pgm_ctx *ctx, const uint8_t *src_base, uint64_t c) {
+    const uint64_t off = c * TEXT_CHUNK_BASES;
+    const uint64_t n = std::min<uint64_t>(TEXT_CHUNK_BASES, ctx->slice_len - off);
+    uint32_t *flo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS, *fhi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
+    KLAUNCH(PGM_K_PACK_TEXT, "pack_text_kernel", pgm::pack_text_kernel<<<grid_for((n + 31) / 32, 256), 256, 0, ctx->stream>>>(
+        src_base + off, n, flo, fhi, off / 32, ctx->err_flag.as<int>()));
+    return PGM_OK;
+}
+
+int rc_text(pgm_ctx *ctx) {
+    if (!ctx->slice_len) return PGM_OK;
+    uint32_t *flo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS, *fhi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
+    uint32_t *rlo = ctx->r_lo.as<uint32_t>() + PGM_PAD_WORDS, *rhi = ctx->r_hi.as<uint32_t>() + PGM_PAD_WORDS;
+    KLAUNCH(PGM_K_RC_TEXT, "rc_text_kernel", pgm::rc_text_kernel<<<grid_for(plane_words(ctx->slice_len), 256), 256, 0, ctx->stream>>>(
+        flo, fhi, ctx->slice_len, rlo, rhi));
+    return PGM_OK;
+}
+
+// Complete a pending host-text upload without overlapping it with a scan.
+int finish_text_upload(pgm_ctx *ctx) {
+    if (!ctx->text_pending) return PGM_OK;
+    int rc = enqueue_text_copies(ctx, true);
+    if (rc) return rc;
+    for (uint64_t c = 0; c < text_chunks(ctx); c++) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->text_ev[c], 0));
+        if ((rc = pack_text_chunk(ctx, ctx->ascii_stage.as<uint8_t>(), c))) return rc;
+    }
+    ctx->text_pending = false;
+    return rc_text(ctx);
+}
+
+struct ReadsPart { const uint8_t *src; uint32_t cnt, plen, stride16; int with_n; uint4 *dst; uint32_t first_read; size_t stage_off; bool host; };
+
+void reads_parts(pgm_ctx *ctx, const uint8_t *lq, const uint8_t *nn, ReadsPart out[2]) {
+    const uint32_t lq_plen = (ctx->read_len + 3) / 4, n_plen = (ctx->read_len + 2) / 3;
+    const size_t lq_bytes = (size_t)ctx->n_lq * lq_plen;
+    out[0] = {lq, ctx->n_lq, lq_plen, ctx->lq_stride16, 0, ctx->lq_recs.as<uint4>(), 0, 0, ctx->n_lq && !is_device_ptr(lq)};
+    out[1] = {nn, ctx->n_n, n_plen, ctx->n_stride16, 1, ctx->n_recs.as<uint4>(), ctx->n_lq, (lq_bytes + 15) & ~(size_t)15,
+              ctx->n_n && !is_device_ptr(nn)};
+}
+
+int unpack_range(pgm_ctx *ctx, const ReadsPart &pt, const uint8_t *src, uint32_t first, uint32_t cnt) {
+    const unsigned int threads = 128;
+    KLAUNCH(PGM_K_UNPACK_READS, "unpack_reads_kernel",
+            pgm::unpack_reads_kernel<<<grid_for(cnt, threads), threads, ((threads * pt.plen + 15) & ~15u) + threads * pt.stride16 * 16, ctx->stream>>>(
+                src + (size_t)first * pt.plen, cnt, ctx->read_len, pt.plen, pt.with_n, pt.dst + (size_t)first * pt.stride16, pt.stride16, ctx->W));
+    return PGM_OK;
+}
+
+int build_range(pgm_ctx *ctx, uint32_t r_begin, uint32_t r_end, int continuation) {
+    if (r_end <= r_begin) return PGM_OK;
+    const uint32_t tail = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
+    const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(r_end - r_begin, 256), (uint64_t)ctx->sm_count * 8);
+    KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid, 256, 0, ctx->stream>>>(
+        reads_view(ctx), table_view(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail,
+        ctx->counters.as<unsigned long long>() + 4));
+    return PGM_OK;
+}
+
+// Upload + unpack pending host reads; when `build` the table inserts of a chunk follow its unpack, so both overlap
+// the H2D copy of the next chunk.  The pending text's copies are queued right behind the reads'.
+int upload_reads(pgm_ctx *ctx, bool build) {
+    if (!ctx->reads_pending) return PGM_OK;
+    ReadsPart parts[2];
+    reads_parts(ctx, ctx->h_lq, ctx->h_n, parts);
+    int rc = fence_copy_stream(ctx);
+    if (rc) return rc;
+    size_t ev = 0;
+    struct Chunk { int part; uint32_t first, cnt; size_t ev; };
+    std::vector<Chunk> chunks;
+    for (int k = 0; k < 2; k++) {
+        const ReadsPart &pt = parts[k];
+        for (uint32_t first = 0; first < pt.cnt; first += READS_CHUNK) {
+            const uint32_t cnt = std::min<uint32_t>(READS_CHUNK, pt.cnt - first);
+            if (pt.host) {
+                CU(cudaMemcpyAsync(ctx->packed_stage.as<uint8_t>() + pt.stage_off + (size_t)first * pt.plen, pt.src + (size_t)first * pt.plen,
+                                   (size_t)cnt * pt.plen, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CU(cudaEventRecord(chunk_event(ctx->reads_ev, ev), ctx->copy_stream));
+            }
+            chunks.push_back({k, first, cnt, ev});
+            ev++;
+        }
+    }
+    if ((rc = enqueue_text_copies(ctx, false))) return rc;
+    for (const Chunk &c : chunks) {
+        const ReadsPart &pt = parts[c.part];
+        const uint8_t *src = pt.src;
+        if (pt.host) {
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->reads_ev[c.ev], 0));
+            src = ctx->packed_stage.as<uint8_t>() + pt.stage_off;
+        }
+        if ((rc = unpack_range(ctx, pt, src, c.first, c.cnt))) return rc;
+        if (build && (rc = build_range(ctx, pt.first_read + c.first, pt.first_read + c.first + c.cnt, 0))) return rc;
+    }
+    ctx->reads_pending = false;
+    ctx->state_fresh = true;
+    return PGM_OK;
+}
+
+// L2 persisting window over the pre-filter for the kernels launched next on the context's stream
+int filter_window(pgm_ctx *ctx, bool on) {
+    if (ctx->l2_hints != 2 || !ctx->filter_words || !ctx->persist_max || !ctx->window_max) return PGM_OK;
+    const size_t bytes = std::min((size_t)ctx->filter_words * 4, ctx->window_max);
+    if (on && ctx->persist_set < std::min(bytes, ctx->persist_max)) {
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, ctx->persist_max)));
+        ctx->persist_set = std::min(bytes, ctx->persist_max);
+    }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.base_ptr = ctx->filter.p;
+    attr.accessPolicyWindow.num_bytes = on ? bytes : 0;
+    attr.accessPolicyWindow.hitRatio = on ? (float)std::min(1.0, (double)ctx->persist_set / (double)bytes) : 0.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return PGM_OK;
+}
+
 template <int NCH>
 void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s) {
     // FAST: only ACGT reads, records of exactly 64 bytes (read length <= 192)
@@ -225,11 +389,20 @@ int pgm_create(int device, pgm_ctx **out) {
     ctx = new pgm_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *g = getenv("PGM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob
+    ctx->persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+    ctx->window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete ctx;
         return cuda_fail(nullptr, e, "cudaStreamCreate");
     }
     ctx->own_stream = true;
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->fence_ev, cudaEventDisableTiming)) != cudaSuccess) {
+        cuda_fail(nullptr, e, "cudaStreamCreate (copy stream)");
+        pgm_destroy(ctx);
+        return PGM_ERR_CUDA;
+    }
     int rc;
     if ((rc = ensure(ctx, ctx->counters, 16 * sizeof(unsigned long long))) != PGM_OK ||
         (rc = ensure(ctx, ctx->hist, 257 * sizeof(unsigned long long))) != PGM_OK ||
@@ -249,6 +422,7 @@ int pgm_create(int device, pgm_ctx **out) {
 void pgm_destroy(pgm_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->f_lo, &ctx->f_hi, &ctx->r_lo, &ctx->r_hi, &ctx->ascii_stage, &ctx->packed_stage,
                       &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
@@ -257,6 +431,10 @@ void pgm_destroy(pgm_ctx *ctx) {
     for (DevBuf *b : bufs) release(*b);
     for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (cudaEvent_t e : ctx->ev_free) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->text_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->reads_ev) cudaEventDestroy(e);
+    if (ctx->fence_ev) cudaEventDestroy(ctx->fence_ev);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -287,7 +465,7 @@ int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, in
     ctx->filter_log2_bits = filter_log2_bits;
     ctx->slots_per_pattern = slots_per_pattern;
     ctx->ctas_per_sm = ctas_per_sm;
-    ctx->l2_hints = l2_hints ? 1 : 0;
+    ctx->l2_hints = l2_hints < 0 ? 0 : (l2_hints > 2 ? 2 : l2_hints);
     return PGM_OK;
 }
 
@@ -353,26 +531,21 @@ int pgm_set_text_shard(pgm_ctx *ctx, const char *slice, uint64_t slice_begin, ui
     CU(cudaMemsetAsync(ctx->f_hi.p, 0, pb, ctx->stream));
     CU(cudaMemsetAsync(ctx->r_lo.p, 0, pb, ctx->stream));
     CU(cudaMemsetAsync(ctx->r_hi.p, 0, pb, ctx->stream));
-    uint32_t *flo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS, *fhi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
-    uint32_t *rlo = ctx->r_lo.as<uint32_t>() + PGM_PAD_WORDS, *rhi = ctx->r_hi.as<uint32_t>() + PGM_PAD_WORDS;
-    const bool on_device = slice_len && is_device_ptr(slice);
-    if (!on_device && slice_len)
-        if ((rc = ensure(ctx, ctx->ascii_stage, (size_t)std::min<uint64_t>(slice_len, TEXT_CHUNK_BASES)))) return rc;
-    for (uint64_t off = 0; off < slice_len; off += TEXT_CHUNK_BASES) {
-        const uint64_t n = std::min<uint64_t>(TEXT_CHUNK_BASES, slice_len - off);
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(slice) + off;
-        if (!on_device) {
-            CU(cudaMemcpyAsync(ctx->ascii_stage.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
-            src = ctx->ascii_stage.as<uint8_t>();
-        }
-        KLAUNCH(PGM_K_PACK_TEXT, "pack_text_kernel", pgm::pack_text_kernel<<<grid_for((n + 31) / 32, 256), 256, 0, ctx->stream>>>(src, n, flo, fhi, off / 32, ctx->err_flag.as<int>()));
-    }
-    if (slice_len) {
-        KLAUNCH(PGM_K_RC_TEXT, "rc_text_kernel", pgm::rc_text_kernel<<<grid_for(plane_words(slice_len), 256), 256, 0, ctx->stream>>>(flo, fhi, slice_len, rlo, rhi));
-    }
     ctx->pg_len = pg_len; ctx->slice_begin = slice_begin; ctx->slice_len = slice_len;
     ctx->own_begin = own_begin; ctx->own_end = own_end;
     ctx->has_text = true;
+    ctx->text_pending = false; ctx->text_copies_enqueued = false; ctx->h_text = nullptr;
+    if (!slice_len) return PGM_OK;
+    if (is_device_ptr(slice)) {
+        for (uint64_t c = 0; c < text_chunks(ctx); c++)
+            if ((rc = pack_text_chunk(ctx, reinterpret_cast<const uint8_t *>(slice), c))) return rc;
+        return rc_text(ctx);
+    }
+    // host text: uploaded lazily (see pgm_match_begin / pgm_scan_pass); the caller keeps the buffer alive and
+    // unchanged until the call that returns the results has completed
+    if ((rc = ensure(ctx, ctx->ascii_stage, (size_t)slice_len))) return rc;
+    ctx->h_text = reinterpret_cast<const uint8_t *>(slice);
+    ctx->text_pending = true;
     return PGM_OK;
 }
 
@@ -390,7 +563,7 @@ int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq, const u
     const uint32_t W = (read_len + 31) / 32;
     // record = header uint4 + planes, rounded up to whole 64-byte requests
     const uint32_t lq_stride16 = (1 + (W + 1) / 2 + 3) & ~3u, n_stride16 = (1 + W + 3) & ~3u;
-    const uint32_t lq_plen = (read_len + 3) / 4, n_plen = (read_len + 2) / 3;
+    const uint32_t n_plen = (read_len + 2) / 3;
     int rc;
     if ((rc = ensure(ctx, ctx->lq_recs, (size_t)std::max<uint32_t>(n_lq, 1) * lq_stride16 * 16))) return rc;
     if ((rc = ensure(ctx, ctx->n_recs, (size_t)std::max<uint32_t>(n_n, 1) * n_stride16 * 16))) return rc;
@@ -400,36 +573,24 @@ int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq, const u
     if ((rc = ensure(ctx, ctx->first_order, n1 * 8)) || (rc = ensure(ctx, ctx->same_mask, n1 * 4)) ||
         (rc = ensure(ctx, ctx->same_mm, n1)) || (rc = ensure(ctx, ctx->out_pos, n1 * 8)) ||
         (rc = ensure(ctx, ctx->out_rc, n1)) || (rc = ensure(ctx, ctx->out_mm, n1))) return rc;
-    struct Part { const uint8_t *src; uint32_t cnt, plen, stride16; int with_n; uint4 *dst; };
-    Part partsv[2] = {{lq_packed, n_lq, lq_plen, lq_stride16, 0, ctx->lq_recs.as<uint4>()},
-                      {n_packed, n_n, n_plen, n_stride16, 1, ctx->n_recs.as<uint4>()}};
-    // both sets share one staging buffer (LQ first, 16-byte aligned start for the N set)
-    const size_t lq_bytes = (size_t)n_lq * lq_plen, n_bytes = (size_t)n_n * n_plen;
-    const size_t n_off = (lq_bytes + 15) & ~(size_t)15;
-    const bool stage_lq = n_lq && !is_device_ptr(lq_packed), stage_n = n_n && !is_device_ptr(n_packed);
-    if (stage_lq || stage_n)
-        if ((rc = ensure(ctx, ctx->packed_stage, n_off + n_bytes + 16))) return rc;
-    for (int k = 0; k < 2; k++) {
-        const Part &pt = partsv[k];
-        if (!pt.cnt) continue;
-        const size_t bytes = (size_t)pt.cnt * pt.plen;
-        const uint8_t *src = pt.src;
-        if (k == 0 ? stage_lq : stage_n) {
-            uint8_t *st = ctx->packed_stage.as<uint8_t>() + (k == 0 ? 0 : n_off);
-            CU(cudaMemcpyAsync(st, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-            src = st;
-        }
-        const unsigned int threads = 128;
-        KLAUNCH(PGM_K_UNPACK_READS, "unpack_reads_kernel", pgm::unpack_reads_kernel<<<grid_for(pt.cnt, threads), threads, ((threads * pt.plen + 15) & ~15u) + threads * pt.stride16 * 16, ctx->stream>>>(
-            src, pt.cnt, read_len, pt.plen, pt.with_n, pt.dst, pt.stride16, W));
-    }
     ctx->n_lq = n_lq; ctx->n_n = n_n; ctx->read_len = read_len; ctx->W = W;
     ctx->lq_stride16 = lq_stride16; ctx->n_stride16 = n_stride16;
     ctx->has_reads = true;
-    ctx->state_fresh = true;
+    ctx->state_fresh = false;
     ctx->outputs_valid = false;
     ctx->phase_active = false;
-    return PGM_OK;
+    ctx->h_lq = lq_packed; ctx->h_n = n_packed;
+    ReadsPart parts[2];
+    reads_parts(ctx, lq_packed, n_packed, parts);
+    if (parts[0].host || parts[1].host) {
+        // host reads: uploaded lazily, chunk by chunk, overlapped with unpacking and the table build
+        // (pgm_match_begin); both sets share one staging buffer
+        if ((rc = ensure(ctx, ctx->packed_stage, parts[1].stage_off + (size_t)n_n * n_plen + 16))) return rc;
+        ctx->reads_pending = true;
+        return PGM_OK;
+    }
+    ctx->reads_pending = true;      // device-resident reads: unpack now
+    return upload_reads(ctx, false);
 }
 
 int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm, int continuation) {
@@ -468,35 +629,34 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     }
     if (!continuation) CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
     else CU(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 4, 0, sizeof(unsigned long long), ctx->stream));
-    if (n && ((!continuation && !ctx->state_fresh) || !ctx->aux_clean)) {
+    ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
+    ctx->outputs_valid = false;
+    if (ctx->reads_pending && continuation && (rc = upload_reads(ctx, false))) return rc;   // (not a sensible call order)
+    const bool pipelined = ctx->reads_pending;
+    if (n && ((!continuation && !ctx->state_fresh && !pipelined) || !ctx->aux_clean)) {
+        // record headers are rewritten by the unpack kernels when the reads are still to be uploaded
         KLAUNCH(PGM_K_INIT_STATE, "reset_state_kernel", pgm::reset_state_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
-            reads_view(ctx), per_read(ctx), n, continuation ? 0 : 1));
+            reads_view(ctx), per_read(ctx), n, continuation ? 0 : 1, pipelined ? 0 : 1));
         CU(cudaMemsetAsync(ctx->touched.p, 0, sizeof(int), ctx->stream));
         ctx->aux_clean = true;
     }
-    ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
-    ctx->outputs_valid = false;
-    if (n_patterns) {
-        const uint32_t tail = seed_len % 32 ? (1u << (seed_len % 32)) - 1u : 0xFFFFFFFFu;
-        const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(n, 256), (uint64_t)ctx->sm_count * 8);
-        KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid, 256, 0, ctx->stream>>>(
-            reads_view(ctx), table_view(ctx), seed_len, parts, min_mm, continuation ? 1 : 0, tail,
-            ctx->counters.as<unsigned long long>() + 4));
+    if (pipelined) {
+        if ((rc = upload_reads(ctx, n_patterns != 0))) return rc;
+    } else if (n_patterns) {
+        if ((rc = build_range(ctx, 0, n, continuation ? 1 : 0))) return rc;
+        if ((rc = enqueue_text_copies(ctx, true))) return rc;      // start a pending text upload behind the build
     }
     ctx->phase_active = true;
     return PGM_OK;
 }
 
-int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
-    if (!ctx) return PGM_ERR_INVALID_ARG;
-    if (!ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_scan_pass: pgm_match_begin has not been called");
-    if (!ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_scan_pass: pgm_set_text has not been called");
-    CU(cudaSetDevice(ctx->device));
-    const uint64_t n = ctx->seed_len, pg = ctx->pg_len;
-    if (pg < n || ctx->n_reads() == 0) return PGM_OK;
-    // owned window starts of this pass (global coordinates of the pass's text)
-    uint64_t fb = ctx->own_begin, fe = std::min<uint64_t>(ctx->own_end, pg - n + 1);
+} // extern "C"
+
+namespace {
+// One scan launch over the seed-window starts [fb, fe) (FORWARD global coordinates) of the pass.
+int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
     if (fb >= fe) return PGM_OK;
+    const uint64_t n = ctx->seed_len, pg = ctx->pg_len;
     pgm::ScanParams sp;
     memset(&sp, 0, sizeof sp);
     if (!rev_mode) {
@@ -516,7 +676,8 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
     sp.seed_len = ctx->seed_len; sp.parts = ctx->parts; sp.max_mm = ctx->max_mm; sp.min_mm = ctx->min_mm;
     sp.tail_mask = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
     sp.rev_mode = rev_mode ? 1 : 0;
-    sp.l2_hints = ctx->l2_hints;
+    sp.l2_hints = ctx->l2_hints == 1 ? 1 : 0;      // window mode: plain filter loads, the window carries the policy
+    sp.stream_hints = ctx->l2_hints != 0;
     sp.tab = table_view(ctx);
     sp.reads = reads_view(ctx);
     sp.pr = per_read(ctx);
@@ -528,6 +689,7 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
     ctx->state_fresh = false;
     ctx->aux_clean = false;
     ctx->outputs_valid = false;
+    { int wrc = filter_window(ctx, true); if (wrc) return wrc; }
     KLAUNCH(PGM_K_SCAN, "scan_kernel", switch (nch) {
         case 1: launch_scan<1>(sp, grid, ctx->stream); break;
         case 2: launch_scan<2>(sp, grid, ctx->stream); break;
@@ -538,7 +700,43 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
         case 7: launch_scan<7>(sp, grid, ctx->stream); break;
         default: launch_scan<8>(sp, grid, ctx->stream); break;
     });
-    return PGM_OK;
+    return filter_window(ctx, false);
+}
+} // namespace
+
+extern "C" {
+
+int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_scan_pass: pgm_match_begin has not been called");
+    if (!ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_scan_pass: pgm_set_text has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->seed_len, pg = ctx->pg_len;
+    int rc;
+    if (pg < n || ctx->n_reads() == 0) return finish_text_upload(ctx);
+    // owned window starts of this pass (forward global coordinates)
+    const uint64_t fb = ctx->own_begin, fe = std::min<uint64_t>(ctx->own_end, pg - n + 1);
+    if (rev_mode || !ctx->text_pending) {
+        if ((rc = finish_text_upload(ctx))) return rc;
+        return scan_range(ctx, rev_mode, fb, fe);
+    }
+    // forward pass over a host text that is still arriving: pack each chunk as it lands and scan the window
+    // starts whose windows and read alignments (<= 255 bases to the right) lie entirely in the chunks seen so far
+    if ((rc = enqueue_text_copies(ctx, true))) return rc;
+    uint64_t done = fb;
+    const uint64_t nchunks = text_chunks(ctx);
+    for (uint64_t c = 0; c < nchunks; c++) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->text_ev[c], 0));
+        if ((rc = pack_text_chunk(ctx, ctx->ascii_stage.as<uint8_t>(), c))) return rc;
+        const uint64_t have = ctx->slice_begin + std::min<uint64_t>(ctx->slice_len, (c + 1) * TEXT_CHUNK_BASES);   // bases [slice_begin, have) are packed
+        uint64_t upto = c + 1 == nchunks ? fe : (have > 2 * 256 ? std::min<uint64_t>(fe, have - 2 * 256) : 0);
+        if (upto > done) {
+            if ((rc = scan_range(ctx, 0, done, upto))) return rc;
+            done = upto;
+        }
+    }
+    ctx->text_pending = false;
+    return rc_text(ctx);
 }
 
 int pgm_get_accumulators(pgm_ctx *ctx, pgm_accumulators *out) {
@@ -608,6 +806,10 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
     if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_get_results: no reads");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->n_reads();
+    {   // inputs that were set but never matched against: bring them in, so that the state and the symbol check are real
+        int rc;
+        if ((rc = upload_reads(ctx, false)) || (rc = finish_text_upload(ctx))) return rc;
+    }
     if (n) {
         if (!ctx->outputs_valid) {
             CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));

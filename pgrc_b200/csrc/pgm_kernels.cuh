@@ -125,7 +125,8 @@ struct ScanParams {
     uint32_t seed_len, parts, max_mm, min_mm;
     uint32_t tail_mask;             // valid bits of the last 32-base chunk of a seed
     int rev_mode;
-    int l2_hints;                   // 1: filter loads evict_last, bucket/record loads evict_first
+    int l2_hints;                   // 1: filter loads carry an L2 evict_last policy
+    int stream_hints;               // 1: bucket / record loads carry an L2 evict_first policy
     TableView tab;
     ReadsView reads;
     PerRead pr;
@@ -374,15 +375,17 @@ __global__ void unpack_reads_kernel(const uint8_t *__restrict__ packed, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------ per-read state
-__global__ void reset_state_kernel(ReadsView reads, PerRead pr, uint32_t n_reads, int reset_state) {
+__global__ void reset_state_kernel(ReadsView reads, PerRead pr, uint32_t n_reads, int reset_state, int records) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
-    uint32_t stride16; bool is_n;
-    uint4 *rec = record_of(reads, r, stride16, is_n);
-    uint4 h = rec[0];
-    if (reset_state) { h.x = 0xFFFFFFFFu; h.y = 0xFF0000FFu; }
-    h.z = 0xFFFFFFFFu; h.w = 0x7FFFFFFFu;
-    rec[0] = h;
+    if (records) {
+        uint32_t stride16; bool is_n;
+        uint4 *rec = record_of(reads, r, stride16, is_n);
+        uint4 h = rec[0];
+        if (reset_state) { h.x = 0xFFFFFFFFu; h.y = 0xFF0000FFu; }
+        h.z = 0xFFFFFFFFu; h.w = 0x7FFFFFFFu;
+        rec[0] = h;
+    }
     pr.first_other_order[r] = PGM_KEY_INF;
     pr.same_pos_mask[r] = 0;
     pr.same_pos_mm[r] = 255;
@@ -403,12 +406,11 @@ __device__ __forceinline__ uint32_t extract32(const uint32_t *w, uint32_t nwords
 // (ConstantLengthPatternsOnTextHashMatcher.cpp:23-42); the reference's pattern index r * parts + j (:39) is
 // kept as (r << part_bits) | j.  Reads already matched with <= min_mm mismatches are left out when
 // `continuation` (the matchedReadsBitmap argument, ReadsMatchers.cpp:290-291).
-__global__ void __launch_bounds__(256) build_table_kernel(ReadsView reads, TableView tab, uint32_t seed_len, uint32_t parts,
-                                                          uint32_t min_mm, int continuation, uint32_t tail_mask,
-                                                          unsigned long long *inserted) {
-    const uint32_t n_reads = reads.n_lq + reads.n_n;
+__global__ void __launch_bounds__(256) build_table_kernel(ReadsView reads, TableView tab, uint32_t r_begin, uint32_t r_end,
+                                                          uint32_t seed_len, uint32_t parts, uint32_t min_mm, int continuation,
+                                                          uint32_t tail_mask, unsigned long long *inserted) {
     unsigned int n_ins = 0;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) {
+    for (uint32_t r = r_begin + blockIdx.x * blockDim.x + threadIdx.x; r < r_end; r += gridDim.x * blockDim.x) {
         uint32_t stride16; bool is_n;
         const uint4 *rec = record_of(reads, r, stride16, is_n);
         if (continuation && (__ldg(reinterpret_cast<const uint32_t *>(rec) + 1) >> 24) <= min_mm) continue;
@@ -563,7 +565,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
     const uint32_t lt_mask = (1u << lane) - 1u;
     unsigned long long n_cand = 0, n_ver = 0, n_acc = 0, n_pos = 0;
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
-    const bool hints = p.l2_hints != 0;
+    const bool hints = p.stream_hints != 0, fhints = p.l2_hints != 0;
 
     auto issue_tile = [&](unsigned int tile, int b) {
         const int64_t w0 = (int64_t)p.first_word + (int64_t)tile * PGM_TILE_WORDS - PGM_HALO_L;
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
                 uint32_t fw[U];
 #pragma unroll
                 for (int u = 0; u < U; u++)
-                    fw[u] = !p.tab.filter ? 0xFFFFFFFFu : hints ? ld_u32_hint(p.tab.filter + fi[u], pol_keep) : __ldg(p.tab.filter + fi[u]);
+                    fw[u] = !p.tab.filter ? 0xFFFFFFFFu : fhints ? ld_u32_hint(p.tab.filter + fi[u], pol_keep) : __ldg(p.tab.filter + fi[u]);
                 uint32_t bal[U], tot = 0;
                 bool hit[U];
 #pragma unroll

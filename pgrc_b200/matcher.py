@@ -114,7 +114,7 @@ class GpuReadsMatcher:
             raise PgmError(rc, self._lib.pgm_last_error(self._h).decode())
 
     # -- inputs
-    def set_tuning(self, filter_log2_bits: int = -1, slots_per_pattern: int = 3, ctas_per_sm: int = 4, l2_hints: bool = True):
+    def set_tuning(self, filter_log2_bits: int = -1, slots_per_pattern: int = 3, ctas_per_sm: int = 4, l2_hints: int = 1):
         self._check(self._lib.pgm_set_tuning(self._h, filter_log2_bits, slots_per_pattern, ctas_per_sm, int(l2_hints)))
 
     def set_text(self, text):

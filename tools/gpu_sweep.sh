@@ -15,14 +15,12 @@ except Exception as e:
     print(" ".join(sys.argv[1:]), "FAILED", e)
 PY
 }
-run
+for a in "$@"; do :; done
+run --l2-hints 1
+run --l2-hints 2
 run --l2-hints 0
-run --filter-bits 29
-run --filter-bits 27
-run --filter-bits 29 --l2-hints 0
-run --slots-per-pattern 3
-run --slots-per-pattern 4
-run --ctas-per-sm 3
-run --ctas-per-sm 5
-run --ctas-per-sm 6
-run --ctas-per-sm 8
+run --l2-hints 2 --filter-bits 29
+run --l2-hints 2 --filter-bits 27
+PGM_L2_FETCH=32 run --l2-hints 1
+PGM_L2_FETCH=32 run --l2-hints 2
+PGM_L2_FETCH=128 run --l2-hints 1

@@ -219,6 +219,25 @@ int main() {
            p.multiProcessorCount, p.l2CacheSize >> 20, p.persistingL2CacheMaxSize >> 20, p.accessPolicyMaxWindowSize >> 20,
            p.sharedMemPerMultiprocessor >> 10);
     const int SM = p.multiProcessorCount;
+    if (getenv("UB_L2_FETCH")) {
+        size_t g = 0;
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("UB_L2_FETCH")));
+        cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity);
+        printf("L2 fetch granularity request %s -> %s, now %zu\n", getenv("UB_L2_FETCH"), cudaGetErrorString(e), g);
+    } else {
+        size_t g = 0; cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity); printf("L2 fetch granularity default %zu\n", g);
+    }
+    if (getenv("UB_SHORT")) {
+        uint64_t *out; CK(cudaMalloc(&out, 64));
+        const size_t big = 1ull << 30; void *table; CK(cudaMalloc(&table, big)); CK(cudaMemset(table, 0xFF, big));
+        const uint64_t N = 1ull << 27; const int blocks = SM * 8, threads = 256;
+        const uint64_t per = N / ((uint64_t)blocks * threads); const double items = (double)per * blocks * threads;
+        float a = time_ms([&] { gather_ld256<2, 32><<<blocks, threads>>>((uint8_t *)table, (uint32_t)(big / 32 - 1), per, out); });
+        float b = time_ms([&] { gather64<2, 2><<<blocks, threads>>>((uint4 *)table, (uint32_t)(big / 64 - 1), per, out); });
+        float c = time_ms([&] { gather4<4><<<blocks, threads>>>((uint32_t *)table, (uint32_t)(big / 4 - 1), per, out); });
+        printf("1 GB table: 32 B items (LDG.256) %.1f G/s | 64 B items (lane pair) %.1f G/s | 4 B gathers %.1f G/s\n", items / a / 1e6, items / 2 / b / 1e6, items / c / 1e6);
+        return 0;
+    }
     uint64_t *out; CK(cudaMalloc(&out, 64));
     const size_t big = 1ull << 30;      // 1 GB "table"
     void *table; CK(cudaMalloc(&table, big)); CK(cudaMemset(table, 0xFF, big));
