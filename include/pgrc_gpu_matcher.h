@@ -86,7 +86,8 @@ int pgm_abi_version(void);
 int pgm_create(int device, pgm_ctx **out);
 void pgm_destroy(pgm_ctx *ctx);
 const char *pgm_last_error(const pgm_ctx *ctx); /* ctx may be NULL: last pgm_create error */
-/* Use an existing CUDA stream (cudaStream_t) for all work of this context; NULL = own stream. */
+/* Use an existing CUDA stream (cudaStream_t) for all work of this context; NULL = own stream
+ * (pass cudaStreamLegacy / cudaStreamPerThread to name a default stream). */
 int pgm_set_stream(pgm_ctx *ctx, void *cuda_stream);
 /* Blocks until all work queued by this context has finished. */
 int pgm_synchronize(pgm_ctx *ctx);

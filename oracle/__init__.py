@@ -29,6 +29,9 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-s", "-C", _HERE, "oracle"], check=True)
     if ref and os.path.isdir("/root/reference/matching"):
         subprocess.run(["make", "-s", "-j8", "-C", _HERE, "ref"], check=True)
+        # the reference's CLI with the C++ GPU shim linked in (tests/test_gpu_cli_archive.py); needs the CUDA library
+        if os.path.exists(os.path.join(_HERE, "..", "pgrc_b200", "libpgrc_gpu.so")):
+            subprocess.run(["make", "-s", "-j8", "-C", _HERE, "cli"], check=True)
 
 
 def have_ref() -> bool:

@@ -1,0 +1,278 @@
+// GpuReadsMatchers.cpp — see GpuReadsMatchers.h.  Host C++ over the C ABI; no CUDA in this file.
+//
+// How it gets into the PgRC binary without touching a reference source file (oracle/Makefile, target `cli`):
+// matching/ReadsMatchers.cpp is compiled with -DmapReadsIntoPg=mapReadsIntoPg_reference, and this file provides
+// PgTools::mapReadsIntoPg, which either runs the GPU matchers or calls the renamed reference function.  A maintainer
+// would instead add the two classes to ReadsMatchers.{h,cpp} and one `case` to the switches at
+// ReadsMatchers.cpp:716-740 / :753-769.
+//
+// The packed read buffers are taken exactly as PackedConstantLengthReadsSet holds them
+// (PackedConstantLengthReadsSet.h:17-18,40).  SumOfConstantLengthReadsSets (ReadsSetInterface.h:45-89) keeps its two
+// sets private and has no accessor; until the two one-line accessors of INTEGRATION.md exist upstream, this
+// translation unit reads them through the `private -> public` trick below (same object layout, nothing else relies
+// on it).  If a reads set is of an unknown class, the reads are re-packed through the public getRead() interface.
+#include "utils/helper.h"            // everything ReadsSetInterface.h pulls in comes first, with normal access rules
+#include "readsset/ReadsSetBase.h"
+#define private public
+#include "readsset/ReadsSetInterface.h"
+#undef private
+#include "GpuReadsMatchers.h"
+#include "readsset/PackedConstantLengthReadsSet.h"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace PgTools {
+
+    // the reference's own function, renamed at compile time (see above)
+    const vector<bool> mapReadsIntoPg_reference(SeparatedPseudoGenome *sPg, bool revComplPg, bool preserveOrderMode,
+                        ConstantLengthReadsSetInterface *readsSet, bool pairFileMode, bool revComplPairFile,
+                        uint_read_len_max matchPrefixLength, uint16_t preReadsExactMatchingChars,
+                        uint16_t readsExactMatchingChars, uint16_t minCharsPerMismatch, char preMatchingMode,
+                        char matchingMode, bool dumpInfo, ostream &pgrcOut, uint8_t compressionLevel,
+                        const string &pgDestFilePrefix, IndexesMapping *orgIndexesMapping);
+
+    // ------------------------------------------------------------------------------------------ session
+    void GpuMatcherSession::check(int rc, pgm_ctx *c, const char *what) {
+        if (rc == PGM_OK) return;
+        // error convention of the reference: message on stderr + exit (e.g. ReadsMatchers.cpp:737-739)
+        fprintf(stderr, "GPU matcher: %s failed: %s\n", what, pgm_last_error(c));
+        exit(EXIT_FAILURE);
+    }
+
+    namespace {
+        struct PackedView { const uint8_t *data = nullptr; uint32_t count = 0; bool withN = false; vector<uint8_t> owned; };
+
+        // re-pack through the public interface (SymbolsPackingFacility.cpp:168-185 layout)
+        void repack(ConstantLengthReadsSetInterface *rs, uint_reads_cnt_max first, uint_reads_cnt_max count, bool withN, PackedView &v) {
+            const uint32_t L = rs->maxReadLength(), spe = withN ? 3 : 4, sigma = withN ? 5 : 4, plen = (L + spe - 1) / spe;
+            v.owned.assign((size_t)count * plen, 0);
+            string read(L, 'A');
+            for (uint_reads_cnt_max i = 0; i < count; i++) {
+                rs->getRead(first + i, (char *)read.data());
+                for (uint32_t b = 0; b < plen; b++) {
+                    uint32_t val = 0;
+                    for (uint32_t k = 0; k < spe; k++) {
+                        const uint32_t p = b * spe + k;
+                        const char c = p < L ? read[p] : 'A';
+                        const uint32_t code = withN ? (c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'N' ? 3 : 4)
+                                                    : (c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3);
+                        val = val * sigma + code;
+                    }
+                    v.owned[(size_t)i * plen + b] = (uint8_t)val;
+                }
+            }
+            v.data = v.owned.data(); v.count = count; v.withN = withN;
+        }
+
+        PackedView viewOf(ConstantLengthReadsSetInterface *rs) {
+            PackedView v;
+            v.count = rs->readsCount();
+            v.withN = rs->getReadsSetProperties()->symbolsCount > 4;
+            if (auto *packed = dynamic_cast<PgReadsSet::PackedConstantLengthReadsSet *>(rs)) {
+                v.data = v.count ? packed->getPackedRead(0) : nullptr;
+            } else {
+                bool hasN = false;
+                string read(rs->maxReadLength(), 'A');
+                for (uint_reads_cnt_max i = 0; i < v.count && !hasN; i++) {
+                    rs->getRead(i, (char *)read.data());
+                    hasN = read.find('N') != string::npos;
+                }
+                repack(rs, 0, v.count, hasN, v);
+            }
+            return v;
+        }
+    }
+
+    GpuMatcherSession::GpuMatcherSession(const char *pgPtr, uint64_t pgLength, ConstantLengthReadsSetInterface *readsSet) {
+        const char *dev = getenv("PGRC_GPU_DEVICE");
+        check(pgm_create(dev ? atoi(dev) : 0, &ctx), nullptr, "pgm_create");
+        check(pgm_set_text(ctx, pgPtr, pgLength), ctx, "pgm_set_text");           // read-only: no in-place reverse complement
+        readsCount = readsSet->readsCount();
+        PackedView a, b;
+        if (auto *sum = dynamic_cast<SumOfConstantLengthReadsSets *>(readsSet)) {
+            a = viewOf(sum->clrs1);                                                 // LQ set, then N set: the global read index
+            b = viewOf(sum->clrs2);                                                 // of SumOfConstantLengthReadsSets
+        } else {
+            a = viewOf(readsSet);
+        }
+        // C ABI: ACGT-packed reads first, ACGNT-packed reads second
+        if (b.count == 0 && a.withN) { b = std::move(a); a = PackedView(); }
+        if (a.withN || (b.count && !b.withN)) {
+            // (never produced by pgrc-encoder: LQ is ACGT and N is ACGNT, or one single set) — re-pack both as ACGNT
+            PackedView all;
+            repack(readsSet, 0, readsCount, true, all);
+            check(pgm_set_reads(ctx, nullptr, 0, all.data, all.count, readsSet->maxReadLength()), ctx, "pgm_set_reads");
+            check(pgm_synchronize(ctx), ctx, "pgm_synchronize");
+            return;
+        }
+        check(pgm_set_reads(ctx, a.data, a.count, b.data, b.count, readsSet->maxReadLength()), ctx, "pgm_set_reads");
+        if (!a.owned.empty() || !b.owned.empty()) {
+            // re-packed copies die with this constructor: force the (lazy) upload now
+            check(pgm_get_results(ctx, nullptr, nullptr, nullptr, nullptr), ctx, "pgm_get_results");
+        }
+    }
+
+    GpuMatcherSession::~GpuMatcherSession() { pgm_destroy(ctx); }
+
+    void GpuMatcherSession::begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation) {
+        check(pgm_match_begin(ctx, seedLength, parts, maxMismatches, minMismatches, continuation ? 1 : 0), ctx, "pgm_match_begin");
+    }
+
+    void GpuMatcherSession::pass(bool revCompMode) {
+        check(pgm_scan_pass(ctx, revCompMode ? 1 : 0), ctx, "pgm_scan_pass");
+        check(pgm_resolve_pass(ctx, revCompMode ? 1 : 0), ctx, "pgm_resolve_pass");
+    }
+
+    void GpuMatcherSession::fetch(vector<uint64_t> &readMatchPos, vector<bool> &readMatchRC, vector<uint8_t> *readMismatchesCount,
+                                  uint_reads_cnt_max &matchedReadsCount, uint_reads_cnt_max *matchedCountPerMismatches) {
+        vector<uint8_t> rc(readsCount), mm(readsCount);
+        readMatchPos.resize(readsCount);
+        pgm_stats st;
+        check(pgm_get_results(ctx, readMatchPos.data(), rc.data(), mm.data(), &st), ctx, "pgm_get_results");
+        readMatchRC.resize(readsCount);
+        for (uint_reads_cnt_max i = 0; i < readsCount; i++) readMatchRC[i] = rc[i] != 0;
+        matchedReadsCount = (uint_reads_cnt_max) st.matched;
+        if (readMismatchesCount) *readMismatchesCount = std::move(mm);
+        if (matchedCountPerMismatches)
+            for (int k = 0; k <= NOT_MATCHED_COUNT; k++) matchedCountPerMismatches[k] = (uint_reads_cnt_max) st.per_mm[k];
+    }
+
+    // ------------------------------------------------------------------------------------------ exact path
+    GpuReadsExactMatcher::GpuReadsExactMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
+                                               ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength)
+            : DefaultReadsExactMatcher(pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength), session(session) {}
+
+    void GpuReadsExactMatcher::initMatching() {                                    // replaces ReadsMatchers.cpp:190-196
+        DefaultReadsMatcher::initMatching();
+        session->begin(matchingLength, 1, 0, 0, false);
+    }
+
+    void GpuReadsExactMatcher::executeMatching(bool revCompMode) {                 // replaces ReadsMatchers.cpp:198-230
+        time_checkpoint();
+        session->pass(revCompMode);
+        if (revCompMode == revComplPg) {                                           // last pass of this matcher
+            session->fetch(readMatchPos, readMatchRC, nullptr, matchedReadsCount, nullptr);
+            cout << "... exact matched " << matchedReadsCount << " reads (" << (readsCount - matchedReadsCount)
+                 << " left) on the GPU in " << time_millis() << " msec (last pass incl. results)." << endl;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------ k-mismatch path
+    GpuReadsApproxMatcher::GpuReadsApproxMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
+                                                 ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength,
+                                                 uint16_t readsExactMatchingChars, uint8_t maxMismatches, uint8_t minMismatches)
+            : AbstractReadsApproxMatcher(pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength, readsExactMatchingChars,
+                                         maxMismatches, minMismatches), session(session), partLength(readsExactMatchingChars) {}
+
+    void GpuReadsApproxMatcher::initMatching() {                                   // replaces ReadsMatchers.cpp:276-285
+        DefaultReadsMatcher::initMatching();
+        readMismatchesCount.clear();
+        readMismatchesCount.insert(readMismatchesCount.end(), readsCount, NOT_MATCHED_COUNT);
+        session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, false);
+    }
+
+    void GpuReadsApproxMatcher::initMatchingContinuation(DefaultReadsMatcher *pMatcher) {   // replaces :287-295
+        // the device still holds the first phase's per-read state; reads matched with <= minMismatches are left
+        // out of the new table there (getMatchedReadsBitmap(minMismatches), ReadsMatchers.cpp:290-291)
+        AbstractReadsApproxMatcher::initMatchingContinuation(pMatcher);
+        session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, true);
+    }
+
+    void GpuReadsApproxMatcher::executeMatching(bool revCompMode) {                // replaces ReadsMatchers.cpp:297-341
+        time_checkpoint();
+        cout << "Matching" << (revCompMode ? " in Pg reverse" : "") << " (GPU)...\n" << endl;
+        session->pass(revCompMode);
+        if (revCompMode == revComplPg)                                             // last pass of this matcher
+            session->fetch(readMatchPos, readMatchRC, &readMismatchesCount, matchedReadsCount, matchedCountPerMismatches);
+        printApproxMatchingStats();
+    }
+
+    // ------------------------------------------------------------------------------------------ mapReadsIntoPg
+    const vector<bool> mapReadsIntoPgOnGpu(SeparatedPseudoGenome *sPg, bool revComplPg, bool preserveOrderMode,
+                        ConstantLengthReadsSetInterface *readsSet, bool pairFileMode, bool revComplPairFile,
+                        uint_read_len_max matchPrefixLength, uint16_t preReadsExactMatchingChars,
+                        uint16_t readsExactMatchingChars, uint16_t minCharsPerMismatch, char preMatchingMode,
+                        char matchingMode, bool dumpInfo, ostream &pgrcOut, uint8_t compressionLevel,
+                        const string &pgDestFilePrefix, IndexesMapping *orgIndexesMapping) {
+        // parameter derivation and phase structure of the reference, ReadsMatchers.cpp:699-779
+        const uint_read_len_max readLength = readsSet->maxReadLength();
+        const uint8_t maxMismatches = readLength / minCharsPerMismatch;
+        readsExactMatchingChars = std::min<uint16_t>(readsExactMatchingChars, readLength);
+        preReadsExactMatchingChars = std::min<uint16_t>(preReadsExactMatchingChars, readLength);
+        const bool twoPhases = preReadsExactMatchingChars > 0;
+        const uint16_t firstSeed = twoPhases ? preReadsExactMatchingChars : readsExactMatchingChars;
+        const char firstMode = twoPhases ? preMatchingMode : matchingMode;
+        const uint8_t firstMinMismatches = isupper((unsigned char) firstMode) ? maxMismatches : 0;
+        uint8_t targetMismatches = readLength / firstSeed - 1;
+        char *pgPtr = (char *) sPg->getPgSequence().data();
+        const uint_pg_len_max pgLength = sPg->getPgSequence().length();
+
+        GpuMatcherSession session(pgPtr, pgLength, readsSet);
+        DefaultReadsMatcher *matcher;
+        if (readLength == firstSeed)
+            matcher = new GpuReadsExactMatcher(&session, pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength);
+        else
+            matcher = new GpuReadsApproxMatcher(&session, pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength,
+                                                firstSeed, maxMismatches, firstMinMismatches);
+        cout << "Target pseudogenome length: " << pgLength << endl;
+        *logout << endl;
+        cout << "readsAlignmentSeedLength (minCharsPerMismatch, matchingMode): " << (int) firstSeed <<
+             " (" << (int) minCharsPerMismatch << ", " << firstMode << ")" << endl;
+        *logout << "targetMismatches (maxMismatches, minMismatches): " << (int) targetMismatches <<
+                " (" << (int) maxMismatches << ", " << (int) firstMinMismatches << ")" << endl;
+        matcher->matchConstantLengthReads();
+
+        if (twoPhases) {
+            const uint8_t secondMinMismatches = isupper((unsigned char) matchingMode) ? maxMismatches : targetMismatches + 1;
+            AbstractReadsApproxMatcher *approxMatcher = new GpuReadsApproxMatcher(&session, pgPtr, pgLength, revComplPg, readsSet,
+                    matchPrefixLength, readsExactMatchingChars, maxMismatches, secondMinMismatches);
+            targetMismatches = readLength / readsExactMatchingChars - 1;
+            cout << endl << "Reads matching 2nd PHASE." << endl;
+            cout << "readsExactMatchingChars (minCharsPerMismatch, matchingMode): " << (int) readsExactMatchingChars <<
+                 " (" << (int) minCharsPerMismatch << ", " << matchingMode << ")" << endl;
+            cout << "targetMismatches (maxMismatches, minMismatches): " << (int) targetMismatches <<
+                 " (" << (int) maxMismatches << ", " << (int) secondMinMismatches << ")" << endl;
+            approxMatcher->continueMatchingConstantLengthReads(matcher);
+            delete matcher;
+            matcher = approxMatcher;
+        }
+        if (dumpInfo) matcher->writeMatchesInfo(pgDestFilePrefix);
+        const vector<bool> res = matcher->getMatchedReadsBitmap();
+        // the reference's own export code, unchanged (ReadsMatchers.cpp:785-792)
+        if (matchPrefixLength == DefaultReadsMatcher::DISABLED_PREFIX_MODE) {
+            if (preserveOrderMode)
+                matcher->exportMatchesInOriginalOrder(sPg, pgrcOut, compressionLevel, pgDestFilePrefix, orgIndexesMapping, pairFileMode, revComplPairFile);
+            else
+                matcher->exportMatchesInPgOrder(sPg, pgrcOut, compressionLevel, pgDestFilePrefix, orgIndexesMapping, pairFileMode, revComplPairFile);
+        }
+        delete matcher;
+        return res;
+    }
+
+    // What pgrc-encoder.cpp:359 calls.
+    const vector<bool> mapReadsIntoPg(SeparatedPseudoGenome *sPg, bool revComplPg, bool preserveOrderMode,
+                        ConstantLengthReadsSetInterface *readsSet, bool pairFileMode, bool revComplPairFile,
+                        uint_read_len_max matchPrefixLength, uint16_t preReadsExactMatchingChars,
+                        uint16_t readsExactMatchingChars, uint16_t minCharsPerMismatch, char preMatchingMode,
+                        char matchingMode, bool dumpInfo, ostream &pgrcOut, uint8_t compressionLevel,
+                        const string &pgDestFilePrefix, IndexesMapping *orgIndexesMapping) {
+        // ConstantLengthPatternsOnTextHashMatcher.cpp:30 takes the pattern count from
+        // getReadsSetProperties()->readsCount, which SumOfConstantLengthReadsSets never fills — mode 'd' then sees 0
+        // patterns.  Filling the (public, otherwise unused) field makes the reference's mode 'd' the oracle it is meant
+        // to be; the reference sources stay untouched.
+        if (readsSet->getReadsSetProperties()->readsCount == 0)
+            readsSet->getReadsSetProperties()->readsCount = readsSet->readsCount();
+        const char *env = getenv("PGRC_GPU_MATCHER");
+        const bool wantGpu = env && *env && strcmp(env, "0") != 0;
+        const bool hashMatcherPath = tolower(matchingMode) == 'd' && (preReadsExactMatchingChars == 0 || tolower(preMatchingMode) == 'd')
+                                     && matchPrefixLength == DefaultReadsMatcher::DISABLED_PREFIX_MODE;
+        if (wantGpu && hashMatcherPath)
+            return mapReadsIntoPgOnGpu(sPg, revComplPg, preserveOrderMode, readsSet, pairFileMode, revComplPairFile, matchPrefixLength,
+                                       preReadsExactMatchingChars, readsExactMatchingChars, minCharsPerMismatch, preMatchingMode,
+                                       matchingMode, dumpInfo, pgrcOut, compressionLevel, pgDestFilePrefix, orgIndexesMapping);
+        return mapReadsIntoPg_reference(sPg, revComplPg, preserveOrderMode, readsSet, pairFileMode, revComplPairFile, matchPrefixLength,
+                                        preReadsExactMatchingChars, readsExactMatchingChars, minCharsPerMismatch, preMatchingMode,
+                                        matchingMode, dumpInfo, pgrcOut, compressionLevel, pgDestFilePrefix, orgIndexesMapping);
+    }
+}

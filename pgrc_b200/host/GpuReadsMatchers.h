@@ -1,0 +1,71 @@
+// GpuReadsMatchers.h — the reference-side binding of the B200 matcher: C++ host code that plugs the C ABI
+// (include/pgrc_gpu_matcher.h) in behind PgRC's own matcher class interface.
+//
+// Two classes sit behind the reference's bases and override exactly the protected virtuals the reference's
+// hash-matcher classes override (matching/ReadsMatchers.h:45-46,128):
+//     GpuReadsExactMatcher  : DefaultReadsExactMatcher     (ReadsMatchers.h:85-107,  .cpp:190-230)
+//     GpuReadsApproxMatcher : AbstractReadsApproxMatcher   (ReadsMatchers.h:109-144, .cpp:276-341)
+// They fill the inherited result members (readMatchPos, readMatchRC, readMismatchesCount, matchedReadsCount,
+// matchedCountPerMismatches), so everything downstream — getMatchedReadsBitmap, exportMatchesInPgOrder /
+// exportMatchesInOriginalOrder, the archive writer — is the reference's unmodified code.
+//
+// This header needs the reference's headers on the include path (-I<PgRC source root>); it is compiled only where
+// the reference sources are present (oracle/Makefile, target `cli`), never on the GPU box.
+#ifndef PGRC_B200_GPU_READS_MATCHERS_H
+#define PGRC_B200_GPU_READS_MATCHERS_H
+
+#include "matching/ReadsMatchers.h"
+#include "pgrc_gpu_matcher.h"
+
+namespace PgTools {
+
+    // One device context per mapReadsIntoPg call: text + reads are uploaded once and shared by both phases.
+    class GpuMatcherSession {
+        pgm_ctx *ctx = nullptr;
+        uint_reads_cnt_max readsCount = 0;
+    public:
+        GpuMatcherSession(const char *pgPtr, uint64_t pgLength, ConstantLengthReadsSetInterface *readsSet);
+        ~GpuMatcherSession();
+        static void check(int rc, pgm_ctx *c, const char *what);   // prints pgm_last_error, exit(EXIT_FAILURE)
+        void begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation);
+        void pass(bool revCompMode);
+        // copies the per-read results into the reference's member vectors
+        void fetch(vector<uint64_t> &readMatchPos, vector<bool> &readMatchRC, vector<uint8_t> *readMismatchesCount,
+                   uint_reads_cnt_max &matchedReadsCount, uint_reads_cnt_max *matchedCountPerMismatches);
+    };
+
+    class GpuReadsExactMatcher : public DefaultReadsExactMatcher {
+        GpuMatcherSession *session;
+    protected:
+        void initMatching() override;
+        void executeMatching(bool revCompMode = false) override;
+    public:
+        GpuReadsExactMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
+                             ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength);
+    };
+
+    class GpuReadsApproxMatcher : public AbstractReadsApproxMatcher {
+        GpuMatcherSession *session;
+        uint_read_len_max partLength;
+    protected:
+        void initMatching() override;
+        void initMatchingContinuation(DefaultReadsMatcher *pMatcher) override;
+        void executeMatching(bool revCompMode = false) override;
+    public:
+        GpuReadsApproxMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
+                              ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength,
+                              uint16_t readsExactMatchingChars, uint8_t maxMismatches, uint8_t minMismatches = 0);
+    };
+
+    // Same signature as PgTools::mapReadsIntoPg (ReadsMatchers.h:202-207).  Matching modes 'd'/'D' run on the GPU when
+    // the environment variable PGRC_GPU_MATCHER is set to something other than 0; every other case is passed on
+    // to the reference's own function.
+    const vector<bool> mapReadsIntoPgOnGpu(SeparatedPseudoGenome *sPg, bool revComplPg, bool preserveOrderMode,
+                        ConstantLengthReadsSetInterface *readsSet, bool pairFileMode, bool revComplPairFile,
+                        uint_read_len_max matchPrefixLength, uint16_t preReadsExactMatchingChars,
+                        uint16_t readsExactMatchingChars, uint16_t minCharsPerMismatch, char preMatchingMode,
+                        char matchingMode, bool dumpInfo, ostream &pgrcOut, uint8_t compressionLevel,
+                        const string &pgDestFilePrefix, IndexesMapping *orgIndexesMapping);
+}
+
+#endif

@@ -89,7 +89,10 @@ class GpuReadsMatcher:
         self.read_len = 0
         if use_torch_stream:
             import torch
-            self._check(self._lib.pgm_set_stream(self._h, ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+            # torch's default stream is the legacy default stream (handle 0); the C ABI reads NULL as "own stream",
+            # so name it explicitly (cudaStreamLegacy = 0x1): kernels then order with torch ops and NCCL collectives
+            handle = torch.cuda.current_stream(device).cuda_stream or 1
+            self._check(self._lib.pgm_set_stream(self._h, ctypes.c_void_p(handle)))
 
     # -- life cycle
     def close(self):

@@ -1,0 +1,66 @@
+"""GPU, end to end through the reference's own CLI: `PgRC-dev` built from the unmodified reference sources with the C++
+shim of pgrc_b200/host/ (oracle/Makefile target `cli`) compresses the same synthetic FASTQ twice — once with the
+reference's CPU hash matchers (mode d), once with the GPU matchers behind the same class interface
+(PGRC_GPU_MATCHER=1) — and the two .pgrc archives must be byte-identical, for every archive mode of BASELINE.json's
+configs (SE, SE_ORD, PE, PE_ORD) and for the two-phase / exact / shortcut parameterisations."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "oracle", "_ref", "PgRC-dev-gpu")
+
+
+def _fastq(tmp, name, pair=False, **kw):
+    out = os.path.join(tmp, name + "_1.fastq")
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "make_fastq.py"), out]
+    out2 = None
+    if pair:
+        out2 = os.path.join(tmp, name + "_2.fastq")
+        cmd += ["--pair", out2]
+    for k, v in kw.items():
+        cmd += ["--" + k.replace("_", "-"), str(v)]
+    subprocess.run(cmd, check=True)
+    return out, out2
+
+
+def _compress(tmp, tag, gpu, fastq, fastq2, flags):
+    d = os.path.join(tmp, tag)
+    os.makedirs(d)
+    env = dict(os.environ)
+    env.pop("PGRC_GPU_MATCHER", None)
+    if gpu:
+        env["PGRC_GPU_MATCHER"] = "1"
+    cmd = [CLI, "-t", "1"] + flags + ["-i", fastq] + ([fastq2] if fastq2 else []) + ["a.pgrc"]
+    r = subprocess.run(cmd, cwd=d, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert ("(GPU)" in r.stdout or "on the GPU" in r.stdout) == gpu, r.stdout[-1500:]
+    return open(os.path.join(d, "a.pgrc"), "rb").read(), r.stdout
+
+
+CASES = {
+    "SE_100bp": dict(pair=False, flags=["-s", "d38"], gen=dict(genome=300_000, reads=60_000, len=100, err=0.005, n_frac=0.01, seed=1)),
+    "SE_ORD_150bp": dict(pair=False, flags=["-o", "-s", "d38"], gen=dict(genome=200_000, reads=40_000, len=150, err=0.005, n_frac=0.01, seed=2)),
+    "PE_150bp": dict(pair=True, flags=["-s", "d38"], gen=dict(genome=200_000, reads=20_000, len=150, err=0.005, seed=3)),
+    "PE_ORD_150bp": dict(pair=True, flags=["-o", "-s", "d38"], gen=dict(genome=200_000, reads=20_000, len=150, err=0.005, n_frac=0.005, seed=4)),
+    "SE_shortcut": dict(pair=False, flags=["-s", "ds38"], gen=dict(genome=200_000, reads=40_000, len=100, err=0.01, seed=5)),
+    "SE_two_phase": dict(pair=False, flags=["-l", "d50", "-s", "d33"], gen=dict(genome=200_000, reads=40_000, len=100, err=0.01, seed=6)),
+    "SE_exact_prephase": dict(pair=False, flags=["-l", "d100", "-s", "d38"], gen=dict(genome=200_000, reads=40_000, len=100, err=0.003, seed=7)),
+    "SE_M2": dict(pair=False, flags=["-M", "2", "-s", "d40"], gen=dict(genome=200_000, reads=40_000, len=120, err=0.02, seed=8)),
+}
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="oracle/_ref/PgRC-dev-gpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_archive_bytes_identical_to_reference_cli(tmp_path, name):
+    c = CASES[name]
+    f1, f2 = _fastq(str(tmp_path), name, c["pair"], **c["gen"])
+    ref, ref_out = _compress(str(tmp_path), "cpu", False, f1, f2, c["flags"])
+    got, got_out = _compress(str(tmp_path), "gpu", True, f1, f2, c["flags"])
+    assert len(ref) > 1000
+    assert "Matched" in ref_out and "Matched" in got_out
+    assert got == ref, f"{name}: archives differ ({len(got)} vs {len(ref)} bytes)"

@@ -157,3 +157,52 @@ def test_hot_seeds_duplicate_reads_and_homopolymers():
     assert got.stats["candidates"] > 100_000
     _check(inp, matching_mode="D")
     _check(inp, reads_exact_matching_chars=100)
+
+
+def _run_sharded_on_one_gpu(inp, world, **kw):
+    """The text-sharded path with `world` contexts on ONE GPU: every context scans its text range, the per-read
+    accumulators are merged with plain torch ops (what NCCL MIN / SUM all-reduces do across GPUs), every context
+    applies the decision.  Exercises the shard geometry of the kernels (halos, RC coordinates of a slice)."""
+    import torch
+    ms = [matcher.GpuReadsMatcher(0, use_torch_stream=True) for _ in range(world)]
+    try:
+        pg_len = inp.text.size
+        for rank, m in enumerate(ms):
+            sb, sl, ob, oe = matcher.shard_plan(pg_len, rank, world)
+            m.set_text_shard(np.ascontiguousarray(inp.text[sb:sb + sl]), sb, pg_len, ob, oe)
+            m.set_reads(inp.lq_packed, inp.n_packed if len(inp.n_reads) else None, inp.read_len)
+        plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), kw.get("min_chars_per_mismatch", 3), kw.get("mode", "d"),
+                                        kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
+        for seed_len, parts, max_mm, min_mm, cont in plan.phases:
+            for m in ms:
+                m.match_begin(seed_len, parts, max_mm, min_mm, cont)
+            for rev in ((False, True) if kw.get("rev_compl", True) else (False,)):
+                for m in ms:
+                    m.scan_pass(rev)
+                accs = [m.accumulators() for m in ms]
+                best = torch.stack([a["best_key"] for a in accs]).min(dim=0).values
+                first = torch.stack([a["first_other_order"] for a in accs]).min(dim=0).values
+                mask = torch.stack([a["same_pos_mask"] for a in accs]).sum(dim=0).to(torch.int32)
+                mm = torch.stack([a["same_pos_mm"] for a in accs]).min(dim=0).values
+                touched = torch.stack([a["touched"] for a in accs]).max(dim=0).values
+                for m, a in zip(ms, accs):
+                    a["best_key"].copy_(best); a["first_other_order"].copy_(first); a["same_pos_mask"].copy_(mask)
+                    a["same_pos_mm"].copy_(mm); a["touched"].copy_(touched)
+                    m.put_accumulators()
+                    m.resolve_pass(rev)
+        return [m.get_results() for m in ms]
+    finally:
+        for m in ms:
+            m.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("kw", [dict(), dict(pre_seed=100), dict(mode="D"), dict(seed=45, rev_compl=False)])
+def test_text_sharded_contexts_match_oracle(world, kw):
+    for inp in (synth.adversarial(31, 100, n_reads=2000, text_len=30000), synth.workload(300_000, 40_000, 150, 0.005, seed=33, name="c2 shape")):
+        want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+        for got in _run_sharded_on_one_gpu(inp, world, **kw):
+            bad = np.nonzero((got.pos != want.pos) | (got.rc != want.rc) | (got.mm != want.mm))[0]
+            assert bad.size == 0, (f"{inp.name} world {world} {kw}: {bad.size} reads differ, first {bad[:5]}: gpu {got.pos[bad[:5]]} "
+                                   f"{got.rc[bad[:5]]} {got.mm[bad[:5]]} oracle {want.pos[bad[:5]]} {want.rc[bad[:5]]} {want.mm[bad[:5]]}")
+            assert got.matched == want.matched
