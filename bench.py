@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale genome and read count (testing)")
-    ap.add_argument("--shard", default="text", choices=["text", "reads"], help="multi-GPU partitioning")
+    ap.add_argument("--shard", default="auto", choices=["auto", "text", "reads"],
+                    help="multi-GPU partitioning: text ranges + NCCL min-merge of the per-read keys, or read ranges (no collective); "
+                         "auto = reads (the table build and the probes shard with the reads; see DESIGN.md §7)")
     ap.add_argument("--cpu-sample", type=float, default=0.05, help="fraction of the workload shape timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -233,7 +235,10 @@ def ours(args):
         raise SystemExit("bench.py: no CUDA device; the matcher has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.shard == "auto":
+        args.shard = "reads"
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = synth.scaled_config(args.workload, args.scale)
@@ -341,21 +346,30 @@ def ours(args):
     except OSError:
         pass
     achieved = b_alg / (scan_ms / max(1, scan_launches) * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    traffic_gbs = traffic / (scan_ms / max(1, scan_launches) * 1e-3) / 1e9 if (traffic and scan_ms > 0 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": "scan_kernel", "achieved": round(achieved, 2), "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)", "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": traffic,
+                "frac": round(achieved / peak, 5), "traffic": traffic if world == 1 else None,
+                "traffic_gbs": round(traffic_gbs, 1) if traffic_gbs else None,
+                "traffic_frac_of_peak": round(traffic_gbs / peak, 4) if traffic_gbs else None,
+                "note": "random 32/64-byte requests cost a full 128-byte DRAM line each (tools/ubench.cu): traffic >> algorithmic bytes",
                 "algorithmic_bytes_per_launch": int(b_alg), "text_bytes_per_launch": int(my_pg / 4),
                 "scan_ms_per_launch": round(scan_ms / max(1, scan_launches), 4),
                 "text_positions_per_s": round(my_pg / (scan_ms / max(1, scan_launches) * 1e-3), 1) if scan_ms > 0 else None,
                 "kernel_ms_per_step": {k: round(v[0] / psteps, 4) for k, v in tm.items()}}
 
+    matched_total = res.matched
+    if world > 1 and args.shard == "reads":
+        mt = torch.tensor([res.matched], device=dev, dtype=torch.int64)
+        dist.all_reduce(mt)
+        matched_total = int(mt.item())
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic",
                 "config": {"workload": workload_name(args), "reads": n_reads, "read_len": L, "text_bases": pg_len,
                            "seed_len": plan.phases[0][0], "parts": plan.phases[0][1], "max_mismatches": plan.phases[0][2],
-                           "matched": res.matched if (world == 1 or args.shard == "text") else None,
+                           "matched": matched_total,
                            "parallelism": "single GPU" if world == 1 else f"{args.shard}-sharded x{world}",
                            "l2": "inputs (text + reads + seed table) exceed the 126 MB L2; no flush between steps",
                            "candidates_per_step": st["candidates"], "filter_positives_per_step": st["filter_positives"],
