@@ -45,6 +45,7 @@ struct pgm_ctx {
     int filter_log2_bits = -1; // -1 = auto
     int slots_per_pattern = 3;
     int ctas_per_sm = 4;
+    int two_step_build = 1;     // region-queued table build (PGM_TWO_STEP_BUILD=0 turns it off)
     int l2_hints = 1;           // 0 none, 1 per-load eviction hints, 2 hints + persisting access-policy window on the filter
     size_t persist_max = 0, window_max = 0, persist_set = 0;
 
@@ -75,7 +76,9 @@ struct pgm_ctx {
     DevBuf first_order, same_mask, same_mm, touched, keys;
 
     // table
-    DevBuf buckets, next, filter;
+    DevBuf buckets, next, filter, bq_entries, bq_counters;
+    uint32_t bq_cap = 0, bq_region_bits = 0;
+    bool bq_pending = false;    // region queues hold patterns that build_insert_kernel has not inserted yet
     uint64_t n_slots = 0;
     uint32_t n_buckets = 0;
     uint32_t filter_words = 0;  // 0 = no filter
@@ -284,13 +287,34 @@ int unpack_range(pgm_ctx *ctx, const ReadsPart &pt, const uint8_t *src, uint32_t
     return PGM_OK;
 }
 
+pgm::BuildQueues build_queues(pgm_ctx *c) {
+    pgm::BuildQueues q;
+    q.entries = c->bq_entries.as<uint4>();
+    q.count = c->bq_counters.as<unsigned int>();
+    q.cursor = c->bq_counters.as<unsigned int>() + PGM_MAX_REGIONS;
+    q.cap = c->bq_cap;
+    q.region_bits = c->bq_region_bits;
+    return q;
+}
+
+// Step 1 of the table build for reads [r_begin, r_end): seeds -> region queues (or straight into a small table).
 int build_range(pgm_ctx *ctx, uint32_t r_begin, uint32_t r_end, int continuation) {
     if (r_end <= r_begin) return PGM_OK;
     const uint32_t tail = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
-    const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(r_end - r_begin, 256), (uint64_t)ctx->sm_count * 8);
-    KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid, 256, 0, ctx->stream>>>(
-        reads_view(ctx), table_view(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail,
+    const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(r_end - r_begin, PGM_BUILD_THREADS), (uint64_t)ctx->sm_count * 8);
+    KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid, PGM_BUILD_THREADS, ctx->bq_region_bits ? (size_t)ctx->parts * PGM_BUILD_THREADS * sizeof(uint4) : 0, ctx->stream>>>(
+        reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail,
         ctx->counters.as<unsigned long long>() + 4));
+    if (ctx->bq_region_bits) ctx->bq_pending = true;
+    return PGM_OK;
+}
+
+// Step 2: insert the queued patterns region by region.
+int build_flush(pgm_ctx *ctx) {
+    if (!ctx->bq_pending) return PGM_OK;
+    KLAUNCH(PGM_K_BUILD_TABLE, "build_insert_kernel", pgm::build_insert_kernel<<<ctx->sm_count * 8, PGM_INSERT_THREADS, 0, ctx->stream>>>(
+        table_view(ctx), build_queues(ctx)));
+    ctx->bq_pending = false;
     return PGM_OK;
 }
 
@@ -389,6 +413,7 @@ int pgm_create(int device, pgm_ctx **out) {
     ctx = new pgm_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *t = getenv("PGM_TWO_STEP_BUILD")) ctx->two_step_build = atoi(t);   // 0 off, 1 auto, 2 always (tests)
     if (const char *g = getenv("PGM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob
     ctx->persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
     ctx->window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
@@ -426,7 +451,7 @@ void pgm_destroy(pgm_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->f_lo, &ctx->f_hi, &ctx->r_lo, &ctx->r_hi, &ctx->ascii_stage, &ctx->packed_stage,
                       &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
-                      &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter,
+                      &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter, &ctx->bq_entries, &ctx->bq_counters,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
     for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -629,6 +654,26 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     }
     if (!continuation) CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
     else CU(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 4, 0, sizeof(unsigned long long), ctx->stream));
+    // region queues of the two-step build: regions of about 16 MB of buckets, only for tables well beyond the L2
+    {
+        const uint64_t table_bytes = nb64 * 32;
+        uint32_t rb = 0;
+        if (ctx->two_step_build && (table_bytes >= (256ull << 20) || ctx->two_step_build == 2)) {
+            rb = (uint32_t)ceil_log2((table_bytes + (16ull << 20) - 1) / (16ull << 20));
+            rb = std::min<uint32_t>(std::max<uint32_t>(rb, ctx->two_step_build == 2 ? 3u : 1u), 6);   // PGM_MAX_REGIONS = 64
+        }
+        ctx->bq_region_bits = rb;
+        ctx->bq_pending = false;
+        if ((rc = ensure(ctx, ctx->bq_counters, 2 * PGM_MAX_REGIONS * sizeof(unsigned int)))) return rc;
+        CU(cudaMemsetAsync(ctx->bq_counters.p, 0, 2 * PGM_MAX_REGIONS * sizeof(unsigned int), ctx->stream));
+        if (rb) {
+            const uint64_t per_region = (n_patterns >> rb) + (n_patterns >> (rb + 4)) + 4096;   // mean + 6 % + slack
+            ctx->bq_cap = (uint32_t)std::min<uint64_t>(per_region, 0xFFFFFFF0ull);
+            if ((rc = ensure(ctx, ctx->bq_entries, ((size_t)ctx->bq_cap << rb) * sizeof(uint4)))) return rc;
+        } else {
+            ctx->bq_cap = 0;
+        }
+    }
     ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
     ctx->outputs_valid = false;
     if (ctx->reads_pending && continuation && (rc = upload_reads(ctx, false))) return rc;   // (not a sensible call order)
@@ -646,6 +691,7 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
         if ((rc = build_range(ctx, 0, n, continuation ? 1 : 0))) return rc;
         if ((rc = enqueue_text_copies(ctx, true))) return rc;      // start a pending text upload behind the build
     }
+    if ((rc = build_flush(ctx))) return rc;
     ctx->phase_active = true;
     return PGM_OK;
 }

@@ -400,80 +400,139 @@ __device__ __forceinline__ uint32_t extract32(const uint32_t *w, uint32_t nwords
     return __funnelshift_r(a, b, bit & 31);
 }
 
-// One thread per read: for each of its `parts` seeds, fold read bases [j*n, (j+1)*n) into the canonical form
-// (the record's plane words come through L1: adjacent lanes read adjacent records), set the filter bits and
-// insert the pattern into the first bucket of its probe sequence with room.  Restates addReadsSetOfPatterns
-// (ConstantLengthPatternsOnTextHashMatcher.cpp:23-42); the reference's pattern index r * parts + j (:39) is
-// kept as (r << part_bits) | j.  Reads already matched with <= min_mm mismatches are left out when
-// `continuation` (the matchedReadsBitmap argument, ReadsMatchers.cpp:290-291).
-__global__ void __launch_bounds__(256) build_table_kernel(ReadsView reads, TableView tab, uint32_t r_begin, uint32_t r_end,
-                                                          uint32_t seed_len, uint32_t parts, uint32_t min_mm, int continuation,
-                                                          uint32_t tail_mask, unsigned long long *inserted) {
+// Insert one pattern: first bucket of its double-hashing sequence with an empty slot (256-bit bucket load + CAS); when
+// PGM_WALK_CAP buckets in a row are full and one of them already holds this key, chain behind that slot instead.
+__device__ __forceinline__ void table_insert(const TableView &tab, uint32_t h1, uint32_t h2, uint32_t pat) {
+    const uint32_t tag = seed_tag(h2);
+    uint32_t b = __umulhi(h1, tab.n_buckets);
+    const uint32_t step = 1u + __umulhi(h2 * 0x9E3779B1u, tab.n_buckets - 1u);
+    const unsigned long long mine = ((unsigned long long)tag << 32) | pat;
+    unsigned long long *same_slot = nullptr;
+    uint32_t walked = 0;
+    for (;;) {
+        unsigned long long *bp = reinterpret_cast<unsigned long long *>(tab.buckets + b);
+        const u32x8 s = ld256_cg(bp);
+        bool done = false, saw_empty = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (done) break;
+            if (s.v[2 * k + 1] == 0xFFFFFFFFu) {
+                saw_empty = true;
+                done = atomicCAS(bp + k, PGM_EMPTY64, mine) == PGM_EMPTY64;   // lost the race: try the next empty slot
+            } else if (same_slot == nullptr && (s.v[2 * k + 1] & 0x7FFFFFFFu) == tag) {
+                same_slot = bp + k;   // a slot that already holds this key
+            }
+        }
+        if (done) return;
+        if (saw_empty) continue;      // every empty slot seen was taken meanwhile: look at the bucket again
+        if (++walked >= PGM_WALK_CAP && same_slot != nullptr) {
+            // hot key: chain this pattern behind a slot that already holds the key
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(same_slot);
+            for (;;) {
+                tab.next[pat] = (uint32_t)old;
+                const unsigned long long nw = (((old >> 32) | 0x80000000ull) << 32) | pat;
+                const unsigned long long prev = atomicCAS(same_slot, old, nw);
+                if (prev == old) return;
+                old = prev;
+            }
+        }
+        b += step;
+        if (b >= tab.n_buckets) b -= tab.n_buckets;
+    }
+}
+
+// Region queues of the two-step table build: the bucket array is cut into 2^region_bits equal ranges of the home
+// bucket index (= ranges of h1); step 1 appends {h1, h2, pattern} to the queue of the pattern's region, step 2 inserts
+// region after region, so that all CTAs work on one L2-sized piece of the table at a time and every table line is
+// fetched from and written back to DRAM once (a direct random insert costs a 128-byte line read and a sector write
+// per pattern: the one-step build ran at the DRAM's random-transaction limit, profiles/kernels_metrics_c2_r01h.csv).
+struct BuildQueues {
+    uint4 *entries;             // region k owns entries [k * cap, (k + 1) * cap)
+    unsigned int *count;        // appended entries per region (may exceed cap: the excess was inserted directly)
+    unsigned int *cursor;       // step 2: next entry to take per region
+    uint32_t cap;
+    uint32_t region_bits;       // 0 = queues off (small tables): step 1 inserts directly
+};
+
+// Step 1.  One thread per read: for each of its `parts` seeds, fold read bases [j*n, (j+1)*n) into the canonical form
+// (the record's plane words come through L1: adjacent lanes read adjacent records), set the filter bits and append
+// the pattern to its region queue (ranks within the block through shared-memory counters, one global reservation per
+// region and block).  Restates addReadsSetOfPatterns (ConstantLengthPatternsOnTextHashMatcher.cpp:23-42); the
+// reference's pattern index r * parts + j (:39) is kept as (r << part_bits) | j.  Reads already matched with
+// <= min_mm mismatches are left out when `continuation` (the matchedReadsBitmap argument, ReadsMatchers.cpp:290-291).
+#define PGM_BUILD_THREADS 256
+#define PGM_MAX_REGIONS 64
+__global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsView reads, TableView tab, BuildQueues q, uint32_t r_begin,
+                                                                        uint32_t r_end, uint32_t seed_len, uint32_t parts, uint32_t min_mm,
+                                                                        int continuation, uint32_t tail_mask, unsigned long long *inserted) {
+    extern __shared__ uint4 s_ent[];                                   // parts x blockDim staged entries {h1, h2, pattern, region | rank << 8}
+    __shared__ unsigned int s_count[PGM_MAX_REGIONS], s_base[PGM_MAX_REGIONS];
+    const uint32_t n_regions = q.region_bits ? 1u << q.region_bits : 0u;
     unsigned int n_ins = 0;
-    for (uint32_t r = r_begin + blockIdx.x * blockDim.x + threadIdx.x; r < r_end; r += gridDim.x * blockDim.x) {
-        uint32_t stride16; bool is_n;
-        const uint4 *rec = record_of(reads, r, stride16, is_n);
-        if (continuation && (__ldg(reinterpret_cast<const uint32_t *>(rec) + 1) >> 24) <= min_mm) continue;
+    const uint32_t span = gridDim.x * blockDim.x;
+    const uint32_t rounds = (r_end - r_begin + span - 1) / span;       // same trip count for the whole block (barriers inside)
+    for (uint32_t it = 0; it < rounds; it++) {
+        const uint32_t r = r_begin + it * span + blockIdx.x * blockDim.x + threadIdx.x;
+        bool active = r < r_end;
+        uint32_t stride16 = 4; bool is_n = false;
+        const uint4 *rec = reads.lq;
+        if (active) {
+            rec = record_of(reads, r, stride16, is_n);
+            if (continuation && (__ldg(reinterpret_cast<const uint32_t *>(rec) + 1) >> 24) <= min_mm) active = false;
+        }
         const uint32_t *pl = reinterpret_cast<const uint32_t *>(rec) + 4;   // ACGT: lo,hi pairs; ACGNT: lo,hi,nm,0 quadruples
         const uint32_t il = is_n ? 4u : 2u;
         const uint32_t nch = (seed_len + 31) >> 5;
+        if (n_regions) {
+            for (uint32_t k = threadIdx.x; k < n_regions; k += blockDim.x) s_count[k] = 0;
+            __syncthreads();
+        }
         for (uint32_t j = 0; j < parts; j++) {
-            uint32_t P = 0, Q = 0, R = 0, FN = 0;
-            for (uint32_t i = 0; i < nch; i++) {
-                const uint32_t bit = j * seed_len + 32 * i;
-                const uint32_t m = (i == nch - 1) ? tail_mask : 0xFFFFFFFFu;
-                const uint32_t l = extract32(pl, reads.W, il, bit) & m;
-                const uint32_t h = extract32(pl + 1, reads.W, il, bit) & m;
-                P ^= l; Q ^= h; R ^= (l & h);
-                if (is_n) FN ^= extract32(pl + 2, reads.W, il, bit) & m;
-            }
-            // a seed whose N parity is odd in some rotation class can never collide with an ACGT window
-            if (FN != 0) continue;
-            const uint64_t hv = seed_hash64(P, Q, R);
-            const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
-            const uint32_t tag = seed_tag(h2);
-            const uint32_t pat = (r << reads.part_bits) | j;
-            if (tab.filter) {
-                const uint32_t f = filter_hash(P, Q, R);
-                atomicOr(tab.filter + (f & tab.filter_mask), filter_bits(f));
-            }
-            uint32_t b = __umulhi(h1, tab.n_buckets);
-            const uint32_t step = 1u + __umulhi(h2 * 0x9E3779B1u, tab.n_buckets - 1u);
-            const unsigned long long mine = ((unsigned long long)tag << 32) | pat;
-            unsigned long long *same_slot = nullptr;
-            uint32_t walked = 0;
-            for (;;) {
-                unsigned long long *bp = reinterpret_cast<unsigned long long *>(tab.buckets + b);
-                const u32x8 s = ld256_cg(bp);
-                bool done = false, saw_empty = false;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (done) break;
-                    if (s.v[2 * k + 1] == 0xFFFFFFFFu) {
-                        saw_empty = true;
-                        done = atomicCAS(bp + k, PGM_EMPTY64, mine) == PGM_EMPTY64;   // lost the race: try the next empty slot
-                    } else if (same_slot == nullptr && (s.v[2 * k + 1] & 0x7FFFFFFFu) == tag) {
-                        same_slot = bp + k;   // a slot that already holds this key
+            uint4 ent = make_uint4(0, 0, 0, 0xFFFFFFFFu);
+            if (active) {
+                uint32_t P = 0, Q = 0, R = 0, FN = 0;
+                for (uint32_t i = 0; i < nch; i++) {
+                    const uint32_t bit = j * seed_len + 32 * i;
+                    const uint32_t m = (i == nch - 1) ? tail_mask : 0xFFFFFFFFu;
+                    const uint32_t l = extract32(pl, reads.W, il, bit) & m;
+                    const uint32_t h = extract32(pl + 1, reads.W, il, bit) & m;
+                    P ^= l; Q ^= h; R ^= (l & h);
+                    if (is_n) FN ^= extract32(pl + 2, reads.W, il, bit) & m;
+                }
+                // a seed whose N parity is odd in some rotation class can never collide with an ACGT window
+                if (FN == 0) {
+                    const uint64_t hv = seed_hash64(P, Q, R);
+                    const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
+                    const uint32_t pat = (r << reads.part_bits) | j;
+                    if (tab.filter) {
+                        const uint32_t f = filter_hash(P, Q, R);
+                        atomicOr(tab.filter + (f & tab.filter_mask), filter_bits(f));
+                    }
+                    n_ins++;
+                    if (n_regions) {
+                        const uint32_t region = h1 >> (32 - q.region_bits);
+                        ent = make_uint4(h1, h2, pat, region | (atomicAdd(&s_count[region], 1u) << 8));
+                    } else {
+                        table_insert(tab, h1, h2, pat);
                     }
                 }
-                if (done) break;
-                if (saw_empty) continue;      // every empty slot seen was taken meanwhile: look at the bucket again
-                if (++walked >= PGM_WALK_CAP && same_slot != nullptr) {
-                    // hot key: chain this pattern behind a slot that already holds the key
-                    unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(same_slot);
-                    for (;;) {
-                        tab.next[pat] = (uint32_t)old;
-                        const unsigned long long nw = (((old >> 32) | 0x80000000ull) << 32) | pat;
-                        const unsigned long long prev = atomicCAS(same_slot, old, nw);
-                        if (prev == old) break;
-                        old = prev;
-                    }
-                    break;
-                }
-                b += step;
-                if (b >= tab.n_buckets) b -= tab.n_buckets;
             }
-            n_ins++;
+            if (n_regions) s_ent[j * blockDim.x + threadIdx.x] = ent;
+        }
+        if (n_regions) {
+            // one reservation per region and block, then every thread writes its own entries
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < n_regions; k += blockDim.x)
+                s_base[k] = s_count[k] ? atomicAdd(q.count + k, s_count[k]) : 0u;
+            __syncthreads();
+            for (uint32_t j = 0; j < parts; j++) {
+                const uint4 e = s_ent[j * blockDim.x + threadIdx.x];
+                if (e.w != 0xFFFFFFFFu) {
+                    const uint32_t region = e.w & 0xFFu, slot = s_base[region] + (e.w >> 8);
+                    if (slot < q.cap) q.entries[(size_t)region * q.cap + slot] = make_uint4(e.x, e.y, e.z, 0);
+                    else table_insert(tab, e.x, e.y, e.z);             // queue full (skewed hashes): insert directly
+                }
+            }
         }
     }
     // one counter update per block
@@ -485,6 +544,33 @@ __global__ void __launch_bounds__(256) build_table_kernel(ReadsView reads, Table
     if ((threadIdx.x & 31) == 0 && n_ins) atomicAdd(&blk, n_ins);
     __syncthreads();
     if (threadIdx.x == 0 && blk) atomicAdd(inserted, (unsigned long long)blk);
+}
+
+// Step 2.  Region after region: CTAs take chunks of the region's queue through a shared cursor and insert; a CTA moves
+// on when the region is used up, so at any time the running CTAs touch one or two L2-sized pieces of the bucket array
+// (a plain grid-stride loop lets the CTAs drift apart over many regions: twice the DRAM traffic, measured).
+#define PGM_INSERT_CHUNK 2048
+#define PGM_INSERT_THREADS 256
+__global__ void __launch_bounds__(PGM_INSERT_THREADS, 8) build_insert_kernel(TableView tab, BuildQueues q) {
+    __shared__ unsigned int s_first[2];
+    const uint32_t n_regions = 1u << q.region_bits;
+    uint32_t flip = 0;
+    for (uint32_t k = 0; k < n_regions; k++) {
+        const uint32_t n = min(__ldg(q.count + k), q.cap);
+        const uint4 *src = q.entries + (size_t)k * q.cap;
+        for (;;) {
+            if (threadIdx.x == 0) s_first[flip] = atomicAdd(q.cursor + k, (unsigned int)PGM_INSERT_CHUNK);
+            __syncthreads();                                           // one barrier per chunk: the slot alternates
+            const uint32_t first = s_first[flip];
+            flip ^= 1;
+            if (first >= n) break;
+            const uint32_t last = min(first + PGM_INSERT_CHUNK, n);
+            for (uint32_t i = first + threadIdx.x; i < last; i += PGM_INSERT_THREADS) {
+                const uint4 e = __ldcs(src + i);
+                table_insert(tab, e.x, e.y, e.z);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ the scan

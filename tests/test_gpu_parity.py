@@ -206,3 +206,17 @@ def test_text_sharded_contexts_match_oracle(world, kw):
             assert bad.size == 0, (f"{inp.name} world {world} {kw}: {bad.size} reads differ, first {bad[:5]}: gpu {got.pos[bad[:5]]} "
                                    f"{got.rc[bad[:5]]} {got.mm[bad[:5]]} oracle {want.pos[bad[:5]]} {want.rc[bad[:5]]} {want.mm[bad[:5]]}")
             assert got.matched == want.matched
+
+
+def test_two_step_table_build_forced(monkeypatch):
+    """The region-queued table build (used for tables beyond the L2) forced onto small inputs, including hot seeds
+    that overflow a region queue and fall back to direct inserts."""
+    monkeypatch.setenv("PGM_TWO_STEP_BUILD", "2")
+    for inp in (synth.adversarial(41, 100), synth.adversarial(42, 150), synth.workload(200_000, 50_000, 150, 0.005, seed=43, n_frac=0.02, name="c2 shape")):
+        _check(inp)
+        _check(inp, pre_reads_exact_matching_chars=inp.read_len)
+    rng = np.random.default_rng(44)
+    g = synth.random_genome(20_000, rng)
+    dup = np.repeat(synth.sample_reads(g, 3, 100, 0.01, rng), 4000, axis=0)      # 3 reads x 4000 copies: skewed regions
+    inp = synth.MatcherInputs(g, np.concatenate([dup, synth.sample_reads(g, 2000, 100, 0.01, rng)]), np.zeros((0, 100), np.uint8), 100, "skew")
+    _check(inp)
