@@ -302,9 +302,15 @@ int build_range(pgm_ctx *ctx, uint32_t r_begin, uint32_t r_end, int continuation
     if (r_end <= r_begin) return PGM_OK;
     const uint32_t tail = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
     const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(r_end - r_begin, PGM_BUILD_THREADS), (uint64_t)ctx->sm_count * 8);
-    KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel", pgm::build_table_kernel<<<grid, PGM_BUILD_THREADS, ctx->bq_region_bits ? (size_t)ctx->parts * PGM_BUILD_THREADS * sizeof(uint4) : 0, ctx->stream>>>(
-        reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail,
-        ctx->counters.as<unsigned long long>() + 4));
+    const size_t smem = ctx->bq_region_bits ? (size_t)ctx->parts * PGM_BUILD_THREADS * sizeof(uint4) : 0;
+    const bool fast = ctx->n_n == 0 && ctx->lq_stride16 == 4;         // only ACGT reads, 64-byte records: record held in registers
+    KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel",
+            if (fast) pgm::build_table_kernel<true><<<grid, PGM_BUILD_THREADS, smem, ctx->stream>>>(
+                reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail,
+                ctx->counters.as<unsigned long long>() + 4);
+            else pgm::build_table_kernel<false><<<grid, PGM_BUILD_THREADS, smem, ctx->stream>>>(
+                reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail,
+                ctx->counters.as<unsigned long long>() + 4));
     if (ctx->bq_region_bits) ctx->bq_pending = true;
     return PGM_OK;
 }
@@ -658,7 +664,8 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     {
         const uint64_t table_bytes = nb64 * 32;
         uint32_t rb = 0;
-        if (ctx->two_step_build && (table_bytes >= (256ull << 20) || ctx->two_step_build == 2)) {
+        // (host reads arriving chunk by chunk: the one-step inserts hide behind the H2D copies, a queue flush would not)
+        if ((ctx->two_step_build == 1 && table_bytes >= (256ull << 20) && !ctx->reads_pending) || ctx->two_step_build == 2) {
             rb = (uint32_t)ceil_log2((table_bytes + (16ull << 20) - 1) / (16ull << 20));
             rb = std::min<uint32_t>(std::max<uint32_t>(rb, ctx->two_step_build == 2 ? 3u : 1u), 6);   // PGM_MAX_REGIONS = 64
         }

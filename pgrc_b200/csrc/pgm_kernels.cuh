@@ -462,6 +462,7 @@ struct BuildQueues {
 // <= min_mm mismatches are left out when `continuation` (the matchedReadsBitmap argument, ReadsMatchers.cpp:290-291).
 #define PGM_BUILD_THREADS 256
 #define PGM_MAX_REGIONS 64
+template <bool FAST>
 __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsView reads, TableView tab, BuildQueues q, uint32_t r_begin,
                                                                         uint32_t r_end, uint32_t seed_len, uint32_t parts, uint32_t min_mm,
                                                                         int continuation, uint32_t tail_mask, unsigned long long *inserted) {
@@ -476,7 +477,16 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
         bool active = r < r_end;
         uint32_t stride16 = 4; bool is_n = false;
         const uint4 *rec = reads.lq;
-        if (active) {
+        u32x8 w0, w1;                                                  // FAST (ACGT set, 64-byte records): the whole record in registers
+        if (FAST) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { w0.v[k] = 0; w1.v[k] = 0; }
+            if (active) {
+                rec = reads.lq + (size_t)r * 4;
+                w0 = ld256_stream(rec); w1 = ld256_stream(rec + 2);
+                if (continuation && (w0.v[1] >> 24) <= min_mm) active = false;
+            }
+        } else if (active) {
             rec = record_of(reads, r, stride16, is_n);
             if (continuation && (__ldg(reinterpret_cast<const uint32_t *>(rec) + 1) >> 24) <= min_mm) active = false;
         }
@@ -491,13 +501,31 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
             uint4 ent = make_uint4(0, 0, 0, 0xFFFFFFFFu);
             if (active) {
                 uint32_t P = 0, Q = 0, R = 0, FN = 0;
-                for (uint32_t i = 0; i < nch; i++) {
-                    const uint32_t bit = j * seed_len + 32 * i;
-                    const uint32_t m = (i == nch - 1) ? tail_mask : 0xFFFFFFFFu;
-                    const uint32_t l = extract32(pl, reads.W, il, bit) & m;
-                    const uint32_t h = extract32(pl + 1, reads.W, il, bit) & m;
-                    P ^= l; Q ^= h; R ^= (l & h);
-                    if (is_n) FN ^= extract32(pl + 2, reads.W, il, bit) & m;
+                if (FAST) {
+                    // a base at read position x lands on bit (x - j*n) mod 32: every 32-base group contributes
+                    // rotr(group & [seed range], (j*n) mod 32) — no cross-register funnel shifts, static register indices
+                    const int b0 = (int)(j * seed_len), b1 = b0 + (int)seed_len;
+                    const uint32_t sh = (uint32_t)b0 & 31u;
+#pragma unroll
+                    for (int g = 0; g < 6; g++) {
+                        const int lo_bit = max(b0 - 32 * g, 0), hi_bit = min(b1 - 32 * g, 32);
+                        if (hi_bit > lo_bit) {
+                            uint32_t m = hi_bit == 32 ? 0xFFFFFFFFu : (1u << hi_bit) - 1u;
+                            m &= ~((1u << lo_bit) - 1u);
+                            const uint32_t l = (g < 2 ? w0.v[4 + 2 * g] : w1.v[2 * (g - 2)]) & m;
+                            const uint32_t h = (g < 2 ? w0.v[5 + 2 * g] : w1.v[2 * (g - 2) + 1]) & m;
+                            P ^= rotr32(l, sh); Q ^= rotr32(h, sh); R ^= rotr32(l & h, sh);
+                        }
+                    }
+                } else {
+                    for (uint32_t i = 0; i < nch; i++) {
+                        const uint32_t bit = j * seed_len + 32 * i;
+                        const uint32_t m = (i == nch - 1) ? tail_mask : 0xFFFFFFFFu;
+                        const uint32_t l = extract32(pl, reads.W, il, bit) & m;
+                        const uint32_t h = extract32(pl + 1, reads.W, il, bit) & m;
+                        P ^= l; Q ^= h; R ^= (l & h);
+                        if (is_n) FN ^= extract32(pl + 2, reads.W, il, bit) & m;
+                    }
                 }
                 // a seed whose N parity is odd in some rotation class can never collide with an ACGT window
                 if (FN == 0) {
