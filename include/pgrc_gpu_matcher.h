@@ -165,7 +165,9 @@ uint64_t pgm_kernel_launches(const pgm_ctx *ctx);
  * synchronizes, adds up the event durations per kernel since the last call and resets them.
  * launches[] counts the launches behind each sum. */
 enum { PGM_K_PACK_TEXT = 0, PGM_K_RC_TEXT, PGM_K_UNPACK_READS, PGM_K_INIT_STATE, PGM_K_BUILD_TABLE,
-       PGM_K_SCAN, PGM_K_RESOLVE, PGM_K_FINALIZE, PGM_K_ACCUM, PGM_K_COUNT };
+       PGM_K_SCAN, PGM_K_RESOLVE, PGM_K_FINALIZE, PGM_K_ACCUM,
+       PGM_K_SCAN_FILTER, PGM_K_SCAN_PROBE, PGM_K_SCAN_VERIFY, /* the three stages of the L2-blocked scan pipeline */
+       PGM_K_COUNT };
 typedef struct pgm_timings {
     double ms[PGM_K_COUNT];
     uint64_t launches[PGM_K_COUNT];

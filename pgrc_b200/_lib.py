@@ -24,7 +24,8 @@ EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pg
            "pgm_scan_pass", "pgm_get_accumulators", "pgm_put_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_map_reads",
            "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings"]
 
-KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators"]
+KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators",
+                "scan_filter", "scan_probe", "scan_verify"]
 
 
 class PgmStats(ctypes.Structure):

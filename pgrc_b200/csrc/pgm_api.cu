@@ -3,6 +3,7 @@
 // restated from PgTools::mapReadsIntoPg (matching/ReadsMatchers.cpp:693-783).
 #include "../../include/pgrc_gpu_matcher.h"
 #include "pgm_kernels.cuh"
+#include "pgm_blocked.cuh"
 
 #include <algorithm>
 #include <cctype>
@@ -47,6 +48,9 @@ struct pgm_ctx {
     int ctas_per_sm = 4;
     int two_step_build = 1;     // region-queued table build (PGM_TWO_STEP_BUILD=0 turns it off)
     int l2_hints = 1;           // 0 none, 1 per-load eviction hints, 2 hints + persisting access-policy window on the filter
+    int insert_prefetch = 1;    // build_insert_kernel prefetches the next region's buckets into the L2 (PGM_INSERT_PREFETCH)
+    int blocked_scan = 0;       // L2-blocked scan pipeline: 0 off, 1 auto (by size), 2 always, 3 always with tiny queues (PGM_BLOCKED_SCAN; tests)
+    int region_mb = 12, range_mb = 16;   // target sizes of a table region / a read range of the pipeline (PGM_REGION_MB, PGM_RANGE_MB)
     size_t persist_max = 0, window_max = 0, persist_set = 0;
 
     // text
@@ -77,6 +81,7 @@ struct pgm_ctx {
 
     // table
     DevBuf buckets, next, filter, bq_entries, bq_counters;
+    DevBuf sq_pos, sq_cand, sq_counters;   // queues of the L2-blocked scan pipeline (pgm_blocked.cuh)
     uint32_t bq_cap = 0, bq_region_bits = 0;
     bool bq_pending = false;    // region queues hold patterns that build_insert_kernel has not inserted yet
     uint64_t n_slots = 0;
@@ -319,7 +324,7 @@ int build_range(pgm_ctx *ctx, uint32_t r_begin, uint32_t r_end, int continuation
 int build_flush(pgm_ctx *ctx) {
     if (!ctx->bq_pending) return PGM_OK;
     KLAUNCH(PGM_K_BUILD_TABLE, "build_insert_kernel", pgm::build_insert_kernel<<<ctx->sm_count * 8, PGM_INSERT_THREADS, 0, ctx->stream>>>(
-        table_view(ctx), build_queues(ctx)));
+        table_view(ctx), build_queues(ctx), ctx->insert_prefetch));
     ctx->bq_pending = false;
     return PGM_OK;
 }
@@ -384,10 +389,58 @@ int filter_window(pgm_ctx *ctx, bool on) {
 }
 
 template <int NCH>
-void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s) {
+void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, bool filter_stage) {
     // FAST: only ACGT reads, records of exactly 64 bytes (read length <= 192)
-    if (sp.reads.n_n == 0 && sp.reads.lq_stride16 == 4) pgm::scan_kernel<NCH, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
-    else pgm::scan_kernel<NCH, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    if (filter_stage) pgm::scan_kernel<NCH, false, 1><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    else if (sp.reads.n_n == 0 && sp.reads.lq_stride16 == 4) pgm::scan_kernel<NCH, true, 0><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    else pgm::scan_kernel<NCH, false, 0><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+}
+
+void launch_scan_nch(int nch, const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, bool filter_stage) {
+    switch (nch) {
+        case 1: launch_scan<1>(sp, grid, s, filter_stage); break;
+        case 2: launch_scan<2>(sp, grid, s, filter_stage); break;
+        case 3: launch_scan<3>(sp, grid, s, filter_stage); break;
+        case 4: launch_scan<4>(sp, grid, s, filter_stage); break;
+        case 5: launch_scan<5>(sp, grid, s, filter_stage); break;
+        case 6: launch_scan<6>(sp, grid, s, filter_stage); break;
+        case 7: launch_scan<7>(sp, grid, s, filter_stage); break;
+        default: launch_scan<8>(sp, grid, s, filter_stage); break;
+    }
+}
+
+int floor_log2(uint64_t v) { int b = 0; while ((2ull << b) <= v) b++; return b; }
+
+// Geometry of the L2-blocked pipeline for one scan launch over `n_pos` window starts; false = use the fused kernel.
+bool plan_blocked(pgm_ctx *ctx, uint64_t n_pos, uint32_t n_tiles, pgm::StageQueues &q) {
+    memset(&q, 0, sizeof q);
+    const int mode = ctx->blocked_scan;
+    if (mode <= 0 || ctx->n_reads() == 0) return false;
+    const uint64_t table_bytes = (uint64_t)ctx->n_buckets * 32;
+    if ((uint64_t)n_tiles * PGM_TILE_POS >= (1ull << 31)) return false;              // queue positions are 31 bits
+    if (mode == 1) {
+        // pays when (i) the table is well beyond the L2, (ii) a region sees many more probes than it has lines
+        // (a long enough launch), (iii) the planes of the slice stay L2-resident next to a read range
+        if (table_bytes < (192ull << 20) || n_pos < (32ull << 20) || ctx->slice_len > (288ull << 20)) return false;
+    }
+    const bool forced = mode >= 2;
+    int rb = ceil_log2((table_bytes + ((uint64_t)ctx->region_mb << 20) - 1) / ((uint64_t)ctx->region_mb << 20));
+    rb = std::min(8, std::max(forced ? 3 : 1, rb));
+    const uint64_t rec_bytes = (uint64_t)ctx->lq_stride16 * 16;
+    int rs = floor_log2(std::max<uint64_t>(1, ((uint64_t)ctx->range_mb << 20) / rec_bytes));
+    const uint32_t n = ctx->n_reads();
+    if (forced) rs = std::max(0, ceil_log2(n) - 3);
+    while (((uint64_t)(n - 1) >> rs) >= PGM_SQ_MAX) rs++;
+    q.region_bits = (uint32_t)rb;
+    q.range_shift = (uint32_t)rs;
+    q.n_ranges = (uint32_t)(((uint64_t)(n - 1) >> rs) + 1);
+    // capacity: 60 % of the windows positive / verified, evenly spread, + slack; beyond that the pass falls back
+    const uint64_t pos_cap = mode == 3 ? 64 : (n_pos * 6 / 10 >> rb) + 4096;
+    const uint64_t cand_cap = mode == 3 ? 64 : n_pos * 6 / 10 / q.n_ranges + 4096;
+    if (pos_cap >= 0xFFFFFFF0ull || cand_cap >= 0xFFFFFFF0ull) return false;
+    q.pos_cap = (uint32_t)pos_cap;
+    q.cand_cap = (uint32_t)cand_cap;
+    return true;
 }
 
 } // namespace
@@ -420,6 +473,10 @@ int pgm_create(int device, pgm_ctx **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *t = getenv("PGM_TWO_STEP_BUILD")) ctx->two_step_build = atoi(t);   // 0 off, 1 auto, 2 always (tests)
+    if (const char *t = getenv("PGM_INSERT_PREFETCH")) ctx->insert_prefetch = atoi(t);
+    if (const char *t = getenv("PGM_BLOCKED_SCAN")) ctx->blocked_scan = atoi(t);
+    if (const char *t = getenv("PGM_REGION_MB")) ctx->region_mb = std::max(1, atoi(t));
+    if (const char *t = getenv("PGM_RANGE_MB")) ctx->range_mb = std::max(1, atoi(t));
     if (const char *g = getenv("PGM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob
     ctx->persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
     ctx->window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
@@ -458,7 +515,7 @@ void pgm_destroy(pgm_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->f_lo, &ctx->f_hi, &ctx->r_lo, &ctx->r_hi, &ctx->ascii_stage, &ctx->packed_stage,
                       &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
                       &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter, &ctx->bq_entries, &ctx->bq_counters,
-                      &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
+                      &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
     for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (cudaEvent_t e : ctx->ev_free) cudaEventDestroy(e);
@@ -647,7 +704,6 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     ctx->n_slots = nb64 * 4;
     ctx->part_bits = part_bits;
     CU(cudaMemsetAsync(ctx->buckets.p, 0xFF, nb64 * 32, ctx->stream));
-    CU(cudaMemsetAsync(ctx->next.p, 0xFF, std::max<uint64_t>(n_ids, 1) * 4, ctx->stream));
     int fbits = ctx->filter_log2_bits;
     if (fbits < 0) fbits = std::min(28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 8)));
     if (fbits > 0) {
@@ -743,16 +799,37 @@ int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
     ctx->aux_clean = false;
     ctx->outputs_valid = false;
     { int wrc = filter_window(ctx, true); if (wrc) return wrc; }
-    KLAUNCH(PGM_K_SCAN, "scan_kernel", switch (nch) {
-        case 1: launch_scan<1>(sp, grid, ctx->stream); break;
-        case 2: launch_scan<2>(sp, grid, ctx->stream); break;
-        case 3: launch_scan<3>(sp, grid, ctx->stream); break;
-        case 4: launch_scan<4>(sp, grid, ctx->stream); break;
-        case 5: launch_scan<5>(sp, grid, ctx->stream); break;
-        case 6: launch_scan<6>(sp, grid, ctx->stream); break;
-        case 7: launch_scan<7>(sp, grid, ctx->stream); break;
-        default: launch_scan<8>(sp, grid, ctx->stream); break;
-    });
+    if (plan_blocked(ctx, le - lb, sp.n_tiles, sp.sq)) {
+        // L2-blocked pipeline: filter stage (text order) -> probe stage (table-region order) -> verify stage (read-range
+        // order), then the fused kernel as a fallback that only runs when a queue overflowed
+        pgm::StageQueues &q = sp.sq;
+        int rc;
+        if ((rc = ensure(ctx, ctx->sq_pos, ((size_t)q.pos_cap << q.region_bits) * sizeof(uint4))) ||
+            (rc = ensure(ctx, ctx->sq_cand, (size_t)q.cand_cap * q.n_ranges * sizeof(uint2))) ||
+            (rc = ensure(ctx, ctx->sq_counters, (4 * PGM_SQ_MAX + 2 + 8) * sizeof(unsigned int)))) return rc;
+        unsigned int *cbase = ctx->sq_counters.as<unsigned int>();
+        q.pos_entries = ctx->sq_pos.as<uint4>(); q.cand_entries = ctx->sq_cand.as<uint2>();
+        q.pos_count = cbase; q.pos_cursor = cbase + PGM_SQ_MAX; q.cand_count = cbase + 2 * PGM_SQ_MAX; q.cand_cursor = cbase + 3 * PGM_SQ_MAX;
+        q.overflow = cbase + 4 * PGM_SQ_MAX;
+        q.counters = reinterpret_cast<unsigned long long *>(cbase + 4 * PGM_SQ_MAX + 2);
+        CU(cudaMemsetAsync(cbase, 0, (4 * PGM_SQ_MAX + 2 + 8) * sizeof(unsigned int), ctx->stream));
+        KLAUNCH(PGM_K_SCAN_FILTER, "scan_kernel (filter stage)", launch_scan_nch(nch, sp, grid, ctx->stream, true));
+        pgm::VerifyParams vp;
+        memset(&vp, 0, sizeof vp);
+        vp.tlo = sp.tlo; vp.thi = sp.thi;
+        vp.pos_origin = sp.slice_origin + (uint64_t)sp.first_word * 32;
+        vp.bit_origin = (uint64_t)sp.first_word * 32;
+        vp.pg_len = pg;
+        vp.seed_len = sp.seed_len; vp.parts = sp.parts; vp.max_mm = sp.max_mm; vp.min_mm = sp.min_mm; vp.rev_mode = sp.rev_mode;
+        vp.tab = sp.tab; vp.reads = sp.reads; vp.pr = sp.pr; vp.sq = q;
+        KLAUNCH(PGM_K_SCAN_PROBE, "probe_kernel", pgm::probe_kernel<<<ctx->sm_count * 6, PGM_PROBE_THREADS, 0, ctx->stream>>>(vp));
+        KLAUNCH(PGM_K_SCAN_VERIFY, "verify_kernel",
+                if (ctx->lq_stride16 == 4) pgm::verify_kernel<true><<<ctx->sm_count * 4, PGM_VERIFY_THREADS, 0, ctx->stream>>>(vp);
+                else pgm::verify_kernel<false><<<ctx->sm_count * 4, PGM_VERIFY_THREADS, 0, ctx->stream>>>(vp));
+        sp.only_if = q.overflow;
+        CU(cudaMemsetAsync(sp.tile_counter, 0, sizeof(unsigned int), ctx->stream));
+    }
+    KLAUNCH(PGM_K_SCAN, "scan_kernel", launch_scan_nch(nch, sp, grid, ctx->stream, false));
     return filter_window(ctx, false);
 }
 } // namespace

@@ -115,6 +115,22 @@ struct PerRead {
     int *touched;                   // set when any of the three above was written in this pass
 };
 
+// Queues of the L2-blocked scan pipeline (pgm_blocked.cuh): the filter stage appends every filter-positive window
+// to the queue of its table region (= range of home buckets = range of h1), the probe stage appends every tag hit
+// to the queue of its read range.  Entries beyond a queue's capacity raise *overflow: the pass is then redone by the
+// fused scan kernel (all per-read accumulators are idempotent MIN / OR updates).
+#define PGM_SQ_MAX 256                      // most table regions / read ranges
+struct StageQueues {
+    uint4 *pos_entries;             // region k owns [k * pos_cap, (k + 1) * pos_cap): {h1, h2, launch-relative position, 0}
+    uint2 *cand_entries;            // range k owns [k * cand_cap, (k + 1) * cand_cap): {position | chain << 31, pattern}
+    unsigned int *pos_count, *pos_cursor, *cand_count, *cand_cursor;   // PGM_SQ_MAX each
+    unsigned int *overflow;
+    unsigned long long *counters;   // staged work counters [0] candidates [1] verified [2] accepted [3] filter positives
+    uint32_t pos_cap, cand_cap;
+    uint32_t region_bits;           // table regions = 1 << region_bits (1..8), region = h1 >> (32 - region_bits)
+    uint32_t range_shift, n_ranges; // read range = read >> range_shift
+};
+
 struct ScanParams {
     const uint32_t *tlo, *thi;      // planes of this pass's text, local origin at word 0
     uint64_t slice_origin;          // global coordinate of local position 0 (this pass's coordinates)
@@ -132,6 +148,8 @@ struct ScanParams {
     PerRead pr;
     unsigned int *tile_counter;
     unsigned long long *counters;   // [0] candidates [1] verified [2] accepted [3] filter positives
+    StageQueues sq;                 // MODE 1 (filter stage of the L2-blocked pipeline) only
+    const unsigned int *only_if;    // fused kernel as the pipeline's fallback: runs only when *only_if != 0, else commits sq.counters
 };
 
 // ------------------------------------------------------------------------------------------ small helpers
@@ -289,6 +307,16 @@ __global__ void rc_text_kernel(const uint32_t *__restrict__ flo, const uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------ reads
+// bits 0, 2, 4, ... 30 of x packed into the low 16 bits
+__device__ __forceinline__ uint32_t compress_even(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+
 // Packed reads (reference layout, SymbolsPackingFacility.cpp:147-185) -> read records (layout above) with a
 // fresh header {unmatched, no key}.  A block stages its reads' packed bytes in shared memory with coalesced
 // loads, one thread builds one record in shared memory, and the block writes the records out coalesced.
@@ -325,28 +353,30 @@ __global__ void unpack_reads_kernel(const uint8_t *__restrict__ packed, uint32_t
         uint4 *dst = sout + (size_t)threadIdx.x * stride16;
         dst[0] = make_uint4(0xFFFFFFFFu, 0xFF0000FFu, 0xFFFFFFFFu, 0x7FFFFFFFu);   // PGM_STATE_UNMATCHED, PGM_KEY_INF
         if (!with_n) {
-            // bases 4b..4b+3 of byte b, first base in the two most significant bits; the tail of the last byte is 'A' = 0
+            // 16 bases per 32-bit word of packed bytes (first base in the two most significant bits of its byte, the
+            // tail of the last byte is 'A' = 0): reversing the bits inside every byte (brev + byte swap) puts base i's
+            // hi bit at bit 2i and its lo bit at 2i+1; two even-bit compressions then give 16 bits of each plane.
+            const uint32_t boff = threadIdx.x * packed_len;
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(sbuf) + (boff >> 2);
+            const uint32_t sel = 0x3210u + 0x1111u * (boff & 3u);
+            const uint32_t nwords = (packed_len + 3) >> 2;
             for (uint32_t u = 1; u < stride16; u++) {
-                uint32_t w4[4] = {0, 0, 0, 0};
+                uint32_t pl[4] = {0, 0, 0, 0};                 // lo, hi of group 2(u-1); lo, hi of group 2(u-1)+1
 #pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const uint32_t g = 2 * (u - 1) + half;
-                    if (g < W) {
-                        uint32_t lo = 0, hi = 0;
-#pragma unroll
-                        for (int b = 0; b < 8; b++) {
-                            const uint32_t bi = g * 8 + b;
-                            const uint32_t v = bi < packed_len ? src[bi] : 0u;
-                            const uint32_t l4 = ((v >> 6) & 1) | (((v >> 4) & 1) << 1) | (((v >> 2) & 1) << 2) | ((v & 1) << 3);
-                            const uint32_t h4 = ((v >> 7) & 1) | (((v >> 5) & 1) << 1) | (((v >> 3) & 1) << 2) | (((v >> 1) & 1) << 3);
-                            lo |= l4 << (4 * b); hi |= h4 << (4 * b);
-                        }
-                        const uint32_t rem = read_len - 32 * g;
-                        if (rem < 32) { lo &= (1u << rem) - 1u; hi &= (1u << rem) - 1u; }
-                        w4[2 * half] = lo; w4[2 * half + 1] = hi;
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t k = 4 * (u - 1) + q;
+                    if (k < nwords) {
+                        const uint32_t v = __byte_perm(sw[k], sw[k + 1], sel);
+                        const uint32_t w = __byte_perm(__brev(v), 0u, 0x0123u);
+                        uint32_t h = compress_even(w), l = compress_even(w >> 1);
+                        const int rem = (int)read_len - 16 * (int)k;   // bases of the read in this word (bytes past the read are masked off)
+                        const uint32_t m = rem >= 16 ? 0xFFFFu : rem <= 0 ? 0u : (1u << rem) - 1u;
+                        l &= m; h &= m;
+                        pl[2 * (q >> 1)] |= l << (16 * (q & 1));
+                        pl[2 * (q >> 1) + 1] |= h << (16 * (q & 1));
                     }
                 }
-                dst[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                dst[u] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
         } else {
             uint32_t lo = 0, hi = 0, nm = 0, g = 0, bitpos = 0, p = 0;
@@ -429,6 +459,8 @@ __device__ __forceinline__ void table_insert(const TableView &tab, uint32_t h1, 
             // hot key: chain this pattern behind a slot that already holds the key
             unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(same_slot);
             for (;;) {
+                // next[] is not initialised: whoever extends a slot that is not chained yet marks its owner as the chain's end
+                if (!(old >> 63)) tab.next[(uint32_t)old] = PGM_NIL;
                 tab.next[pat] = (uint32_t)old;
                 const unsigned long long nw = (((old >> 32) | 0x80000000ull) << 32) | pat;
                 const unsigned long long prev = atomicCAS(same_slot, old, nw);
@@ -579,13 +611,20 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
 // (a plain grid-stride loop lets the CTAs drift apart over many regions: twice the DRAM traffic, measured).
 #define PGM_INSERT_CHUNK 2048
 #define PGM_INSERT_THREADS 256
-__global__ void __launch_bounds__(PGM_INSERT_THREADS, 8) build_insert_kernel(TableView tab, BuildQueues q) {
+__global__ void __launch_bounds__(PGM_INSERT_THREADS, 8) build_insert_kernel(TableView tab, BuildQueues q, int prefetch) {
     __shared__ unsigned int s_first[2];
     const uint32_t n_regions = 1u << q.region_bits;
     uint32_t flip = 0;
     for (uint32_t k = 0; k < n_regions; k++) {
         const uint32_t n = min(__ldg(q.count + k), q.cap);
         const uint4 *src = q.entries + (size_t)k * q.cap;
+        if (prefetch && k + 1 < n_regions) {
+            // pull this CTA's share of the next region's bucket lines into the L2 while this region is being filled
+            const uint64_t b0 = ((uint64_t)(k + 1) * tab.n_buckets) >> q.region_bits, b1 = ((uint64_t)(k + 2) * tab.n_buckets) >> q.region_bits;
+            const uint64_t lines = (b1 - b0 + 3) / 4;
+            for (uint64_t l = (uint64_t)blockIdx.x * PGM_INSERT_THREADS + threadIdx.x; l < lines; l += (uint64_t)gridDim.x * PGM_INSERT_THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tab.buckets + b0 + 4 * l));
+        }
         for (;;) {
             if (threadIdx.x == 0) s_first[flip] = atomicAdd(q.cursor + k, (unsigned int)PGM_INSERT_CHUNK);
             __syncthreads();                                           // one barrier per chunk: the slot alternates
@@ -671,9 +710,18 @@ __device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, cons
 //      atomicMin's the key inside the record.  Restates iterateOver/moveNext (HashMatcher.h:42-68) +
 //      executeMatching (ReadsMatchers.cpp:297-341) without their sequential order; the decision is deferred to
 //      resolve_kernel.
-template <int NCH, bool FAST>
+// MODE 1 is the first stage of the L2-blocked pipeline (pgm_blocked.cuh): A1 as above, then every filter positive is
+// hashed and appended to the queue of its table region instead of being probed (ranks within the tile through
+// shared-memory counters, one global reservation per region and tile); the per-warp candidate queues' shared memory
+// holds the ranks.
+template <int NCH, bool FAST, int MODE>
 __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_constant__ ScanParams p) {
     __shared__ __align__(128) ScanShared sm;
+    if (MODE == 0 && p.only_if != nullptr && *p.only_if == 0) {
+        // the pipeline finished without a queue overflow: nothing to redo, its staged counters become final
+        if (blockIdx.x == 0 && threadIdx.x < 4) p.counters[threadIdx.x] += p.sq.counters[threadIdx.x];
+        return;
+    }
     // the warp index through a shuffle: lets the compiler treat it (and every branch on it) as warp-uniform
     const uint32_t t = threadIdx.x, warp = __shfl_sync(PGM_FULL, t >> 5, 0), lane = t & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -697,6 +745,8 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
         sm.q1_count[0] = 0; sm.q1_cursor[0] = 0;
         if (tile < p.n_tiles) issue_tile(tile, 0);
     }
+    if (MODE == 1)   // per-region counters of the tile being queued (behind the rank storage, see below)
+        for (uint32_t k = t; k < PGM_SQ_MAX; k += PGM_SCAN_THREADS) reinterpret_cast<unsigned int *>(&sm.wq[0][0])[PGM_TILE_POS + k] = 0;
     __syncthreads();
     uint32_t parity[2] = {0, 0};
     int buf = 0;
@@ -765,6 +815,40 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
             }
         }
         __syncthreads();
+
+        if constexpr (MODE == 1) {
+            static_assert(sizeof(sm.wq) >= PGM_TILE_POS * 4 + 2 * PGM_SQ_MAX * 4, "rank storage aliases the candidate queues");
+            uint32_t *slot = reinterpret_cast<uint32_t *>(&sm.wq[0][0]);            // per positive: region | rank << 8
+            unsigned int *cnt = reinterpret_cast<unsigned int *>(slot + PGM_TILE_POS), *rbase = cnt + PGM_SQ_MAX;
+            const uint32_t q1n = sm.q1_count[buf];
+            const uint32_t n_regions = 1u << p.sq.region_bits, rshift = 32u - p.sq.region_bits;
+            for (uint32_t i = t; i < q1n; i += PGM_SCAN_THREADS) {
+                const uint32_t h1 = (uint32_t)window_hash<NCH>(slo, shi, sm.q1[i], p.tail_mask);
+                const uint32_t region = h1 >> rshift;
+                slot[i] = region | (atomicAdd(&cnt[region], 1u) << 8);
+            }
+            __syncthreads();
+            for (uint32_t k = t; k < n_regions; k += PGM_SCAN_THREADS) {
+                const unsigned int c = cnt[k];
+                rbase[k] = c ? atomicAdd(p.sq.pos_count + k, c) : 0u;
+                cnt[k] = 0;
+            }
+            __syncthreads();
+            bool over = false;
+            for (uint32_t i = t; i < q1n; i += PGM_SCAN_THREADS) {
+                const uint32_t ppos = sm.q1[i];
+                const uint64_t hv = window_hash<NCH>(slo, shi, ppos, p.tail_mask);
+                const uint32_t s = slot[i], region = s & 0xFFu, idx = rbase[region] + (s >> 8);
+                if (idx < p.sq.pos_cap)
+                    __stcs(p.sq.pos_entries + (size_t)region * p.sq.pos_cap + idx,
+                           make_uint4((uint32_t)hv, (uint32_t)(hv >> 32), tile * PGM_TILE_POS + ppos, 0u));
+                else over = true;
+            }
+            if (over) *p.sq.overflow = 1u;
+            __syncthreads();
+            buf ^= 1;
+            continue;
+        }
 
         // ---- A2 + B, warp-autonomous
         const uint32_t q1n = sm.q1_count[buf];
@@ -1011,7 +1095,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
     for (int k = 0; k < 4; k++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cv[k] += __shfl_xor_sync(PGM_FULL, cv[k], o);
-        if (lane == 0 && cv[k]) atomicAdd(p.counters + k, cv[k]);
+        if (lane == 0 && cv[k]) atomicAdd((MODE == 1 ? p.sq.counters : p.counters) + k, cv[k]);
     }
 }
 

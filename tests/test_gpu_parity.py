@@ -220,3 +220,41 @@ def test_two_step_table_build_forced(monkeypatch):
     dup = np.repeat(synth.sample_reads(g, 3, 100, 0.01, rng), 4000, axis=0)      # 3 reads x 4000 copies: skewed regions
     inp = synth.MatcherInputs(g, np.concatenate([dup, synth.sample_reads(g, 2000, 100, 0.01, rng)]), np.zeros((0, 100), np.uint8), 100, "skew")
     _check(inp)
+
+
+@pytest.mark.parametrize("mode", ["2", "3"])
+def test_blocked_scan_pipeline_forced(monkeypatch, mode):
+    """The L2-blocked scan pipeline (filter -> probe by table region -> verify by read range; used for tables beyond
+    the L2) forced onto small inputs.  Mode 3 shrinks the stage queues to 64 entries, so they overflow and the fused
+    kernel redoes the pass (idempotent accumulators): both routes must give the oracle's result."""
+    monkeypatch.setenv("PGM_BLOCKED_SCAN", mode)
+    for inp in (synth.adversarial(51, 100), synth.adversarial(52, 150), synth.adversarial(53, 255), synth.adversarial(54, 64),
+                synth.workload(200_000, 50_000, 150, 0.005, seed=55, n_frac=0.02, name="c2 shape"),
+                synth.workload(300_000, 40_000, 100, 0.01, seed=56, name="c4 shape")):
+        got, _ = _check(inp)
+        assert got.stats["candidates"] > 0 and got.stats["filter_positives"] > 0
+        _check(inp, pre_reads_exact_matching_chars=inp.read_len)
+        _check(inp, matching_mode="D")
+    for kw in (dict(reads_exact_matching_chars=30), dict(reads_exact_matching_chars=45), dict(reads_exact_matching_chars=100),
+               dict(min_chars_per_mismatch=2), dict(rev_compl_pg=False), dict(pre_reads_exact_matching_chars=50)):
+        _check(synth.adversarial(57, 100), **kw)
+
+
+def test_blocked_scan_pipeline_hot_seeds_and_shards(monkeypatch):
+    """Hot seeds (duplicates, homopolymers: chains behind a slot, skewed queues) and text shards through the pipeline."""
+    monkeypatch.setenv("PGM_BLOCKED_SCAN", "2")
+    rng = np.random.default_rng(58)
+    g = synth.random_genome(30_000, rng)
+    text = np.concatenate([g[:10_000], np.full(400, ord("A"), np.uint8), g[10_000:20_000], np.full(300, ord("T"), np.uint8), g[20_000:]])
+    base = synth.sample_reads(g, 40, 100, 0.02, rng)
+    polya = np.full((300, 100), ord("A"), np.uint8)
+    polya[np.arange(300), rng.integers(0, 100, 300)] = ord("C")
+    reads = np.concatenate([np.repeat(base, 60, axis=0), polya, synth.sample_reads(g, 500, 100, 0.01, rng)])
+    reads = reads[rng.permutation(len(reads))]
+    nn = synth.inject_n(np.repeat(base[:5], 40, axis=0), rng)
+    inp = synth.MatcherInputs(np.ascontiguousarray(text), np.ascontiguousarray(reads), nn, 100, "hot seeds")
+    _check(inp)
+    inp = synth.adversarial(59, 100, n_reads=2000, text_len=30000)
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len)
+    for got in _run_sharded_on_one_gpu(inp, 3):
+        assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)
