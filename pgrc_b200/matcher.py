@@ -272,6 +272,34 @@ def shard_plan(pg_len: int, rank: int, world: int):
     return tuple(int(x.value) for x in v)
 
 
+def text_share(pg_len: int, rank: int, world: int):
+    """(begin, end, per): the part of the pseudogenome rank `rank` uploads in ``all_gather_text``; `per` is the
+    16-byte-aligned share size every rank contributes (the last one is padded)."""
+    per = ((pg_len + world - 1) // world + 15) // 16 * 16
+    return min(pg_len, rank * per), min(pg_len, (rank + 1) * per), per
+
+
+def all_gather_text(share_host, pg_len: int, rank: int, world: int, device, bufs: dict | None = None, group=None):
+    """Read-sharded multi-GPU runs need the whole pseudogenome on every GPU.  Instead of `world` copies of it
+    crossing the host's PCIe links, every rank uploads its ``text_share`` (host tensor, pinned for speed) and one
+    NCCL all-gather over NVLink / NVSwitch replicates it (replication from the GPU that received the
+    H2D copy).  Returns the ASCII text as a device tensor of pg_len bytes; `bufs` caches the device buffers between calls."""
+    import torch
+    import torch.distributed as dist
+    b, e, per = text_share(pg_len, rank, world)
+    bufs = bufs if bufs is not None else {}
+    if bufs.get("per") != per or bufs.get("world") != world:
+        bufs.update(per=per, world=world, full=torch.empty(per * world, dtype=torch.uint8, device=device))
+    full = bufs["full"]
+    mine = full[rank * per:(rank + 1) * per]
+    mine[:e - b].copy_(share_host[:e - b], non_blocking=True)
+    if e - b < per:
+        mine[e - b:].fill_(ord("A"))
+    if world > 1:
+        dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:pg_len]
+
+
 def merge_accumulators(m: GpuReadsMatcher, group=None):
     """The one exchange step of the sharded path: per-read MIN / SUM all-reduce of the pass
     accumulators over NCCL (NVLink / NVSwitch).  The rarely used ones are merged only when some

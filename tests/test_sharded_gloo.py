@@ -72,3 +72,25 @@ def test_match_plan_mirrors_reference_parameter_derivation():
     for bad in ("c", "i", "x"):
         with pytest.raises(PgmError):
             MatchPlan.derive(100, 38, 3, bad)
+
+
+def _gather_worker(rank, world, port, pg_len):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from pgrc_b200 import matcher
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    text = torch.from_numpy(np.random.default_rng(1).choice(np.frombuffer(b"ACGT", np.uint8), pg_len))
+    b, e, per = matcher.text_share(pg_len, rank, world)
+    bufs = {}
+    for _ in range(2):   # second call reuses the buffers
+        got = matcher.all_gather_text(text[b:e], pg_len, rank, world, "cpu", bufs)
+        assert torch.equal(got, text), rank
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pg_len", [1003, 4096])
+def test_text_all_gather_three_ranks_gloo(pg_len):
+    """Read-sharded runs: every rank uploads 1/N of the pseudogenome, one all-gather replicates it."""
+    mp.spawn(_gather_worker, args=(3, _free_port(), pg_len), nprocs=3, join=True)
