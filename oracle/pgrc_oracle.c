@@ -6,8 +6,11 @@
  *   rolling hash      rollinghash/cyclichash.h:29-35,100-123             (CyclicHash<uint32>(n, 32))
  *   exact matcher     ReadsMatchers.cpp:190-230
  *   approx matcher    ReadsMatchers.cpp:276-341
+ *   interleaved mode  ReadsMatchers.cpp:343-409 (InterleavedReadsApproxMatcher),
+ *                     ConstantLengthPatternsOnTextHashMatcher.h:70-137, .cpp:52-101 (strided patterns: pattern j of a
+ *                     read = its symbols j, j+parts, j+2*parts, ...; one rolling hash per text position residue)
  *   pass structure    ReadsMatchers.cpp:162-184
- *   driver            ReadsMatchers.cpp:693-783 (mapReadsIntoPg, modes 'd'/'D')
+ *   driver            ReadsMatchers.cpp:693-783 (mapReadsIntoPg, modes 'd'/'D' and 'i'/'I')
  *   read layout       SymbolsPackingFacility.cpp:147-185, PackedConstantLengthReadsSet.h:40-46
  *   mismatch count    SymbolsPackingFacility.cpp:344-374 (contract: exact count if <= limit, else 255)
  *   reverse compl.    utils/helper.cpp:383-393
@@ -182,7 +185,7 @@ static void table_free(pat_table *t) { free(t->e); free(t->dir); t->e = NULL; t-
 
 /* addReadsSetOfPatterns(readsSet, partsCount, matchedReadsBitmap) */
 static int table_build(pat_table *t, const reads_view *rs, uint32_t n_reads, uint32_t pattern_len,
-                       uint32_t parts, const uint8_t *skip_bitmap) {
+                       uint32_t parts, const uint8_t *skip_bitmap, int interleaved) {
     memset(t, 0, sizeof(*t));
     t->pattern_len = pattern_len; t->parts = parts;
     buz_init(&t->hf, pattern_len);
@@ -195,8 +198,8 @@ static int table_build(pat_table *t, const reads_view *rs, uint32_t n_reads, uin
         uint32_t offset = 0;
         for (uint32_t j = 0; j < parts; j++, offset += pattern_len) {
             buz_reset(&t->hf);
-            for (uint32_t k = 0; k < pattern_len; k++)
-                buz_eat(&t->hf, (unsigned char)read_symbol(rs, i, offset + k));
+            for (uint32_t k = 0; k < pattern_len; k++)   /* addPackedPatterns (HashMatcher.cpp:89-91): symbols j + k*parts */
+                buz_eat(&t->hf, (unsigned char)read_symbol(rs, i, interleaved ? j + k * parts : offset + k));
             t->e[m].key = buz_value(&t->hf);
             t->e[m].idx = i * parts + j;
             m++;
@@ -245,8 +248,21 @@ typedef struct {
     pgo_stats *st;
     /* approx parameters */
     uint32_t part_len, parts; uint8_t max_mm, min_mm;
-    char *cur_read, *seed_buf;
+    int interleaved;
+    char *cur_read, *seed_buf, *win_buf;
 } matcher;
+
+/* interleaved mode: the same test on the strided seed (read symbols j + k*parts) and the strided window */
+static int seed_equivalent_strided(const matcher *m, uint32_t read_idx, uint32_t j, uint32_t n, const char *txt_at_pos) {
+    uint8_t f1[32], f2[32];
+    for (uint32_t k = 0; k < n; k++) {
+        m->seed_buf[k] = read_symbol(m->rs, read_idx, j + k * m->parts);
+        m->win_buf[k] = txt_at_pos[(size_t)k * m->parts];
+    }
+    canonical_form(m->seed_buf, n, f1);
+    canonical_form(m->win_buf, n, f2);
+    return memcmp(f1, f2, 32) == 0;
+}
 
 /* true iff the hash hit is a table-independent (structural) one */
 static int seed_equivalent(const matcher *m, uint32_t read_idx, uint32_t offset, uint32_t n, const char *window) {
@@ -333,6 +349,62 @@ static void approx_pass(matcher *m, pat_table *t, const char *txt, int rev_mode)
     }
 }
 
+/* InterleavedReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:365-409) over
+ * InterleavedConstantLengthPatternsOnTextHashMatcher::iterateOver / moveNext (HashMatcher.h:108-135): `parts` rolling
+ * hashes, the one of residue txtPos mod parts covers txt[txtPos + k*parts], k < patternLength; a hit of pattern
+ * i*parts + j at txtPos aligns the read at txtPos - j.  (A text shorter than patternSpan makes the reference's
+ * unsigned loop bound wrap around: undefined there, no events here.) */
+static int interleaved_pass(matcher *m, pat_table *t, const char *txt, int rev_mode) {
+    const uint64_t n = t->pattern_len, parts = m->parts, span = n * parts;
+    if (m->pg_len < span) return 0;
+    buzhash *hf = (buzhash *)malloc(parts * sizeof(buzhash));
+    if (!hf) return -2;
+    for (uint64_t h = 0; h < parts; h++) {
+        hf[h] = t->hf;
+        buz_reset(&hf[h]);
+        for (uint64_t i = h; i < m->pg_len && i < span + h; i += parts) buz_eat(&hf[h], (unsigned char)txt[i]);
+    }
+    uint64_t cur = 0;
+    for (uint64_t p = 0; p + span <= m->pg_len; p++) {
+        uint64_t first, cnt = table_lookup(t, buz_value(&hf[cur]), &first);
+        unsigned char in = p + span < m->pg_len ? (unsigned char)txt[p + span] : 0; /* txt[len] is the NUL */
+        buz_update(&hf[cur], (unsigned char)txt[p], in);
+        if (++cur == parts) cur = 0;
+        for (uint64_t q = 0; q < cnt; q++) {
+            const uint32_t pat = t->e[first + q].idx;
+            const uint32_t r = pat / m->parts, j = pat % m->parts;
+            m->st->n_events++;
+            if (!seed_equivalent_strided(m, r, j, (uint32_t)n, txt + p)) continue;
+            if (m->mm[r] <= m->min_mm) continue;
+            uint64_t match_pos = p;
+            if (j > match_pos) continue;                       /* positionShift = j (:373-376) */
+            match_pos -= j;
+            if (match_pos + m->read_len > m->pg_len) continue;
+            const uint64_t rep = rev_mode ? m->pg_len - (match_pos + m->matching_len) : match_pos;
+            if (m->pos[r] == rep) {
+                if (m->rc[r] != (uint8_t)(rev_mode ? 1 : 0)) m->st->n_cross_strand_skips++;
+                continue;
+            }
+            const uint8_t limit = m->mm[r] == PGO_NOT_MATCHED_COUNT ? m->max_mm : (uint8_t)(m->mm[r] - 1);
+            get_read(m->rs, r, m->cur_read);
+            m->st->n_verified++;
+            const uint8_t c = count_mismatches(m->cur_read, txt + match_pos, m->matching_len, limit);
+            if (c < m->mm[r]) {
+                if (m->mm[r] == PGO_NOT_MATCHED_COUNT) m->st->matched++;
+                else m->st->better++;
+                m->st->per_mm[m->mm[r]]--;
+                m->st->per_mm[c]++;
+                m->pos[r] = rep;
+                m->rc[r] = (uint8_t)(rev_mode ? 1 : 0);
+                m->mm[r] = c;
+            } else
+                m->st->false_matches++;
+        }
+    }
+    free(hf);
+    return 0;
+}
+
 /* reverseComplementInPlace semantics on a copy (helper.cpp:383-393) */
 static char *reverse_complement(const char *s, uint64_t n) {
     char *o = (char *)malloc(n + 1);
@@ -346,15 +418,22 @@ static char *reverse_complement(const char *s, uint64_t n) {
 }
 
 /* matchConstantLengthReads / continueMatchingConstantLengthReads pass structure */
+static int one_pass(matcher *m, pat_table *t, int exact, const char *txt, int rev_mode) {
+    if (exact) exact_pass(m, t, txt, rev_mode);
+    else if (m->interleaved) return interleaved_pass(m, t, txt, rev_mode);
+    else approx_pass(m, t, txt, rev_mode);
+    return 0;
+}
+
 static int run_passes(matcher *m, pat_table *t, int exact) {
-    if (exact) exact_pass(m, t, m->pg, 0); else approx_pass(m, t, m->pg, 0);
-    if (m->rev_compl) {
+    int rcode = one_pass(m, t, exact, m->pg, 0);
+    if (rcode == 0 && m->rev_compl) {
         char *rcpg = reverse_complement(m->pg, m->pg_len);
         if (!rcpg) return -2;
-        if (exact) exact_pass(m, t, rcpg, 1); else approx_pass(m, t, rcpg, 1);
+        rcode = one_pass(m, t, exact, rcpg, 1);
         free(rcpg);
     }
-    return 0;
+    return rcode;
 }
 
 /* ------------------------------------------------------------------ driver (a12, a13) */
@@ -369,7 +448,8 @@ int pgo_map_reads(const char *text, uint64_t text_len,
                   uint32_t min_chars_per_mismatch, char pre_mode, char mode, int rev_compl,
                   uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgo_stats *stats) {
     if (!text || read_len == 0 || read_len > 255 || seed == 0 || min_chars_per_mismatch == 0) return -1;
-    if (lower_mode(mode) != 'd' || (pre_seed && lower_mode(pre_mode) != 'd')) return -1;
+    if ((lower_mode(mode) != 'd' && lower_mode(mode) != 'i') ||
+        (pre_seed && lower_mode(pre_mode) != 'd' && lower_mode(pre_mode) != 'i')) return -1;
     pgo_stats local;
     if (!stats) stats = &local;
     memset(stats, 0, sizeof(*stats));
@@ -394,7 +474,8 @@ int pgo_map_reads(const char *text, uint64_t text_len,
     m.pos = out_pos; m.rc = out_rc; m.mm = out_mm; m.st = stats;
     m.cur_read = (char *)malloc(read_len + 1);
     m.seed_buf = (char *)malloc(read_len + 1);
-    if (!m.cur_read || !m.seed_buf) { free(m.cur_read); free(m.seed_buf); return -2; }
+    m.win_buf = (char *)malloc(read_len + 1);
+    if (!m.cur_read || !m.seed_buf || !m.win_buf) { free(m.cur_read); free(m.seed_buf); free(m.win_buf); return -2; }
 
     /* DefaultReadsMatcher::initMatching (ReadsMatchers.cpp:97-105) */
     for (uint32_t i = 0; i < n; i++) { out_pos[i] = PGO_NOT_MATCHED_POSITION; out_rc[i] = 0; out_mm[i] = PGO_NOT_MATCHED_COUNT; }
@@ -404,7 +485,7 @@ int pgo_map_reads(const char *text, uint64_t text_len,
     const int first_exact = (read_len == cur_exact);
     if (first_exact) {
         /* DefaultReadsExactMatcher::initMatching: whole reads as patterns (parts = 1) */
-        rcode = table_build(&t, &rs, n, m.matching_len, 1, NULL);
+        rcode = table_build(&t, &rs, n, m.matching_len, 1, NULL, 0);
         if (rcode == 0) { stats->n_patterns = t.n; rcode = run_passes(&m, &t, 1); table_free(&t); }
         /* DefaultReadsExactMatcher::transferMatchingResults (ReadsMatchers.cpp:127-133) */
         for (uint32_t i = 0; i < n; i++) out_mm[i] = out_pos[i] == PGO_NOT_MATCHED_POSITION ? PGO_NOT_MATCHED_COUNT : 0;
@@ -413,8 +494,9 @@ int pgo_map_reads(const char *text, uint64_t text_len,
     } else {
         /* AbstractReadsApproxMatcher ctor + DefaultReadsApproxMatcher::initMatching */
         m.part_len = cur_exact; m.parts = (uint32_t)target_mm + 1; m.max_mm = max_mm; m.min_mm = cur_min_mm;
+        m.interleaved = lower_mode(cur_mode) == 'i';
         stats->per_mm[PGO_NOT_MATCHED_COUNT] = n;
-        rcode = table_build(&t, &rs, n, m.part_len, m.parts, NULL);
+        rcode = table_build(&t, &rs, n, m.part_len, m.parts, NULL, m.interleaved);
         if (rcode == 0) { stats->n_patterns = t.n; rcode = run_passes(&m, &t, 0); table_free(&t); }
     }
 
@@ -424,6 +506,7 @@ int pgo_map_reads(const char *text, uint64_t text_len,
         m.part_len = reads_exact;
         m.parts = read_len / reads_exact; /* targetMismatches + 1 of the new matcher */
         m.max_mm = max_mm; m.min_mm = min_mm2;
+        m.interleaved = lower_mode(mode) == 'i';
         /* initMatchingContinuation: getMatchedReadsBitmap(minMismatches) of the previous matcher:
          * exact matcher ignores the argument (:677-683), approx matcher uses mm <= arg (:685-691) */
         uint8_t *skip = (uint8_t *)malloc(n ? n : 1);
@@ -431,11 +514,11 @@ int pgo_map_reads(const char *text, uint64_t text_len,
         else {
             for (uint32_t i = 0; i < n; i++)
                 skip[i] = first_exact ? (out_pos[i] != PGO_NOT_MATCHED_POSITION) : (out_mm[i] <= min_mm2);
-            rcode = table_build(&t, &rs, n, m.part_len, m.parts, skip);
+            rcode = table_build(&t, &rs, n, m.part_len, m.parts, skip, m.interleaved);
             free(skip);
             if (rcode == 0) { stats->n_patterns = t.n; rcode = run_passes(&m, &t, 0); table_free(&t); }
         }
     }
-    free(m.cur_read); free(m.seed_buf);
+    free(m.cur_read); free(m.seed_buf); free(m.win_buf);
     return rcode;
 }

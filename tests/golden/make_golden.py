@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz — golden vectors for the read-vs-pseudogenome matching path.
 
 The reference ships no fixtures for this path, so the pins are outputs of the
-reference's OWN classes (DefaultReadsApproxMatcher / DefaultReadsExactMatcher, unmodified objects
+reference's OWN classes (DefaultReadsApproxMatcher / InterleavedReadsApproxMatcher / DefaultReadsExactMatcher, unmodified objects
 built from /root/reference by oracle/Makefile) run in the build container through
 oracle/ref_harness.cpp.  This script needs oracle/_ref/libpgrc_ref.so, i.e. it only runs where
 /root/reference exists; the .npz files it writes are committed and travel to the GPU box.
@@ -40,6 +40,15 @@ CASES = [
     ("c1_shape_small", lambda: synth.workload(40_000, 3_000, 100, 0.001, seed=213, name="c1 shape"), {}),
     ("c2_shape_small", lambda: synth.workload(40_000, 4_000, 150, 0.005, seed=214, n_frac=0.03, name="c2 shape"), {}),
     ("c4_shape_small", lambda: synth.workload(40_000, 4_000, 100, 0.01, seed=215, name="c4 shape"), {}),
+    # mode 'i' (InterleavedReadsApproxMatcher, ReadsMatchers.cpp:343-409): strided seeds
+    ("ilv_L100_default", lambda: synth.adversarial(221, 100, n_reads=900, text_len=16000), dict(mode="i")),
+    ("ilv_L150_default", lambda: synth.adversarial(222, 150, n_reads=900, text_len=20000), dict(mode="i")),
+    ("ilv_L120_seed30", lambda: synth.adversarial(223, 120, n_reads=700, text_len=16000), dict(mode="i", seed=30)),
+    ("ilv_L100_shortcut", lambda: synth.adversarial(224, 100, n_reads=700, text_len=16000), dict(mode="I")),
+    ("ilv_L100_prephase_exact", lambda: synth.adversarial(225, 100, n_reads=700, text_len=16000), dict(mode="i", pre_seed=100)),
+    ("ilv_L100_prephase50_i", lambda: synth.adversarial(226, 100, n_reads=700, text_len=16000), dict(mode="i", pre_seed=50, pre_mode="i")),
+    ("ilv_L255_default", lambda: synth.adversarial(227, 255, n_reads=400, text_len=24000), dict(mode="i")),
+    ("ilv_c2_shape_small", lambda: synth.workload(40_000, 4_000, 150, 0.005, seed=228, n_frac=0.03, name="c2 shape"), dict(mode="i")),
 ]
 
 DEFAULTS = dict(seed=38, min_chars_per_mismatch=3, mode="d", pre_seed=0, pre_mode="d", rev_compl=True)
@@ -49,6 +58,8 @@ def main():
     if not oracle.have_ref():
         raise SystemExit("oracle/_ref/libpgrc_ref.so missing: run `make -C oracle ref` where /root/reference exists")
     for name, make, kw in CASES:
+        if os.path.exists(os.path.join(HERE, name + ".npz")) and "--all" not in sys.argv:
+            continue   # committed vectors are kept as they are; --all regenerates every case
         inp = make()
         p = dict(DEFAULTS); p.update(kw)
         r = oracle.ref_map_reads(inp.text, inp.lq_reads, inp.n_reads, inp.read_len, **p)

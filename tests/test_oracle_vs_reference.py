@@ -49,3 +49,23 @@ def test_device_generator_shape():
     o = oracle.oracle_map_reads(text, packed, None, c["read_len"])
     assert np.array_equal(o.pos, r.pos) and np.array_equal(o.mm, r.mm) and np.array_equal(o.rc, r.rc)
     assert r.matched > 0.95 * len(r.pos)
+
+
+@pytest.mark.parametrize("seed,L", [(61, 100), (62, 150), (63, 120), (64, 255)])
+def test_interleaved_mode_adversarial(seed, L):
+    """Mode 'i' (InterleavedReadsApproxMatcher, ReadsMatchers.cpp:343-409): strided seeds, shift j instead of j * seed."""
+    o = _cmp(synth.adversarial(seed, L, n_reads=1500, text_len=30000), mode="i")
+    assert o.matched > 100
+
+
+@pytest.mark.parametrize("kw", [dict(mode="i", seed=30), dict(mode="i", seed=33), dict(mode="i", seed=45), dict(mode="I"),
+                                dict(mode="i", pre_seed=100), dict(mode="i", pre_seed=50, pre_mode="i"),
+                                dict(mode="d", pre_seed=50, pre_mode="i"), dict(mode="I", pre_seed=50, pre_mode="d"),
+                                dict(mode="i", min_chars_per_mismatch=2), dict(mode="i", rev_compl=False), dict(mode="i", seed=20)])
+def test_interleaved_mode_parameter_matrix(kw):
+    _cmp(synth.adversarial(65, 100, n_reads=1200, text_len=24000), **kw)
+
+
+def test_interleaved_mode_workload_shapes():
+    _cmp(synth.workload(100_000, 8_000, 100, 0.001, seed=66), mode="i")
+    _cmp(synth.workload(100_000, 12_000, 150, 0.005, seed=67, n_frac=0.02), mode="i")
