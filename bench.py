@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale genome and read count (testing)")
+    ap.add_argument("--mode", default="d", choices=["d", "i"], help="matching mode: d = contiguous seeds (the headline), "
+                    "i = interleaved seeds (InterleavedReadsApproxMatcher, SURVEY §8(f) row 3)")
     ap.add_argument("--shard", default="auto", choices=["auto", "text", "reads"],
                     help="multi-GPU partitioning: text ranges + NCCL min-merge of the per-read keys, or read ranges (no collective); "
                          "auto = reads (the table build and the probes shard with the reads; see DESIGN.md §7)")
@@ -148,10 +150,10 @@ def cpu_baseline(args) -> dict:
     frac = args.cpu_sample
     shape = f"{args.workload} shape x {args.scale * frac:g} (genome, reads scaled; same read length, error rate, coverage)"
     if oracle.have_ref():
-        v, info = run_reference_cpu(args, frac, "d", 1)
+        v, info = run_reference_cpu(args, frac, args.mode, 1)
         return {"value": round(v, 1), "unit": UNIT, "cores": 1, "kind": "reference",
-                "sample": f"{shape}: {info['reads']} reads vs {info['text_bases']} bases, {info['seconds']} s, reference mode d "
-                          "(DefaultReadsApproxMatcher, single-threaded by construction)"}
+                "sample": f"{shape}: {info['reads']} reads vs {info['text_bases']} bases, {info['seconds']} s, reference mode {args.mode} "
+                          f"({'DefaultReadsApproxMatcher' if args.mode == 'd' else 'InterleavedReadsApproxMatcher'}, single-threaded by construction)"}
     v, info = run_oracle_cpu(args, frac)
     return {"value": round(v, 1), "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{shape}: {info['reads']} reads vs {info['text_bases']} bases, {info['seconds']} s, oracle/pgrc_oracle.c"}
@@ -385,6 +387,7 @@ def ours(args):
                 "dtype": "u32", "data": "synthetic",
                 "config": {"workload": workload_name(args), "reads": n_reads, "read_len": L, "text_bases": pg_len,
                            "seed_len": plan.phases[0][0], "parts": plan.phases[0][1], "max_mismatches": plan.phases[0][2],
+                           "matching_mode": MATCH_KW["mode"],
                            "matched": matched_total,
                            "parallelism": "single GPU" if world == 1 else f"{args.shard}-sharded x{world}",
                            "l2": "inputs (text + reads + seed table) exceed the 126 MB L2; no flush between steps",
@@ -405,6 +408,7 @@ def ours(args):
 
 def main():
     args = parse_args()
+    MATCH_KW["mode"] = args.mode
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -127,7 +127,16 @@ int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq,
  * (getMatchedReadsBitmap(minMismatches), ReadsMatchers.cpp:287-295,677-691). */
 int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm,
                     uint32_t min_mm, int continuation);
-/* pgm_scan_pass replaces executeMatching(revCompMode) (ReadsMatchers.cpp:198-230,297-341)
+/* pgm_match_begin_interleaved replaces InterleavedReadsApproxMatcher::initMatching() /
+ * initMatchingContinuation() (ReadsMatchers.cpp:343-362) and the pattern set of
+ * InterleavedConstantLengthPatternsOnTextHashMatcher::addPackedPatterns
+ * (ConstantLengthPatternsOnTextHashMatcher.cpp:82-96): seed j of a read = its bases j, j+parts,
+ * j+2*parts, ... (seed_len of them), matched against text[x], text[x+parts], ...; a hit aligns
+ * the read at x - j (ReadsMatchers.cpp:373-376).  Same arguments as pgm_match_begin; the passes,
+ * the accumulators and the decision are the same calls.  parts <= 31. */
+int pgm_match_begin_interleaved(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm,
+                                uint32_t min_mm, int continuation);
+/* pgm_scan_pass replaces executeMatching(revCompMode) (ReadsMatchers.cpp:198-230,297-341,365-409)
  * up to, but excluding, the per-read decision: scan of the (reverse-complemented, if
  * rev_mode) text, table probes, XOR/popcount verification, per-read accumulators. */
 int pgm_scan_pass(pgm_ctx *ctx, int rev_mode);
@@ -147,7 +156,8 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
 
 /* ---- the whole stage on one GPU ---------------------------------------------------------
  * pgm_map_reads replaces the matching part of PgTools::mapReadsIntoPg
- * (ReadsMatchers.cpp:693-783) for matching modes 'd'/'D': parameter derivation
+ * (ReadsMatchers.cpp:693-783) for matching modes 'd'/'D' (DefaultReadsApproxMatcher) and 'i'/'I'
+ * (InterleavedReadsApproxMatcher): parameter derivation
  * (:699-713), first matcher (:714-747), optional second phase (:749-779), same argument
  * meaning as the reference (pre_seed = preReadsExactMatchingChars, seed =
  * readsExactMatchingChars, min_chars_per_mismatch = minCharsPerMismatch, upper-case mode

@@ -20,7 +20,7 @@ STATUS_NAMES = {0: "PGM_OK", -1: "PGM_ERR_INVALID_ARG", -2: "PGM_ERR_NO_DEVICE",
 
 # every symbol include/pgrc_gpu_matcher.h declares
 EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pgm_set_stream", "pgm_synchronize",
-           "pgm_set_text", "pgm_set_text_shard", "pgm_shard_plan", "pgm_set_reads", "pgm_match_begin",
+           "pgm_set_text", "pgm_set_text_shard", "pgm_shard_plan", "pgm_set_reads", "pgm_match_begin", "pgm_match_begin_interleaved",
            "pgm_scan_pass", "pgm_get_accumulators", "pgm_put_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_map_reads",
            "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings"]
 
@@ -75,6 +75,7 @@ def load() -> ctypes.CDLL:
     lib.pgm_shard_plan.argtypes = [u64, ci, ci] + [ctypes.POINTER(u64)] * 4
     lib.pgm_set_reads.restype = ci; lib.pgm_set_reads.argtypes = [vp, vp, u32, vp, u32, u32]
     lib.pgm_match_begin.restype = ci; lib.pgm_match_begin.argtypes = [vp, u32, u32, u32, u32, ci]
+    lib.pgm_match_begin_interleaved.restype = ci; lib.pgm_match_begin_interleaved.argtypes = [vp, u32, u32, u32, u32, ci]
     lib.pgm_scan_pass.restype = ci; lib.pgm_scan_pass.argtypes = [vp, ci]
     lib.pgm_get_accumulators.restype = ci; lib.pgm_get_accumulators.argtypes = [vp, ctypes.POINTER(PgmAccumulators)]
     lib.pgm_put_accumulators.restype = ci; lib.pgm_put_accumulators.argtypes = [vp]

@@ -90,7 +90,12 @@ struct pgm_ctx {
 
     // phase
     uint32_t seed_len = 0, parts = 0, max_mm = 0, min_mm = 0, part_bits = 0;
+    bool interleaved = false;   // mode 'i': seed j = read bases j, j + parts, j + 2 parts, ...
     bool phase_active = false;
+
+    uint32_t ilv() const { return interleaved ? parts : 0u; }                        // stride of the seeds, 0 = contiguous
+    uint32_t shift_unit() const { return interleaved ? 1u : seed_len; }              // alignment start = window start - j * shift_unit
+    uint64_t seed_span() const { return (uint64_t)seed_len * (interleaved ? parts : 1u); }   // text bases a seed window covers
 
     // misc device scalars: counters[0..3] scan, [4] inserted, [5] tile counter (low 32 bits)
     DevBuf counters, hist, err_flag;
@@ -308,13 +313,13 @@ int build_range(pgm_ctx *ctx, uint32_t r_begin, uint32_t r_end, int continuation
     const uint32_t tail = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
     const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(r_end - r_begin, PGM_BUILD_THREADS), (uint64_t)ctx->sm_count * 8);
     const size_t smem = ctx->bq_region_bits ? (size_t)ctx->parts * PGM_BUILD_THREADS * sizeof(uint4) : 0;
-    const bool fast = ctx->n_n == 0 && ctx->lq_stride16 == 4;         // only ACGT reads, 64-byte records: record held in registers
+    const bool fast = ctx->n_n == 0 && ctx->lq_stride16 == 4 && !ctx->interleaved;   // only ACGT reads, 64-byte records, contiguous seeds: record held in registers
     KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel",
             if (fast) pgm::build_table_kernel<true><<<grid, PGM_BUILD_THREADS, smem, ctx->stream>>>(
-                reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail,
+                reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail, ctx->ilv(),
                 ctx->counters.as<unsigned long long>() + 4);
             else pgm::build_table_kernel<false><<<grid, PGM_BUILD_THREADS, smem, ctx->stream>>>(
-                reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail,
+                reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail, ctx->ilv(),
                 ctx->counters.as<unsigned long long>() + 4));
     if (ctx->bq_region_bits) ctx->bq_pending = true;
     return PGM_OK;
@@ -391,9 +396,13 @@ int filter_window(pgm_ctx *ctx, bool on) {
 template <int NCH>
 void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, bool filter_stage) {
     // FAST: only ACGT reads, records of exactly 64 bytes (read length <= 192)
-    if (filter_stage) pgm::scan_kernel<NCH, false, 1><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
-    else if (sp.reads.n_n == 0 && sp.reads.lq_stride16 == 4) pgm::scan_kernel<NCH, true, 0><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
-    else pgm::scan_kernel<NCH, false, 0><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    const bool fast = sp.reads.n_n == 0 && sp.reads.lq_stride16 == 4;
+    if (filter_stage) pgm::scan_kernel<NCH, false, 1, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    else if (sp.ilv) {
+        if (fast) pgm::scan_kernel<NCH, true, 0, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+        else pgm::scan_kernel<NCH, false, 0, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    } else if (fast) pgm::scan_kernel<NCH, true, 0, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    else pgm::scan_kernel<NCH, false, 0, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
 }
 
 void launch_scan_nch(int nch, const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, bool filter_stage) {
@@ -415,7 +424,7 @@ int floor_log2(uint64_t v) { int b = 0; while ((2ull << b) <= v) b++; return b; 
 bool plan_blocked(pgm_ctx *ctx, uint64_t n_pos, uint32_t n_tiles, pgm::StageQueues &q) {
     memset(&q, 0, sizeof q);
     const int mode = ctx->blocked_scan;
-    if (mode <= 0 || ctx->n_reads() == 0) return false;
+    if (mode <= 0 || ctx->n_reads() == 0 || ctx->interleaved) return false;
     const uint64_t table_bytes = (uint64_t)ctx->n_buckets * 32;
     if ((uint64_t)n_tiles * PGM_TILE_POS >= (1ull << 31)) return false;              // queue positions are 31 bits
     if (mode == 1) {
@@ -681,8 +690,30 @@ int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq, const u
     return upload_reads(ctx, false);
 }
 
+} // extern "C"
+
+namespace {
+int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm, int continuation, bool interleaved);
+}
+
+extern "C" {
+
 int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm, int continuation) {
+    return match_begin_impl(ctx, seed_len, parts, max_mm, min_mm, continuation, false);
+}
+
+int pgm_match_begin_interleaved(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm, int continuation) {
+    return match_begin_impl(ctx, seed_len, parts, max_mm, min_mm, continuation, true);
+}
+
+} // extern "C"
+
+namespace {
+int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm, int continuation, bool interleaved) {
     if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (interleaved && parts > PGM_ILV_MAX_PARTS)
+        return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_match_begin_interleaved: more than 31 seeds per read");
+    if (parts == 1) interleaved = false;            // one seed: stride 1, the contiguous case
     if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_match_begin: pgm_set_reads has not been called");
     if (seed_len == 0 || parts == 0 || (uint64_t)seed_len * parts > ctx->read_len)
         return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_match_begin: need seed_len >= 1 and seed_len * parts <= read_len");
@@ -738,6 +769,7 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
         }
     }
     ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm;
+    ctx->interleaved = interleaved;
     ctx->outputs_valid = false;
     if (ctx->reads_pending && continuation && (rc = upload_reads(ctx, false))) return rc;   // (not a sensible call order)
     const bool pipelined = ctx->reads_pending;
@@ -759,13 +791,10 @@ int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     return PGM_OK;
 }
 
-} // extern "C"
-
-namespace {
 // One scan launch over the seed-window starts [fb, fe) (FORWARD global coordinates) of the pass.
 int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
     if (fb >= fe) return PGM_OK;
-    const uint64_t n = ctx->seed_len, pg = ctx->pg_len;
+    const uint64_t n = ctx->seed_span(), pg = ctx->pg_len;     // n: text bases a seed window covers
     pgm::ScanParams sp;
     memset(&sp, 0, sizeof sp);
     if (!rev_mode) {
@@ -783,6 +812,7 @@ int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
     sp.first_word = (uint32_t)((lb / 32) & ~3ull);
     sp.n_tiles = (uint32_t)((le - (uint64_t)sp.first_word * 32 + PGM_TILE_POS - 1) / PGM_TILE_POS);
     sp.seed_len = ctx->seed_len; sp.parts = ctx->parts; sp.max_mm = ctx->max_mm; sp.min_mm = ctx->min_mm;
+    sp.shift_unit = ctx->shift_unit(); sp.ilv = ctx->ilv();
     sp.tail_mask = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
     sp.rev_mode = rev_mode ? 1 : 0;
     sp.l2_hints = ctx->l2_hints == 1 ? 1 : 0;      // window mode: plain filter loads, the window carries the policy
@@ -841,7 +871,7 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
     if (!ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_scan_pass: pgm_match_begin has not been called");
     if (!ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_scan_pass: pgm_set_text has not been called");
     CU(cudaSetDevice(ctx->device));
-    const uint64_t n = ctx->seed_len, pg = ctx->pg_len;
+    const uint64_t n = ctx->seed_span(), pg = ctx->pg_len;
     int rc;
     if (pg < n || ctx->n_reads() == 0) return finish_text_upload(ctx);
     // owned window starts of this pass (forward global coordinates)
@@ -910,12 +940,12 @@ int resolve_impl(pgm_ctx *ctx, int rev_mode, bool fin) {
     if (fin) {
         CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
         KLAUNCH(PGM_K_RESOLVE, "resolve_kernel", pgm::resolve_kernel<true><<<grid_for(n, 256), 256, 0, ctx->stream>>>(
-            reads_view(ctx), per_read(ctx), n, ctx->pg_len, ctx->seed_len, ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0,
+            reads_view(ctx), per_read(ctx), n, ctx->pg_len, ctx->shift_unit(), ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0,
             ctx->out_pos.as<unsigned long long>(), ctx->out_rc.as<uint8_t>(), ctx->out_mm.as<uint8_t>(), ctx->hist.as<unsigned long long>()));
         ctx->outputs_valid = true;
     } else {
         KLAUNCH(PGM_K_RESOLVE, "resolve_kernel", pgm::resolve_kernel<false><<<grid_for(n, 256), 256, 0, ctx->stream>>>(
-            reads_view(ctx), per_read(ctx), n, ctx->pg_len, ctx->seed_len, ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0,
+            reads_view(ctx), per_read(ctx), n, ctx->pg_len, ctx->shift_unit(), ctx->parts, ctx->max_mm, ctx->min_mm, rev_mode ? 1 : 0,
             nullptr, nullptr, nullptr, nullptr));
     }
     CU(cudaMemsetAsync(ctx->touched.p, 0, sizeof(int), ctx->stream));
@@ -981,9 +1011,10 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
     if (match_prefix_length != PGM_DISABLED_PREFIX_MODE && match_prefix_length < L)
         return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_map_reads: prefix matching (matchPrefixLength < readLength) is not used by pgrc-encoder and not supported");
     if (seed == 0 || min_chars_per_mismatch == 0) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_map_reads: seed and min_chars_per_mismatch must be > 0");
-    if (std::tolower(mode) != 'd' || (pre_seed && std::tolower(pre_mode) != 'd')) {
+    auto hash_mode = [](char c) { return std::tolower(c) == 'd' || std::tolower(c) == 'i'; };
+    if (!hash_mode(mode) || (pre_seed && !hash_mode(pre_mode))) {
         // error convention of the reference: "Unknown matching mode" + exit (ReadsMatchers.cpp:737-739); here a status
-        return fail(ctx, PGM_ERR_UNSUPPORTED, std::string("pgm_map_reads: matching mode '") + mode + "' is not the hash-matcher path ('d'/'D')");
+        return fail(ctx, PGM_ERR_UNSUPPORTED, std::string("pgm_map_reads: matching mode '") + mode + "' is not a hash-matcher path ('d'/'D', 'i'/'I')");
     }
     // ReadsMatchers.cpp:699-713
     const uint32_t max_mm = L / min_chars_per_mismatch;
@@ -1002,12 +1033,13 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
         return PGM_OK;
     };
     if (L == cur_exact) rc = pgm_match_begin(ctx, L, 1, 0, 0, 0);                    // DefaultReadsExactMatcher (:718-722)
-    else rc = pgm_match_begin(ctx, cur_exact, target_mm + 1, max_mm, cur_min, 0);     // DefaultReadsApproxMatcher (:724-727)
+    else rc = match_begin_impl(ctx, cur_exact, target_mm + 1, max_mm, cur_min, 0,    // DefaultReadsApproxMatcher (:724-727) /
+                               std::tolower(cur_mode) == 'i');                        // InterleavedReadsApproxMatcher (:728-731)
     if (rc || (rc = run_passes(pre_exact == 0))) return rc;
     if (pre_exact > 0) {
         // second phase (:749-779); minMismatches comes from the FIRST phase's targetMismatches (:755)
         const uint32_t min2 = std::isupper((unsigned char)mode) ? max_mm : target_mm + 1;
-        if ((rc = pgm_match_begin(ctx, reads_exact, L / reads_exact, max_mm, min2, 1)) || (rc = run_passes(true))) return rc;
+        if ((rc = match_begin_impl(ctx, reads_exact, L / reads_exact, max_mm, min2, 1, std::tolower(mode) == 'i')) || (rc = run_passes(true))) return rc;
     }
     return pgm_get_results(ctx, out_pos, out_rc, out_mm, stats);
 }

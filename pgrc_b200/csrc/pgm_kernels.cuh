@@ -50,6 +50,8 @@
 #define PGM_WORDS_PER_WARP (PGM_TILE_WORDS / PGM_SCAN_WARPS)
 #define PGM_WQ_CAP 320                     // per-warp candidate queue entries
 #define PGM_WQ_ROUND 128                   // most entries one probe round can add (32 lanes x 4 slots)
+#define PGM_ILV_WORDS 256                  // mode 'i': words of the de-interleaved tile per plane (stride <= PGM_ILV_MAX_PARTS)
+#define PGM_ILV_MAX_PARTS 31
 #define PGM_WALK_CAP 6                     // full buckets walked before a duplicate key is chained
 
 #define PGM_EMPTY64 0xFFFFFFFFFFFFFFFFull
@@ -139,6 +141,8 @@ struct ScanParams {
     uint32_t first_word;            // first local word of tile 0 (multiple of 4)
     uint32_t n_tiles;
     uint32_t seed_len, parts, max_mm, min_mm;
+    uint32_t shift_unit;            // alignment start = window start - j * shift_unit: seed_len (mode 'd'), 1 (mode 'i')
+    uint32_t ilv;                   // 0: seed j = read bases [j*n, (j+1)*n) (mode 'd'); else the stride (= parts) of mode 'i'
     uint32_t tail_mask;             // valid bits of the last 32-base chunk of a seed
     int rev_mode;
     int l2_hints;                   // 1: filter loads carry an L2 evict_last policy
@@ -497,7 +501,8 @@ struct BuildQueues {
 template <bool FAST>
 __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsView reads, TableView tab, BuildQueues q, uint32_t r_begin,
                                                                         uint32_t r_end, uint32_t seed_len, uint32_t parts, uint32_t min_mm,
-                                                                        int continuation, uint32_t tail_mask, unsigned long long *inserted) {
+                                                                        int continuation, uint32_t tail_mask, uint32_t ilv,
+                                                                        unsigned long long *inserted) {
     extern __shared__ uint4 s_ent[];                                   // parts x blockDim staged entries {h1, h2, pattern, region | rank << 8}
     __shared__ unsigned int s_count[PGM_MAX_REGIONS], s_base[PGM_MAX_REGIONS];
     const uint32_t n_regions = q.region_bits ? 1u << q.region_bits : 0u;
@@ -548,6 +553,20 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
                             const uint32_t h = (g < 2 ? w0.v[5 + 2 * g] : w1.v[2 * (g - 2) + 1]) & m;
                             P ^= rotr32(l, sh); Q ^= rotr32(h, sh); R ^= rotr32(l & h, sh);
                         }
+                    }
+                } else if (ilv) {
+                    // mode 'i': seed j = read bases j, j + s, j + 2s, ... (addPackedPatterns, HashMatcher.cpp:82-96)
+                    for (uint32_t i = 0; i < nch; i++) {
+                        uint32_t l = 0, h = 0, nm = 0;
+                        const uint32_t cnt = min(32u, seed_len - 32 * i);
+                        uint32_t b = j + 32 * i * ilv;
+                        for (uint32_t k = 0; k < cnt; k++, b += ilv) {
+                            const uint32_t wi = (b >> 5) * il, sh = b & 31u;
+                            l |= ((__ldg(pl + wi) >> sh) & 1u) << k;
+                            h |= ((__ldg(pl + wi + 1) >> sh) & 1u) << k;
+                            if (is_n) nm |= ((__ldg(pl + wi + 2) >> sh) & 1u) << k;
+                        }
+                        P ^= l; Q ^= h; R ^= (l & h); FN ^= nm;
                     }
                 } else {
                     for (uint32_t i = 0; i < nch; i++) {
@@ -646,6 +665,7 @@ struct ScanShared {
     uint32_t hi[2][PGM_BUF_WORDS];
     uint2 wq[PGM_SCAN_WARPS][PGM_WQ_CAP];   // per-warp candidate queues {pos_in_tile | chain << 31, pattern}
     uint16_t q1[PGM_TILE_POS];              // filter-positive positions of the tile
+    uint32_t dl[PGM_ILV_WORDS], dh[PGM_ILV_WORDS];   // mode 'i': the tile's planes de-interleaved by position residue
     uint64_t bar[2];
     unsigned int q1_count[2], q1_cursor[2], tile[2];
 };
@@ -714,7 +734,12 @@ __device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, cons
 // hashed and appended to the queue of its table region instead of being probed (ranks within the tile through
 // shared-memory counters, one global reservation per region and tile); the per-warp candidate queues' shared memory
 // holds the ranks.
-template <int NCH, bool FAST, int MODE>
+// ILV (mode 'i', InterleavedReadsApproxMatcher, ReadsMatchers.cpp:343-409): the seed window at text position x is
+// text[x], text[x+s], text[x+2s], ... (s = parts; InterleavedConstantLengthPatternsOnTextHashMatcher, HashMatcher.h:108-135),
+// and seed j aligns the read at x - j.  Per tile the staged planes are de-interleaved by position residue into `s` phase
+// strings in shared memory (phase r, index q <-> tile position r + q*s): in phase space the window is contiguous again and
+// stage A1 / the rehash of A2 run unchanged on it; verification (stage B) uses the original planes.
+template <int NCH, bool FAST, int MODE, bool ILV>
 __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_constant__ ScanParams p) {
     __shared__ __align__(128) ScanShared sm;
     if (MODE == 0 && p.only_if != nullptr && *p.only_if == 0) {
@@ -773,7 +798,44 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
         const int64_t vb64 = (int64_t)p.own_begin - (int64_t)tile_g0, ve64 = (int64_t)p.own_end - (int64_t)tile_g0;
         const uint32_t vb = (uint32_t)max((int64_t)0, min(vb64, (int64_t)PGM_TILE_POS));
         const uint32_t ve = (uint32_t)max((int64_t)0, min(ve64, (int64_t)PGM_TILE_POS));
-        {
+        // mode 'i': phase r of the tile = bits r, r+s, r+2s, ... of the staged planes, MW words per phase
+        const uint32_t ilv_s = ILV ? p.ilv : 1u;
+        const uint32_t ilv_qc = (((PGM_TILE_POS + ilv_s - 1) / ilv_s) + 31) >> 5;   // 32-position chunks per phase
+        const uint32_t ilv_mw = ilv_qc + NCH + 1;
+        if constexpr (ILV) {
+            constexpr uint32_t SRC_BITS = (PGM_BUF_WORDS - PGM_HALO_L) * 32;
+            const uint32_t per_plane = ilv_s * ilv_mw;
+            for (uint32_t w = t; w < 2 * per_plane; w += PGM_SCAN_THREADS) {
+                const bool hi_plane = w >= per_plane;
+                const uint32_t v = hi_plane ? w - per_plane : w, r = v / ilv_mw, m = v - r * ilv_mw;
+                const uint32_t *src = hi_plane ? shi : slo;
+                uint32_t word = 0, bit = r + 32 * m * ilv_s;
+#pragma unroll 8
+                for (int k = 0; k < 32; k++, bit += ilv_s)
+                    if (bit < SRC_BITS) word |= ((src[bit >> 5] >> (bit & 31u)) & 1u) << k;
+                (hi_plane ? sm.dh : sm.dl)[v] = word;
+            }
+            __syncthreads();
+            for (uint32_t c = warp; c < ilv_s * ilv_qc; c += PGM_SCAN_WARPS) {
+                const uint32_t r = c / ilv_qc, q = (c - r * ilv_qc) * 32 + lane;
+                const uint32_t pos = r + q * ilv_s;
+                uint32_t P, Q, R;
+                window_form<NCH>(sm.dl + r * ilv_mw, sm.dh + r * ilv_mw, q, p.tail_mask, P, Q, R);
+                const uint32_t f = filter_hash(P, Q, R);
+                const uint32_t fm = filter_bits(f);
+                const uint32_t fw = !p.tab.filter ? 0xFFFFFFFFu : fhints ? ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep)
+                                                                         : __ldg(p.tab.filter + (f & p.tab.filter_mask));
+                const bool hit = pos < PGM_TILE_POS && pos >= vb && pos < ve && (fw & fm) == fm;
+                const uint32_t bal = __ballot_sync(PGM_FULL, hit);
+                if (bal) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.q1_count[buf], __popc(bal));
+                    base = __shfl_sync(PGM_FULL, base, 0);
+                    if (hit) sm.q1[base + __popc(bal & lt_mask)] = (uint16_t)pos;
+                    if (lane == 0) n_pos += __popc(bal);
+                }
+            }
+        } else {
             constexpr int U = 4;
             const uint32_t w_first = warp * PGM_WORDS_PER_WARP;
 #pragma unroll 1
@@ -871,7 +933,11 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
                         if (!act && mine < q1n) {
                             act = true;
                             ppos = sm.q1[mine];
-                            const uint64_t hv = window_hash<NCH>(slo, shi, ppos, p.tail_mask);
+                            uint64_t hv;
+                            if constexpr (ILV) {
+                                const uint32_t q = ppos / ilv_s, r = ppos - q * ilv_s;
+                                hv = window_hash<NCH>(sm.dl + r * ilv_mw, sm.dh + r * ilv_mw, q, p.tail_mask);
+                            } else hv = window_hash<NCH>(slo, shi, ppos, p.tail_mask);
                             const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
                             ptag = seed_tag(h2);
                             pb = __umulhi(h1, p.tab.n_buckets);
@@ -939,7 +1005,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
                     uint32_t cr = cpat >> p.reads.part_bits, cj = cpat & pmask;
                     for (;;) {
                         const uint32_t L = p.reads.read_len;
-                        const uint32_t shift = on ? cj * p.seed_len : 0u;
+                        const uint32_t shift = on ? cj * p.shift_unit : 0u;
                         // tile-relative alignment: always inside the staged buffer, so the count needs no validity checks
                         const uint32_t boff = PGM_HALO_L * 32 + cpos - shift;
                         const uint32_t tw = boff >> 5, ts = boff & 31u;
@@ -1026,7 +1092,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
                         if (on) v = hints ? ld256_stream_hint(reinterpret_cast<const u32x8 *>(crec) + half, pol_stream)
                                           : ld256_cg(reinterpret_cast<const u32x8 *>(crec) + half);
                         // tile-relative alignment: always inside the staged buffer, so the count needs no validity checks
-                        const uint32_t shift = cj * p.seed_len;
+                        const uint32_t shift = cj * p.shift_unit;
                         const uint32_t boff = PGM_HALO_L * 32 + cpos - (on ? shift : 0u);
                         const uint32_t L = p.reads.read_len, W = p.reads.W;
                         int c = count_groups(2 * half, isn, make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]), blo, bhi, boff, W, L)

@@ -115,8 +115,13 @@ namespace PgTools {
 
     GpuMatcherSession::~GpuMatcherSession() { pgm_destroy(ctx); }
 
-    void GpuMatcherSession::begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation) {
-        check(pgm_match_begin(ctx, seedLength, parts, maxMismatches, minMismatches, continuation ? 1 : 0), ctx, "pgm_match_begin");
+    void GpuMatcherSession::begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation,
+                                  bool interleaved) {
+        if (interleaved)
+            check(pgm_match_begin_interleaved(ctx, seedLength, parts, maxMismatches, minMismatches, continuation ? 1 : 0), ctx,
+                  "pgm_match_begin_interleaved");
+        else
+            check(pgm_match_begin(ctx, seedLength, parts, maxMismatches, minMismatches, continuation ? 1 : 0), ctx, "pgm_match_begin");
     }
 
     void GpuMatcherSession::pass(bool revCompMode) {
@@ -161,22 +166,24 @@ namespace PgTools {
     // ------------------------------------------------------------------------------------------ k-mismatch path
     GpuReadsApproxMatcher::GpuReadsApproxMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
                                                  ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength,
-                                                 uint16_t readsExactMatchingChars, uint8_t maxMismatches, uint8_t minMismatches)
+                                                 uint16_t readsExactMatchingChars, uint8_t maxMismatches, uint8_t minMismatches,
+                                                 bool interleaved)
             : AbstractReadsApproxMatcher(pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength, readsExactMatchingChars,
-                                         maxMismatches, minMismatches), session(session), partLength(readsExactMatchingChars) {}
+                                         maxMismatches, minMismatches), session(session), partLength(readsExactMatchingChars),
+              interleaved(interleaved) {}
 
     void GpuReadsApproxMatcher::initMatching() {                                   // replaces ReadsMatchers.cpp:276-285
         DefaultReadsMatcher::initMatching();
         readMismatchesCount.clear();
         readMismatchesCount.insert(readMismatchesCount.end(), readsCount, NOT_MATCHED_COUNT);
-        session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, false);
+        session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, false, interleaved);
     }
 
     void GpuReadsApproxMatcher::initMatchingContinuation(DefaultReadsMatcher *pMatcher) {   // replaces :287-295
         // the device still holds the first phase's per-read state; reads matched with <= minMismatches are left
         // out of the new table there (getMatchedReadsBitmap(minMismatches), ReadsMatchers.cpp:290-291)
         AbstractReadsApproxMatcher::initMatchingContinuation(pMatcher);
-        session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, true);
+        session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, true, interleaved);
     }
 
     void GpuReadsApproxMatcher::executeMatching(bool revCompMode) {                // replaces ReadsMatchers.cpp:297-341
@@ -214,7 +221,7 @@ namespace PgTools {
             matcher = new GpuReadsExactMatcher(&session, pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength);
         else
             matcher = new GpuReadsApproxMatcher(&session, pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength,
-                                                firstSeed, maxMismatches, firstMinMismatches);
+                                                firstSeed, maxMismatches, firstMinMismatches, tolower(firstMode) == 'i');
         cout << "Target pseudogenome length: " << pgLength << endl;
         *logout << endl;
         cout << "readsAlignmentSeedLength (minCharsPerMismatch, matchingMode): " << (int) firstSeed <<
@@ -226,7 +233,7 @@ namespace PgTools {
         if (twoPhases) {
             const uint8_t secondMinMismatches = isupper((unsigned char) matchingMode) ? maxMismatches : targetMismatches + 1;
             AbstractReadsApproxMatcher *approxMatcher = new GpuReadsApproxMatcher(&session, pgPtr, pgLength, revComplPg, readsSet,
-                    matchPrefixLength, readsExactMatchingChars, maxMismatches, secondMinMismatches);
+                    matchPrefixLength, readsExactMatchingChars, maxMismatches, secondMinMismatches, tolower(matchingMode) == 'i');
             targetMismatches = readLength / readsExactMatchingChars - 1;
             cout << endl << "Reads matching 2nd PHASE." << endl;
             cout << "readsExactMatchingChars (minCharsPerMismatch, matchingMode): " << (int) readsExactMatchingChars <<
@@ -265,7 +272,8 @@ namespace PgTools {
             readsSet->getReadsSetProperties()->readsCount = readsSet->readsCount();
         const char *env = getenv("PGRC_GPU_MATCHER");
         const bool wantGpu = env && *env && strcmp(env, "0") != 0;
-        const bool hashMatcherPath = tolower(matchingMode) == 'd' && (preReadsExactMatchingChars == 0 || tolower(preMatchingMode) == 'd')
+        auto hashMode = [](char c) { return tolower(c) == 'd' || tolower(c) == 'i'; };
+        const bool hashMatcherPath = hashMode(matchingMode) && (preReadsExactMatchingChars == 0 || hashMode(preMatchingMode))
                                      && matchPrefixLength == DefaultReadsMatcher::DISABLED_PREFIX_MODE;
         if (wantGpu && hashMatcherPath)
             return mapReadsIntoPgOnGpu(sPg, revComplPg, preserveOrderMode, readsSet, pairFileMode, revComplPairFile, matchPrefixLength,

@@ -4,7 +4,7 @@
 // Two classes sit behind the reference's bases and override exactly the protected virtuals the reference's
 // hash-matcher classes override (matching/ReadsMatchers.h:45-46,128):
 //     GpuReadsExactMatcher  : DefaultReadsExactMatcher     (ReadsMatchers.h:85-107,  .cpp:190-230)
-//     GpuReadsApproxMatcher : AbstractReadsApproxMatcher   (ReadsMatchers.h:109-144, .cpp:276-341)
+//     GpuReadsApproxMatcher : AbstractReadsApproxMatcher   (ReadsMatchers.h:109-144, .cpp:276-341; mode 'i': .cpp:343-409)
 // They fill the inherited result members (readMatchPos, readMatchRC, readMismatchesCount, matchedReadsCount,
 // matchedCountPerMismatches), so everything downstream — getMatchedReadsBitmap, exportMatchesInPgOrder /
 // exportMatchesInOriginalOrder, the archive writer — is the reference's unmodified code.
@@ -27,7 +27,8 @@ namespace PgTools {
         GpuMatcherSession(const char *pgPtr, uint64_t pgLength, ConstantLengthReadsSetInterface *readsSet);
         ~GpuMatcherSession();
         static void check(int rc, pgm_ctx *c, const char *what);   // prints pgm_last_error, exit(EXIT_FAILURE)
-        void begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation);
+        void begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation,
+                   bool interleaved = false);
         void pass(bool revCompMode);
         // copies the per-read results into the reference's member vectors
         void fetch(vector<uint64_t> &readMatchPos, vector<bool> &readMatchRC, vector<uint8_t> *readMismatchesCount,
@@ -44,9 +45,12 @@ namespace PgTools {
                              ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength);
     };
 
+    // interleaved = true stands in for InterleavedReadsApproxMatcher (mode 'i', ReadsMatchers.h:146-165, .cpp:343-409),
+    // false for DefaultReadsApproxMatcher (mode 'd'): same base class, same members, only the seed geometry differs.
     class GpuReadsApproxMatcher : public AbstractReadsApproxMatcher {
         GpuMatcherSession *session;
         uint_read_len_max partLength;
+        bool interleaved;
     protected:
         void initMatching() override;
         void initMatchingContinuation(DefaultReadsMatcher *pMatcher) override;
@@ -54,10 +58,11 @@ namespace PgTools {
     public:
         GpuReadsApproxMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
                               ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength,
-                              uint16_t readsExactMatchingChars, uint8_t maxMismatches, uint8_t minMismatches = 0);
+                              uint16_t readsExactMatchingChars, uint8_t maxMismatches, uint8_t minMismatches = 0,
+                              bool interleaved = false);
     };
 
-    // Same signature as PgTools::mapReadsIntoPg (ReadsMatchers.h:202-207).  Matching modes 'd'/'D' run on the GPU when
+    // Same signature as PgTools::mapReadsIntoPg (ReadsMatchers.h:202-207).  Matching modes 'd'/'D' and 'i'/'I' run on the GPU when
     // the environment variable PGRC_GPU_MATCHER is set to something other than 0; every other case is passed on
     // to the reference's own function.
     const vector<bool> mapReadsIntoPgOnGpu(SeparatedPseudoGenome *sPg, bool revComplPg, bool preserveOrderMode,

@@ -145,8 +145,11 @@ class GpuReadsMatcher:
         self.read_len = read_len
 
     # -- per-pass steps (initMatching / executeMatching split at the cross-GPU merge point)
-    def match_begin(self, seed_len: int, parts: int, max_mm: int, min_mm: int, continuation: bool = False):
-        self._check(self._lib.pgm_match_begin(self._h, seed_len, parts, max_mm, min_mm, int(continuation)))
+    def match_begin(self, seed_len: int, parts: int, max_mm: int, min_mm: int, continuation: bool = False,
+                    interleaved: bool = False):
+        """initMatching / initMatchingContinuation of the default (contiguous seeds) or the interleaved matcher."""
+        fn = self._lib.pgm_match_begin_interleaved if interleaved else self._lib.pgm_match_begin
+        self._check(fn(self._h, seed_len, parts, max_mm, min_mm, int(continuation)))
 
     def scan_pass(self, rev_mode: bool):
         self._check(self._lib.pgm_scan_pass(self._h, int(rev_mode)))
@@ -219,14 +222,14 @@ class GpuReadsMatcher:
 @dataclass
 class MatchPlan:
     """Parameter derivation of mapReadsIntoPg (ReadsMatchers.cpp:699-713,749-756): a list of
-    matcher phases, each (seed_len, parts, max_mm, min_mm, continuation)."""
+    matcher phases, each (seed_len, parts, max_mm, min_mm, continuation, interleaved)."""
     phases: list
 
     @staticmethod
     def derive(read_len: int, seed: int, min_chars_per_mismatch: int, mode: str, pre_seed: int = 0,
                pre_mode: str = "d") -> "MatchPlan":
-        if mode.lower() != "d" or (pre_seed and pre_mode.lower() != "d"):
-            raise PgmError(-6, f"matching mode '{mode}' is not the hash-matcher path ('d'/'D')")
+        if mode.lower() not in "di" or (pre_seed and pre_mode.lower() not in "di") or len(mode) != 1 or len(pre_mode) != 1:
+            raise PgmError(-6, f"matching mode '{mode}' is not a hash-matcher path ('d'/'D', 'i'/'I')")
         if seed <= 0 or min_chars_per_mismatch <= 0:
             raise PgmError(-1, "seed and min_chars_per_mismatch must be > 0")
         L = read_len
@@ -235,10 +238,12 @@ class MatchPlan:
         cur_exact, cur_mode = (pre_exact, pre_mode) if pre_exact > 0 else (reads_exact, mode)
         cur_min = max_mm if cur_mode.isupper() else 0
         target_mm = L // cur_exact - 1
-        phases = [(L, 1, 0, 0, False)] if L == cur_exact else [(cur_exact, target_mm + 1, max_mm, cur_min, False)]
+        ilv = lambda c, parts: c.lower() == "i" and parts > 1   # InterleavedReadsApproxMatcher (:728-731, :760-763)
+        phases = ([(L, 1, 0, 0, False, False)] if L == cur_exact
+                  else [(cur_exact, target_mm + 1, max_mm, cur_min, False, ilv(cur_mode, target_mm + 1))])
         if pre_exact > 0:
             min2 = max_mm if mode.isupper() else target_mm + 1
-            phases.append((reads_exact, L // reads_exact, max_mm, min2, True))
+            phases.append((reads_exact, L // reads_exact, max_mm, min2, True, ilv(mode, L // reads_exact)))
         return MatchPlan(phases)
 
 
@@ -322,8 +327,8 @@ def run_plan_sharded(m: GpuReadsMatcher, plan: MatchPlan, rev_compl_pg: bool = T
     """Runs the matcher phases on a context that holds one text shard; after every scan the
     per-read accumulators are merged across ranks, then every rank applies the decision, so the
     per-read state stays replicated."""
-    for seed_len, parts, max_mm, min_mm, cont in plan.phases:
-        m.match_begin(seed_len, parts, max_mm, min_mm, cont)
+    for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
+        m.match_begin(seed_len, parts, max_mm, min_mm, cont, ilv)
         for rev in ((False, True) if rev_compl_pg else (False,)):
             m.scan_pass(rev)
             merge(m, group)

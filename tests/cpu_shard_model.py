@@ -35,8 +35,12 @@ class CpuShardMatcher:
         n = self.n_reads
         self.state = [(255, 0, None)] * n   # (mm, rc, pos)
 
-    def match_begin(self, seed_len, parts, max_mm, min_mm, continuation=False):
+    def match_begin(self, seed_len, parts, max_mm, min_mm, continuation=False, interleaved=False):
         self.seed_len, self.parts, self.max_mm, self.min_mm = seed_len, parts, max_mm, min_mm
+        # mode 'i': seed j = read bases j, j+parts, ...; window at g = text[g], text[g+parts], ...; alignment g - j
+        self.stride = parts if interleaved and parts > 1 else 1
+        self.shift = 1 if self.stride > 1 else seed_len
+        self.span = seed_len * self.stride
         n = self.n_reads
         if not continuation:
             self.state = [(255, 0, None)] * n
@@ -45,7 +49,8 @@ class CpuShardMatcher:
             if continuation and self.state[r][0] <= min_mm:
                 continue
             for j in range(parts):
-                self.table.setdefault(_canon(self.reads[r][j * seed_len:(j + 1) * seed_len], seed_len), []).append(r * parts + j)
+                seed = self.reads[r][j:j + self.span:self.stride] if self.stride > 1 else self.reads[r][j * seed_len:(j + 1) * seed_len]
+                self.table.setdefault(_canon(seed, seed_len), []).append(r * parts + j)
         self._reset_acc()
 
     def _reset_acc(self):
@@ -62,29 +67,30 @@ class CpuShardMatcher:
 
     def scan_pass(self, rev):
         n, L, pg = self.seed_len, self.read_len, self.pg_len
-        if pg < n or not self.n_reads:
+        span, sh = self.span, self.shift
+        if pg < span or not self.n_reads:
             return
-        fb, fe = self.own[0], min(self.own[1], pg - n + 1)
+        fb, fe = self.own[0], min(self.own[1], pg - span + 1)
         if fb >= fe:
             return
         sl = self.slice
         if rev:   # this rank's slice of the reverse-complemented text, and its owned window starts there
             sl = np.array([_COMP[int(c)] for c in sl[::-1]], np.uint8)
             origin = pg - (self.slice_begin + len(self.slice))
-            ob, oe = pg - n - (fe - 1), pg - n - fb + 1
+            ob, oe = pg - span - (fe - 1), pg - span - fb + 1
         else:
             origin, ob, oe = self.slice_begin, fb, fe
         a = self.acc
         for g in range(ob, oe):
-            pats = self.table.get(_canon(sl[g - origin:g - origin + n], n))
+            pats = self.table.get(_canon(sl[g - origin:g - origin + span:self.stride], n))
             if not pats:
                 continue
             for pat in pats:
                 r, j = divmod(pat, self.parts)
                 c_in, _, X = self.state[r]
-                if c_in <= self.min_mm or j * n > g:
+                if c_in <= self.min_mm or j * sh > g:
                     continue
-                al = g - j * n
+                al = g - j * sh
                 if al + L > pg:
                     continue
                 assert al - origin >= 0 and al - origin + L <= len(sl), "halo too small"
@@ -107,7 +113,7 @@ class CpuShardMatcher:
                         a["touched"][0] = 1
 
     def resolve_pass(self, rev):
-        n, L, pg = self.seed_len, self.read_len, self.pg_len
+        n, L, pg = self.shift, self.read_len, self.pg_len
         a = self.acc
         for r in range(self.n_reads):
             c_in, _, X = self.state[r]

@@ -1,6 +1,6 @@
 """GPU, end to end through the reference's own CLI: `PgRC-dev` built from the unmodified reference sources with the C++
 shim of pgrc_b200/host/ (oracle/Makefile target `cli`) compresses the same synthetic FASTQ twice — once with the
-reference's CPU hash matchers (mode d), once with the GPU matchers behind the same class interface
+reference's CPU hash matchers (mode d or i), once with the GPU matchers behind the same class interface
 (PGRC_GPU_MATCHER=1) — and the two .pgrc archives must be byte-identical, for every archive mode of BASELINE.json's
 configs (SE, SE_ORD, PE, PE_ORD) and for the two-phase / exact / shortcut parameterisations."""
 import os
@@ -51,6 +51,11 @@ CASES = {
     "SE_two_phase": dict(pair=False, flags=["-l", "d50", "-s", "d33"], gen=dict(genome=200_000, reads=40_000, len=100, err=0.01, seed=6)),
     "SE_exact_prephase": dict(pair=False, flags=["-l", "d100", "-s", "d38"], gen=dict(genome=200_000, reads=40_000, len=100, err=0.003, seed=7)),
     "SE_M2": dict(pair=False, flags=["-M", "2", "-s", "d40"], gen=dict(genome=200_000, reads=40_000, len=120, err=0.02, seed=8)),
+    # mode 'i' (InterleavedReadsApproxMatcher): the same shim classes with strided seeds
+    "SE_ilv_100bp": dict(pair=False, flags=["-s", "i38"], gen=dict(genome=300_000, reads=60_000, len=100, err=0.005, n_frac=0.01, seed=9)),
+    "SE_ORD_ilv_150bp": dict(pair=False, flags=["-o", "-s", "i38"], gen=dict(genome=200_000, reads=40_000, len=150, err=0.005, n_frac=0.01, seed=10)),
+    "PE_ilv_150bp": dict(pair=True, flags=["-s", "i38"], gen=dict(genome=200_000, reads=20_000, len=150, err=0.005, seed=11)),
+    "SE_ilv_two_phase": dict(pair=False, flags=["-l", "i50", "-s", "i33"], gen=dict(genome=200_000, reads=40_000, len=100, err=0.01, seed=12)),
 }
 
 

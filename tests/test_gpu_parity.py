@@ -103,7 +103,7 @@ def test_unsupported_modes_fail_loudly():
     rng = np.random.default_rng(7)
     g = synth.random_genome(4000, rng)
     reads = synth.sample_reads(g, 10, 100, 0.01, rng)
-    for kw in (dict(matching_mode="c"), dict(matching_mode="i"), dict(match_prefix_length=50)):
+    for kw in (dict(matching_mode="c"), dict(matching_mode="x"), dict(match_prefix_length=50)):
         with pytest.raises(matcher.PgmError) as e:
             matcher.map_reads_into_pg(g, synth.pack_reads(reads), None, 100, **kw)
         assert e.value.status == -6
@@ -173,9 +173,9 @@ def _run_sharded_on_one_gpu(inp, world, **kw):
             m.set_reads(inp.lq_packed, inp.n_packed if len(inp.n_reads) else None, inp.read_len)
         plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), kw.get("min_chars_per_mismatch", 3), kw.get("mode", "d"),
                                         kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
-        for seed_len, parts, max_mm, min_mm, cont in plan.phases:
+        for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
             for m in ms:
-                m.match_begin(seed_len, parts, max_mm, min_mm, cont)
+                m.match_begin(seed_len, parts, max_mm, min_mm, cont, ilv)
             for rev in ((False, True) if kw.get("rev_compl", True) else (False,)):
                 for m in ms:
                     m.scan_pass(rev)
@@ -257,4 +257,45 @@ def test_blocked_scan_pipeline_hot_seeds_and_shards(monkeypatch):
     inp = synth.adversarial(59, 100, n_reads=2000, text_len=30000)
     want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len)
     for got in _run_sharded_on_one_gpu(inp, 3):
+        assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)
+
+
+@pytest.mark.parametrize("seed,L", [(71, 100), (72, 150), (73, 120), (74, 64), (75, 255)])
+def test_interleaved_mode_adversarial(seed, L):
+    """Mode 'i' (InterleavedReadsApproxMatcher, ReadsMatchers.cpp:343-409): strided seeds, alignment = hit - j."""
+    got, want = _check(synth.adversarial(seed, L), matching_mode="i")
+    assert want.matched > 50
+
+
+@pytest.mark.parametrize("kw", [
+    dict(matching_mode="i", reads_exact_matching_chars=30),
+    dict(matching_mode="i", reads_exact_matching_chars=33),
+    dict(matching_mode="i", reads_exact_matching_chars=45),
+    dict(matching_mode="i", reads_exact_matching_chars=20),                      # 5 seeds per read
+    dict(matching_mode="i", reads_exact_matching_chars=100),                     # exact path
+    dict(matching_mode="I"),                                                     # shortcut mode
+    dict(matching_mode="i", pre_reads_exact_matching_chars=100),
+    dict(matching_mode="i", pre_reads_exact_matching_chars=50, pre_matching_mode="i"),
+    dict(matching_mode="d", pre_reads_exact_matching_chars=50, pre_matching_mode="i"),
+    dict(matching_mode="I", pre_reads_exact_matching_chars=50, pre_matching_mode="d"),
+    dict(matching_mode="i", min_chars_per_mismatch=2),
+    dict(matching_mode="i", rev_compl_pg=False),
+])
+def test_interleaved_mode_parameter_matrix(kw):
+    for s in (76, 77):
+        _check(synth.adversarial(s, 100), **kw)
+
+
+def test_interleaved_mode_workloads_edges_and_shards():
+    _check(synth.workload(250_000, 20_000, 100, 0.001, seed=78, name="c1/20"), matching_mode="i")
+    _check(synth.workload(500_000, 100_000, 150, 0.005, seed=79, n_frac=0.02, name="c2/100"), matching_mode="i")
+    rng = np.random.default_rng(80)
+    g = synth.random_genome(5000, rng)
+    reads = synth.sample_reads(g, 300, 100, 0.01, rng)
+    for text in (g[:99], g[:75], g[:76], g[:77], g[:100], g[:101]):       # around the seed span (2 x 38) and the read length
+        _check(synth.MatcherInputs(np.ascontiguousarray(text), reads, np.zeros((0, 100), np.uint8), 100, f"text{len(text)}"), matching_mode="i")
+    _check(synth.MatcherInputs(g, np.zeros((0, 100), np.uint8), synth.inject_n(reads[:50], rng), 100, "only N reads"), matching_mode="i")
+    inp = synth.adversarial(81, 100, n_reads=2000, text_len=30000)
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, mode="i")
+    for got in _run_sharded_on_one_gpu(inp, 3, mode="i"):
         assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)

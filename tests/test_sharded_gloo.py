@@ -43,7 +43,8 @@ def _worker(rank, world, port, case, kw, ret_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(pre_seed=100), dict(mode="D"), dict(seed=45, rev_compl=False)])
+@pytest.mark.parametrize("kw", [dict(), dict(pre_seed=100), dict(mode="D"), dict(seed=45, rev_compl=False), dict(mode="i"),
+                                dict(mode="i", pre_seed=50, pre_mode="i")])
 def test_text_sharded_two_ranks_gloo(tmp_path, kw):
     import oracle
     from pgrc_b200 import synth
@@ -61,15 +62,21 @@ def test_text_sharded_two_ranks_gloo(tmp_path, kw):
 def test_match_plan_mirrors_reference_parameter_derivation():
     from pgrc_b200.matcher import MatchPlan, PgmError
     # (ReadsMatchers.cpp:699-713,749-756)
-    assert MatchPlan.derive(100, 38, 3, "d").phases == [(38, 2, 33, 0, False)]
-    assert MatchPlan.derive(150, 38, 3, "d").phases == [(38, 3, 50, 0, False)]
-    assert MatchPlan.derive(100, 38, 3, "D").phases == [(38, 2, 33, 33, False)]
-    assert MatchPlan.derive(100, 100, 3, "d").phases == [(100, 1, 0, 0, False)]
-    assert MatchPlan.derive(100, 250, 3, "d").phases == [(100, 1, 0, 0, False)]
-    assert MatchPlan.derive(100, 38, 3, "d", pre_seed=100).phases == [(100, 1, 0, 0, False), (38, 2, 33, 1, True)]
-    assert MatchPlan.derive(100, 38, 3, "d", pre_seed=50).phases == [(50, 2, 33, 0, False), (38, 2, 33, 2, True)]
-    assert MatchPlan.derive(100, 38, 3, "D", pre_seed=50).phases == [(50, 2, 33, 0, False), (38, 2, 33, 33, True)]
-    for bad in ("c", "i", "x"):
+    F = False
+    assert MatchPlan.derive(100, 38, 3, "d").phases == [(38, 2, 33, 0, F, F)]
+    assert MatchPlan.derive(150, 38, 3, "d").phases == [(38, 3, 50, 0, F, F)]
+    assert MatchPlan.derive(100, 38, 3, "D").phases == [(38, 2, 33, 33, F, F)]
+    assert MatchPlan.derive(100, 100, 3, "d").phases == [(100, 1, 0, 0, F, F)]
+    assert MatchPlan.derive(100, 250, 3, "d").phases == [(100, 1, 0, 0, F, F)]
+    assert MatchPlan.derive(100, 38, 3, "d", pre_seed=100).phases == [(100, 1, 0, 0, F, F), (38, 2, 33, 1, True, F)]
+    assert MatchPlan.derive(100, 38, 3, "d", pre_seed=50).phases == [(50, 2, 33, 0, F, F), (38, 2, 33, 2, True, F)]
+    assert MatchPlan.derive(100, 38, 3, "D", pre_seed=50).phases == [(50, 2, 33, 0, F, F), (38, 2, 33, 33, True, F)]
+    # mode 'i': the interleaved matcher wherever the reference constructs it (:728-731, :760-763)
+    assert MatchPlan.derive(150, 38, 3, "i").phases == [(38, 3, 50, 0, F, True)]
+    assert MatchPlan.derive(100, 100, 3, "i").phases == [(100, 1, 0, 0, F, F)]
+    assert MatchPlan.derive(100, 38, 3, "I", pre_seed=50, pre_mode="d").phases == [(50, 2, 33, 0, F, F), (38, 2, 33, 33, True, True)]
+    assert MatchPlan.derive(100, 38, 3, "d", pre_seed=50, pre_mode="i").phases == [(50, 2, 33, 0, F, True), (38, 2, 33, 2, True, F)]
+    for bad in ("c", "x"):
         with pytest.raises(PgmError):
             MatchPlan.derive(100, 38, 3, bad)
 
