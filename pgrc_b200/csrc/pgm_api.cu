@@ -313,7 +313,7 @@ int build_range(pgm_ctx *ctx, uint32_t r_begin, uint32_t r_end, int continuation
     const uint32_t tail = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
     const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(r_end - r_begin, PGM_BUILD_THREADS), (uint64_t)ctx->sm_count * 8);
     const size_t smem = ctx->bq_region_bits ? (size_t)ctx->parts * PGM_BUILD_THREADS * sizeof(uint4) : 0;
-    const bool fast = ctx->n_n == 0 && ctx->lq_stride16 == 4 && !ctx->interleaved;   // only ACGT reads, 64-byte records, contiguous seeds: record held in registers
+    const bool fast = ctx->n_n == 0 && ctx->lq_stride16 == 4;         // only ACGT reads, 64-byte records: record held in registers
     KLAUNCH(PGM_K_BUILD_TABLE, "build_table_kernel",
             if (fast) pgm::build_table_kernel<true><<<grid, PGM_BUILD_THREADS, smem, ctx->stream>>>(
                 reads_view(ctx), table_view(ctx), build_queues(ctx), r_begin, r_end, ctx->seed_len, ctx->parts, ctx->min_mm, continuation, tail, ctx->ilv(),

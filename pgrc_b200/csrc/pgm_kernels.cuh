@@ -477,6 +477,19 @@ __device__ __forceinline__ void table_insert(const TableView &tab, uint32_t h1, 
     }
 }
 
+// Mode 'i': the part of seed j (read bases j, j + s, j + 2s, ...; n of them) that lies in the 32-base group g of a read,
+// XOR-folded into the canonical form (base j + k*s lands on bit k mod 32).
+__device__ __forceinline__ void ilv_fold_group(uint32_t wl, uint32_t wh, uint32_t wn, uint32_t g, uint32_t j, uint32_t s, uint32_t n,
+                                               uint32_t &P, uint32_t &Q, uint32_t &R, uint32_t &FN) {
+    const uint32_t first = 32u * g, end = min(first + 32u, j + n * s);
+    uint32_t k = first > j ? (first - j + s - 1u) / s : 0u;
+    for (uint32_t b = j + k * s; b < end; b += s, k++) {
+        const uint32_t sh = b - first, kk = k & 31u;
+        const uint32_t l = (wl >> sh) & 1u, h = (wh >> sh) & 1u;
+        P ^= l << kk; Q ^= h << kk; R ^= (l & h) << kk; FN ^= ((wn >> sh) & 1u) << kk;
+    }
+}
+
 // Region queues of the two-step table build: the bucket array is cut into 2^region_bits equal ranges of the home
 // bucket index (= ranges of h1); step 1 appends {h1, h2, pattern} to the queue of the pattern's region, step 2 inserts
 // region after region, so that all CTAs work on one L2-sized piece of the table at a time and every table line is
@@ -538,7 +551,12 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
             uint4 ent = make_uint4(0, 0, 0, 0xFFFFFFFFu);
             if (active) {
                 uint32_t P = 0, Q = 0, R = 0, FN = 0;
-                if (FAST) {
+                if (FAST && ilv) {
+#pragma unroll
+                    for (int g = 0; g < 6; g++)
+                        ilv_fold_group(g < 2 ? w0.v[4 + 2 * g] : w1.v[2 * (g - 2)], g < 2 ? w0.v[5 + 2 * g] : w1.v[2 * (g - 2) + 1], 0u,
+                                       (uint32_t)g, j, ilv, seed_len, P, Q, R, FN);
+                } else if (FAST) {
                     // a base at read position x lands on bit (x - j*n) mod 32: every 32-base group contributes
                     // rotr(group & [seed range], (j*n) mod 32) — no cross-register funnel shifts, static register indices
                     const int b0 = (int)(j * seed_len), b1 = b0 + (int)seed_len;
@@ -556,18 +574,9 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
                     }
                 } else if (ilv) {
                     // mode 'i': seed j = read bases j, j + s, j + 2s, ... (addPackedPatterns, HashMatcher.cpp:82-96)
-                    for (uint32_t i = 0; i < nch; i++) {
-                        uint32_t l = 0, h = 0, nm = 0;
-                        const uint32_t cnt = min(32u, seed_len - 32 * i);
-                        uint32_t b = j + 32 * i * ilv;
-                        for (uint32_t k = 0; k < cnt; k++, b += ilv) {
-                            const uint32_t wi = (b >> 5) * il, sh = b & 31u;
-                            l |= ((__ldg(pl + wi) >> sh) & 1u) << k;
-                            h |= ((__ldg(pl + wi + 1) >> sh) & 1u) << k;
-                            if (is_n) nm |= ((__ldg(pl + wi + 2) >> sh) & 1u) << k;
-                        }
-                        P ^= l; Q ^= h; R ^= (l & h); FN ^= nm;
-                    }
+                    for (uint32_t g = 0; g < reads.W; g++)
+                        ilv_fold_group(__ldg(pl + g * il), __ldg(pl + g * il + 1), is_n ? __ldg(pl + g * il + 2) : 0u, g, j, ilv, seed_len,
+                                       P, Q, R, FN);
                 } else {
                     for (uint32_t i = 0; i < nch; i++) {
                         const uint32_t bit = j * seed_len + 32 * i;
@@ -660,12 +669,13 @@ __global__ void __launch_bounds__(PGM_INSERT_THREADS, 8) build_insert_kernel(Tab
 }
 
 // ------------------------------------------------------------------------------------------ the scan
+template <bool ILV>
 struct ScanShared {
     uint32_t lo[2][PGM_BUF_WORDS];
     uint32_t hi[2][PGM_BUF_WORDS];
     uint2 wq[PGM_SCAN_WARPS][PGM_WQ_CAP];   // per-warp candidate queues {pos_in_tile | chain << 31, pattern}
     uint16_t q1[PGM_TILE_POS];              // filter-positive positions of the tile
-    uint32_t dl[PGM_ILV_WORDS], dh[PGM_ILV_WORDS];   // mode 'i': the tile's planes de-interleaved by position residue
+    uint32_t dl[ILV ? PGM_ILV_WORDS : 1], dh[ILV ? PGM_ILV_WORDS : 1];   // mode 'i': the tile's planes de-interleaved by position residue
     uint64_t bar[2];
     unsigned int q1_count[2], q1_cursor[2], tile[2];
 };
@@ -741,7 +751,7 @@ __device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, cons
 // stage A1 / the rehash of A2 run unchanged on it; verification (stage B) uses the original planes.
 template <int NCH, bool FAST, int MODE, bool ILV>
 __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_constant__ ScanParams p) {
-    __shared__ __align__(128) ScanShared sm;
+    __shared__ __align__(128) ScanShared<ILV> sm;
     if (MODE == 0 && p.only_if != nullptr && *p.only_if == 0) {
         // the pipeline finished without a queue overflow: nothing to redo, its staged counters become final
         if (blockIdx.x == 0 && threadIdx.x < 4) p.counters[threadIdx.x] += p.sq.counters[threadIdx.x];
