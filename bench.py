@@ -2,7 +2,7 @@
 """bench.py — matching reads/sec of the read-vs-pseudogenome matcher (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c1..c5] [--scale F] [--shard text|reads]
+                    [--workload c1..c5] [--scale F] [--shard text|reads|2d]
 
 One "step" = one whole matcher invocation (what PgTools::mapReadsIntoPg does between
 ReadsMatchers.cpp:714 and :783): text upload/packing, read upload/unpacking, seed-table build,
@@ -48,12 +48,16 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="scale genome and read count (testing)")
     ap.add_argument("--mode", default="d", choices=["d", "i"], help="matching mode: d = contiguous seeds (the headline), "
                     "i = interleaved seeds (InterleavedReadsApproxMatcher, SURVEY §8(f) row 3)")
-    ap.add_argument("--shard", default="auto", choices=["auto", "text", "reads"],
-                    help="multi-GPU partitioning: text ranges + NCCL min-merge of the per-read keys, or read ranges (no collective); "
-                         "auto = reads (the table build and the probes shard with the reads; see DESIGN.md §7)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "text", "reads", "2d"],
+                    help="multi-GPU partitioning: text ranges + NCCL min-merge of the per-read keys, read ranges (no collective), or "
+                         "2d = --text-shards T text ranges x N/T read groups (merge inside each group of T ranks); auto = reads, "
+                         "or 2d with T = 2 for texts beyond 1 Gbase on >= 4 GPUs (the per-position stage then dominates; DESIGN.md §7)")
+    ap.add_argument("--text-shards", type=int, default=0, help="T of --shard 2d (0 = auto: 2)")
     ap.add_argument("--cpu-sample", type=float, default=0.05, help="fraction of the workload shape timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="after the timed region: re-count every reported alignment on the "
+                    "device with plain torch ops (size-independent parity property for the full-size configs)")
     # kernel tuning knobs (pgm_set_tuning); defaults = the library's
     ap.add_argument("--filter-bits", type=int, default=-1)
     ap.add_argument("--slots-per-pattern", type=int, default=3)
@@ -237,13 +241,29 @@ def ours(args):
         raise SystemExit("bench.py: no CUDA device; the matcher has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cfg = synth.scaled_config(args.workload, args.scale)
     if args.shard == "auto":
-        args.shard = "reads"
+        args.shard = "2d" if (world >= 4 and cfg["genome_len"] * cfg["copies"] >= 1e9) else "reads"
+    T = 1
+    if args.shard == "2d":
+        T = args.text_shards or 2
+        if world % T or T < 1:
+            raise SystemExit(f"--text-shards {T} does not divide --gpus {world}")
+        if T == 1:
+            args.shard = "reads"
+        elif T == world:
+            args.shard = "text"
+    group = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
+        if args.shard == "2d":
+            # rank = r * T + t: text range t of T, read group r of world / T; the per-read accumulators are merged inside a group
+            for r0 in range(0, world, T):
+                g = dist.new_group(list(range(r0, r0 + T)))
+                if r0 <= rank < r0 + T:
+                    group = g
 
-    cfg = synth.scaled_config(args.workload, args.scale)
     L = cfg["read_len"]
     text_d, lq_d = synth.workload_device(**cfg, seed=SEED, device=dev)   # same seed on every rank: replicated inputs
     n_reads, pg_len = lq_d.shape[0], text_d.numel()
@@ -254,10 +274,16 @@ def ours(args):
     plan = matcher.MatchPlan.derive(L, MATCH_KW["seed"], MATCH_KW["min_chars_per_mismatch"], MATCH_KW["mode"])
 
     # shard (N > 1)
+    t_rank, r_rank, R = rank % T, rank // T, world // T
     if world > 1 and args.shard == "text":
         sb, sl, ob, oe = matcher.shard_plan(pg_len, rank, world)
         my_text_d = text_d[sb:sb + sl].contiguous()
         my_reads_d = lq_d
+    elif world > 1 and args.shard == "2d":
+        sb, sl, ob, oe = matcher.shard_plan(pg_len, t_rank, T)
+        my_text_d = text_d[sb:sb + sl].contiguous()
+        lo, hi = (n_reads * r_rank) // R, (n_reads * (r_rank + 1)) // R
+        my_reads_d = lq_d[lo:hi].contiguous()
     elif world > 1:
         lo, hi = (n_reads * rank) // world, (n_reads * (rank + 1)) // world
         my_text_d, my_reads_d = text_d, lq_d[lo:hi].contiguous()
@@ -268,10 +294,10 @@ def ours(args):
              torch.empty(n_mine, dtype=torch.uint8, device=dev))
 
     def step(text, reads, out):
-        if world > 1 and args.shard == "text":
+        if world > 1 and args.shard in ("text", "2d"):
             m.set_text_shard(text, sb, pg_len, ob, oe)
             m.set_reads(reads, None, L)
-            matcher.run_plan_sharded(m, plan, True, None)
+            matcher.run_plan_sharded(m, plan, True, group)
             return m.get_results(out)
         m.set_text(text)
         m.set_reads(reads, None, L)
@@ -376,9 +402,20 @@ def ours(args):
                 "text_positions_per_s": round(my_pg / (scan_ms / max(1, scan_launches) * 1e-3), 1) if scan_ms > 0 else None,
                 "kernel_ms_per_step": {k: round(v[0] / psteps, 4) for k, v in tm.items()}}
 
+    verify = None
+    if args.verify:
+        res_v = step(my_text_d, my_reads_d, out_d)
+        torch.cuda.synchronize()
+        verify = synth.check_matches_device(text_d, my_reads_d, L, out_d[0], out_d[1], out_d[2])
+        verify["hist_matches_outputs"] = bool(int((out_d[2] != 255).sum().item()) == res_v.matched)
+        if world > 1:
+            once = args.shard == "reads" or (args.shard == "2d" and t_rank == 0) or (args.shard == "text" and rank == 0)
+            vb = torch.tensor([verify["bad"], verify["matched"] if once else 0], device=dev, dtype=torch.int64)
+            dist.all_reduce(vb)
+            verify["bad"], verify["matched"] = int(vb[0].item()), int(vb[1].item())
     matched_total = res.matched
-    if world > 1 and args.shard == "reads":
-        mt = torch.tensor([res.matched], device=dev, dtype=torch.int64)
+    if world > 1 and args.shard in ("reads", "2d"):
+        mt = torch.tensor([res.matched if (args.shard == "reads" or t_rank == 0) else 0], device=dev, dtype=torch.int64)
         dist.all_reduce(mt)
         matched_total = int(mt.item())
     if rank == 0:
@@ -389,13 +426,16 @@ def ours(args):
                            "seed_len": plan.phases[0][0], "parts": plan.phases[0][1], "max_mismatches": plan.phases[0][2],
                            "matching_mode": MATCH_KW["mode"],
                            "matched": matched_total,
-                           "parallelism": "single GPU" if world == 1 else f"{args.shard}-sharded x{world}",
+                           "parallelism": "single GPU" if world == 1 else (f"2d-sharded: {T} text ranges x {R} read groups" if args.shard == "2d"
+                                                                           else f"{args.shard}-sharded x{world}"),
                            "l2": "inputs (text + reads + seed table) exceed the 126 MB L2; no flush between steps",
                            "candidates_per_step": st["candidates"], "filter_positives_per_step": st["filter_positives"],
                            "table_slots": st["table_slots"],
                            "tuning": {"filter_bits": args.filter_bits, "slots_per_pattern": args.slots_per_pattern,
                                       "ctas_per_sm": args.ctas_per_sm, "l2_hints": args.l2_hints}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        if verify is not None:
+            line["verify"] = verify
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

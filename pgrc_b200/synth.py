@@ -270,10 +270,11 @@ def workload_device(genome_len: int, n_reads: int, read_len: int, err: float, co
             piece = genome[src]
             pieces.append(torch.where(f, 3 - piece, piece))
         remaining -= frac
-    text_codes = torch.cat(pieces)
+    text = torch.cat(pieces)
+    del pieces
     lut = torch.tensor([ord(c) for c in "ACGT"], dtype=torch.uint8, device=device)
-    text = lut[text_codes.long()]
-    del text_codes, pieces
+    for s in range(0, text.numel(), 1 << 28):          # codes -> ASCII in place, chunked (an int64 index of the whole text would not fit)
+        text[s:s + (1 << 28)] = lut[text[s:s + (1 << 28)].long()]
     plen = (L + 3) // 4
     packed = torch.empty((n_reads, plen), dtype=torch.uint8, device=device)
     ar = torch.arange(L, device=device)
@@ -302,3 +303,38 @@ def unpack_reads_ascii(packed: np.ndarray, read_len: int) -> np.ndarray:
     p = np.ascontiguousarray(packed, np.uint8)
     codes = np.stack([(p >> 6) & 3, (p >> 4) & 3, (p >> 2) & 3, p & 3], axis=2).reshape(p.shape[0], -1)[:, :read_len]
     return _CODE2ASCII[codes]
+
+
+def check_matches_device(text, lq_packed, read_len: int, pos, rc, mm, chunk: int = 1 << 20) -> dict:
+    """Size-independent check of the archive-visible outputs, with plain torch ops on the tensors' device (test
+    infrastructure, used by the full-size GPU tests and `bench.py --verify`): every matched read, reverse-complemented
+    when rc is set, must lie inside the text at `pos` with exactly `mm` mismatches.  Returns counts; `bad` must be 0."""
+    import torch
+    dev = text.device
+    L, n = read_len, lq_packed.shape[0]
+    pg_len = text.numel()
+    code = torch.full((256,), 255, dtype=torch.uint8, device=dev)
+    code[torch.tensor([ord(c) for c in "ACGT"], device=dev)] = torch.arange(4, dtype=torch.uint8, device=dev)
+    ar = torch.arange(L, device=dev)
+    pos = torch.as_tensor(pos, device=dev).view(torch.int64) if not isinstance(pos, torch.Tensor) else pos.view(torch.int64)
+    rc = torch.as_tensor(rc, device=dev)
+    mm = torch.as_tensor(mm, device=dev)
+    bad = matched = 0
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        m_ok = mm[s:e] != 255
+        p = torch.where(m_ok, pos[s:e], torch.zeros_like(pos[s:e]))
+        in_text = (p >= 0) & (p + L <= pg_len)
+        p = torch.where(in_text, p, torch.zeros_like(p))
+        pk = lq_packed[s:e]
+        r = torch.stack([(pk >> 6) & 3, (pk >> 4) & 3, (pk >> 2) & 3, pk & 3], dim=2).reshape(e - s, -1)[:, :L]
+        flip = rc[s:e] != 0
+        r = torch.where(flip[:, None], 3 - r.flip(1), r)                   # the read as it lies on the forward text
+        t = code[text[p[:, None] + ar[None, :]].long()]
+        d = (r != t).sum(dim=1)
+        ok = in_text & (d == mm[s:e].long())
+        bad += int((m_ok & ~ok).sum().item())
+        matched += int(m_ok.sum().item())
+        # an unmatched read carries the sentinels
+        bad += int(((~m_ok) & ((pos[s:e] != -1) | flip)).sum().item())
+    return {"reads": n, "matched": matched, "bad": bad}

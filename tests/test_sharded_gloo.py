@@ -101,3 +101,47 @@ def _gather_worker(rank, world, port, pg_len):
 def test_text_all_gather_three_ranks_gloo(pg_len):
     """Read-sharded runs: every rank uploads 1/N of the pseudogenome, one all-gather replicates it."""
     mp.spawn(_gather_worker, args=(3, _free_port(), pg_len), nprocs=3, join=True)
+
+
+def _worker_2d(rank, world, port, case, T, ret_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from cpu_shard_model import CpuShardMatcher
+    from pgrc_b200 import matcher, synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    group = None
+    for r0 in range(0, world, T):                 # rank = r * T + t, as in bench.py --shard 2d
+        g = dist.new_group(list(range(r0, r0 + T)))
+        if r0 <= rank < r0 + T:
+            group = g
+    t, r, R = rank % T, rank // T, world // T
+    inp = synth.adversarial(case["seed"], case["L"], n_reads=case["n_reads"], text_len=case["text_len"], with_n=False)
+    n = len(inp.lq_reads)
+    lo, hi = (n * r) // R, (n * (r + 1)) // R
+    m = CpuShardMatcher()
+    pg_len = inp.text.size
+    sb, sl, ob, oe = matcher.shard_plan(pg_len, t, T)
+    m.set_text_shard(inp.text[sb:sb + sl], sb, pg_len, ob, oe)
+    m.set_reads(inp.lq_reads[lo:hi], None, inp.read_len)
+    matcher.run_plan_sharded(m, matcher.MatchPlan.derive(inp.read_len, 38, 3, "d"), True, group)
+    res = m.get_results()
+    np.savez(os.path.join(ret_dir, f"rank{rank}.npz"), pos=res.pos, rc=res.rc, mm=res.mm, lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+def test_2d_sharded_four_ranks_gloo(tmp_path):
+    """2 text ranges x 2 read groups: the accumulators are merged inside each group of ranks that share the reads."""
+    import oracle
+    from pgrc_b200 import synth
+    case = dict(seed=78, L=100, n_reads=240, text_len=5000)
+    mp.spawn(_worker_2d, args=(4, _free_port(), case, 2, str(tmp_path)), nprocs=4, join=True)
+    inp = synth.adversarial(case["seed"], case["L"], n_reads=case["n_reads"], text_len=case["text_len"], with_n=False)
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, None, inp.read_len)
+    assert want.matched > 20
+    for rank in range(4):
+        got = np.load(tmp_path / f"rank{rank}.npz")
+        lo, hi = int(got["lo"]), int(got["hi"])
+        assert np.array_equal(got["pos"], want.pos[lo:hi]), f"rank {rank}"
+        assert np.array_equal(got["rc"], want.rc[lo:hi]) and np.array_equal(got["mm"], want.mm[lo:hi])
