@@ -333,7 +333,8 @@ def ours(args):
     # end to end: pinned host buffers in, pinned host buffers out
     e2e = None
     if not args.no_e2e:
-        gather_text = world > 1 and args.shard == "reads"
+        gather_text = world > 1 and args.shard in ("reads", "2d")
+        gather_reads = world > 1 and args.shard == "2d"
         if gather_text:
             # every rank uploads 1/N of the text over its own PCIe link; an NCCL all-gather over NVLink replicates it
             tb, te, _ = matcher.text_share(pg_len, rank, world)
@@ -341,13 +342,25 @@ def ours(args):
             gbufs = {}
         else:
             text_h = torch.empty(my_text_d.shape, dtype=torch.uint8, pin_memory=True); text_h.copy_(my_text_d)
-        reads_h = torch.empty(my_reads_d.shape, dtype=torch.uint8, pin_memory=True); reads_h.copy_(my_reads_d)
+        if gather_reads:
+            # 2d: the T ranks of a read group upload 1/T of the group's packed reads each and all-gather them inside the group
+            rbytes = my_reads_d.numel()
+            rb, re_, _ = matcher.text_share(rbytes, t_rank, T)
+            reads_h = torch.empty(re_ - rb, dtype=torch.uint8, pin_memory=True); reads_h.copy_(my_reads_d.view(-1)[rb:re_])
+            rbufs = {}
+        else:
+            reads_h = torch.empty(my_reads_d.shape, dtype=torch.uint8, pin_memory=True); reads_h.copy_(my_reads_d)
         out_h = (torch.empty(n_mine, dtype=torch.uint64, pin_memory=True), torch.empty(n_mine, dtype=torch.uint8, pin_memory=True),
                  torch.empty(n_mine, dtype=torch.uint8, pin_memory=True))
         def step_e2e():
+            text_in, reads_in = text_h, reads_h
             if gather_text:
-                return step(matcher.all_gather_text(text_h, pg_len, rank, world, dev, gbufs), reads_h, out_h)
-            return step(text_h, reads_h, out_h)
+                text_in = matcher.all_gather_text(text_h, pg_len, rank, world, dev, gbufs)
+                if args.shard == "2d":
+                    text_in = text_in[sb:sb + sl]
+            if gather_reads:
+                reads_in = matcher.all_gather_text(reads_h, rbytes, t_rank, T, dev, rbufs, group).view(my_reads_d.shape)
+            return step(text_in, reads_in, out_h)
         for _ in range(min(args.warmup, 2)):
             step_e2e()
         e2e_ms, _, res_h = timed(step_e2e, args.steps)
@@ -355,7 +368,7 @@ def ours(args):
         e2e = {"value": round(n_reads * args.steps / (e2e_ms * 1e-3), 1), "unit": UNIT,
                "h2d_bytes_per_step": int(text_h.numel() + reads_h.numel()), "d2h_bytes_per_step": int(n_mine * 10),
                "ms_per_step": round(e2e_ms / args.steps, 3),
-               "text_upload": "1/N per rank over PCIe + NCCL all-gather over NVLink" if gather_text else "whole text per rank"}
+               "upload": ("text: 1/N per rank over PCIe + NCCL all-gather over NVLink" + ("; reads: 1/T per rank of a read group + all-gather inside the group" if gather_reads else "")) if gather_text else "whole inputs per rank"}
     clocks = sampler.stop() if rank == 0 else None
 
     # roofline of the dominant kernel (scan): separate short run with per-kernel events

@@ -87,6 +87,8 @@ struct pgm_ctx {
     uint64_t n_slots = 0;
     uint32_t n_buckets = 0;
     uint32_t filter_words = 0;  // 0 = no filter
+    uint32_t filter_k = 2;      // bits per pattern in its filter word
+    int filter_k_force = 0;     // PGM_FILTER_K (sweeps)
 
     // phase
     uint32_t seed_len = 0, parts = 0, max_mm = 0, min_mm = 0, part_bits = 0;
@@ -199,6 +201,7 @@ pgm::TableView table_view(pgm_ctx *c) {
     tv.filter = c->filter_words ? c->filter.as<uint32_t>() : nullptr;
     tv.n_buckets = c->n_buckets;
     tv.filter_mask = c->filter_words ? c->filter_words - 1 : 0;
+    tv.filter_k = c->filter_k;
     return tv;
 }
 
@@ -482,6 +485,7 @@ int pgm_create(int device, pgm_ctx **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *t = getenv("PGM_TWO_STEP_BUILD")) ctx->two_step_build = atoi(t);   // 0 off, 1 auto, 2 always (tests)
+    if (const char *t = getenv("PGM_FILTER_K")) ctx->filter_k_force = atoi(t);
     if (const char *t = getenv("PGM_INSERT_PREFETCH")) ctx->insert_prefetch = atoi(t);
     if (const char *t = getenv("PGM_BLOCKED_SCAN")) ctx->blocked_scan = atoi(t);
     if (const char *t = getenv("PGM_REGION_MB")) ctx->region_mb = std::max(1, atoi(t));
@@ -736,8 +740,14 @@ int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t m
     ctx->part_bits = part_bits;
     CU(cudaMemsetAsync(ctx->buckets.p, 0xFF, nb64 * 32, ctx->stream));
     int fbits = ctx->filter_log2_bits;
-    if (fbits < 0) fbits = std::min(28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 8)));
+    // auto: 8 bits per pattern up to 2^28 bits (32 MB stays L2-resident next to the streaming traffic); pattern sets far
+    // beyond that get 2^29 bits (64 MB: still mostly resident) — a saturated filter sends every text window to the table
+    if (fbits < 0) fbits = std::min(n_patterns > (100ull << 20) ? 29 : 28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 8)));
     if (fbits > 0) {
+        // bits per pattern: k = 0.69 * filter bits / patterns minimises the false-positive rate (1..4, all in one word)
+        const double per = (double)(1ull << fbits) / (double)std::max<uint64_t>(n_patterns, 1);
+        ctx->filter_k = ctx->filter_k_force ? (uint32_t)std::min(4, std::max(1, ctx->filter_k_force))
+                                            : (uint32_t)std::min(4.0, std::max(1.0, 0.69 * per + 0.5));
         ctx->filter_words = 1u << (fbits - 5);
         const size_t fbytes = (size_t)1 << (fbits - 3);
         if ((rc = ensure(ctx, ctx->filter, fbytes))) return rc;

@@ -16,7 +16,7 @@
 //               bucket of its probe sequence that has room (so a lookup stops at the first bucket with
 //               an empty slot); only when PGM_WALK_CAP buckets in a row are full of the same key (hot
 //               seeds: poly-A, satellites) a pattern is chained behind a slot through next[].
-//   filter      2^f-bit blocked Bloom filter (2 bits in one word), sized to stay L2-resident.
+//   filter      2^f-bit blocked Bloom filter (1..4 bits in one word, by load), sized to stay L2-resident.
 //   per read    first_other_order (int64 MIN), same_pos_mask (int32 OR), same_pos_mm (uint8): only
 //               touched when a read that already has a match meets a better candidate (rule a-R).
 //
@@ -86,8 +86,17 @@ __host__ __device__ __forceinline__ uint32_t filter_hash(uint32_t P, uint32_t Q,
     x ^= x >> 16;
     return x;
 }
-__host__ __device__ __forceinline__ uint32_t filter_bits(uint32_t f) {
-    return (1u << (f >> 27)) | (1u << ((f >> 22) & 31u));
+// k bits of one filter word (k = 1..4, chosen on the host from the filter's bits per pattern: about 0.69 * bits / patterns
+// minimises the false-positive rate; a table far beyond the L2-resident filter's capacity wants k = 1)
+__host__ __device__ __forceinline__ uint32_t filter_bits(uint32_t f, uint32_t k) {
+    uint32_t m = 1u << (f >> 27);
+    if (k > 1) {
+        const uint32_t g = f * 0x9E3779B1u;
+        m |= 1u << (g >> 27);
+        if (k > 2) m |= 1u << ((g >> 22) & 31u);
+        if (k > 3) m |= 1u << ((g >> 17) & 31u);
+    }
+    return m;
 }
 
 // ------------------------------------------------------------------------------------------ parameters
@@ -99,6 +108,7 @@ struct TableView {
     uint32_t *filter;           // may be null
     uint32_t n_buckets;         // prime
     uint32_t filter_mask;       // #filter words - 1
+    uint32_t filter_k;          // bits per pattern in its filter word (1..4)
 };
 
 struct ReadsView {
@@ -594,7 +604,7 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
                     const uint32_t pat = (r << reads.part_bits) | j;
                     if (tab.filter) {
                         const uint32_t f = filter_hash(P, Q, R);
-                        atomicOr(tab.filter + (f & tab.filter_mask), filter_bits(f));
+                        atomicOr(tab.filter + (f & tab.filter_mask), filter_bits(f, tab.filter_k));
                     }
                     n_ins++;
                     if (n_regions) {
@@ -832,7 +842,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
                 uint32_t P, Q, R;
                 window_form<NCH>(sm.dl + r * ilv_mw, sm.dh + r * ilv_mw, q, p.tail_mask, P, Q, R);
                 const uint32_t f = filter_hash(P, Q, R);
-                const uint32_t fm = filter_bits(f);
+                const uint32_t fm = filter_bits(f, p.tab.filter_k);
                 const uint32_t fw = !p.tab.filter ? 0xFFFFFFFFu : fhints ? ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep)
                                                                          : __ldg(p.tab.filter + (f & p.tab.filter_mask));
                 const bool hit = pos < PGM_TILE_POS && pos >= vb && pos < ve && (fw & fm) == fm;
@@ -858,7 +868,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_
                     window_form<NCH>(slo, shi, pos0 + 32 * u + lane, p.tail_mask, P, Q, R);
                     const uint32_t f = filter_hash(P, Q, R);
                     fi[u] = f & p.tab.filter_mask;
-                    fm[u] = filter_bits(f);
+                    fm[u] = filter_bits(f, p.tab.filter_k);
                 }
                 uint32_t fw[U];
 #pragma unroll
