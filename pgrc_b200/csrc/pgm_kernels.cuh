@@ -47,6 +47,9 @@
 #define PGM_TAIL_WORDS (PGM_TILE_WORDS + 64)
 #define PGM_SCAN_THREADS 256
 #define PGM_SCAN_WARPS (PGM_SCAN_THREADS / 32)
+#ifndef PGM_SCAN_MIN_CTAS
+#define PGM_SCAN_MIN_CTAS 4                 // resident CTAs per SM the scan kernel is compiled for (register budget)
+#endif
 #define PGM_WORDS_PER_WARP (PGM_TILE_WORDS / PGM_SCAN_WARPS)
 #define PGM_WQ_CAP 320                     // per-warp candidate queue entries
 #define PGM_WQ_ROUND 128                   // most entries one probe round can add (32 lanes x 4 slots)
@@ -760,7 +763,7 @@ __device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, cons
 // strings in shared memory (phase r, index q <-> tile position r + q*s): in phase space the window is contiguous again and
 // stage A1 / the rehash of A2 run unchanged on it; verification (stage B) uses the original planes.
 template <int NCH, bool FAST, int MODE, bool ILV>
-__global__ void __launch_bounds__(PGM_SCAN_THREADS, 4) scan_kernel(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kernel(const __grid_constant__ ScanParams p) {
     __shared__ __align__(128) ScanShared<ILV> sm;
     if (MODE == 0 && p.only_if != nullptr && *p.only_if == 0) {
         // the pipeline finished without a queue overflow: nothing to redo, its staged counters become final
