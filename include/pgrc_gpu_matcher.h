@@ -154,6 +154,24 @@ int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode);
  * stats may be NULL.  Synchronizes the context's stream. */
 int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats);
 
+/* pgm_get_mismatches replaces the per-read work of AbstractReadsApproxMatcher::updateEntry
+ * (ReadsMatchers.cpp:555-566: getRead + reverseComplementInPlace + fillEntryWithMismatches,
+ * :40-52), i.e. what the reference's export recomputes on the host for every matched read: the
+ * list of its mismatches against the pseudogenome at readMatchPos, the read taken
+ * reverse-complemented when readMatchRC is set, in ascending read offset.
+ *   out_offsets[n_reads + 1]  prefix sums of readMismatchesCount (unmatched reads count 0):
+ *                             the entries of read i are [out_offsets[i], out_offsets[i+1])
+ *   out_pos[k]                offset in the (possibly reverse-complemented) read
+ *   out_syms[k]               pseudogenome symbol : 2 bits | read symbol : 3 bits << 2, codes
+ *                             A C G T = 0..3, N = 4 (the caller maps them to mismatch2CxtCode,
+ *                             helper.cpp:358; fillEntryWithReversedMismatches, :54-66, is this list
+ *                             walked backwards with complemented symbols and offsets L-1-off)
+ * `capacity` = entries out_pos / out_syms can hold; the number needed is the sum of
+ * k * per_mm[k] (pgm_stats) and is returned in *total (call with null arrays to query it).
+ * Host or device pointers.  Needs the whole text on this GPU; call after pgm_get_results. */
+int pgm_get_mismatches(pgm_ctx *ctx, uint64_t *out_offsets, uint8_t *out_pos, uint8_t *out_syms,
+                       uint64_t capacity, uint64_t *total);
+
 /* ---- the whole stage on one GPU ---------------------------------------------------------
  * pgm_map_reads replaces the matching part of PgTools::mapReadsIntoPg
  * (ReadsMatchers.cpp:693-783) for matching modes 'd'/'D' (DefaultReadsApproxMatcher) and 'i'/'I'
@@ -177,6 +195,7 @@ uint64_t pgm_kernel_launches(const pgm_ctx *ctx);
 enum { PGM_K_PACK_TEXT = 0, PGM_K_RC_TEXT, PGM_K_UNPACK_READS, PGM_K_INIT_STATE, PGM_K_BUILD_TABLE,
        PGM_K_SCAN, PGM_K_RESOLVE, PGM_K_FINALIZE, PGM_K_ACCUM,
        PGM_K_SCAN_FILTER, PGM_K_SCAN_PROBE, PGM_K_SCAN_VERIFY, /* the three stages of the L2-blocked scan pipeline */
+       PGM_K_MISMATCHES,
        PGM_K_COUNT };
 typedef struct pgm_timings {
     double ms[PGM_K_COUNT];

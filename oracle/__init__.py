@@ -75,6 +75,10 @@ def _oracle():
                                       ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                       ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char, ctypes.c_char, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.pgo_mismatch_lists.restype = ctypes.c_int
+        lib.pgo_mismatch_lists.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
+                                           ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _oracle_lib = lib
     return _oracle_lib
 
@@ -94,6 +98,13 @@ def _ref():
                                         ctypes.c_void_p]
         lib.pgref_pack_reads.restype = ctypes.c_int
         lib.pgref_pack_reads.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+        lib.pgref_mismatch_lists.restype = ctypes.c_int
+        lib.pgref_mismatch_lists.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint32,
+                                             ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char, ctypes.c_char,
+                                             ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _ref_lib = lib
     return _ref_lib
 
@@ -168,3 +179,51 @@ def ref_map_reads(text: np.ndarray, lq_ascii: np.ndarray, n_ascii: np.ndarray | 
     if not np.array_equal(buf[:-1], np.asarray(text, dtype=np.uint8)):
         raise RuntimeError("reference left the text modified")
     return MatchResult(pos, rc, mm, int(st[0]), int(st[1]), int(st[2]), st[3:].copy(), seconds=secs.value)
+
+
+_SYM_CODE = np.full(256, 255, np.uint8)
+_SYM_CODE[[ord(c) for c in "ACGTN"]] = np.arange(5, dtype=np.uint8)
+
+
+def oracle_mismatch_lists(text, lq_packed, n_packed, read_len: int, pos, rc, mm, variant: int = 0):
+    """Mismatch lists of the export step (pgo_mismatch_lists; AbstractReadsApproxMatcher::updateEntry,
+    ReadsMatchers.cpp:548-558): (offsets uint64[n+1], off uint8[], pg_sym uint8[], read_sym uint8[]), symbols as codes
+    A C G T N = 0..4.  variant 0: forward fill for every read (the pgm_get_mismatches contract); 1 / 2: updateEntry with
+    revComplPairFile false / true."""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    lq = np.ascontiguousarray(lq_packed, dtype=np.uint8)
+    n_lq = lq.shape[0] if lq.size else 0
+    nn = np.ascontiguousarray(n_packed, dtype=np.uint8) if n_packed is not None and len(n_packed) else np.zeros((0, 1), np.uint8)
+    n_n = nn.shape[0] if nn.size else 0
+    pos = np.ascontiguousarray(pos, np.uint64); rc = np.ascontiguousarray(rc, np.uint8); mm = np.ascontiguousarray(mm, np.uint8)
+    total = int(mm[mm != 255].astype(np.int64).sum())
+    off = np.empty(n_lq + n_n + 1, np.uint64)
+    o, pg, rd = (np.empty(max(total, 1), np.uint8) for _ in range(3))
+    r = _oracle().pgo_mismatch_lists(text.ctypes.data, text.size, lq.ctypes.data, n_lq, nn.ctypes.data, n_n, read_len,
+                                     pos.ctypes.data, rc.ctypes.data, mm.ctypes.data, variant,
+                                     off.ctypes.data, o.ctypes.data, pg.ctypes.data, rd.ctypes.data)
+    if r != 0:
+        raise RuntimeError(f"pgo_mismatch_lists failed ({r})")
+    return off, o[:total], _SYM_CODE[pg[:total]], _SYM_CODE[rd[:total]]
+
+
+def ref_mismatch_lists(text, lq_ascii, n_ascii, read_len: int, rev_compl_pair_file: bool = False, seed: int = 38,
+                       min_chars_per_mismatch: int = 3, mode: str = "d", pre_seed: int = 0, pre_mode: str = "d", rev_compl: bool = True):
+    """The reference's own export step (updateEntry through the harness): returns (MatchResult, offsets, off, pg_sym, read_sym)."""
+    buf = np.zeros(np.asarray(text).size + 1, np.uint8)
+    buf[:-1] = np.asarray(text, dtype=np.uint8)
+    lq = _ascii2d(lq_ascii, read_len)
+    nn = _ascii2d(n_ascii, read_len) if n_ascii is not None and len(n_ascii) else np.zeros((0, read_len), np.uint8)
+    n = lq.shape[0] + nn.shape[0]
+    pos = np.empty(n, np.uint64); rc = np.empty(n, np.uint8); mm = np.empty(n, np.uint8)
+    off = np.empty(n + 1, np.uint64)
+    cap = n * 256
+    o, pg, rd = (np.empty(cap, np.uint8) for _ in range(3))
+    r = _ref().pgref_mismatch_lists(buf.ctypes.data, buf.size - 1, lq.ctypes.data, lq.shape[0], nn.ctypes.data, nn.shape[0],
+                                    read_len, pre_seed, seed, min_chars_per_mismatch, _mode(pre_mode), _mode(mode),
+                                    int(rev_compl), int(rev_compl_pair_file), pos.ctypes.data, rc.ctypes.data, mm.ctypes.data,
+                                    off.ctypes.data, o.ctypes.data, pg.ctypes.data, rd.ctypes.data)
+    if r != 0:
+        raise RuntimeError(f"pgref_mismatch_lists failed ({r})")
+    t = int(off[-1])
+    return MatchResult(pos, rc, mm, int((mm != 255).sum()), 0, 0, np.bincount(mm, minlength=256).astype(np.uint64)), off, o[:t], _SYM_CODE[pg[:t]], _SYM_CODE[rd[:t]]

@@ -522,3 +522,52 @@ int pgo_map_reads(const char *text, uint64_t text_len,
     free(m.cur_read); free(m.seed_buf); free(m.win_buf);
     return rcode;
 }
+
+/* ------------------------------------------------------------------ mismatch lists of the export (a-next, §8(f) rank 2)
+ * AbstractReadsApproxMatcher::updateEntry (ReadsMatchers.cpp:548-558) with fillEntryWithMismatches (:40-52) and
+ * fillEntryWithReversedMismatches (:54-66): per matched read, the (offset, pseudogenome symbol, read symbol) triples the
+ * export hands to mismatch2CxtCode / addMismatch.
+ *   variant 0: the forward fill for every read (the read reverse-complemented when rc is set) — the contract of
+ *              pgm_get_mismatches, from which the shim derives the other two on the host;
+ *   variant 1: updateEntry(entry, i, revComplPairFile = false): reversed fill iff rc;
+ *   variant 2: updateEntry(entry, i, revComplPairFile = true):  reversed fill iff rc != (idx % 2), idx = i. */
+static char comp_sym(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c; }
+
+int pgo_mismatch_lists(const char *text, uint64_t text_len, const uint8_t *lq_packed, uint32_t n_lq,
+                       const uint8_t *n_packed, uint32_t n_n, uint32_t read_len,
+                       const uint64_t *pos, const uint8_t *rc, const uint8_t *mm, int variant,
+                       uint64_t *out_offsets, uint8_t *out_off, char *out_pg, char *out_read) {
+    reads_view rs = { lq_packed, n_lq, (read_len + 3) / 4, n_packed, n_n, (read_len + 2) / 3, read_len };
+    const uint32_t n = n_lq + n_n;
+    char *cur = (char *)malloc(read_len + 1);
+    if (!cur) return -2;
+    uint64_t at = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        out_offsets[i] = at;
+        if (mm[i] == PGO_NOT_MATCHED_COUNT || pos[i] == PGO_NOT_MATCHED_POSITION) continue;
+        if (pos[i] + read_len > text_len) { free(cur); return -1; }
+        get_read(&rs, i, cur);                                              /* readsSet->getRead */
+        if (rc[i])                                                          /* reverseComplementInPlace(currentRead) */
+            for (uint32_t a = 0, b = read_len - 1; a <= b && b < read_len; a++, b--) {
+                char x = comp_sym(cur[a]), y = comp_sym(cur[b]);
+                cur[a] = y; cur[b] = x;
+            }
+        const char *pg = text + pos[i];
+        const int reversed = variant == 0 ? 0 : variant == 1 ? (rc[i] != 0) : ((rc[i] != 0) != (int)(i % 2));
+        uint8_t count = 0;
+        if (!reversed) {
+            for (uint64_t p = 0; count < mm[i] && p < read_len; p++)
+                if (cur[p] != pg[p]) { out_off[at] = (uint8_t)p; out_pg[at] = pg[p]; out_read[at] = cur[p]; at++; count++; }
+        } else {
+            for (uint64_t p = read_len; count < mm[i] && p-- > 0;)
+                if (cur[p] != pg[p]) {
+                    out_off[at] = (uint8_t)(read_len - p - 1); out_pg[at] = comp_sym(pg[p]); out_read[at] = comp_sym(cur[p]);
+                    at++; count++;
+                }
+        }
+        if (count != mm[i]) { free(cur); return -3; }                       /* mm is not the Hamming distance at pos */
+    }
+    out_offsets[n] = at;
+    free(cur);
+    return 0;
+}

@@ -41,6 +41,7 @@ struct Probe : M {
     uint64_t better() { return this->betterMatchCount; }
     uint64_t falses() { return this->falseMatchCount; }
     uint_reads_cnt_max* hist() { return this->matchedCountPerMismatches; }
+    void fill(DefaultReadsListEntry& e, uint_reads_cnt_max idx, bool revComplPairFile) { this->updateEntry(e, idx, revComplPairFile); }
 };
 
 struct ExactProbe : DefaultReadsExactMatcher {
@@ -97,6 +98,36 @@ AbstractReadsApproxMatcher* newApprox(char mode, char* pg, uint64_t pgLen, bool 
     return nullptr;
 }
 
+// The reference's own export step for one read (exportMatchesInPgOrder, ReadsMatchers.cpp:583-588): entry at the match
+// position, then updateEntry (:548-558) fills the mismatches.  Dumps (offset, actual symbol, mismatch symbol).
+struct MisOut { uint64_t* offsets; uint8_t* off; char* pg; char* read; int rev_pair; };
+
+template <class P>
+void dumpMismatches(P* m, uint32_t n, const MisOut& o) {
+    uint64_t at = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        o.offsets[i] = at;
+        if (m->pos()[i] == DefaultReadsMatcher::NOT_MATCHED_POSITION) continue;
+        DefaultReadsListEntry entry(0);
+        entry.advanceEntryByPosition(m->pos()[i], i, m->rc()[i]);
+        m->fill(entry, i, o.rev_pair != 0);
+        for (uint8_t k = 0; k < entry.mismatchesCount; k++, at++) {
+            o.off[at] = (uint8_t)entry.mismatchOffset[k];
+            o.pg[at] = PgHelpers::value2symbol(PgHelpers::cxtCode2ActualValue(entry.mismatchCode[k]));
+            o.read[at] = PgHelpers::value2symbol(PgHelpers::cxtCode2MismatchValue(entry.mismatchCode[k]));
+        }
+    }
+    o.offsets[n] = at;
+}
+
+void dumpMismatchesAny(AbstractReadsApproxMatcher* m, char mode, uint32_t n, const MisOut& o) {
+    switch (tolower(mode)) {
+        case 'd': dumpMismatches(static_cast<Probe<DefaultReadsApproxMatcher>*>(m), n, o); break;
+        case 'i': dumpMismatches(static_cast<Probe<InterleavedReadsApproxMatcher>*>(m), n, o); break;
+        case 'c': dumpMismatches(static_cast<Probe<CopMEMReadsApproxMatcher>*>(m), n, o); break;
+    }
+}
+
 void dumpAny(AbstractReadsApproxMatcher* m, char mode, uint32_t n, uint64_t* p, uint8_t* r, uint8_t* c, uint64_t* st) {
     switch (tolower(mode)) {
         case 'd': dumpApprox(static_cast<Probe<DefaultReadsApproxMatcher>*>(m), n, p, r, c, st); break;
@@ -105,9 +136,40 @@ void dumpAny(AbstractReadsApproxMatcher* m, char mode, uint32_t n, uint64_t* p, 
     }
 }
 
+int runReference(char* text, uint64_t text_len, const char* lq_reads, uint32_t n_lq, const char* n_reads, uint32_t n_n,
+                 uint32_t read_len, uint32_t pre_seed, uint32_t seed, uint32_t min_chars_per_mismatch, char pre_mode, char mode,
+                 int rev_compl, int threads, uint64_t* out_pos, uint8_t* out_rc, uint8_t* out_mm, uint64_t* out_stats,
+                 double* out_seconds, const MisOut* mis);
+
 }  // namespace
 
 extern "C" {
+
+int pgref_map_reads(char* text, uint64_t text_len, const char* lq_reads, uint32_t n_lq, const char* n_reads, uint32_t n_n,
+                    uint32_t read_len, uint32_t pre_seed, uint32_t seed, uint32_t min_chars_per_mismatch, char pre_mode, char mode,
+                    int rev_compl, int threads, uint64_t* out_pos, uint8_t* out_rc, uint8_t* out_mm, uint64_t* out_stats,
+                    double* out_seconds) {
+    return runReference(text, text_len, lq_reads, n_lq, n_reads, n_n, read_len, pre_seed, seed, min_chars_per_mismatch, pre_mode,
+                        mode, rev_compl, threads, out_pos, out_rc, out_mm, out_stats, out_seconds, nullptr);
+}
+
+// pgref_map_reads + the mismatch lists the reference's export step builds for every matched read (updateEntry,
+// ReadsMatchers.cpp:548-558, called as exportMatchesInPgOrder does, :583-588, with entry.idx = the read index):
+// out_offsets[n+1], then per mismatch its offset, the actual (pseudogenome) symbol and the mismatch (read) symbol as
+// decoded from the reference's context code.  The last matcher must be an approximate one.
+int pgref_mismatch_lists(char* text, uint64_t text_len, const char* lq_reads, uint32_t n_lq, const char* n_reads, uint32_t n_n,
+                         uint32_t read_len, uint32_t pre_seed, uint32_t seed, uint32_t min_chars_per_mismatch, char pre_mode,
+                         char mode, int rev_compl, int rev_compl_pair_file, uint64_t* out_pos, uint8_t* out_rc, uint8_t* out_mm,
+                         uint64_t* out_offsets, uint8_t* out_off, char* out_pg, char* out_read) {
+    uint64_t stats[259];
+    MisOut mis{out_offsets, out_off, out_pg, out_read, rev_compl_pair_file};
+    return runReference(text, text_len, lq_reads, n_lq, n_reads, n_n, read_len, pre_seed, seed, min_chars_per_mismatch, pre_mode,
+                        mode, rev_compl, 1, out_pos, out_rc, out_mm, stats, nullptr, &mis);
+}
+
+}  // extern "C"
+
+namespace {
 
 // Runs the reference's stage-4 matching exactly as mapReadsIntoPg would configure it
 // (ReadsMatchers.cpp:699-779) and returns the three archive-visible per-read arrays.
@@ -122,14 +184,14 @@ extern "C" {
 //   out_seconds: wall time of matchConstantLengthReads (+ continuation), i.e. table build
 //                + forward pass + RC pass, export excluded
 // Returns 0, or -1 on bad arguments.
-int pgref_map_reads(char* text, uint64_t text_len,
-                    const char* lq_reads, uint32_t n_lq,
-                    const char* n_reads, uint32_t n_n,
-                    uint32_t read_len, uint32_t pre_seed, uint32_t seed,
-                    uint32_t min_chars_per_mismatch, char pre_mode, char mode,
-                    int rev_compl, int threads,
-                    uint64_t* out_pos, uint8_t* out_rc, uint8_t* out_mm,
-                    uint64_t* out_stats, double* out_seconds) {
+int runReference(char* text, uint64_t text_len,
+                 const char* lq_reads, uint32_t n_lq,
+                 const char* n_reads, uint32_t n_n,
+                 uint32_t read_len, uint32_t pre_seed, uint32_t seed,
+                 uint32_t min_chars_per_mismatch, char pre_mode, char mode,
+                 int rev_compl, int threads,
+                 uint64_t* out_pos, uint8_t* out_rc, uint8_t* out_mm,
+                 uint64_t* out_stats, double* out_seconds, const MisOut* mis) {
     if (!text || read_len == 0 || read_len > 255 || seed == 0 || min_chars_per_mismatch == 0) return -1;
     CoutSilencer quiet;
     if (threads > 0) { omp_set_num_threads(threads); PgHelpers::numberOfThreads = threads; }
@@ -196,10 +258,16 @@ int pgref_map_reads(char* text, uint64_t text_len,
         out_stats[0] = e->matched(); out_stats[1] = e->better(); out_stats[2] = e->falses();
     } else {
         dumpAny(static_cast<AbstractReadsApproxMatcher*>(matcher), lastMode, n, out_pos, out_rc, out_mm, out_stats);
+        if (mis) dumpMismatchesAny(static_cast<AbstractReadsApproxMatcher*>(matcher), lastMode, n, *mis);
     }
+    if (mis && firstIsExact) { delete matcher; return -1; }
     delete matcher;
     return 0;
 }
+
+}  // namespace
+
+extern "C" {
 
 // Packs ASCII reads with the reference's own SymbolsPackingFacility (layout pin for a11).
 // symbols = "ACGT" (4/byte) or "ACGNT" (3/byte). Returns bytes per read.

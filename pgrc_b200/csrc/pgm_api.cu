@@ -82,6 +82,7 @@ struct pgm_ctx {
     // table
     DevBuf buckets, next, filter, bq_entries, bq_counters;
     DevBuf sq_pos, sq_cand, sq_counters;   // queues of the L2-blocked scan pipeline (pgm_blocked.cuh)
+    DevBuf mis_sums, mis_offsets, mis_pos, mis_syms;   // mismatch lists (pgm_get_mismatches)
     uint32_t bq_cap = 0, bq_region_bits = 0;
     bool bq_pending = false;    // region queues hold patterns that build_insert_kernel has not inserted yet
     uint64_t n_slots = 0;
@@ -528,7 +529,8 @@ void pgm_destroy(pgm_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->f_lo, &ctx->f_hi, &ctx->r_lo, &ctx->r_hi, &ctx->ascii_stage, &ctx->packed_stage,
                       &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
                       &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter, &ctx->bq_entries, &ctx->bq_counters,
-                      &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
+                      &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->mis_sums, &ctx->mis_offsets, &ctx->mis_pos, &ctx->mis_syms,
+                      &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
     for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (cudaEvent_t e : ctx->ev_free) cudaEventDestroy(e);
@@ -1009,6 +1011,53 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
         stats->table_slots = ctx->n_slots;
         stats->candidates = cnt[0]; stats->verified = cnt[1]; stats->accepted = cnt[2]; stats->filter_positives = cnt[3];
     }
+    return PGM_OK;
+}
+
+int pgm_get_mismatches(pgm_ctx *ctx, uint64_t *out_offsets, uint8_t *out_pos, uint8_t *out_syms, uint64_t capacity, uint64_t *total) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->has_reads || !ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_get_mismatches: set the text and the reads first");
+    if (ctx->slice_begin != 0 || ctx->slice_len != ctx->pg_len)
+        return fail(ctx, PGM_ERR_STATE, "pgm_get_mismatches: needs the whole text on this GPU (not a text shard)");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload_reads(ctx, false)) || (rc = finish_text_upload(ctx))) return rc;
+    const uint32_t n = ctx->n_reads();
+    const uint32_t n_blocks = grid_for(std::max<uint32_t>(n, 1), PGM_MIS_THREADS);
+    if ((rc = ensure(ctx, ctx->mis_sums, ((size_t)n_blocks + 1) * 8)) || (rc = ensure(ctx, ctx->mis_offsets, ((size_t)n + 1) * 8))) return rc;
+    unsigned long long *sums = ctx->mis_sums.as<unsigned long long>();
+    unsigned long long tot = 0;
+    if (n) {
+        KLAUNCH(PGM_K_MISMATCHES, "mismatch_count_kernel", pgm::mismatch_count_kernel<<<n_blocks, PGM_MIS_THREADS, 0, ctx->stream>>>(reads_view(ctx), n, sums));
+        KLAUNCH(PGM_K_MISMATCHES, "mismatch_scan_kernel", pgm::mismatch_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sums, n_blocks, sums + n_blocks));
+        CU(cudaMemcpyAsync(&tot, sums + n_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    } else {
+        CU(cudaMemsetAsync(ctx->mis_offsets.p, 0, 8, ctx->stream));
+    }
+    if (total) *total = tot;
+    if (n && (out_pos || out_syms || out_offsets)) {
+        if ((out_pos || out_syms) && capacity < tot)
+            return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_get_mismatches: capacity is smaller than the number of mismatches (sum of k * per_mm[k])");
+        if ((rc = ensure(ctx, ctx->mis_pos, std::max<size_t>(tot, 1))) || (rc = ensure(ctx, ctx->mis_syms, std::max<size_t>(tot, 1)))) return rc;
+        pgm::MismatchParams mp;
+        memset(&mp, 0, sizeof mp);
+        mp.flo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS; mp.fhi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
+        mp.rlo = ctx->r_lo.as<uint32_t>() + PGM_PAD_WORDS; mp.rhi = ctx->r_hi.as<uint32_t>() + PGM_PAD_WORDS;
+        mp.pg_len = ctx->pg_len; mp.reads = reads_view(ctx); mp.n_reads = n;
+        mp.block_base = sums; mp.out_offsets = ctx->mis_offsets.as<unsigned long long>();
+        mp.out_pos = ctx->mis_pos.as<uint8_t>(); mp.out_syms = ctx->mis_syms.as<uint8_t>();
+        mp.capacity = tot; mp.err = ctx->err_flag.as<int>();
+        KLAUNCH(PGM_K_MISMATCHES, "mismatch_emit_kernel", pgm::mismatch_emit_kernel<<<n_blocks, PGM_MIS_THREADS, 0, ctx->stream>>>(mp));
+    }
+    if (out_offsets) CU(cudaMemcpyAsync(out_offsets, ctx->mis_offsets.p, ((size_t)n + 1) * 8, cudaMemcpyDefault, ctx->stream));
+    if (out_pos && tot) CU(cudaMemcpyAsync(out_pos, ctx->mis_pos.p, tot, cudaMemcpyDefault, ctx->stream));
+    if (out_syms && tot) CU(cudaMemcpyAsync(out_syms, ctx->mis_syms.p, tot, cudaMemcpyDefault, ctx->stream));
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, ctx->err_flag.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (bad == 1) return fail(ctx, PGM_ERR_BAD_SYMBOL, "pseudogenome text contains a symbol outside ACGT (2-bit text planes cannot hold it)");
+    if (bad) return fail(ctx, PGM_ERR_CUDA, "pgm_get_mismatches: a mismatch list does not have readMismatchesCount entries (internal error)");
     return PGM_OK;
 }
 

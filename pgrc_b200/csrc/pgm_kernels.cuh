@@ -1289,6 +1289,158 @@ __global__ void finalize_kernel(ReadsView reads, uint32_t n_reads, unsigned long
     if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------------------ mismatch lists (export)
+// What AbstractReadsApproxMatcher::updateEntry recomputes on the host for every matched read (ReadsMatchers.cpp:555-566:
+// getRead + reverseComplementInPlace + fillEntryWithMismatches, :40-52): the read's mismatches against the pseudogenome at
+// readMatchPos, the read taken reverse-complemented when readMatchRC, in ascending offset.  Three small kernels: per-block
+// sums of the mismatch counts, an exclusive scan of those sums, and the emit pass (thread per read: XOR of the record's
+// planes with the text window; an RC match is compared on the reverse-complement planes, where the read lies as it is
+// stored, and its offsets / symbols are mapped back — offset L-1-q, complemented symbols).
+#define PGM_MIS_THREADS 256
+__global__ void __launch_bounds__(PGM_MIS_THREADS) mismatch_count_kernel(ReadsView reads, uint32_t n_reads, unsigned long long *block_sums) {
+    __shared__ unsigned int s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const uint32_t r = blockIdx.x * PGM_MIS_THREADS + threadIdx.x;
+    unsigned int c = 0;
+    if (r < n_reads) {
+        uint32_t stride16; bool is_n;
+        const uint2 h = __ldcg(reinterpret_cast<const uint2 *>(record_of(reads, r, stride16, is_n)));
+        c = h.y >> 24;
+        if (c == 255u) c = 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(PGM_FULL, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_sum, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s_sum;
+}
+
+// in-place exclusive scan of block_sums by one block; *total = the sum
+__global__ void __launch_bounds__(1024) mismatch_scan_kernel(unsigned long long *block_sums, uint32_t n_blocks, unsigned long long *total) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const uint32_t i = b0 + t;
+        const unsigned long long v = i < n_blocks ? block_sums[i] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(PGM_FULL, x, o);
+            if (lane >= (uint32_t)o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(PGM_FULL, w, o);
+                if (lane >= (uint32_t)o) w += y;
+            }
+            s_warp[lane] = w;                                   // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long before = s_carry + (warp ? s_warp[warp - 1] : 0ull) + (x - v);
+        if (i < n_blocks) block_sums[i] = before;
+        __syncthreads();
+        if (t == 1023) s_carry = before + v;
+        __syncthreads();
+    }
+    if (t == 0) *total = s_carry;
+}
+
+struct MismatchParams {
+    const uint32_t *flo, *fhi, *rlo, *rhi;   // forward / reverse-complement planes of the WHOLE text, origin at word 0
+    uint64_t pg_len;
+    ReadsView reads;
+    uint32_t n_reads;
+    const unsigned long long *block_base;     // exclusive prefix of the per-block counts
+    unsigned long long *out_offsets;          // n_reads + 1
+    uint8_t *out_pos, *out_syms;              // out_syms = pgSymbol:2 | readSymbol:3 << 2 (A C G T = 0..3, N = 4)
+    unsigned long long capacity;
+    int *err;                                 // set when a list does not have readMismatchesCount entries (internal error)
+};
+
+__global__ void __launch_bounds__(PGM_MIS_THREADS) mismatch_emit_kernel(const __grid_constant__ MismatchParams p) {
+    __shared__ unsigned int s_warp[PGM_MIS_THREADS / 32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t r = blockIdx.x * PGM_MIS_THREADS + t;
+    const uint32_t L = p.reads.read_len, W = p.reads.W;
+    uint32_t c = 0, stride16 = 4;
+    bool is_n = false, rc = false;
+    uint64_t pos = 0;
+    const uint4 *rec = nullptr;
+    if (r < p.n_reads) {
+        rec = record_of(p.reads, r, stride16, is_n);
+        const uint2 h = __ldcg(reinterpret_cast<const uint2 *>(rec));
+        const unsigned long long st = ((unsigned long long)h.y << 32) | h.x;
+        c = (uint32_t)(st >> 56);
+        rc = ((st >> 55) & 1) != 0;
+        pos = st & PGM_POS_MASK;
+        if (c == 255u) c = 0;
+    }
+    // exclusive scan of c within the block
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(PGM_FULL, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t w = 0; w < warp; w++) wbase += s_warp[w];
+    unsigned long long at = p.block_base[blockIdx.x] + wbase + (x - c);
+    if (r >= p.n_reads) return;
+    p.out_offsets[r] = at;
+    if (r == p.n_reads - 1) p.out_offsets[p.n_reads] = at + c;
+    if (c == 0) return;
+    const uint64_t a = rc ? p.pg_len - pos - L : pos;          // where the stored read lies on this strand's planes
+    const uint32_t *tlo = rc ? p.rlo : p.flo, *thi = rc ? p.rhi : p.fhi;
+    const uint64_t wi = a >> 5;
+    const uint32_t ts = (uint32_t)(a & 31);
+    uint32_t emitted = 0;
+    for (uint32_t gi = 0; gi < W; gi++) {
+        const uint32_t g = rc ? W - 1 - gi : gi;               // ascending offsets of the reverse-complemented read = descending q
+        const uint32_t tl = __funnelshift_r(__ldg(tlo + wi + g), __ldg(tlo + wi + g + 1), ts);
+        const uint32_t th = __funnelshift_r(__ldg(thi + wi + g), __ldg(thi + wi + g + 1), ts);
+        uint32_t rl, rh, nm = 0;
+        if (is_n) {
+            const uint4 v = __ldcg(rec + 1 + g);
+            rl = v.x; rh = v.y; nm = v.z;
+        } else {
+            const uint4 v = __ldcg(rec + 1 + (g >> 1));
+            rl = (g & 1) ? v.z : v.x; rh = (g & 1) ? v.w : v.y;
+        }
+        uint32_t diff = (rl ^ tl) | (rh ^ th) | nm;
+        const uint32_t rem = L - 32 * g;
+        if (rem < 32) diff &= (1u << rem) - 1u;
+        while (diff) {
+            const uint32_t b = rc ? 31u - (uint32_t)__clz(diff) : (uint32_t)__ffs(diff) - 1u;
+            diff &= ~(1u << b);
+            const uint32_t q = 32 * g + b;
+            uint32_t pg_sym = ((tl >> b) & 1u) | (((th >> b) & 1u) << 1);
+            uint32_t rd_sym = ((nm >> b) & 1u) ? 4u : (((rl >> b) & 1u) | (((rh >> b) & 1u) << 1));
+            uint32_t off = q;
+            if (rc) {                                           // back to the reverse-complemented read on the forward text
+                off = L - 1 - q;
+                pg_sym = 3u - pg_sym;
+                if (rd_sym != 4u) rd_sym = 3u - rd_sym;
+            }
+            if (at + emitted < p.capacity) {
+                p.out_pos[at + emitted] = (uint8_t)off;
+                p.out_syms[at + emitted] = (uint8_t)(pg_sym | (rd_sym << 2));
+            }
+            emitted++;
+        }
+    }
+    if (emitted != c) atomicExch(p.err, 2);
+}
+
 // Multi-GPU exchange: the per-read keys live inside the records; these two kernels copy them to / from a
 // contiguous array that the caller all-reduces (MIN) across the text shards.
 __global__ void export_keys_kernel(ReadsView reads, uint32_t n_reads, long long *__restrict__ keys) {

@@ -143,6 +143,15 @@ namespace PgTools {
             for (int k = 0; k <= NOT_MATCHED_COUNT; k++) matchedCountPerMismatches[k] = (uint_reads_cnt_max) st.per_mm[k];
     }
 
+    void GpuMatcherSession::fetchMismatches(vector<uint64_t> &offsets, vector<uint8_t> &pos, vector<uint8_t> &syms) {
+        uint64_t total = 0;
+        check(pgm_get_mismatches(ctx, nullptr, nullptr, nullptr, 0, &total), ctx, "pgm_get_mismatches");
+        offsets.resize((size_t) readsCount + 1);
+        pos.resize(total + 1);
+        syms.resize(total + 1);
+        check(pgm_get_mismatches(ctx, offsets.data(), pos.data(), syms.data(), total, &total), ctx, "pgm_get_mismatches");
+    }
+
     // ------------------------------------------------------------------------------------------ exact path
     GpuReadsExactMatcher::GpuReadsExactMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
                                                ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength)
@@ -193,6 +202,44 @@ namespace PgTools {
         if (revCompMode == revComplPg)                                             // last pass of this matcher
             session->fetch(readMatchPos, readMatchRC, &readMismatchesCount, matchedReadsCount, matchedCountPerMismatches);
         printApproxMatchingStats();
+    }
+
+    void GpuReadsApproxMatcher::initEntryUpdating() {                              // replaces ReadsMatchers.cpp:546
+        const char *env = getenv("PGRC_GPU_EXPORT");
+        deviceLists = !(env && strcmp(env, "0") == 0);
+        if (deviceLists) {
+            time_checkpoint();
+            session->fetchMismatches(misOffsets, misPos, misSyms);
+            *logout << "... mismatch lists of " << matchedReadsCount << " reads (" << misOffsets.back() << " mismatches) from the GPU in "
+                    << time_millis() << " msec. " << endl;
+        }
+    }
+
+    void GpuReadsApproxMatcher::updateEntry(DefaultReadsListEntry &entry, uint_reads_cnt_max matchIdx, bool revComplPairFile) {
+        if (!deviceLists) {                                                        // the reference's host code, unchanged
+            AbstractReadsApproxMatcher::updateEntry(entry, matchIdx, revComplPairFile);
+            return;
+        }
+        // replaces ReadsMatchers.cpp:548-558: the device list is the forward fill (fillEntryWithMismatches, :40-52) of the
+        // read as it lies on the pseudogenome; fillEntryWithReversedMismatches (:54-66) is the same list walked backwards
+        // with complemented symbols and mirrored offsets
+        static const char SYM[5] = {'A', 'C', 'G', 'T', 'N'};
+        const uint64_t b = misOffsets[matchIdx], e = misOffsets[matchIdx + 1];
+        const bool reversed = revComplPairFile ? (readMatchRC[matchIdx] != (bool) (entry.idx % 2)) : (bool) readMatchRC[matchIdx];
+        if (!reversed) {
+            for (uint64_t k = b; k < e; k++)
+                entry.addMismatch(mismatch2CxtCode(SYM[misSyms[k] & 3], SYM[misSyms[k] >> 2]), misPos[k]);
+        } else {
+            for (uint64_t k = e; k-- > b;)
+                entry.addMismatch(mismatch2CxtCode(reverseComplement(SYM[misSyms[k] & 3]), reverseComplement(SYM[misSyms[k] >> 2])),
+                                  readLength - misPos[k] - 1);
+        }
+    }
+
+    void GpuReadsApproxMatcher::closeEntryUpdating() {
+        vector<uint64_t>().swap(misOffsets);
+        vector<uint8_t>().swap(misPos);
+        vector<uint8_t>().swap(misSyms);
     }
 
     // ------------------------------------------------------------------------------------------ mapReadsIntoPg

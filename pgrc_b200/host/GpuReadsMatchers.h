@@ -33,6 +33,8 @@ namespace PgTools {
         // copies the per-read results into the reference's member vectors
         void fetch(vector<uint64_t> &readMatchPos, vector<bool> &readMatchRC, vector<uint8_t> *readMismatchesCount,
                    uint_reads_cnt_max &matchedReadsCount, uint_reads_cnt_max *matchedCountPerMismatches);
+        // mismatch lists of all matched reads (pgm_get_mismatches): offsets[readsCount + 1], read offsets, symbol codes
+        void fetchMismatches(vector<uint64_t> &offsets, vector<uint8_t> &pos, vector<uint8_t> &syms);
     };
 
     class GpuReadsExactMatcher : public DefaultReadsExactMatcher {
@@ -55,6 +57,15 @@ namespace PgTools {
         void initMatching() override;
         void initMatchingContinuation(DefaultReadsMatcher *pMatcher) override;
         void executeMatching(bool revCompMode = false) override;
+        // export hooks (ReadsMatchers.h:52-54): the reference unpacks every matched read, reverse-complements it and
+        // compares it with the pseudogenome again (ReadsMatchers.cpp:548-558); here the lists come from the device
+        // (PGRC_GPU_EXPORT=0 keeps the reference's host code)
+        void initEntryUpdating() override;
+        void updateEntry(DefaultReadsListEntry &entry, uint_reads_cnt_max matchIdx, bool revComplPairFile) override;
+        void closeEntryUpdating() override;
+        bool deviceLists = false;
+        vector<uint64_t> misOffsets;
+        vector<uint8_t> misPos, misSyms;
     public:
         GpuReadsApproxMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
                               ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength,

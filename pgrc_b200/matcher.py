@@ -207,6 +207,19 @@ class GpuReadsMatcher:
         self._check(self._lib.pgm_get_results(self._h, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), ctypes.byref(st)))
         return self._result(out, st)
 
+    def get_mismatches(self):
+        """Mismatch lists of the matched reads (pgm_get_mismatches; what the reference's export recomputes per read,
+        ReadsMatchers.cpp:555-566): (offsets uint64[n+1], pos uint8[total], pg_sym uint8[total], read_sym uint8[total]),
+        symbols as codes A C G T N = 0..4, the read taken reverse-complemented when readMatchRC."""
+        total = ctypes.c_uint64()
+        self._check(self._lib.pgm_get_mismatches(self._h, None, None, None, 0, ctypes.byref(total)))
+        n = int(total.value)
+        off = np.empty(self.n_reads + 1, np.uint64)
+        pos, syms = np.empty(max(n, 1), np.uint8), np.empty(max(n, 1), np.uint8)
+        self._check(self._lib.pgm_get_mismatches(self._h, _ptr(off), _ptr(pos), _ptr(syms), n, ctypes.byref(total)))
+        pos, syms = pos[:n], syms[:n]
+        return off, pos, syms & 3, syms >> 2
+
     # -- the whole stage on this GPU
     def map_reads(self, seed: int = 38, min_chars_per_mismatch: int = 3, mode: str = "d", pre_seed: int = 0,
                   pre_mode: str = "d", rev_compl: bool = True, match_prefix_length: int = DISABLED_PREFIX_MODE,

@@ -299,3 +299,30 @@ def test_interleaved_mode_workloads_edges_and_shards():
     want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, mode="i")
     for got in _run_sharded_on_one_gpu(inp, 3, mode="i"):
         assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)
+
+
+@pytest.mark.parametrize("mode", ["d", "i"])
+def test_mismatch_lists_match_the_oracle(mode):
+    """pgm_get_mismatches (what the reference's export recomputes per matched read on the host, ReadsMatchers.cpp:548-558)
+    against the oracle's restatement, on adversarial inputs with N reads, both strands, two-phase and a c2-shaped workload."""
+    cases = [(synth.adversarial(95, 100), {}), (synth.adversarial(96, 150), {}), (synth.adversarial(97, 255), {}),
+             (synth.adversarial(98, 100), dict(pre_seed=50)), (synth.workload(300_000, 60_000, 150, 0.005, seed=99, n_frac=0.02), {})]
+    for inp, kw in cases:
+        with matcher.GpuReadsMatcher(0) as m:
+            m.set_text(inp.text)
+            m.set_reads(inp.lq_packed, inp.n_packed if len(inp.n_reads) else None, inp.read_len)
+            got = m.map_reads(38, 3, mode, kw.get("pre_seed", 0), mode)
+            off, o, pg, rd = m.get_mismatches()
+        want = oracle.oracle_mismatch_lists(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, got.pos, got.rc, got.mm, variant=0)
+        assert int(off[-1]) == int(got.mm[got.mm != 255].astype(np.int64).sum()) > 0
+        assert np.array_equal(off, want[0]) and np.array_equal(o, want[1]) and np.array_equal(pg, want[2]) and np.array_equal(rd, want[3])
+    # no reads matched / empty inputs
+    rng = np.random.default_rng(5)
+    g = synth.random_genome(3000, rng)
+    other = synth.sample_reads(synth.random_genome(3000, rng), 20, 100, 0.0, rng, require_error=False)
+    with matcher.GpuReadsMatcher(0) as m:
+        m.set_text(g)
+        m.set_reads(synth.pack_reads(other), None, 100)
+        got = m.map_reads()
+        off, o, pg, rd = m.get_mismatches()
+    assert got.matched == 0 and not off.any() and o.size == 0

@@ -69,3 +69,28 @@ def test_interleaved_mode_parameter_matrix(kw):
 def test_interleaved_mode_workload_shapes():
     _cmp(synth.workload(100_000, 8_000, 100, 0.001, seed=66), mode="i")
     _cmp(synth.workload(100_000, 12_000, 150, 0.005, seed=67, n_frac=0.02), mode="i")
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("mode", ["d", "i"])
+def test_mismatch_lists_of_the_export_step(pair, mode):
+    """pgo_mismatch_lists (variants 1 / 2) against the reference's own updateEntry (ReadsMatchers.cpp:548-558) driven as
+    exportMatchesInPgOrder drives it; variant 0 (the GPU contract) is the forward fill the other two are derived from."""
+    inp = synth.adversarial(91, 100, n_reads=1500, text_len=30000)
+    r, off, o, pg, rd = oracle.ref_mismatch_lists(inp.text, inp.lq_reads, inp.n_reads, 100, rev_compl_pair_file=pair, mode=mode)
+    assert r.matched > 100 and int(off[-1]) == int(r.mm[r.mm != 255].astype(np.int64).sum()) > 500
+    assert (rd == 4).sum() > 0                                          # N reads contribute N mismatches
+    want = oracle.oracle_mismatch_lists(inp.text, inp.lq_packed, inp.n_packed, 100, r.pos, r.rc, r.mm, variant=2 if pair else 1)
+    for a, b in zip((off, o, pg, rd), want):
+        assert np.array_equal(a, b)
+    # variant 0 -> variant 1 by the host rule the C++ shim applies: walk the list backwards, complement, mirror the offsets
+    f_off, f_o, f_pg, f_rd = oracle.oracle_mismatch_lists(inp.text, inp.lq_packed, inp.n_packed, 100, r.pos, r.rc, r.mm, variant=0)
+    assert np.array_equal(f_off, off)
+    comp = np.array([3, 2, 1, 0, 4], np.uint8)
+    for i in np.nonzero(r.mm != 255)[0][:400]:
+        s, e = int(off[i]), int(off[i + 1])
+        reversed_fill = (bool(r.rc[i]) != bool(i % 2)) if pair else bool(r.rc[i])
+        if reversed_fill:
+            assert np.array_equal(o[s:e], (99 - f_o[s:e])[::-1]) and np.array_equal(pg[s:e], comp[f_pg[s:e]][::-1]) and np.array_equal(rd[s:e], comp[f_rd[s:e]][::-1])
+        else:
+            assert np.array_equal(o[s:e], f_o[s:e]) and np.array_equal(pg[s:e], f_pg[s:e]) and np.array_equal(rd[s:e], f_rd[s:e])
