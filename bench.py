@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=float, default=0.05, help="fraction of the workload shape timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--export", action="store_true", help="also time the mismatch lists of the export step (SURVEY §8(f) rank 2): "
+                    "pgm_get_mismatches into pinned host arrays at full size, next to the reference's own per-read loop "
+                    "(updateEntry) on the CPU sample")
     ap.add_argument("--verify", action="store_true", help="after the timed region: re-count every reported alignment on the "
                     "device with plain torch ops (size-independent parity property for the full-size configs)")
     # kernel tuning knobs (pgm_set_tuning); defaults = the library's
@@ -426,6 +429,37 @@ def ours(args):
             vb = torch.tensor([verify["bad"], verify["matched"] if once else 0], device=dev, dtype=torch.int64)
             dist.all_reduce(vb)
             verify["bad"], verify["matched"] = int(vb[0].item()), int(vb[1].item())
+    export = None
+    if args.export and world == 1:
+        import ctypes
+        import numpy as np
+        step(my_text_d, my_reads_d, out_d)
+        total = ctypes.c_uint64()
+        m._check(m._lib.pgm_get_mismatches(m._h, None, None, None, 0, ctypes.byref(total)))
+        tot = int(total.value)
+        off_h = torch.empty(n_mine + 1, dtype=torch.int64, pin_memory=True)
+        pos_h = torch.empty(max(tot, 1), dtype=torch.uint8, pin_memory=True)
+        sym_h = torch.empty(max(tot, 1), dtype=torch.uint8, pin_memory=True)
+        def lists():
+            m._check(m._lib.pgm_get_mismatches(m._h, off_h.data_ptr(), pos_h.data_ptr(), sym_h.data_ptr(), tot, ctypes.byref(total)))
+        lists()
+        m.set_profiling(True); m.timings()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            lists()
+        wall_ms = (time.perf_counter() - t0) / 3 * 1e3
+        k_ms = m.timings()["mismatches"][0] / 3
+        m.set_profiling(False)
+        export = {"what": "mismatch lists of all matched reads (offsets + 2 bytes per mismatch) into pinned host arrays",
+                  "reads": n_mine, "mismatches": tot, "ms_per_call": round(wall_ms, 3), "kernel_ms": round(k_ms, 4),
+                  "reads_per_s": round(n_mine / (wall_ms * 1e-3), 1), "d2h_bytes": int(8 * (n_mine + 1) + 2 * tot)}
+        import oracle
+        if oracle.have_ref() and not args.no_cpu_baseline:
+            c, text_s, packed_s, ascii_s = cpu_sample_inputs(args, args.cpu_sample)
+            r, *_ = oracle.ref_mismatch_lists(text_s, ascii_s, None, c["read_len"], mode=args.mode)
+            export["cpu_reference"] = {"reads": c["n_reads"], "seconds": round(r.seconds, 4), "reads_per_s": round(c["n_reads"] / r.seconds, 1),
+                                       "what": "the reference's updateEntry loop (getRead + reverse complement + compare + addMismatch, "
+                                               "ReadsMatchers.cpp:548-558) on the CPU sample, 1 thread (serial in the reference)"}
     matched_total = res.matched
     if world > 1 and args.shard in ("reads", "2d"):
         mt = torch.tensor([res.matched if (args.shard == "reads" or t_rank == 0) else 0], device=dev, dtype=torch.int64)
@@ -449,6 +483,8 @@ def ours(args):
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
         if verify is not None:
             line["verify"] = verify
+        if export is not None:
+            line["export"] = export
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -104,7 +104,8 @@ def _ref():
                                              ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char, ctypes.c_char,
                                              ctypes.c_int, ctypes.c_int,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]
         _ref_lib = lib
     return _ref_lib
 
@@ -219,11 +220,13 @@ def ref_mismatch_lists(text, lq_ascii, n_ascii, read_len: int, rev_compl_pair_fi
     off = np.empty(n + 1, np.uint64)
     cap = n * 256
     o, pg, rd = (np.empty(cap, np.uint8) for _ in range(3))
+    secs = ctypes.c_double(0.0)
     r = _ref().pgref_mismatch_lists(buf.ctypes.data, buf.size - 1, lq.ctypes.data, lq.shape[0], nn.ctypes.data, nn.shape[0],
                                     read_len, pre_seed, seed, min_chars_per_mismatch, _mode(pre_mode), _mode(mode),
                                     int(rev_compl), int(rev_compl_pair_file), pos.ctypes.data, rc.ctypes.data, mm.ctypes.data,
-                                    off.ctypes.data, o.ctypes.data, pg.ctypes.data, rd.ctypes.data)
+                                    off.ctypes.data, o.ctypes.data, pg.ctypes.data, rd.ctypes.data, ctypes.byref(secs))
     if r != 0:
         raise RuntimeError(f"pgref_mismatch_lists failed ({r})")
     t = int(off[-1])
-    return MatchResult(pos, rc, mm, int((mm != 255).sum()), 0, 0, np.bincount(mm, minlength=256).astype(np.uint64)), off, o[:t], _SYM_CODE[pg[:t]], _SYM_CODE[rd[:t]]
+    return (MatchResult(pos, rc, mm, int((mm != 255).sum()), 0, 0, np.bincount(mm, minlength=256).astype(np.uint64), seconds=secs.value),
+            off, o[:t], _SYM_CODE[pg[:t]], _SYM_CODE[rd[:t]])

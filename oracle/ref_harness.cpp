@@ -100,7 +100,7 @@ AbstractReadsApproxMatcher* newApprox(char mode, char* pg, uint64_t pgLen, bool 
 
 // The reference's own export step for one read (exportMatchesInPgOrder, ReadsMatchers.cpp:583-588): entry at the match
 // position, then updateEntry (:548-558) fills the mismatches.  Dumps (offset, actual symbol, mismatch symbol).
-struct MisOut { uint64_t* offsets; uint8_t* off; char* pg; char* read; int rev_pair; };
+struct MisOut { uint64_t* offsets; uint8_t* off; char* pg; char* read; int rev_pair; double* seconds; };
 
 template <class P>
 void dumpMismatches(P* m, uint32_t n, const MisOut& o) {
@@ -156,13 +156,14 @@ int pgref_map_reads(char* text, uint64_t text_len, const char* lq_reads, uint32_
 // pgref_map_reads + the mismatch lists the reference's export step builds for every matched read (updateEntry,
 // ReadsMatchers.cpp:548-558, called as exportMatchesInPgOrder does, :583-588, with entry.idx = the read index):
 // out_offsets[n+1], then per mismatch its offset, the actual (pseudogenome) symbol and the mismatch (read) symbol as
-// decoded from the reference's context code.  The last matcher must be an approximate one.
+// decoded from the reference's context code.  The last matcher must be an approximate one.  *out_fill_seconds = wall
+// time of that per-read loop alone (getRead + reverse complement + compare + addMismatch, and the dump).
 int pgref_mismatch_lists(char* text, uint64_t text_len, const char* lq_reads, uint32_t n_lq, const char* n_reads, uint32_t n_n,
                          uint32_t read_len, uint32_t pre_seed, uint32_t seed, uint32_t min_chars_per_mismatch, char pre_mode,
                          char mode, int rev_compl, int rev_compl_pair_file, uint64_t* out_pos, uint8_t* out_rc, uint8_t* out_mm,
-                         uint64_t* out_offsets, uint8_t* out_off, char* out_pg, char* out_read) {
+                         uint64_t* out_offsets, uint8_t* out_off, char* out_pg, char* out_read, double* out_fill_seconds) {
     uint64_t stats[259];
-    MisOut mis{out_offsets, out_off, out_pg, out_read, rev_compl_pair_file};
+    MisOut mis{out_offsets, out_off, out_pg, out_read, rev_compl_pair_file, out_fill_seconds};
     return runReference(text, text_len, lq_reads, n_lq, n_reads, n_n, read_len, pre_seed, seed, min_chars_per_mismatch, pre_mode,
                         mode, rev_compl, 1, out_pos, out_rc, out_mm, stats, nullptr, &mis);
 }
@@ -258,7 +259,11 @@ int runReference(char* text, uint64_t text_len,
         out_stats[0] = e->matched(); out_stats[1] = e->better(); out_stats[2] = e->falses();
     } else {
         dumpAny(static_cast<AbstractReadsApproxMatcher*>(matcher), lastMode, n, out_pos, out_rc, out_mm, out_stats);
-        if (mis) dumpMismatchesAny(static_cast<AbstractReadsApproxMatcher*>(matcher), lastMode, n, *mis);
+        if (mis) {
+            auto m0 = std::chrono::steady_clock::now();
+            dumpMismatchesAny(static_cast<AbstractReadsApproxMatcher*>(matcher), lastMode, n, *mis);
+            if (mis->seconds) *mis->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - m0).count();
+        }
     }
     if (mis && firstIsExact) { delete matcher; return -1; }
     delete matcher;
