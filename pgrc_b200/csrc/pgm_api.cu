@@ -90,6 +90,8 @@ struct pgm_ctx {
     uint32_t filter_words = 0;  // 0 = no filter
     uint32_t filter_k = 2;      // bits per pattern in its filter word
     int filter_k_force = 0;     // PGM_FILTER_K (sweeps)
+    int filter_pair_mode = 1;   // paired filter lookups: 0 off, 1 auto (by load), 2 always (PGM_FILTER_PAIR)
+    uint32_t filter_pair = 0, pair_lo = 0, pair_mask = 0;
 
     // phase
     uint32_t seed_len = 0, parts = 0, max_mm = 0, min_mm = 0, part_bits = 0;
@@ -203,6 +205,7 @@ pgm::TableView table_view(pgm_ctx *c) {
     tv.n_buckets = c->n_buckets;
     tv.filter_mask = c->filter_words ? c->filter_words - 1 : 0;
     tv.filter_k = c->filter_k;
+    tv.pair = c->filter_words ? c->filter_pair : 0; tv.pair_lo = c->pair_lo; tv.pair_mask = c->pair_mask;
     return tv;
 }
 
@@ -401,12 +404,18 @@ template <int NCH>
 void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, bool filter_stage) {
     // FAST: only ACGT reads, records of exactly 64 bytes (read length <= 192)
     const bool fast = sp.reads.n_n == 0 && sp.reads.lq_stride16 == 4;
-    if (filter_stage) pgm::scan_kernel<NCH, false, 1, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
-    else if (sp.ilv) {
-        if (fast) pgm::scan_kernel<NCH, true, 0, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
-        else pgm::scan_kernel<NCH, false, 0, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
-    } else if (fast) pgm::scan_kernel<NCH, true, 0, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
-    else pgm::scan_kernel<NCH, false, 0, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    const bool pair = sp.tab.pair != 0;          // (never set together with ilv)
+    if (filter_stage) {
+        if (pair) pgm::scan_kernel<NCH, false, 1, false, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+        else pgm::scan_kernel<NCH, false, 1, false, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    } else if (sp.ilv) {
+        if (fast) pgm::scan_kernel<NCH, true, 0, true, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+        else pgm::scan_kernel<NCH, false, 0, true, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    } else if (pair) {
+        if (fast) pgm::scan_kernel<NCH, true, 0, false, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+        else pgm::scan_kernel<NCH, false, 0, false, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    } else if (fast) pgm::scan_kernel<NCH, true, 0, false, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    else pgm::scan_kernel<NCH, false, 0, false, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
 }
 
 void launch_scan_nch(int nch, const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, bool filter_stage) {
@@ -487,6 +496,7 @@ int pgm_create(int device, pgm_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *t = getenv("PGM_TWO_STEP_BUILD")) ctx->two_step_build = atoi(t);   // 0 off, 1 auto, 2 always (tests)
     if (const char *t = getenv("PGM_FILTER_K")) ctx->filter_k_force = atoi(t);
+    if (const char *t = getenv("PGM_FILTER_PAIR")) ctx->filter_pair_mode = atoi(t);
     if (const char *t = getenv("PGM_INSERT_PREFETCH")) ctx->insert_prefetch = atoi(t);
     if (const char *t = getenv("PGM_BLOCKED_SCAN")) ctx->blocked_scan = atoi(t);
     if (const char *t = getenv("PGM_REGION_MB")) ctx->region_mb = std::max(1, atoi(t));
@@ -745,11 +755,22 @@ int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t m
     // auto: 8 bits per pattern up to 2^28 bits (32 MB stays L2-resident next to the streaming traffic); pattern sets far
     // beyond that get 2^29 bits (64 MB: still mostly resident) — a saturated filter sends every text window to the table
     if (fbits < 0) fbits = std::min(n_patterns > (100ull << 20) ? 29 : 28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 8)));
+    const bool auto_bits = ctx->filter_log2_bits < 0;
     if (fbits > 0) {
-        // bits per pattern: k = 0.69 * filter bits / patterns minimises the false-positive rate (1..4, all in one word)
-        const double per = (double)(1ull << fbits) / (double)std::max<uint64_t>(n_patterns, 1);
+        // paired lookups (pgm_kernels.cuh, pair_word): one gather for two adjacent windows, every pattern entered in two
+        // words; only for contiguous seeds with >= 12 exactly-hashed shared bases, and only while the doubled load stays low
+        const uint32_t lo_off = seed_len > 32 ? seed_len - 32 : 0, hi_off = std::min<uint32_t>(seed_len, 32);
+        const int core = (int)hi_off - (int)lo_off - 1;
+        if (auto_bits && ctx->filter_pair_mode == 1 && !interleaved && core >= 12 && n_patterns * 24 <= (1ull << 28))
+            fbits = std::max(fbits, std::min(28, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 24)));   // room for the second entry
+        ctx->filter_pair = !interleaved && core >= 12 &&
+                           (ctx->filter_pair_mode == 2 || (ctx->filter_pair_mode == 1 && n_patterns * 12 <= (1ull << fbits)));
+        ctx->pair_lo = lo_off;
+        ctx->pair_mask = core >= 12 ? (uint32_t)((1ull << core) - 1) : 0;
+        // bits per pattern: k = 0.69 * filter bits / entries minimises the false-positive rate; 1 or 2, in one word
+        const double per = (double)(1ull << fbits) / (double)(std::max<uint64_t>(n_patterns, 1) * (ctx->filter_pair ? 2 : 1));
         ctx->filter_k = ctx->filter_k_force ? (uint32_t)std::min(4, std::max(1, ctx->filter_k_force))
-                                            : (uint32_t)std::min(4.0, std::max(1.0, 0.69 * per + 0.5));
+                                            : (uint32_t)std::min(2.0, std::max(1.0, 0.69 * per + 0.5));   // (3 or 4 bits: more ALU per window than probes saved, measured)
         ctx->filter_words = 1u << (fbits - 5);
         const size_t fbytes = (size_t)1 << (fbits - 3);
         if ((rc = ensure(ctx, ctx->filter, fbytes))) return rc;

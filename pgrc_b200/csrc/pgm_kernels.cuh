@@ -102,6 +102,23 @@ __host__ __device__ __forceinline__ uint32_t filter_bits(uint32_t f, uint32_t k)
     return m;
 }
 
+// Paired lookups.  The windows starting at text positions x and x+1 share all but one base; offsets [lo, hi) of a
+// window (lo = max(0, n-32), hi = min(n, 32)) are the ones the 32-bit rotate-xor hash sees exactly (one symbol per
+// rotation class), so bits [lo, hi) of P and Q ARE those bases.  The filter word of a window is chosen by a hash of the
+// core it shares with its pair partner — offsets [lo+1, hi) when it is the first of the pair (role 0), [lo, hi-1) when
+// it is the second (role 1): the same text bases, hence the same word, and ONE gather answers both windows (the bits
+// inside the word still come from the window's full form).  A pattern cannot know its role: it is entered in both
+// words, which doubles the filter's load — the host turns pairing on only while that is harmless (few patterns per
+// filter bit: multi-GPU read shards, small inputs), where the per-window gather is what bounds the scan.
+__host__ __device__ __forceinline__ uint32_t pair_word(uint32_t P, uint32_t Q, uint32_t role, uint32_t lo, uint32_t cmask) {
+    const uint32_t sh = lo + 1u - role;
+    const uint32_t a = ((P >> sh) & cmask) * 0x9E3779B1u, b = ((Q >> sh) & cmask) * 0x85EBCA77u;
+    uint32_t x = a ^ ((b << 15) | (b >> 17));
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    return x;
+}
+
 // ------------------------------------------------------------------------------------------ parameters
 struct __align__(32) u32x8 { uint32_t v[8]; };
 
@@ -112,6 +129,8 @@ struct TableView {
     uint32_t n_buckets;         // prime
     uint32_t filter_mask;       // #filter words - 1
     uint32_t filter_k;          // bits per pattern in its filter word (1..4)
+    uint32_t pair;              // 1: paired lookups — the filter word is chosen by the bases two adjacent windows share (below)
+    uint32_t pair_lo, pair_mask;   // first exactly-hashed window offset, mask of the shared core's bits
 };
 
 struct ReadsView {
@@ -607,7 +626,10 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
                     const uint32_t pat = (r << reads.part_bits) | j;
                     if (tab.filter) {
                         const uint32_t f = filter_hash(P, Q, R);
-                        atomicOr(tab.filter + (f & tab.filter_mask), filter_bits(f, tab.filter_k));
+                        if (tab.pair) {
+                            atomicOr(tab.filter + (pair_word(P, Q, 0, tab.pair_lo, tab.pair_mask) & tab.filter_mask), filter_bits(f, tab.filter_k));
+                            atomicOr(tab.filter + (pair_word(P, Q, 1, tab.pair_lo, tab.pair_mask) & tab.filter_mask), filter_bits(f, tab.filter_k));
+                        } else atomicOr(tab.filter + (f & tab.filter_mask), filter_bits(f, tab.filter_k));
                     }
                     n_ins++;
                     if (n_regions) {
@@ -762,7 +784,7 @@ __device__ __forceinline__ int count_groups(uint32_t u, bool is_n, uint4 v, cons
 // and seed j aligns the read at x - j.  Per tile the staged planes are de-interleaved by position residue into `s` phase
 // strings in shared memory (phase r, index q <-> tile position r + q*s): in phase space the window is contiguous again and
 // stage A1 / the rehash of A2 run unchanged on it; verification (stage B) uses the original planes.
-template <int NCH, bool FAST, int MODE, bool ILV>
+template <int NCH, bool FAST, int MODE, bool ILV, bool PAIR>
 __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kernel(const __grid_constant__ ScanParams p) {
     __shared__ __align__(128) ScanShared<ILV> sm;
     if (MODE == 0 && p.only_if != nullptr && *p.only_if == 0) {
@@ -864,24 +886,30 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
 #pragma unroll 1
             for (uint32_t it0 = 0; it0 < PGM_WORDS_PER_WARP; it0 += U) {
                 const uint32_t pos0 = (w_first + it0) * 32;
-                uint32_t fm[U], fi[U];
+                // slot u of a lane: position pos0 + 32u + lane, or — paired lookups — slots 2v, 2v+1 are the two windows
+                // pos0 + 64v + 2 lane (+1), which share one filter word and one gather
+                constexpr bool pair = PAIR;
+                uint32_t fm[U], fi[U], ps[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     uint32_t P, Q, R;
-                    window_form<NCH>(slo, shi, pos0 + 32 * u + lane, p.tail_mask, P, Q, R);
+                    ps[u] = pair ? pos0 + 64 * (u >> 1) + 2 * lane + (u & 1) : pos0 + 32 * u + lane;
+                    window_form<NCH>(slo, shi, ps[u], p.tail_mask, P, Q, R);
                     const uint32_t f = filter_hash(P, Q, R);
-                    fi[u] = f & p.tab.filter_mask;
+                    fi[u] = (pair ? pair_word(P, Q, 0, p.tab.pair_lo, p.tab.pair_mask) : f) & p.tab.filter_mask;
                     fm[u] = filter_bits(f, p.tab.filter_k);
                 }
                 uint32_t fw[U];
 #pragma unroll
-                for (int u = 0; u < U; u++)
-                    fw[u] = !p.tab.filter ? 0xFFFFFFFFu : fhints ? ld_u32_hint(p.tab.filter + fi[u], pol_keep) : __ldg(p.tab.filter + fi[u]);
+                for (int u = 0; u < U; u++) {
+                    if (pair && (u & 1)) fw[u] = fw[u - 1];
+                    else fw[u] = !p.tab.filter ? 0xFFFFFFFFu : fhints ? ld_u32_hint(p.tab.filter + fi[u], pol_keep) : __ldg(p.tab.filter + fi[u]);
+                }
                 uint32_t bal[U], tot = 0;
                 bool hit[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const uint32_t pos = pos0 + 32 * u + lane;
+                    const uint32_t pos = ps[u];
                     hit[u] = pos >= vb && pos < ve && (fw[u] & fm[u]) == fm[u];
                     bal[u] = __ballot_sync(PGM_FULL, hit[u]);
                     tot += __popc(bal[u]);
@@ -892,7 +920,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                     base = __shfl_sync(PGM_FULL, base, 0);
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        if (hit[u]) sm.q1[base + __popc(bal[u] & lt_mask)] = (uint16_t)(pos0 + 32 * u + lane);
+                        if (hit[u]) sm.q1[base + __popc(bal[u] & lt_mask)] = (uint16_t)ps[u];
                         base += __popc(bal[u]);
                     }
                     if (lane == 0) n_pos += tot;

@@ -326,3 +326,25 @@ def test_mismatch_lists_match_the_oracle(mode):
         got = m.map_reads()
         off, o, pg, rd = m.get_mismatches()
     assert got.matched == 0 and not off.any() and o.size == 0
+
+
+@pytest.mark.parametrize("pair", ["0", "2"])
+def test_paired_filter_lookups_forced_on_and_off(monkeypatch, pair):
+    """Paired pre-filter lookups (one gather per two adjacent text windows, every pattern entered under both roles): off,
+    and forced on regardless of the load — seed lengths around the 32-bit word (exactly-hashed core of 64 - n bases),
+    N reads, hot seeds, text shards, the blocked pipeline."""
+    monkeypatch.setenv("PGM_FILTER_PAIR", pair)
+    for seed, L in ((101, 100), (102, 150), (103, 64), (104, 255)):
+        _check(synth.adversarial(seed, L))
+    for kw in (dict(reads_exact_matching_chars=20), dict(reads_exact_matching_chars=32), dict(reads_exact_matching_chars=33),
+               dict(reads_exact_matching_chars=45), dict(reads_exact_matching_chars=50), dict(reads_exact_matching_chars=51),
+               dict(reads_exact_matching_chars=100), dict(matching_mode="D"), dict(pre_reads_exact_matching_chars=50),
+               dict(matching_mode="i"), dict(rev_compl_pg=False)):
+        _check(synth.adversarial(105, 100), **kw)
+    _check(synth.workload(500_000, 100_000, 150, 0.005, seed=106, n_frac=0.02, name="c2/100"))
+    inp = synth.adversarial(107, 100, n_reads=2000, text_len=30000)
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len)
+    for got in _run_sharded_on_one_gpu(inp, 3):
+        assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)
+    monkeypatch.setenv("PGM_BLOCKED_SCAN", "2")
+    _check(synth.adversarial(108, 100))
