@@ -650,8 +650,10 @@ int pgm_set_text_shard(pgm_ctx *ctx, const char *slice, uint64_t slice_begin, ui
     ctx->text_pending = false; ctx->text_copies_enqueued = false; ctx->h_text = nullptr;
     if (!slice_len) return PGM_OK;
     if (is_device_ptr(slice)) {
-        for (uint64_t c = 0; c < text_chunks(ctx); c++)
-            if ((rc = pack_text_chunk(ctx, reinterpret_cast<const uint8_t *>(slice), c))) return rc;
+        // device-resident text: one launch over the whole slice (the chunks exist for the pipelined host upload)
+        uint32_t *flo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS, *fhi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
+        KLAUNCH(PGM_K_PACK_TEXT, "pack_text_kernel", pgm::pack_text_kernel<<<grid_for((slice_len + 31) / 32, 256), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const uint8_t *>(slice), slice_len, flo, fhi, 0, ctx->err_flag.as<int>()));
         return rc_text(ctx);
     }
     // host text: uploaded lazily (see pgm_match_begin / pgm_scan_pass); the caller keeps the buffer alive and

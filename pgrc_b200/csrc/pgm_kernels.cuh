@@ -889,12 +889,12 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                 // slot u of a lane: position pos0 + 32u + lane, or — paired lookups — slots 2v, 2v+1 are the two windows
                 // pos0 + 64v + 2 lane (+1), which share one filter word and one gather
                 constexpr bool pair = PAIR;
-                uint32_t fm[U], fi[U], ps[U];
+                auto pos_of = [&](int u) -> uint32_t { return pair ? pos0 + 64 * (u >> 1) + 2 * lane + (u & 1) : pos0 + 32 * u + lane; };
+                uint32_t fm[U], fi[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     uint32_t P, Q, R;
-                    ps[u] = pair ? pos0 + 64 * (u >> 1) + 2 * lane + (u & 1) : pos0 + 32 * u + lane;
-                    window_form<NCH>(slo, shi, ps[u], p.tail_mask, P, Q, R);
+                    window_form<NCH>(slo, shi, pos_of(u), p.tail_mask, P, Q, R);
                     const uint32_t f = filter_hash(P, Q, R);
                     fi[u] = (pair ? pair_word(P, Q, 0, p.tab.pair_lo, p.tab.pair_mask) : f) & p.tab.filter_mask;
                     fm[u] = filter_bits(f, p.tab.filter_k);
@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                 bool hit[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const uint32_t pos = ps[u];
+                    const uint32_t pos = pos_of(u);
                     hit[u] = pos >= vb && pos < ve && (fw[u] & fm[u]) == fm[u];
                     bal[u] = __ballot_sync(PGM_FULL, hit[u]);
                     tot += __popc(bal[u]);
@@ -920,7 +920,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                     base = __shfl_sync(PGM_FULL, base, 0);
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        if (hit[u]) sm.q1[base + __popc(bal[u] & lt_mask)] = (uint16_t)ps[u];
+                        if (hit[u]) sm.q1[base + __popc(bal[u] & lt_mask)] = (uint16_t)pos_of(u);
                         base += __popc(bal[u]);
                     }
                     if (lane == 0) n_pos += tot;
