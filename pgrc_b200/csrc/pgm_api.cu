@@ -771,7 +771,7 @@ int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t m
         ctx->pair_mask = core >= 12 ? (uint32_t)((1ull << core) - 1) : 0;
         // bits per pattern: k = 0.69 * filter bits / entries minimises the false-positive rate; 1 or 2, in one word
         const double per = (double)(1ull << fbits) / (double)(std::max<uint64_t>(n_patterns, 1) * (ctx->filter_pair ? 2 : 1));
-        ctx->filter_k = ctx->filter_k_force ? (uint32_t)std::min(4, std::max(1, ctx->filter_k_force))
+        ctx->filter_k = ctx->filter_k_force ? (uint32_t)std::min(2, std::max(1, ctx->filter_k_force))
                                             : (uint32_t)std::min(2.0, std::max(1.0, 0.69 * per + 0.5));   // (3 or 4 bits: more ALU per window than probes saved, measured)
         ctx->filter_words = 1u << (fbits - 5);
         const size_t fbytes = (size_t)1 << (fbits - 3);

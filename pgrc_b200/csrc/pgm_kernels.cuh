@@ -89,17 +89,12 @@ __host__ __device__ __forceinline__ uint32_t filter_hash(uint32_t P, uint32_t Q,
     x ^= x >> 16;
     return x;
 }
-// k bits of one filter word (k = 1..4, chosen on the host from the filter's bits per pattern: about 0.69 * bits / patterns
-// minimises the false-positive rate; a table far beyond the L2-resident filter's capacity wants k = 1)
+// k = 1 or 2 bits of one filter word, chosen on the host from the filter's bits per entry (about 0.69 * bits / entries
+// minimises the false-positive rate; 3 and 4 bits were measured: they cost more instructions per text window than they
+// save probes; a table far beyond the L2-resident filter's capacity wants k = 1)
 __host__ __device__ __forceinline__ uint32_t filter_bits(uint32_t f, uint32_t k) {
-    uint32_t m = 1u << (f >> 27);
-    if (k > 1) {
-        const uint32_t g = f * 0x9E3779B1u;
-        m |= 1u << (g >> 27);
-        if (k > 2) m |= 1u << ((g >> 22) & 31u);
-        if (k > 3) m |= 1u << ((g >> 17) & 31u);
-    }
-    return m;
+    const uint32_t g = f * 0x9E3779B1u;
+    return (1u << (f >> 27)) | (k > 1u ? 1u << (g >> 27) : 0u);
 }
 
 // Paired lookups.  The windows starting at text positions x and x+1 share all but one base; offsets [lo, hi) of a
@@ -128,7 +123,7 @@ struct TableView {
     uint32_t *filter;           // may be null
     uint32_t n_buckets;         // prime
     uint32_t filter_mask;       // #filter words - 1
-    uint32_t filter_k;          // bits per pattern in its filter word (1..4)
+    uint32_t filter_k;          // bits per pattern in its filter word (1 or 2)
     uint32_t pair;              // 1: paired lookups — the filter word is chosen by the bases two adjacent windows share (below)
     uint32_t pair_lo, pair_mask;   // first exactly-hashed window offset, mask of the shared core's bits
 };
@@ -177,7 +172,7 @@ struct ScanParams {
     uint32_t ilv;                   // 0: seed j = read bases [j*n, (j+1)*n) (mode 'd'); else the stride (= parts) of mode 'i'
     uint32_t tail_mask;             // valid bits of the last 32-base chunk of a seed
     int rev_mode;
-    int l2_hints;                   // 1: filter loads carry an L2 evict_last policy
+    int l2_hints;                   // (unused: filter loads always carry an L2 evict_last policy)
     int stream_hints;               // 1: bucket / record loads carry an L2 evict_first policy
     TableView tab;
     ReadsView reads;
@@ -797,7 +792,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
     const uint32_t lt_mask = (1u << lane) - 1u;
     unsigned long long n_cand = 0, n_ver = 0, n_acc = 0, n_pos = 0;
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
-    const bool hints = p.stream_hints != 0, fhints = p.l2_hints != 0;
+    const bool hints = p.stream_hints != 0;
 
     auto issue_tile = [&](unsigned int tile, int b) {
         const int64_t w0 = (int64_t)p.first_word + (int64_t)tile * PGM_TILE_WORDS - PGM_HALO_L;
@@ -868,8 +863,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                 window_form<NCH>(sm.dl + r * ilv_mw, sm.dh + r * ilv_mw, q, p.tail_mask, P, Q, R);
                 const uint32_t f = filter_hash(P, Q, R);
                 const uint32_t fm = filter_bits(f, p.tab.filter_k);
-                const uint32_t fw = !p.tab.filter ? 0xFFFFFFFFu : fhints ? ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep)
-                                                                         : __ldg(p.tab.filter + (f & p.tab.filter_mask));
+                const uint32_t fw = !p.tab.filter ? 0xFFFFFFFFu : ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep);
                 const bool hit = pos < PGM_TILE_POS && pos >= vb && pos < ve && (fw & fm) == fm;
                 const uint32_t bal = __ballot_sync(PGM_FULL, hit);
                 if (bal) {
@@ -903,7 +897,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     if (pair && (u & 1)) fw[u] = fw[u - 1];
-                    else fw[u] = !p.tab.filter ? 0xFFFFFFFFu : fhints ? ld_u32_hint(p.tab.filter + fi[u], pol_keep) : __ldg(p.tab.filter + fi[u]);
+                    else fw[u] = !p.tab.filter ? 0xFFFFFFFFu : ld_u32_hint(p.tab.filter + fi[u], pol_keep);   // evict_last: the filter is the one L2-resident structure
                 }
                 uint32_t bal[U], tot = 0;
                 bool hit[U];
