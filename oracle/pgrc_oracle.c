@@ -10,7 +10,10 @@
  *                     ConstantLengthPatternsOnTextHashMatcher.h:70-137, .cpp:52-101 (strided patterns: pattern j of a
  *                     read = its symbols j, j+parts, j+2*parts, ...; one rolling hash per text position residue)
  *   pass structure    ReadsMatchers.cpp:162-184
- *   driver            ReadsMatchers.cpp:693-783 (mapReadsIntoPg, modes 'd'/'D' and 'i'/'I')
+ *   CopMEM mode       ReadsMatchers.cpp:411-451 (CopMEMReadsApproxMatcher), copmem/CopMEMMatcher.cpp:71-137 (parameters),
+ *                     :139-233 (index of every k1-th text position, serial build = -t 1), :483-566 (per-read query),
+ *                     copmem/Hashes.h:54-76 (maRushPrime1HashSparsified)
+ *   driver            ReadsMatchers.cpp:693-783 (mapReadsIntoPg, modes 'd'/'D', 'i'/'I' and 'c'/'C')
  *   read layout       SymbolsPackingFacility.cpp:147-185, PackedConstantLengthReadsSet.h:40-46
  *   mismatch count    SymbolsPackingFacility.cpp:344-374 (contract: exact count if <= limit, else 255)
  *   reverse compl.    utils/helper.cpp:383-393
@@ -248,7 +251,7 @@ typedef struct {
     pgo_stats *st;
     /* approx parameters */
     uint32_t part_len, parts; uint8_t max_mm, min_mm;
-    int interleaved;
+    int interleaved, copmem;
     char *cur_read, *seed_buf, *win_buf;
 } matcher;
 
@@ -405,6 +408,165 @@ static int interleaved_pass(matcher *m, pat_table *t, const char *txt, int rev_m
     return 0;
 }
 
+/* ------------------------------------------------------------------ CopMEM mode ('c')
+ * CopMEMReadsApproxMatcher (ReadsMatchers.cpp:411-451): per pass an index of the (reverse-complemented) text — every
+ * k1-th position, hashed over K characters, at most 13 positions per hash value, first come first kept — and per read a
+ * sequential query: every k2-th read offset, bucket entries in text order, verification with an early exit, strict
+ * improvement, a budget of false matches after which buckets are cut to 4 entries.  This restates the SERIAL index
+ * build (processRef, CopMEMMatcher.cpp:171-233), i.e. the reference at -t 1; its multithreaded build
+ * (processRefMultithreaded, :277-324) orders buckets differently and races. */
+#define CM_COLLISIONS_LIMIT 12      /* HASH_COLLISIONS_PER_POSITION_LIMIT            CopMEMMatcher.h:11 */
+#define CM_AVG_COLLISIONS_LIMIT 1   /* AVERAGE_HASH_COLLISIONS_PER_POSITION_LIMIT    :12 */
+#define CM_TRUNCATED_BUCKET 4       /* UNLIMITED_NUMBER_OF_HASH_COLLISIONS_PER_POSITION :13 */
+#define CM_HASH_MIN_ORDER 24
+#define CM_HASH_MAX_ORDER 31
+
+typedef struct {
+    uint32_t L, K, k1, k2, hash_size;
+    uint64_t N;
+    const char *text;
+    uint32_t *cumm;      /* hash_size + 2 */
+    uint64_t *pos;       /* sampled positions, bucket h = [cumm[h], cumm[h+1]) */
+} copmem_index;
+
+/* initParams + calcCoprimes (CopMEMMatcher.cpp:71-137); minMatchLength = min(UINT32_MAX, L) = L.  Returns -1 where the
+ * reference exits ("Minimal matching length too short", "L and K mismatch"). */
+static int copmem_params(copmem_index *x, uint32_t L, uint64_t N) {
+    int K;
+    if (L > 110) K = 56; else if (L > 62) K = 44; else if (L > 53) K = 40; else if (L > 46) K = 36;
+    else if (L > 42) K = 32; else if (L > 32) K = 28; else K = ((int)L / 4 - 1) * 4;
+    if (L < 24) return -1;
+    const int kmml = ((int)L / 4 - 1) * 4;
+    if (kmml < K) K = kmml;
+    const int t = (int)L - K + 1;
+    if (t <= 0) return -1;
+    int k1, k2;
+    if (t >= 20) {
+        k1 = 1; while ((k1 + 1) * (k1 + 1) <= t) k1++;      /* (int) pow(t, 0.5) */
+        k1 += 1; k2 = k1 - 1;
+        if (k1 * k2 > t) { --k2; --k1; }
+    } else if (t >= 15) { k1 = 5; k2 = 3; } else if (t >= 12) { k1 = 4; k2 = 3; } else if (t >= 10) { k1 = 5; k2 = 2; }
+    else if (t >= 6) { k1 = 3; k2 = 2; } else { k1 = t; k2 = 1; }
+    x->L = L; x->K = (uint32_t)K; x->k1 = (uint32_t)k1; x->k2 = (uint32_t)k2; x->N = N;
+    int i = CM_HASH_MIN_ORDER;
+    do { x->hash_size = 1u << (i++); } while (i <= CM_HASH_MAX_ORDER && x->hash_size < N / (uint64_t)k1);
+    return 0;
+}
+
+/* maRushPrime1HashSparsified<K> (Hashes.h:54-76): K/4 little-endian 32-bit words of the text, the first three masked to
+ * their low 3 bytes, the others to their low 2 bytes */
+static uint32_t copmem_hash(const copmem_index *x, const char *str) {
+    uint64_t hash = x->K;
+    for (uint32_t j = 0; j < x->K / 4; j++, str += 4) {
+        uint32_t k = (uint32_t)(unsigned char)str[0] | ((uint32_t)(unsigned char)str[1] << 8) |
+                     ((uint32_t)(unsigned char)str[2] << 16) | ((uint32_t)(unsigned char)str[3] << 24);
+        k &= j < 3 ? 0x00FFFFFFu : 0x0000FFFFu;
+        k += j;
+        hash ^= k;
+        hash *= 171717;
+    }
+    return (uint32_t)hash & (x->hash_size - 1);
+}
+
+static void copmem_free(copmem_index *x) { free(x->cumm); free(x->pos); x->cumm = NULL; x->pos = NULL; }
+
+/* genCumm + processRef (CopMEMMatcher.cpp:139-233): positions 0, k1, 2 k1, ... <= N - K in ascending order; a hash value
+ * keeps its first CM_COLLISIONS_LIMIT + 1 positions */
+static int copmem_build(copmem_index *x, const char *text) {
+    x->text = text;
+    x->cumm = (uint32_t *)calloc((size_t)x->hash_size + 2, sizeof(uint32_t));
+    if (!x->cumm) return -2;
+    uint32_t *cnt = x->cumm + 1;          /* cnt[h] = entries of bucket h; prefix sums below turn cumm[h] into its start */
+    if (x->N >= x->K)
+        for (uint64_t i = 0; i + x->K <= x->N; i += x->k1) {
+            const uint32_t h = copmem_hash(x, text + i);
+            if (cnt[h] <= CM_COLLISIONS_LIMIT) cnt[h]++;
+        }
+    uint64_t total = 0;
+    for (uint64_t h = 0; h <= x->hash_size; h++) { const uint32_t c = cnt[h]; x->cumm[h] = (uint32_t)total; total += c; }
+    x->cumm[x->hash_size + 1] = (uint32_t)total;
+    /* (cumm[h] is now the start of bucket h, cumm[h+1] its end; cnt aliases cumm + 1, rewritten in the loop above) */
+    x->pos = (uint64_t *)malloc((total + 2) * sizeof(uint64_t));
+    uint32_t *fill = (uint32_t *)calloc((size_t)x->hash_size + 1, sizeof(uint32_t));
+    if (!x->pos || !fill) { free(fill); return -2; }
+    if (x->N >= x->K)
+        for (uint64_t i = 0; i + x->K <= x->N; i += x->k1) {
+            const uint32_t h = copmem_hash(x, text + i);
+            if (fill[h] <= CM_COLLISIONS_LIMIT) { x->pos[x->cumm[h] + fill[h]] = i; fill[h]++; }
+        }
+    free(fill);
+    return 0;
+}
+
+/* processApproxMatchQueryTight (CopMEMMatcher.cpp:483-566) */
+static uint64_t copmem_query(const copmem_index *x, const char *read, uint32_t N2, uint8_t max_mm, uint8_t min_mm,
+                             uint8_t *mismatches, uint64_t *better, uint64_t *false_matches) {
+    if (*mismatches < max_mm) max_mm = (uint8_t)(*mismatches - 1);
+    const uint32_t n2trim8 = (N2 / 8) * 8;
+    const uint64_t limit = (uint64_t)((N2 + 1 - x->K) / x->k2) * CM_AVG_COLLISIONS_LIMIT;
+    uint64_t cur_false = 0, match_pos = PGO_NOT_MATCHED_POSITION;
+    for (uint32_t i1 = 0; i1 + x->K < N2 + 1; i1 += x->k2) {
+        const uint32_t h = copmem_hash(x, read + i1);
+        uint32_t b0 = x->cumm[h], b1 = x->cumm[h + 1];
+        if (b0 == b1) continue;
+        if (limit < cur_false && b1 > b0 + CM_TRUNCATED_BUCKET) b1 = b0 + CM_TRUNCATED_BUCKET;
+        for (uint32_t j = b0; j < b1; j++) {
+            const uint64_t sp = x->pos[j];
+            if (i1 > sp) continue;
+            if (sp - i1 + N2 > x->N) continue;
+            const char *txt = x->text + (sp - i1);
+            uint8_t res = 0;
+            uint32_t p = 0;
+            while (res <= max_mm && p != n2trim8) {            /* 8 characters at a time, exit only between blocks */
+                for (int q = 0; q < 8; q++) res = (uint8_t)(res + (read[p + q] != txt[p + q]));
+                p += 8;
+            }
+            if (res > max_mm) { cur_false++; continue; }
+            while (p != N2) {
+                if (read[p] != txt[p]) {
+                    p++;
+                    if (res++ >= max_mm) { cur_false++; break; }   /* (counted once more just below, as in the reference) */
+                } else p++;
+            }
+            if (res > max_mm) { cur_false++; continue; }
+            if (*mismatches != 255) (*better)++;
+            *mismatches = res;
+            match_pos = sp - i1;
+            if (res <= min_mm) { *false_matches += cur_false; return match_pos; }
+            max_mm = (uint8_t)(res - 1);
+        }
+    }
+    *false_matches += cur_false;
+    return match_pos;
+}
+
+/* CopMEMReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:421-451), one thread */
+static int copmem_pass(matcher *m, const char *txt, int rev_mode) {
+    copmem_index x;
+    memset(&x, 0, sizeof x);
+    if (copmem_params(&x, m->part_len, m->pg_len) != 0) return -1;
+    int rcode = copmem_build(&x, txt);
+    if (rcode != 0) { copmem_free(&x); return rcode; }
+    for (uint32_t r = 0; r < m->n_reads; r++) {
+        if (m->mm[r] <= m->min_mm) continue;
+        get_read(m->rs, r, m->cur_read);
+        uint8_t c = m->mm[r];
+        const uint64_t p = copmem_query(&x, m->cur_read, m->matching_len, m->max_mm, m->min_mm, &c, &m->st->better,
+                                        &m->st->false_matches);
+        if (p == PGO_NOT_MATCHED_POSITION) continue;
+        if (c < m->mm[r]) {
+            if (m->mm[r] == PGO_NOT_MATCHED_COUNT) m->st->matched++;
+            m->st->per_mm[m->mm[r]]--;
+            m->st->per_mm[c]++;
+            m->pos[r] = rev_mode ? m->pg_len - (p + m->matching_len) : p;
+            m->rc[r] = (uint8_t)(rev_mode ? 1 : 0);
+            m->mm[r] = c;
+        }
+    }
+    copmem_free(&x);
+    return 0;
+}
+
 /* reverseComplementInPlace semantics on a copy (helper.cpp:383-393) */
 static char *reverse_complement(const char *s, uint64_t n) {
     char *o = (char *)malloc(n + 1);
@@ -419,6 +581,7 @@ static char *reverse_complement(const char *s, uint64_t n) {
 
 /* matchConstantLengthReads / continueMatchingConstantLengthReads pass structure */
 static int one_pass(matcher *m, pat_table *t, int exact, const char *txt, int rev_mode) {
+    if (m->copmem) return copmem_pass(m, txt, rev_mode);
     if (exact) exact_pass(m, t, txt, rev_mode);
     else if (m->interleaved) return interleaved_pass(m, t, txt, rev_mode);
     else approx_pass(m, t, txt, rev_mode);
@@ -448,8 +611,8 @@ int pgo_map_reads(const char *text, uint64_t text_len,
                   uint32_t min_chars_per_mismatch, char pre_mode, char mode, int rev_compl,
                   uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgo_stats *stats) {
     if (!text || read_len == 0 || read_len > 255 || seed == 0 || min_chars_per_mismatch == 0) return -1;
-    if ((lower_mode(mode) != 'd' && lower_mode(mode) != 'i') ||
-        (pre_seed && lower_mode(pre_mode) != 'd' && lower_mode(pre_mode) != 'i')) return -1;
+    if ((lower_mode(mode) != 'd' && lower_mode(mode) != 'i' && lower_mode(mode) != 'c') ||
+        (pre_seed && lower_mode(pre_mode) != 'd' && lower_mode(pre_mode) != 'i' && lower_mode(pre_mode) != 'c')) return -1;
     pgo_stats local;
     if (!stats) stats = &local;
     memset(stats, 0, sizeof(*stats));
@@ -482,8 +645,14 @@ int pgo_map_reads(const char *text, uint64_t text_len,
 
     int rcode = 0;
     pat_table t;
-    const int first_exact = (read_len == cur_exact);
-    if (first_exact) {
+    const int first_copmem = lower_mode(cur_mode) == 'c';            /* :717-720, :732-735: CopMEM also when readLength == seed */
+    const int first_exact = (read_len == cur_exact) && !first_copmem;
+    if (first_copmem) {
+        m.copmem = 1;
+        m.part_len = cur_exact; m.parts = (uint32_t)target_mm + 1; m.max_mm = max_mm; m.min_mm = cur_min_mm;
+        stats->per_mm[PGO_NOT_MATCHED_COUNT] = n;
+        rcode = run_passes(&m, NULL, 0);
+    } else if (first_exact) {
         /* DefaultReadsExactMatcher::initMatching: whole reads as patterns (parts = 1) */
         rcode = table_build(&t, &rs, n, m.matching_len, 1, NULL, 0);
         if (rcode == 0) { stats->n_patterns = t.n; rcode = run_passes(&m, &t, 1); table_free(&t); }
@@ -507,11 +676,16 @@ int pgo_map_reads(const char *text, uint64_t text_len,
         m.parts = read_len / reads_exact; /* targetMismatches + 1 of the new matcher */
         m.max_mm = max_mm; m.min_mm = min_mm2;
         m.interleaved = lower_mode(mode) == 'i';
+        m.copmem = lower_mode(mode) == 'c';
         /* initMatchingContinuation: getMatchedReadsBitmap(minMismatches) of the previous matcher:
          * exact matcher ignores the argument (:677-683), approx matcher uses mm <= arg (:685-691) */
         uint8_t *skip = (uint8_t *)malloc(n ? n : 1);
         if (!skip) rcode = -2;
-        else {
+        else if (m.copmem) {
+            /* CopMEMReadsApproxMatcher::initMatchingContinuation only takes the results over; its pass skips mm <= minMismatches */
+            free(skip);
+            rcode = run_passes(&m, NULL, 0);
+        } else {
             for (uint32_t i = 0; i < n; i++)
                 skip[i] = first_exact ? (out_pos[i] != PGO_NOT_MATCHED_POSITION) : (out_mm[i] <= min_mm2);
             rcode = table_build(&t, &rs, n, m.part_len, m.parts, skip, m.interleaved);

@@ -49,6 +49,18 @@ CASES = [
     ("ilv_L100_prephase50_i", lambda: synth.adversarial(226, 100, n_reads=700, text_len=16000), dict(mode="i", pre_seed=50, pre_mode="i")),
     ("ilv_L255_default", lambda: synth.adversarial(227, 255, n_reads=400, text_len=24000), dict(mode="i")),
     ("ilv_c2_shape_small", lambda: synth.workload(40_000, 4_000, 150, 0.005, seed=228, n_frac=0.03, name="c2 shape"), dict(mode="i")),
+    # mode 'c' (CopMEMReadsApproxMatcher, ReadsMatchers.cpp:411-451; what the release CLI runs), reference at ONE thread:
+    # its serial index build (CopMEMMatcher.cpp:171-233) is the deterministic one
+    ("cop_L100_default", lambda: synth.adversarial(231, 100, n_reads=900, text_len=16000), dict(mode="c")),
+    ("cop_L150_default", lambda: synth.adversarial(232, 150, n_reads=900, text_len=20000), dict(mode="c")),
+    ("cop_L120_seed30", lambda: synth.adversarial(233, 120, n_reads=700, text_len=16000), dict(mode="c", seed=30)),
+    ("cop_L100_seed64", lambda: synth.adversarial(234, 100, n_reads=700, text_len=16000), dict(mode="c", seed=64)),
+    ("cop_L100_shortcut", lambda: synth.adversarial(235, 100, n_reads=700, text_len=16000), dict(mode="C")),
+    ("cop_L100_prephase50_c", lambda: synth.adversarial(236, 100, n_reads=700, text_len=16000), dict(mode="c", pre_seed=50, pre_mode="c")),
+    ("cop_L100_prephase_exact_d", lambda: synth.adversarial(237, 100, n_reads=700, text_len=16000), dict(mode="c", pre_seed=100, pre_mode="d")),
+    ("cop_L255_default", lambda: synth.adversarial(238, 255, n_reads=400, text_len=24000), dict(mode="c")),
+    ("cop_c2_shape_small", lambda: synth.workload(40_000, 4_000, 150, 0.005, seed=239, n_frac=0.03, name="c2 shape"), dict(mode="c")),
+    ("cop_c1_shape_small", lambda: synth.workload(40_000, 3_000, 100, 0.001, seed=240, name="c1 shape"), dict(mode="c")),
 ]
 
 DEFAULTS = dict(seed=38, min_chars_per_mismatch=3, mode="d", pre_seed=0, pre_mode="d", rev_compl=True)
@@ -62,7 +74,7 @@ def main():
             continue   # committed vectors are kept as they are; --all regenerates every case
         inp = make()
         p = dict(DEFAULTS); p.update(kw)
-        r = oracle.ref_map_reads(inp.text, inp.lq_reads, inp.n_reads, inp.read_len, **p)
+        r = oracle.ref_map_reads(inp.text, inp.lq_reads, inp.n_reads, inp.read_len, threads=1 if "c" in (p["mode"] + p["pre_mode"]).lower() else 0, **p)
         # layout pin (a11): the reference's own packing of these reads
         lq_packed = oracle.pack_reads(inp.lq_reads, inp.read_len, False, use_ref=True)
         n_packed = oracle.pack_reads(inp.n_reads, inp.read_len, True, use_ref=True)

@@ -34,8 +34,10 @@ def test_oracle_matches_reference_golden(name):
     # the oracle reproduces, some table-dependent ones fire in a fraction of the runs (observed: +3 in 2 of 12
     # runs on c4_shape_small; with seed length == word size 32, periodic windows such as poly-A collapse to a
     # few parity-determined hash values and the count moves by hundreds).  None of them survives verification.
+    if name.startswith("cop_"):   # CopMEM's hash is not time-seeded: its counters are deterministic
+        assert int(g["false_matches"]) == r.false_matches
     assert int(g["false_matches"]) >= r.false_matches
-    if name.startswith("c"):   # random genomes: only rare accidental extras
+    if name.startswith("c") and not name.startswith("cop_"):   # random genomes: only rare accidental extras
         assert int(g["false_matches"]) <= r.false_matches + 16
     exact_only = L == min(g["params"]["seed"], L) and g["params"]["pre_seed"] == 0
     if not exact_only:

@@ -94,3 +94,34 @@ def test_mismatch_lists_of_the_export_step(pair, mode):
             assert np.array_equal(o[s:e], (99 - f_o[s:e])[::-1]) and np.array_equal(pg[s:e], comp[f_pg[s:e]][::-1]) and np.array_equal(rd[s:e], comp[f_rd[s:e]][::-1])
         else:
             assert np.array_equal(o[s:e], f_o[s:e]) and np.array_equal(pg[s:e], f_pg[s:e]) and np.array_equal(rd[s:e], f_rd[s:e])
+
+
+def _cmp_c(inp, **kw):
+    """Mode 'c' (CopMEMReadsApproxMatcher) against the reference with ONE thread: its serial index build is the deterministic one."""
+    r = oracle.ref_map_reads(inp.text, inp.lq_reads, inp.n_reads, inp.read_len, threads=1, **kw)
+    o = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+    bad = np.nonzero((o.pos != r.pos) | (o.rc != r.rc) | (o.mm != r.mm))[0]
+    assert bad.size == 0, (inp.name, kw, bad[:5], o.pos[bad[:5]], r.pos[bad[:5]], o.mm[bad[:5]], r.mm[bad[:5]])
+    assert (o.matched, o.better, o.false_matches) == (r.matched, r.better, r.false_matches)
+    return o
+
+
+@pytest.mark.parametrize("seed,L", [(111, 100), (112, 150), (113, 120), (114, 64), (115, 255)])
+def test_copmem_mode_adversarial(seed, L):
+    o = _cmp_c(synth.adversarial(seed, L, n_reads=1500, text_len=30000), mode="c")
+    assert o.matched > 100
+
+
+@pytest.mark.parametrize("kw", [dict(mode="c", seed=30), dict(mode="c", seed=33), dict(mode="c", seed=45), dict(mode="c", seed=64),
+                                dict(mode="c", seed=100), dict(mode="C"), dict(mode="c", pre_seed=100, pre_mode="c"),
+                                dict(mode="c", pre_seed=50, pre_mode="c"), dict(mode="c", pre_seed=100, pre_mode="d"),
+                                dict(mode="d", pre_seed=50, pre_mode="c"), dict(mode="c", min_chars_per_mismatch=2),
+                                dict(mode="c", rev_compl=False), dict(mode="c", seed=24), dict(mode="c", seed=120)])
+def test_copmem_mode_parameter_matrix(kw):
+    _cmp_c(synth.adversarial(116, 100, n_reads=1200, text_len=24000), **kw)
+
+
+def test_copmem_mode_workload_shapes():
+    _cmp_c(synth.workload(100_000, 8_000, 100, 0.001, seed=117), mode="c")
+    _cmp_c(synth.workload(100_000, 12_000, 150, 0.005, seed=118, n_frac=0.02), mode="c")
+    _cmp_c(synth.workload(100_000, 12_000, 100, 0.01, seed=119), mode="c")
