@@ -154,6 +154,19 @@ int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode);
  * stats may be NULL.  Synchronizes the context's stream. */
 int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats);
 
+/* ---- matching mode 'c' ---------------------------------------------------------------------
+ * pgm_copmem_begin replaces CopMEMReadsApproxMatcher::initMatching / initMatchingContinuation
+ * (ReadsMatchers.cpp:411-419): part_len = readsExactMatchingChars (the CopMEMMatcher's target match
+ * length, from which K, k1, k2 and the hash size follow: copmem/CopMEMMatcher.cpp:71-137);
+ * continuation = 0 resets the per-read state.  pgm_copmem_pass replaces
+ * CopMEMReadsApproxMatcher::executeMatching(revCompMode) (ReadsMatchers.cpp:421-451): the index of the
+ * (reverse-complemented) text — new CopMEMMatcher(pgPtr, pgLength, partLength), SERIAL build, i.e. the
+ * reference at -t 1 (CopMEMMatcher.cpp:139-233) — and the query of every read with more than min_mm
+ * mismatches (processApproxMatchQueryTight, :483-566).  No accumulators and no resolve step: reads are
+ * independent, the per-read state is final after the pass.  Needs the whole text on this GPU. */
+int pgm_copmem_begin(pgm_ctx *ctx, uint32_t part_len, uint32_t max_mm, uint32_t min_mm, int continuation);
+int pgm_copmem_pass(pgm_ctx *ctx, int rev_mode);
+
 /* pgm_get_mismatches replaces the per-read work of AbstractReadsApproxMatcher::updateEntry
  * (ReadsMatchers.cpp:555-566: getRead + reverseComplementInPlace + fillEntryWithMismatches,
  * :40-52), i.e. what the reference's export recomputes on the host for every matched read: the
@@ -174,8 +187,9 @@ int pgm_get_mismatches(pgm_ctx *ctx, uint64_t *out_offsets, uint8_t *out_pos, ui
 
 /* ---- the whole stage on one GPU ---------------------------------------------------------
  * pgm_map_reads replaces the matching part of PgTools::mapReadsIntoPg
- * (ReadsMatchers.cpp:693-783) for matching modes 'd'/'D' (DefaultReadsApproxMatcher) and 'i'/'I'
- * (InterleavedReadsApproxMatcher): parameter derivation
+ * (ReadsMatchers.cpp:693-783) for matching modes 'd'/'D' (DefaultReadsApproxMatcher), 'i'/'I'
+ * (InterleavedReadsApproxMatcher) and 'c'/'C' (CopMEMReadsApproxMatcher, results of the reference at
+ * -t 1): parameter derivation
  * (:699-713), first matcher (:714-747), optional second phase (:749-779), same argument
  * meaning as the reference (pre_seed = preReadsExactMatchingChars, seed =
  * readsExactMatchingChars, min_chars_per_mismatch = minCharsPerMismatch, upper-case mode
@@ -195,7 +209,7 @@ uint64_t pgm_kernel_launches(const pgm_ctx *ctx);
 enum { PGM_K_PACK_TEXT = 0, PGM_K_RC_TEXT, PGM_K_UNPACK_READS, PGM_K_INIT_STATE, PGM_K_BUILD_TABLE,
        PGM_K_SCAN, PGM_K_RESOLVE, PGM_K_FINALIZE, PGM_K_ACCUM,
        PGM_K_SCAN_FILTER, PGM_K_SCAN_PROBE, PGM_K_SCAN_VERIFY, /* the three stages of the L2-blocked scan pipeline */
-       PGM_K_MISMATCHES,
+       PGM_K_MISMATCHES, PGM_K_COPMEM_INDEX, PGM_K_COPMEM_QUERY,
        PGM_K_COUNT };
 typedef struct pgm_timings {
     double ms[PGM_K_COUNT];

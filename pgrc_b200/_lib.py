@@ -21,11 +21,11 @@ STATUS_NAMES = {0: "PGM_OK", -1: "PGM_ERR_INVALID_ARG", -2: "PGM_ERR_NO_DEVICE",
 # every symbol include/pgrc_gpu_matcher.h declares
 EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pgm_set_stream", "pgm_synchronize",
            "pgm_set_text", "pgm_set_text_shard", "pgm_shard_plan", "pgm_set_reads", "pgm_match_begin", "pgm_match_begin_interleaved",
-           "pgm_scan_pass", "pgm_get_accumulators", "pgm_put_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_get_mismatches", "pgm_map_reads",
+           "pgm_scan_pass", "pgm_get_accumulators", "pgm_put_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_get_mismatches", "pgm_copmem_begin", "pgm_copmem_pass", "pgm_map_reads",
            "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings"]
 
 KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators",
-                "scan_filter", "scan_probe", "scan_verify", "mismatches"]
+                "scan_filter", "scan_probe", "scan_verify", "mismatches", "copmem_index", "copmem_query"]
 
 
 class PgmStats(ctypes.Structure):
@@ -83,6 +83,8 @@ def load() -> ctypes.CDLL:
     lib.pgm_get_results.restype = ci; lib.pgm_get_results.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PgmStats)]
     lib.pgm_get_mismatches.restype = ci
     lib.pgm_get_mismatches.argtypes = [vp, vp, vp, vp, u64, ctypes.POINTER(u64)]
+    lib.pgm_copmem_begin.restype = ci; lib.pgm_copmem_begin.argtypes = [vp, u32, u32, u32, ci]
+    lib.pgm_copmem_pass.restype = ci; lib.pgm_copmem_pass.argtypes = [vp, ci]
     lib.pgm_map_reads.restype = ci
     lib.pgm_map_reads.argtypes = [vp, u32, u32, u32, u32, ctypes.c_char, ctypes.c_char, ci, vp, vp, vp,
                                   ctypes.POINTER(PgmStats)]

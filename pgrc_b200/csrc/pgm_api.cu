@@ -4,6 +4,7 @@
 #include "../../include/pgrc_gpu_matcher.h"
 #include "pgm_kernels.cuh"
 #include "pgm_blocked.cuh"
+#include "pgm_copmem.cuh"
 
 #include <algorithm>
 #include <cctype>
@@ -83,6 +84,10 @@ struct pgm_ctx {
     DevBuf buckets, next, filter, bq_entries, bq_counters;
     DevBuf sq_pos, sq_cand, sq_counters;   // queues of the L2-blocked scan pipeline (pgm_blocked.cuh)
     DevBuf mis_sums, mis_offsets, mis_pos, mis_syms;   // mismatch lists (pgm_get_mismatches)
+    // mode 'c' (pgm_copmem.cuh): per-pass text index + parameters of the current CopMEM phase
+    DevBuf cm_count, cm_start, cm_cumm, cm_fill, cm_hash, cm_all, cm_entries, cm_sums;
+    uint32_t cm_K = 0, cm_k1 = 0, cm_k2 = 0, cm_hash_size = 0;
+    bool copmem_active = false;
     uint32_t bq_cap = 0, bq_region_bits = 0;
     bool bq_pending = false;    // region queues hold patterns that build_insert_kernel has not inserted yet
     uint64_t n_slots = 0;
@@ -540,6 +545,7 @@ void pgm_destroy(pgm_ctx *ctx) {
                       &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
                       &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter, &ctx->bq_entries, &ctx->bq_counters,
                       &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->mis_sums, &ctx->mis_offsets, &ctx->mis_pos, &ctx->mis_syms,
+                      &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
     for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1037,6 +1043,126 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
     return PGM_OK;
 }
 
+} // extern "C"
+
+namespace {
+// initParams + calcCoprimes of CopMEMMatcher (copmem/CopMEMMatcher.cpp:71-137) for targetMatchLength = L and
+// minMatchLength = L; false where the reference exits ("Minimal matching length too short", "L and K mismatch")
+bool copmem_derive(uint32_t L, uint64_t N, uint32_t &K, uint32_t &k1, uint32_t &k2, uint32_t &hash_size) {
+    int k;
+    if (L > 110) k = 56; else if (L > 62) k = 44; else if (L > 53) k = 40; else if (L > 46) k = 36;
+    else if (L > 42) k = 32; else if (L > 32) k = 28; else k = ((int)L / 4 - 1) * 4;
+    if (L < 24) return false;
+    k = std::min(k, ((int)L / 4 - 1) * 4);
+    const int t = (int)L - k + 1;
+    if (t <= 0) return false;
+    int a, b;
+    if (t >= 20) {
+        a = 1; while ((a + 1) * (a + 1) <= t) a++;          // (int) pow(t, 0.5)
+        a += 1; b = a - 1;
+        if (a * b > t) { --b; --a; }
+    } else if (t >= 15) { a = 5; b = 3; } else if (t >= 12) { a = 4; b = 3; } else if (t >= 10) { a = 5; b = 2; }
+    else if (t >= 6) { a = 3; b = 2; } else { a = t; b = 1; }
+    K = (uint32_t)k; k1 = (uint32_t)a; k2 = (uint32_t)b;
+    int i = 24;                                              // HASH_SIZE_MIN_ORDER .. HASH_SIZE_MAX_ORDER
+    do { hash_size = 1u << (i++); } while (i <= 31 && hash_size < N / (uint64_t)a);
+    return true;
+}
+
+// exclusive prefix sums out[0..n] of v[0..n) (of min(v, 13) when capped) on the context's stream
+template <uint32_t CAP>
+int device_scan(pgm_ctx *ctx, const uint32_t *v, uint32_t n, uint32_t *out) {
+    const uint32_t n_blocks = grid_for(n, PGM_CM_SCAN_BLOCK);
+    int rc;
+    if ((rc = ensure(ctx, ctx->cm_sums, ((size_t)n_blocks + 1) * 8))) return rc;
+    unsigned long long *sums = ctx->cm_sums.as<unsigned long long>();
+    KLAUNCH(PGM_K_COPMEM_INDEX, "cm_block_sums_kernel", pgm::cm_block_sums_kernel<CAP><<<n_blocks, PGM_CM_SCAN_BLOCK, 0, ctx->stream>>>(v, n, sums));
+    KLAUNCH(PGM_K_COPMEM_INDEX, "mismatch_scan_kernel", pgm::mismatch_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sums, n_blocks, sums + n_blocks));
+    KLAUNCH(PGM_K_COPMEM_INDEX, "cm_block_scan_kernel", pgm::cm_block_scan_kernel<CAP><<<n_blocks, PGM_CM_SCAN_BLOCK, 0, ctx->stream>>>(v, n, sums, out));
+    return PGM_OK;
+}
+} // namespace
+
+extern "C" {
+
+int pgm_copmem_begin(pgm_ctx *ctx, uint32_t part_len, uint32_t max_mm, uint32_t min_mm, int continuation) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->has_reads || !ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_copmem_begin: set the text and the reads first");
+    if (ctx->slice_begin != 0 || ctx->slice_len != ctx->pg_len)
+        return fail(ctx, PGM_ERR_STATE, "pgm_copmem_begin: mode 'c' needs the whole text on this GPU (not a text shard)");
+    if (max_mm > 127 || min_mm > 127) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_copmem_begin: mismatch limits must be <= 127");
+    if (part_len == 0 || part_len > ctx->read_len) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_copmem_begin: need 1 <= part_len <= read_len");
+    uint32_t K, k1, k2, hs;
+    if (!copmem_derive(part_len, ctx->pg_len, K, k1, k2, hs))
+        return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_copmem_begin: seed length below 24 (the reference exits: minimal matching length too short)");
+    if (ctx->pg_len / k1 >= 0xFFFFFFF0ull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_copmem_begin: text too long for 32-bit sample indices");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload_reads(ctx, false))) return rc;
+    ctx->cm_K = K; ctx->cm_k1 = k1; ctx->cm_k2 = k2; ctx->cm_hash_size = hs;
+    ctx->max_mm = max_mm; ctx->min_mm = min_mm;
+    ctx->outputs_valid = false;
+    ctx->phase_active = false;
+    ctx->copmem_active = true;
+    const uint32_t n = ctx->n_reads();
+    if (!continuation) {
+        CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+        if (n && !ctx->state_fresh) {
+            // DefaultReadsMatcher::initMatching + readMismatchesCount = NOT_MATCHED_COUNT (ReadsMatchers.cpp:411-415)
+            KLAUNCH(PGM_K_INIT_STATE, "reset_state_kernel", pgm::reset_state_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+                reads_view(ctx), per_read(ctx), n, 1, 1));
+            CU(cudaMemsetAsync(ctx->touched.p, 0, sizeof(int), ctx->stream));
+            ctx->aux_clean = true;
+        }
+    }
+    return PGM_OK;
+}
+
+int pgm_copmem_pass(pgm_ctx *ctx, int rev_mode) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->copmem_active) return fail(ctx, PGM_ERR_STATE, "pgm_copmem_pass: pgm_copmem_begin has not been called");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = finish_text_upload(ctx))) return rc;
+    const uint32_t n = ctx->n_reads();
+    const uint64_t N = ctx->pg_len;
+    if (!n) return PGM_OK;
+    pgm::CopmemParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.tlo = (rev_mode ? ctx->r_lo : ctx->f_lo).as<uint32_t>() + PGM_PAD_WORDS;
+    cp.thi = (rev_mode ? ctx->r_hi : ctx->f_hi).as<uint32_t>() + PGM_PAD_WORDS;
+    cp.pg_len = N;
+    cp.K = ctx->cm_K; cp.k1 = ctx->cm_k1; cp.k2 = ctx->cm_k2; cp.hash_mask = ctx->cm_hash_size - 1;
+    cp.n_sampled = N >= cp.K ? (uint32_t)((N - cp.K) / cp.k1 + 1) : 0u;
+    const size_t hs = ctx->cm_hash_size;
+    if ((rc = ensure(ctx, ctx->cm_count, (hs + 1) * 4)) || (rc = ensure(ctx, ctx->cm_start, (hs + 1) * 4)) ||
+        (rc = ensure(ctx, ctx->cm_cumm, (hs + 2) * 4)) || (rc = ensure(ctx, ctx->cm_fill, hs * 4)) ||
+        (rc = ensure(ctx, ctx->cm_hash, (size_t)std::max<uint32_t>(cp.n_sampled, 1) * 4)) ||
+        (rc = ensure(ctx, ctx->cm_all, (size_t)std::max<uint32_t>(cp.n_sampled, 1) * 4)) ||
+        (rc = ensure(ctx, ctx->cm_entries, (size_t)std::max<uint32_t>(cp.n_sampled, 1) * 4))) return rc;
+    cp.count = ctx->cm_count.as<uint32_t>(); cp.start_all = ctx->cm_start.as<uint32_t>(); cp.cumm = ctx->cm_cumm.as<uint32_t>();
+    cp.fill = ctx->cm_fill.as<uint32_t>(); cp.sample_hash = ctx->cm_hash.as<uint32_t>(); cp.all_entries = ctx->cm_all.as<uint32_t>();
+    cp.entries = ctx->cm_entries.as<uint32_t>();
+    cp.reads = reads_view(ctx); cp.n_reads = n; cp.max_mm = ctx->max_mm; cp.min_mm = ctx->min_mm; cp.rev_mode = rev_mode ? 1 : 0;
+    // the index of this pass's text: new CopMEMMatcher(pgPtr, pgLength, partLength) (ReadsMatchers.cpp:424)
+    CU(cudaMemsetAsync(cp.count, 0, (hs + 1) * 4, ctx->stream));
+    CU(cudaMemsetAsync(cp.fill, 0, hs * 4, ctx->stream));
+    if (cp.n_sampled)
+        KLAUNCH(PGM_K_COPMEM_INDEX, "cm_hash_kernel", pgm::cm_hash_kernel<<<grid_for(cp.n_sampled, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
+    if ((rc = device_scan<0>(ctx, cp.count, (uint32_t)hs, cp.start_all)) ||
+        (rc = device_scan<PGM_CM_COLLISIONS_LIMIT + 1>(ctx, cp.count, (uint32_t)hs, cp.cumm))) return rc;
+    if (cp.n_sampled) {
+        KLAUNCH(PGM_K_COPMEM_INDEX, "cm_scatter_kernel", pgm::cm_scatter_kernel<<<grid_for(cp.n_sampled, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
+        KLAUNCH(PGM_K_COPMEM_INDEX, "cm_select_kernel", pgm::cm_select_kernel<<<grid_for(hs, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
+    }
+    // every read on its own (ReadsMatchers.cpp:425-448)
+    ctx->state_fresh = false;
+    ctx->outputs_valid = false;
+    KLAUNCH(PGM_K_COPMEM_QUERY, "cm_query_kernel", pgm::cm_query_kernel<<<grid_for(n, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(
+        cp, ctx->counters.as<unsigned long long>()));
+    return PGM_OK;
+}
+
 int pgm_get_mismatches(pgm_ctx *ctx, uint64_t *out_offsets, uint8_t *out_pos, uint8_t *out_syms, uint64_t capacity, uint64_t *total) {
     if (!ctx) return PGM_ERR_INVALID_ARG;
     if (!ctx->has_reads || !ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_get_mismatches: set the text and the reads first");
@@ -1093,10 +1219,10 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
     if (match_prefix_length != PGM_DISABLED_PREFIX_MODE && match_prefix_length < L)
         return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_map_reads: prefix matching (matchPrefixLength < readLength) is not used by pgrc-encoder and not supported");
     if (seed == 0 || min_chars_per_mismatch == 0) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_map_reads: seed and min_chars_per_mismatch must be > 0");
-    auto hash_mode = [](char c) { return std::tolower(c) == 'd' || std::tolower(c) == 'i'; };
-    if (!hash_mode(mode) || (pre_seed && !hash_mode(pre_mode))) {
+    auto known_mode = [](char c) { return std::tolower(c) == 'd' || std::tolower(c) == 'i' || std::tolower(c) == 'c'; };
+    if (!known_mode(mode) || (pre_seed && !known_mode(pre_mode))) {
         // error convention of the reference: "Unknown matching mode" + exit (ReadsMatchers.cpp:737-739); here a status
-        return fail(ctx, PGM_ERR_UNSUPPORTED, std::string("pgm_map_reads: matching mode '") + mode + "' is not a hash-matcher path ('d'/'D', 'i'/'I')");
+        return fail(ctx, PGM_ERR_UNSUPPORTED, std::string("pgm_map_reads: unknown matching mode '") + mode + "' ('d'/'D', 'i'/'I', 'c'/'C')");
     }
     // ReadsMatchers.cpp:699-713
     const uint32_t max_mm = L / min_chars_per_mismatch;
@@ -1114,13 +1240,26 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
         if (rev_compl && ((r = pgm_scan_pass(ctx, 1)) || (r = resolve_impl(ctx, 1, last_phase)))) return r;
         return PGM_OK;
     };
+    auto copmem_passes = [&]() -> int {                                               // CopMEMReadsApproxMatcher::executeMatching x 2
+        int r;
+        if ((r = pgm_copmem_pass(ctx, 0))) return r;
+        if (rev_compl && (r = pgm_copmem_pass(ctx, 1))) return r;
+        return PGM_OK;
+    };
+    if (std::tolower(cur_mode) == 'c') {                                              // :717-720 / :732-735 (also when readLength == seed)
+        if ((rc = pgm_copmem_begin(ctx, cur_exact, max_mm, cur_min, 0)) || (rc = copmem_passes())) return rc;
+    } else {
     if (L == cur_exact) rc = pgm_match_begin(ctx, L, 1, 0, 0, 0);                    // DefaultReadsExactMatcher (:718-722)
     else rc = match_begin_impl(ctx, cur_exact, target_mm + 1, max_mm, cur_min, 0,    // DefaultReadsApproxMatcher (:724-727) /
                                std::tolower(cur_mode) == 'i');                        // InterleavedReadsApproxMatcher (:728-731)
     if (rc || (rc = run_passes(pre_exact == 0))) return rc;
+    }
     if (pre_exact > 0) {
         // second phase (:749-779); minMismatches comes from the FIRST phase's targetMismatches (:755)
         const uint32_t min2 = std::isupper((unsigned char)mode) ? max_mm : target_mm + 1;
+        if (std::tolower(mode) == 'c') {
+            if ((rc = pgm_copmem_begin(ctx, reads_exact, max_mm, min2, 1)) || (rc = copmem_passes())) return rc;
+        } else
         if ((rc = match_begin_impl(ctx, reads_exact, L / reads_exact, max_mm, min2, 1, std::tolower(mode) == 'i')) || (rc = run_passes(true))) return rc;
     }
     return pgm_get_results(ctx, out_pos, out_rc, out_mm, stats);

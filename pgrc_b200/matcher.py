@@ -157,6 +157,14 @@ class GpuReadsMatcher:
     def resolve_pass(self, rev_mode: bool):
         self._check(self._lib.pgm_resolve_pass(self._h, int(rev_mode)))
 
+    def copmem_begin(self, part_len: int, max_mm: int, min_mm: int, continuation: bool = False):
+        """CopMEMReadsApproxMatcher::initMatching / initMatchingContinuation (mode 'c')."""
+        self._check(self._lib.pgm_copmem_begin(self._h, part_len, max_mm, min_mm, int(continuation)))
+
+    def copmem_pass(self, rev_mode: bool):
+        """CopMEMReadsApproxMatcher::executeMatching: index of the (RC) text + the query of every read."""
+        self._check(self._lib.pgm_copmem_pass(self._h, int(rev_mode)))
+
     def accumulators(self):
         """torch views (no copy) of the per-read accumulators of the current pass."""
         import torch
@@ -241,8 +249,8 @@ class MatchPlan:
     @staticmethod
     def derive(read_len: int, seed: int, min_chars_per_mismatch: int, mode: str, pre_seed: int = 0,
                pre_mode: str = "d") -> "MatchPlan":
-        if mode.lower() not in "di" or (pre_seed and pre_mode.lower() not in "di") or len(mode) != 1 or len(pre_mode) != 1:
-            raise PgmError(-6, f"matching mode '{mode}' is not a hash-matcher path ('d'/'D', 'i'/'I')")
+        if len(mode) != 1 or len(pre_mode) != 1 or mode.lower() not in "dic" or (pre_seed and pre_mode.lower() not in "dic"):
+            raise PgmError(-6, f"unknown matching mode '{mode}' ('d'/'D', 'i'/'I', 'c'/'C')")
         if seed <= 0 or min_chars_per_mismatch <= 0:
             raise PgmError(-1, "seed and min_chars_per_mismatch must be > 0")
         L = read_len
@@ -252,11 +260,16 @@ class MatchPlan:
         cur_min = max_mm if cur_mode.isupper() else 0
         target_mm = L // cur_exact - 1
         ilv = lambda c, parts: c.lower() == "i" and parts > 1   # InterleavedReadsApproxMatcher (:728-731, :760-763)
-        phases = ([(L, 1, 0, 0, False, False)] if L == cur_exact
-                  else [(cur_exact, target_mm + 1, max_mm, cur_min, False, ilv(cur_mode, target_mm + 1))])
+        # mode 'c' (CopMEMReadsApproxMatcher, also when readLength == seed: :717-720) has no seed table: its phases carry
+        # the marker "c" in place of the interleaved flag and run through pgm_copmem_begin / pgm_copmem_pass
+        if cur_mode.lower() == "c":
+            phases = [(cur_exact, target_mm + 1, max_mm, cur_min, False, "c")]
+        else:
+            phases = ([(L, 1, 0, 0, False, False)] if L == cur_exact
+                      else [(cur_exact, target_mm + 1, max_mm, cur_min, False, ilv(cur_mode, target_mm + 1))])
         if pre_exact > 0:
             min2 = max_mm if mode.isupper() else target_mm + 1
-            phases.append((reads_exact, L // reads_exact, max_mm, min2, True, ilv(mode, L // reads_exact)))
+            phases.append((reads_exact, L // reads_exact, max_mm, min2, True, "c" if mode.lower() == "c" else ilv(mode, L // reads_exact)))
         return MatchPlan(phases)
 
 
@@ -341,6 +354,8 @@ def run_plan_sharded(m: GpuReadsMatcher, plan: MatchPlan, rev_compl_pg: bool = T
     per-read accumulators are merged across ranks, then every rank applies the decision, so the
     per-read state stays replicated."""
     for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
+        if ilv == "c":
+            raise PgmError(-6, "matching mode 'c' indexes the whole text: it shards by reads only (no text shards)")
         m.match_begin(seed_len, parts, max_mm, min_mm, cont, ilv)
         for rev in ((False, True) if rev_compl_pg else (False,)):
             m.scan_pass(rev)

@@ -103,7 +103,8 @@ def test_unsupported_modes_fail_loudly():
     rng = np.random.default_rng(7)
     g = synth.random_genome(4000, rng)
     reads = synth.sample_reads(g, 10, 100, 0.01, rng)
-    for kw in (dict(matching_mode="c"), dict(matching_mode="x"), dict(match_prefix_length=50)):
+    for kw in (dict(matching_mode="x"), dict(matching_mode="d", pre_reads_exact_matching_chars=50, pre_matching_mode="q"),
+               dict(match_prefix_length=50), dict(matching_mode="c", reads_exact_matching_chars=20)):   # (CopMEM: seed < 24)
         with pytest.raises(matcher.PgmError) as e:
             matcher.map_reads_into_pg(g, synth.pack_reads(reads), None, 100, **kw)
         assert e.value.status == -6
@@ -348,3 +349,51 @@ def test_paired_filter_lookups_forced_on_and_off(monkeypatch, pair):
         assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)
     monkeypatch.setenv("PGM_BLOCKED_SCAN", "2")
     _check(synth.adversarial(108, 100))
+
+
+@pytest.mark.parametrize("seed,L", [(121, 100), (122, 150), (123, 120), (124, 64), (125, 255)])
+def test_copmem_mode_adversarial(seed, L):
+    """Mode 'c' (CopMEMReadsApproxMatcher, what the release CLI runs): text index + per-read query, the reference's results at -t 1."""
+    got, want = _check(synth.adversarial(seed, L), matching_mode="c")
+    assert want.matched > 50
+
+
+@pytest.mark.parametrize("kw", [
+    dict(matching_mode="c", reads_exact_matching_chars=30),
+    dict(matching_mode="c", reads_exact_matching_chars=33),
+    dict(matching_mode="c", reads_exact_matching_chars=45),
+    dict(matching_mode="c", reads_exact_matching_chars=64),
+    dict(matching_mode="c", reads_exact_matching_chars=100),
+    dict(matching_mode="c", reads_exact_matching_chars=24),
+    dict(matching_mode="C"),
+    dict(matching_mode="c", pre_reads_exact_matching_chars=100, pre_matching_mode="c"),
+    dict(matching_mode="c", pre_reads_exact_matching_chars=50, pre_matching_mode="c"),
+    dict(matching_mode="c", pre_reads_exact_matching_chars=100, pre_matching_mode="d"),
+    dict(matching_mode="d", pre_reads_exact_matching_chars=50, pre_matching_mode="c"),
+    dict(matching_mode="i", pre_reads_exact_matching_chars=50, pre_matching_mode="c"),
+    dict(matching_mode="c", min_chars_per_mismatch=2),
+    dict(matching_mode="c", rev_compl_pg=False),
+])
+def test_copmem_mode_parameter_matrix(kw):
+    for s in (126, 127):
+        _check(synth.adversarial(s, 100), **kw)
+
+
+def test_copmem_mode_workloads_and_edges():
+    _check(synth.workload(250_000, 20_000, 100, 0.001, seed=128, name="c1/20"), matching_mode="c")
+    _check(synth.workload(500_000, 100_000, 150, 0.005, seed=129, n_frac=0.02, name="c2/100"), matching_mode="c")
+    _check(synth.workload(400_000, 60_000, 100, 0.01, seed=130, name="c4 scaled"), matching_mode="c")
+    rng = np.random.default_rng(131)
+    g = synth.random_genome(5000, rng)
+    reads = synth.sample_reads(g, 300, 100, 0.01, rng)
+    for text in (g[:99], g[:27], g[:28], g[:100], g[:101], g[:130]):       # around K = 28 and the read length
+        _check(synth.MatcherInputs(np.ascontiguousarray(text), reads, np.zeros((0, 100), np.uint8), 100, f"text{len(text)}"), matching_mode="c")
+    _check(synth.MatcherInputs(g, np.zeros((0, 100), np.uint8), synth.inject_n(reads[:50], rng), 100, "only N reads"), matching_mode="c")
+    # hot seeds: more than 13 text positions per hash value (bucket cap) and the false-match budget
+    dup = np.repeat(reads[:10], 40, axis=0)
+    text = np.concatenate([g[:1500], np.full(3000, ord("A"), np.uint8), g[1500:3000], np.tile(g[200:420], 30)])
+    areads = np.full((200, 100), ord("A"), np.uint8)
+    areads[np.arange(200), rng.integers(0, 100, 200)] = ord("C")
+    rep = synth.sample_reads(np.tile(g[200:420], 3), 300, 100, 0.02, rng)
+    inp = synth.MatcherInputs(np.ascontiguousarray(text), np.concatenate([dup, areads, rep]), np.zeros((0, 100), np.uint8), 100, "hot")
+    _check(inp, matching_mode="c")

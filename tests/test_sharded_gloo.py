@@ -76,7 +76,10 @@ def test_match_plan_mirrors_reference_parameter_derivation():
     assert MatchPlan.derive(100, 100, 3, "i").phases == [(100, 1, 0, 0, F, F)]
     assert MatchPlan.derive(100, 38, 3, "I", pre_seed=50, pre_mode="d").phases == [(50, 2, 33, 0, F, F), (38, 2, 33, 33, True, True)]
     assert MatchPlan.derive(100, 38, 3, "d", pre_seed=50, pre_mode="i").phases == [(50, 2, 33, 0, F, True), (38, 2, 33, 2, True, F)]
-    for bad in ("c", "x"):
+    assert MatchPlan.derive(100, 38, 3, "c").phases == [(38, 2, 33, 0, F, "c")]
+    assert MatchPlan.derive(100, 100, 3, "c").phases == [(100, 1, 33, 0, F, "c")]
+    assert MatchPlan.derive(100, 38, 3, "c", pre_seed=50, pre_mode="d").phases == [(50, 2, 33, 0, F, F), (38, 2, 33, 2, True, "c")]
+    for bad in ("x", "dd"):
         with pytest.raises(PgmError):
             MatchPlan.derive(100, 38, 3, bad)
 
