@@ -124,6 +124,14 @@ namespace PgTools {
             check(pgm_match_begin(ctx, seedLength, parts, maxMismatches, minMismatches, continuation ? 1 : 0), ctx, "pgm_match_begin");
     }
 
+    void GpuMatcherSession::beginCopmem(uint32_t partLength, uint32_t maxMismatches, uint32_t minMismatches, bool continuation) {
+        check(pgm_copmem_begin(ctx, partLength, maxMismatches, minMismatches, continuation ? 1 : 0), ctx, "pgm_copmem_begin");
+    }
+
+    void GpuMatcherSession::passCopmem(bool revCompMode) {
+        check(pgm_copmem_pass(ctx, revCompMode ? 1 : 0), ctx, "pgm_copmem_pass");
+    }
+
     void GpuMatcherSession::pass(bool revCompMode) {
         check(pgm_scan_pass(ctx, revCompMode ? 1 : 0), ctx, "pgm_scan_pass");
         check(pgm_resolve_pass(ctx, revCompMode ? 1 : 0), ctx, "pgm_resolve_pass");
@@ -176,29 +184,32 @@ namespace PgTools {
     GpuReadsApproxMatcher::GpuReadsApproxMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
                                                  ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength,
                                                  uint16_t readsExactMatchingChars, uint8_t maxMismatches, uint8_t minMismatches,
-                                                 bool interleaved)
+                                                 bool interleaved, bool copmem)
             : AbstractReadsApproxMatcher(pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength, readsExactMatchingChars,
                                          maxMismatches, minMismatches), session(session), partLength(readsExactMatchingChars),
-              interleaved(interleaved) {}
+              interleaved(interleaved), copmem(copmem) {}
 
     void GpuReadsApproxMatcher::initMatching() {                                   // replaces ReadsMatchers.cpp:276-285
         DefaultReadsMatcher::initMatching();
         readMismatchesCount.clear();
         readMismatchesCount.insert(readMismatchesCount.end(), readsCount, NOT_MATCHED_COUNT);
-        session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, false, interleaved);
+        if (copmem) session->beginCopmem(partLength, maxMismatches, minMismatches, false);   // replaces ReadsMatchers.cpp:411-415
+        else session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, false, interleaved);
     }
 
     void GpuReadsApproxMatcher::initMatchingContinuation(DefaultReadsMatcher *pMatcher) {   // replaces :287-295
         // the device still holds the first phase's per-read state; reads matched with <= minMismatches are left
         // out of the new table there (getMatchedReadsBitmap(minMismatches), ReadsMatchers.cpp:290-291)
         AbstractReadsApproxMatcher::initMatchingContinuation(pMatcher);
-        session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, true, interleaved);
+        if (copmem) session->beginCopmem(partLength, maxMismatches, minMismatches, true);    // replaces ReadsMatchers.cpp:417-419
+        else session->begin(partLength, targetMismatches + 1, maxMismatches, minMismatches, true, interleaved);
     }
 
     void GpuReadsApproxMatcher::executeMatching(bool revCompMode) {                // replaces ReadsMatchers.cpp:297-341
         time_checkpoint();
         cout << "Matching" << (revCompMode ? " in Pg reverse" : "") << " (GPU)...\n" << endl;
-        session->pass(revCompMode);
+        if (copmem) session->passCopmem(revCompMode);                             // replaces ReadsMatchers.cpp:421-451
+        else session->pass(revCompMode);
         if (revCompMode == revComplPg)                                             // last pass of this matcher
             session->fetch(readMatchPos, readMatchRC, &readMismatchesCount, matchedReadsCount, matchedCountPerMismatches);
         printApproxMatchingStats();
@@ -264,11 +275,12 @@ namespace PgTools {
 
         GpuMatcherSession session(pgPtr, pgLength, readsSet);
         DefaultReadsMatcher *matcher;
-        if (readLength == firstSeed)
+        if (readLength == firstSeed && tolower(firstMode) != 'c')                  // (mode 'c' uses CopMEM here too, :717-720)
             matcher = new GpuReadsExactMatcher(&session, pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength);
         else
             matcher = new GpuReadsApproxMatcher(&session, pgPtr, pgLength, revComplPg, readsSet, matchPrefixLength,
-                                                firstSeed, maxMismatches, firstMinMismatches, tolower(firstMode) == 'i');
+                                                firstSeed, maxMismatches, firstMinMismatches, tolower(firstMode) == 'i',
+                                                tolower(firstMode) == 'c');
         cout << "Target pseudogenome length: " << pgLength << endl;
         *logout << endl;
         cout << "readsAlignmentSeedLength (minCharsPerMismatch, matchingMode): " << (int) firstSeed <<
@@ -280,7 +292,8 @@ namespace PgTools {
         if (twoPhases) {
             const uint8_t secondMinMismatches = isupper((unsigned char) matchingMode) ? maxMismatches : targetMismatches + 1;
             AbstractReadsApproxMatcher *approxMatcher = new GpuReadsApproxMatcher(&session, pgPtr, pgLength, revComplPg, readsSet,
-                    matchPrefixLength, readsExactMatchingChars, maxMismatches, secondMinMismatches, tolower(matchingMode) == 'i');
+                    matchPrefixLength, readsExactMatchingChars, maxMismatches, secondMinMismatches, tolower(matchingMode) == 'i',
+                    tolower(matchingMode) == 'c');
             targetMismatches = readLength / readsExactMatchingChars - 1;
             cout << endl << "Reads matching 2nd PHASE." << endl;
             cout << "readsExactMatchingChars (minCharsPerMismatch, matchingMode): " << (int) readsExactMatchingChars <<
@@ -319,7 +332,7 @@ namespace PgTools {
             readsSet->getReadsSetProperties()->readsCount = readsSet->readsCount();
         const char *env = getenv("PGRC_GPU_MATCHER");
         const bool wantGpu = env && *env && strcmp(env, "0") != 0;
-        auto hashMode = [](char c) { return tolower(c) == 'd' || tolower(c) == 'i'; };
+        auto hashMode = [](char c) { return tolower(c) == 'd' || tolower(c) == 'i' || tolower(c) == 'c'; };   // (c: the -t 1 results)
         const bool hashMatcherPath = hashMode(matchingMode) && (preReadsExactMatchingChars == 0 || hashMode(preMatchingMode))
                                      && matchPrefixLength == DefaultReadsMatcher::DISABLED_PREFIX_MODE;
         if (wantGpu && hashMatcherPath)

@@ -30,6 +30,9 @@ namespace PgTools {
         void begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation,
                    bool interleaved = false);
         void pass(bool revCompMode);
+        // mode 'c' (CopMEMReadsApproxMatcher): no seed table; a pass = text index + per-read queries
+        void beginCopmem(uint32_t partLength, uint32_t maxMismatches, uint32_t minMismatches, bool continuation);
+        void passCopmem(bool revCompMode);
         // copies the per-read results into the reference's member vectors
         void fetch(vector<uint64_t> &readMatchPos, vector<bool> &readMatchRC, vector<uint8_t> *readMismatchesCount,
                    uint_reads_cnt_max &matchedReadsCount, uint_reads_cnt_max *matchedCountPerMismatches);
@@ -53,6 +56,7 @@ namespace PgTools {
         GpuMatcherSession *session;
         uint_read_len_max partLength;
         bool interleaved;
+        bool copmem;       // stands in for CopMEMReadsApproxMatcher (mode 'c', ReadsMatchers.h:167-185, .cpp:411-451; results of -t 1)
     protected:
         void initMatching() override;
         void initMatchingContinuation(DefaultReadsMatcher *pMatcher) override;
@@ -70,10 +74,10 @@ namespace PgTools {
         GpuReadsApproxMatcher(GpuMatcherSession *session, char *pgPtr, const uint_pg_len_max pgLength, bool revComplPg,
                               ConstantLengthReadsSetInterface *readsSet, uint32_t matchPrefixLength,
                               uint16_t readsExactMatchingChars, uint8_t maxMismatches, uint8_t minMismatches = 0,
-                              bool interleaved = false);
+                              bool interleaved = false, bool copmem = false);
     };
 
-    // Same signature as PgTools::mapReadsIntoPg (ReadsMatchers.h:202-207).  Matching modes 'd'/'D' and 'i'/'I' run on the GPU when
+    // Same signature as PgTools::mapReadsIntoPg (ReadsMatchers.h:202-207).  Matching modes 'd'/'D', 'i'/'I' and 'c'/'C' run on the GPU when
     // the environment variable PGRC_GPU_MATCHER is set to something other than 0; every other case is passed on
     // to the reference's own function.
     const vector<bool> mapReadsIntoPgOnGpu(SeparatedPseudoGenome *sPg, bool revComplPg, bool preserveOrderMode,

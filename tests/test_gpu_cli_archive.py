@@ -1,6 +1,6 @@
 """GPU, end to end through the reference's own CLI: `PgRC-dev` built from the unmodified reference sources with the C++
 shim of pgrc_b200/host/ (oracle/Makefile target `cli`) compresses the same synthetic FASTQ twice — once with the
-reference's CPU hash matchers (mode d or i), once with the GPU matchers behind the same class interface
+reference's CPU matchers (mode d, i or c), once with the GPU matchers behind the same class interface
 (PGRC_GPU_MATCHER=1) — and the two .pgrc archives must be byte-identical, for every archive mode of BASELINE.json's
 configs (SE, SE_ORD, PE, PE_ORD) and for the two-phase / exact / shortcut parameterisations."""
 import os
@@ -56,6 +56,12 @@ CASES = {
     "SE_ORD_ilv_150bp": dict(pair=False, flags=["-o", "-s", "i38"], gen=dict(genome=200_000, reads=40_000, len=150, err=0.005, n_frac=0.01, seed=10)),
     "PE_ilv_150bp": dict(pair=True, flags=["-s", "i38"], gen=dict(genome=200_000, reads=20_000, len=150, err=0.005, seed=11)),
     "SE_ilv_two_phase": dict(pair=False, flags=["-l", "i50", "-s", "i33"], gen=dict(genome=200_000, reads=40_000, len=100, err=0.01, seed=12)),
+    # mode 'c' (CopMEMReadsApproxMatcher) — what the CLI runs when no mode is given; -t 1: the reference's serial index build
+    "SE_default_cli": dict(pair=False, flags=[], gen=dict(genome=300_000, reads=60_000, len=100, err=0.005, n_frac=0.01, seed=13)),
+    "SE_ORD_copmem_150bp": dict(pair=False, flags=["-o", "-s", "c38"], gen=dict(genome=200_000, reads=40_000, len=150, err=0.005, n_frac=0.01, seed=14)),
+    "PE_copmem_150bp": dict(pair=True, flags=["-s", "c38"], gen=dict(genome=200_000, reads=20_000, len=150, err=0.005, seed=15)),
+    "PE_ORD_default_cli": dict(pair=True, flags=["-o"], gen=dict(genome=200_000, reads=20_000, len=150, err=0.005, n_frac=0.005, seed=16)),
+    "SE_copmem_two_phase": dict(pair=False, flags=["-l", "c50", "-s", "c33"], gen=dict(genome=200_000, reads=40_000, len=100, err=0.01, seed=17)),
 }
 
 
