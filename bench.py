@@ -46,8 +46,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale genome and read count (testing)")
-    ap.add_argument("--mode", default="d", choices=["d", "i"], help="matching mode: d = contiguous seeds (the headline), "
-                    "i = interleaved seeds (InterleavedReadsApproxMatcher, SURVEY §8(f) row 3)")
+    ap.add_argument("--mode", default="d", choices=["d", "i", "c"], help="matching mode: d = contiguous seeds (the headline), "
+                    "i = interleaved seeds (InterleavedReadsApproxMatcher, SURVEY §8(f) rank 3), "
+                    "c = CopMEM (CopMEMReadsApproxMatcher, what the release CLI runs; §8(f) rank 1)")
     ap.add_argument("--shard", default="auto", choices=["auto", "text", "reads", "2d"],
                     help="multi-GPU partitioning: text ranges + NCCL min-merge of the per-read keys, read ranges (no collective), or "
                          "2d = --text-shards T text ranges x N/T read groups (merge inside each group of T ranks); auto = reads, "
@@ -157,7 +158,12 @@ def cpu_baseline(args) -> dict:
     frac = args.cpu_sample
     shape = f"{args.workload} shape x {args.scale * frac:g} (genome, reads scaled; same read length, error rate, coverage)"
     if oracle.have_ref():
-        v, info = run_reference_cpu(args, frac, args.mode, 1)
+        cores = (os.cpu_count() or 1) if args.mode == "c" else 1       # mode c is the reference's one multithreaded matcher
+        v, info = run_reference_cpu(args, frac, args.mode, cores)
+        if args.mode == "c":
+            return {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "reference",
+                    "sample": f"{shape}: {info['reads']} reads vs {info['text_bases']} bases, {info['seconds']} s, reference mode c "
+                              f"(CopMEMReadsApproxMatcher, {cores} threads)"}
         return {"value": round(v, 1), "unit": UNIT, "cores": 1, "kind": "reference",
                 "sample": f"{shape}: {info['reads']} reads vs {info['text_bases']} bases, {info['seconds']} s, reference mode {args.mode} "
                           f"({'DefaultReadsApproxMatcher' if args.mode == 'd' else 'InterleavedReadsApproxMatcher'}, single-threaded by construction)"}
@@ -386,14 +392,24 @@ def ours(args):
     # a scan pass = one launch of the fused scan kernel, or the three stage kernels of the L2-blocked pipeline (+ the
     # fused kernel's no-op fallback launch); per-pass time = everything the pass launched
     blocked = tm["scan_filter"][1] > 0
+    copmem = tm["copmem_query"][1] > 0
     scan_ms = tm["scan"][0] + tm["scan_filter"][0] + tm["scan_probe"][0] + tm["scan_verify"][0]
     scan_launches = tm["scan_filter"][1] if blocked else tm["scan"][1]
+    if copmem:      # mode c: a pass = the text index (hash, scans, scatter, select) + the per-read query kernel
+        scan_ms = tm["copmem_index"][0] + tm["copmem_query"][0]
+        scan_launches = tm["copmem_query"][1]
     cand_per_launch = st["candidates"] / max(1, len(plan.phases) * 2)
     packed_len = lq_d.shape[1]
     my_pg = my_text_d.numel()
     # algorithmic bytes of ONE scan launch: 2-bit text once + packed read per candidate
     # + one 8-byte table slot per inserted pattern + one 8-byte key per read
     b_alg = my_pg / 4 + cand_per_launch * packed_len + 8 * st["patterns_inserted"] + 8 * n_mine
+    if copmem:
+        # mode c, one pass: 2-bit text once for the index + 4 bytes per sampled position written and read, the packed read
+        # once, 8 bytes of bucket bounds per query offset, and per verified candidate its 4-byte entry + the text window
+        K, k1, k2 = 28, 5, 2                                   # CopMEMMatcher parameters at seed 38 (CopMEMMatcher.cpp:71-137)
+        lookups = n_mine * ((L - K) // k2 + 1)
+        b_alg = my_pg / 4 + 2 * 4 * (my_pg / k1) + n_mine * packed_len + 8 * lookups + cand_per_launch * (4 + packed_len) + 8 * n_mine
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -402,12 +418,13 @@ def ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json"))).get((args.workload + ("_blocked" if blocked else "")) if args.scale == 1.0 else "", None)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json"))).get((args.workload + ("_blocked" if blocked else "") + ("_mode_c" if copmem else "")) if args.scale == 1.0 else "", None)
     except OSError:
         pass
     achieved = b_alg / (scan_ms / max(1, scan_launches) * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     traffic_gbs = traffic / (scan_ms / max(1, scan_launches) * 1e-3) / 1e9 if (traffic and scan_ms > 0 and world == 1) else None
-    roofline = {"bound": "hbm", "kernel": "scan pass: scan_kernel<filter stage> + probe_kernel + verify_kernel" if blocked else "scan_kernel", "achieved": round(achieved, 2), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "copmem pass: index kernels + cm_query_kernel" if copmem else
+                ("scan pass: scan_kernel<filter stage> + probe_kernel + verify_kernel" if blocked else "scan_kernel"), "achieved": round(achieved, 2), "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)", "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": traffic if world == 1 else None,
                 "traffic_gbs": round(traffic_gbs, 1) if traffic_gbs else None,

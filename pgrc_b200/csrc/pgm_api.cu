@@ -1136,17 +1136,16 @@ int pgm_copmem_pass(pgm_ctx *ctx, int rev_mode) {
     cp.n_sampled = N >= cp.K ? (uint32_t)((N - cp.K) / cp.k1 + 1) : 0u;
     const size_t hs = ctx->cm_hash_size;
     if ((rc = ensure(ctx, ctx->cm_count, (hs + 1) * 4)) || (rc = ensure(ctx, ctx->cm_start, (hs + 1) * 4)) ||
-        (rc = ensure(ctx, ctx->cm_cumm, (hs + 2) * 4)) || (rc = ensure(ctx, ctx->cm_fill, hs * 4)) ||
+        (rc = ensure(ctx, ctx->cm_cumm, (hs + 2) * 4)) || (rc = ensure(ctx, ctx->cm_fill, (size_t)std::max<uint32_t>(cp.n_sampled, 1) * 4)) ||
         (rc = ensure(ctx, ctx->cm_hash, (size_t)std::max<uint32_t>(cp.n_sampled, 1) * 4)) ||
         (rc = ensure(ctx, ctx->cm_all, (size_t)std::max<uint32_t>(cp.n_sampled, 1) * 4)) ||
         (rc = ensure(ctx, ctx->cm_entries, (size_t)std::max<uint32_t>(cp.n_sampled, 1) * 4))) return rc;
     cp.count = ctx->cm_count.as<uint32_t>(); cp.start_all = ctx->cm_start.as<uint32_t>(); cp.cumm = ctx->cm_cumm.as<uint32_t>();
-    cp.fill = ctx->cm_fill.as<uint32_t>(); cp.sample_hash = ctx->cm_hash.as<uint32_t>(); cp.all_entries = ctx->cm_all.as<uint32_t>();
+    cp.sample_rank = ctx->cm_fill.as<uint32_t>(); cp.sample_hash = ctx->cm_hash.as<uint32_t>(); cp.all_entries = ctx->cm_all.as<uint32_t>();
     cp.entries = ctx->cm_entries.as<uint32_t>();
     cp.reads = reads_view(ctx); cp.n_reads = n; cp.max_mm = ctx->max_mm; cp.min_mm = ctx->min_mm; cp.rev_mode = rev_mode ? 1 : 0;
     // the index of this pass's text: new CopMEMMatcher(pgPtr, pgLength, partLength) (ReadsMatchers.cpp:424)
     CU(cudaMemsetAsync(cp.count, 0, (hs + 1) * 4, ctx->stream));
-    CU(cudaMemsetAsync(cp.fill, 0, hs * 4, ctx->stream));
     if (cp.n_sampled)
         KLAUNCH(PGM_K_COPMEM_INDEX, "cm_hash_kernel", pgm::cm_hash_kernel<<<grid_for(cp.n_sampled, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
     if ((rc = device_scan<0>(ctx, cp.count, (uint32_t)hs, cp.start_all)) ||

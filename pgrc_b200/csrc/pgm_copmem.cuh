@@ -31,7 +31,7 @@ struct CopmemParams {
     uint32_t *count;                // [hash_size + 1] entries per hash value (all of them)
     uint32_t *start_all;            // [hash_size + 1] exclusive prefix of count
     uint32_t *cumm;                 // [hash_size + 1] exclusive prefix of min(count, 13): bucket h = [cumm[h], cumm[h+1])
-    uint32_t *fill;                 // [hash_size]
+    uint32_t *sample_rank;          // [n_sampled] arrival rank of the sample among those with its hash value
     uint32_t *sample_hash;          // [n_sampled]
     uint32_t *all_entries;          // [n_sampled] sample indices, full buckets, unordered
     uint32_t *entries;              // kept sample indices (position = index * k1), ascending inside a bucket
@@ -53,13 +53,14 @@ __device__ __forceinline__ uint32_t cm_ascii4(uint32_t lo4, uint32_t hi4) {
 }
 
 // maRushPrime1HashSparsified<K> (Hashes.h:54-76) of K characters given as bit strings (character t at bit t):
-// K / 4 little-endian words, the first three masked to 3 characters, the others to 2; `n` marks 'N' characters (reads only)
-__device__ __forceinline__ uint32_t cm_hash(uint32_t K, uint64_t lo, uint64_t hi, uint64_t n, uint32_t hash_mask) {
+// K / 4 little-endian words, the first three masked to 3 characters, the others to 2; `n` marks 'N' characters (reads only).
+// lut[lo nibble | hi nibble << 4] = the four ASCII characters of four codes (256 entries, shared memory).
+__device__ __forceinline__ uint32_t cm_hash(uint32_t K, uint64_t lo, uint64_t hi, uint64_t n, uint32_t hash_mask, const uint32_t *lut) {
     unsigned long long hash = K;
     const uint32_t words = K >> 2;
     for (uint32_t j = 0; j < words; j++) {
         const uint32_t sh = 4 * j;
-        uint32_t k = cm_ascii4((uint32_t)(lo >> sh) & 0xFu, (uint32_t)(hi >> sh) & 0xFu);
+        uint32_t k = lut[((uint32_t)(lo >> sh) & 0xFu) | (((uint32_t)(hi >> sh) & 0xFu) << 4)];
         const uint32_t nn = (uint32_t)(n >> sh) & 0xFu;
         if (nn) {
 #pragma unroll
@@ -74,6 +75,11 @@ __device__ __forceinline__ uint32_t cm_hash(uint32_t K, uint64_t lo, uint64_t hi
     return (uint32_t)hash & hash_mask;
 }
 
+__device__ __forceinline__ void cm_build_lut(uint32_t *lut) {      // by a block of >= 256 threads, followed by a barrier
+    if (threadIdx.x < 256) lut[threadIdx.x] = cm_ascii4(threadIdx.x & 15u, threadIdx.x >> 4);
+    __syncthreads();
+}
+
 // bits [x, x + 64) of a plane (words beyond the data are zero pad / tail)
 __device__ __forceinline__ uint64_t cm_bits64(const uint32_t *plane, uint64_t x) {
     const uint64_t w = x >> 5;
@@ -83,12 +89,14 @@ __device__ __forceinline__ uint64_t cm_bits64(const uint32_t *plane, uint64_t x)
 }
 
 __global__ void __launch_bounds__(PGM_CM_THREADS) cm_hash_kernel(const __grid_constant__ CopmemParams p) {
+    __shared__ uint32_t lut[256];
+    cm_build_lut(lut);
     const uint32_t s = blockIdx.x * PGM_CM_THREADS + threadIdx.x;
     if (s >= p.n_sampled) return;
     const uint64_t x = (uint64_t)s * p.k1;
-    const uint32_t h = cm_hash(p.K, cm_bits64(p.tlo, x), cm_bits64(p.thi, x), 0ull, p.hash_mask);
+    const uint32_t h = cm_hash(p.K, cm_bits64(p.tlo, x), cm_bits64(p.thi, x), 0ull, p.hash_mask, lut);
     p.sample_hash[s] = h;
-    atomicAdd(p.count + h, 1u);
+    p.sample_rank[s] = atomicAdd(p.count + h, 1u);
 }
 
 // exclusive prefix sums of a uint32 array in three steps (sums of 1024-element blocks, scan of those — mismatch_scan_kernel —,
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(PGM_CM_THREADS) cm_scatter_kernel(const __grid
     const uint32_t s = blockIdx.x * PGM_CM_THREADS + threadIdx.x;
     if (s >= p.n_sampled) return;
     const uint32_t h = p.sample_hash[s];
-    p.all_entries[p.start_all[h] + atomicAdd(p.fill + h, 1u)] = s;
+    p.all_entries[p.start_all[h] + p.sample_rank[s]] = s;
 }
 
 // per hash value: the min(count, 13) smallest sample indices of its full bucket, ascending (= the first in text order, what
@@ -162,7 +170,9 @@ __global__ void __launch_bounds__(PGM_CM_THREADS) cm_select_kernel(const __grid_
 
 // processApproxMatchQueryTight (CopMEMMatcher.cpp:483-566) + the per-read part of CopMEMReadsApproxMatcher::executeMatching
 // (ReadsMatchers.cpp:427-448), one thread per read; the read's state in its record is updated in place.
-__global__ void __launch_bounds__(PGM_CM_THREADS) cm_query_kernel(const __grid_constant__ CopmemParams p, unsigned long long *counters) {
+__global__ void __launch_bounds__(PGM_CM_THREADS, 4) cm_query_kernel(const __grid_constant__ CopmemParams p, unsigned long long *counters) {
+    __shared__ uint32_t lut[256];
+    cm_build_lut(lut);
     const uint32_t r = blockIdx.x * PGM_CM_THREADS + threadIdx.x;
     if (r >= p.n_reads) return;
     uint32_t stride16; bool is_n;
@@ -172,13 +182,15 @@ __global__ void __launch_bounds__(PGM_CM_THREADS) cm_query_kernel(const __grid_c
     const uint32_t mm0 = (uint32_t)(st >> 56);
     if (mm0 <= p.min_mm) return;                                        // ReadsMatchers.cpp:429
     const uint32_t N2 = p.reads.read_len, W = p.reads.W, K = p.K;
-    // the read's planes (8 words each at most: read length <= 255); zero beyond the read
-    uint32_t rl[9], rh[9], rn[9];
+    // the read's planes in registers (8 words each at most: read length <= 255; every index below is static); zero beyond the read
+    uint32_t rl[10], rh[10], rn[10];
 #pragma unroll
-    for (int g = 0; g < 9; g++) { rl[g] = 0; rh[g] = 0; rn[g] = 0; }
-    for (uint32_t g = 0; g < W; g++) {
-        if (is_n) { const uint4 v = __ldcg(rec + 1 + g); rl[g] = v.x; rh[g] = v.y; rn[g] = v.z; }
-        else { const uint4 v = __ldcg(rec + 1 + (g >> 1)); rl[g] = (g & 1) ? v.z : v.x; rh[g] = (g & 1) ? v.w : v.y; }
+    for (int g = 0; g < 10; g++) {
+        rl[g] = 0; rh[g] = 0; rn[g] = 0;
+        if (g < 8 && (uint32_t)g < W) {
+            if (is_n) { const uint4 v = __ldcg(rec + 1 + g); rl[g] = v.x; rh[g] = v.y; rn[g] = v.z; }
+            else { const uint4 v = __ldcg(rec + 1 + (g >> 1)); rl[g] = (g & 1) ? v.z : v.x; rh[g] = (g & 1) ? v.w : v.y; }
+        }
     }
     uint32_t max_mm = p.max_mm;
     if (mm0 < max_mm) max_mm = mm0 - 1u;                                 // :488-489
@@ -188,47 +200,53 @@ __global__ void __launch_bounds__(PGM_CM_THREADS) cm_query_kernel(const __grid_c
     uint64_t match_pos = 0;
     uint32_t cur = mm0;
     bool found = false, done = false;
-    for (uint32_t i1 = 0; i1 + K < N2 + 1 && !done; i1 += p.k2) {
-        // K (<= 56) characters of the read from offset i1
-        const uint32_t w = i1 >> 5, s = i1 & 31u;
-        const uint64_t lo = (uint64_t)__funnelshift_r(rl[w], rl[w + 1], s) | ((uint64_t)__funnelshift_r(rl[w + 1], w + 2 < 9 ? rl[w + 2] : 0u, s) << 32);
-        const uint64_t hi = (uint64_t)__funnelshift_r(rh[w], rh[w + 1], s) | ((uint64_t)__funnelshift_r(rh[w + 1], w + 2 < 9 ? rh[w + 2] : 0u, s) << 32);
-        const uint64_t nn = (uint64_t)__funnelshift_r(rn[w], rn[w + 1], s) | ((uint64_t)__funnelshift_r(rn[w + 1], w + 2 < 9 ? rn[w + 2] : 0u, s) << 32);
-        const uint32_t h = cm_hash(K, lo, hi, nn, p.hash_mask);
-        const uint32_t b0 = __ldg(p.cumm + h);
-        uint32_t b1 = __ldg(p.cumm + h + 1);
-        if (b0 == b1) continue;
-        if (limit < cur_false && b1 > b0 + PGM_CM_TRUNCATED_BUCKET) b1 = b0 + PGM_CM_TRUNCATED_BUCKET;   // :505-509
-        for (uint32_t j = b0; j < b1; j++) {
-            const uint64_t sp = (uint64_t)__ldg(p.entries + j) * p.k1;
-            if (i1 > sp) continue;                                      // :512
-            const uint64_t a = sp - i1;
-            if (a + N2 > p.pg_len) continue;                            // :514
-            n_ver++;
-            // mismatches in the first trim8 characters (compared 8 at a time in the reference, exit between blocks) and in the tail
-            const uint64_t tw = a >> 5;
-            const uint32_t ts = (uint32_t)(a & 31);
-            uint32_t d_blocks = 0, d_tail = 0;
-            uint32_t la = __ldg(p.tlo + tw), ha = __ldg(p.thi + tw);
-            for (uint32_t g = 0; g < W; g++) {
-                const uint32_t lb = __ldg(p.tlo + tw + g + 1), hb = __ldg(p.thi + tw + g + 1);
-                uint32_t diff = (rl[g] ^ __funnelshift_r(la, lb, ts)) | (rh[g] ^ __funnelshift_r(ha, hb, ts)) | rn[g];
-                la = lb; ha = hb;
-                const uint32_t base = 32 * g;
-                if (N2 - base < 32) diff &= (1u << (N2 - base)) - 1u;
-                uint32_t in_blocks = 0xFFFFFFFFu;                      // bits of this group below trim8
-                if (trim8 <= base) in_blocks = 0;
-                else if (trim8 - base < 32) in_blocks = (1u << (trim8 - base)) - 1u;
-                d_blocks += __popc(diff & in_blocks);
-                d_tail += __popc(diff & ~in_blocks);
+    uint32_t i1 = 0;                                                     // read offsets 0, k2, 2 k2, ... while i1 + K <= N2
+#pragma unroll
+    for (int w = 0; w < 8; w++) {                                        // offsets inside word w of the planes: rl[w .. w+2] are registers
+        for (; (i1 >> 5) == (uint32_t)w && i1 + K < N2 + 1 && !done; i1 += p.k2) {
+            const uint32_t s = i1 & 31u;
+            const uint64_t lo = (uint64_t)__funnelshift_r(rl[w], rl[w + 1], s) | ((uint64_t)__funnelshift_r(rl[w + 1], rl[w + 2], s) << 32);
+            const uint64_t hi = (uint64_t)__funnelshift_r(rh[w], rh[w + 1], s) | ((uint64_t)__funnelshift_r(rh[w + 1], rh[w + 2], s) << 32);
+            const uint64_t nn = is_n ? (uint64_t)__funnelshift_r(rn[w], rn[w + 1], s) | ((uint64_t)__funnelshift_r(rn[w + 1], rn[w + 2], s) << 32) : 0ull;
+            const uint32_t h = cm_hash(K, lo, hi, nn, p.hash_mask, lut);
+            const uint32_t b0 = __ldg(p.cumm + h);
+            uint32_t b1 = __ldg(p.cumm + h + 1);
+            if (b0 == b1) continue;
+            if (limit < cur_false && b1 > b0 + PGM_CM_TRUNCATED_BUCKET) b1 = b0 + PGM_CM_TRUNCATED_BUCKET;   // :505-509
+            for (uint32_t j = b0; j < b1; j++) {
+                const uint64_t sp = (uint64_t)__ldg(p.entries + j) * p.k1;
+                if (i1 > sp) continue;                                  // :512
+                const uint64_t a = sp - i1;
+                if (a + N2 > p.pg_len) continue;                        // :514
+                n_ver++;
+                // mismatches in the first trim8 characters (compared 8 at a time in the reference, exit between blocks) and in the tail
+                uint32_t d_blocks = 0, d_tail = 0;
+                const uint64_t tw = a >> 5;
+                const uint32_t ts = (uint32_t)(a & 31);
+                uint32_t la = __ldg(p.tlo + tw), ha = __ldg(p.thi + tw);
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    if ((uint32_t)g < W) {
+                        const uint32_t lb = __ldg(p.tlo + tw + g + 1), hb = __ldg(p.thi + tw + g + 1);
+                        uint32_t diff = (rl[g] ^ __funnelshift_r(la, lb, ts)) | (rh[g] ^ __funnelshift_r(ha, hb, ts)) | rn[g];
+                        la = lb; ha = hb;
+                        const uint32_t base = 32 * g;
+                        if (N2 - base < 32) diff &= (1u << (N2 - base)) - 1u;
+                        uint32_t in_blocks = 0xFFFFFFFFu;              // bits of this group below trim8
+                        if (trim8 <= base) in_blocks = 0;
+                        else if (trim8 - base < 32) in_blocks = (1u << (trim8 - base)) - 1u;
+                        d_blocks += __popc(diff & in_blocks);
+                        d_tail += __popc(diff & ~in_blocks);
+                    }
+                }
+                if (d_blocks > max_mm) { cur_false++; continue; }       // :528-531
+                if (d_blocks + d_tail > max_mm) { cur_false += 2; continue; }   // :532-543: counted in the tail loop and once more after it
+                cur = d_blocks + d_tail;                                 // :546-548
+                match_pos = a;
+                found = true;
+                if (cur <= p.min_mm) { done = true; break; }             // :549-552
+                max_mm = cur - 1u;                                       // :553
             }
-            if (d_blocks > max_mm) { cur_false++; continue; }           // :528-531
-            if (d_blocks + d_tail > max_mm) { cur_false += 2; continue; }   // :532-543: counted in the tail loop and once more after it
-            cur = d_blocks + d_tail;                                     // :546-548
-            match_pos = a;
-            found = true;
-            if (cur <= p.min_mm) { done = true; break; }                 // :549-552
-            max_mm = cur - 1u;                                           // :553
         }
     }
     if (found && cur < mm0) {                                            // ReadsMatchers.cpp:437-446
