@@ -226,7 +226,9 @@ __global__ void __launch_bounds__(PGM_CM_THREADS, 4) cm_query_kernel(const __gri
                 uint32_t la = __ldg(p.tlo + tw), ha = __ldg(p.thi + tw);
 #pragma unroll
                 for (int g = 0; g < 8; g++) {
-                    if ((uint32_t)g < W) {
+                    // (once the count inside the blocks exceeds the limit the candidate is rejected whatever follows: the rest
+                    // of its text window is not fetched — most candidates are chance hits of the sparsified hash)
+                    if ((uint32_t)g < W && d_blocks <= max_mm) {
                         const uint32_t lb = __ldg(p.tlo + tw + g + 1), hb = __ldg(p.thi + tw + g + 1);
                         uint32_t diff = (rl[g] ^ __funnelshift_r(la, lb, ts)) | (rh[g] ^ __funnelshift_r(ha, hb, ts)) | rn[g];
                         la = lb; ha = hb;
