@@ -17,6 +17,8 @@
 #include "readsset/ReadsSetInterface.h"
 #undef private
 #include "GpuReadsMatchers.h"
+
+#include <thread>
 #include "readsset/PackedConstantLengthReadsSet.h"
 
 #include <cstdlib>
@@ -84,7 +86,28 @@ namespace PgTools {
         }
     }
 
+    namespace {
+        // Creating the CUDA context and loading the library's kernels takes about a second on a B200 — as long as the whole
+        // matching stage of a small input.  With PGRC_GPU_MATCHER set, a thread started at program load does it while
+        // PgRC reads the FASTQ and builds the pseudogenome (stages 1-3); the session joins it before its first call.
+        struct GpuWarmup {
+            std::thread th;
+            GpuWarmup() {
+                const char *env = getenv("PGRC_GPU_MATCHER");
+                if (env && *env && strcmp(env, "0") != 0)
+                    th = std::thread([] {
+                        const char *dev = getenv("PGRC_GPU_DEVICE");
+                        pgm_ctx *c = nullptr;
+                        if (pgm_create(dev ? atoi(dev) : 0, &c) == PGM_OK) pgm_destroy(c);
+                    });
+            }
+            void wait() { if (th.joinable()) th.join(); }
+            ~GpuWarmup() { wait(); }
+        } gpuWarmup;
+    }
+
     GpuMatcherSession::GpuMatcherSession(const char *pgPtr, uint64_t pgLength, ConstantLengthReadsSetInterface *readsSet) {
+        gpuWarmup.wait();
         const char *dev = getenv("PGRC_GPU_DEVICE");
         check(pgm_create(dev ? atoi(dev) : 0, &ctx), nullptr, "pgm_create");
         check(pgm_set_text(ctx, pgPtr, pgLength), ctx, "pgm_set_text");           // read-only: no in-place reverse complement
