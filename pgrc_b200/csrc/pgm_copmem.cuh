@@ -156,16 +156,24 @@ __global__ void __launch_bounds__(PGM_CM_THREADS) cm_select_kernel(const __grid_
     const uint32_t *src = p.all_entries + p.start_all[h];
     uint32_t *dst = p.entries + p.cumm[h];
     const uint32_t keep = min(c, (uint32_t)PGM_CM_COLLISIONS_LIMIT + 1u);
-    long long prev = -1;
-    for (uint32_t r = 0; r < keep; r++) {           // selection: O(keep * c); c is small except for degenerate texts
-        uint32_t best = 0xFFFFFFFFu;
-        for (uint32_t k = 0; k < c; k++) {
-            const uint32_t v = src[k];
-            if ((long long)v > prev && v < best) best = v;
+    // one pass with the 13 smallest so far kept sorted in registers: an element below the largest of them bubbles in
+    // (hot hash values — homopolymers, satellites — have millions of samples; almost all of them fail the first compare)
+    uint32_t best[PGM_CM_COLLISIONS_LIMIT + 1];
+#pragma unroll
+    for (int t = 0; t <= PGM_CM_COLLISIONS_LIMIT; t++) best[t] = 0xFFFFFFFFu;
+    for (uint32_t k = 0; k < c; k++) {
+        uint32_t x = src[k];
+        if (x < best[PGM_CM_COLLISIONS_LIMIT]) {
+#pragma unroll
+            for (int t = 0; t <= PGM_CM_COLLISIONS_LIMIT; t++) {
+                const uint32_t lo = min(best[t], x), hi = max(best[t], x);
+                best[t] = lo; x = hi;
+            }
         }
-        dst[r] = best;
-        prev = best;
     }
+#pragma unroll
+    for (int t = 0; t <= PGM_CM_COLLISIONS_LIMIT; t++)
+        if ((uint32_t)t < keep) dst[t] = best[t];
 }
 
 // processApproxMatchQueryTight (CopMEMMatcher.cpp:483-566) + the per-read part of CopMEMReadsApproxMatcher::executeMatching
