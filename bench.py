@@ -252,7 +252,8 @@ def ours(args):
     dev = torch.device("cuda", local)
     cfg = synth.scaled_config(args.workload, args.scale)
     if args.shard == "auto":
-        args.shard = "2d" if (world >= 4 and cfg["genome_len"] * cfg["copies"] >= 1e9) else "reads"
+        # (mode c indexes the whole text on every GPU: it shards by reads only)
+        args.shard = "2d" if (world >= 4 and cfg["genome_len"] * cfg["copies"] >= 1e9 and args.mode != "c") else "reads"
     T = 1
     if args.shard == "2d":
         T = args.text_shards or 2
