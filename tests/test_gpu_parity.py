@@ -397,3 +397,22 @@ def test_copmem_mode_workloads_and_edges():
     rep = synth.sample_reads(np.tile(g[200:420], 3), 300, 100, 0.02, rng)
     inp = synth.MatcherInputs(np.ascontiguousarray(text), np.concatenate([dup, areads, rep]), np.zeros((0, 100), np.uint8), 100, "hot")
     _check(inp, matching_mode="c")
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_randomized_sweep_over_modes_and_parameters(chunk):
+    """40 random (input, parameter) combinations — read lengths 40..255, seeds from 12 (24 for CopMEM) to beyond the read length,
+    all mode letters in both phases, with and without the RC pass — CUDA path against the oracle (the same sweep pins the oracle
+    against the reference's classes in tests/test_oracle_vs_reference.py)."""
+    rng = np.random.default_rng(2000 + chunk)
+    for _ in range(10):
+        L = int(rng.choice([40, 50, 64, 75, 100, 101, 125, 150, 200, 255]))
+        mode = str(rng.choice(list("dDiIcC")))
+        kw = dict(matching_mode=mode, reads_exact_matching_chars=int(rng.integers(24 if mode.lower() == "c" else 12, L + 20)),
+                  min_chars_per_mismatch=int(rng.choice([2, 3, 3, 4, 6, 10])), rev_compl_pg=bool(rng.random() < 0.8))
+        if rng.random() < 0.4:
+            pre_mode = str(rng.choice(list("dDiIcC")))
+            kw.update(pre_matching_mode=pre_mode,
+                      pre_reads_exact_matching_chars=int(rng.integers(24 if pre_mode.lower() == "c" else 12, L + 20)))
+        inp = synth.adversarial(int(rng.integers(1 << 30)), L, n_reads=int(rng.integers(50, 400)), text_len=int(rng.integers(3000, 12000)))
+        _check(inp, **kw)

@@ -125,3 +125,31 @@ def test_copmem_mode_workload_shapes():
     _cmp_c(synth.workload(100_000, 8_000, 100, 0.001, seed=117), mode="c")
     _cmp_c(synth.workload(100_000, 12_000, 150, 0.005, seed=118, n_frac=0.02), mode="c")
     _cmp_c(synth.workload(100_000, 12_000, 100, 0.01, seed=119), mode="c")
+
+
+def _random_case(rng):
+    """A random small matcher input and a random, valid parameter set over all three matching modes."""
+    L = int(rng.choice([40, 50, 64, 75, 100, 101, 125, 150, 200, 255]))
+    mode = str(rng.choice(list("dDiIcC")))
+    lo_seed = 24 if mode.lower() == "c" else 12
+    seed = int(rng.integers(lo_seed, L + 20))
+    kw = dict(mode=mode, seed=seed, min_chars_per_mismatch=int(rng.choice([2, 3, 3, 4, 6, 10])), rev_compl=bool(rng.random() < 0.8))
+    if rng.random() < 0.4:
+        pre_mode = str(rng.choice(list("dDiIcC")))
+        kw.update(pre_mode=pre_mode, pre_seed=int(rng.integers(24 if pre_mode.lower() == "c" else 12, L + 20)))
+    inp = synth.adversarial(int(rng.integers(1 << 30)), L, n_reads=int(rng.integers(50, 400)), text_len=int(rng.integers(3000, 12000)))
+    return inp, kw
+
+
+@pytest.mark.parametrize("chunk", range(6))
+def test_randomized_sweep_over_modes_and_parameters(chunk):
+    """60 random (input, parameter) combinations — read lengths 40..255, seeds from 12 (24 for CopMEM) to beyond the read length,
+    all mode letters in both phases, with and without the RC pass — oracle against the reference's own classes (one thread)."""
+    rng = np.random.default_rng(1000 + chunk)
+    for _ in range(10):
+        inp, kw = _random_case(rng)
+        r = oracle.ref_map_reads(inp.text, inp.lq_reads, inp.n_reads, inp.read_len, threads=1, **kw)
+        o = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+        bad = np.nonzero((o.pos != r.pos) | (o.rc != r.rc) | (o.mm != r.mm))[0]
+        assert bad.size == 0, (inp.read_len, kw, bad[:5], o.pos[bad[:5]], r.pos[bad[:5]], o.mm[bad[:5]], r.mm[bad[:5]])
+        assert o.matched == r.matched
