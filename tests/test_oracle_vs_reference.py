@@ -72,7 +72,7 @@ def test_interleaved_mode_workload_shapes():
 
 
 @pytest.mark.parametrize("pair", [False, True])
-@pytest.mark.parametrize("mode", ["d", "i"])
+@pytest.mark.parametrize("mode", ["d", "i", "c"])
 def test_mismatch_lists_of_the_export_step(pair, mode):
     """pgo_mismatch_lists (variants 1 / 2) against the reference's own updateEntry (ReadsMatchers.cpp:548-558) driven as
     exportMatchesInPgOrder drives it; variant 0 (the GPU contract) is the forward fill the other two are derived from."""
