@@ -47,6 +47,9 @@
 #define PGM_TAIL_WORDS (PGM_TILE_WORDS + 64)
 #define PGM_SCAN_THREADS 256
 #define PGM_SCAN_WARPS (PGM_SCAN_THREADS / 32)
+#ifndef PGM_A1_UNROLL
+#define PGM_A1_UNROLL 4                     // text words (x 32 positions) per A1 iteration of a warp: filter gathers in flight per lane
+#endif
 #ifndef PGM_SCAN_MIN_CTAS
 #define PGM_SCAN_MIN_CTAS 4                 // resident CTAs per SM the scan kernel is compiled for (register budget)
 #endif
@@ -875,7 +878,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                 }
             }
         } else {
-            constexpr int U = 4;
+            constexpr int U = PGM_A1_UNROLL;
             const uint32_t w_first = warp * PGM_WORDS_PER_WARP;
 #pragma unroll 1
             for (uint32_t it0 = 0; it0 < PGM_WORDS_PER_WARP; it0 += U) {
