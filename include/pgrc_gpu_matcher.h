@@ -10,6 +10,11 @@
  *  - plain C types only; all buffers are owned by the caller.  Input and output pointers may
  *    be host memory (pageable or pinned) or device memory of the context's GPU; the library
  *    detects which and never writes to an input.
+ *  - LIFETIME of host inputs: pgm_set_text / pgm_set_text_shard / pgm_set_reads given a HOST pointer only
+ *    record it; the bytes are copied later, chunk by chunk, overlapped with the kernels that consume
+ *    them (pgm_match_begin, pgm_scan_pass).  The caller keeps such a buffer alive and unchanged until
+ *    pgm_upload, pgm_get_results or pgm_map_reads has returned.  Device inputs are consumed by the
+ *    call itself (stream-ordered).
  *  - every function returns PGM_OK (0) or a negative pgm_status; pgm_last_error() gives the
  *    message.  There is NO CPU fallback: without a usable sm_100 device pgm_create fails.
  *  - a context is bound to one GPU and one stream and is not thread-safe (the reference
@@ -91,6 +96,9 @@ const char *pgm_last_error(const pgm_ctx *ctx); /* ctx may be NULL: last pgm_cre
 int pgm_set_stream(pgm_ctx *ctx, void *cuda_stream);
 /* Blocks until all work queued by this context has finished. */
 int pgm_synchronize(pgm_ctx *ctx);
+/* Completes the lazy upload of host inputs (see LIFETIME above): when it returns the text is packed and the
+ * reads are unpacked on the device and the library no longer reads the caller's buffers. */
+int pgm_upload(pgm_ctx *ctx);
 
 /* ---- inputs ----------------------------------------------------------------------------
  * pgm_set_text replaces the (char* pgPtr, uint_pg_len_max pgLength) constructor arguments
@@ -124,7 +132,9 @@ int pgm_set_reads(pgm_ctx *ctx, const uint8_t *lq_packed, uint32_t n_lq,
  * `parts` seeds of `seed_len` per read.  seed_len == read_len && parts == 1 && max_mm == 0 is
  * the exact path (DefaultReadsExactMatcher).  continuation = 0 resets the per-read state;
  * continuation = 1 keeps it and leaves out reads already matched with <= min_mm mismatches
- * (getMatchedReadsBitmap(minMismatches), ReadsMatchers.cpp:287-295,677-691). */
+ * (getMatchedReadsBitmap(minMismatches), ReadsMatchers.cpp:287-295,677-691).
+ * max_mm, min_mm <= 127: PgRC's CLI refuses minCharsPerMismatch < 2 (pgrc-params.h:30,254-257), so
+ * maxMismatches = readLength / minCharsPerMismatch <= 255 / 2. */
 int pgm_match_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm,
                     uint32_t min_mm, int continuation);
 /* pgm_match_begin_interleaved replaces InterleavedReadsApproxMatcher::initMatching() /
@@ -185,6 +195,45 @@ int pgm_copmem_pass(pgm_ctx *ctx, int rev_mode);
 int pgm_get_mismatches(pgm_ctx *ctx, uint64_t *out_offsets, uint8_t *out_pos, uint8_t *out_syms,
                        uint64_t capacity, uint64_t *total);
 
+/* ---- routed multi-GPU scheme: every stage divides by the number of GPUs -----------------------------
+ * One context per GPU (one process per GPU, or one process driving all of them: pgm_group_* below).  GPU g
+ *   - owns the reads [read_begin[g], read_begin[g+1]) (pgm_set_reads is given exactly these): their records, keys,
+ *     decision and results are local — no cross-GPU merge of keys;
+ *   - owns the part of the seed table whose hashes map to g (its own L2-resident pre-filter);
+ *   - holds the whole text (pgm_set_text; the 2-bit planes are pg_len / 4 bytes per strand) and hashes the window
+ *     starts of ITS range of the text only.
+ * Per phase:  pgm_route_begin -> exchange `send` (patterns, 16-byte entries) -> pgm_route_build.
+ * Per pass, for round = 0 .. pgm_route_rounds - 1:
+ *     pgm_route_scan  -> exchange (windows, 12-byte entries)    -> pgm_route_probe
+ *                     -> exchange (candidates, 12-byte entries) -> pgm_route_verify;
+ * then pgm_resolve_pass (local).  An exchange is an all-to-all: segment d of `send` (count[d] entries at
+ * base + d * stride_bytes) goes to GPU d, which receives the segments of all senders back to back, in sender
+ * order, into pgm_route_recv's buffer (NCCL send/recv over NVLink, or peer copies inside one process).
+ * Results (pgm_get_results) are those of the context's own reads.  Replaces, across GPUs, what one
+ * DefaultReadsApproxMatcher / DefaultReadsExactMatcher object does (ReadsMatchers.cpp:190-341); modes 'd'/'D'. */
+#define PGM_ROUTE_MAX_WORLD 16
+enum { PGM_ROUTE_PATTERNS = 0, PGM_ROUTE_WINDOWS = 1, PGM_ROUTE_CANDIDATES = 2 };
+typedef struct pgm_route_buffer {
+    void *base;                              /* device memory */
+    uint64_t stride_bytes;                   /* segment d starts at base + d * stride_bytes */
+    uint32_t entry_bytes;
+    uint32_t world;
+    uint64_t count[PGM_ROUTE_MAX_WORLD];     /* entries for destination d */
+} pgm_route_buffer;
+/* read_begin[world + 1]: global read ranges of the GPUs; round_windows = window starts a GPU emits per round
+ * (0 = default; bounds the exchange buffers). */
+int pgm_route_config(pgm_ctx *ctx, int rank, int world, const uint64_t *read_begin, uint64_t round_windows);
+int pgm_route_rounds(pgm_ctx *ctx, uint32_t *rounds);
+int pgm_route_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm,
+                    int continuation, pgm_route_buffer *send);
+/* Device buffer for `n_entries` incoming entries of `kind` (PGM_ROUTE_*). */
+int pgm_route_recv(pgm_ctx *ctx, int kind, uint64_t n_entries, void **ptr);
+int pgm_route_build(pgm_ctx *ctx, uint64_t n_patterns_in);
+int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer *send);
+/* in_counts[world]: window entries received from each sender (in sender order in the receive buffer). */
+int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *in_counts, pgm_route_buffer *send);
+int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_candidates_in);
+
 /* ---- the whole stage on one GPU ---------------------------------------------------------
  * pgm_map_reads replaces the matching part of PgTools::mapReadsIntoPg
  * (ReadsMatchers.cpp:693-783) for matching modes 'd'/'D' (DefaultReadsApproxMatcher), 'i'/'I'
@@ -210,6 +259,7 @@ enum { PGM_K_PACK_TEXT = 0, PGM_K_RC_TEXT, PGM_K_UNPACK_READS, PGM_K_INIT_STATE,
        PGM_K_SCAN, PGM_K_RESOLVE, PGM_K_FINALIZE, PGM_K_ACCUM,
        PGM_K_SCAN_FILTER, PGM_K_SCAN_PROBE, PGM_K_SCAN_VERIFY, /* the three stages of the L2-blocked scan pipeline */
        PGM_K_MISMATCHES, PGM_K_COPMEM_INDEX, PGM_K_COPMEM_QUERY,
+       PGM_K_ROUTE_BUILD, PGM_K_ROUTE_SCAN, PGM_K_ROUTE_PROBE, PGM_K_ROUTE_VERIFY, /* the routed multi-GPU scheme */
        PGM_K_COUNT };
 typedef struct pgm_timings {
     double ms[PGM_K_COUNT];

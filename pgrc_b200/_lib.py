@@ -19,13 +19,18 @@ STATUS_NAMES = {0: "PGM_OK", -1: "PGM_ERR_INVALID_ARG", -2: "PGM_ERR_NO_DEVICE",
                 -4: "PGM_ERR_OOM", -5: "PGM_ERR_BAD_SYMBOL", -6: "PGM_ERR_UNSUPPORTED", -7: "PGM_ERR_STATE"}
 
 # every symbol include/pgrc_gpu_matcher.h declares
-EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pgm_set_stream", "pgm_synchronize",
+EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pgm_set_stream", "pgm_synchronize", "pgm_upload",
            "pgm_set_text", "pgm_set_text_shard", "pgm_shard_plan", "pgm_set_reads", "pgm_match_begin", "pgm_match_begin_interleaved",
            "pgm_scan_pass", "pgm_get_accumulators", "pgm_put_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_get_mismatches", "pgm_copmem_begin", "pgm_copmem_pass", "pgm_map_reads",
-           "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings"]
+           "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings",
+           "pgm_route_config", "pgm_route_rounds", "pgm_route_begin", "pgm_route_recv", "pgm_route_build", "pgm_route_scan", "pgm_route_probe",
+           "pgm_route_verify"]
 
 KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators",
-                "scan_filter", "scan_probe", "scan_verify", "mismatches", "copmem_index", "copmem_query"]
+                "scan_filter", "scan_probe", "scan_verify", "mismatches", "copmem_index", "copmem_query",
+                "route_build", "route_scan", "route_probe", "route_verify"]
+PGM_ROUTE_MAX_WORLD = 16
+PGM_ROUTE_PATTERNS, PGM_ROUTE_WINDOWS, PGM_ROUTE_CANDIDATES = 0, 1, 2
 
 
 class PgmStats(ctypes.Structure):
@@ -43,6 +48,11 @@ class PgmAccumulators(ctypes.Structure):
     _fields_ = [("best_key", ctypes.c_void_p), ("first_other_order", ctypes.c_void_p),
                 ("same_pos_mask", ctypes.c_void_p), ("same_pos_mm", ctypes.c_void_p),
                 ("touched", ctypes.c_void_p), ("n_reads", ctypes.c_uint64)]
+
+
+class PgmRouteBuffer(ctypes.Structure):
+    _fields_ = [("base", ctypes.c_void_p), ("stride_bytes", ctypes.c_uint64), ("entry_bytes", ctypes.c_uint32),
+                ("world", ctypes.c_uint32), ("count", ctypes.c_uint64 * PGM_ROUTE_MAX_WORLD)]
 
 
 class PgmError(RuntimeError):
@@ -69,6 +79,7 @@ def load() -> ctypes.CDLL:
     lib.pgm_last_error.restype = ctypes.c_char_p; lib.pgm_last_error.argtypes = [vp]
     lib.pgm_set_stream.restype = ci; lib.pgm_set_stream.argtypes = [vp, vp]
     lib.pgm_synchronize.restype = ci; lib.pgm_synchronize.argtypes = [vp]
+    lib.pgm_upload.restype = ci; lib.pgm_upload.argtypes = [vp]
     lib.pgm_set_text.restype = ci; lib.pgm_set_text.argtypes = [vp, vp, u64]
     lib.pgm_set_text_shard.restype = ci; lib.pgm_set_text_shard.argtypes = [vp, vp, u64, u64, u64, u64, u64]
     lib.pgm_shard_plan.restype = ci
@@ -92,5 +103,14 @@ def load() -> ctypes.CDLL:
     lib.pgm_set_tuning.restype = ci; lib.pgm_set_tuning.argtypes = [vp, ci, ci, ci, ci]
     lib.pgm_set_profiling.restype = ci; lib.pgm_set_profiling.argtypes = [vp, ci]
     lib.pgm_get_timings.restype = ci; lib.pgm_get_timings.argtypes = [vp, ctypes.POINTER(PgmTimings)]
+    rb = ctypes.POINTER(PgmRouteBuffer)
+    lib.pgm_route_config.restype = ci; lib.pgm_route_config.argtypes = [vp, ci, ci, ctypes.POINTER(u64), u64]
+    lib.pgm_route_rounds.restype = ci; lib.pgm_route_rounds.argtypes = [vp, ctypes.POINTER(u32)]
+    lib.pgm_route_begin.restype = ci; lib.pgm_route_begin.argtypes = [vp, u32, u32, u32, u32, ci, rb]
+    lib.pgm_route_recv.restype = ci; lib.pgm_route_recv.argtypes = [vp, ci, u64, ctypes.POINTER(vp)]
+    lib.pgm_route_build.restype = ci; lib.pgm_route_build.argtypes = [vp, u64]
+    lib.pgm_route_scan.restype = ci; lib.pgm_route_scan.argtypes = [vp, ci, u32, rb]
+    lib.pgm_route_probe.restype = ci; lib.pgm_route_probe.argtypes = [vp, ci, u32, ctypes.POINTER(u64), rb]
+    lib.pgm_route_verify.restype = ci; lib.pgm_route_verify.argtypes = [vp, ci, u64]
     _lib = lib
     return lib

@@ -5,6 +5,7 @@
 #include "pgm_kernels.cuh"
 #include "pgm_blocked.cuh"
 #include "pgm_copmem.cuh"
+#include "pgm_routed.cuh"
 
 #include <algorithm>
 #include <cctype>
@@ -106,6 +107,16 @@ struct pgm_ctx {
     uint32_t ilv() const { return interleaved ? parts : 0u; }                        // stride of the seeds, 0 = contiguous
     uint32_t shift_unit() const { return interleaved ? 1u : seed_len; }              // alignment start = window start - j * shift_unit
     uint64_t seed_span() const { return (uint64_t)seed_len * (interleaved ? parts : 1u); }   // text bases a seed window covers
+
+    // routed multi-GPU scheme (pgm_routed.cuh)
+    struct Route {
+        int rank = 0, world = 0;            // world = 0: not configured
+        uint64_t read_begin[PGM_ROUTE_MAX_WORLD + 1] = {0};
+        uint64_t round_windows = 0;         // window starts a GPU emits per round
+        uint32_t cap_pat = 0, cap_win = 0, cap_cand = 0;
+        uint64_t n_pat_in = 0;
+    } route;
+    DevBuf rt_win_send, rt_win_recv, rt_cand_send, rt_cand_recv, rt_pat_recv, rt_counters;
 
     // misc device scalars: counters[0..3] scan, [4] inserted, [5] tile counter (low 32 bits)
     DevBuf counters, hist, err_flag;
@@ -316,6 +327,7 @@ pgm::BuildQueues build_queues(pgm_ctx *c) {
     q.cursor = c->bq_counters.as<unsigned int>() + PGM_MAX_REGIONS;
     q.cap = c->bq_cap;
     q.region_bits = c->bq_region_bits;
+    q.route_world = 0; q.read_base = 0; q.overflow = nullptr;
     return q;
 }
 
@@ -545,6 +557,7 @@ void pgm_destroy(pgm_ctx *ctx) {
                       &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
                       &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter, &ctx->bq_entries, &ctx->bq_counters,
                       &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->mis_sums, &ctx->mis_offsets, &ctx->mis_pos, &ctx->mis_syms,
+                      &ctx->rt_win_send, &ctx->rt_win_recv, &ctx->rt_cand_send, &ctx->rt_cand_recv, &ctx->rt_pat_recv, &ctx->rt_counters,
                       &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
@@ -574,6 +587,8 @@ int pgm_synchronize(pgm_ctx *ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     return PGM_OK;
 }
+
+int pgm_upload(pgm_ctx *ctx);   // (defined behind upload_reads / finish_text_upload's users below)
 
 int pgm_set_tuning(pgm_ctx *ctx, int filter_log2_bits, int slots_per_pattern, int ctas_per_sm, int l2_hints) {
     if (!ctx) return PGM_ERR_INVALID_ARG;
@@ -654,6 +669,7 @@ int pgm_set_text_shard(pgm_ctx *ctx, const char *slice, uint64_t slice_begin, ui
     ctx->own_begin = own_begin; ctx->own_end = own_end;
     ctx->has_text = true;
     ctx->text_pending = false; ctx->text_copies_enqueued = false; ctx->h_text = nullptr;
+    CU(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), ctx->stream));   // a new text: the symbol check starts over
     if (!slice_len) return PGM_OK;
     if (is_device_ptr(slice)) {
         // device-resident text: one launch over the whole slice (the chunks exist for the pipelined host upload)
@@ -1002,6 +1018,16 @@ int pgm_resolve_pass(pgm_ctx *ctx, int rev_mode) {
     return resolve_impl(ctx, rev_mode, false);
 }
 
+int pgm_upload(pgm_ctx *ctx) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((ctx->has_reads && (rc = upload_reads(ctx, false))) || (ctx->has_text && (rc = finish_text_upload(ctx)))) return rc;
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PGM_OK;
+}
+
 int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats) {
     if (!ctx) return PGM_ERR_INVALID_ARG;
     if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_get_results: no reads");
@@ -1206,6 +1232,307 @@ int pgm_get_mismatches(pgm_ctx *ctx, uint64_t *out_offsets, uint8_t *out_pos, ui
     CU(cudaStreamSynchronize(ctx->stream));
     if (bad == 1) return fail(ctx, PGM_ERR_BAD_SYMBOL, "pseudogenome text contains a symbol outside ACGT (2-bit text planes cannot hold it)");
     if (bad) return fail(ctx, PGM_ERR_CUDA, "pgm_get_mismatches: a mismatch list does not have readMismatchesCount entries (internal error)");
+    return PGM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ routed multi-GPU scheme
+} // extern "C"
+
+namespace {
+
+// window starts of one pass: [0, pg_len - span]; GPU g owns [cut(g), cut(g + 1)), cuts are multiples of 128 (tile copies stay
+// 16-byte aligned); round r of GPU g covers [cut(g) + r * round_windows, ...)
+uint64_t route_windows(const pgm_ctx *ctx) {
+    const uint64_t span = ctx->seed_span();
+    return ctx->pg_len >= span ? ctx->pg_len - span + 1 : 0;
+}
+uint64_t route_cut(const pgm_ctx *ctx, int k) {
+    const uint64_t nw = route_windows(ctx);
+    if (k >= ctx->route.world) return nw;
+    return (uint64_t)((unsigned __int128)nw * (unsigned)k / (unsigned)ctx->route.world) / 128 * 128;
+}
+void route_range(const pgm_ctx *ctx, int g, uint32_t round, uint64_t &b, uint64_t &e) {
+    const uint64_t lo = route_cut(ctx, g), hi = route_cut(ctx, g + 1);
+    b = std::min(hi, lo + (uint64_t)round * ctx->route.round_windows);
+    e = std::min(hi, b + ctx->route.round_windows);
+}
+uint32_t route_rounds(const pgm_ctx *ctx) {
+    uint64_t longest = 0;
+    for (int g = 0; g < ctx->route.world; g++) longest = std::max(longest, route_cut(ctx, g + 1) - route_cut(ctx, g));
+    return (uint32_t)std::max<uint64_t>(1, (longest + ctx->route.round_windows - 1) / ctx->route.round_windows);
+}
+
+uint32_t route_cap(uint64_t total, int world) {
+    // a destination's share + 25 % + slack, never more than everything (hot seeds / low-complexity text skew the shares)
+    return (uint32_t)std::min<uint64_t>(std::min<uint64_t>(total, total / world + total / (4 * world) + (1u << 20)) + 16, 0xFFFFFFF0ull);
+}
+
+unsigned int *route_counts(pgm_ctx *ctx, int kind) { return ctx->rt_counters.as<unsigned int>() + kind * PGM_ROUTE_MAX_WORLD; }
+unsigned int *route_overflow(pgm_ctx *ctx) { return ctx->rt_counters.as<unsigned int>() + 3 * PGM_ROUTE_MAX_WORLD; }
+unsigned int *route_tile_counter(pgm_ctx *ctx) { return ctx->rt_counters.as<unsigned int>() + 3 * PGM_ROUTE_MAX_WORLD + 1; }
+
+// copies the per-destination counts of `kind` (and the overflow flag) to the host; synchronizes the stream
+int route_fetch_counts(pgm_ctx *ctx, int kind, pgm_route_buffer *send, void *base, uint64_t stride, uint32_t entry_bytes, const char *what) {
+    unsigned int h[3 * PGM_ROUTE_MAX_WORLD + 2];
+    CU(cudaMemcpyAsync(h, ctx->rt_counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (h[3 * PGM_ROUTE_MAX_WORLD])
+        return fail(ctx, PGM_ERR_STATE, std::string(what) + ": an exchange queue overflowed (a GPU's share of the hashes / candidates is far above "
+                                        "the average: extremely skewed input); rerun with the read-sharded scheme");
+    memset(send, 0, sizeof *send);
+    send->base = base; send->stride_bytes = stride; send->entry_bytes = entry_bytes; send->world = (uint32_t)ctx->route.world;
+    for (int d = 0; d < ctx->route.world; d++) send->count[d] = h[kind * PGM_ROUTE_MAX_WORLD + d];
+    return PGM_OK;
+}
+
+template <int NCH>
+cudaError_t launch_route_scan(const pgm::RouteScanParams &sp, unsigned int grid, cudaStream_t s) {
+    const size_t smem = sizeof(pgm::RouteScanShared);
+    cudaError_t e = cudaFuncSetAttribute(pgm::route_scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pgm::route_scan_kernel<NCH><<<grid, PGM_ROUTE_THREADS, smem, s>>>(sp);
+    return cudaSuccess;
+}
+
+} // namespace
+
+extern "C" {
+
+int pgm_route_config(pgm_ctx *ctx, int rank, int world, const uint64_t *read_begin, uint64_t round_windows) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (world < 1 || world > PGM_ROUTE_MAX_WORLD || rank < 0 || rank >= world || !read_begin)
+        return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_route_config: need 1 <= world <= 16, 0 <= rank < world and the read ranges");
+    for (int k = 0; k < world; k++)
+        if (read_begin[k] > read_begin[k + 1]) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_route_config: read ranges must ascend");
+    if (read_begin[world] >= 0xFFFFFFFFull) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_route_config: too many reads");
+    CU(cudaSetDevice(ctx->device));
+    ctx->route.rank = rank; ctx->route.world = world;
+    for (int k = 0; k <= world; k++) ctx->route.read_begin[k] = read_begin[k];
+    ctx->route.round_windows = round_windows ? std::max<uint64_t>(PGM_TILE_POS, (round_windows + PGM_TILE_POS - 1) / PGM_TILE_POS * PGM_TILE_POS)
+                                             : (512ull << 20);
+    int rc;
+    if ((rc = ensure(ctx, ctx->rt_counters, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int)))) return rc;
+    return PGM_OK;
+}
+
+int pgm_route_rounds(pgm_ctx *ctx, uint32_t *rounds) {
+    if (!ctx || !rounds) return PGM_ERR_INVALID_ARG;
+    if (!ctx->route.world || !ctx->phase_active || !ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_route_rounds: call pgm_route_config, pgm_set_text and pgm_route_begin first");
+    *rounds = route_rounds(ctx);
+    return PGM_OK;
+}
+
+int pgm_route_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm, int continuation, pgm_route_buffer *send) {
+    if (!ctx || !send) return PGM_ERR_INVALID_ARG;
+    const pgm_ctx::Route &rt = ctx->route;
+    if (!rt.world) return fail(ctx, PGM_ERR_STATE, "pgm_route_begin: pgm_route_config has not been called");
+    if (!ctx->has_reads) return fail(ctx, PGM_ERR_STATE, "pgm_route_begin: pgm_set_reads has not been called");
+    if (ctx->n_reads() != rt.read_begin[rt.rank + 1] - rt.read_begin[rt.rank])
+        return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_route_begin: pgm_set_reads must be given exactly this GPU's read range");
+    if (seed_len == 0 || parts == 0 || (uint64_t)seed_len * parts > ctx->read_len)
+        return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_route_begin: need seed_len >= 1 and seed_len * parts <= read_len");
+    if (max_mm > 127 || min_mm > 127) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_route_begin: mismatch limits must be <= 127");
+    const uint32_t part_bits = (uint32_t)ceil_log2(parts);
+    if ((rt.read_begin[rt.world] << part_bits) >= 0xFFFFFFFFull)
+        return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_route_begin: pattern index exceeds 32 bits (reads << ceil(log2(parts)))");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload_reads(ctx, false))) return rc;
+    const uint32_t n = ctx->n_reads();
+    ctx->seed_len = seed_len; ctx->parts = parts; ctx->max_mm = max_mm; ctx->min_mm = min_mm; ctx->part_bits = part_bits;
+    ctx->interleaved = false;
+    ctx->outputs_valid = false;
+    if (!continuation) CU(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    else CU(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 4, 0, sizeof(unsigned long long), ctx->stream));
+    if (n && ((!continuation && !ctx->state_fresh) || !ctx->aux_clean)) {
+        KLAUNCH(PGM_K_INIT_STATE, "reset_state_kernel", pgm::reset_state_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(
+            reads_view(ctx), per_read(ctx), n, continuation ? 0 : 1, 1));
+        CU(cudaMemsetAsync(ctx->touched.p, 0, sizeof(int), ctx->stream));
+        ctx->aux_clean = true;
+    }
+    // my reads' seeds -> send segments by hash owner
+    const uint64_t n_local = (uint64_t)n * parts;
+    ctx->route.cap_pat = route_cap(n_local, rt.world);
+    if ((rc = ensure(ctx, ctx->bq_entries, (size_t)ctx->route.cap_pat * rt.world * sizeof(uint4)))) return rc;
+    CU(cudaMemsetAsync(ctx->rt_counters.p, 0, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int), ctx->stream));
+    if (n) {
+        pgm::BuildQueues q;
+        q.entries = ctx->bq_entries.as<uint4>();
+        q.count = route_counts(ctx, PGM_ROUTE_PATTERNS); q.cursor = nullptr;
+        q.cap = ctx->route.cap_pat; q.region_bits = 0;
+        q.route_world = (uint32_t)rt.world; q.read_base = (uint32_t)rt.read_begin[rt.rank]; q.overflow = route_overflow(ctx);
+        const uint32_t tail = seed_len % 32 ? (1u << (seed_len % 32)) - 1u : 0xFFFFFFFFu;
+        const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(n, PGM_BUILD_THREADS), (uint64_t)ctx->sm_count * 8);
+        const size_t smem = (size_t)parts * PGM_BUILD_THREADS * sizeof(uint4);
+        const bool fast = ctx->n_n == 0 && ctx->lq_stride16 == 4;
+        pgm::TableView none;
+        memset(&none, 0, sizeof none);
+        KLAUNCH(PGM_K_ROUTE_BUILD, "build_table_kernel (routed)",
+                if (fast) pgm::build_table_kernel<true><<<grid, PGM_BUILD_THREADS, smem, ctx->stream>>>(
+                    reads_view(ctx), none, q, 0, n, seed_len, parts, min_mm, continuation, tail, 0, ctx->counters.as<unsigned long long>() + 4);
+                else pgm::build_table_kernel<false><<<grid, PGM_BUILD_THREADS, smem, ctx->stream>>>(
+                    reads_view(ctx), none, q, 0, n, seed_len, parts, min_mm, continuation, tail, 0, ctx->counters.as<unsigned long long>() + 4));
+    }
+    ctx->phase_active = true;
+    ctx->copmem_active = false;
+    return route_fetch_counts(ctx, PGM_ROUTE_PATTERNS, send, ctx->bq_entries.p, (uint64_t)ctx->route.cap_pat * sizeof(uint4), sizeof(uint4), "pgm_route_begin");
+}
+
+int pgm_route_recv(pgm_ctx *ctx, int kind, uint64_t n_entries, void **ptr) {
+    if (!ctx || !ptr || kind < 0 || kind > 2) return PGM_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf &b = kind == PGM_ROUTE_PATTERNS ? ctx->rt_pat_recv : kind == PGM_ROUTE_WINDOWS ? ctx->rt_win_recv : ctx->rt_cand_recv;
+    const size_t eb = kind == PGM_ROUTE_PATTERNS ? 16 : 12;
+    if (b.cap < std::max<size_t>(n_entries, 1) * eb) CU(cudaStreamSynchronize(ctx->stream));   // (a kernel may still read the old buffer)
+    int rc;
+    if ((rc = ensure(ctx, b, std::max<size_t>(n_entries, 1) * eb))) return rc;
+    *ptr = b.p;
+    return PGM_OK;
+}
+
+int pgm_route_build(pgm_ctx *ctx, uint64_t n_in) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->route.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_build: pgm_route_begin has not been called");
+    if (n_in && ctx->rt_pat_recv.cap < n_in * 16) return fail(ctx, PGM_ERR_STATE, "pgm_route_build: the patterns have not been received (pgm_route_recv)");
+    CU(cudaSetDevice(ctx->device));
+    const pgm_ctx::Route &rt = ctx->route;
+    // table geometry for the patterns that actually arrived (hash skew included)
+    const uint64_t want_slots = std::max<uint64_t>(512, n_in * (uint64_t)ctx->slots_per_pattern);
+    const uint64_t nb64 = next_prime((want_slots + 3) / 4);
+    if (nb64 >= 0x7FFFFFFFull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_route_build: table too large");
+    const uint64_t n_ids = rt.read_begin[rt.world] << ctx->part_bits;         // next[] is indexed by the GLOBAL pattern id
+    int rc;
+    if ((rc = ensure(ctx, ctx->buckets, nb64 * 32)) || (rc = ensure(ctx, ctx->next, std::max<uint64_t>(n_ids, 1) * 4))) return rc;
+    ctx->n_buckets = (uint32_t)nb64;
+    ctx->n_slots = nb64 * 4;
+    CU(cudaMemsetAsync(ctx->buckets.p, 0xFF, nb64 * 32, ctx->stream));
+    int fbits = ctx->filter_log2_bits;
+    if (fbits < 0) fbits = std::min(n_in > (100ull << 20) ? 29 : 28, std::max(15, ceil_log2(std::max<uint64_t>(n_in, 1) * 8)));
+    ctx->filter_pair = 0;
+    if (fbits > 0) {
+        const double per = (double)(1ull << fbits) / (double)std::max<uint64_t>(n_in, 1);
+        ctx->filter_k = ctx->filter_k_force ? (uint32_t)std::min(2, std::max(1, ctx->filter_k_force))
+                                            : (uint32_t)std::min(2.0, std::max(1.0, 0.69 * per + 0.5));
+        ctx->filter_words = 1u << (fbits - 5);
+        const size_t fbytes = (size_t)1 << (fbits - 3);
+        if ((rc = ensure(ctx, ctx->filter, fbytes))) return rc;
+        CU(cudaMemsetAsync(ctx->filter.p, 0, fbytes, ctx->stream));
+    } else ctx->filter_words = 0;
+    ctx->bq_region_bits = 0; ctx->bq_pending = false;
+    ctx->route.n_pat_in = n_in;
+    if (n_in)
+        KLAUNCH(PGM_K_ROUTE_BUILD, "route_insert_kernel", pgm::route_insert_kernel<<<ctx->sm_count * 8, PGM_INSERT_THREADS, 0, ctx->stream>>>(
+            table_view(ctx), ctx->rt_pat_recv.as<uint4>(), n_in));
+    return PGM_OK;
+}
+
+int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer *send) {
+    if (!ctx || !send) return PGM_ERR_INVALID_ARG;
+    const pgm_ctx::Route &rt = ctx->route;
+    if (!rt.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_scan: pgm_route_begin has not been called");
+    if (!ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_route_scan: pgm_set_text has not been called");
+    if (ctx->slice_begin != 0 || ctx->slice_len != ctx->pg_len)
+        return fail(ctx, PGM_ERR_STATE, "pgm_route_scan: the routed scheme needs the whole text on every GPU (pgm_set_text, not a text shard)");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = finish_text_upload(ctx))) return rc;
+    uint64_t b, e;
+    route_range(ctx, rt.rank, round, b, e);
+    ctx->route.cap_win = route_cap(rt.round_windows, rt.world);
+    if ((rc = ensure(ctx, ctx->rt_win_send, (size_t)ctx->route.cap_win * rt.world * 12))) return rc;
+    CU(cudaMemsetAsync(ctx->rt_counters.p, 0, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int), ctx->stream));
+    if (e > b && ctx->n_buckets) {
+        pgm::RouteScanParams sp;
+        memset(&sp, 0, sizeof sp);
+        sp.tlo = (rev_mode ? ctx->r_lo : ctx->f_lo).as<uint32_t>() + PGM_PAD_WORDS;
+        sp.thi = (rev_mode ? ctx->r_hi : ctx->f_hi).as<uint32_t>() + PGM_PAD_WORDS;
+        sp.begin = b; sp.end = e;
+        sp.first_word = (uint32_t)(b / 32);
+        sp.n_tiles = (uint32_t)((e - b + PGM_TILE_POS - 1) / PGM_TILE_POS);
+        sp.tail_mask = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
+        sp.tile_counter = route_tile_counter(ctx);
+        sp.q.entries = ctx->rt_win_send.as<uint32_t>(); sp.q.count = route_counts(ctx, PGM_ROUTE_WINDOWS);
+        sp.q.overflow = route_overflow(ctx); sp.q.cap = ctx->route.cap_win; sp.q.world = (uint32_t)rt.world;
+        const unsigned int grid = (unsigned int)std::min<uint64_t>(sp.n_tiles, (uint64_t)ctx->sm_count * 4);
+        cudaError_t le = cudaSuccess;
+        KLAUNCH(PGM_K_ROUTE_SCAN, "route_scan_kernel",
+                switch ((ctx->seed_len + 31) / 32) {
+                    case 1: le = launch_route_scan<1>(sp, grid, ctx->stream); break;
+                    case 2: le = launch_route_scan<2>(sp, grid, ctx->stream); break;
+                    case 3: le = launch_route_scan<3>(sp, grid, ctx->stream); break;
+                    case 4: le = launch_route_scan<4>(sp, grid, ctx->stream); break;
+                    case 5: le = launch_route_scan<5>(sp, grid, ctx->stream); break;
+                    case 6: le = launch_route_scan<6>(sp, grid, ctx->stream); break;
+                    case 7: le = launch_route_scan<7>(sp, grid, ctx->stream); break;
+                    default: le = launch_route_scan<8>(sp, grid, ctx->stream); break;
+                });
+        if (le != cudaSuccess) return cuda_fail(ctx, le, "route_scan_kernel (shared memory attribute)");
+    }
+    ctx->state_fresh = false;
+    return route_fetch_counts(ctx, PGM_ROUTE_WINDOWS, send, ctx->rt_win_send.p, (uint64_t)ctx->route.cap_win * 12, 12, "pgm_route_scan");
+}
+
+int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *in_counts, pgm_route_buffer *send) {
+    if (!ctx || !send || !in_counts) return PGM_ERR_INVALID_ARG;
+    const pgm_ctx::Route &rt = ctx->route;
+    if (!rt.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: pgm_route_begin has not been called");
+    (void)rev_mode;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t n_in = 0;
+    for (int s = 0; s < rt.world; s++) n_in += in_counts[s];
+    if (n_in && ctx->rt_win_recv.cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: the windows have not been received (pgm_route_recv)");
+    // on average well under one candidate per window; hot keys are covered by the slack
+    ctx->route.cap_cand = (uint32_t)std::min<uint64_t>(n_in / rt.world + (4u << 20), 0xFFFFFFF0ull);
+    int rc;
+    if ((rc = ensure(ctx, ctx->rt_cand_send, (size_t)ctx->route.cap_cand * rt.world * 12))) return rc;
+    CU(cudaMemsetAsync(ctx->rt_counters.p, 0, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int), ctx->stream));
+    uint64_t off = 0;
+    for (int s = 0; s < rt.world; s++) {
+        if (!in_counts[s]) continue;
+        uint64_t b, e;
+        route_range(ctx, s, round, b, e);
+        pgm::RouteProbeParams pp;
+        memset(&pp, 0, sizeof pp);
+        pp.src = ctx->rt_win_recv.as<uint32_t>() + off * 3;
+        pp.n = in_counts[s];
+        pp.pos_base = b;
+        pp.tab = table_view(ctx);
+        pp.part_bits = ctx->part_bits; pp.world = (uint32_t)rt.world;
+        for (int k = 0; k <= rt.world; k++) pp.read_begin[k] = rt.read_begin[k];
+        pp.q.entries = ctx->rt_cand_send.as<uint32_t>(); pp.q.count = route_counts(ctx, PGM_ROUTE_CANDIDATES);
+        pp.q.overflow = route_overflow(ctx); pp.q.cap = ctx->route.cap_cand; pp.q.world = (uint32_t)rt.world;
+        pp.counters = ctx->counters.as<unsigned long long>();
+        const uint64_t chunks = (pp.n + PGM_ROUTE_PROBE_CHUNK - 1) / PGM_ROUTE_PROBE_CHUNK;
+        const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * 6);
+        KLAUNCH(PGM_K_ROUTE_PROBE, "route_probe_kernel", pgm::route_probe_kernel<<<grid, PGM_ROUTE_THREADS, 0, ctx->stream>>>(pp));
+        off += in_counts[s];
+    }
+    return route_fetch_counts(ctx, PGM_ROUTE_CANDIDATES, send, ctx->rt_cand_send.p, (uint64_t)ctx->route.cap_cand * 12, 12, "pgm_route_probe");
+}
+
+int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_in) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    const pgm_ctx::Route &rt = ctx->route;
+    if (!rt.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_verify: pgm_route_begin has not been called");
+    if (n_in && ctx->rt_cand_recv.cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_verify: the candidates have not been received (pgm_route_recv)");
+    CU(cudaSetDevice(ctx->device));
+    if (!n_in || !ctx->n_reads()) return PGM_OK;
+    pgm::RouteVerifyParams vp;
+    memset(&vp, 0, sizeof vp);
+    vp.v.tlo = (rev_mode ? ctx->r_lo : ctx->f_lo).as<uint32_t>() + PGM_PAD_WORDS;
+    vp.v.thi = (rev_mode ? ctx->r_hi : ctx->f_hi).as<uint32_t>() + PGM_PAD_WORDS;
+    vp.v.pos_origin = 0; vp.v.bit_origin = 0; vp.v.pg_len = ctx->pg_len;
+    vp.v.seed_len = ctx->shift_unit(); vp.v.parts = ctx->parts; vp.v.max_mm = ctx->max_mm; vp.v.min_mm = ctx->min_mm;
+    vp.v.rev_mode = rev_mode ? 1 : 0;
+    vp.v.tab = table_view(ctx); vp.v.reads = reads_view(ctx); vp.v.pr = per_read(ctx);
+    vp.src = ctx->rt_cand_recv.as<uint32_t>(); vp.n = n_in;
+    vp.read_base = (uint32_t)rt.read_begin[rt.rank];
+    vp.counters = ctx->counters.as<unsigned long long>();
+    ctx->state_fresh = false; ctx->aux_clean = false; ctx->outputs_valid = false;
+    const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(n_in, PGM_VERIFY_THREADS), (uint64_t)ctx->sm_count * 8);
+    KLAUNCH(PGM_K_ROUTE_VERIFY, "route_verify_kernel",
+            if (ctx->lq_stride16 == 4) pgm::route_verify_kernel<true><<<grid, PGM_VERIFY_THREADS, 0, ctx->stream>>>(vp);
+            else pgm::route_verify_kernel<false><<<grid, PGM_VERIFY_THREADS, 0, ctx->stream>>>(vp));
     return PGM_OK;
 }
 

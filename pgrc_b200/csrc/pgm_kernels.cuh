@@ -531,6 +531,12 @@ struct BuildQueues {
     unsigned int *cursor;       // step 2: next entry to take per region
     uint32_t cap;
     uint32_t region_bits;       // 0 = queues off (small tables): step 1 inserts directly
+    // routed multi-GPU build (pgm_routed.cuh): the "regions" are the `route_world` GPUs, region = umulhi(h1, route_world) = the
+    // owner of the hash, the entry carries h1 * route_world (the part of h1 the routing did not use) and the GLOBAL pattern id
+    // (read_base = global index of this GPU's first read); a full queue raises *overflow (nothing is inserted locally)
+    uint32_t route_world;
+    uint32_t read_base;
+    unsigned int *overflow;
 };
 
 // Step 1.  One thread per read: for each of its `parts` seeds, fold read bases [j*n, (j+1)*n) into the canonical form
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
                                                                         unsigned long long *inserted) {
     extern __shared__ uint4 s_ent[];                                   // parts x blockDim staged entries {h1, h2, pattern, region | rank << 8}
     __shared__ unsigned int s_count[PGM_MAX_REGIONS], s_base[PGM_MAX_REGIONS];
-    const uint32_t n_regions = q.region_bits ? 1u << q.region_bits : 0u;
+    const uint32_t n_regions = q.route_world ? q.route_world : (q.region_bits ? 1u << q.region_bits : 0u);
     unsigned int n_ins = 0;
     const uint32_t span = gridDim.x * blockDim.x;
     const uint32_t rounds = (r_end - r_begin + span - 1) / span;       // same trip count for the whole block (barriers inside)
@@ -621,8 +627,8 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
                 if (FN == 0) {
                     const uint64_t hv = seed_hash64(P, Q, R);
                     const uint32_t h1 = (uint32_t)hv, h2 = (uint32_t)(hv >> 32);
-                    const uint32_t pat = (r << reads.part_bits) | j;
-                    if (tab.filter) {
+                    const uint32_t pat = ((r + q.read_base) << reads.part_bits) | j;
+                    if (tab.filter && !q.route_world) {
                         const uint32_t f = filter_hash(P, Q, R);
                         if (tab.pair) {
                             atomicOr(tab.filter + (pair_word(P, Q, 0, tab.pair_lo, tab.pair_mask) & tab.filter_mask), filter_bits(f, tab.filter_k));
@@ -631,8 +637,8 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
                     }
                     n_ins++;
                     if (n_regions) {
-                        const uint32_t region = h1 >> (32 - q.region_bits);
-                        ent = make_uint4(h1, h2, pat, region | (atomicAdd(&s_count[region], 1u) << 8));
+                        const uint32_t region = q.route_world ? __umulhi(h1, q.route_world) : h1 >> (32 - q.region_bits);
+                        ent = make_uint4(q.route_world ? h1 * q.route_world : h1, h2, pat, region | (atomicAdd(&s_count[region], 1u) << 8));
                     } else {
                         table_insert(tab, h1, h2, pat);
                     }
@@ -651,6 +657,7 @@ __global__ void __launch_bounds__(PGM_BUILD_THREADS) build_table_kernel(ReadsVie
                 if (e.w != 0xFFFFFFFFu) {
                     const uint32_t region = e.w & 0xFFu, slot = s_base[region] + (e.w >> 8);
                     if (slot < q.cap) q.entries[(size_t)region * q.cap + slot] = make_uint4(e.x, e.y, e.z, 0);
+                    else if (q.route_world) *q.overflow = 1u;
                     else table_insert(tab, e.x, e.y, e.z);             // queue full (skewed hashes): insert directly
                 }
             }

@@ -20,7 +20,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import KERNEL_NAMES, PGM_DISABLED_PREFIX_MODE, PgmAccumulators, PgmError, PgmStats, PgmTimings
+from ._lib import (KERNEL_NAMES, PGM_DISABLED_PREFIX_MODE, PGM_ROUTE_CANDIDATES, PGM_ROUTE_PATTERNS, PGM_ROUTE_WINDOWS, PgmAccumulators,
+                   PgmError, PgmRouteBuffer, PgmStats, PgmTimings)
 
 NOT_MATCHED_POSITION = np.uint64(0xFFFFFFFFFFFFFFFF)   # DefaultReadsMatcher::NOT_MATCHED_POSITION
 NOT_MATCHED_COUNT = 255                                 # PgTools::NOT_MATCHED_COUNT
@@ -184,6 +185,67 @@ class GpuReadsMatcher:
     def synchronize(self):
         self._check(self._lib.pgm_synchronize(self._h))
 
+    def upload(self):
+        """Completes the lazy upload of host inputs: afterwards the caller's buffers are no longer read (pgm_upload)."""
+        self._check(self._lib.pgm_upload(self._h))
+
+    # -- routed multi-GPU scheme (pgm_route_*): one context per GPU, exchanges done by the caller
+    def _segments(self, buf: PgmRouteBuffer):
+        """torch uint8 views of the per-destination segments of a send buffer (None where a segment is empty)."""
+        import torch
+        dev = f"cuda:{self.device}"
+        out = []
+        for d in range(buf.world):
+            nb = int(buf.count[d]) * buf.entry_bytes
+            out.append(torch.as_tensor(_DevArray(buf.base + d * buf.stride_bytes, nb, "|u1", self), device=dev) if nb else None)
+        return out
+
+    def route_config(self, rank: int, world: int, read_begin, round_windows: int = 0):
+        arr = (ctypes.c_uint64 * (world + 1))(*[int(x) for x in read_begin])
+        self._check(self._lib.pgm_route_config(self._h, rank, world, arr, round_windows))
+        self._route_world = world
+
+    def route_rounds(self) -> int:
+        r = ctypes.c_uint32()
+        self._check(self._lib.pgm_route_rounds(self._h, ctypes.byref(r)))
+        return int(r.value)
+
+    def route_begin(self, seed_len, parts, max_mm, min_mm, continuation=False):
+        buf = PgmRouteBuffer()
+        self._check(self._lib.pgm_route_begin(self._h, seed_len, parts, max_mm, min_mm, int(continuation), ctypes.byref(buf)))
+        return [int(buf.count[d]) for d in range(buf.world)], self._segments(buf), buf.entry_bytes
+
+    def route_recv(self, kind: int, in_counts, entry_bytes: int):
+        """Receive buffer for the given per-sender counts: list of uint8 views, one per sender (None where empty)."""
+        import torch
+        total = int(sum(in_counts))
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.pgm_route_recv(self._h, kind, total, ctypes.byref(ptr)))
+        dev = f"cuda:{self.device}"
+        views, off = [], 0
+        for c in in_counts:
+            nb = int(c) * entry_bytes
+            views.append(torch.as_tensor(_DevArray(ptr.value + off, nb, "|u1", self), device=dev) if nb else None)
+            off += nb
+        return views
+
+    def route_build(self, n_in: int):
+        self._check(self._lib.pgm_route_build(self._h, n_in))
+
+    def route_scan(self, rev_mode: bool, rnd: int):
+        buf = PgmRouteBuffer()
+        self._check(self._lib.pgm_route_scan(self._h, int(rev_mode), rnd, ctypes.byref(buf)))
+        return [int(buf.count[d]) for d in range(buf.world)], self._segments(buf), buf.entry_bytes
+
+    def route_probe(self, rev_mode: bool, rnd: int, in_counts):
+        buf = PgmRouteBuffer()
+        arr = (ctypes.c_uint64 * len(in_counts))(*[int(x) for x in in_counts])
+        self._check(self._lib.pgm_route_probe(self._h, int(rev_mode), rnd, arr, ctypes.byref(buf)))
+        return [int(buf.count[d]) for d in range(buf.world)], self._segments(buf), buf.entry_bytes
+
+    def route_verify(self, rev_mode: bool, n_in: int):
+        self._check(self._lib.pgm_route_verify(self._h, int(rev_mode), n_in))
+
     def kernel_launches(self) -> int:
         return int(self._lib.pgm_kernel_launches(self._h))
 
@@ -331,36 +393,122 @@ def all_gather_text(share_host, pg_len: int, rank: int, world: int, device, bufs
     return full[:pg_len]
 
 
-def merge_accumulators(m: GpuReadsMatcher, group=None):
-    """The one exchange step of the sharded path: per-read MIN / SUM all-reduce of the pass
-    accumulators over NCCL (NVLink / NVSwitch).  The rarely used ones are merged only when some
-    rank touched them."""
-    import torch
-    import torch.distributed as dist
+class TorchComm:
+    """The collectives the sharded schemes need, over torch.distributed (NCCL across GPUs: NVLink / NVSwitch; gloo in the
+    CPU tests).  Tests substitute an object with the same methods that connects several contexts inside one process."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._peers = [dist.get_global_rank(group, r) for r in range(self.world)] if group is not None else list(range(self.world))
+
+    def all_reduce(self, t, op: str):
+        import torch.distributed as dist
+        dist.all_reduce(t, op={"min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}[op], group=self.group)
+
+    def exchange_counts(self, counts, device):
+        """counts[d] = entries this rank sends to d  ->  list of entries this rank receives from every sender."""
+        import torch
+        import torch.distributed as dist
+        mine = torch.tensor(counts, dtype=torch.int64, device=device)
+        allc = torch.empty(self.world * self.world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        return allc.view(self.world, self.world)[:, self.rank].tolist()
+
+    def all_to_all(self, recv, send):
+        """send[d] -> rank d, recv[s] <- rank s (uint8 tensors or None for empty segments)."""
+        import torch.distributed as dist
+        ops = []
+        for k in range(1, self.world):
+            d, s_ = (self.rank + k) % self.world, (self.rank - k) % self.world
+            if send[d] is not None:
+                ops.append(dist.P2POp(dist.isend, send[d], self._peers[d], group=self.group))
+            if recv[s_] is not None:
+                ops.append(dist.P2POp(dist.irecv, recv[s_], self._peers[s_], group=self.group))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        if recv[self.rank] is not None:
+            recv[self.rank].copy_(send[self.rank])
+        for r in reqs:
+            r.wait()
+
+
+def _as_comm(comm_or_group):
+    return comm_or_group if hasattr(comm_or_group, "all_reduce") else TorchComm(comm_or_group)
+
+
+def merge_accumulators(m, comm=None):
+    """The one exchange step of the text-sharded path: per-read MIN / SUM all-reduce of the pass accumulators over NCCL
+    (NVLink / NVSwitch).  `touched` is MAX-reduced IN PLACE first — resolve_kernel gates on it, so every rank must see the
+    merged flag — and the three rarely used accumulators are merged only when some rank touched them."""
+    comm = _as_comm(comm)
     acc = m.accumulators()
-    dist.all_reduce(acc["best_key"], op=dist.ReduceOp.MIN, group=group)
-    flag = acc["touched"].clone()
-    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-    if int(flag.item()):
-        dist.all_reduce(acc["first_other_order"], op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(acc["same_pos_mask"], op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(acc["same_pos_mm"], op=dist.ReduceOp.MIN, group=group)
+    comm.all_reduce(acc["best_key"], "min")
+    comm.all_reduce(acc["touched"], "max")
+    if int(acc["touched"].item()):
+        comm.all_reduce(acc["first_other_order"], "min")
+        comm.all_reduce(acc["same_pos_mask"], "sum")
+        comm.all_reduce(acc["same_pos_mm"], "min")
     m.put_accumulators()
     return acc
 
 
-def run_plan_sharded(m: GpuReadsMatcher, plan: MatchPlan, rev_compl_pg: bool = True, group=None, merge=merge_accumulators):
+def run_plan_sharded(m, plan: MatchPlan, rev_compl_pg: bool = True, comm=None, merge=merge_accumulators):
     """Runs the matcher phases on a context that holds one text shard; after every scan the
     per-read accumulators are merged across ranks, then every rank applies the decision, so the
     per-read state stays replicated."""
+    comm = _as_comm(comm)
     for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
         if ilv == "c":
             raise PgmError(-6, "matching mode 'c' indexes the whole text: it shards by reads only (no text shards)")
         m.match_begin(seed_len, parts, max_mm, min_mm, cont, ilv)
         for rev in ((False, True) if rev_compl_pg else (False,)):
             m.scan_pass(rev)
-            merge(m, group)
+            merge(m, comm)
             m.resolve_pass(rev)
+
+
+def read_ranges(n_reads: int, world: int):
+    """Even read ranges of the routed / read-sharded schemes: rank g owns [b[g], b[g+1])."""
+    return [(n_reads * g) // world for g in range(world + 1)]
+
+
+def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total: int, round_windows: int = 0) -> dict:
+    """The routed scheme (include/pgrc_gpu_matcher.h, pgm_route_*): this rank's context holds the whole text and its own
+    read range (`read_ranges`).  Per phase the seeds are exchanged once (all-to-all by hash owner); per pass and round the
+    windows of this rank's text range go to the hash owners and the candidates they find go to the read owners.  Returns
+    the bytes this rank sent per kind."""
+    comm = _as_comm(comm)
+    dev = f"cuda:{m.device}" if isinstance(m.device, int) else m.device
+    m.route_config(comm.rank, comm.world, read_ranges(n_reads_total, comm.world), round_windows)
+    sent = {"patterns": 0, "windows": 0, "candidates": 0}
+
+    def exchange(kind, counts, segs, eb):
+        in_counts = comm.exchange_counts(counts, dev)
+        recv = m.route_recv(kind, in_counts, eb)
+        comm.all_to_all(recv, segs)
+        return in_counts
+
+    for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
+        if ilv:
+            raise PgmError(-6, "the routed scheme covers matching modes 'd'/'D' (contiguous seeds); use read ranges for 'i' and 'c'")
+        counts, segs, eb = m.route_begin(seed_len, parts, max_mm, min_mm, cont)
+        sent["patterns"] += sum(counts) * eb
+        in_counts = exchange(PGM_ROUTE_PATTERNS, counts, segs, eb)
+        m.route_build(sum(in_counts))
+        rounds = m.route_rounds()
+        for rev in ((False, True) if rev_compl_pg else (False,)):
+            for rnd in range(rounds):
+                counts, segs, eb = m.route_scan(rev, rnd)
+                sent["windows"] += sum(counts) * eb
+                win_in = exchange(PGM_ROUTE_WINDOWS, counts, segs, eb)
+                counts, segs, eb = m.route_probe(rev, rnd, win_in)
+                sent["candidates"] += sum(counts) * eb
+                cand_in = exchange(PGM_ROUTE_CANDIDATES, counts, segs, eb)
+                m.route_verify(rev, sum(cand_in))
+            m.resolve_pass(rev)
+    return {"sent_bytes": sent, "rounds_per_pass": rounds}
 
 
 def map_reads_into_pg_sharded(text, lq_packed, n_packed, read_len: int, *, rank: int, world: int, device: int,
@@ -380,7 +528,7 @@ def map_reads_into_pg_sharded(text, lq_packed, n_packed, read_len: int, *, rank:
         m.set_reads(lq_packed, n_packed, read_len)
         plan = MatchPlan.derive(read_len, reads_exact_matching_chars, min_chars_per_mismatch, matching_mode,
                                 pre_reads_exact_matching_chars, pre_matching_mode)
-        run_plan_sharded(m, plan, rev_compl_pg, group)
+        run_plan_sharded(m, plan, rev_compl_pg, TorchComm(group))
         return m.get_results()
     finally:
         if own:

@@ -218,9 +218,6 @@ def adversarial(seed: int, read_len: int = 100, n_reads: int = 3000, text_len: i
 
 
 # ---------------------------------------------------------------------------------------------
-# Device-side generator for the full-size bench workloads (same shapes as `workload`, built with
-# torch on the GPU because numpy needs minutes for 10^7 reads).  torch is plumbing here.
-
 # BASELINE.json configs at matcher level: genome length, LQ reads handed to the
 # matcher, read length, substitution rate, pseudogenome length / genome length.
 # C1 and C2 sizes are the reference's own (probed) matcher inputs; C3-C5 are the survey's estimates.
@@ -240,62 +237,95 @@ def scaled_config(name: str, scale: float = 1.0) -> dict:
     return c
 
 
-def workload_device(genome_len: int, n_reads: int, read_len: int, err: float, copies: float, seed: int,
-                    device, mean_contig: int = 4000, chunk: int = 1 << 20):
-    """Returns (text_ascii uint8[pg_len], lq_packed uint8[n_reads, ceil(L/4)]) as torch tensors on
-    `device`: uniform-random genome, contigs in random orientation repeated `copies` times, reads
-    from uniform positions, 50 % reverse-complemented, i.i.d. substitutions with probability `err`
-    and at least one per read (the matcher only sees error-containing reads)."""
+# ---------------------------------------------------------------------------------------------
+# Counter-based generator (pgrc_b200/csrc/pgs_synth.cu -> libpgrc_synth.so): every byte is a pure function of
+# (seed, index), bit-identical on the host (OpenMP) and on the device (kernel).  This is what the bench and the
+# full-size parity tests use: fixtures under tests/golden/ hold what the reference / the oracle computed in the
+# build container for inputs that the GPU box re-creates from the same parameters.
+import ctypes as _ct
+import os as _os
+
+SYNTH_LIB_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "libpgrc_synth.so")
+_synth_lib = None
+
+
+class PgsParams(_ct.Structure):
+    _fields_ = [("seed", _ct.c_uint64), ("genome_len", _ct.c_uint64), ("text_len", _ct.c_uint64), ("contig", _ct.c_uint32),
+                ("read_len", _ct.c_uint32), ("err_q24", _ct.c_uint32), ("reserved", _ct.c_uint32)]
+
+
+def _synth():
+    global _synth_lib
+    if _synth_lib is None:
+        if not _os.path.exists(SYNTH_LIB_PATH):
+            raise ImportError(f"{SYNTH_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = _ct.CDLL(SYNTH_LIB_PATH)
+        for fn in (lib.pgs_text, lib.pgs_reads):
+            fn.restype = _ct.c_int
+            fn.argtypes = [_ct.POINTER(PgsParams), _ct.c_void_p, _ct.c_uint64, _ct.c_uint64]
+        _synth_lib = lib
+    return _synth_lib
+
+
+def hashed_params(genome_len: int, n_reads: int, read_len: int, err: float, copies: float, seed: int, contig: int = 4000) -> PgsParams:
+    return PgsParams(seed, genome_len, int(genome_len * copies), contig, read_len, int(round(err * (1 << 24))), 0)
+
+
+def hashed_text(p: PgsParams, begin: int = 0, count: int | None = None, device="cpu"):
+    """ASCII text [begin, begin + count) as a torch uint8 tensor on `device`."""
     import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    G, L = genome_len, read_len
-    genome = torch.randint(0, 4, (G,), dtype=torch.uint8, device=device, generator=g)
-    pieces = []
-    remaining = copies
-    while remaining > 1e-9:
-        frac = min(1.0, remaining)
-        span = max(1, int(G * frac))
-        lo = 0 if span >= G else int(torch.randint(0, G - span + 1, (1,), device=device, generator=g).item())
-        ncut = max(0, span // max(1, mean_contig) - 1)
-        cuts = torch.unique(torch.randint(lo + 1, lo + span, (ncut,), device=device, generator=g)) if ncut and span > 1 \
-            else torch.empty(0, dtype=torch.int64, device=device)
-        bounds = torch.cat([torch.tensor([lo], device=device), cuts, torch.tensor([lo + span], device=device)])
-        flips = torch.rand(bounds.numel() - 1, device=device, generator=g) < 0.5
-        for s in range(lo, lo + span, 1 << 26):
-            pos = torch.arange(s, min(lo + span, s + (1 << 26)), device=device)
-            seg = torch.searchsorted(bounds, pos, right=True) - 1
-            f = flips[seg]
-            src = torch.where(f, bounds[seg] + bounds[seg + 1] - 1 - pos, pos)
-            piece = genome[src]
-            pieces.append(torch.where(f, 3 - piece, piece))
-        remaining -= frac
-    text = torch.cat(pieces)
-    del pieces
-    lut = torch.tensor([ord(c) for c in "ACGT"], dtype=torch.uint8, device=device)
-    for s in range(0, text.numel(), 1 << 28):          # codes -> ASCII in place, chunked (an int64 index of the whole text would not fit)
-        text[s:s + (1 << 28)] = lut[text[s:s + (1 << 28)].long()]
-    plen = (L + 3) // 4
-    packed = torch.empty((n_reads, plen), dtype=torch.uint8, device=device)
-    ar = torch.arange(L, device=device)
-    for s in range(0, n_reads, chunk):
-        m = min(chunk, n_reads - s)
-        start = torch.randint(0, G - L + 1, (m,), device=device, generator=g)
-        flip = torch.rand(m, device=device, generator=g) < 0.5
-        idx = torch.where(flip[:, None], start[:, None] + (L - 1 - ar)[None, :], start[:, None] + ar[None, :])
-        r = genome[idx]
-        r = torch.where(flip[:, None], 3 - r, r)
-        mask = torch.rand((m, L), device=device, generator=g) < err
-        none = ~mask.any(dim=1)
-        forced = torch.randint(0, L, (m,), device=device, generator=g)
-        mask |= none[:, None] & (ar[None, :] == forced[:, None])
-        shift = torch.randint(1, 4, (m, L), dtype=torch.uint8, device=device, generator=g)
-        r = torch.where(mask, (r + shift) & 3, r)
-        if plen * 4 != L:
-            r = torch.cat([r, torch.zeros((m, plen * 4 - L), dtype=torch.uint8, device=device)], dim=1)
-        r = r.view(m, plen, 4)
-        packed[s:s + m] = (r[:, :, 0] << 6) | (r[:, :, 1] << 4) | (r[:, :, 2] << 2) | r[:, :, 3]
-    return text, packed
+    count = p.text_len - begin if count is None else count
+    out = torch.empty(count, dtype=torch.uint8, device=device)
+    if out.is_cuda:
+        torch.cuda.current_stream(out.device).synchronize()
+    with (torch.cuda.device(out.device) if out.is_cuda else _NullCtx()):
+        rc = _synth().pgs_text(_ct.byref(p), out.data_ptr(), begin, count)
+        if out.is_cuda:
+            torch.cuda.synchronize(out.device)      # the generator launches on the legacy default stream
+    if rc:
+        raise RuntimeError(f"pgs_text failed ({rc})")
+    return out
+
+
+def hashed_reads(p: PgsParams, first: int, count: int, device="cpu"):
+    """Packed reads [first, first + count) (count x ceil(L/4) uint8) on `device`."""
+    import torch
+    out = torch.empty((count, (p.read_len + 3) // 4), dtype=torch.uint8, device=device)
+    if out.is_cuda:
+        torch.cuda.current_stream(out.device).synchronize()
+    with (torch.cuda.device(out.device) if out.is_cuda else _NullCtx()):
+        rc = _synth().pgs_reads(_ct.byref(p), out.data_ptr(), first, count)
+        if out.is_cuda:
+            torch.cuda.synchronize(out.device)
+    if rc:
+        raise RuntimeError(f"pgs_reads failed ({rc})")
+    return out
+
+
+def hashed_reads_at(p: PgsParams, indices) -> np.ndarray:
+    """Packed reads with the given global indices (host; for the sampled-oracle fixtures)."""
+    out = np.empty((len(indices), (p.read_len + 3) // 4), np.uint8)
+    lib = _synth()
+    for k, r in enumerate(indices):
+        rc = lib.pgs_reads(_ct.byref(p), out[k].ctypes.data, int(r), 1)
+        if rc:
+            raise RuntimeError(f"pgs_reads failed ({rc})")
+    return out
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def workload_hashed(name: str, scale: float = 1.0, seed: int = 20261017, device="cpu"):
+    """(params, text, packed reads) of a BASELINE config shape from the counter-based generator."""
+    c = scaled_config(name, scale)
+    p = hashed_params(**c, seed=seed)
+    return p, hashed_text(p, 0, None, device), hashed_reads(p, 0, c["n_reads"], device)
 
 
 def unpack_reads_ascii(packed: np.ndarray, read_len: int) -> np.ndarray:

@@ -80,45 +80,49 @@ class CpuShardMatcher:
             ob, oe = pg - span - (fe - 1), pg - span - fb + 1
         else:
             origin, ob, oe = self.slice_begin, fb, fe
-        a = self.acc
         for g in range(ob, oe):
             pats = self.table.get(_canon(sl[g - origin:g - origin + span:self.stride], n))
             if not pats:
                 continue
             for pat in pats:
-                r, j = divmod(pat, self.parts)
-                c_in, _, X = self.state[r]
-                if c_in <= self.min_mm or j * sh > g:
-                    continue
-                al = g - j * sh
-                if al + L > pg:
-                    continue
-                assert al - origin >= 0 and al - origin + L <= len(sl), "halo too small"
-                rep = pg - (al + L) if rev else al
-                has_pos = c_in != 255
-                limit = c_in - 1 if has_pos else self.max_mm
-                c = int(np.count_nonzero(self.reads[r] != sl[al - origin:al - origin + L]))
-                if c > limit:
-                    continue
-                order = (g << 8) | (self.parts - 1 - j)
-                if has_pos and X == rep:
-                    a["same_pos_mask"][r] |= 1 << j
-                    a["same_pos_mm"][r] = c
-                    a["touched"][0] = 1
-                else:
-                    cls = 0 if c <= self.min_mm else c
-                    a["best_key"][r] = min(int(a["best_key"][r]), (cls << 56) | (order << 8) | c)
-                    if has_pos:
-                        a["first_other_order"][r] = min(int(a["first_other_order"][r]), order)
-                        a["touched"][0] = 1
+                self._event(pat // self.parts, pat % self.parts, g, sl, origin, rev)
+
+    def _event(self, r, j, g, sl, origin, rev):
+        """One (window start g, read r, seed j) hit: what verify / apply_event do in the kernels."""
+        L, pg, sh, a = self.read_len, self.pg_len, self.shift, self.acc
+        c_in, _, X = self.state[r]
+        if c_in <= self.min_mm or j * sh > g:
+            return
+        al = g - j * sh
+        if al + L > pg:
+            return
+        assert al - origin >= 0 and al - origin + L <= len(sl), "halo too small"
+        rep = pg - (al + L) if rev else al
+        has_pos = c_in != 255
+        limit = c_in - 1 if has_pos else self.max_mm
+        c = int(np.count_nonzero(self.reads[r] != sl[al - origin:al - origin + L]))
+        if c > limit:
+            return
+        order = (g << 8) | (self.parts - 1 - j)
+        if has_pos and X == rep:
+            a["same_pos_mask"][r] |= 1 << j
+            a["same_pos_mm"][r] = c
+            a["touched"][0] = 1
+        else:
+            cls = 0 if c <= self.min_mm else c
+            a["best_key"][r] = min(int(a["best_key"][r]), (cls << 56) | (order << 8) | c)
+            if has_pos:
+                a["first_other_order"][r] = min(int(a["first_other_order"][r]), order)
+                a["touched"][0] = 1
 
     def resolve_pass(self, rev):
         n, L, pg = self.shift, self.read_len, self.pg_len
         a = self.acc
+        touched = int(a["touched"][0])      # like resolve_kernel: the rare accumulators are only read when the (merged) flag is set
         for r in range(self.n_reads):
             c_in, _, X = self.state[r]
-            best, o1 = int(a["best_key"][r]), int(a["first_other_order"][r])
-            mask, cx = int(a["same_pos_mask"][r]), int(a["same_pos_mm"][r])
+            best, o1 = int(a["best_key"][r]), (int(a["first_other_order"][r]) if touched else KEY_INF)
+            mask, cx = (int(a["same_pos_mask"][r]), int(a["same_pos_mm"][r])) if touched else (0, 255)
             if c_in <= self.min_mm:
                 continue
             limit = c_in - 1 if c_in != 255 else self.max_mm

@@ -69,3 +69,11 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import oracle|from oracle)", src, flags=re.M), f
                 assert "pgrc_oracle" not in src and "libpgrc_ref" not in src, f
+
+
+def test_route_buffer_layout_and_calls_without_gpu():
+    assert ctypes.sizeof(_lib.PgmRouteBuffer) == 8 + 8 + 4 + 4 + 8 * _lib.PGM_ROUTE_MAX_WORLD
+    lib = _lib.load()
+    assert lib.pgm_route_config(None, 0, 1, None, 0) == -1          # null context: invalid argument, no crash
+    from pgrc_b200 import matcher
+    assert matcher.read_ranges(10, 3) == [0, 3, 6, 10] and matcher.read_ranges(0, 2) == [0, 0, 0]

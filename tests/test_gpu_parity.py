@@ -161,40 +161,84 @@ def test_hot_seeds_duplicate_reads_and_homopolymers():
 
 
 def _run_sharded_on_one_gpu(inp, world, **kw):
-    """The text-sharded path with `world` contexts on ONE GPU: every context scans its text range, the per-read
-    accumulators are merged with plain torch ops (what NCCL MIN / SUM all-reduces do across GPUs), every context
-    applies the decision.  Exercises the shard geometry of the kernels (halos, RC coordinates of a slice)."""
-    import torch
-    ms = [matcher.GpuReadsMatcher(0, use_torch_stream=True) for _ in range(world)]
-    try:
-        pg_len = inp.text.size
-        for rank, m in enumerate(ms):
+    """The text-sharded path with `world` contexts on ONE GPU, one thread per rank: every context scans its text range and
+    the product's own run_plan_sharded / merge_accumulators exchange the per-read accumulators (tests/local_comm.py stands in
+    for the NCCL all-reduces).  Exercises the shard geometry of the kernels (halos, RC coordinates of a slice) AND the merge
+    protocol, including the in-place reduction of the `touched` flag that resolve_kernel gates on."""
+    from local_comm import LocalWorld
+    pg_len = inp.text.size
+    plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), kw.get("min_chars_per_mismatch", 3), kw.get("mode", "d"),
+                                    kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
+
+    def rank_body(rank, comm):
+        with matcher.GpuReadsMatcher(0, use_torch_stream=True) as m:
             sb, sl, ob, oe = matcher.shard_plan(pg_len, rank, world)
             m.set_text_shard(np.ascontiguousarray(inp.text[sb:sb + sl]), sb, pg_len, ob, oe)
             m.set_reads(inp.lq_packed, inp.n_packed if len(inp.n_reads) else None, inp.read_len)
-        plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), kw.get("min_chars_per_mismatch", 3), kw.get("mode", "d"),
-                                        kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
-        for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
-            for m in ms:
-                m.match_begin(seed_len, parts, max_mm, min_mm, cont, ilv)
-            for rev in ((False, True) if kw.get("rev_compl", True) else (False,)):
-                for m in ms:
-                    m.scan_pass(rev)
-                accs = [m.accumulators() for m in ms]
-                best = torch.stack([a["best_key"] for a in accs]).min(dim=0).values
-                first = torch.stack([a["first_other_order"] for a in accs]).min(dim=0).values
-                mask = torch.stack([a["same_pos_mask"] for a in accs]).sum(dim=0).to(torch.int32)
-                mm = torch.stack([a["same_pos_mm"] for a in accs]).min(dim=0).values
-                touched = torch.stack([a["touched"] for a in accs]).max(dim=0).values
-                for m, a in zip(ms, accs):
-                    a["best_key"].copy_(best); a["first_other_order"].copy_(first); a["same_pos_mask"].copy_(mask)
-                    a["same_pos_mm"].copy_(mm); a["touched"].copy_(touched)
-                    m.put_accumulators()
-                    m.resolve_pass(rev)
-        return [m.get_results() for m in ms]
-    finally:
-        for m in ms:
-            m.close()
+            matcher.run_plan_sharded(m, plan, kw.get("rev_compl", True), comm)
+            return m.get_results()
+
+    return LocalWorld(world).run(rank_body)
+
+
+def _run_routed_on_one_gpu(inp, world, round_windows=0, **kw):
+    """The routed scheme (pgm_route_*) with `world` contexts on ONE GPU, one thread per rank, driven by the product's
+    run_plan_routed; returns the per-rank results concatenated in read order (rank g owns read range g)."""
+    from local_comm import LocalWorld
+    plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), kw.get("min_chars_per_mismatch", 3), kw.get("mode", "d"),
+                                    kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
+    n_lq, n_n = inp.lq_packed.shape[0], (inp.n_packed.shape[0] if len(inp.n_reads) else 0)
+    n = n_lq + n_n
+    rb = matcher.read_ranges(n, world)
+
+    def rank_body(rank, comm):
+        lo, hi = rb[rank], rb[rank + 1]
+        lq = inp.lq_packed[min(lo, n_lq):min(hi, n_lq)]          # global read index: LQ reads first, then N reads
+        nn = inp.n_packed[max(lo, n_lq) - n_lq:max(hi, n_lq) - n_lq] if n_n else None
+        with matcher.GpuReadsMatcher(0, use_torch_stream=True) as m:
+            m.set_text(inp.text)
+            m.set_reads(np.ascontiguousarray(lq), np.ascontiguousarray(nn) if nn is not None and len(nn) else None, inp.read_len)
+            info = matcher.run_plan_routed(m, plan, kw.get("rev_compl", True), comm, n, round_windows)
+            return m.get_results(), info
+
+    outs = LocalWorld(world).run(rank_body)
+    res = [o[0] for o in outs]
+    return (np.concatenate([r.pos for r in res]), np.concatenate([r.rc for r in res]), np.concatenate([r.mm for r in res]),
+            sum(r.matched for r in res), [o[1] for o in outs], res)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("kw", [dict(), dict(pre_seed=100), dict(mode="D"), dict(seed=45, rev_compl=False), dict(seed=100), dict(pre_seed=50)])
+def test_routed_contexts_match_oracle(world, kw):
+    """Hash-partitioned seed table + routed windows / candidates: the result is the single-matcher result bit for bit —
+    adversarial inputs (hot seeds with chains, N reads, palindromes: the rule-3 accumulators), the scaled config shapes,
+    one and several rounds per pass."""
+    for inp, rw in ((synth.adversarial(61, 100, n_reads=2000, text_len=30000), 0), (synth.adversarial(62, 150, n_reads=1500, text_len=30000), 8192),
+                    (synth.workload(300_000, 40_000, 150, 0.005, seed=63, n_frac=0.03, name="c2 shape"), 65536)):
+        want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+        pos, rc, mm, matched, infos, res = _run_routed_on_one_gpu(inp, world, rw, **kw)
+        bad = np.nonzero((pos != want.pos) | (rc != want.rc) | (mm != want.mm))[0]
+        assert bad.size == 0, (f"{inp.name} world {world} {kw}: {bad.size} reads differ, first {bad[:5]}: gpu {pos[bad[:5]]} "
+                               f"{rc[bad[:5]]} {mm[bad[:5]]} oracle {want.pos[bad[:5]]} {want.rc[bad[:5]]} {want.mm[bad[:5]]}")
+        assert matched == want.matched
+        if rw:
+            assert infos[0]["rounds_per_pass"] > 1
+        assert sum(i["sent_bytes"]["windows"] for i in infos) > 0 and sum(r.stats["candidates"] for r in res) > 0
+
+
+def test_routed_hot_seeds_and_empty_ranks():
+    """Duplicated reads (one hash owner gets almost every pattern, chains behind one slot) and more ranks than reads."""
+    rng = np.random.default_rng(64)
+    g = synth.random_genome(20_000, rng)
+    dup = np.repeat(synth.sample_reads(g, 3, 100, 0.01, rng), 3000, axis=0)
+    inp = synth.MatcherInputs(g, np.concatenate([dup, synth.sample_reads(g, 2000, 100, 0.01, rng)]), np.zeros((0, 100), np.uint8), 100, "skew")
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len)
+    pos, rc, mm, matched, _, _ = _run_routed_on_one_gpu(inp, 4)
+    assert np.array_equal(pos, want.pos) and np.array_equal(rc, want.rc) and np.array_equal(mm, want.mm) and matched == want.matched
+    tiny = synth.MatcherInputs(g, synth.sample_reads(g, 3, 100, 0.01, rng), np.zeros((0, 100), np.uint8), 100, "tiny")
+    want = oracle.oracle_map_reads(tiny.text, tiny.lq_packed, None, 100)
+    pos, rc, mm, matched, _, _ = _run_routed_on_one_gpu(tiny, 8)
+    assert np.array_equal(pos, want.pos) and np.array_equal(rc, want.rc) and np.array_equal(mm, want.mm)
 
 
 @pytest.mark.parametrize("world", [2, 3])

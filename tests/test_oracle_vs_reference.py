@@ -40,9 +40,9 @@ def test_workload_shapes():
 
 
 def test_device_generator_shape():
-    # the bench generator (torch) produces inputs the reference accepts and mostly matches
+    # the bench generator (counter-based, pgs_synth.cu) produces inputs the reference accepts and mostly matches
     c = synth.scaled_config("c2", 0.001)
-    text, packed = synth.workload_device(**c, seed=5, device="cpu")
+    _, text, packed = synth.workload_hashed("c2", 0.001, seed=5)
     text, packed = text.numpy(), packed.numpy()
     asc = synth.unpack_reads_ascii(packed, c["read_len"])
     r = oracle.ref_map_reads(text, asc, None, c["read_len"])

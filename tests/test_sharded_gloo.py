@@ -148,3 +148,45 @@ def test_2d_sharded_four_ranks_gloo(tmp_path):
         lo, hi = int(got["lo"]), int(got["hi"])
         assert np.array_equal(got["pos"], want.pos[lo:hi]), f"rank {rank}"
         assert np.array_equal(got["rc"], want.rc[lo:hi]) and np.array_equal(got["mm"], want.mm[lo:hi])
+
+
+def _worker_routed(rank, world, port, case, kw, round_windows, ret_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from cpu_route_model import CpuRouteMatcher
+    from pgrc_b200 import matcher, synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inp = synth.adversarial(case["seed"], case["L"], n_reads=case["n_reads"], text_len=case["text_len"])
+    reads = list(inp.lq_reads) + list(inp.n_reads)
+    rb = matcher.read_ranges(len(reads), world)
+    m = CpuRouteMatcher()
+    m.set_text(inp.text)
+    m.set_reads(reads[rb[rank]:rb[rank + 1]], None, inp.read_len)
+    plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), kw.get("min_chars_per_mismatch", 3), kw.get("mode", "d"),
+                                    kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
+    info = matcher.run_plan_routed(m, plan, kw.get("rev_compl", True), matcher.TorchComm(), len(reads), round_windows)
+    res = m.get_results()
+    np.savez(os.path.join(ret_dir, f"rank{rank}.npz"), pos=res.pos, rc=res.rc, mm=res.mm, lo=rb[rank], hi=rb[rank + 1], rounds=info["rounds_per_pass"])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,round_windows", [(2, 0), (3, 1024)])
+@pytest.mark.parametrize("kw", [dict(), dict(pre_seed=100), dict(mode="D")])
+def test_routed_ranks_gloo(tmp_path, world, round_windows, kw):
+    """The routed scheme's host logic (run_plan_routed: counts exchange, all-to-all of patterns / windows / candidates over
+    send/recv, rounds, local decision) over gloo; the per-rank kernels are the plain-Python model of tests/cpu_route_model.py."""
+    import oracle
+    from pgrc_b200 import synth
+    case = dict(seed=79, L=100, n_reads=200, text_len=4000)
+    mp.spawn(_worker_routed, args=(world, _free_port(), case, kw, round_windows, str(tmp_path)), nprocs=world, join=True)
+    inp = synth.adversarial(case["seed"], case["L"], n_reads=case["n_reads"], text_len=case["text_len"])
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+    assert want.matched > 20
+    for rank in range(world):
+        got = np.load(tmp_path / f"rank{rank}.npz")
+        lo, hi = int(got["lo"]), int(got["hi"])
+        assert np.array_equal(got["pos"], want.pos[lo:hi]), f"rank {rank}"
+        assert np.array_equal(got["rc"], want.rc[lo:hi]) and np.array_equal(got["mm"], want.mm[lo:hi])
+        assert (int(got["rounds"]) > 1) == bool(round_windows)

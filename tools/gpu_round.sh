@@ -1,22 +1,42 @@
 #!/bin/bash
-# One GPU-box session: parity tests, bench, ncu launch list, ncu full capture of the scan + build kernels.
-# Usage (through gpurun): bash tools/gpu_round.sh [tag] [quick]
-TAG=${1:-r01}
-MODE=${2:-full}
+# One GPU-box session (through gpurun): what each step does is selected by words in $2.
+#   bash tools/gpu_round.sh <tag> "routed tests bench ncu"
+TAG=${1:-r02}
+WHAT=${2:-"tests bench"}
 OUT=gpurun_out
 mkdir -p $OUT
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu_$TAG.txt 2>&1
-timeout 900 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
-tail -15 $OUT/pytest_gpu_$TAG.log
-timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"
-cat $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
-if [ "$MODE" = "quick" ]; then exit 0; fi
-timeout 600 python bench.py --workload c1 --no-cpu-baseline > $OUT/bench_c1_$TAG.json 2>> $OUT/bench_$TAG.err
-cat $OUT/bench_c1_$TAG.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:pgm:: -c 200 --csv \
-    --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_launches_$TAG.log 2>&1
-echo "ncu launches exit $?"
-timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'pgm::(scan_kernel|build_table_kernel)' -s 3 -c 3 \
-    -f -o $OUT/scan_$TAG python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1
-echo "ncu full exit $?"
-ls -la $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
+(nproc; free -g | head -2) >> $OUT/gpu_$TAG.txt 2>&1
+has() { [[ " $WHAT " == *" $1 "* ]]; }
+if has routed; then    # the new multi-GPU scheme first (several contexts on this one GPU): fail fast
+    timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "routed or sharded" > $OUT/pytest_routed_$TAG.log 2>&1; echo "pytest routed exit $?" | tee -a $OUT/pytest_routed_$TAG.log
+    tail -25 $OUT/pytest_routed_$TAG.log
+fi
+if has tests; then
+    timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest_gpu_$TAG.log
+    tail -25 $OUT/pytest_gpu_$TAG.log
+fi
+if has bench; then     # the default bench (C5, N = 1) with the full-size parity checks
+    timeout 1200 python bench.py --verify --steps 5 --warmup 3 > $OUT/bench_c5_n1_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"
+    cat $OUT/bench_c5_n1_$TAG.json; tail -5 $OUT/bench_$TAG.err
+fi
+if has benchall; then  # the other configs at N = 1, with their fixtures
+    for w in c1 c2 c3 c4; do
+        timeout 900 python bench.py --workload $w --verify --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_${w}_n1_$TAG.json 2>> $OUT/bench_$TAG.err
+        cat $OUT/bench_${w}_n1_$TAG.json
+    done
+fi
+if has ref; then
+    timeout 1200 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err; cat $OUT/bench_ref_$TAG.json
+fi
+if has ncu; then
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:pgm:: -c 400 --csv \
+        --log-file $OUT/launches_c5_$TAG.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_launches_$TAG.log 2>&1
+    echo "ncu launches exit $?"
+fi
+if has ncufull; then   # one full capture of the scan kernel at C4 size (C5's footprint makes the replays' save/restore slow)
+    timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'pgm::scan_kernel' -s 2 -c 1 \
+        -f -o $OUT/scan_c4_$TAG python bench.py --workload c4 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1
+    echo "ncu full exit $?"
+fi
+ls -la $OUT | tail -30
