@@ -234,6 +234,35 @@ int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer 
 int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *in_counts, pgm_route_buffer *send);
 int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_candidates_in);
 
+/* ---- several GPUs behind one handle (one process, one host thread per GPU inside the library) ----------------
+ * What the C++ host side of PgRC uses (pgrc_b200/host/GpuReadsMatchers.cpp; PGRC_GPU_DEVICES=0,1,...): the same
+ * step-wise calls as a single context, on a group of contexts.  With one device it IS the single-context path
+ * (fused scan kernel).  With several: matching modes 'd'/'D' run the routed scheme above, the exchanges being
+ * peer-to-peer copies over NVLink (cudaMemcpyPeerAsync between the GPUs' buffers); modes 'i'/'I' and 'c'/'C' give
+ * every GPU the whole text and a read range (no exchange).  A device may be listed more than once (several
+ * contexts on one GPU: how the single-GPU test box exercises this code).  Inputs are host or device pointers as
+ * for a context (device pointers must be accessible from every listed GPU); outputs cover all reads, in the
+ * global read order (LQ reads, then N reads).  Errors: pgm_group_last_error. */
+typedef struct pgm_group pgm_group;
+int pgm_group_create(int n_devices, const int *devices /* NULL = 0 .. n_devices-1 */, pgm_group **out);
+void pgm_group_destroy(pgm_group *g);
+const char *pgm_group_last_error(const pgm_group *g);   /* g may be NULL: last pgm_group_create error */
+int pgm_group_size(const pgm_group *g);
+int pgm_group_set_text(pgm_group *g, const char *text, uint64_t pg_len);
+int pgm_group_set_reads(pgm_group *g, const uint8_t *lq_packed, uint32_t n_lq, const uint8_t *n_packed, uint32_t n_n,
+                        uint32_t read_len);
+int pgm_group_upload(pgm_group *g);
+/* initMatching / initMatchingContinuation of the exact, default (interleaved = 0) or interleaved matcher */
+int pgm_group_match_begin(pgm_group *g, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm,
+                          int continuation, int interleaved);
+/* executeMatching(revCompMode): scan (+ exchanges) + the per-read decision */
+int pgm_group_pass(pgm_group *g, int rev_mode);
+int pgm_group_copmem_begin(pgm_group *g, uint32_t part_len, uint32_t max_mm, uint32_t min_mm, int continuation);
+int pgm_group_copmem_pass(pgm_group *g, int rev_mode);
+int pgm_group_get_results(pgm_group *g, uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats);
+int pgm_group_get_mismatches(pgm_group *g, uint64_t *out_offsets, uint8_t *out_pos, uint8_t *out_syms,
+                             uint64_t capacity, uint64_t *total);
+
 /* ---- the whole stage on one GPU ---------------------------------------------------------
  * pgm_map_reads replaces the matching part of PgTools::mapReadsIntoPg
  * (ReadsMatchers.cpp:693-783) for matching modes 'd'/'D' (DefaultReadsApproxMatcher), 'i'/'I'

@@ -24,7 +24,10 @@ EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pg
            "pgm_scan_pass", "pgm_get_accumulators", "pgm_put_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_get_mismatches", "pgm_copmem_begin", "pgm_copmem_pass", "pgm_map_reads",
            "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings",
            "pgm_route_config", "pgm_route_rounds", "pgm_route_begin", "pgm_route_recv", "pgm_route_build", "pgm_route_scan", "pgm_route_probe",
-           "pgm_route_verify"]
+           "pgm_route_verify",
+           "pgm_group_create", "pgm_group_destroy", "pgm_group_last_error", "pgm_group_size", "pgm_group_set_text", "pgm_group_set_reads",
+           "pgm_group_upload", "pgm_group_match_begin", "pgm_group_pass", "pgm_group_copmem_begin", "pgm_group_copmem_pass",
+           "pgm_group_get_results", "pgm_group_get_mismatches"]
 
 KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators",
                 "scan_filter", "scan_probe", "scan_verify", "mismatches", "copmem_index", "copmem_query",
@@ -112,5 +115,18 @@ def load() -> ctypes.CDLL:
     lib.pgm_route_scan.restype = ci; lib.pgm_route_scan.argtypes = [vp, ci, u32, rb]
     lib.pgm_route_probe.restype = ci; lib.pgm_route_probe.argtypes = [vp, ci, u32, ctypes.POINTER(u64), rb]
     lib.pgm_route_verify.restype = ci; lib.pgm_route_verify.argtypes = [vp, ci, u64]
+    lib.pgm_group_create.restype = ci; lib.pgm_group_create.argtypes = [ci, ctypes.POINTER(ci), ctypes.POINTER(vp)]
+    lib.pgm_group_destroy.restype = None; lib.pgm_group_destroy.argtypes = [vp]
+    lib.pgm_group_last_error.restype = ctypes.c_char_p; lib.pgm_group_last_error.argtypes = [vp]
+    lib.pgm_group_size.restype = ci; lib.pgm_group_size.argtypes = [vp]
+    lib.pgm_group_set_text.restype = ci; lib.pgm_group_set_text.argtypes = [vp, vp, u64]
+    lib.pgm_group_set_reads.restype = ci; lib.pgm_group_set_reads.argtypes = [vp, vp, u32, vp, u32, u32]
+    lib.pgm_group_upload.restype = ci; lib.pgm_group_upload.argtypes = [vp]
+    lib.pgm_group_match_begin.restype = ci; lib.pgm_group_match_begin.argtypes = [vp, u32, u32, u32, u32, ci, ci]
+    lib.pgm_group_pass.restype = ci; lib.pgm_group_pass.argtypes = [vp, ci]
+    lib.pgm_group_copmem_begin.restype = ci; lib.pgm_group_copmem_begin.argtypes = [vp, u32, u32, u32, ci]
+    lib.pgm_group_copmem_pass.restype = ci; lib.pgm_group_copmem_pass.argtypes = [vp, ci]
+    lib.pgm_group_get_results.restype = ci; lib.pgm_group_get_results.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PgmStats)]
+    lib.pgm_group_get_mismatches.restype = ci; lib.pgm_group_get_mismatches.argtypes = [vp, vp, vp, vp, u64, ctypes.POINTER(u64)]
     _lib = lib
     return lib

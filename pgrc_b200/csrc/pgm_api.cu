@@ -1592,3 +1592,5 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
 }
 
 } // extern "C"
+
+#include "pgm_group.inl"

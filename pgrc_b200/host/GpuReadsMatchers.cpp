@@ -9,13 +9,9 @@
 // The packed read buffers are taken exactly as PackedConstantLengthReadsSet holds them
 // (PackedConstantLengthReadsSet.h:17-18,40).  SumOfConstantLengthReadsSets (ReadsSetInterface.h:45-89) keeps its two
 // sets private and has no accessor; until the two one-line accessors of INTEGRATION.md exist upstream, this
-// translation unit reads them through the `private -> public` trick below (same object layout, nothing else relies
-// on it).  If a reads set is of an unknown class, the reads are re-packed through the public getRead() interface.
-#include "utils/helper.h"            // everything ReadsSetInterface.h pulls in comes first, with normal access rules
-#include "readsset/ReadsSetBase.h"
-#define private public
-#include "readsset/ReadsSetInterface.h"
-#undef private
+// translation unit reaches them through pointers to members obtained by explicit template instantiation (which the
+// language exempts from access checking: [temp.spec]/6) — no macro games, no assumption about the object layout.  If
+// a reads set is of an unknown class, the reads are re-packed through the public getRead() interface.
 #include "GpuReadsMatchers.h"
 
 #include <thread>
@@ -23,6 +19,15 @@
 
 #include <cstdlib>
 #include <cstring>
+
+namespace {
+    // pointer-to-private-member access (see the header comment)
+    template <class Tag, typename Tag::type Member> struct MemberThief { friend typename Tag::type stolen(Tag) { return Member; } };
+    struct SumFirst { typedef ConstantLengthReadsSetInterface *SumOfConstantLengthReadsSets::*type; friend type stolen(SumFirst); };
+    struct SumSecond { typedef ConstantLengthReadsSetInterface *SumOfConstantLengthReadsSets::*type; friend type stolen(SumSecond); };
+    template struct MemberThief<SumFirst, &SumOfConstantLengthReadsSets::clrs1>;
+    template struct MemberThief<SumSecond, &SumOfConstantLengthReadsSets::clrs2>;
+}
 
 namespace PgTools {
 
@@ -35,11 +40,38 @@ namespace PgTools {
                         const string &pgDestFilePrefix, IndexesMapping *orgIndexesMapping);
 
     // ------------------------------------------------------------------------------------------ session
-    void GpuMatcherSession::check(int rc, pgm_ctx *c, const char *what) {
+    void GpuMatcherSession::check(int rc, pgm_group *g, const char *what) {
         if (rc == PGM_OK) return;
         // error convention of the reference: message on stderr + exit (e.g. ReadsMatchers.cpp:737-739)
-        fprintf(stderr, "GPU matcher: %s failed: %s\n", what, pgm_last_error(c));
+        fprintf(stderr, "GPU matcher: %s failed: %s\n", what, pgm_group_last_error(g));
         exit(EXIT_FAILURE);
+    }
+
+    // PGRC_GPU_DEVICES = "0,1,2,3" (device ordinals; an ordinal may repeat) or "<count>" (devices 0 .. count-1);
+    // PGRC_GPU_DEVICE = one ordinal; default: device 0
+    vector<int> GpuMatcherSession::devicesFromEnvironment() {
+        vector<int> devs;
+        if (const char *list = getenv("PGRC_GPU_DEVICES")) {
+            const string s(list);
+            if (s.find(',') == string::npos) {
+                for (int k = 0; k < atoi(s.c_str()); k++) devs.push_back(k);
+            } else {
+                size_t at = 0;
+                while (at <= s.size()) {
+                    const size_t end = s.find(',', at) == string::npos ? s.size() : s.find(',', at);
+                    if (end > at) devs.push_back(atoi(s.substr(at, end - at).c_str()));
+                    at = end + 1;
+                }
+            }
+            if (devs.empty()) {
+                fprintf(stderr, "GPU matcher: PGRC_GPU_DEVICES=%s names no device.\n", list);
+                exit(EXIT_FAILURE);
+            }
+        } else {
+            const char *dev = getenv("PGRC_GPU_DEVICE");
+            devs.push_back(dev ? atoi(dev) : 0);
+        }
+        return devs;
     }
 
     namespace {
@@ -94,11 +126,12 @@ namespace PgTools {
             std::thread th;
             GpuWarmup() {
                 const char *env = getenv("PGRC_GPU_MATCHER");
-                if (env && *env && strcmp(env, "0") != 0)
+                if (env && strcmp(env, "1") == 0)
                     th = std::thread([] {
-                        const char *dev = getenv("PGRC_GPU_DEVICE");
-                        pgm_ctx *c = nullptr;
-                        if (pgm_create(dev ? atoi(dev) : 0, &c) == PGM_OK) pgm_destroy(c);
+                        for (int dev : GpuMatcherSession::devicesFromEnvironment()) {
+                            pgm_ctx *c = nullptr;
+                            if (pgm_create(dev, &c) == PGM_OK) pgm_destroy(c);
+                        }
                     });
             }
             void wait() { if (th.joinable()) th.join(); }
@@ -108,14 +141,15 @@ namespace PgTools {
 
     GpuMatcherSession::GpuMatcherSession(const char *pgPtr, uint64_t pgLength, ConstantLengthReadsSetInterface *readsSet) {
         gpuWarmup.wait();
-        const char *dev = getenv("PGRC_GPU_DEVICE");
-        check(pgm_create(dev ? atoi(dev) : 0, &ctx), nullptr, "pgm_create");
-        check(pgm_set_text(ctx, pgPtr, pgLength), ctx, "pgm_set_text");           // read-only: no in-place reverse complement
+        const vector<int> devs = devicesFromEnvironment();
+        check(pgm_group_create((int) devs.size(), devs.data(), &grp), nullptr, "pgm_group_create");
+        if (devs.size() > 1) cout << "GPU matcher: stage sharded over " << devs.size() << " device contexts." << endl;
+        check(pgm_group_set_text(grp, pgPtr, pgLength), grp, "pgm_group_set_text");   // read-only: no in-place reverse complement
         readsCount = readsSet->readsCount();
         PackedView a, b;
         if (auto *sum = dynamic_cast<SumOfConstantLengthReadsSets *>(readsSet)) {
-            a = viewOf(sum->clrs1);                                                 // LQ set, then N set: the global read index
-            b = viewOf(sum->clrs2);                                                 // of SumOfConstantLengthReadsSets
+            a = viewOf(sum->*stolen(SumFirst()));                                   // LQ set, then N set: the global read index
+            b = viewOf(sum->*stolen(SumSecond()));                                  // of SumOfConstantLengthReadsSets
         } else {
             a = viewOf(readsSet);
         }
@@ -125,39 +159,33 @@ namespace PgTools {
             // (never produced by pgrc-encoder: LQ is ACGT and N is ACGNT, or one single set) — re-pack both as ACGNT
             PackedView all;
             repack(readsSet, 0, readsCount, true, all);
-            check(pgm_set_reads(ctx, nullptr, 0, all.data, all.count, readsSet->maxReadLength()), ctx, "pgm_set_reads");
-            check(pgm_synchronize(ctx), ctx, "pgm_synchronize");
+            check(pgm_group_set_reads(grp, nullptr, 0, all.data, all.count, readsSet->maxReadLength()), grp, "pgm_group_set_reads");
+            check(pgm_group_upload(grp), grp, "pgm_group_upload");                  // the re-packed copy dies with this constructor
             return;
         }
-        check(pgm_set_reads(ctx, a.data, a.count, b.data, b.count, readsSet->maxReadLength()), ctx, "pgm_set_reads");
-        if (!a.owned.empty() || !b.owned.empty()) {
-            // re-packed copies die with this constructor: force the (lazy) upload now
-            check(pgm_get_results(ctx, nullptr, nullptr, nullptr, nullptr), ctx, "pgm_get_results");
-        }
+        check(pgm_group_set_reads(grp, a.data, a.count, b.data, b.count, readsSet->maxReadLength()), grp, "pgm_group_set_reads");
+        if (!a.owned.empty() || !b.owned.empty())
+            check(pgm_group_upload(grp), grp, "pgm_group_upload");                  // re-packed copies die with this constructor
     }
 
-    GpuMatcherSession::~GpuMatcherSession() { pgm_destroy(ctx); }
+    GpuMatcherSession::~GpuMatcherSession() { pgm_group_destroy(grp); }
 
     void GpuMatcherSession::begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation,
                                   bool interleaved) {
-        if (interleaved)
-            check(pgm_match_begin_interleaved(ctx, seedLength, parts, maxMismatches, minMismatches, continuation ? 1 : 0), ctx,
-                  "pgm_match_begin_interleaved");
-        else
-            check(pgm_match_begin(ctx, seedLength, parts, maxMismatches, minMismatches, continuation ? 1 : 0), ctx, "pgm_match_begin");
+        check(pgm_group_match_begin(grp, seedLength, parts, maxMismatches, minMismatches, continuation ? 1 : 0, interleaved ? 1 : 0), grp,
+              "pgm_group_match_begin");
     }
 
     void GpuMatcherSession::beginCopmem(uint32_t partLength, uint32_t maxMismatches, uint32_t minMismatches, bool continuation) {
-        check(pgm_copmem_begin(ctx, partLength, maxMismatches, minMismatches, continuation ? 1 : 0), ctx, "pgm_copmem_begin");
+        check(pgm_group_copmem_begin(grp, partLength, maxMismatches, minMismatches, continuation ? 1 : 0), grp, "pgm_group_copmem_begin");
     }
 
     void GpuMatcherSession::passCopmem(bool revCompMode) {
-        check(pgm_copmem_pass(ctx, revCompMode ? 1 : 0), ctx, "pgm_copmem_pass");
+        check(pgm_group_copmem_pass(grp, revCompMode ? 1 : 0), grp, "pgm_group_copmem_pass");
     }
 
     void GpuMatcherSession::pass(bool revCompMode) {
-        check(pgm_scan_pass(ctx, revCompMode ? 1 : 0), ctx, "pgm_scan_pass");
-        check(pgm_resolve_pass(ctx, revCompMode ? 1 : 0), ctx, "pgm_resolve_pass");
+        check(pgm_group_pass(grp, revCompMode ? 1 : 0), grp, "pgm_group_pass");
     }
 
     void GpuMatcherSession::fetch(vector<uint64_t> &readMatchPos, vector<bool> &readMatchRC, vector<uint8_t> *readMismatchesCount,
@@ -165,7 +193,7 @@ namespace PgTools {
         vector<uint8_t> rc(readsCount), mm(readsCount);
         readMatchPos.resize(readsCount);
         pgm_stats st;
-        check(pgm_get_results(ctx, readMatchPos.data(), rc.data(), mm.data(), &st), ctx, "pgm_get_results");
+        check(pgm_group_get_results(grp, readMatchPos.data(), rc.data(), mm.data(), &st), grp, "pgm_group_get_results");
         readMatchRC.resize(readsCount);
         for (uint_reads_cnt_max i = 0; i < readsCount; i++) readMatchRC[i] = rc[i] != 0;
         matchedReadsCount = (uint_reads_cnt_max) st.matched;
@@ -176,11 +204,11 @@ namespace PgTools {
 
     void GpuMatcherSession::fetchMismatches(vector<uint64_t> &offsets, vector<uint8_t> &pos, vector<uint8_t> &syms) {
         uint64_t total = 0;
-        check(pgm_get_mismatches(ctx, nullptr, nullptr, nullptr, 0, &total), ctx, "pgm_get_mismatches");
+        check(pgm_group_get_mismatches(grp, nullptr, nullptr, nullptr, 0, &total), grp, "pgm_group_get_mismatches");
         offsets.resize((size_t) readsCount + 1);
         pos.resize(total + 1);
         syms.resize(total + 1);
-        check(pgm_get_mismatches(ctx, offsets.data(), pos.data(), syms.data(), total, &total), ctx, "pgm_get_mismatches");
+        check(pgm_group_get_mismatches(grp, offsets.data(), pos.data(), syms.data(), total, &total), grp, "pgm_group_get_mismatches");
     }
 
     // ------------------------------------------------------------------------------------------ exact path
@@ -353,15 +381,50 @@ namespace PgTools {
         // to be; the reference sources stay untouched.
         if (readsSet->getReadsSetProperties()->readsCount == 0)
             readsSet->getReadsSetProperties()->readsCount = readsSet->readsCount();
+        // Selection.  Mode letter 'g' / 'G' (dev build: -s g38): the GPU matchers with the semantics of 'd' / 'D'.
+        // PGRC_GPU_MATCHER=1: the GPU matchers for the letters the CPU build knows ('d', 'i', 'c': same letter in the archive
+        // header, byte-identical archives).  Unset, empty or 0: the reference's own function.  Anything else is an error —
+        // a mistyped value must not become a silent CPU run.
         const char *env = getenv("PGRC_GPU_MATCHER");
-        const bool wantGpu = env && *env && strcmp(env, "0") != 0;
-        auto hashMode = [](char c) { return tolower(c) == 'd' || tolower(c) == 'i' || tolower(c) == 'c'; };   // (c: the -t 1 results)
-        const bool hashMatcherPath = hashMode(matchingMode) && (preReadsExactMatchingChars == 0 || hashMode(preMatchingMode))
-                                     && matchPrefixLength == DefaultReadsMatcher::DISABLED_PREFIX_MODE;
-        if (wantGpu && hashMatcherPath)
+        bool wantGpu = false;
+        if (env && *env && strcmp(env, "0") != 0) {
+            if (strcmp(env, "1") != 0) {
+                fprintf(stderr, "GPU matcher: PGRC_GPU_MATCHER=%s is not understood (use 1 or 0).\n", env);
+                exit(EXIT_FAILURE);
+            }
+            wantGpu = true;
+        }
+        auto gpuLetter = [](char c) { return tolower(c) == 'g'; };
+        if (gpuLetter(matchingMode) || (preReadsExactMatchingChars > 0 && gpuLetter(preMatchingMode))) {
+            wantGpu = true;
+            if (gpuLetter(matchingMode)) matchingMode = isupper((unsigned char) matchingMode) ? 'D' : 'd';
+            if (gpuLetter(preMatchingMode)) preMatchingMode = isupper((unsigned char) preMatchingMode) ? 'D' : 'd';
+        }
+        if (wantGpu) {
+            auto hashMode = [](char c) { return tolower(c) == 'd' || tolower(c) == 'i' || tolower(c) == 'c'; };   // (c: the -t 1 results)
+            if (!hashMode(matchingMode) || (preReadsExactMatchingChars > 0 && !hashMode(preMatchingMode))) {
+                fprintf(stderr, "GPU matcher: unknown matching mode %c (GPU matchers exist for d, i, c and g).\n", matchingMode);
+                exit(EXIT_FAILURE);
+            }
+            if (matchPrefixLength != DefaultReadsMatcher::DISABLED_PREFIX_MODE) {
+                fprintf(stderr, "GPU matcher: prefix matching is not supported on the GPU (unset PGRC_GPU_MATCHER to run the CPU matchers).\n");
+                exit(EXIT_FAILURE);
+            }
+            // the device holds the pseudogenome in 2 bits per base: with the dev option -N (N reads not separated) the HQ
+            // pseudogenome may contain N (DividedPCLReadsSets.cpp:12-13) — refuse up front, not after the matching has run
+            const string &pg = sPg->getPgSequence();
+            for (size_t i = 0; i < pg.size(); i++) {
+                const char c = pg[i];
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
+                    fprintf(stderr, "GPU matcher: the pseudogenome contains the symbol %c at %zu: only ACGT pseudogenomes (N reads separated, the default) "
+                                    "can be matched on the GPU (unset PGRC_GPU_MATCHER to run the CPU matchers).\n", c, i);
+                    exit(EXIT_FAILURE);
+                }
+            }
             return mapReadsIntoPgOnGpu(sPg, revComplPg, preserveOrderMode, readsSet, pairFileMode, revComplPairFile, matchPrefixLength,
                                        preReadsExactMatchingChars, readsExactMatchingChars, minCharsPerMismatch, preMatchingMode,
                                        matchingMode, dumpInfo, pgrcOut, compressionLevel, pgDestFilePrefix, orgIndexesMapping);
+        }
         return mapReadsIntoPg_reference(sPg, revComplPg, preserveOrderMode, readsSet, pairFileMode, revComplPairFile, matchPrefixLength,
                                         preReadsExactMatchingChars, readsExactMatchingChars, minCharsPerMismatch, preMatchingMode,
                                         matchingMode, dumpInfo, pgrcOut, compressionLevel, pgDestFilePrefix, orgIndexesMapping);

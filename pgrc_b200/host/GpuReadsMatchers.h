@@ -19,14 +19,16 @@
 
 namespace PgTools {
 
-    // One device context per mapReadsIntoPg call: text + reads are uploaded once and shared by both phases.
+    // One group of device contexts per mapReadsIntoPg call (one GPU by default; PGRC_GPU_DEVICES=0,1,... or =<count>
+    // shards the stage over several): text + reads are uploaded once and shared by both phases.
     class GpuMatcherSession {
-        pgm_ctx *ctx = nullptr;
+        pgm_group *grp = nullptr;
         uint_reads_cnt_max readsCount = 0;
     public:
         GpuMatcherSession(const char *pgPtr, uint64_t pgLength, ConstantLengthReadsSetInterface *readsSet);
         ~GpuMatcherSession();
-        static void check(int rc, pgm_ctx *c, const char *what);   // prints pgm_last_error, exit(EXIT_FAILURE)
+        static void check(int rc, pgm_group *g, const char *what);   // prints pgm_group_last_error, exit(EXIT_FAILURE)
+        static vector<int> devicesFromEnvironment();                 // PGRC_GPU_DEVICES / PGRC_GPU_DEVICE, default {0}
         void begin(uint32_t seedLength, uint32_t parts, uint32_t maxMismatches, uint32_t minMismatches, bool continuation,
                    bool interleaved = false);
         void pass(bool revCompMode);
@@ -77,9 +79,11 @@ namespace PgTools {
                               bool interleaved = false, bool copmem = false);
     };
 
-    // Same signature as PgTools::mapReadsIntoPg (ReadsMatchers.h:202-207).  Matching modes 'd'/'D', 'i'/'I' and 'c'/'C' run on the GPU when
-    // the environment variable PGRC_GPU_MATCHER is set to something other than 0; every other case is passed on
-    // to the reference's own function.
+    // Same signature as PgTools::mapReadsIntoPg (ReadsMatchers.h:202-207).  The GPU matchers run when the matching mode letter
+    // is 'g' / 'G' (dev build: -s g38; the hash-matcher semantics of 'd' / 'D'), or when PGRC_GPU_MATCHER=1 and the mode is
+    // 'd'/'D', 'i'/'I' or 'c'/'C' (same letter as the CPU run: byte-identical archives).  There is no silent CPU run: a GPU
+    // request that cannot be served (no device, prefix matching, a pseudogenome with N, an unknown PGRC_GPU_MATCHER value)
+    // ends the program with a message, as the reference does for its own errors.
     const vector<bool> mapReadsIntoPgOnGpu(SeparatedPseudoGenome *sPg, bool revComplPg, bool preserveOrderMode,
                         ConstantLengthReadsSetInterface *readsSet, bool pairFileMode, bool revComplPairFile,
                         uint_read_len_max matchPrefixLength, uint16_t preReadsExactMatchingChars,

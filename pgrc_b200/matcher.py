@@ -302,6 +302,83 @@ class GpuReadsMatcher:
         return self._result(out, st)
 
 
+class GpuMatcherGroup:
+    """Several GPUs behind one handle, inside one process (wraps ``pgm_group``; what the C++ host side of PgRC uses:
+    pgrc_b200/host/GpuReadsMatchers.cpp).  Modes 'd'/'D' run the routed scheme with peer-to-peer copies over NVLink,
+    'i' and 'c' give every GPU the whole text and a read range.  A device may be listed more than once."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        devs = [int(d) for d in devices]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        h = ctypes.c_void_p()
+        rc = self._lib.pgm_group_create(len(devs), arr, ctypes.byref(h))
+        if rc != 0:
+            raise PgmError(rc, self._lib.pgm_group_last_error(None).decode())
+        self._h, self.devices, self._keep, self.n_reads = h, devs, [], 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pgm_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PgmError(rc, self._lib.pgm_group_last_error(self._h).decode())
+
+    def set_text(self, text):
+        n = text.numel() if hasattr(text, "numel") else text.size
+        self._keep = [k for k in self._keep if k[0] != "text"] + [("text", text)]
+        self._check(self._lib.pgm_group_set_text(self._h, _ptr(text), n))
+
+    def set_reads(self, lq_packed, n_packed, read_len: int):
+        n_lq, n_n = _rows(lq_packed, (read_len + 3) // 4), _rows(n_packed, (read_len + 2) // 3)
+        self._keep = [k for k in self._keep if k[0] != "reads"] + [("reads", lq_packed, n_packed)]
+        self._check(self._lib.pgm_group_set_reads(self._h, _ptr(lq_packed) if n_lq else None, n_lq, _ptr(n_packed) if n_n else None, n_n, read_len))
+        self.n_reads, self.read_len = n_lq + n_n, read_len
+
+    def run_plan(self, plan: "MatchPlan", rev_compl_pg: bool = True):
+        """The phases of mapReadsIntoPg through the step-wise group calls (as the C++ matcher classes issue them)."""
+        for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
+            if ilv == "c":
+                self._check(self._lib.pgm_group_copmem_begin(self._h, seed_len, max_mm, min_mm, int(cont)))
+                for rev in ((0, 1) if rev_compl_pg else (0,)):
+                    self._check(self._lib.pgm_group_copmem_pass(self._h, rev))
+            else:
+                self._check(self._lib.pgm_group_match_begin(self._h, seed_len, parts, max_mm, min_mm, int(cont), int(bool(ilv))))
+                for rev in ((0, 1) if rev_compl_pg else (0,)):
+                    self._check(self._lib.pgm_group_pass(self._h, rev))
+
+    def get_results(self, out=None) -> MatchResult:
+        n = self.n_reads
+        out = out if out is not None else (np.empty(n, np.uint64), np.empty(n, np.uint8), np.empty(n, np.uint8))
+        st = PgmStats()
+        self._check(self._lib.pgm_group_get_results(self._h, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), ctypes.byref(st)))
+        return GpuReadsMatcher._result(out, st)
+
+    def get_mismatches(self):
+        total = ctypes.c_uint64()
+        self._check(self._lib.pgm_group_get_mismatches(self._h, None, None, None, 0, ctypes.byref(total)))
+        n = int(total.value)
+        off = np.empty(self.n_reads + 1, np.uint64)
+        pos, syms = np.empty(max(n, 1), np.uint8), np.empty(max(n, 1), np.uint8)
+        self._check(self._lib.pgm_group_get_mismatches(self._h, _ptr(off), _ptr(pos), _ptr(syms), n, ctypes.byref(total)))
+        pos, syms = pos[:n], syms[:n]
+        return off, pos, syms & 3, syms >> 2
+
+
 @dataclass
 class MatchPlan:
     """Parameter derivation of mapReadsIntoPg (ReadsMatchers.cpp:699-713,749-756): a list of

@@ -28,13 +28,16 @@ def _fastq(tmp, name, pair=False, **kw):
     return out, out2
 
 
-def _compress(tmp, tag, gpu, fastq, fastq2, flags):
+def _compress(tmp, tag, gpu, fastq, fastq2, flags, devices=None, env_matcher="1"):
     d = os.path.join(tmp, tag)
     os.makedirs(d)
     env = dict(os.environ)
-    env.pop("PGRC_GPU_MATCHER", None)
-    if gpu:
-        env["PGRC_GPU_MATCHER"] = "1"
+    for k in ("PGRC_GPU_MATCHER", "PGRC_GPU_DEVICES", "PGRC_GPU_DEVICE"):
+        env.pop(k, None)
+    if gpu and env_matcher is not None:
+        env["PGRC_GPU_MATCHER"] = env_matcher
+    if devices:
+        env["PGRC_GPU_DEVICES"] = devices
     cmd = [CLI, "-t", "1"] + flags + ["-i", fastq] + ([fastq2] if fastq2 else []) + ["a.pgrc"]
     r = subprocess.run(cmd, cwd=d, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -75,3 +78,42 @@ def test_archive_bytes_identical_to_reference_cli(tmp_path, name):
     assert len(ref) > 1000
     assert "Matched" in ref_out and "Matched" in got_out
     assert got == ref, f"{name}: archives differ ({len(got)} vs {len(ref)} bytes)"
+
+
+MULTI = ["SE_100bp", "SE_ORD_150bp", "PE_ORD_150bp", "SE_two_phase", "SE_exact_prephase", "SE_ilv_100bp", "SE_default_cli"]
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="oracle/_ref/PgRC-dev-gpu not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", MULTI)
+def test_archive_identical_with_the_stage_sharded_over_several_device_contexts(tmp_path, name):
+    """PGRC_GPU_DEVICES: the C++ host side shards stage 4 over a group of device contexts (pgm_group_*: routed scheme for the
+    hash-matcher modes, read ranges for i / c).  Two real GPUs when the box has them, else two contexts on GPU 0."""
+    import torch
+    c = CASES[name]
+    f1, f2 = _fastq(str(tmp_path), name, c["pair"], **c["gen"])
+    ref, _ = _compress(str(tmp_path), "cpu", False, f1, f2, c["flags"])
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    got, out = _compress(str(tmp_path), "gpu2", True, f1, f2, c["flags"], devices=devs)
+    assert "sharded over 2 device contexts" in out
+    assert got == ref, f"{name}: archives differ with PGRC_GPU_DEVICES={devs}"
+    got3, _ = _compress(str(tmp_path), "gpu3", True, f1, f2, c["flags"], devices="0,0,0")
+    assert got3 == ref
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="oracle/_ref/PgRC-dev-gpu not built (needs /root/reference at build time)")
+def test_no_silent_cpu_run(tmp_path):
+    """A GPU request that cannot be served is an error, never a CPU run: a mistyped PGRC_GPU_MATCHER value, a device that
+    does not exist.  (The in-band selection — mode letter g, `-s g38` — needs the one-line `case 'g'` in PgRC.cpp's option
+    parser that INTEGRATION.md shows; this binary is built from the unmodified PgRC.cpp.)"""
+    import torch
+    c = CASES["SE_ORD_150bp"]
+    f1, f2 = _fastq(str(tmp_path), "g", c["pair"], **c["gen"])
+    for tag, env_add, needle in (("typo", dict(PGRC_GPU_MATCHER="yes"), "not understood"),
+                                 ("nodev", dict(PGRC_GPU_MATCHER="1", PGRC_GPU_DEVICE="15"), "GPU matcher")):
+        if tag == "nodev" and torch.cuda.device_count() > 15:
+            continue
+        d = os.path.join(str(tmp_path), tag)
+        os.makedirs(d)
+        r = subprocess.run([CLI, "-t", "1", "-s", "d38", "-i", f1, "a.pgrc"], cwd=d, env=dict(os.environ, **env_add), capture_output=True, text=True, timeout=600)
+        assert r.returncode != 0 and needle in r.stderr, r.stderr[-500:]
+        assert "Matched" not in r.stdout

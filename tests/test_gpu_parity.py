@@ -213,7 +213,7 @@ def test_routed_contexts_match_oracle(world, kw):
     """Hash-partitioned seed table + routed windows / candidates: the result is the single-matcher result bit for bit —
     adversarial inputs (hot seeds with chains, N reads, palindromes: the rule-3 accumulators), the scaled config shapes,
     one and several rounds per pass."""
-    for inp, rw in ((synth.adversarial(61, 100, n_reads=2000, text_len=30000), 0), (synth.adversarial(62, 150, n_reads=1500, text_len=30000), 8192),
+    for inp, rw in ((synth.adversarial(61, 100, n_reads=2000, text_len=30000), 0), (synth.adversarial(62, 150, n_reads=1500, text_len=30000), 4096),
                     (synth.workload(300_000, 40_000, 150, 0.005, seed=63, n_frac=0.03, name="c2 shape"), 65536)):
         want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
         pos, rc, mm, matched, infos, res = _run_routed_on_one_gpu(inp, world, rw, **kw)
@@ -221,7 +221,7 @@ def test_routed_contexts_match_oracle(world, kw):
         assert bad.size == 0, (f"{inp.name} world {world} {kw}: {bad.size} reads differ, first {bad[:5]}: gpu {pos[bad[:5]]} "
                                f"{rc[bad[:5]]} {mm[bad[:5]]} oracle {want.pos[bad[:5]]} {want.rc[bad[:5]]} {want.mm[bad[:5]]}")
         assert matched == want.matched
-        if rw:
+        if rw and world <= 3:
             assert infos[0]["rounds_per_pass"] > 1
         assert sum(i["sent_bytes"]["windows"] for i in infos) > 0 and sum(r.stats["candidates"] for r in res) > 0
 
@@ -460,3 +460,25 @@ def test_randomized_sweep_over_modes_and_parameters(chunk):
                       pre_reads_exact_matching_chars=int(rng.integers(24 if pre_mode.lower() == "c" else 12, L + 20)))
         inp = synth.adversarial(int(rng.integers(1 << 30)), L, n_reads=int(rng.integers(50, 400)), text_len=int(rng.integers(3000, 12000)))
         _check(inp, **kw)
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0]])
+@pytest.mark.parametrize("kw", [dict(), dict(pre_seed=100), dict(mode="D"), dict(mode="i"), dict(mode="c"), dict(pre_seed=50, pre_mode="i", mode="c")])
+def test_group_of_contexts_in_one_process(devices, kw):
+    """pgm_group_* (what the C++ host side of PgRC calls): one handle over several contexts — listed on this one GPU more
+    than once here, so the whole path (host threads, barriers, peer copies of the exchanges, global read order across the
+    LQ / N boundary, result and mismatch-list assembly) runs on a single-GPU box."""
+    for inp in (synth.adversarial(71, 100, n_reads=2000, text_len=30000), synth.workload(200_000, 30_000, 150, 0.005, seed=72, n_frac=0.03, name="c2 shape")):
+        want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, **kw)
+        plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), 3, kw.get("mode", "d"), kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
+        with matcher.GpuMatcherGroup(devices) as g:
+            g.set_text(inp.text)
+            g.set_reads(inp.lq_packed, inp.n_packed if len(inp.n_reads) else None, inp.read_len)
+            g.run_plan(plan)
+            got = g.get_results()
+            lists = g.get_mismatches()
+        bad = np.nonzero((got.pos != want.pos) | (got.rc != want.rc) | (got.mm != want.mm))[0]
+        assert bad.size == 0, f"{inp.name} {devices} {kw}: {bad.size} reads differ, first {bad[:5]}"
+        assert got.matched == want.matched and np.array_equal(got.per_mm, want.per_mm)
+        wl = oracle.oracle_mismatch_lists(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, got.pos, got.rc, got.mm, variant=0)
+        assert all(np.array_equal(a, b) for a, b in zip(lists, wl)), "mismatch lists differ from the oracle"
