@@ -399,8 +399,8 @@ int upload_reads(pgm_ctx *ctx, bool build) {
 }
 
 // L2 persisting window over the pre-filter for the kernels launched next on the context's stream
-int filter_window(pgm_ctx *ctx, bool on) {
-    if (ctx->l2_hints != 2 || !ctx->filter_words || !ctx->persist_max || !ctx->window_max) return PGM_OK;
+int filter_window(pgm_ctx *ctx, bool on, bool force = false) {
+    if ((ctx->l2_hints != 2 && !force) || !ctx->filter_words || !ctx->persist_max || !ctx->window_max) return PGM_OK;
     const size_t bytes = std::min((size_t)ctx->filter_words * 4, ctx->window_max);
     if (on && ctx->persist_set < std::min(bytes, ctx->persist_max)) {
         CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, ctx->persist_max)));
@@ -1486,6 +1486,10 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
     int rc;
     if ((rc = ensure(ctx, ctx->rt_cand_send, (size_t)ctx->route.cap_cand * rt.world * 12))) return rc;
     CU(cudaMemsetAsync(ctx->rt_counters.p, 0, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int), ctx->stream));
+    // the received windows stream through the L2 (12 bytes per window, 48 x the text they came from): without a persisting
+    // window the stream evicts the filter and every filter lookup becomes a DRAM access (PGM_ROUTE_PERSIST=0 turns it off)
+    static const bool persist = !(getenv("PGM_ROUTE_PERSIST") && atoi(getenv("PGM_ROUTE_PERSIST")) == 0);
+    if (persist && (rc = filter_window(ctx, true, true))) return rc;
     uint64_t off = 0;
     for (int s = 0; s < rt.world; s++) {
         if (!in_counts[s]) continue;
@@ -1507,6 +1511,7 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
         KLAUNCH(PGM_K_ROUTE_PROBE, "route_probe_kernel", pgm::route_probe_kernel<<<grid, PGM_ROUTE_THREADS, 0, ctx->stream>>>(pp));
         off += in_counts[s];
     }
+    if (persist && (rc = filter_window(ctx, false, true))) return rc;
     return route_fetch_counts(ctx, PGM_ROUTE_CANDIDATES, send, ctx->rt_cand_send.p, (uint64_t)ctx->route.cap_cand * 12, 12, "pgm_route_probe");
 }
 

@@ -59,6 +59,8 @@
 #define PGM_ILV_WORDS 256                  // mode 'i': words of the de-interleaved tile per plane (stride <= PGM_ILV_MAX_PARTS)
 #define PGM_ILV_MAX_PARTS 31
 #define PGM_WALK_CAP 6                     // full buckets walked before a duplicate key is chained
+#define PGM_DD_SLOTS 2048                  // per-tile set of verified (read, alignment) pairs (scan_kernel, stage B)
+#define PGM_DD_PROBES 4
 
 #define PGM_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define PGM_NIL 0xFFFFFFFFu
@@ -716,9 +718,45 @@ struct ScanShared {
     uint2 wq[PGM_SCAN_WARPS][PGM_WQ_CAP];   // per-warp candidate queues {pos_in_tile | chain << 31, pattern}
     uint16_t q1[PGM_TILE_POS];              // filter-positive positions of the tile
     uint32_t dl[ILV ? PGM_ILV_WORDS : 1], dh[ILV ? PGM_ILV_WORDS : 1];   // mode 'i': the tile's planes de-interleaved by position residue
+    // (read, alignment) pairs already verified in this tile: {read:32 | alignment in tile:13 | .. | seed index or 0xFF:8}
+    // (contiguous seeds only: the static 48 KB do not hold it next to the de-interleaved planes)
+    unsigned long long dd[ILV ? 1 : PGM_DD_SLOTS];
     uint64_t bar[2];
     unsigned int q1_count[2], q1_cursor[2], tile[2];
 };
+
+// Duplicate events.  The `parts` seeds of a read that lie on one alignment hit the table at window starts shift_unit
+// apart — up to `parts` candidates for ONE (read, alignment) pair, each costing a 64-byte record fetch from DRAM (C2: 31 M
+// candidates per pass for about 13 M pairs).  All events of a pair share the mismatch count and every drop / accept test
+// of ReadsMatchers.cpp:304-315; they differ in the scan order only, and the order-free accumulators keep the EARLIEST one
+// (best_key and first_other_order are minima over (.., order)).  So an event is dominated — contributes nothing — once an
+// event of the same pair with a smaller seed index has been verified, EXCEPT for the alignment that reports the read's
+// stored position (rule :313), whose events all enter same_pos_mask.  A lane looks its pair up before fetching the record
+// and skips a dominated event; after verifying, it enters the pair with its seed index (0xFF for the stored-position
+// alignment, which is a property of the pair, so every event of it writes the same value: those are never skipped).
+// Misses (another CTA's tile, a full neighbourhood, an event still in flight) just verify as before.
+__device__ __forceinline__ bool dd_dominated(const unsigned long long *dd, unsigned long long key, uint32_t cj) {
+    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (PGM_DD_SLOTS - 1);
+#pragma unroll
+    for (int k = 0; k < PGM_DD_PROBES; k++) {
+        const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(dd + slot);
+        if (e == PGM_EMPTY64) return false;
+        if ((e >> 8) == key) return (uint32_t)(e & 0xFFu) < cj;
+        slot = (slot + 1) & (PGM_DD_SLOTS - 1);
+    }
+    return false;
+}
+__device__ __forceinline__ void dd_enter(unsigned long long *dd, unsigned long long key, uint32_t val) {
+    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (PGM_DD_SLOTS - 1);
+    const unsigned long long mine = (key << 8) | val;
+#pragma unroll
+    for (int k = 0; k < PGM_DD_PROBES; k++) {
+        const unsigned long long e = atomicCAS(dd + slot, PGM_EMPTY64, mine);
+        if (e == PGM_EMPTY64) return;
+        if ((e >> 8) == key) { atomicMin(dd + slot, mine); return; }
+        slot = (slot + 1) & (PGM_DD_SLOTS - 1);
+    }
+}
 
 // canonical form of the seed window starting at tile position `pos` (text staged in shared memory)
 template <int NCH>
@@ -844,6 +882,8 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
         const uint32_t *blo = sm.lo[buf], *bhi = sm.hi[buf];
         const uint32_t *slo = blo + PGM_HALO_L, *shi = bhi + PGM_HALO_L;       // tile position 0
 
+        if constexpr (!ILV && FAST && MODE == 0)
+            for (uint32_t k = t; k < PGM_DD_SLOTS; k += PGM_SCAN_THREADS) sm.dd[k] = PGM_EMPTY64;
         // ---- A1: hash + filter, lane <-> position
         const int64_t vb64 = (int64_t)p.own_begin - (int64_t)tile_g0, ve64 = (int64_t)p.own_end - (int64_t)tile_g0;
         const uint32_t vb = (uint32_t)max((int64_t)0, min(vb64, (int64_t)PGM_TILE_POS));
@@ -1039,6 +1079,19 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                     const uint32_t cpos = e.x & 0x7FFFFFFFu;
                     const bool chain = (e.x >> 31) != 0;
                     uint32_t cpat = e.y;
+                    // the pair (read, alignment) of this event; its events share everything but the scan order (see dd_dominated)
+                    unsigned long long dkey = 0;
+                    bool dd_first = false;
+                    if constexpr (!ILV) {
+                        if (on) {
+                            n_cand++;
+                            const uint32_t a_rel = PGM_HALO_L * 32 + cpos - (cpat & pmask) * p.shift_unit;
+                            dkey = ((unsigned long long)(cpat >> p.reads.part_bits) << 13) | a_rel;
+                            if (!chain && dd_dominated(sm.dd, dkey, cpat & pmask)) on = false;
+                            dd_first = on;
+                        }
+                    }
+                    const bool counted = !ILV;
                     const uint32_t pat_o = __shfl_xor_sync(PGM_FULL, cpat, 1);
                     const bool on_o = __shfl_xor_sync(PGM_FULL, (int)on, 1) != 0;
                     const uint32_t patA = half ? pat_o : cpat, patB = half ? cpat : pat_o;
@@ -1079,22 +1132,25 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                         }
                         if (on) {
                             // body of DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:301-331) up to the decision
-                            n_cand++;
+                            if (!(counted && dd_first)) n_cand++;
                             const uint32_t st_lo = s0[0], st_hi = s0[1];
                             const uint32_t c_in = st_hi >> 24;
                             const uint64_t gpos = tile_g0 + cpos;
+                            uint32_t dd_val = 0;                  // a dropped pair: none of its events contributes
                             if (c_in > p.min_mm && (uint64_t)shift <= gpos) {                              // :304, :308
                                 const uint64_t a = gpos - shift;
                                 if (a + L <= p.pg_len) {                                                   // :311
                                     n_ver++;
                                     const bool has_pos = c_in != 255u;
                                     const int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;             // :315
+                                    const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;             // :313,:326 (matchingLength == readLength)
+                                    const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
+                                    const bool same_pos = has_pos && st_pos == rep;                        // coordinate-only compare, :313
+                                    dd_val = same_pos ? 0xFFu : cj;
                                     if (c <= limit) {
                                         n_acc++;
-                                        const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;         // :313,:326 (matchingLength == readLength)
-                                        const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
                                         const unsigned long long order = (gpos << 8) | (unsigned long long)(p.parts - 1 - cj);
-                                        if (!(has_pos && st_pos == rep)) {                                 // coordinate-only compare, :313
+                                        if (!same_pos) {
                                             const unsigned long long cls = (uint32_t)c <= p.min_mm ? 0ull : (unsigned long long)c;
                                             const long long key = (long long)((cls << 56) | (order << 8) | (unsigned long long)c);
                                             const long long seen = (long long)(((uint64_t)s0[3] << 32) | s0[2]);   // never below the live value
@@ -1111,7 +1167,11 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                                     }
                                 }
                             }
+                            if constexpr (!ILV) {
+                                if (dd_first) dd_enter(sm.dd, dkey, dd_val);      // this pair is verified: later events of it with a larger seed index are dominated
+                            }
                         }
+                        dd_first = false;
                         // hot keys: walk the chain behind the slot (this lane alone fetches the next record)
                         if (on && chain) {
                             cpat = __ldg(p.tab.next + cpat);

@@ -34,9 +34,15 @@ if has ncu; then
         --log-file $OUT/launches_c5_$TAG.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_launches_$TAG.log 2>&1
     echo "ncu launches exit $?"
 fi
-if has ncufull; then   # one full capture of the scan kernel at C4 size (C5's footprint makes the replays' save/restore slow)
-    timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'pgm::scan_kernel' -s 2 -c 1 \
-        -f -o $OUT/scan_c4_$TAG python bench.py --workload c4 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1
-    echo "ncu full exit $?"
+if has ncufull; then   # full captures of the scan kernel: C2 (both passes of one step) and C4 (C5's footprint makes the replays' save/restore slow)
+    for w in ${NCU_WORKLOADS:-c2 c4}; do
+        timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'pgm::scan_kernel' -s 2 -c 2 \
+            -f -o $OUT/scan_${w}_$TAG python bench.py --workload $w --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full_${w}_$TAG.log 2>&1
+        echo "ncu full $w exit $?"
+    done
+fi
+if has c2; then
+    timeout 900 python bench.py --workload c2 --verify --steps 20 --warmup 5 > $OUT/bench_c2_n1_$TAG.json 2>> $OUT/bench_$TAG.err
+    cat $OUT/bench_c2_n1_$TAG.json
 fi
 ls -la $OUT | tail -30
