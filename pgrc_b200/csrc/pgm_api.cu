@@ -94,6 +94,8 @@ struct pgm_ctx {
     uint64_t n_slots = 0;
     uint32_t n_buckets = 0;
     uint32_t filter_words = 0;  // 0 = no filter
+    uint32_t filter_slice_bits = 0;   // log2 of the number of 64 MB slices of the filter (hash-sliced scan, pgm_kernels.cuh TableView)
+    int filter_slices_force = -1;     // PGM_FILTER_SLICES: log2 of the slice count (-1 = auto)
     uint32_t filter_k = 2;      // bits per pattern in its filter word
     int filter_k_force = 0;     // PGM_FILTER_K (sweeps)
     int filter_pair_mode = 1;   // paired filter lookups: 0 off, 1 auto (by load), 2 always (PGM_FILTER_PAIR)
@@ -213,6 +215,8 @@ pgm::ReadsView reads_view(pgm_ctx *c) {
     return rv;
 }
 
+int floor_log2_u(uint64_t v) { int b = 0; while ((2ull << b) <= v) b++; return b; }
+
 pgm::TableView table_view(pgm_ctx *c) {
     pgm::TableView tv;
     tv.buckets = c->buckets.as<pgm::u32x8>();
@@ -222,10 +226,13 @@ pgm::TableView table_view(pgm_ctx *c) {
     tv.filter_mask = c->filter_words ? c->filter_words - 1 : 0;
     tv.filter_k = c->filter_k;
     tv.pair = c->filter_words ? c->filter_pair : 0; tv.pair_lo = c->pair_lo; tv.pair_mask = c->pair_mask;
+    // slice = top filter_slice_bits bits of the word index
+    tv.slice_shift = (c->filter_words && c->filter_slice_bits) ? (uint32_t)floor_log2_u(c->filter_words) - c->filter_slice_bits : 31u;
     return tv;
 }
 
 int ceil_log2(uint64_t v) { int b = 0; while ((1ull << b) < v) b++; return b; }
+
 
 uint32_t next_prime(uint64_t v) {
     if (v < 3) return 2;
@@ -514,6 +521,7 @@ int pgm_create(int device, pgm_ctx **out) {
     if (const char *t = getenv("PGM_TWO_STEP_BUILD")) ctx->two_step_build = atoi(t);   // 0 off, 1 auto, 2 always (tests)
     if (const char *t = getenv("PGM_FILTER_K")) ctx->filter_k_force = atoi(t);
     if (const char *t = getenv("PGM_FILTER_PAIR")) ctx->filter_pair_mode = atoi(t);
+    if (const char *t = getenv("PGM_FILTER_SLICES")) ctx->filter_slices_force = std::min(3, std::max(0, atoi(t)));
     if (const char *t = getenv("PGM_INSERT_PREFETCH")) ctx->insert_prefetch = atoi(t);
     if (const char *t = getenv("PGM_BLOCKED_SCAN")) ctx->blocked_scan = atoi(t);
     if (const char *t = getenv("PGM_REGION_MB")) ctx->region_mb = std::max(1, atoi(t));
@@ -780,6 +788,19 @@ int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t m
     // beyond that get 2^29 bits (64 MB: still mostly resident) — a saturated filter sends every text window to the table
     if (fbits < 0) fbits = std::min(n_patterns > (100ull << 20) ? 29 : 28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 8)));
     const bool auto_bits = ctx->filter_log2_bits < 0;
+    // hash-sliced filter: beyond ~130 M patterns a 2^29-bit filter has fewer than 4 bits per pattern and lets most windows
+    // through; give it about 4 bits per pattern in 2^s slices of 2^29 bits (up to 8: 512 MB) and scan once per slice
+    ctx->filter_slice_bits = 0;
+    if (auto_bits && !interleaved && ctx->blocked_scan <= 0) {
+        if (ctx->filter_slices_force >= 0) {
+            // (tests / sweeps: the filter as sized above, cut into 2^force slices; at full size it grows like the auto rule)
+            ctx->filter_slice_bits = (uint32_t)std::min(ctx->filter_slices_force, std::max(0, fbits - 8));
+            if (fbits == 29) fbits += (int)ctx->filter_slice_bits;
+        } else if (fbits == 29) {
+            ctx->filter_slice_bits = (uint32_t)std::min(3, std::max(0, ceil_log2(n_patterns * 4) - 29));
+            fbits += (int)ctx->filter_slice_bits;
+        }
+    }
     if (fbits > 0) {
         // paired lookups (pgm_kernels.cuh, pair_word): one gather for two adjacent windows, every pattern entered in two
         // words; only for contiguous seeds with >= 12 exactly-hashed shared bases, and only while the doubled load stays low
@@ -787,7 +808,7 @@ int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t m
         const int core = (int)hi_off - (int)lo_off - 1;
         if (auto_bits && ctx->filter_pair_mode == 1 && !interleaved && core >= 12 && n_patterns * 24 <= (1ull << 28))
             fbits = std::max(fbits, std::min(28, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 24)));   // room for the second entry
-        ctx->filter_pair = !interleaved && core >= 12 &&
+        ctx->filter_pair = !interleaved && core >= 12 && !ctx->filter_slice_bits &&
                            (ctx->filter_pair_mode == 2 || (ctx->filter_pair_mode == 1 && n_patterns * 12 <= (1ull << fbits)));
         ctx->pair_lo = lo_off;
         ctx->pair_mask = core >= 12 ? (uint32_t)((1ull << core) - 1) : 0;
@@ -916,7 +937,14 @@ int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
         sp.only_if = q.overflow;
         CU(cudaMemsetAsync(sp.tile_counter, 0, sizeof(unsigned int), ctx->stream));
     }
-    KLAUNCH(PGM_K_SCAN, "scan_kernel", launch_scan_nch(nch, sp, grid, ctx->stream, false));
+    // one launch per filter slice (one, unless the pattern set is far beyond an L2-resident filter): every launch streams the
+    // whole text range again (2 bits per base) but gathers from its own 64 MB of the filter only
+    const uint32_t n_slices = (ctx->filter_words && !sp.only_if) ? 1u << ctx->filter_slice_bits : 1u;
+    for (uint32_t h = 0; h < n_slices; h++) {
+        sp.slice = h;
+        if (h) CU(cudaMemsetAsync(sp.tile_counter, 0, sizeof(unsigned int), ctx->stream));
+        KLAUNCH(PGM_K_SCAN, "scan_kernel", launch_scan_nch(nch, sp, grid, ctx->stream, false));
+    }
     return filter_window(ctx, false);
 }
 } // namespace

@@ -59,8 +59,6 @@
 #define PGM_ILV_WORDS 256                  // mode 'i': words of the de-interleaved tile per plane (stride <= PGM_ILV_MAX_PARTS)
 #define PGM_ILV_MAX_PARTS 31
 #define PGM_WALK_CAP 6                     // full buckets walked before a duplicate key is chained
-#define PGM_DD_SLOTS 2048                  // per-tile set of verified (read, alignment) pairs (scan_kernel, stage B)
-#define PGM_DD_PROBES 4
 
 #define PGM_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define PGM_NIL 0xFFFFFFFFu
@@ -131,6 +129,11 @@ struct TableView {
     uint32_t filter_k;          // bits per pattern in its filter word (1 or 2)
     uint32_t pair;              // 1: paired lookups — the filter word is chosen by the bases two adjacent windows share (below)
     uint32_t pair_lo, pair_mask;   // first exactly-hashed window offset, mask of the shared core's bits
+    // Hash-sliced filter (pattern sets far beyond what an L2-resident filter can hold apart): the filter has 2^slice_bits
+    // slices of 64 MB, slice = word index >> slice_shift; a scan launch looks at the windows of ONE slice only, so the part
+    // of the filter it gathers from stays L2-resident while the whole filter has 4+ bits per pattern.  The text (2 bits per
+    // base) is re-hashed once per slice: ALU work instead of one random DRAM line per false positive.
+    uint32_t slice_shift;       // 31 when the filter has one slice
 };
 
 struct ReadsView {
@@ -176,6 +179,7 @@ struct ScanParams {
     uint32_t shift_unit;            // alignment start = window start - j * shift_unit: seed_len (mode 'd'), 1 (mode 'i')
     uint32_t ilv;                   // 0: seed j = read bases [j*n, (j+1)*n) (mode 'd'); else the stride (= parts) of mode 'i'
     uint32_t tail_mask;             // valid bits of the last 32-base chunk of a seed
+    uint32_t slice;                 // filter slice this launch handles (TableView::slice_shift)
     int rev_mode;
     int l2_hints;                   // (unused: filter loads always carry an L2 evict_last policy)
     int stream_hints;               // 1: bucket / record loads carry an L2 evict_first policy
@@ -718,45 +722,9 @@ struct ScanShared {
     uint2 wq[PGM_SCAN_WARPS][PGM_WQ_CAP];   // per-warp candidate queues {pos_in_tile | chain << 31, pattern}
     uint16_t q1[PGM_TILE_POS];              // filter-positive positions of the tile
     uint32_t dl[ILV ? PGM_ILV_WORDS : 1], dh[ILV ? PGM_ILV_WORDS : 1];   // mode 'i': the tile's planes de-interleaved by position residue
-    // (read, alignment) pairs already verified in this tile: {read:32 | alignment in tile:13 | .. | seed index or 0xFF:8}
-    // (contiguous seeds only: the static 48 KB do not hold it next to the de-interleaved planes)
-    unsigned long long dd[ILV ? 1 : PGM_DD_SLOTS];
     uint64_t bar[2];
     unsigned int q1_count[2], q1_cursor[2], tile[2];
 };
-
-// Duplicate events.  The `parts` seeds of a read that lie on one alignment hit the table at window starts shift_unit
-// apart — up to `parts` candidates for ONE (read, alignment) pair, each costing a 64-byte record fetch from DRAM (C2: 31 M
-// candidates per pass for about 13 M pairs).  All events of a pair share the mismatch count and every drop / accept test
-// of ReadsMatchers.cpp:304-315; they differ in the scan order only, and the order-free accumulators keep the EARLIEST one
-// (best_key and first_other_order are minima over (.., order)).  So an event is dominated — contributes nothing — once an
-// event of the same pair with a smaller seed index has been verified, EXCEPT for the alignment that reports the read's
-// stored position (rule :313), whose events all enter same_pos_mask.  A lane looks its pair up before fetching the record
-// and skips a dominated event; after verifying, it enters the pair with its seed index (0xFF for the stored-position
-// alignment, which is a property of the pair, so every event of it writes the same value: those are never skipped).
-// Misses (another CTA's tile, a full neighbourhood, an event still in flight) just verify as before.
-__device__ __forceinline__ bool dd_dominated(const unsigned long long *dd, unsigned long long key, uint32_t cj) {
-    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (PGM_DD_SLOTS - 1);
-#pragma unroll
-    for (int k = 0; k < PGM_DD_PROBES; k++) {
-        const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(dd + slot);
-        if (e == PGM_EMPTY64) return false;
-        if ((e >> 8) == key) return (uint32_t)(e & 0xFFu) < cj;
-        slot = (slot + 1) & (PGM_DD_SLOTS - 1);
-    }
-    return false;
-}
-__device__ __forceinline__ void dd_enter(unsigned long long *dd, unsigned long long key, uint32_t val) {
-    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (PGM_DD_SLOTS - 1);
-    const unsigned long long mine = (key << 8) | val;
-#pragma unroll
-    for (int k = 0; k < PGM_DD_PROBES; k++) {
-        const unsigned long long e = atomicCAS(dd + slot, PGM_EMPTY64, mine);
-        if (e == PGM_EMPTY64) return;
-        if ((e >> 8) == key) { atomicMin(dd + slot, mine); return; }
-        slot = (slot + 1) & (PGM_DD_SLOTS - 1);
-    }
-}
 
 // canonical form of the seed window starting at tile position `pos` (text staged in shared memory)
 template <int NCH>
@@ -882,8 +850,6 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
         const uint32_t *blo = sm.lo[buf], *bhi = sm.hi[buf];
         const uint32_t *slo = blo + PGM_HALO_L, *shi = bhi + PGM_HALO_L;       // tile position 0
 
-        if constexpr (!ILV && FAST && MODE == 0)
-            for (uint32_t k = t; k < PGM_DD_SLOTS; k += PGM_SCAN_THREADS) sm.dd[k] = PGM_EMPTY64;
         // ---- A1: hash + filter, lane <-> position
         const int64_t vb64 = (int64_t)p.own_begin - (int64_t)tile_g0, ve64 = (int64_t)p.own_end - (int64_t)tile_g0;
         const uint32_t vb = (uint32_t)max((int64_t)0, min(vb64, (int64_t)PGM_TILE_POS));
@@ -913,7 +879,9 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                 window_form<NCH>(sm.dl + r * ilv_mw, sm.dh + r * ilv_mw, q, p.tail_mask, P, Q, R);
                 const uint32_t f = filter_hash(P, Q, R);
                 const uint32_t fm = filter_bits(f, p.tab.filter_k);
-                const uint32_t fw = !p.tab.filter ? 0xFFFFFFFFu : ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep);
+                const uint32_t fidx = f & p.tab.filter_mask;
+                const bool mine = (fidx >> p.tab.slice_shift) == p.slice;
+                const uint32_t fw = !p.tab.filter ? (p.slice == 0 ? 0xFFFFFFFFu : 0u) : (mine ? ld_u32_hint(p.tab.filter + fidx, pol_keep) : 0u);
                 const bool hit = pos < PGM_TILE_POS && pos >= vb && pos < ve && (fw & fm) == fm;
                 const uint32_t bal = __ballot_sync(PGM_FULL, hit);
                 if (bal) {
@@ -947,7 +915,8 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     if (pair && (u & 1)) fw[u] = fw[u - 1];
-                    else fw[u] = !p.tab.filter ? 0xFFFFFFFFu : ld_u32_hint(p.tab.filter + fi[u], pol_keep);   // evict_last: the filter is the one L2-resident structure
+                    else if (!p.tab.filter) fw[u] = 0xFFFFFFFFu;
+                    else fw[u] = (fi[u] >> p.tab.slice_shift) == p.slice ? ld_u32_hint(p.tab.filter + fi[u], pol_keep) : 0u;   // evict_last: the filter('s slice) is the one L2-resident structure
                 }
                 uint32_t bal[U], tot = 0;
                 bool hit[U];
@@ -1079,19 +1048,6 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                     const uint32_t cpos = e.x & 0x7FFFFFFFu;
                     const bool chain = (e.x >> 31) != 0;
                     uint32_t cpat = e.y;
-                    // the pair (read, alignment) of this event; its events share everything but the scan order (see dd_dominated)
-                    unsigned long long dkey = 0;
-                    bool dd_first = false;
-                    if constexpr (!ILV) {
-                        if (on) {
-                            n_cand++;
-                            const uint32_t a_rel = PGM_HALO_L * 32 + cpos - (cpat & pmask) * p.shift_unit;
-                            dkey = ((unsigned long long)(cpat >> p.reads.part_bits) << 13) | a_rel;
-                            if (!chain && dd_dominated(sm.dd, dkey, cpat & pmask)) on = false;
-                            dd_first = on;
-                        }
-                    }
-                    const bool counted = !ILV;
                     const uint32_t pat_o = __shfl_xor_sync(PGM_FULL, cpat, 1);
                     const bool on_o = __shfl_xor_sync(PGM_FULL, (int)on, 1) != 0;
                     const uint32_t patA = half ? pat_o : cpat, patB = half ? cpat : pat_o;
@@ -1132,25 +1088,22 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                         }
                         if (on) {
                             // body of DefaultReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:301-331) up to the decision
-                            if (!(counted && dd_first)) n_cand++;
+                            n_cand++;
                             const uint32_t st_lo = s0[0], st_hi = s0[1];
                             const uint32_t c_in = st_hi >> 24;
                             const uint64_t gpos = tile_g0 + cpos;
-                            uint32_t dd_val = 0;                  // a dropped pair: none of its events contributes
                             if (c_in > p.min_mm && (uint64_t)shift <= gpos) {                              // :304, :308
                                 const uint64_t a = gpos - shift;
                                 if (a + L <= p.pg_len) {                                                   // :311
                                     n_ver++;
                                     const bool has_pos = c_in != 255u;
                                     const int limit = has_pos ? (int)c_in - 1 : (int)p.max_mm;             // :315
-                                    const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;             // :313,:326 (matchingLength == readLength)
-                                    const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
-                                    const bool same_pos = has_pos && st_pos == rep;                        // coordinate-only compare, :313
-                                    dd_val = same_pos ? 0xFFu : cj;
                                     if (c <= limit) {
                                         n_acc++;
+                                        const uint64_t rep = p.rev_mode ? p.pg_len - (a + L) : a;         // :313,:326 (matchingLength == readLength)
+                                        const uint64_t st_pos = (((uint64_t)st_hi << 32) | st_lo) & PGM_POS_MASK;
                                         const unsigned long long order = (gpos << 8) | (unsigned long long)(p.parts - 1 - cj);
-                                        if (!same_pos) {
+                                        if (!(has_pos && st_pos == rep)) {                                 // coordinate-only compare, :313
                                             const unsigned long long cls = (uint32_t)c <= p.min_mm ? 0ull : (unsigned long long)c;
                                             const long long key = (long long)((cls << 56) | (order << 8) | (unsigned long long)c);
                                             const long long seen = (long long)(((uint64_t)s0[3] << 32) | s0[2]);   // never below the live value
@@ -1167,11 +1120,7 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                                     }
                                 }
                             }
-                            if constexpr (!ILV) {
-                                if (dd_first) dd_enter(sm.dd, dkey, dd_val);      // this pair is verified: later events of it with a larger seed index are dominated
-                            }
                         }
-                        dd_first = false;
                         // hot keys: walk the chain behind the slot (this lane alone fetches the next record)
                         if (on && chain) {
                             cpat = __ldg(p.tab.next + cpat);

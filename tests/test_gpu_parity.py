@@ -482,3 +482,18 @@ def test_group_of_contexts_in_one_process(devices, kw):
         assert got.matched == want.matched and np.array_equal(got.per_mm, want.per_mm)
         wl = oracle.oracle_mismatch_lists(inp.text, inp.lq_packed, inp.n_packed, inp.read_len, got.pos, got.rc, got.mm, variant=0)
         assert all(np.array_equal(a, b) for a, b in zip(lists, wl)), "mismatch lists differ from the oracle"
+
+
+@pytest.mark.parametrize("slices", ["1", "2", "3"])
+def test_hash_sliced_filter_forced(monkeypatch, slices):
+    """The hash-sliced filter (used for pattern sets far beyond an L2-resident filter: one scan launch per 64 MB slice of a
+    4-bits-per-pattern filter) forced onto small inputs: same results, and — the filter being the same bits, only visited
+    slice by slice — the same filter positives and candidates as the single-launch scan."""
+    inputs = (synth.adversarial(81, 100), synth.adversarial(82, 150), synth.workload(200_000, 50_000, 150, 0.005, seed=83, n_frac=0.02, name="c2 shape"))
+    base = [_check(inp)[0] for inp in inputs]
+    monkeypatch.setenv("PGM_FILTER_SLICES", slices)
+    for inp, b in zip(inputs, base):
+        got, _ = _check(inp)
+        assert got.stats["filter_positives"] == b.stats["filter_positives"] and got.stats["candidates"] == b.stats["candidates"]
+        _check(inp, pre_reads_exact_matching_chars=inp.read_len)
+        _check(inp, matching_mode="D")

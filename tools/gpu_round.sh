@@ -7,6 +7,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu_$TAG.txt 2>&1
 (nproc; free -g | head -2) >> $OUT/gpu_$TAG.txt 2>&1
+python -c "import bench; print(bench.kernels_sha())" > $OUT/kernels_sha_$TAG.txt 2>/dev/null
 has() { [[ " $WHAT " == *" $1 "* ]]; }
 if has routed; then    # the new multi-GPU scheme first (several contexts on this one GPU): fail fast
     timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "routed or sharded" > $OUT/pytest_routed_$TAG.log 2>&1; echo "pytest routed exit $?" | tee -a $OUT/pytest_routed_$TAG.log
@@ -28,6 +29,16 @@ if has benchall; then  # the other configs at N = 1, with their fixtures
 fi
 if has ref; then
     timeout 1200 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err; cat $OUT/bench_ref_$TAG.json
+fi
+if has c4; then
+    timeout 900 python bench.py --workload c4 --verify --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_c4_n1_$TAG.json 2>> $OUT/bench_$TAG.err
+    cat $OUT/bench_c4_n1_$TAG.json
+fi
+if has slices; then    # sweep of the hash-sliced filter at C5 (PGM_FILTER_SLICES = log2 of the slice count)
+    for sb in 0 1 2 3; do
+        PGM_FILTER_SLICES=$sb timeout 900 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > $OUT/bench_c5_slices${sb}_$TAG.json 2>> $OUT/bench_$TAG.err
+        python tools/show_bench.py $OUT/bench_c5_slices${sb}_$TAG.json
+    done
 fi
 if has ncu; then
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:pgm:: -c 400 --csv \

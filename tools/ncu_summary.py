@@ -2,8 +2,10 @@
 """Summarise an `ncu --set full` capture (read here, no GPU needed) into profiles/:
     python tools/ncu_summary.py gpurun_out/scan_r01a.ncu-rep r01a [workload] [kernel label]
 writes profiles/<label>_full_<tag>.json (selected counters per launch) and, for the scan kernel, updates
-profiles/scan_traffic.json (dram read+write bytes per launch, averaged over the captured launches; bench.py
-reports it as roofline.traffic)."""
+profiles/scan_traffic.json (dram read+write bytes per launch, averaged over the captured launches, together with the
+sha of the kernel sources the capture was taken with: bench.py reports it as roofline.traffic only while that sha is
+the one of the sources it runs — run this BEFORE editing pgrc_b200/csrc/pgm_* again, or pass the sha as 5th argument)."""
+import hashlib
 import csv
 import io
 import json
@@ -56,8 +58,14 @@ def main():
     if label == "scan":
         p = os.path.join(ROOT, "profiles", "scan_traffic.json")
         t = json.load(open(p)) if os.path.exists(p) else {}
-        t[workload] = int(sum(traffic) / len(traffic))
-        t[workload + "_source"] = f"profiles/scan_full_{tag}.json, mean of {len(traffic)} launches"
+        h = hashlib.sha256()
+        csrc = os.path.join(ROOT, "pgrc_b200", "csrc")
+        for f in sorted(os.listdir(csrc)):
+            if f.startswith("pgm_"):
+                h.update(open(os.path.join(csrc, f), "rb").read())
+        t[workload] = {"dram_bytes_per_launch": int(sum(traffic) / len(traffic)),
+                       "kernels_sha": sys.argv[5] if len(sys.argv) > 5 else h.hexdigest()[:16],
+                       "source": f"profiles/scan_full_{tag}.json, mean of {len(traffic)} launches"}
         json.dump(t, open(p, "w"), indent=1)
     for o in out:
         print(json.dumps(o))
