@@ -224,6 +224,9 @@ typedef struct pgm_route_buffer {
  * (0 = default; bounds the exchange buffers). */
 int pgm_route_config(pgm_ctx *ctx, int rank, int world, const uint64_t *read_begin, uint64_t round_windows);
 int pgm_route_rounds(pgm_ctx *ctx, uint32_t *rounds);
+/* The exchange buffers exist twice: pgm_route_scan / _recv / _probe / _verify use the set selected here (0 or 1), so a
+ * caller can emit and ship the windows of round r + 1 (other set) while round r is being probed and verified. */
+int pgm_route_slot(pgm_ctx *ctx, int slot);
 int pgm_route_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm,
                     int continuation, pgm_route_buffer *send);
 /* Device buffer for `n_entries` incoming entries of `kind` (PGM_ROUTE_*). */

@@ -117,8 +117,14 @@ struct pgm_ctx {
         uint64_t round_windows = 0;         // window starts a GPU emits per round
         uint32_t cap_pat = 0, cap_win = 0, cap_cand = 0;
         uint64_t n_pat_in = 0;
+        int slot = 0;                       // which of the two sets of exchange buffers the route_* calls use (pgm_route_slot)
     } route;
-    DevBuf rt_win_send, rt_win_recv, rt_cand_send, rt_cand_recv, rt_pat_recv, rt_counters;
+    // two sets of exchange buffers: the windows of round r + 1 can be emitted and travel while round r is probed and verified
+    DevBuf rt_win_send2[2], rt_win_recv2[2], rt_cand_send2[2], rt_cand_recv2[2], rt_pat_recv, rt_counters;
+    DevBuf &rt_win_send_() { return rt_win_send2[route.slot]; }
+    DevBuf &rt_win_recv_() { return rt_win_recv2[route.slot]; }
+    DevBuf &rt_cand_send_() { return rt_cand_send2[route.slot]; }
+    DevBuf &rt_cand_recv_() { return rt_cand_recv2[route.slot]; }
 
     // misc device scalars: counters[0..3] scan, [4] inserted, [5] tile counter (low 32 bits)
     DevBuf counters, hist, err_flag;
@@ -565,7 +571,8 @@ void pgm_destroy(pgm_ctx *ctx) {
                       &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
                       &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter, &ctx->bq_entries, &ctx->bq_counters,
                       &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->mis_sums, &ctx->mis_offsets, &ctx->mis_pos, &ctx->mis_syms,
-                      &ctx->rt_win_send, &ctx->rt_win_recv, &ctx->rt_cand_send, &ctx->rt_cand_recv, &ctx->rt_pat_recv, &ctx->rt_counters,
+                      &ctx->rt_win_send2[0], &ctx->rt_win_send2[1], &ctx->rt_win_recv2[0], &ctx->rt_win_recv2[1], &ctx->rt_cand_send2[0],
+                      &ctx->rt_cand_send2[1], &ctx->rt_cand_recv2[0], &ctx->rt_cand_recv2[1], &ctx->rt_pat_recv, &ctx->rt_counters,
                       &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
@@ -1295,21 +1302,23 @@ uint32_t route_cap(uint64_t total, int world) {
     return (uint32_t)std::min<uint64_t>(std::min<uint64_t>(total, total / world + total / (4 * world) + (1u << 20)) + 16, 0xFFFFFFF0ull);
 }
 
-unsigned int *route_counts(pgm_ctx *ctx, int kind) { return ctx->rt_counters.as<unsigned int>() + kind * PGM_ROUTE_MAX_WORLD; }
-unsigned int *route_overflow(pgm_ctx *ctx) { return ctx->rt_counters.as<unsigned int>() + 3 * PGM_ROUTE_MAX_WORLD; }
-unsigned int *route_tile_counter(pgm_ctx *ctx) { return ctx->rt_counters.as<unsigned int>() + 3 * PGM_ROUTE_MAX_WORLD + 1; }
+// device counters of the exchanges: per buffer slot and per kind {counts[16], overflow, tile counter, ..} = 32 words
+constexpr int RT_KIND_WORDS = 32, RT_SLOT_WORDS = 3 * RT_KIND_WORDS;
+unsigned int *route_counts(pgm_ctx *ctx, int kind) { return ctx->rt_counters.as<unsigned int>() + ctx->route.slot * RT_SLOT_WORDS + kind * RT_KIND_WORDS; }
+unsigned int *route_overflow(pgm_ctx *ctx, int kind) { return route_counts(ctx, kind) + PGM_ROUTE_MAX_WORLD; }
+unsigned int *route_tile_counter(pgm_ctx *ctx, int kind) { return route_counts(ctx, kind) + PGM_ROUTE_MAX_WORLD + 1; }
 
 // copies the per-destination counts of `kind` (and the overflow flag) to the host; synchronizes the stream
 int route_fetch_counts(pgm_ctx *ctx, int kind, pgm_route_buffer *send, void *base, uint64_t stride, uint32_t entry_bytes, const char *what) {
-    unsigned int h[3 * PGM_ROUTE_MAX_WORLD + 2];
-    CU(cudaMemcpyAsync(h, ctx->rt_counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned int h[RT_KIND_WORDS];
+    CU(cudaMemcpyAsync(h, route_counts(ctx, kind), sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    if (h[3 * PGM_ROUTE_MAX_WORLD])
+    if (h[PGM_ROUTE_MAX_WORLD])
         return fail(ctx, PGM_ERR_STATE, std::string(what) + ": an exchange queue overflowed (a GPU's share of the hashes / candidates is far above "
                                         "the average: extremely skewed input); rerun with the read-sharded scheme");
     memset(send, 0, sizeof *send);
     send->base = base; send->stride_bytes = stride; send->entry_bytes = entry_bytes; send->world = (uint32_t)ctx->route.world;
-    for (int d = 0; d < ctx->route.world; d++) send->count[d] = h[kind * PGM_ROUTE_MAX_WORLD + d];
+    for (int d = 0; d < ctx->route.world; d++) send->count[d] = h[d];
     return PGM_OK;
 }
 
@@ -1339,7 +1348,14 @@ int pgm_route_config(pgm_ctx *ctx, int rank, int world, const uint64_t *read_beg
     ctx->route.round_windows = round_windows ? std::max<uint64_t>(PGM_TILE_POS, (round_windows + PGM_TILE_POS - 1) / PGM_TILE_POS * PGM_TILE_POS)
                                              : (512ull << 20);
     int rc;
-    if ((rc = ensure(ctx, ctx->rt_counters, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int)))) return rc;
+    if ((rc = ensure(ctx, ctx->rt_counters, 2 * RT_SLOT_WORDS * sizeof(unsigned int)))) return rc;
+    ctx->route.slot = 0;
+    return PGM_OK;
+}
+
+int pgm_route_slot(pgm_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot > 1) return PGM_ERR_INVALID_ARG;
+    ctx->route.slot = slot;
     return PGM_OK;
 }
 
@@ -1382,13 +1398,13 @@ int pgm_route_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     const uint64_t n_local = (uint64_t)n * parts;
     ctx->route.cap_pat = route_cap(n_local, rt.world);
     if ((rc = ensure(ctx, ctx->bq_entries, (size_t)ctx->route.cap_pat * rt.world * sizeof(uint4)))) return rc;
-    CU(cudaMemsetAsync(ctx->rt_counters.p, 0, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int), ctx->stream));
+    CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_PATTERNS), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
     if (n) {
         pgm::BuildQueues q;
         q.entries = ctx->bq_entries.as<uint4>();
         q.count = route_counts(ctx, PGM_ROUTE_PATTERNS); q.cursor = nullptr;
         q.cap = ctx->route.cap_pat; q.region_bits = 0;
-        q.route_world = (uint32_t)rt.world; q.read_base = (uint32_t)rt.read_begin[rt.rank]; q.overflow = route_overflow(ctx);
+        q.route_world = (uint32_t)rt.world; q.read_base = (uint32_t)rt.read_begin[rt.rank]; q.overflow = route_overflow(ctx, PGM_ROUTE_PATTERNS);
         const uint32_t tail = seed_len % 32 ? (1u << (seed_len % 32)) - 1u : 0xFFFFFFFFu;
         const unsigned int grid = (unsigned int)std::min<uint64_t>(grid_for(n, PGM_BUILD_THREADS), (uint64_t)ctx->sm_count * 8);
         const size_t smem = (size_t)parts * PGM_BUILD_THREADS * sizeof(uint4);
@@ -1409,7 +1425,7 @@ int pgm_route_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
 int pgm_route_recv(pgm_ctx *ctx, int kind, uint64_t n_entries, void **ptr) {
     if (!ctx || !ptr || kind < 0 || kind > 2) return PGM_ERR_INVALID_ARG;
     CU(cudaSetDevice(ctx->device));
-    DevBuf &b = kind == PGM_ROUTE_PATTERNS ? ctx->rt_pat_recv : kind == PGM_ROUTE_WINDOWS ? ctx->rt_win_recv : ctx->rt_cand_recv;
+    DevBuf &b = kind == PGM_ROUTE_PATTERNS ? ctx->rt_pat_recv : kind == PGM_ROUTE_WINDOWS ? ctx->rt_win_recv_() : ctx->rt_cand_recv_();
     const size_t eb = kind == PGM_ROUTE_PATTERNS ? 16 : 12;
     if (b.cap < std::max<size_t>(n_entries, 1) * eb) CU(cudaStreamSynchronize(ctx->stream));   // (a kernel may still read the old buffer)
     int rc;
@@ -1467,8 +1483,8 @@ int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer 
     uint64_t b, e;
     route_range(ctx, rt.rank, round, b, e);
     ctx->route.cap_win = route_cap(rt.round_windows, rt.world);
-    if ((rc = ensure(ctx, ctx->rt_win_send, (size_t)ctx->route.cap_win * rt.world * 12))) return rc;
-    CU(cudaMemsetAsync(ctx->rt_counters.p, 0, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int), ctx->stream));
+    if ((rc = ensure(ctx, ctx->rt_win_send_(), (size_t)ctx->route.cap_win * rt.world * 12))) return rc;
+    CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_WINDOWS), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
     if (e > b && ctx->n_buckets) {
         pgm::RouteScanParams sp;
         memset(&sp, 0, sizeof sp);
@@ -1478,9 +1494,9 @@ int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer 
         sp.first_word = (uint32_t)(b / 32);
         sp.n_tiles = (uint32_t)((e - b + PGM_TILE_POS - 1) / PGM_TILE_POS);
         sp.tail_mask = ctx->seed_len % 32 ? (1u << (ctx->seed_len % 32)) - 1u : 0xFFFFFFFFu;
-        sp.tile_counter = route_tile_counter(ctx);
-        sp.q.entries = ctx->rt_win_send.as<uint32_t>(); sp.q.count = route_counts(ctx, PGM_ROUTE_WINDOWS);
-        sp.q.overflow = route_overflow(ctx); sp.q.cap = ctx->route.cap_win; sp.q.world = (uint32_t)rt.world;
+        sp.tile_counter = route_tile_counter(ctx, PGM_ROUTE_WINDOWS);
+        sp.q.entries = ctx->rt_win_send_().as<uint32_t>(); sp.q.count = route_counts(ctx, PGM_ROUTE_WINDOWS);
+        sp.q.overflow = route_overflow(ctx, PGM_ROUTE_WINDOWS); sp.q.cap = ctx->route.cap_win; sp.q.world = (uint32_t)rt.world;
         const unsigned int grid = (unsigned int)std::min<uint64_t>(sp.n_tiles, (uint64_t)ctx->sm_count * 4);
         cudaError_t le = cudaSuccess;
         KLAUNCH(PGM_K_ROUTE_SCAN, "route_scan_kernel",
@@ -1497,7 +1513,7 @@ int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer 
         if (le != cudaSuccess) return cuda_fail(ctx, le, "route_scan_kernel (shared memory attribute)");
     }
     ctx->state_fresh = false;
-    return route_fetch_counts(ctx, PGM_ROUTE_WINDOWS, send, ctx->rt_win_send.p, (uint64_t)ctx->route.cap_win * 12, 12, "pgm_route_scan");
+    return route_fetch_counts(ctx, PGM_ROUTE_WINDOWS, send, ctx->rt_win_send_().p, (uint64_t)ctx->route.cap_win * 12, 12, "pgm_route_scan");
 }
 
 int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *in_counts, pgm_route_buffer *send) {
@@ -1508,12 +1524,12 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
     CU(cudaSetDevice(ctx->device));
     uint64_t n_in = 0;
     for (int s = 0; s < rt.world; s++) n_in += in_counts[s];
-    if (n_in && ctx->rt_win_recv.cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: the windows have not been received (pgm_route_recv)");
+    if (n_in && ctx->rt_win_recv_().cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: the windows have not been received (pgm_route_recv)");
     // on average well under one candidate per window; hot keys are covered by the slack
     ctx->route.cap_cand = (uint32_t)std::min<uint64_t>(n_in / rt.world + (4u << 20), 0xFFFFFFF0ull);
     int rc;
-    if ((rc = ensure(ctx, ctx->rt_cand_send, (size_t)ctx->route.cap_cand * rt.world * 12))) return rc;
-    CU(cudaMemsetAsync(ctx->rt_counters.p, 0, (3 * PGM_ROUTE_MAX_WORLD + 2) * sizeof(unsigned int), ctx->stream));
+    if ((rc = ensure(ctx, ctx->rt_cand_send_(), (size_t)ctx->route.cap_cand * rt.world * 12))) return rc;
+    CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_CANDIDATES), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
     // the received windows stream through the L2 (12 bytes per window, 48 x the text they came from): without a persisting
     // window the stream evicts the filter and every filter lookup becomes a DRAM access (PGM_ROUTE_PERSIST=0 turns it off)
     static const bool persist = !(getenv("PGM_ROUTE_PERSIST") && atoi(getenv("PGM_ROUTE_PERSIST")) == 0);
@@ -1525,14 +1541,14 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
         route_range(ctx, s, round, b, e);
         pgm::RouteProbeParams pp;
         memset(&pp, 0, sizeof pp);
-        pp.src = ctx->rt_win_recv.as<uint32_t>() + off * 3;
+        pp.src = ctx->rt_win_recv_().as<uint32_t>() + off * 3;
         pp.n = in_counts[s];
         pp.pos_base = b;
         pp.tab = table_view(ctx);
         pp.part_bits = ctx->part_bits; pp.world = (uint32_t)rt.world;
         for (int k = 0; k <= rt.world; k++) pp.read_begin[k] = rt.read_begin[k];
-        pp.q.entries = ctx->rt_cand_send.as<uint32_t>(); pp.q.count = route_counts(ctx, PGM_ROUTE_CANDIDATES);
-        pp.q.overflow = route_overflow(ctx); pp.q.cap = ctx->route.cap_cand; pp.q.world = (uint32_t)rt.world;
+        pp.q.entries = ctx->rt_cand_send_().as<uint32_t>(); pp.q.count = route_counts(ctx, PGM_ROUTE_CANDIDATES);
+        pp.q.overflow = route_overflow(ctx, PGM_ROUTE_CANDIDATES); pp.q.cap = ctx->route.cap_cand; pp.q.world = (uint32_t)rt.world;
         pp.counters = ctx->counters.as<unsigned long long>();
         const uint64_t chunks = (pp.n + PGM_ROUTE_PROBE_CHUNK - 1) / PGM_ROUTE_PROBE_CHUNK;
         const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * 6);
@@ -1540,14 +1556,14 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
         off += in_counts[s];
     }
     if (persist && (rc = filter_window(ctx, false, true))) return rc;
-    return route_fetch_counts(ctx, PGM_ROUTE_CANDIDATES, send, ctx->rt_cand_send.p, (uint64_t)ctx->route.cap_cand * 12, 12, "pgm_route_probe");
+    return route_fetch_counts(ctx, PGM_ROUTE_CANDIDATES, send, ctx->rt_cand_send_().p, (uint64_t)ctx->route.cap_cand * 12, 12, "pgm_route_probe");
 }
 
 int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_in) {
     if (!ctx) return PGM_ERR_INVALID_ARG;
     const pgm_ctx::Route &rt = ctx->route;
     if (!rt.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_verify: pgm_route_begin has not been called");
-    if (n_in && ctx->rt_cand_recv.cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_verify: the candidates have not been received (pgm_route_recv)");
+    if (n_in && ctx->rt_cand_recv_().cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_verify: the candidates have not been received (pgm_route_recv)");
     CU(cudaSetDevice(ctx->device));
     if (!n_in || !ctx->n_reads()) return PGM_OK;
     pgm::RouteVerifyParams vp;
@@ -1558,7 +1574,7 @@ int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_in) {
     vp.v.seed_len = ctx->shift_unit(); vp.v.parts = ctx->parts; vp.v.max_mm = ctx->max_mm; vp.v.min_mm = ctx->min_mm;
     vp.v.rev_mode = rev_mode ? 1 : 0;
     vp.v.tab = table_view(ctx); vp.v.reads = reads_view(ctx); vp.v.pr = per_read(ctx);
-    vp.src = ctx->rt_cand_recv.as<uint32_t>(); vp.n = n_in;
+    vp.src = ctx->rt_cand_recv_().as<uint32_t>(); vp.n = n_in;
     vp.read_base = (uint32_t)rt.read_begin[rt.rank];
     vp.counters = ctx->counters.as<unsigned long long>();
     ctx->state_fresh = false; ctx->aux_clean = false; ctx->outputs_valid = false;

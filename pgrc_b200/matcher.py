@@ -205,6 +205,9 @@ class GpuReadsMatcher:
         self._check(self._lib.pgm_route_config(self._h, rank, world, arr, round_windows))
         self._route_world = world
 
+    def route_slot(self, slot: int):
+        self._check(self._lib.pgm_route_slot(self._h, slot))
+
     def route_rounds(self) -> int:
         r = ctypes.c_uint32()
         self._check(self._lib.pgm_route_rounds(self._h, ctypes.byref(r)))
@@ -494,8 +497,9 @@ class TorchComm:
         dist.all_gather_into_tensor(allc, mine, group=self.group)
         return allc.view(self.world, self.world)[:, self.rank].tolist()
 
-    def all_to_all(self, recv, send):
-        """send[d] -> rank d, recv[s] <- rank s (uint8 tensors or None for empty segments)."""
+    def all_to_all_async(self, recv, send):
+        """send[d] -> rank d, recv[s] <- rank s (uint8 tensors or None for empty segments): NCCL send/recv pairs on the
+        communicator's own stream; returns an object whose wait() orders the current stream behind the transfer."""
         import torch.distributed as dist
         ops = []
         for k in range(1, self.world):
@@ -507,8 +511,26 @@ class TorchComm:
         reqs = dist.batch_isend_irecv(ops) if ops else []
         if recv[self.rank] is not None:
             recv[self.rank].copy_(send[self.rank])
-        for r in reqs:
+        return _Pending(reqs, (recv, send))
+
+    def all_to_all(self, recv, send):
+        self.all_to_all_async(recv, send).wait()
+
+    def sibling(self):
+        """A second communicator over the same ranks (its own NCCL stream): transfers on it do not queue behind this one's.
+        Collective: every rank of the group calls it."""
+        import torch.distributed as dist
+        return TorchComm(dist.new_group(self._peers))
+
+
+class _Pending:
+    def __init__(self, reqs, keep):
+        self._reqs, self._keep = reqs, keep
+
+    def wait(self):
+        for r in self._reqs:
             r.wait()
+        self._keep = None
 
 
 def _as_comm(comm_or_group):
@@ -551,41 +573,62 @@ def read_ranges(n_reads: int, world: int):
     return [(n_reads * g) // world for g in range(world + 1)]
 
 
-def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total: int, round_windows: int = 0) -> dict:
+def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total: int, round_windows: int = 0, comm2=None) -> dict:
     """The routed scheme (include/pgrc_gpu_matcher.h, pgm_route_*): this rank's context holds the whole text and its own
     read range (`read_ranges`).  Per phase the seeds are exchanged once (all-to-all by hash owner); per pass and round the
-    windows of this rank's text range go to the hash owners and the candidates they find go to the read owners.  Returns
-    the bytes this rank sent per kind."""
+    windows of this rank's text range go to the hash owners and the candidates they find go to the read owners.
+    With a second communicator (`comm2`, e.g. comm.sibling()) the rounds are software-pipelined: the windows of round
+    r + 1 are emitted and travel (comm) while round r is probed, its candidates exchanged (comm2) and verified — the two
+    sets of exchange buffers of the context (pgm_route_slot) make that safe.  Returns the bytes this rank sent per kind."""
     comm = _as_comm(comm)
     dev = f"cuda:{m.device}" if isinstance(m.device, int) else m.device
     m.route_config(comm.rank, comm.world, read_ranges(n_reads_total, comm.world), round_windows)
     sent = {"patterns": 0, "windows": 0, "candidates": 0}
+    small = comm2 if comm2 is not None else comm          # counts and candidates
 
-    def exchange(kind, counts, segs, eb):
-        in_counts = comm.exchange_counts(counts, dev)
-        recv = m.route_recv(kind, in_counts, eb)
-        comm.all_to_all(recv, segs)
-        return in_counts
+    def emit(rev, rnd):
+        m.route_slot(rnd & 1)
+        counts, segs, eb = m.route_scan(rev, rnd)
+        sent["windows"] += sum(counts) * eb
+        win_in = small.exchange_counts(counts, dev)
+        recv = m.route_recv(PGM_ROUTE_WINDOWS, win_in, eb)
+        return win_in, comm.all_to_all_async(recv, segs)
 
+    def consume(rev, rnd, win_in, pending):
+        pending.wait()
+        m.route_slot(rnd & 1)
+        counts, segs, eb = m.route_probe(rev, rnd, win_in)
+        sent["candidates"] += sum(counts) * eb
+        cand_in = small.exchange_counts(counts, dev)
+        recv = m.route_recv(PGM_ROUTE_CANDIDATES, cand_in, eb)
+        small.all_to_all(recv, segs)
+        m.route_verify(rev, sum(cand_in))
+
+    rounds = 1
     for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
         if ilv:
             raise PgmError(-6, "the routed scheme covers matching modes 'd'/'D' (contiguous seeds); use read ranges for 'i' and 'c'")
+        m.route_slot(0)
         counts, segs, eb = m.route_begin(seed_len, parts, max_mm, min_mm, cont)
         sent["patterns"] += sum(counts) * eb
-        in_counts = exchange(PGM_ROUTE_PATTERNS, counts, segs, eb)
-        m.route_build(sum(in_counts))
+        pat_in = small.exchange_counts(counts, dev)
+        recv = m.route_recv(PGM_ROUTE_PATTERNS, pat_in, eb)
+        comm.all_to_all(recv, segs)
+        m.route_build(sum(pat_in))
         rounds = m.route_rounds()
         for rev in ((False, True) if rev_compl_pg else (False,)):
-            for rnd in range(rounds):
-                counts, segs, eb = m.route_scan(rev, rnd)
-                sent["windows"] += sum(counts) * eb
-                win_in = exchange(PGM_ROUTE_WINDOWS, counts, segs, eb)
-                counts, segs, eb = m.route_probe(rev, rnd, win_in)
-                sent["candidates"] += sum(counts) * eb
-                cand_in = exchange(PGM_ROUTE_CANDIDATES, counts, segs, eb)
-                m.route_verify(rev, sum(cand_in))
+            if comm2 is None:
+                for rnd in range(rounds):
+                    consume(rev, rnd, *emit(rev, rnd))
+            else:
+                cur = emit(rev, 0)
+                for rnd in range(rounds):
+                    nxt = emit(rev, rnd + 1) if rnd + 1 < rounds else None
+                    consume(rev, rnd, *cur)
+                    cur = nxt
             m.resolve_pass(rev)
-    return {"sent_bytes": sent, "rounds_per_pass": rounds}
+    m.route_slot(0)
+    return {"sent_bytes": sent, "rounds_per_pass": rounds, "pipelined": comm2 is not None}
 
 
 def map_reads_into_pg_sharded(text, lq_packed, n_packed, read_len: int, *, rank: int, world: int, device: int,

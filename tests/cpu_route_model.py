@@ -20,7 +20,12 @@ class CpuRouteMatcher(CpuShardMatcher):
         self.pg_len = len(self.text)
         self.rc_text = np.array([_COMP[int(c)] for c in self.text[::-1]], np.uint8)
 
+    def route_slot(self, slot):
+        """Two sets of exchange buffers in the product; the model keeps the receive buffers per slot."""
+        self.slot = slot
+
     def route_config(self, rank, world, read_begin, round_windows=0):
+        self.slot, self.recvs = 0, {}
         self.rank, self.world, self.read_begin = rank, world, [int(x) for x in read_begin]
         self.round_windows = round_windows or (1 << 30)
 
@@ -64,15 +69,15 @@ class CpuRouteMatcher(CpuShardMatcher):
         return self._segs(out, self.world)
 
     def route_recv(self, kind, in_counts, entry_bytes):
-        self.recv = [torch.empty(int(c) * entry_bytes, dtype=torch.uint8) if c else None for c in in_counts]
-        return self.recv
+        self.recvs[(kind, self.slot)] = [torch.empty(int(c) * entry_bytes, dtype=torch.uint8) if c else None for c in in_counts]
+        return self.recvs[(kind, self.slot)]
 
-    def _rows(self):
-        return [(v.view(torch.int64).reshape(-1, 2).tolist() if v is not None else []) for v in self.recv]
+    def _rows(self, kind):
+        return [(v.view(torch.int64).reshape(-1, 2).tolist() if v is not None else []) for v in self.recvs[(kind, self.slot)]]
 
     def route_build(self, n_in):
         self.table = {}
-        for rows in self._rows():
+        for rows in self._rows(0):
             for k, pat in rows:
                 self.table.setdefault(k, []).append(pat)
         assert sum(len(v) for v in self.table.values()) == n_in
@@ -88,7 +93,7 @@ class CpuRouteMatcher(CpuShardMatcher):
 
     def route_probe(self, rev, rnd, in_counts):
         out = {}
-        for s, rows in enumerate(self._rows()):
+        for s, rows in enumerate(self._rows(1)):
             assert len(rows) == in_counts[s]
             base = self._range(s, rnd)[0]
             for k, rel in rows:
@@ -101,7 +106,7 @@ class CpuRouteMatcher(CpuShardMatcher):
     def route_verify(self, rev, n_in):
         t = self.rc_text if rev else self.text
         seen = 0
-        for rows in self._rows():
+        for rows in self._rows(2):
             for g, pat in rows:
                 seen += 1
                 self._event(pat // self.parts - self.read_begin[self.rank], pat % self.parts, g, t, 0, rev)

@@ -67,6 +67,17 @@ class LocalComm:
         self._sync()
         return res
 
+    def sibling(self):
+        return self
+
+    def all_to_all_async(self, recv, send):
+        self.all_to_all(recv, send)
+
+        class _Done:
+            def wait(self):
+                pass
+        return _Done()
+
     def all_to_all(self, recv, send):
         w = self.w
         w.slots[self.rank] = send

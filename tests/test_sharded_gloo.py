@@ -166,7 +166,9 @@ def _worker_routed(rank, world, port, case, kw, round_windows, ret_dir):
     m.set_reads(reads[rb[rank]:rb[rank + 1]], None, inp.read_len)
     plan = matcher.MatchPlan.derive(inp.read_len, kw.get("seed", 38), kw.get("min_chars_per_mismatch", 3), kw.get("mode", "d"),
                                     kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
-    info = matcher.run_plan_routed(m, plan, kw.get("rev_compl", True), matcher.TorchComm(), len(reads), round_windows)
+    comm = matcher.TorchComm()
+    info = matcher.run_plan_routed(m, plan, kw.get("rev_compl", True), comm, len(reads), round_windows,
+                                   comm2=comm.sibling() if round_windows else None)      # several rounds: the pipelined schedule
     res = m.get_results()
     np.savez(os.path.join(ret_dir, f"rank{rank}.npz"), pos=res.pos, rc=res.rc, mm=res.mm, lo=rb[rank], hi=rb[rank + 1], rounds=info["rounds_per_pass"])
     dist.destroy_process_group()
