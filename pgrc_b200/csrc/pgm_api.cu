@@ -796,7 +796,9 @@ int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t m
     if (fbits < 0) fbits = std::min(n_patterns > (100ull << 20) ? 29 : 28, std::max(15, ceil_log2(std::max<uint64_t>(n_patterns, 1) * 8)));
     const bool auto_bits = ctx->filter_log2_bits < 0;
     // hash-sliced filter: beyond ~130 M patterns a 2^29-bit filter has fewer than 4 bits per pattern and lets most windows
-    // through; give it about 4 bits per pattern in 2^s slices of 2^29 bits (up to 8: 512 MB) and scan once per slice
+    // through; a second 64 MB slice (one more scan launch) pays — measured at C5 (990 M patterns, profiles/bench_c5_slices*_r02e.json):
+    // scan 389 -> 334 ms per step with 2 slices (63 % of the windows still pass), 340 with 4, 521 with 8: re-hashing the text
+    // costs 22 ms per launch, about what the next doubling of the filter saves in table probes
     ctx->filter_slice_bits = 0;
     if (auto_bits && !interleaved && ctx->blocked_scan <= 0) {
         if (ctx->filter_slices_force >= 0) {
@@ -804,7 +806,7 @@ int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t m
             ctx->filter_slice_bits = (uint32_t)std::min(ctx->filter_slices_force, std::max(0, fbits - 8));
             if (fbits == 29) fbits += (int)ctx->filter_slice_bits;
         } else if (fbits == 29) {
-            ctx->filter_slice_bits = (uint32_t)std::min(3, std::max(0, ceil_log2(n_patterns * 4) - 29));
+            ctx->filter_slice_bits = (uint32_t)std::min(1, std::max(0, ceil_log2(n_patterns * 4) - 29));
             fbits += (int)ctx->filter_slice_bits;
         }
     }
@@ -1550,8 +1552,8 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
         pp.q.entries = ctx->rt_cand_send_().as<uint32_t>(); pp.q.count = route_counts(ctx, PGM_ROUTE_CANDIDATES);
         pp.q.overflow = route_overflow(ctx, PGM_ROUTE_CANDIDATES); pp.q.cap = ctx->route.cap_cand; pp.q.world = (uint32_t)rt.world;
         pp.counters = ctx->counters.as<unsigned long long>();
-        const uint64_t chunks = (pp.n + PGM_ROUTE_PROBE_CHUNK - 1) / PGM_ROUTE_PROBE_CHUNK;
-        const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * 6);
+        const uint64_t chunks = (pp.n + PGM_ROUTE_PROBE_CHUNK2 - 1) / PGM_ROUTE_PROBE_CHUNK2;
+        const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * 4);
         KLAUNCH(PGM_K_ROUTE_PROBE, "route_probe_kernel", pgm::route_probe_kernel<<<grid, PGM_ROUTE_THREADS, 0, ctx->stream>>>(pp));
         off += in_counts[s];
     }

@@ -25,7 +25,6 @@
 
 #define PGM_ROUTE_MAX_WORLD 16
 #define PGM_ROUTE_THREADS 256
-#define PGM_ROUTE_PROBE_CHUNK 1024
 #define PGM_ROUTE_PROBE_STAGE 3072
 
 namespace pgm {
@@ -186,23 +185,29 @@ __device__ __forceinline__ uint32_t route_owner(const RouteProbeParams &p, uint3
     return d;
 }
 
-// A CTA takes chunks of the sender's segment; every thread tests its window against the filter, probes the table (one
-// 256-bit load per bucket), walks hot-key chains here (next[] belongs to the table owner), and stages the candidates in
-// shared memory with their rank per read owner; one global reservation per owner and chunk.  Candidates beyond the
-// stage (hot keys) take the slow path: one global atomic each.
+// A CTA takes chunks of 1024 received windows.  Phase 0: the chunk's words land in shared memory with coalesced loads.
+// Phase 1, all threads: four entries per thread, four filter gathers in flight, the survivors (a fifth of the windows
+// once the table is spread over 8 GPUs) ballot-compacted into an index list.  Phase 2: the threads pull survivors from
+// the list and probe the table (one 256-bit load per bucket), walk hot-key chains here (next[] belongs to the table
+// owner) and stage the candidates in shared memory with their rank per read owner; one global reservation per owner and
+// chunk.  Candidates beyond the stage (hot keys) take the slow path: one global atomic each.
+#define PGM_ROUTE_PROBE_PER_THREAD 4
+#define PGM_ROUTE_PROBE_CHUNK2 (PGM_ROUTE_THREADS * PGM_ROUTE_PROBE_PER_THREAD)
 __global__ void __launch_bounds__(PGM_ROUTE_THREADS) route_probe_kernel(const __grid_constant__ RouteProbeParams p) {
     __shared__ uint32_t s_pos[PGM_ROUTE_PROBE_STAGE], s_pat[PGM_ROUTE_PROBE_STAGE];
     __shared__ uint16_t s_rank[PGM_ROUTE_PROBE_STAGE];
     __shared__ uint8_t s_dest[PGM_ROUTE_PROBE_STAGE];
+    __shared__ uint32_t s_in[3 * PGM_ROUTE_PROBE_CHUNK2];                    // the chunk: {h1', h2, rel} per entry
+    __shared__ uint16_t s_idx[PGM_ROUTE_PROBE_CHUNK2];                       // entries that passed the filter
     __shared__ unsigned int s_cnt[PGM_ROUTE_MAX_WORLD], s_base[PGM_ROUTE_MAX_WORLD];
-    __shared__ unsigned int s_n;
-    const uint32_t t = threadIdx.x;
+    __shared__ unsigned int s_n, s_nlive;
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     if (t < PGM_ROUTE_MAX_WORLD) s_cnt[t] = 0;
-    if (t == 0) s_n = 0;
+    if (t == 0) { s_n = 0; s_nlive = 0; }
     __syncthreads();
     bool over = false;
-    unsigned long long n_pos = 0;
-    const uint64_t n_chunks = (p.n + PGM_ROUTE_PROBE_CHUNK - 1) / PGM_ROUTE_PROBE_CHUNK;
+    const uint64_t n_chunks = (p.n + PGM_ROUTE_PROBE_CHUNK2 - 1) / PGM_ROUTE_PROBE_CHUNK2;
     const uint64_t pol_keep = policy_evict_last();
     auto emit_slow = [&](uint32_t rel, uint32_t pat) {
         const uint64_t gpos = p.pos_base + rel;
@@ -222,28 +227,58 @@ __global__ void __launch_bounds__(PGM_ROUTE_THREADS) route_probe_kernel(const __
         } else emit_slow(rel, pat);
     };
     for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const uint64_t first = c * PGM_ROUTE_PROBE_CHUNK, last = min(first + PGM_ROUTE_PROBE_CHUNK, p.n);
-        for (uint64_t i = first + t; i < last; i += PGM_ROUTE_THREADS) {
-            const uint32_t h1p = __ldcs(p.src + 3 * i), h2 = __ldcs(p.src + 3 * i + 1), rel = __ldcs(p.src + 3 * i + 2);
-            if (p.tab.filter) {
-                const uint32_t f = route_filter_hash(h1p, h2);
-                const uint32_t fm = filter_bits(f, p.tab.filter_k);
-                if ((ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep) & fm) != fm) continue;
+        // ---- phase 0: the chunk -> shared memory
+        const uint64_t e0 = c * PGM_ROUTE_PROBE_CHUNK2;
+        const uint32_t n_here = (uint32_t)min((uint64_t)PGM_ROUTE_PROBE_CHUNK2, p.n - e0);
+        for (uint32_t k = t; k < 3 * n_here; k += PGM_ROUTE_THREADS) s_in[k] = __ldcs(p.src + 3 * e0 + k);
+        __syncthreads();
+        // ---- phase 1: filter
+        uint32_t fw[PGM_ROUTE_PROBE_PER_THREAD], fm[PGM_ROUTE_PROBE_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < PGM_ROUTE_PROBE_PER_THREAD; k++) {
+            const uint32_t i = t + k * PGM_ROUTE_THREADS;
+            fw[k] = 0xFFFFFFFFu; fm[k] = 0;
+            if (i < n_here) {
+                const uint32_t f = route_filter_hash(s_in[3 * i], s_in[3 * i + 1]);
+                fm[k] = filter_bits(f, p.tab.filter_k);
+                if (p.tab.filter) fw[k] = ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep);
             }
-            n_pos++;
+        }
+        uint32_t bal[PGM_ROUTE_PROBE_PER_THREAD], tot = 0;
+#pragma unroll
+        for (int k = 0; k < PGM_ROUTE_PROBE_PER_THREAD; k++) {
+            bal[k] = __ballot_sync(PGM_FULL, t + k * PGM_ROUTE_THREADS < n_here && (fw[k] & fm[k]) == fm[k]);
+            tot += __popc(bal[k]);
+        }
+        if (tot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_nlive, tot);
+            base = __shfl_sync(PGM_FULL, base, 0);
+#pragma unroll
+            for (int k = 0; k < PGM_ROUTE_PROBE_PER_THREAD; k++) {
+                if ((bal[k] >> lane) & 1u) s_idx[base + __popc(bal[k] & lt_mask)] = (uint16_t)(t + k * PGM_ROUTE_THREADS);
+                base += __popc(bal[k]);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: table probes of the survivors
+        const uint32_t n_live = s_nlive;
+        for (uint32_t i = t; i < n_live; i += PGM_ROUTE_THREADS) {
+            const uint32_t at = s_idx[i];
+            const uint32_t h1p = s_in[3 * at], h2 = s_in[3 * at + 1], rel = s_in[3 * at + 2];
             const uint32_t tag = seed_tag(h2);
             uint32_t b = __umulhi(h1p, p.tab.n_buckets);
             const uint32_t step = 1u + __umulhi(h2 * 0x9E3779B1u, p.tab.n_buckets - 1u);
             for (;;) {
-                const u32x8 s = ld256_stream(p.tab.buckets + b);
+                const u32x8 sl = ld256_stream(p.tab.buckets + b);
                 bool em = false;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    em |= s.v[2 * k + 1] == 0xFFFFFFFFu;
-                    if ((s.v[2 * k + 1] & 0x7FFFFFFFu) == tag) {
-                        uint32_t pat = s.v[2 * k];
+                    em |= sl.v[2 * k + 1] == 0xFFFFFFFFu;
+                    if ((sl.v[2 * k + 1] & 0x7FFFFFFFu) == tag) {
+                        uint32_t pat = sl.v[2 * k];
                         emit(rel, pat);
-                        if (s.v[2 * k + 1] & 0x80000000u)          // hot key: the patterns chained behind this slot
+                        if (sl.v[2 * k + 1] & 0x80000000u)         // hot key: the patterns chained behind this slot
                             for (pat = __ldg(p.tab.next + pat); pat != PGM_NIL; pat = __ldg(p.tab.next + pat)) emit(rel, pat);
                     }
                 }
@@ -259,8 +294,9 @@ __global__ void __launch_bounds__(PGM_ROUTE_THREADS) route_probe_kernel(const __
             s_base[t] = cc ? atomicAdd(p.q.count + t, cc) : 0u;
             s_cnt[t] = 0;
         }
+        if (t == 0 && n_live) atomicAdd(p.counters + 3, (unsigned long long)n_live);
         __syncthreads();
-        if (t == 0) s_n = 0;
+        if (t == 0) { s_n = 0; s_nlive = 0; }
         for (uint32_t i = t; i < staged; i += PGM_ROUTE_THREADS) {
             const uint32_t dest = s_dest[i], idx = s_base[dest] + s_rank[i];
             if (idx < p.q.cap) {
@@ -272,9 +308,6 @@ __global__ void __launch_bounds__(PGM_ROUTE_THREADS) route_probe_kernel(const __
         __syncthreads();
     }
     if (over) *p.q.overflow = 1u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n_pos += __shfl_xor_sync(PGM_FULL, n_pos, o);
-    if ((t & 31u) == 0 && n_pos) atomicAdd(p.counters + 3, n_pos);
 }
 
 // ------------------------------------------------------------------------------------------ pass: verify
