@@ -1532,9 +1532,10 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
     int rc;
     if ((rc = ensure(ctx, ctx->rt_cand_send_(), (size_t)ctx->route.cap_cand * rt.world * 12))) return rc;
     CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_CANDIDATES), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
-    // the received windows stream through the L2 (12 bytes per window, 48 x the text they came from): without a persisting
-    // window the stream evicts the filter and every filter lookup becomes a DRAM access (PGM_ROUTE_PERSIST=0 turns it off)
-    static const bool persist = !(getenv("PGM_ROUTE_PERSIST") && atoi(getenv("PGM_ROUTE_PERSIST")) == 0);
+    // the received windows stream through the L2 (12 bytes per window, 48 x the text they came from) next to the filter;
+    // PGM_ROUTE_PERSIST=1 puts a persisting access-policy window over the filter for this kernel (experiment knob: the L2
+    // carve-out it needs stays set for the device and takes the same 64 MB away from every other kernel)
+    static const bool persist = getenv("PGM_ROUTE_PERSIST") && atoi(getenv("PGM_ROUTE_PERSIST")) != 0;
     if (persist && (rc = filter_window(ctx, true, true))) return rc;
     uint64_t off = 0;
     for (int s = 0; s < rt.world; s++) {

@@ -490,6 +490,7 @@ def test_hash_sliced_filter_forced(monkeypatch, slices):
     4-bits-per-pattern filter) forced onto small inputs: same results, and — the filter being the same bits, only visited
     slice by slice — the same filter positives and candidates as the single-launch scan."""
     inputs = (synth.adversarial(81, 100), synth.adversarial(82, 150), synth.workload(200_000, 50_000, 150, 0.005, seed=83, n_frac=0.02, name="c2 shape"))
+    monkeypatch.setenv("PGM_FILTER_PAIR", "0")        # (paired lookups are another filter layout, never combined with slices)
     base = [_check(inp)[0] for inp in inputs]
     monkeypatch.setenv("PGM_FILTER_SLICES", slices)
     for inp, b in zip(inputs, base):
