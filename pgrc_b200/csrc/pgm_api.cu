@@ -1554,7 +1554,7 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
         pp.q.overflow = route_overflow(ctx, PGM_ROUTE_CANDIDATES); pp.q.cap = ctx->route.cap_cand; pp.q.world = (uint32_t)rt.world;
         pp.counters = ctx->counters.as<unsigned long long>();
         const uint64_t chunks = (pp.n + PGM_ROUTE_PROBE_CHUNK2 - 1) / PGM_ROUTE_PROBE_CHUNK2;
-        const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * 4);
+        const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * PGM_ROUTE_PROBE_CTAS);
         KLAUNCH(PGM_K_ROUTE_PROBE, "route_probe_kernel", pgm::route_probe_kernel<<<grid, PGM_ROUTE_THREADS, 0, ctx->stream>>>(pp));
         off += in_counts[s];
     }

@@ -25,7 +25,8 @@
 
 #define PGM_ROUTE_MAX_WORLD 16
 #define PGM_ROUTE_THREADS 256
-#define PGM_ROUTE_PROBE_STAGE 3072
+#define PGM_ROUTE_PROBE_STAGE 1024          // candidates of one chunk staged in shared memory (about 120 expected; hot keys overflow to the slow path)
+#define PGM_ROUTE_PROBE_CTAS 6               // resident CTAs per SM: the chunk phases (load, filter, probe, flush) are latency-bound, other CTAs fill the gaps
 
 namespace pgm {
 
@@ -193,7 +194,7 @@ __device__ __forceinline__ uint32_t route_owner(const RouteProbeParams &p, uint3
 // chunk.  Candidates beyond the stage (hot keys) take the slow path: one global atomic each.
 #define PGM_ROUTE_PROBE_PER_THREAD 4
 #define PGM_ROUTE_PROBE_CHUNK2 (PGM_ROUTE_THREADS * PGM_ROUTE_PROBE_PER_THREAD)
-__global__ void __launch_bounds__(PGM_ROUTE_THREADS) route_probe_kernel(const __grid_constant__ RouteProbeParams p) {
+__global__ void __launch_bounds__(PGM_ROUTE_THREADS, PGM_ROUTE_PROBE_CTAS) route_probe_kernel(const __grid_constant__ RouteProbeParams p) {
     __shared__ uint32_t s_pos[PGM_ROUTE_PROBE_STAGE], s_pat[PGM_ROUTE_PROBE_STAGE];
     __shared__ uint16_t s_rank[PGM_ROUTE_PROBE_STAGE];
     __shared__ uint8_t s_dest[PGM_ROUTE_PROBE_STAGE];

@@ -8,14 +8,17 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=index,name,memory.total --format=csv > $OUT/gpus_$TAG.txt 2>&1
 nvidia-smi topo -m >> $OUT/gpus_$TAG.txt 2>&1
 PORT=29511
+MODEFLAGS="--verify"
+if [ -n "$QUICK" ]; then MODEFLAGS="--no-e2e"; fi
+RUNNER=${RUNNER:-}
 for run in $RUNS; do
     IFS=: read -r w shard extra envs label <<< "$run"
     extra=${extra//,/ }
     envs=${envs//,/ }
     name=bench_${w}_n${N}_${shard}${label:+_$label}_$TAG
     PORT=$((PORT + 1))
-    env $envs timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \
-        bench.py --gpus $N --workload $w --shard $shard --verify --steps 5 --warmup 2 --no-cpu-baseline $extra > $OUT/$name.json 2> $OUT/$name.err
+    $RUNNER env $envs timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \
+        bench.py --gpus $N --workload $w --shard $shard $MODEFLAGS --steps 5 --warmup 2 --no-cpu-baseline $extra > $OUT/$name.json 2> $OUT/$name.err
     echo "== $name exit $?"
     tail -c 3000 $OUT/$name.json; grep -v "^W1\|^\[W\|^$" $OUT/$name.err | tail -8
 done
