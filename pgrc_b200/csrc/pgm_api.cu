@@ -120,7 +120,7 @@ struct pgm_ctx {
         int slot = 0;                       // which of the two sets of exchange buffers the route_* calls use (pgm_route_slot)
     } route;
     // two sets of exchange buffers: the windows of round r + 1 can be emitted and travel while round r is probed and verified
-    DevBuf rt_win_send2[2], rt_win_recv2[2], rt_cand_send2[2], rt_cand_recv2[2], rt_pat_recv, rt_counters;
+    DevBuf rt_win_send2[2], rt_win_recv2[2], rt_cand_send2[2], rt_cand_recv2[2], rt_pat_recv, rt_counters, rt_live, rt_live_count;
     DevBuf &rt_win_send_() { return rt_win_send2[route.slot]; }
     DevBuf &rt_win_recv_() { return rt_win_recv2[route.slot]; }
     DevBuf &rt_cand_send_() { return rt_cand_send2[route.slot]; }
@@ -572,7 +572,7 @@ void pgm_destroy(pgm_ctx *ctx) {
                       &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter, &ctx->bq_entries, &ctx->bq_counters,
                       &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->mis_sums, &ctx->mis_offsets, &ctx->mis_pos, &ctx->mis_syms,
                       &ctx->rt_win_send2[0], &ctx->rt_win_send2[1], &ctx->rt_win_recv2[0], &ctx->rt_win_recv2[1], &ctx->rt_cand_send2[0],
-                      &ctx->rt_cand_send2[1], &ctx->rt_cand_recv2[0], &ctx->rt_cand_recv2[1], &ctx->rt_pat_recv, &ctx->rt_counters,
+                      &ctx->rt_cand_send2[1], &ctx->rt_cand_recv2[0], &ctx->rt_cand_recv2[1], &ctx->rt_pat_recv, &ctx->rt_counters, &ctx->rt_live, &ctx->rt_live_count,
                       &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
@@ -1537,15 +1537,33 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
     // carve-out it needs stays set for the device and takes the same 64 MB away from every other kernel)
     static const bool persist = getenv("PGM_ROUTE_PERSIST") && atoi(getenv("PGM_ROUTE_PERSIST")) != 0;
     if (persist && (rc = filter_window(ctx, true, true))) return rc;
+    // scratch for the windows that pass the filter (at most the largest sender segment) + their device counter per sender
+    uint64_t n_max = 0;
+    for (int s = 0; s < rt.world; s++) n_max = std::max(n_max, in_counts[s]);
+    if ((rc = ensure(ctx, ctx->rt_live, std::max<uint64_t>(n_max, 1) * 12)) || (rc = ensure(ctx, ctx->rt_live_count, PGM_ROUTE_MAX_WORLD * sizeof(unsigned int)))) return rc;
+    CU(cudaMemsetAsync(ctx->rt_live_count.p, 0, PGM_ROUTE_MAX_WORLD * sizeof(unsigned int), ctx->stream));
     uint64_t off = 0;
     for (int s = 0; s < rt.world; s++) {
         if (!in_counts[s]) continue;
         uint64_t b, e;
         route_range(ctx, s, round, b, e);
+        pgm::RouteFilterParams fp;
+        memset(&fp, 0, sizeof fp);
+        fp.src = ctx->rt_win_recv_().as<uint32_t>() + off * 3;
+        fp.n = in_counts[s];
+        fp.tab = table_view(ctx);
+        fp.live = ctx->rt_live.as<uint32_t>();
+        fp.n_live = ctx->rt_live_count.as<unsigned int>() + s;
+        {
+            const uint64_t chunks = (fp.n + PGM_ROUTE_FILTER_CHUNK - 1) / PGM_ROUTE_FILTER_CHUNK;
+            const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * 8);
+            KLAUNCH(PGM_K_ROUTE_PROBE, "route_filter_kernel", pgm::route_filter_kernel<<<grid, PGM_ROUTE_THREADS, 0, ctx->stream>>>(fp));
+        }
         pgm::RouteProbeParams pp;
         memset(&pp, 0, sizeof pp);
-        pp.src = ctx->rt_win_recv_().as<uint32_t>() + off * 3;
+        pp.src = fp.live;
         pp.n = in_counts[s];
+        pp.n_ptr = fp.n_live;
         pp.pos_base = b;
         pp.tab = table_view(ctx);
         pp.part_bits = ctx->part_bits; pp.world = (uint32_t)rt.world;
@@ -1553,9 +1571,11 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
         pp.q.entries = ctx->rt_cand_send_().as<uint32_t>(); pp.q.count = route_counts(ctx, PGM_ROUTE_CANDIDATES);
         pp.q.overflow = route_overflow(ctx, PGM_ROUTE_CANDIDATES); pp.q.cap = ctx->route.cap_cand; pp.q.world = (uint32_t)rt.world;
         pp.counters = ctx->counters.as<unsigned long long>();
-        const uint64_t chunks = (pp.n + PGM_ROUTE_PROBE_CHUNK2 - 1) / PGM_ROUTE_PROBE_CHUNK2;
-        const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * PGM_ROUTE_PROBE_CTAS);
-        KLAUNCH(PGM_K_ROUTE_PROBE, "route_probe_kernel", pgm::route_probe_kernel<<<grid, PGM_ROUTE_THREADS, 0, ctx->stream>>>(pp));
+        {   // (the survivors' number is only known on the device: size the grid for a third of the segment, the kernel strides)
+            const uint64_t chunks = (pp.n / 3 + PGM_ROUTE_PROBE_CHUNK2) / PGM_ROUTE_PROBE_CHUNK2;
+            const unsigned int grid = (unsigned int)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * PGM_ROUTE_PROBE_CTAS);
+            KLAUNCH(PGM_K_ROUTE_PROBE, "route_probe_kernel", pgm::route_probe_kernel<<<grid, PGM_ROUTE_THREADS, 0, ctx->stream>>>(pp));
+        }
         off += in_counts[s];
     }
     if (persist && (rc = filter_window(ctx, false, true))) return rc;

@@ -26,7 +26,7 @@
 #define PGM_ROUTE_MAX_WORLD 16
 #define PGM_ROUTE_THREADS 256
 #define PGM_ROUTE_PROBE_STAGE 1024          // candidates of one chunk staged in shared memory (about 120 expected; hot keys overflow to the slow path)
-#define PGM_ROUTE_PROBE_CTAS 6               // resident CTAs per SM: the chunk phases (load, filter, probe, flush) are latency-bound, other CTAs fill the gaps
+#define PGM_ROUTE_PROBE_CTAS 8               // resident CTAs per SM: a chunk is one DRAM latency (the probe) + a flush; other CTAs fill the gaps
 
 namespace pgm {
 
@@ -168,8 +168,9 @@ __global__ void __launch_bounds__(PGM_ROUTE_THREADS, 4) route_scan_kernel(const 
 
 // ------------------------------------------------------------------------------------------ pass: probe
 struct RouteProbeParams {
-    const uint32_t *src;            // received window entries of ONE sender, 3 words each
-    uint64_t n;
+    const uint32_t *src;            // windows of ONE sender that passed the filter (route_filter_kernel), 3 words each
+    uint64_t n;                     // their number, or
+    const unsigned int *n_ptr;      // ... where the filter kernel counted them (device memory)
     uint64_t pos_base;              // pass coordinate of the sender's position 0
     TableView tab;
     uint32_t part_bits;
@@ -186,30 +187,96 @@ __device__ __forceinline__ uint32_t route_owner(const RouteProbeParams &p, uint3
     return d;
 }
 
-// A CTA takes chunks of 1024 received windows.  Phase 0: the chunk's words land in shared memory with coalesced loads.
-// Phase 1, all threads: four entries per thread, four filter gathers in flight, the survivors (a fifth of the windows
-// once the table is spread over 8 GPUs) ballot-compacted into an index list.  Phase 2: the threads pull survivors from
-// the list and probe the table (one 256-bit load per bucket), walk hot-key chains here (next[] belongs to the table
-// owner) and stage the candidates in shared memory with their rank per read owner; one global reservation per owner and
-// chunk.  Candidates beyond the stage (hot keys) take the slow path: one global atomic each.
-#define PGM_ROUTE_PROBE_PER_THREAD 4
-#define PGM_ROUTE_PROBE_CHUNK2 (PGM_ROUTE_THREADS * PGM_ROUTE_PROBE_PER_THREAD)
+// The probe of the received windows is two kernels with one kind of latency each (a single kernel with a load, a filter,
+// a probe and a flush phase per chunk spent most of its time at barriers: 38 ms per step at the per-rank sizes of an 8-GPU
+// config-5 run, and the same 38-44 ms whether 0.45 G or 1.2 G windows went on to the table):
+//   route_filter_kernel  streams the received windows (12 bytes each, coalesced into shared memory), four L2-resident filter
+//                        gathers in flight per thread, and writes the survivors — a fifth to a quarter of the windows once
+//                        the table is spread over 8 GPUs — compacted into a scratch array (one global reservation per chunk);
+//   route_probe_kernel   one survivor per thread: one 256-bit load per probed bucket, hot-key chains walked here (next[]
+//                        belongs to the table owner), candidates staged in shared memory with their rank per read owner,
+//                        one global reservation per owner and chunk (beyond the stage: one global atomic each).
+#define PGM_ROUTE_FILTER_PER_THREAD 4
+#define PGM_ROUTE_FILTER_CHUNK (PGM_ROUTE_THREADS * PGM_ROUTE_FILTER_PER_THREAD)
+struct RouteFilterParams {
+    const uint32_t *src;            // received window entries of ONE sender, 3 words each
+    uint64_t n;
+    TableView tab;
+    uint32_t *live;                 // survivors, 3 words each (capacity n)
+    unsigned int *n_live;           // their number (device counter, zeroed by the host)
+};
+
+__global__ void __launch_bounds__(PGM_ROUTE_THREADS, 8) route_filter_kernel(const __grid_constant__ RouteFilterParams p) {
+    __shared__ uint32_t s_in[3 * PGM_ROUTE_FILTER_CHUNK];
+    __shared__ uint16_t s_idx[PGM_ROUTE_FILTER_CHUNK];
+    __shared__ unsigned int s_nlive, s_base;
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    if (t == 0) s_nlive = 0;
+    __syncthreads();
+    const uint64_t n_chunks = (p.n + PGM_ROUTE_FILTER_CHUNK - 1) / PGM_ROUTE_FILTER_CHUNK;
+    const uint64_t pol_keep = policy_evict_last();
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const uint64_t e0 = c * PGM_ROUTE_FILTER_CHUNK;
+        const uint32_t n_here = (uint32_t)min((uint64_t)PGM_ROUTE_FILTER_CHUNK, p.n - e0);
+        for (uint32_t k = t; k < 3 * n_here; k += PGM_ROUTE_THREADS) s_in[k] = __ldcs(p.src + 3 * e0 + k);
+        __syncthreads();
+        uint32_t fw[PGM_ROUTE_FILTER_PER_THREAD], fm[PGM_ROUTE_FILTER_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < PGM_ROUTE_FILTER_PER_THREAD; k++) {
+            const uint32_t i = t + k * PGM_ROUTE_THREADS;
+            fw[k] = 0xFFFFFFFFu; fm[k] = 0;
+            if (i < n_here) {
+                const uint32_t f = route_filter_hash(s_in[3 * i], s_in[3 * i + 1]);
+                fm[k] = filter_bits(f, p.tab.filter_k);
+                if (p.tab.filter) fw[k] = ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep);
+            }
+        }
+        uint32_t bal[PGM_ROUTE_FILTER_PER_THREAD], tot = 0;
+#pragma unroll
+        for (int k = 0; k < PGM_ROUTE_FILTER_PER_THREAD; k++) {
+            bal[k] = __ballot_sync(PGM_FULL, t + k * PGM_ROUTE_THREADS < n_here && (fw[k] & fm[k]) == fm[k]);
+            tot += __popc(bal[k]);
+        }
+        if (tot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_nlive, tot);
+            base = __shfl_sync(PGM_FULL, base, 0);
+#pragma unroll
+            for (int k = 0; k < PGM_ROUTE_FILTER_PER_THREAD; k++) {
+                if ((bal[k] >> lane) & 1u) s_idx[base + __popc(bal[k] & lt_mask)] = (uint16_t)(t + k * PGM_ROUTE_THREADS);
+                base += __popc(bal[k]);
+            }
+        }
+        __syncthreads();
+        const uint32_t n_live = s_nlive;
+        if (t == 0) s_base = n_live ? atomicAdd(p.n_live, n_live) : 0u;
+        __syncthreads();
+        if (t == 0) s_nlive = 0;
+        uint32_t *out = p.live + 3 * (size_t)s_base;
+        for (uint32_t k = t; k < 3 * n_live; k += PGM_ROUTE_THREADS) {
+            const uint32_t i = k / 3u, w = k - 3u * i;
+            out[k] = s_in[3 * s_idx[i] + w];
+        }
+        __syncthreads();
+    }
+}
+
+#define PGM_ROUTE_PROBE_CHUNK2 (PGM_ROUTE_THREADS * 2)
 __global__ void __launch_bounds__(PGM_ROUTE_THREADS, PGM_ROUTE_PROBE_CTAS) route_probe_kernel(const __grid_constant__ RouteProbeParams p) {
     __shared__ uint32_t s_pos[PGM_ROUTE_PROBE_STAGE], s_pat[PGM_ROUTE_PROBE_STAGE];
     __shared__ uint16_t s_rank[PGM_ROUTE_PROBE_STAGE];
     __shared__ uint8_t s_dest[PGM_ROUTE_PROBE_STAGE];
-    __shared__ uint32_t s_in[3 * PGM_ROUTE_PROBE_CHUNK2];                    // the chunk: {h1', h2, rel} per entry
-    __shared__ uint16_t s_idx[PGM_ROUTE_PROBE_CHUNK2];                       // entries that passed the filter
     __shared__ unsigned int s_cnt[PGM_ROUTE_MAX_WORLD], s_base[PGM_ROUTE_MAX_WORLD];
-    __shared__ unsigned int s_n, s_nlive;
-    const uint32_t t = threadIdx.x, lane = t & 31u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    __shared__ unsigned int s_n;
+    const uint32_t t = threadIdx.x;
     if (t < PGM_ROUTE_MAX_WORLD) s_cnt[t] = 0;
-    if (t == 0) { s_n = 0; s_nlive = 0; }
+    if (t == 0) s_n = 0;
     __syncthreads();
     bool over = false;
-    const uint64_t n_chunks = (p.n + PGM_ROUTE_PROBE_CHUNK2 - 1) / PGM_ROUTE_PROBE_CHUNK2;
-    const uint64_t pol_keep = policy_evict_last();
+    const uint64_t pol_stream = policy_evict_first();      // bucket lines are one-shot traffic: keep them from evicting the filter
+    const uint64_t n = p.n_ptr ? (uint64_t)*p.n_ptr : p.n;
+    const uint64_t n_chunks = (n + PGM_ROUTE_PROBE_CHUNK2 - 1) / PGM_ROUTE_PROBE_CHUNK2;
     auto emit_slow = [&](uint32_t rel, uint32_t pat) {
         const uint64_t gpos = p.pos_base + rel;
         const uint32_t dest = route_owner(p, pat >> p.part_bits);
@@ -228,50 +295,14 @@ __global__ void __launch_bounds__(PGM_ROUTE_THREADS, PGM_ROUTE_PROBE_CTAS) route
         } else emit_slow(rel, pat);
     };
     for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        // ---- phase 0: the chunk -> shared memory
-        const uint64_t e0 = c * PGM_ROUTE_PROBE_CHUNK2;
-        const uint32_t n_here = (uint32_t)min((uint64_t)PGM_ROUTE_PROBE_CHUNK2, p.n - e0);
-        for (uint32_t k = t; k < 3 * n_here; k += PGM_ROUTE_THREADS) s_in[k] = __ldcs(p.src + 3 * e0 + k);
-        __syncthreads();
-        // ---- phase 1: filter
-        uint32_t fw[PGM_ROUTE_PROBE_PER_THREAD], fm[PGM_ROUTE_PROBE_PER_THREAD];
-#pragma unroll
-        for (int k = 0; k < PGM_ROUTE_PROBE_PER_THREAD; k++) {
-            const uint32_t i = t + k * PGM_ROUTE_THREADS;
-            fw[k] = 0xFFFFFFFFu; fm[k] = 0;
-            if (i < n_here) {
-                const uint32_t f = route_filter_hash(s_in[3 * i], s_in[3 * i + 1]);
-                fm[k] = filter_bits(f, p.tab.filter_k);
-                if (p.tab.filter) fw[k] = ld_u32_hint(p.tab.filter + (f & p.tab.filter_mask), pol_keep);
-            }
-        }
-        uint32_t bal[PGM_ROUTE_PROBE_PER_THREAD], tot = 0;
-#pragma unroll
-        for (int k = 0; k < PGM_ROUTE_PROBE_PER_THREAD; k++) {
-            bal[k] = __ballot_sync(PGM_FULL, t + k * PGM_ROUTE_THREADS < n_here && (fw[k] & fm[k]) == fm[k]);
-            tot += __popc(bal[k]);
-        }
-        if (tot) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&s_nlive, tot);
-            base = __shfl_sync(PGM_FULL, base, 0);
-#pragma unroll
-            for (int k = 0; k < PGM_ROUTE_PROBE_PER_THREAD; k++) {
-                if ((bal[k] >> lane) & 1u) s_idx[base + __popc(bal[k] & lt_mask)] = (uint16_t)(t + k * PGM_ROUTE_THREADS);
-                base += __popc(bal[k]);
-            }
-        }
-        __syncthreads();
-        // ---- phase 2: table probes of the survivors
-        const uint32_t n_live = s_nlive;
-        for (uint32_t i = t; i < n_live; i += PGM_ROUTE_THREADS) {
-            const uint32_t at = s_idx[i];
-            const uint32_t h1p = s_in[3 * at], h2 = s_in[3 * at + 1], rel = s_in[3 * at + 2];
+        const uint64_t first = c * PGM_ROUTE_PROBE_CHUNK2, last = min(first + PGM_ROUTE_PROBE_CHUNK2, n);
+        for (uint64_t i = first + t; i < last; i += PGM_ROUTE_THREADS) {
+            const uint32_t h1p = __ldcs(p.src + 3 * i), h2 = __ldcs(p.src + 3 * i + 1), rel = __ldcs(p.src + 3 * i + 2);
             const uint32_t tag = seed_tag(h2);
             uint32_t b = __umulhi(h1p, p.tab.n_buckets);
             const uint32_t step = 1u + __umulhi(h2 * 0x9E3779B1u, p.tab.n_buckets - 1u);
             for (;;) {
-                const u32x8 sl = ld256_stream(p.tab.buckets + b);
+                const u32x8 sl = ld256_stream_hint(p.tab.buckets + b, pol_stream);
                 bool em = false;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -295,9 +326,8 @@ __global__ void __launch_bounds__(PGM_ROUTE_THREADS, PGM_ROUTE_PROBE_CTAS) route
             s_base[t] = cc ? atomicAdd(p.q.count + t, cc) : 0u;
             s_cnt[t] = 0;
         }
-        if (t == 0 && n_live) atomicAdd(p.counters + 3, (unsigned long long)n_live);
         __syncthreads();
-        if (t == 0) { s_n = 0; s_nlive = 0; }
+        if (t == 0) s_n = 0;
         for (uint32_t i = t; i < staged; i += PGM_ROUTE_THREADS) {
             const uint32_t dest = s_dest[i], idx = s_base[dest] + s_rank[i];
             if (idx < p.q.cap) {
@@ -309,6 +339,7 @@ __global__ void __launch_bounds__(PGM_ROUTE_THREADS, PGM_ROUTE_PROBE_CTAS) route
         __syncthreads();
     }
     if (over) *p.q.overflow = 1u;
+    if (blockIdx.x == 0 && t == 0 && p.n_ptr) atomicAdd(p.counters + 3, (unsigned long long)n);   // windows that passed the filter
 }
 
 // ------------------------------------------------------------------------------------------ pass: verify
