@@ -1487,7 +1487,7 @@ int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer 
     ctx->route.cap_win = route_cap(rt.round_windows, rt.world);
     if ((rc = ensure(ctx, ctx->rt_win_send_(), (size_t)ctx->route.cap_win * rt.world * 12))) return rc;
     CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_WINDOWS), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
-    if (e > b && ctx->n_buckets) {
+    if (e > b) {                                   // (reads the text only: may run before the table of this phase exists)
         pgm::RouteScanParams sp;
         memset(&sp, 0, sizeof sp);
         sp.tlo = (rev_mode ? ctx->r_lo : ctx->f_lo).as<uint32_t>() + PGM_PAD_WORDS;

@@ -380,6 +380,16 @@ __global__ void __launch_bounds__(PGM_VERIFY_THREADS) route_verify_kernel(const 
             for (int w = 0; w < 8; w++) { xA.v[w] = 0; xB.v[w] = 0; }
             if (onA) xA = ld256_cg(reinterpret_cast<const u32x8 *>(p.reads.lq) + (size_t)rA * 2 + half);
             if (onB) xB = ld256_cg(reinterpret_cast<const u32x8 *>(p.reads.lq) + (size_t)rB * 2 + half);
+            // the text window's address is known from the candidate alone: its loads go out BEFORE the shuffles below wait
+            // for the record (a warp issues in order: behind the shuffles they would cost a second DRAM latency)
+            const int64_t lbit = (int64_t)gpos - (int64_t)(cj * p.seed_len);
+            uint32_t yl[7], yh[7];
+#pragma unroll
+            for (int w = 0; w < 7; w++) { yl[w] = 0; yh[w] = 0; }
+            if (fast) {
+                gather7(p.tlo, lbit >> 5, yl);
+                gather7(p.thi, lbit >> 5, yh);
+            }
             uint32_t s0[8], s1[8];
 #pragma unroll
             for (int w = 0; w < 8; w++) {
@@ -389,12 +399,8 @@ __global__ void __launch_bounds__(PGM_VERIFY_THREADS) route_verify_kernel(const 
             }
             if (fast) {
                 n_cand++;
-                const int64_t lbit = (int64_t)gpos - (int64_t)(cj * p.seed_len);
                 const uint32_t ts = (uint32_t)(lbit & 31);
                 const uint32_t L = p.reads.read_len;
-                uint32_t yl[7], yh[7];
-                gather7(p.tlo, lbit >> 5, yl);
-                gather7(p.thi, lbit >> 5, yh);
                 int c = 0;
 #pragma unroll
                 for (int g = 0; g < 6; g++) {

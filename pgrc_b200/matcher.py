@@ -587,16 +587,22 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
     small = comm2 if comm2 is not None else comm          # counts and candidates
 
     def emit(rev, rnd):
-        m.route_slot(rnd & 1)
+        return emit_slot(rev, rnd, rnd & 1)
+
+    def consume(rev, rnd, win_in, pending):
+        consume_slot(rev, rnd, rnd & 1, win_in, pending)
+
+    def emit_slot(rev, rnd, slot):
+        m.route_slot(slot)
         counts, segs, eb = m.route_scan(rev, rnd)
         sent["windows"] += sum(counts) * eb
         win_in = small.exchange_counts(counts, dev)
         recv = m.route_recv(PGM_ROUTE_WINDOWS, win_in, eb)
         return win_in, comm.all_to_all_async(recv, segs)
 
-    def consume(rev, rnd, win_in, pending):
+    def consume_slot(rev, rnd, slot, win_in, pending):
         pending.wait()
-        m.route_slot(rnd & 1)
+        m.route_slot(slot)
         counts, segs, eb = m.route_probe(rev, rnd, win_in)
         sent["candidates"] += sum(counts) * eb
         cand_in = small.exchange_counts(counts, dev)
@@ -605,6 +611,7 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
         m.route_verify(rev, sum(cand_in))
 
     rounds = 1
+    passes = (False, True) if rev_compl_pg else (False,)
     for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:
         if ilv:
             raise PgmError(-6, "the routed scheme covers matching modes 'd'/'D' (contiguous seeds); use read ranges for 'i' and 'c'")
@@ -613,20 +620,30 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
         sent["patterns"] += sum(counts) * eb
         pat_in = small.exchange_counts(counts, dev)
         recv = m.route_recv(PGM_ROUTE_PATTERNS, pat_in, eb)
-        comm.all_to_all(recv, segs)
-        m.route_build(sum(pat_in))
+        pat_pending = comm.all_to_all_async(recv, segs)
         rounds = m.route_rounds()
-        for rev in ((False, True) if rev_compl_pg else (False,)):
-            if comm2 is None:
+        if comm2 is None:
+            pat_pending.wait()
+            m.route_build(sum(pat_in))
+            for rev in passes:
                 for rnd in range(rounds):
                     consume(rev, rnd, *emit(rev, rnd))
-            else:
-                cur = emit(rev, 0)
-                for rnd in range(rounds):
-                    nxt = emit(rev, rnd + 1) if rnd + 1 < rounds else None
-                    consume(rev, rnd, *cur)
-                    cur = nxt
-            m.resolve_pass(rev)
+                m.resolve_pass(rev)
+            continue
+        # pipelined: the (pass, round) pairs form one sequence; the windows of step k + 1 are hashed and shipped while step k is
+        # probed and verified — across the pass boundary too (hashing and probing the RC text need no forward result; the
+        # verification does: the forward decision is applied before the first RC round is consumed), and the first emit runs
+        # while the patterns travel and the table is built (the scan only reads the text)
+        seq = [(rev, rnd) for rev in passes for rnd in range(rounds)]
+        cur = emit_slot(*seq[0], 0)
+        pat_pending.wait()
+        m.route_build(sum(pat_in))
+        for k, (rev, rnd) in enumerate(seq):
+            nxt = emit_slot(*seq[k + 1], (k + 1) & 1) if k + 1 < len(seq) else None
+            consume_slot(rev, rnd, k & 1, *cur)
+            if rnd == rounds - 1:
+                m.resolve_pass(rev)
+            cur = nxt
     m.route_slot(0)
     return {"sent_bytes": sent, "rounds_per_pass": rounds, "pipelined": comm2 is not None}
 
