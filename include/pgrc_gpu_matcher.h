@@ -229,6 +229,24 @@ int pgm_route_rounds(pgm_ctx *ctx, uint32_t *rounds);
 int pgm_route_slot(pgm_ctx *ctx, int slot);
 int pgm_route_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t max_mm, uint32_t min_mm,
                     int continuation, pgm_route_buffer *send);
+/* The exchange as peer-to-peer copies (copy engines over NVLink, no SM time): after an emit step (pgm_route_begin / _scan /
+ * _probe) a rank publishes where its send buffer of that kind lives (pgm_route_export: a CUDA IPC handle for other
+ * processes, the pointer itself for contexts of the same process); once every rank's pgm_route_buffer (counts) and
+ * pgm_route_peer are known, pgm_route_pull copies this rank's segment of every peer's send buffer into the receive buffer
+ * of the current slot, asynchronously on the context's pull stream — the consuming call (pgm_route_build / _probe /
+ * _verify) waits for it on the device.  The caller guarantees what any all-to-all needs: a pull starts after every
+ * sender's emit step has completed (exchanging the counts implies it: they are read after a stream synchronize), and a
+ * sender re-emits into a send buffer only after every receiver has consumed the previous contents (two slots + the count
+ * exchanges of the following steps give that order in matcher.run_plan_routed). */
+typedef struct pgm_route_peer {
+    uint64_t pid;                /* process that owns the buffer */
+    void *ptr;                   /* its address there */
+    int32_t device;
+    int32_t reserved;
+    unsigned char ipc_handle[64];
+} pgm_route_peer;
+int pgm_route_export(pgm_ctx *ctx, int kind, pgm_route_peer *out);
+int pgm_route_pull(pgm_ctx *ctx, int kind, const pgm_route_peer *peers /*[world]*/, const pgm_route_buffer *peer_sends /*[world]*/);
 /* Device buffer for `n_entries` incoming entries of `kind` (PGM_ROUTE_*). */
 int pgm_route_recv(pgm_ctx *ctx, int kind, uint64_t n_entries, void **ptr);
 int pgm_route_build(pgm_ctx *ctx, uint64_t n_patterns_in);

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -121,6 +122,12 @@ struct pgm_ctx {
     } route;
     // two sets of exchange buffers: the windows of round r + 1 can be emitted and travel while round r is probed and verified
     DevBuf rt_win_send2[2], rt_win_recv2[2], rt_cand_send2[2], rt_cand_recv2[2], rt_pat_recv, rt_counters, rt_live, rt_live_count;
+    // exchange by peer copies (pgm_route_export / pgm_route_pull): copies run on their own stream, one "arrived" event per
+    // kind and slot; peer buffers opened through CUDA IPC are cached by handle
+    cudaStream_t pull_stream = nullptr;
+    cudaEvent_t pull_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    bool pull_pending[3][2] = {{false, false}, {false, false}, {false, false}};
+    std::vector<std::pair<std::string, void *>> ipc_open;
     DevBuf &rt_win_send_() { return rt_win_send2[route.slot]; }
     DevBuf &rt_win_recv_() { return rt_win_recv2[route.slot]; }
     DevBuf &rt_cand_send_() { return rt_cand_send2[route.slot]; }
@@ -580,6 +587,9 @@ void pgm_destroy(pgm_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_free) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->text_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->reads_ev) cudaEventDestroy(e);
+    for (auto &kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
+    for (int k = 0; k < 3; k++) for (int sl = 0; sl < 2; sl++) if (ctx->pull_ev[k][sl]) cudaEventDestroy(ctx->pull_ev[k][sl]);
+    if (ctx->pull_stream) { cudaStreamSynchronize(ctx->pull_stream); cudaStreamDestroy(ctx->pull_stream); }
     if (ctx->fence_ev) cudaEventDestroy(ctx->fence_ev);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1436,11 +1446,88 @@ int pgm_route_recv(pgm_ctx *ctx, int kind, uint64_t n_entries, void **ptr) {
     return PGM_OK;
 }
 
+} // extern "C"
+
+namespace {
+// orders the context's stream behind a pending peer pull of (kind, current slot)
+int route_wait_pull(pgm_ctx *ctx, int kind) {
+    const int sl = kind == PGM_ROUTE_PATTERNS ? 0 : ctx->route.slot;
+    if (ctx->pull_pending[kind][sl]) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->pull_ev[kind][sl], 0));
+        ctx->pull_pending[kind][sl] = false;
+    }
+    return PGM_OK;
+}
+} // namespace
+
+extern "C" {
+
+int pgm_route_export(pgm_ctx *ctx, int kind, pgm_route_peer *out) {
+    if (!ctx || !out || kind < 0 || kind > 2) return PGM_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf &b = kind == PGM_ROUTE_PATTERNS ? ctx->bq_entries : kind == PGM_ROUTE_WINDOWS ? ctx->rt_win_send_() : ctx->rt_cand_send_();
+    memset(out, 0, sizeof *out);
+    if (!b.p) return fail(ctx, PGM_ERR_STATE, "pgm_route_export: nothing has been emitted for this kind yet");
+    out->pid = (uint64_t)getpid();
+    out->device = ctx->device;
+    out->ptr = b.p;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, b.p));
+    static_assert(sizeof h == sizeof out->ipc_handle, "CUDA IPC handle size");
+    memcpy(out->ipc_handle, &h, sizeof h);
+    return PGM_OK;
+}
+
+int pgm_route_pull(pgm_ctx *ctx, int kind, const pgm_route_peer *peers, const pgm_route_buffer *peer_sends) {
+    if (!ctx || !peers || !peer_sends || kind < 0 || kind > 2) return PGM_ERR_INVALID_ARG;
+    const pgm_ctx::Route &rt = ctx->route;
+    if (!rt.world) return fail(ctx, PGM_ERR_STATE, "pgm_route_pull: pgm_route_config has not been called");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->pull_stream) CU(cudaStreamCreateWithFlags(&ctx->pull_stream, cudaStreamNonBlocking));
+    const int sl = kind == PGM_ROUTE_PATTERNS ? 0 : rt.slot;
+    if (!ctx->pull_ev[kind][sl]) CU(cudaEventCreateWithFlags(&ctx->pull_ev[kind][sl], cudaEventDisableTiming));
+    uint64_t total = 0;
+    for (int s = 0; s < rt.world; s++) total += peer_sends[s].count[rt.rank];
+    void *dst = nullptr;
+    int rc;
+    if ((rc = pgm_route_recv(ctx, kind, total, &dst))) return rc;
+    // the copies may start once everything queued on the context's stream so far (the previous reader of this receive buffer) is done
+    CU(cudaEventRecord(ctx->fence_ev, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->pull_stream, ctx->fence_ev, 0));
+    for (int k = 0; k < rt.world; k++) {
+        const int s = (rt.rank + k) % rt.world;                    // own segment first, then round-robin over the peers
+        uint64_t off = 0;
+        for (int q = 0; q < s; q++) off += peer_sends[q].count[rt.rank] * peer_sends[q].entry_bytes;
+        const uint64_t bytes = peer_sends[s].count[rt.rank] * peer_sends[s].entry_bytes;
+        if (!bytes) continue;
+        const char *base = nullptr;
+        if (peers[s].pid == (uint64_t)getpid()) base = static_cast<const char *>(peers[s].ptr);      // same process: the pointer itself
+        else {
+            const std::string key(reinterpret_cast<const char *>(peers[s].ipc_handle), sizeof peers[s].ipc_handle);
+            for (auto &kv : ctx->ipc_open) if (kv.first == key) base = static_cast<const char *>(kv.second);
+            if (!base) {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, peers[s].ipc_handle, sizeof h);
+                void *mapped = nullptr;
+                CU(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+                ctx->ipc_open.emplace_back(key, mapped);
+                base = static_cast<const char *>(mapped);
+            }
+        }
+        const char *src = base + (uint64_t)rt.rank * peer_sends[s].stride_bytes;
+        CU(cudaMemcpyAsync(static_cast<char *>(dst) + off, src, bytes, cudaMemcpyDefault, ctx->pull_stream));
+    }
+    CU(cudaEventRecord(ctx->pull_ev[kind][sl], ctx->pull_stream));
+    ctx->pull_pending[kind][sl] = true;
+    return PGM_OK;
+}
+
 int pgm_route_build(pgm_ctx *ctx, uint64_t n_in) {
     if (!ctx) return PGM_ERR_INVALID_ARG;
     if (!ctx->route.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_build: pgm_route_begin has not been called");
     if (n_in && ctx->rt_pat_recv.cap < n_in * 16) return fail(ctx, PGM_ERR_STATE, "pgm_route_build: the patterns have not been received (pgm_route_recv)");
     CU(cudaSetDevice(ctx->device));
+    { int wrc = route_wait_pull(ctx, PGM_ROUTE_PATTERNS); if (wrc) return wrc; }
     const pgm_ctx::Route &rt = ctx->route;
     // table geometry for the patterns that actually arrived (hash skew included)
     const uint64_t want_slots = std::max<uint64_t>(512, n_in * (uint64_t)ctx->slots_per_pattern);
@@ -1524,11 +1611,13 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
     if (!rt.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: pgm_route_begin has not been called");
     (void)rev_mode;
     CU(cudaSetDevice(ctx->device));
+    { int wrc = route_wait_pull(ctx, PGM_ROUTE_WINDOWS); if (wrc) return wrc; }
     uint64_t n_in = 0;
     for (int s = 0; s < rt.world; s++) n_in += in_counts[s];
     if (n_in && ctx->rt_win_recv_().cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: the windows have not been received (pgm_route_recv)");
     // on average well under one candidate per window; hot keys are covered by the slack
-    ctx->route.cap_cand = (uint32_t)std::min<uint64_t>(n_in / rt.world + (4u << 20), 0xFFFFFFF0ull);
+    // (a fixed capacity: the buffer, hence its address — peers may hold it open over IPC — never changes between rounds)
+    ctx->route.cap_cand = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(n_in, rt.round_windows) / rt.world + (4u << 20), 0xFFFFFFF0ull);
     int rc;
     if ((rc = ensure(ctx, ctx->rt_cand_send_(), (size_t)ctx->route.cap_cand * rt.world * 12))) return rc;
     CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_CANDIDATES), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
@@ -1588,6 +1677,7 @@ int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_in) {
     if (!rt.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_verify: pgm_route_begin has not been called");
     if (n_in && ctx->rt_cand_recv_().cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_verify: the candidates have not been received (pgm_route_recv)");
     CU(cudaSetDevice(ctx->device));
+    { int wrc = route_wait_pull(ctx, PGM_ROUTE_CANDIDATES); if (wrc) return wrc; }
     if (!n_in || !ctx->n_reads()) return PGM_OK;
     pgm::RouteVerifyParams vp;
     memset(&vp, 0, sizeof vp);

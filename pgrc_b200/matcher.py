@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (KERNEL_NAMES, PGM_DISABLED_PREFIX_MODE, PGM_ROUTE_CANDIDATES, PGM_ROUTE_PATTERNS, PGM_ROUTE_WINDOWS, PgmAccumulators,
-                   PgmError, PgmRouteBuffer, PgmStats, PgmTimings)
+                   PgmError, PgmRouteBuffer, PgmRoutePeer, PgmStats, PgmTimings)
 
 NOT_MATCHED_POSITION = np.uint64(0xFFFFFFFFFFFFFFFF)   # DefaultReadsMatcher::NOT_MATCHED_POSITION
 NOT_MATCHED_COUNT = 255                                 # PgTools::NOT_MATCHED_COUNT
@@ -203,7 +203,7 @@ class GpuReadsMatcher:
     def route_config(self, rank: int, world: int, read_begin, round_windows: int = 0):
         arr = (ctypes.c_uint64 * (world + 1))(*[int(x) for x in read_begin])
         self._check(self._lib.pgm_route_config(self._h, rank, world, arr, round_windows))
-        self._route_world = world
+        self._route_world, self._route_rank = world, rank
 
     def route_slot(self, slot: int):
         self._check(self._lib.pgm_route_slot(self._h, slot))
@@ -216,7 +216,7 @@ class GpuReadsMatcher:
     def route_begin(self, seed_len, parts, max_mm, min_mm, continuation=False):
         buf = PgmRouteBuffer()
         self._check(self._lib.pgm_route_begin(self._h, seed_len, parts, max_mm, min_mm, int(continuation), ctypes.byref(buf)))
-        return [int(buf.count[d]) for d in range(buf.world)], self._segments(buf), buf.entry_bytes
+        return _Emit(self, buf)
 
     def route_recv(self, kind: int, in_counts, entry_bytes: int):
         """Receive buffer for the given per-sender counts: list of uint8 views, one per sender (None where empty)."""
@@ -238,13 +238,29 @@ class GpuReadsMatcher:
     def route_scan(self, rev_mode: bool, rnd: int):
         buf = PgmRouteBuffer()
         self._check(self._lib.pgm_route_scan(self._h, int(rev_mode), rnd, ctypes.byref(buf)))
-        return [int(buf.count[d]) for d in range(buf.world)], self._segments(buf), buf.entry_bytes
+        return _Emit(self, buf)
 
     def route_probe(self, rev_mode: bool, rnd: int, in_counts):
         buf = PgmRouteBuffer()
         arr = (ctypes.c_uint64 * len(in_counts))(*[int(x) for x in in_counts])
         self._check(self._lib.pgm_route_probe(self._h, int(rev_mode), rnd, arr, ctypes.byref(buf)))
-        return [int(buf.count[d]) for d in range(buf.world)], self._segments(buf), buf.entry_bytes
+        return _Emit(self, buf)
+
+    def route_export(self, kind: int, buf: PgmRouteBuffer) -> bytes:
+        """What the peers need to pull their segments of this rank's send buffer: the buffer descriptor (counts, stride)
+        and where it lives (pgm_route_export), as one blob for an all-gather."""
+        peer = PgmRoutePeer()
+        self._check(self._lib.pgm_route_export(self._h, kind, ctypes.byref(peer)))
+        return bytes(buf) + bytes(peer)
+
+    def route_pull(self, kind: int, blobs) -> list:
+        """Starts the copies of this rank's segments out of every peer's send buffer (pgm_route_pull; asynchronous: the
+        consuming call waits on the device).  blobs[s] = route_export of rank s.  Returns the entries received per sender."""
+        n, nb = len(blobs), ctypes.sizeof(PgmRouteBuffer)
+        sends = (PgmRouteBuffer * n)(*[PgmRouteBuffer.from_buffer_copy(b[:nb]) for b in blobs])
+        peers = (PgmRoutePeer * n)(*[PgmRoutePeer.from_buffer_copy(b[nb:]) for b in blobs])
+        self._check(self._lib.pgm_route_pull(self._h, kind, peers, sends))
+        return [int(sends[s].count[self._route_rank]) for s in range(n)]
 
     def route_verify(self, rev_mode: bool, n_in: int):
         self._check(self._lib.pgm_route_verify(self._h, int(rev_mode), n_in))
@@ -473,6 +489,23 @@ def all_gather_text(share_host, pg_len: int, rank: int, world: int, device, bufs
     return full[:pg_len]
 
 
+class _Emit:
+    """Result of an emit step (route_begin / route_scan / route_probe): the send buffer's descriptor."""
+
+    def __init__(self, m, buf):
+        self.m, self.buf, self.eb = m, buf, buf.entry_bytes
+        self.counts = [int(buf.count[d]) for d in range(buf.world)]
+
+    @property
+    def segs(self):
+        return self.m._segments(self.buf)
+
+
+class _Arrived:
+    def wait(self):
+        pass
+
+
 class TorchComm:
     """The collectives the sharded schemes need, over torch.distributed (NCCL across GPUs: NVLink / NVSwitch; gloo in the
     CPU tests).  Tests substitute an object with the same methods that connects several contexts inside one process."""
@@ -496,6 +529,16 @@ class TorchComm:
         allc = torch.empty(self.world * self.world, dtype=torch.int64, device=device)
         dist.all_gather_into_tensor(allc, mine, group=self.group)
         return allc.view(self.world, self.world)[:, self.rank].tolist()
+
+    def all_gather_bytes(self, blob: bytes, device):
+        """Every rank's blob (equal sizes), in rank order."""
+        import torch
+        import torch.distributed as dist
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+        allb = torch.empty(self.world * len(blob), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allb, mine, group=self.group)
+        raw = allb.cpu().numpy().tobytes()
+        return [raw[r * len(blob):(r + 1) * len(blob)] for r in range(self.world)]
 
     def all_to_all_async(self, recv, send):
         """send[d] -> rank d, recv[s] <- rank s (uint8 tensors or None for empty segments): NCCL send/recv pairs on the
@@ -573,41 +616,42 @@ def read_ranges(n_reads: int, world: int):
     return [(n_reads * g) // world for g in range(world + 1)]
 
 
-def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total: int, round_windows: int = 0, comm2=None) -> dict:
+def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total: int, round_windows: int = 0, comm2=None,
+                    exchange: str = "nccl") -> dict:
     """The routed scheme (include/pgrc_gpu_matcher.h, pgm_route_*): this rank's context holds the whole text and its own
     read range (`read_ranges`).  Per phase the seeds are exchanged once (all-to-all by hash owner); per pass and round the
     windows of this rank's text range go to the hash owners and the candidates they find go to the read owners.
-    With a second communicator (`comm2`, e.g. comm.sibling()) the rounds are software-pipelined: the windows of round
-    r + 1 are emitted and travel (comm) while round r is probed, its candidates exchanged (comm2) and verified — the two
-    sets of exchange buffers of the context (pgm_route_slot) make that safe.  Returns the bytes this rank sent per kind."""
+    exchange = "nccl": NCCL send/recv pairs of the send segments; "pull": every rank publishes its send buffer (CUDA IPC) and
+    pulls its segments out of the peers' buffers with copy engines over NVLink (pgm_route_pull) — no SM time, and the copy
+    overlaps whatever kernels follow.  With a second communicator (`comm2`, e.g. comm.sibling(); used for the small
+    all-gathers of counts, so that they do not queue behind a transfer) the (pass, round) steps are software-pipelined: the
+    windows of step k + 1 are hashed and shipped while step k is probed and verified — the two sets of exchange buffers of the
+    context (pgm_route_slot) make that safe.  Returns the bytes this rank sent per kind."""
     comm = _as_comm(comm)
     dev = f"cuda:{m.device}" if isinstance(m.device, int) else m.device
     m.route_config(comm.rank, comm.world, read_ranges(n_reads_total, comm.world), round_windows)
     sent = {"patterns": 0, "windows": 0, "candidates": 0}
     small = comm2 if comm2 is not None else comm          # counts and candidates
+    names = {PGM_ROUTE_PATTERNS: "patterns", PGM_ROUTE_WINDOWS: "windows", PGM_ROUTE_CANDIDATES: "candidates"}
 
-    def emit(rev, rnd):
-        return emit_slot(rev, rnd, rnd & 1)
-
-    def consume(rev, rnd, win_in, pending):
-        consume_slot(rev, rnd, rnd & 1, win_in, pending)
+    def ship(kind, em, data_comm):
+        """Starts the all-to-all of an emit step; returns (entries received per sender, pending transfer)."""
+        sent[names[kind]] += sum(em.counts) * em.eb
+        if exchange == "pull":
+            return m.route_pull(kind, small.all_gather_bytes(m.route_export(kind, em.buf), dev)), _Arrived()
+        in_counts = small.exchange_counts(em.counts, dev)
+        recv = m.route_recv(kind, in_counts, em.eb)
+        return in_counts, data_comm.all_to_all_async(recv, em.segs)
 
     def emit_slot(rev, rnd, slot):
         m.route_slot(slot)
-        counts, segs, eb = m.route_scan(rev, rnd)
-        sent["windows"] += sum(counts) * eb
-        win_in = small.exchange_counts(counts, dev)
-        recv = m.route_recv(PGM_ROUTE_WINDOWS, win_in, eb)
-        return win_in, comm.all_to_all_async(recv, segs)
+        return ship(PGM_ROUTE_WINDOWS, m.route_scan(rev, rnd), comm)
 
     def consume_slot(rev, rnd, slot, win_in, pending):
         pending.wait()
         m.route_slot(slot)
-        counts, segs, eb = m.route_probe(rev, rnd, win_in)
-        sent["candidates"] += sum(counts) * eb
-        cand_in = small.exchange_counts(counts, dev)
-        recv = m.route_recv(PGM_ROUTE_CANDIDATES, cand_in, eb)
-        small.all_to_all(recv, segs)
+        cand_in, p2 = ship(PGM_ROUTE_CANDIDATES, m.route_probe(rev, rnd, win_in), small)
+        p2.wait()
         m.route_verify(rev, sum(cand_in))
 
     rounds = 1
@@ -616,25 +660,21 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
         if ilv:
             raise PgmError(-6, "the routed scheme covers matching modes 'd'/'D' (contiguous seeds); use read ranges for 'i' and 'c'")
         m.route_slot(0)
-        counts, segs, eb = m.route_begin(seed_len, parts, max_mm, min_mm, cont)
-        sent["patterns"] += sum(counts) * eb
-        pat_in = small.exchange_counts(counts, dev)
-        recv = m.route_recv(PGM_ROUTE_PATTERNS, pat_in, eb)
-        pat_pending = comm.all_to_all_async(recv, segs)
+        pat_in, pat_pending = ship(PGM_ROUTE_PATTERNS, m.route_begin(seed_len, parts, max_mm, min_mm, cont), comm)
         rounds = m.route_rounds()
+        seq = [(rev, rnd) for rev in passes for rnd in range(rounds)]
         if comm2 is None:
             pat_pending.wait()
             m.route_build(sum(pat_in))
-            for rev in passes:
-                for rnd in range(rounds):
-                    consume(rev, rnd, *emit(rev, rnd))
-                m.resolve_pass(rev)
+            for k, (rev, rnd) in enumerate(seq):
+                consume_slot(rev, rnd, k & 1, *emit_slot(rev, rnd, k & 1))
+                if rnd == rounds - 1:
+                    m.resolve_pass(rev)
             continue
         # pipelined: the (pass, round) pairs form one sequence; the windows of step k + 1 are hashed and shipped while step k is
         # probed and verified — across the pass boundary too (hashing and probing the RC text need no forward result; the
         # verification does: the forward decision is applied before the first RC round is consumed), and the first emit runs
         # while the patterns travel and the table is built (the scan only reads the text)
-        seq = [(rev, rnd) for rev in passes for rnd in range(rounds)]
         cur = emit_slot(*seq[0], 0)
         pat_pending.wait()
         m.route_build(sum(pat_in))
@@ -645,7 +685,7 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
                 m.resolve_pass(rev)
             cur = nxt
     m.route_slot(0)
-    return {"sent_bytes": sent, "rounds_per_pass": rounds, "pipelined": comm2 is not None}
+    return {"sent_bytes": sent, "rounds_per_pass": rounds, "pipelined": comm2 is not None, "exchange": exchange}
 
 
 def map_reads_into_pg_sharded(text, lq_packed, n_packed, read_len: int, *, rank: int, world: int, device: int,

@@ -50,7 +50,12 @@ class CpuRouteMatcher(CpuShardMatcher):
             rows = rows_by_dest.get(d, [])
             counts.append(len(rows))
             segs.append(torch.from_numpy(np.array(rows, np.int64).reshape(-1, 2).copy()).view(torch.uint8).reshape(-1) if rows else None)
-        return counts, segs, 16
+
+        class _E:      # what GpuReadsMatcher's emit steps return (matcher._Emit)
+            pass
+        e = _E()
+        e.counts, e.segs, e.eb, e.buf = counts, segs, 16, None
+        return e
 
     def route_begin(self, seed_len, parts, max_mm, min_mm, continuation=False):
         self.seed_len, self.parts, self.max_mm, self.min_mm = seed_len, parts, max_mm, min_mm

@@ -151,7 +151,7 @@ def test_c2_routed_four_contexts_equal_the_single_context(c2):
         with matcher.GpuReadsMatcher(0, use_torch_stream=True) as m:
             m.set_text(text)
             m.set_reads(reads[rb[rank]:rb[rank + 1]].contiguous(), None, L)
-            matcher.run_plan_routed(m, plan, True, comm, n, 16 << 20)
+            matcher.run_plan_routed(m, plan, True, comm, n, 16 << 20, comm2=comm.sibling(), exchange="pull")
             o = tuple(torch.empty(rb[rank + 1] - rb[rank], dtype=t.dtype, device="cuda") for t in out)
             return m.get_results(o)
 

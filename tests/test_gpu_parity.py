@@ -181,7 +181,7 @@ def _run_sharded_on_one_gpu(inp, world, **kw):
     return LocalWorld(world).run(rank_body)
 
 
-def _run_routed_on_one_gpu(inp, world, round_windows=0, **kw):
+def _run_routed_on_one_gpu(inp, world, round_windows=0, exchange=None, **kw):
     """The routed scheme (pgm_route_*) with `world` contexts on ONE GPU, one thread per rank, driven by the product's
     run_plan_routed; returns the per-rank results concatenated in read order (rank g owns read range g)."""
     from local_comm import LocalWorld
@@ -198,7 +198,11 @@ def _run_routed_on_one_gpu(inp, world, round_windows=0, **kw):
         with matcher.GpuReadsMatcher(0, use_torch_stream=True) as m:
             m.set_text(inp.text)
             m.set_reads(np.ascontiguousarray(lq), np.ascontiguousarray(nn) if nn is not None and len(nn) else None, inp.read_len)
-            info = matcher.run_plan_routed(m, plan, kw.get("rev_compl", True), comm, n, round_windows)
+            # world 2 / 3: the pipelined schedule with the peer-pull exchange (what bench.py runs on real GPUs; here the peers
+            # are contexts of this process, so the pull copies device-to-device without IPC); world 8: plain send / receive
+            ex = exchange or ("pull" if world <= 3 else "nccl")
+            info = matcher.run_plan_routed(m, plan, kw.get("rev_compl", True), comm, n, round_windows,
+                                           comm2=comm.sibling() if ex == "pull" else None, exchange=ex)
             return m.get_results(), info
 
     outs = LocalWorld(world).run(rank_body)

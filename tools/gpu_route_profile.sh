@@ -5,6 +5,6 @@ for fb in ${FBS:--1}; do
     FILTER_BITS=$fb timeout 600 python tools/route_one_gpu.py 2 0.25 2 > $OUT/route1gpu_fb${fb}_$TAG.txt 2>&1; tail -4 $OUT/route1gpu_fb${fb}_$TAG.txt
 done
 if [ -n "$RW" ]; then ROUND_WINDOWS=134217728 timeout 600 python tools/route_one_gpu.py 2 0.25 2 > $OUT/route1gpu_rw128_$TAG.txt 2>&1; tail -3 $OUT/route1gpu_rw128_$TAG.txt; fi
-timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'route_probe_kernel|route_scan_kernel|route_verify_kernel' -s 10 -c 8 \
+timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'route_filter_kernel|route_probe_kernel' -s 8 -c 4 \
     -f -o $OUT/route_kernels_$TAG python tools/route_one_gpu.py 2 0.25 1 > $OUT/ncu_route_$TAG.log 2>&1
 echo "ncu exit $?"; tail -3 $OUT/ncu_route_$TAG.log
