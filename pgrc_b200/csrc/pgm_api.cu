@@ -1303,11 +1303,16 @@ void route_range(const pgm_ctx *ctx, int g, uint32_t round, uint64_t &b, uint64_
     b = std::min(hi, lo + (uint64_t)round * ctx->route.round_windows);
     e = std::min(hi, b + ctx->route.round_windows);
 }
-uint32_t route_rounds(const pgm_ctx *ctx) {
+uint64_t route_longest(const pgm_ctx *ctx) {
     uint64_t longest = 0;
     for (int g = 0; g < ctx->route.world; g++) longest = std::max(longest, route_cut(ctx, g + 1) - route_cut(ctx, g));
-    return (uint32_t)std::max<uint64_t>(1, (longest + ctx->route.round_windows - 1) / ctx->route.round_windows);
+    return longest;
 }
+uint32_t route_rounds(const pgm_ctx *ctx) {
+    return (uint32_t)std::max<uint64_t>(1, (route_longest(ctx) + ctx->route.round_windows - 1) / ctx->route.round_windows);
+}
+// window starts a GPU emits in one round at most (what the exchange buffers are sized for)
+uint64_t route_round_size(const pgm_ctx *ctx) { return std::max<uint64_t>(PGM_TILE_POS, std::min(ctx->route.round_windows, route_longest(ctx))); }
 
 uint32_t route_cap(uint64_t total, int world) {
     // a destination's share + 25 % + slack, never more than everything (hot seeds / low-complexity text skew the shares)
@@ -1571,7 +1576,7 @@ int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer 
     if ((rc = finish_text_upload(ctx))) return rc;
     uint64_t b, e;
     route_range(ctx, rt.rank, round, b, e);
-    ctx->route.cap_win = route_cap(rt.round_windows, rt.world);
+    ctx->route.cap_win = route_cap(route_round_size(ctx), rt.world);
     if ((rc = ensure(ctx, ctx->rt_win_send_(), (size_t)ctx->route.cap_win * rt.world * 12))) return rc;
     CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_WINDOWS), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
     if (e > b) {                                   // (reads the text only: may run before the table of this phase exists)
@@ -1617,7 +1622,7 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
     if (n_in && ctx->rt_win_recv_().cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: the windows have not been received (pgm_route_recv)");
     // on average well under one candidate per window; hot keys are covered by the slack
     // (a fixed capacity: the buffer, hence its address — peers may hold it open over IPC — never changes between rounds)
-    ctx->route.cap_cand = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(n_in, rt.round_windows) / rt.world + (4u << 20), 0xFFFFFFF0ull);
+    ctx->route.cap_cand = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(n_in, route_round_size(ctx)) / rt.world + (4u << 20), 0xFFFFFFF0ull);
     int rc;
     if ((rc = ensure(ctx, ctx->rt_cand_send_(), (size_t)ctx->route.cap_cand * rt.world * 12))) return rc;
     CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_CANDIDATES), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
