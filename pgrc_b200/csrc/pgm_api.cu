@@ -1622,7 +1622,7 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
     if (n_in && ctx->rt_win_recv_().cap < n_in * 12) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: the windows have not been received (pgm_route_recv)");
     // on average well under one candidate per window; hot keys are covered by the slack
     // (a fixed capacity: the buffer, hence its address — peers may hold it open over IPC — never changes between rounds)
-    ctx->route.cap_cand = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(n_in, route_round_size(ctx)) / rt.world + (4u << 20), 0xFFFFFFF0ull);
+    ctx->route.cap_cand = (uint32_t)std::min<uint64_t>((std::max<uint64_t>(n_in, route_round_size(ctx)) + route_round_size(ctx) / 8) / rt.world + (4u << 20), 0xFFFFFFF0ull);
     int rc;
     if ((rc = ensure(ctx, ctx->rt_cand_send_(), (size_t)ctx->route.cap_cand * rt.world * 12))) return rc;
     CU(cudaMemsetAsync(route_counts(ctx, PGM_ROUTE_CANDIDATES), 0, RT_KIND_WORDS * sizeof(unsigned int), ctx->stream));
