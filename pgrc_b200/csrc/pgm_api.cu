@@ -124,7 +124,9 @@ struct pgm_ctx {
     DevBuf rt_win_send2[2], rt_win_recv2[2], rt_cand_send2[2], rt_cand_recv2[2], rt_pat_recv, rt_counters, rt_live, rt_live_count;
     // exchange by peer copies (pgm_route_export / pgm_route_pull): copies run on their own stream, one "arrived" event per
     // kind and slot; peer buffers opened through CUDA IPC are cached by handle
-    cudaStream_t pull_stream = nullptr;
+    cudaStream_t pull_stream = nullptr;          // carries the "arrived" events; the copies fan out over pull_more[] too (several copy engines)
+    cudaStream_t pull_more[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pull_join[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pull_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     bool pull_pending[3][2] = {{false, false}, {false, false}, {false, false}};
     std::vector<std::pair<std::string, void *>> ipc_open;
@@ -589,6 +591,10 @@ void pgm_destroy(pgm_ctx *ctx) {
     for (cudaEvent_t e : ctx->reads_ev) cudaEventDestroy(e);
     for (auto &kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
     for (int k = 0; k < 3; k++) for (int sl = 0; sl < 2; sl++) if (ctx->pull_ev[k][sl]) cudaEventDestroy(ctx->pull_ev[k][sl]);
+    for (int k = 0; k < 3; k++) {
+        if (ctx->pull_more[k]) { cudaStreamSynchronize(ctx->pull_more[k]); cudaStreamDestroy(ctx->pull_more[k]); }
+        if (ctx->pull_join[k]) cudaEventDestroy(ctx->pull_join[k]);
+    }
     if (ctx->pull_stream) { cudaStreamSynchronize(ctx->pull_stream); cudaStreamDestroy(ctx->pull_stream); }
     if (ctx->fence_ev) cudaEventDestroy(ctx->fence_ev);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -1488,7 +1494,13 @@ int pgm_route_pull(pgm_ctx *ctx, int kind, const pgm_route_peer *peers, const pg
     const pgm_ctx::Route &rt = ctx->route;
     if (!rt.world) return fail(ctx, PGM_ERR_STATE, "pgm_route_pull: pgm_route_config has not been called");
     CU(cudaSetDevice(ctx->device));
-    if (!ctx->pull_stream) CU(cudaStreamCreateWithFlags(&ctx->pull_stream, cudaStreamNonBlocking));
+    if (!ctx->pull_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->pull_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 3; k++) {
+            CU(cudaStreamCreateWithFlags(&ctx->pull_more[k], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ctx->pull_join[k], cudaEventDisableTiming));
+        }
+    }
     const int sl = kind == PGM_ROUTE_PATTERNS ? 0 : rt.slot;
     if (!ctx->pull_ev[kind][sl]) CU(cudaEventCreateWithFlags(&ctx->pull_ev[kind][sl], cudaEventDisableTiming));
     uint64_t total = 0;
@@ -1499,8 +1511,10 @@ int pgm_route_pull(pgm_ctx *ctx, int kind, const pgm_route_peer *peers, const pg
     // the copies may start once everything queued on the context's stream so far (the previous reader of this receive buffer) is done
     CU(cudaEventRecord(ctx->fence_ev, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->pull_stream, ctx->fence_ev, 0));
+    for (int k = 0; k < 3; k++) CU(cudaStreamWaitEvent(ctx->pull_more[k], ctx->fence_ev, 0));
     for (int k = 0; k < rt.world; k++) {
         const int s = (rt.rank + k) % rt.world;                    // own segment first, then round-robin over the peers
+        cudaStream_t cs = (k & 3) == 0 ? ctx->pull_stream : ctx->pull_more[(k & 3) - 1];
         uint64_t off = 0;
         for (int q = 0; q < s; q++) off += peer_sends[q].count[rt.rank] * peer_sends[q].entry_bytes;
         const uint64_t bytes = peer_sends[s].count[rt.rank] * peer_sends[s].entry_bytes;
@@ -1520,7 +1534,11 @@ int pgm_route_pull(pgm_ctx *ctx, int kind, const pgm_route_peer *peers, const pg
             }
         }
         const char *src = base + (uint64_t)rt.rank * peer_sends[s].stride_bytes;
-        CU(cudaMemcpyAsync(static_cast<char *>(dst) + off, src, bytes, cudaMemcpyDefault, ctx->pull_stream));
+        CU(cudaMemcpyAsync(static_cast<char *>(dst) + off, src, bytes, cudaMemcpyDefault, cs));
+    }
+    for (int k = 0; k < 3; k++) {
+        CU(cudaEventRecord(ctx->pull_join[k], ctx->pull_more[k]));
+        CU(cudaStreamWaitEvent(ctx->pull_stream, ctx->pull_join[k], 0));
     }
     CU(cudaEventRecord(ctx->pull_ev[kind][sl], ctx->pull_stream));
     ctx->pull_pending[kind][sl] = true;
