@@ -52,6 +52,12 @@ if has ncufull; then   # full captures of the scan kernel: C2 (both passes of on
         echo "ncu full $w exit $?"
     done
 fi
+if has ncuc5; then     # DRAM bytes of the scan launches at C5 (two metrics only: a full capture would replay 170 ms launches over a 100 GB footprint)
+    timeout 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none \
+        --kernel-name-base demangled -k regex:'pgm::scan_kernel' -s 4 -c 4 --csv --log-file $OUT/scan_c5_dram_$TAG.csv \
+        python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_c5_$TAG.log 2>&1
+    echo "ncu c5 exit $?"; tail -6 $OUT/scan_c5_dram_$TAG.csv
+fi
 if has c2; then
     timeout 900 python bench.py --workload c2 --verify --steps 20 --warmup 5 > $OUT/bench_c2_n1_$TAG.json 2>> $OUT/bench_$TAG.err
     cat $OUT/bench_c2_n1_$TAG.json
