@@ -254,6 +254,12 @@ int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer 
 /* in_counts[world]: window entries received from each sender (in sender order in the receive buffer). */
 int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *in_counts, pgm_route_buffer *send);
 int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_candidates_in);
+/* The emit steps in two halves, for callers that keep the GPU queue filled while they exchange counts: _launch queues the
+ * kernels (and the copy of the per-destination counts to pinned host memory); pgm_route_fetch waits for THAT step only —
+ * not for work queued behind it — and describes the send buffer.  pgm_route_scan / pgm_route_probe = launch + fetch. */
+int pgm_route_scan_launch(pgm_ctx *ctx, int rev_mode, uint32_t round);
+int pgm_route_probe_launch(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *in_counts);
+int pgm_route_fetch(pgm_ctx *ctx, int kind, pgm_route_buffer *send);
 
 /* ---- several GPUs behind one handle (one process, one host thread per GPU inside the library) ----------------
  * What the C++ host side of PgRC uses (pgrc_b200/host/GpuReadsMatchers.cpp; PGRC_GPU_DEVICES=0,1,...): the same

@@ -23,7 +23,7 @@ EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pg
            "pgm_set_text", "pgm_set_text_shard", "pgm_shard_plan", "pgm_set_reads", "pgm_match_begin", "pgm_match_begin_interleaved",
            "pgm_scan_pass", "pgm_get_accumulators", "pgm_put_accumulators", "pgm_resolve_pass", "pgm_get_results", "pgm_get_mismatches", "pgm_copmem_begin", "pgm_copmem_pass", "pgm_map_reads",
            "pgm_kernel_launches", "pgm_set_tuning", "pgm_set_profiling", "pgm_get_timings",
-           "pgm_route_config", "pgm_route_rounds", "pgm_route_slot", "pgm_route_export", "pgm_route_pull", "pgm_route_begin", "pgm_route_recv", "pgm_route_build", "pgm_route_scan", "pgm_route_probe",
+           "pgm_route_config", "pgm_route_rounds", "pgm_route_slot", "pgm_route_export", "pgm_route_pull", "pgm_route_scan_launch", "pgm_route_probe_launch", "pgm_route_fetch", "pgm_route_begin", "pgm_route_recv", "pgm_route_build", "pgm_route_scan", "pgm_route_probe",
            "pgm_route_verify",
            "pgm_group_create", "pgm_group_destroy", "pgm_group_last_error", "pgm_group_size", "pgm_group_set_text", "pgm_group_set_reads",
            "pgm_group_upload", "pgm_group_match_begin", "pgm_group_pass", "pgm_group_copmem_begin", "pgm_group_copmem_pass",
@@ -115,6 +115,9 @@ def load() -> ctypes.CDLL:
     lib.pgm_route_config.restype = ci; lib.pgm_route_config.argtypes = [vp, ci, ci, ctypes.POINTER(u64), u64]
     lib.pgm_route_rounds.restype = ci; lib.pgm_route_rounds.argtypes = [vp, ctypes.POINTER(u32)]
     lib.pgm_route_slot.restype = ci; lib.pgm_route_slot.argtypes = [vp, ci]
+    lib.pgm_route_scan_launch.restype = ci; lib.pgm_route_scan_launch.argtypes = [vp, ci, u32]
+    lib.pgm_route_probe_launch.restype = ci; lib.pgm_route_probe_launch.argtypes = [vp, ci, u32, ctypes.POINTER(u64)]
+    lib.pgm_route_fetch.restype = ci; lib.pgm_route_fetch.argtypes = [vp, ci, rb]
     lib.pgm_route_export.restype = ci; lib.pgm_route_export.argtypes = [vp, ci, ctypes.POINTER(PgmRoutePeer)]
     lib.pgm_route_pull.restype = ci; lib.pgm_route_pull.argtypes = [vp, ci, ctypes.POINTER(PgmRoutePeer), ctypes.POINTER(PgmRouteBuffer)]
     lib.pgm_route_begin.restype = ci; lib.pgm_route_begin.argtypes = [vp, u32, u32, u32, u32, ci, rb]

@@ -129,6 +129,9 @@ struct pgm_ctx {
     cudaEvent_t pull_join[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pull_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     bool pull_pending[3][2] = {{false, false}, {false, false}, {false, false}};
+    cudaEvent_t consumed_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // last reader of a receive buffer
+    unsigned int *rt_counts_host = nullptr;      // pinned: the counts of the emit steps, per slot and kind
+    cudaEvent_t counts_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     std::vector<std::pair<std::string, void *>> ipc_open;
     DevBuf &rt_win_send_() { return rt_win_send2[route.slot]; }
     DevBuf &rt_win_recv_() { return rt_win_recv2[route.slot]; }
@@ -590,6 +593,9 @@ void pgm_destroy(pgm_ctx *ctx) {
     for (cudaEvent_t e : ctx->text_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->reads_ev) cudaEventDestroy(e);
     for (auto &kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
+    if (ctx->rt_counts_host) cudaFreeHost(ctx->rt_counts_host);
+    for (int k = 0; k < 3; k++) for (int sl = 0; sl < 2; sl++) if (ctx->counts_ev[k][sl]) cudaEventDestroy(ctx->counts_ev[k][sl]);
+    for (int k = 0; k < 3; k++) for (int sl = 0; sl < 2; sl++) if (ctx->consumed_ev[k][sl]) cudaEventDestroy(ctx->consumed_ev[k][sl]);
     for (int k = 0; k < 3; k++) for (int sl = 0; sl < 2; sl++) if (ctx->pull_ev[k][sl]) cudaEventDestroy(ctx->pull_ev[k][sl]);
     for (int k = 0; k < 3; k++) {
         if (ctx->pull_more[k]) { cudaStreamSynchronize(ctx->pull_more[k]); cudaStreamDestroy(ctx->pull_more[k]); }
@@ -1332,10 +1338,23 @@ unsigned int *route_overflow(pgm_ctx *ctx, int kind) { return route_counts(ctx, 
 unsigned int *route_tile_counter(pgm_ctx *ctx, int kind) { return route_counts(ctx, kind) + PGM_ROUTE_MAX_WORLD + 1; }
 
 // copies the per-destination counts of `kind` (and the overflow flag) to the host; synchronizes the stream
+// queues the copy of the per-destination counts of (kind, current slot) to pinned host memory behind the emit kernels, and an event
+int route_post_counts(pgm_ctx *ctx, int kind) {
+    const int sl = ctx->route.slot;
+    if (!ctx->rt_counts_host) CU(cudaMallocHost(reinterpret_cast<void **>(&ctx->rt_counts_host), 2 * RT_SLOT_WORDS * sizeof(unsigned int)));
+    if (!ctx->counts_ev[kind][sl]) CU(cudaEventCreateWithFlags(&ctx->counts_ev[kind][sl], cudaEventDisableTiming));
+    CU(cudaMemcpyAsync(ctx->rt_counts_host + sl * RT_SLOT_WORDS + kind * RT_KIND_WORDS, route_counts(ctx, kind), RT_KIND_WORDS * sizeof(unsigned int),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->counts_ev[kind][sl], ctx->stream));
+    return PGM_OK;
+}
+
+// waits for the emit step of (kind, current slot) — not for anything queued behind it — and describes its send buffer
 int route_fetch_counts(pgm_ctx *ctx, int kind, pgm_route_buffer *send, void *base, uint64_t stride, uint32_t entry_bytes, const char *what) {
-    unsigned int h[RT_KIND_WORDS];
-    CU(cudaMemcpyAsync(h, route_counts(ctx, kind), sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    const int sl = ctx->route.slot;
+    if (!ctx->rt_counts_host || !ctx->counts_ev[kind][sl]) return fail(ctx, PGM_ERR_STATE, std::string(what) + ": nothing was emitted");
+    CU(cudaEventSynchronize(ctx->counts_ev[kind][sl]));
+    const unsigned int *h = ctx->rt_counts_host + sl * RT_SLOT_WORDS + kind * RT_KIND_WORDS;
     if (h[PGM_ROUTE_MAX_WORLD])
         return fail(ctx, PGM_ERR_STATE, std::string(what) + ": an exchange queue overflowed (a GPU's share of the hashes / candidates is far above "
                                         "the average: extremely skewed input); rerun with the read-sharded scheme");
@@ -1442,6 +1461,7 @@ int pgm_route_begin(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t ma
     }
     ctx->phase_active = true;
     ctx->copmem_active = false;
+    if ((rc = route_post_counts(ctx, PGM_ROUTE_PATTERNS))) return rc;
     return route_fetch_counts(ctx, PGM_ROUTE_PATTERNS, send, ctx->bq_entries.p, (uint64_t)ctx->route.cap_pat * sizeof(uint4), sizeof(uint4), "pgm_route_begin");
 }
 
@@ -1460,6 +1480,14 @@ int pgm_route_recv(pgm_ctx *ctx, int kind, uint64_t n_entries, void **ptr) {
 } // extern "C"
 
 namespace {
+// marks the receive buffer of (kind, current slot) as read by what has been queued so far
+int route_mark_consumed(pgm_ctx *ctx, int kind) {
+    const int sl = kind == PGM_ROUTE_PATTERNS ? 0 : ctx->route.slot;
+    if (!ctx->consumed_ev[kind][sl]) CU(cudaEventCreateWithFlags(&ctx->consumed_ev[kind][sl], cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->consumed_ev[kind][sl], ctx->stream));
+    return PGM_OK;
+}
+
 // orders the context's stream behind a pending peer pull of (kind, current slot)
 int route_wait_pull(pgm_ctx *ctx, int kind) {
     const int sl = kind == PGM_ROUTE_PATTERNS ? 0 : ctx->route.slot;
@@ -1508,10 +1536,12 @@ int pgm_route_pull(pgm_ctx *ctx, int kind, const pgm_route_peer *peers, const pg
     void *dst = nullptr;
     int rc;
     if ((rc = pgm_route_recv(ctx, kind, total, &dst))) return rc;
-    // the copies may start once everything queued on the context's stream so far (the previous reader of this receive buffer) is done
-    CU(cudaEventRecord(ctx->fence_ev, ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->pull_stream, ctx->fence_ev, 0));
-    for (int k = 0; k < 3; k++) CU(cudaStreamWaitEvent(ctx->pull_more[k], ctx->fence_ev, 0));
+    // the copies may start once the previous reader of this receive buffer is done (NOT everything queued on the stream: the
+    // caller keeps the queue filled with other steps while this transfer runs)
+    if (ctx->consumed_ev[kind][sl]) {
+        CU(cudaStreamWaitEvent(ctx->pull_stream, ctx->consumed_ev[kind][sl], 0));
+        for (int k = 0; k < 3; k++) CU(cudaStreamWaitEvent(ctx->pull_more[k], ctx->consumed_ev[kind][sl], 0));
+    }
     for (int k = 0; k < rt.world; k++) {
         const int s = (rt.rank + k) % rt.world;                    // own segment first, then round-robin over the peers
         cudaStream_t cs = (k & 3) == 0 ? ctx->pull_stream : ctx->pull_more[(k & 3) - 1];
@@ -1579,11 +1609,27 @@ int pgm_route_build(pgm_ctx *ctx, uint64_t n_in) {
     if (n_in)
         KLAUNCH(PGM_K_ROUTE_BUILD, "route_insert_kernel", pgm::route_insert_kernel<<<ctx->sm_count * 8, PGM_INSERT_THREADS, 0, ctx->stream>>>(
             table_view(ctx), ctx->rt_pat_recv.as<uint4>(), n_in));
-    return PGM_OK;
+    return route_mark_consumed(ctx, PGM_ROUTE_PATTERNS);
 }
 
 int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer *send) {
     if (!ctx || !send) return PGM_ERR_INVALID_ARG;
+    const int rc = pgm_route_scan_launch(ctx, rev_mode, round);
+    return rc ? rc : pgm_route_fetch(ctx, PGM_ROUTE_WINDOWS, send);
+}
+
+int pgm_route_fetch(pgm_ctx *ctx, int kind, pgm_route_buffer *send) {
+    if (!ctx || !send || kind < 0 || kind > 2) return PGM_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (kind == PGM_ROUTE_PATTERNS)
+        return route_fetch_counts(ctx, kind, send, ctx->bq_entries.p, (uint64_t)ctx->route.cap_pat * sizeof(uint4), sizeof(uint4), "pgm_route_fetch");
+    if (kind == PGM_ROUTE_WINDOWS)
+        return route_fetch_counts(ctx, kind, send, ctx->rt_win_send_().p, (uint64_t)ctx->route.cap_win * 12, 12, "pgm_route_fetch");
+    return route_fetch_counts(ctx, kind, send, ctx->rt_cand_send_().p, (uint64_t)ctx->route.cap_cand * 12, 12, "pgm_route_fetch");
+}
+
+int pgm_route_scan_launch(pgm_ctx *ctx, int rev_mode, uint32_t round) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
     const pgm_ctx::Route &rt = ctx->route;
     if (!rt.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_scan: pgm_route_begin has not been called");
     if (!ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_route_scan: pgm_set_text has not been called");
@@ -1625,11 +1671,17 @@ int pgm_route_scan(pgm_ctx *ctx, int rev_mode, uint32_t round, pgm_route_buffer 
         if (le != cudaSuccess) return cuda_fail(ctx, le, "route_scan_kernel (shared memory attribute)");
     }
     ctx->state_fresh = false;
-    return route_fetch_counts(ctx, PGM_ROUTE_WINDOWS, send, ctx->rt_win_send_().p, (uint64_t)ctx->route.cap_win * 12, 12, "pgm_route_scan");
+    return route_post_counts(ctx, PGM_ROUTE_WINDOWS);
 }
 
 int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *in_counts, pgm_route_buffer *send) {
     if (!ctx || !send || !in_counts) return PGM_ERR_INVALID_ARG;
+    const int rc = pgm_route_probe_launch(ctx, rev_mode, round, in_counts);
+    return rc ? rc : pgm_route_fetch(ctx, PGM_ROUTE_CANDIDATES, send);
+}
+
+int pgm_route_probe_launch(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *in_counts) {
+    if (!ctx || !in_counts) return PGM_ERR_INVALID_ARG;
     const pgm_ctx::Route &rt = ctx->route;
     if (!rt.world || !ctx->phase_active) return fail(ctx, PGM_ERR_STATE, "pgm_route_probe: pgm_route_begin has not been called");
     (void)rev_mode;
@@ -1691,7 +1743,8 @@ int pgm_route_probe(pgm_ctx *ctx, int rev_mode, uint32_t round, const uint64_t *
         off += in_counts[s];
     }
     if (persist && (rc = filter_window(ctx, false, true))) return rc;
-    return route_fetch_counts(ctx, PGM_ROUTE_CANDIDATES, send, ctx->rt_cand_send_().p, (uint64_t)ctx->route.cap_cand * 12, 12, "pgm_route_probe");
+    if ((rc = route_mark_consumed(ctx, PGM_ROUTE_WINDOWS))) return rc;
+    return route_post_counts(ctx, PGM_ROUTE_CANDIDATES);
 }
 
 int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_in) {
@@ -1718,7 +1771,7 @@ int pgm_route_verify(pgm_ctx *ctx, int rev_mode, uint64_t n_in) {
     KLAUNCH(PGM_K_ROUTE_VERIFY, "route_verify_kernel",
             if (ctx->lq_stride16 == 4) pgm::route_verify_kernel<true><<<grid, PGM_VERIFY_THREADS, 0, ctx->stream>>>(vp);
             else pgm::route_verify_kernel<false><<<grid, PGM_VERIFY_THREADS, 0, ctx->stream>>>(vp));
-    return PGM_OK;
+    return route_mark_consumed(ctx, PGM_ROUTE_CANDIDATES);
 }
 
 int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed, uint32_t seed,

@@ -246,6 +246,19 @@ class GpuReadsMatcher:
         self._check(self._lib.pgm_route_probe(self._h, int(rev_mode), rnd, arr, ctypes.byref(buf)))
         return _Emit(self, buf)
 
+    def route_scan_launch(self, rev_mode: bool, rnd: int):
+        self._check(self._lib.pgm_route_scan_launch(self._h, int(rev_mode), rnd))
+
+    def route_probe_launch(self, rev_mode: bool, rnd: int, in_counts):
+        arr = (ctypes.c_uint64 * len(in_counts))(*[int(x) for x in in_counts])
+        self._check(self._lib.pgm_route_probe_launch(self._h, int(rev_mode), rnd, arr))
+
+    def route_fetch(self, kind: int):
+        """Waits for the emit step of `kind` in the current slot (not for work queued behind it) and returns its send buffer."""
+        buf = PgmRouteBuffer()
+        self._check(self._lib.pgm_route_fetch(self._h, kind, ctypes.byref(buf)))
+        return _Emit(self, buf)
+
     def route_export(self, kind: int, buf: PgmRouteBuffer) -> bytes:
         """What the peers need to pull their segments of this rank's send buffer: the buffer descriptor (counts, stride)
         and where it lives (pgm_route_export), as one blob for an all-gather."""
@@ -671,19 +684,47 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
                 if rnd == rounds - 1:
                     m.resolve_pass(rev)
             continue
-        # pipelined: the (pass, round) pairs form one sequence; the windows of step k + 1 are hashed and shipped while step k is
-        # probed and verified — across the pass boundary too (hashing and probing the RC text need no forward result; the
-        # verification does: the forward decision is applied before the first RC round is consumed), and the first emit runs
-        # while the patterns travel and the table is built (the scan only reads the text)
-        cur = emit_slot(*seq[0], 0)
+        # pipelined: the (pass, round) pairs form one sequence k = 0, 1, ...; the GPU queue always holds work while the host
+        # exchanges counts.  Stream order: ... scan(k+2), probe(k+1), verify(k), scan(k+3), probe(k+2), verify(k+1) ...
+        #   * the windows of step k + 2 are hashed and shipped while step k + 1 is probed and step k verified — across the pass
+        #     boundary too: hashing and probing the RC text need no forward result; the verification does, and the forward
+        #     decision (resolve) is queued behind the last forward verify, ahead of the first RC verify;
+        #   * the first two scans run while the patterns travel and the table is built (a scan only reads the text);
+        #   * buffer reuse: scan(k+2) overwrites the send slot of windows(k), probe(k+1) the one of candidates(k-1): both follow
+        #     the stream synchronize + the all-gather of step (a), after which every rank has probed step k and verified k-1,
+        #     i.e. has finished pulling both.
+        n = len(seq)
+        win = [None] * n
+        m.route_slot(0)
+        m.route_scan_launch(*seq[0])
+        win[0] = ship(PGM_ROUTE_WINDOWS, m.route_fetch(PGM_ROUTE_WINDOWS), comm)
         pat_pending.wait()
         m.route_build(sum(pat_in))
+        if n > 1:
+            m.route_slot(1)
+            m.route_scan_launch(*seq[1])
+            win[1] = ship(PGM_ROUTE_WINDOWS, m.route_fetch(PGM_ROUTE_WINDOWS), comm)
+        m.route_slot(0)
+        win[0][1].wait()
+        m.route_probe_launch(*seq[0], win[0][0])
         for k, (rev, rnd) in enumerate(seq):
-            nxt = emit_slot(*seq[k + 1], (k + 1) & 1) if k + 1 < len(seq) else None
-            consume_slot(rev, rnd, k & 1, *cur)
+            m.synchronize()                                               # (a) probe(k) and verify(k-1) are done
+            m.route_slot(k & 1)
+            cand_in, cand_pending = ship(PGM_ROUTE_CANDIDATES, m.route_fetch(PGM_ROUTE_CANDIDATES), small)
+            if k + 2 < n:                                                 # (b)
+                m.route_scan_launch(*seq[k + 2])
+            if k + 1 < n:                                                 # (c)
+                m.route_slot((k + 1) & 1)
+                win[k + 1][1].wait()
+                m.route_probe_launch(*seq[k + 1], win[k + 1][0])
+            m.route_slot(k & 1)                                           # (d)
+            cand_pending.wait()
+            m.route_verify(rev, sum(cand_in))
             if rnd == rounds - 1:
                 m.resolve_pass(rev)
-            cur = nxt
+            if k + 2 < n:                                                 # (e) waits for scan(k+2) only
+                win[k + 2] = ship(PGM_ROUTE_WINDOWS, m.route_fetch(PGM_ROUTE_WINDOWS), comm)
+            win[k] = None
     m.route_slot(0)
     return {"sent_bytes": sent, "rounds_per_pass": rounds, "pipelined": comm2 is not None, "exchange": exchange}
 

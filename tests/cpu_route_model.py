@@ -108,6 +108,21 @@ class CpuRouteMatcher(CpuShardMatcher):
                     out.setdefault(owner, []).append((base + rel, pat))
         return self._segs(out, self.world)
 
+    # launch / fetch halves (the product overlaps them with exchanges; the model computes at launch and hands over at fetch)
+    def route_scan_launch(self, rev, rnd):
+        self._emitted = getattr(self, "_emitted", {})
+        self._emitted[(1, self.slot)] = self.route_scan(rev, rnd)
+
+    def route_probe_launch(self, rev, rnd, in_counts):
+        self._emitted = getattr(self, "_emitted", {})
+        self._emitted[(2, self.slot)] = self.route_probe(rev, rnd, in_counts)
+
+    def route_fetch(self, kind):
+        return self._emitted[(kind, self.slot)]
+
+    def synchronize(self):
+        pass
+
     def route_verify(self, rev, n_in):
         t = self.rc_text if rev else self.text
         seen = 0
