@@ -630,7 +630,7 @@ def read_ranges(n_reads: int, world: int):
 
 
 def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total: int, round_windows: int = 0, comm2=None,
-                    exchange: str = "nccl") -> dict:
+                    exchange: str = "nccl", deep: bool = False) -> dict:
     """The routed scheme (include/pgrc_gpu_matcher.h, pgm_route_*): this rank's context holds the whole text and its own
     read range (`read_ranges`).  Per phase the seeds are exchanged once (all-to-all by hash owner); per pass and round the
     windows of this rank's text range go to the hash owners and the candidates they find go to the read owners.
@@ -639,7 +639,9 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
     overlaps whatever kernels follow.  With a second communicator (`comm2`, e.g. comm.sibling(); used for the small
     all-gathers of counts, so that they do not queue behind a transfer) the (pass, round) steps are software-pipelined: the
     windows of step k + 1 are hashed and shipped while step k is probed and verified — the two sets of exchange buffers of the
-    context (pgm_route_slot) make that safe.  Returns the bytes this rank sent per kind."""
+    context (pgm_route_slot) make that safe.  `deep` = the three-stage variant of the pipeline (scan k+2 / probe k+1 / verify k
+    queued together, the host waits per emit step through pgm_route_fetch); measured slower at N = 8 (103.7 vs 94.4 ms per
+    step at C5: the exchange, not the host, is what the probe waits for), kept selectable.  Returns the bytes sent per kind."""
     comm = _as_comm(comm)
     dev = f"cuda:{m.device}" if isinstance(m.device, int) else m.device
     m.route_config(comm.rank, comm.world, read_ranges(n_reads_total, comm.world), round_windows)
@@ -684,6 +686,21 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
                 if rnd == rounds - 1:
                     m.resolve_pass(rev)
             continue
+        if not deep:
+            # pipelined: the (pass, round) pairs form one sequence; the windows of step k + 1 are hashed and shipped while step k is
+            # probed and verified — across the pass boundary too (hashing and probing the RC text need no forward result; the
+            # verification does: the forward decision is applied before the first RC round is consumed), and the first emit runs
+            # while the patterns travel and the table is built (the scan only reads the text)
+            cur = emit_slot(*seq[0], 0)
+            pat_pending.wait()
+            m.route_build(sum(pat_in))
+            for k, (rev, rnd) in enumerate(seq):
+                nxt = emit_slot(*seq[k + 1], (k + 1) & 1) if k + 1 < len(seq) else None
+                consume_slot(rev, rnd, k & 1, *cur)
+                if rnd == rounds - 1:
+                    m.resolve_pass(rev)
+                cur = nxt
+            continue
         # pipelined: the (pass, round) pairs form one sequence k = 0, 1, ...; the GPU queue always holds work while the host
         # exchanges counts.  Stream order: ... scan(k+2), probe(k+1), verify(k), scan(k+3), probe(k+2), verify(k+1) ...
         #   * the windows of step k + 2 are hashed and shipped while step k + 1 is probed and step k verified — across the pass
@@ -726,7 +743,7 @@ def run_plan_routed(m, plan: MatchPlan, rev_compl_pg: bool, comm, n_reads_total:
                 win[k + 2] = ship(PGM_ROUTE_WINDOWS, m.route_fetch(PGM_ROUTE_WINDOWS), comm)
             win[k] = None
     m.route_slot(0)
-    return {"sent_bytes": sent, "rounds_per_pass": rounds, "pipelined": comm2 is not None, "exchange": exchange}
+    return {"sent_bytes": sent, "rounds_per_pass": rounds, "pipelined": ("deep" if deep else True) if comm2 is not None else False, "exchange": exchange}
 
 
 def map_reads_into_pg_sharded(text, lq_packed, n_packed, read_len: int, *, rank: int, world: int, device: int,

@@ -202,7 +202,7 @@ def _run_routed_on_one_gpu(inp, world, round_windows=0, exchange=None, **kw):
             # are contexts of this process, so the pull copies device-to-device without IPC); world 8: plain send / receive
             ex = exchange or ("pull" if world <= 3 else "nccl")
             info = matcher.run_plan_routed(m, plan, kw.get("rev_compl", True), comm, n, round_windows,
-                                           comm2=comm.sibling() if ex == "pull" else None, exchange=ex)
+                                           comm2=comm.sibling() if ex == "pull" else None, exchange=ex, deep=(world == 3))
             return m.get_results(), info
 
     outs = LocalWorld(world).run(rank_body)

@@ -168,7 +168,8 @@ def _worker_routed(rank, world, port, case, kw, round_windows, ret_dir):
                                     kw.get("pre_seed", 0), kw.get("pre_mode", "d"))
     comm = matcher.TorchComm()
     info = matcher.run_plan_routed(m, plan, kw.get("rev_compl", True), comm, len(reads), round_windows,
-                                   comm2=comm.sibling() if round_windows else None)      # several rounds: the pipelined schedule
+                                   comm2=comm.sibling() if round_windows else None,      # several rounds: the pipelined schedules
+                                   deep=bool(kw.get("pre_seed")))
     res = m.get_results()
     np.savez(os.path.join(ret_dir, f"rank{rank}.npz"), pos=res.pos, rc=res.rc, mm=res.mm, lo=rb[rank], hi=rb[rank + 1], rounds=info["rounds_per_pass"])
     dist.destroy_process_group()
