@@ -79,6 +79,9 @@ def _oracle():
         lib.pgo_mismatch_lists.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
                                            ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.pgo_match_texts.restype = ctypes.c_int
+        lib.pgo_match_texts.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
         _oracle_lib = lib
     return _oracle_lib
 
@@ -106,6 +109,15 @@ def _ref():
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p]
+        lib.pgref_match_texts.restype = ctypes.c_int
+        lib.pgref_match_texts.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                          ctypes.c_void_p, ctypes.c_void_p]
+        lib.pgref_mark_matches.restype = ctypes.c_int
+        lib.pgref_mark_matches.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                           ctypes.c_void_p, ctypes.c_void_p]
         _ref_lib = lib
     return _ref_lib
 
@@ -230,3 +242,74 @@ def ref_mismatch_lists(text, lq_ascii, n_ascii, read_len: int, rev_compl_pair_fi
     t = int(off[-1])
     return (MatchResult(pos, rc, mm, int((mm != 255).sum()), 0, 0, np.bincount(mm, minlength=256).astype(np.uint64), seconds=secs.value),
             off, o[:t], _SYM_CODE[pg[:t]], _SYM_CODE[rd[:t]])
+
+
+# ------------------------------------------------------------------------------------------ stage 7 (exact matches between pseudogenomes)
+_COMPLEMENT = np.arange(256, dtype=np.uint8)
+for _a, _b in ("AT", "CG", "GC", "TA"):
+    _COMPLEMENT[ord(_a)] = ord(_b)
+
+
+def reverse_complement(text) -> np.ndarray:
+    """PgHelpers::reverseComplement (utils/helper.cpp:395-403): symbols outside ACGT stay as they are."""
+    return np.ascontiguousarray(_COMPLEMENT[np.asarray(text, dtype=np.uint8)[::-1]])
+
+
+def _match_texts(fn, src, dest, dest_is_src, rev_compl, target_len, min_len, extra):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dest = np.ascontiguousarray(dest, dtype=np.uint8)
+    cap = max(1024, dest.size // 8)
+    while True:
+        out = np.empty((cap, 3), np.uint64)
+        cnt = ctypes.c_uint64(0)
+        r = fn(src.ctypes.data, src.size, dest.ctypes.data, dest.size, int(dest_is_src), int(rev_compl), target_len,
+               min(min_len, 0xFFFFFFFF), *extra(out, cap, cnt))
+        if r == -3:
+            cap = int(cnt.value)
+            continue
+        if r != 0:
+            raise RuntimeError(f"match_texts failed ({r})")
+        return out[:int(cnt.value)].copy()
+
+
+def oracle_match_texts(src, dest, dest_is_src: bool = False, rev_compl: bool = True, target_len: int = 45,
+                       min_len: int = 0xFFFFFFFF, params: dict | None = None) -> np.ndarray:
+    """pgo_match_texts: resMatches of CopMEMMatcher::matchTexts as an (n, 3) uint64 array {posSrcText, length, posDestText}
+    in push order.  `dest` is the text handed to the matcher (already reverse-complemented by the caller when rev_compl)."""
+    par = np.zeros(5, np.uint64)
+    res = _match_texts(_oracle().pgo_match_texts, src, dest, dest_is_src, rev_compl, target_len, min_len,
+                       lambda out, cap, cnt: (out.ctypes.data, cap, ctypes.byref(cnt), par.ctypes.data))
+    if params is not None:
+        params.update(K=int(par[0]), k1=int(par[1]), k2=int(par[2]), hash_size=int(par[3]), extensions=int(par[4]))
+    return res
+
+
+def ref_match_texts(src, dest, dest_is_src: bool = False, rev_compl: bool = True, target_len: int = 45,
+                    min_len: int = 0xFFFFFFFF, threads: int = 1, seconds: list | None = None) -> np.ndarray:
+    """The reference's own CopMEMMatcher (constructor + matchTexts) through the harness."""
+    secs = (ctypes.c_double * 2)()
+    res = _match_texts(_ref().pgref_match_texts, src, dest, dest_is_src, rev_compl, target_len, min_len,
+                       lambda out, cap, cnt: (threads, out.ctypes.data, cap, ctypes.byref(cnt), secs))
+    if seconds is not None:
+        seconds[:] = [secs[0], secs[1]]
+    return res
+
+
+def ref_mark_matches(src, dest, dest_is_src: bool = False, rev_compl: bool = True, target_len: int = 45,
+                     min_len: int = 0xFFFFFFFF, threads: int = 1):
+    """SimplePgMatcher::markAndRemoveExactMatches through the harness: (mapped destination, resPgMapOff, resPgMapLen) as
+    uint8 arrays.  `dest` is NOT reverse-complemented by the caller (the class does it)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    n2 = src.size if dest_is_src else np.asarray(dest).size
+    buf = np.zeros(max(n2, 1), np.uint8)
+    if not dest_is_src:
+        buf[:n2] = np.asarray(dest, dtype=np.uint8)
+    off = np.empty(n2 + 64, np.uint8); ln = np.empty(n2 + 64, np.uint8)
+    m, ol, ll = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+    secs = ctypes.c_double(0.0)
+    r = _ref().pgref_mark_matches(src.ctypes.data, src.size, buf.ctypes.data, n2, int(dest_is_src), int(rev_compl), target_len,
+                                  min(min_len, 0xFFFFFFFF), threads, ctypes.byref(m), off.ctypes.data, off.size, ctypes.byref(ol),
+                                  ln.ctypes.data, ln.size, ctypes.byref(ll), ctypes.byref(secs))
+    if r != 0:
+        raise RuntimeError(f"pgref_mark_matches failed ({r})")
+    return buf[:int(m.value)].copy(), off[:int(ol.value)].copy(), ln[:int(ll.value)].copy()

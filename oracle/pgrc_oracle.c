@@ -745,3 +745,140 @@ int pgo_mismatch_lists(const char *text, uint64_t text_len, const uint8_t *lq_pa
     free(cur);
     return 0;
 }
+
+/* ------------------------------------------------------------------ stage 7: exact matches between pseudogenomes (§8(f) rank 4)
+ * CopMEMMatcher::matchTexts -> processExactMatchQueryTight (copmem/CopMEMMatcher.cpp:332-481) over the serial index
+ * (:139-233, the reference at -t 1), as SimplePgMatcher::exactMatchPg calls it (SimplePgMatcher.cpp:26-55): the source
+ * text is indexed once (constructor, :571-593), every k2-th K-mer of the destination text is looked up, the bucket
+ * entries are tried in text order, and the first one that extends to at least minMatchLength characters is pushed; the
+ * query then jumps `skip` positions ahead — inside the current group of 256 query positions only.
+ * A literal, sequential transcription, including
+ *   - the "already covered by the previous match" test against resMatches.back() (:388-393),
+ *   - the 4-byte guards l1/l2/r1/r2 that keep a stale value when a load would leave the text (:384-385, :396-397),
+ *   - the left extension, which stops BEFORE comparing when it reaches the start of either text: the match then begins
+ *     one character late (:405).
+ * One deliberate difference: the tail loop of the reference loads l1 / r1 without the bounds check of the main loop
+ * (:447-448, reading outside the source text for the first / last sampled positions); the oracle keeps the check there too.
+ * Result-neutral: the guards only pre-filter, a candidate that extends to minMatchLength has at least (L-K)/2 equal
+ * characters on one side, all of them inside both texts, so the guard of that side is loaded and equal. */
+typedef struct { uint64_t src, len, dest; } pgo_text_match;
+
+static int copmem_params2(copmem_index *x, uint32_t L, uint32_t min_len, uint64_t N) {
+    /* initParams(minMatchLength) with minMatchLength = min(min_len, L) (constructor :574-576) */
+    if (min_len > L) min_len = L;
+    int K;
+    if (L > 110) K = 56; else if (L > 62) K = 44; else if (L > 53) K = 40; else if (L > 46) K = 36;
+    else if (L > 42) K = 32; else if (L > 32) K = 28; else K = ((int)L / 4 - 1) * 4;
+    if (min_len < 24) return -1;
+    const int kmml = ((int)min_len / 4 - 1) * 4;
+    if (kmml < K) K = kmml;
+    const int t = (int)L - K + 1;
+    if (t <= 0) return -1;
+    int k1, k2;
+    if (t >= 20) {
+        k1 = 1; while ((k1 + 1) * (k1 + 1) <= t) k1++;
+        k1 += 1; k2 = k1 - 1;
+        if (k1 * k2 > t) { --k2; --k1; }
+    } else if (t >= 15) { k1 = 5; k2 = 3; } else if (t >= 12) { k1 = 4; k2 = 3; } else if (t >= 10) { k1 = 5; k2 = 2; }
+    else if (t >= 6) { k1 = 3; k2 = 2; } else { k1 = t; k2 = 1; }
+    x->L = L; x->K = (uint32_t)K; x->k1 = (uint32_t)k1; x->k2 = (uint32_t)k2; x->N = N;
+    int i = CM_HASH_MIN_ORDER;
+    do { x->hash_size = 1u << (i++); } while (i <= CM_HASH_MAX_ORDER && x->hash_size < N / (uint64_t)k1);
+    return 0;
+}
+
+static uint32_t load_u32(const char *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+typedef struct { pgo_text_match *v; uint64_t n, cap; } match_vec;
+
+static int match_push(match_vec *mv, uint64_t src, uint64_t len, uint64_t dest) {
+    if (mv->n == mv->cap) {
+        const uint64_t nc = mv->cap ? mv->cap * 2 : 1024;
+        pgo_text_match *nv = (pgo_text_match *)realloc(mv->v, nc * sizeof *nv);
+        if (!nv) return -2;
+        mv->v = nv; mv->cap = nc;
+    }
+    mv->v[mv->n].src = src; mv->v[mv->n].len = len; mv->v[mv->n].dest = dest; mv->n++;
+    return 0;
+}
+
+/* One query position (the body shared by the grouped loop :375-418 and the tail loop :424-472).  Returns 1 when the
+ * query has to jump ahead (a push, or a position covered by the previous match), 0 otherwise, < 0 on error. */
+static int mem_query_position(const copmem_index *x, const char *start2, uint64_t N2, uint64_t q, uint32_t b0, uint32_t b1,
+                              int dest_is_src, int rev_compl, uint32_t min_len, uint32_t *l1, uint32_t *l2, uint32_t *r1,
+                              uint32_t *r2, match_vec *res, uint64_t *ext) {
+    const uint32_t K = x->K;
+    const int LK2 = ((int)x->L - (int)K) / 2, K_PLUS_LK24 = (int)K + LK2 - 4;
+    const char *start1 = x->text, *end1 = x->text + x->N, *end2 = start2 + N2;
+    const char *curr2 = start2 + q;
+    if (curr2 - LK2 >= start2) *l2 = load_u32(curr2 - LK2);
+    if (curr2 + K_PLUS_LK24 + 4 <= end2) *r2 = load_u32(curr2 + K_PLUS_LK24);
+    for (uint32_t j = b0; j < b1; j++) {
+        (*ext)++;
+        const uint64_t s = x->pos[j];
+        const char *curr1 = start1 + s;
+        if (dest_is_src && (rev_compl ? N2 - s < q : q >= s)) continue;                                        /* :384-386 */
+        if (res->n > 0 && q - s == res->v[res->n - 1].dest - res->v[res->n - 1].src &&
+            q + K < res->v[res->n - 1].dest + res->v[res->n - 1].len) return 1;                                /* :388-393 */
+        if (curr1 - LK2 >= start1) *l1 = load_u32(curr1 - LK2);
+        if (curr1 + K_PLUS_LK24 + 4 <= end1) *r1 = load_u32(curr1 + K_PLUS_LK24);
+        if (*r1 == *r2 || *l1 == *l2) {
+            const char *p1 = curr1 + K - 1, *p2 = curr2 + K - 1;
+            while (++p1 != end1 && ++p2 != end2 && *p1 == *p2) {}
+            const char *right = p1;
+            p1 = curr1; p2 = curr2;
+            while (p1 != start1 && p2 != start2 && *--p1 == *--p2) {}
+            if (right - p1 > (long)min_len && memcmp(curr1, curr2, K) == 0) {                                  /* :407 */
+                int rcode = match_push(res, (uint64_t)(p1 + 1 - start1), (uint64_t)(right - p1 - 1), (uint64_t)(p2 + 1 - start2));
+                return rcode ? rcode : 1;
+            }
+        }
+    }
+    return 0;
+}
+
+int pgo_match_texts(const char *src, uint64_t n, const char *dest, uint64_t n2, int dest_is_src, int rev_compl,
+                    uint32_t target_len, uint32_t min_len, uint64_t *out, uint64_t cap, uint64_t *count, uint64_t *params) {
+    copmem_index x;
+    memset(&x, 0, sizeof x);
+    if (!src || !dest || !count) return -1;
+    if (copmem_params2(&x, target_len, min_len, n) != 0 || n < x.K) return -1;
+    if (min_len > target_len) min_len = target_len;
+    if (min_len < x.K) return -1;                                             /* matchTexts :607-610 */
+    int rcode = copmem_build(&x, src);
+    if (rcode) { copmem_free(&x); return rcode; }
+    if (params) { params[0] = x.K; params[1] = x.k1; params[2] = x.k2; params[3] = x.hash_size; }
+    const uint32_t K = x.K, k2 = x.k2, MULTI = 256;
+    const uint64_t k2MULTI = (uint64_t)k2 * MULTI;
+    const int skip = (int)(K / x.k1) - 1;
+    uint32_t l1 = 0, l2 = 0, r1 = 0, r2 = 0;
+    uint64_t ext = 0;
+    match_vec res = {NULL, 0, 0};
+    uint32_t *h_arr = (uint32_t *)malloc(MULTI * sizeof(uint32_t));
+    uint64_t i1 = 0;
+    for (i1 = 0; i1 + K + k2MULTI < n2 + 1; i1 += k2MULTI) {                  /* :364-419 */
+        for (uint32_t t = 0; t < MULTI; t++) h_arr[t] = copmem_hash(&x, dest + i1 + (uint64_t)t * k2);
+        for (int64_t t = 0; t < (int64_t)MULTI; t++) {
+            const uint32_t b0 = x.cumm[h_arr[t]], b1 = x.cumm[h_arr[t] + 1];
+            if (b0 == b1) continue;
+            int r = mem_query_position(&x, dest, n2, i1 + (uint64_t)t * k2, b0, b1, dest_is_src, rev_compl, min_len, &l1, &l2, &r1, &r2, &res, &ext);
+            if (r < 0) { rcode = r; goto done; }
+            if (r) t += skip;                                                 /* curr2 += skipK2; i2 += skip */
+        }
+    }
+    for (; i1 + K < n2 + 1; i1 += k2) {                                       /* :422-473 */
+        const uint32_t h = copmem_hash(&x, dest + i1);
+        const uint32_t b0 = x.cumm[h], b1 = x.cumm[h + 1];
+        if (b0 == b1) continue;
+        int r = mem_query_position(&x, dest, n2, i1, b0, b1, dest_is_src, rev_compl, min_len, &l1, &l2, &r1, &r2, &res, &ext);
+        if (r < 0) { rcode = r; goto done; }
+        if (r) i1 += (uint64_t)skip * k2;
+    }
+    *count = res.n;
+    if (params) params[4] = ext;
+    if (res.n > cap) rcode = -3;
+    else for (uint64_t i = 0; i < res.n; i++) { out[3 * i] = res.v[i].src; out[3 * i + 1] = res.v[i].len; out[3 * i + 2] = res.v[i].dest; }
+done:
+    free(h_arr); free(res.v); copmem_free(&x);
+    return rcode;
+}

@@ -288,3 +288,74 @@ int pgref_pack_reads(const char* reads, uint32_t n, uint32_t read_len, int with_
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stage 7: exact matches between pseudogenomes.
+//   CopMEMMatcher(src, n, targetMatchLength, minMatchLength)   matching/copmem/CopMEMMatcher.cpp:571-593  (text index)
+//   CopMEMMatcher::matchTexts                                  :605-624 -> processExactMatchQueryTight :332-481
+//   SimplePgMatcher::markAndRemoveExactMatches                 matching/SimplePgMatcher.cpp:69-155
+#include "matching/SimplePgMatcher.h"
+#include "matching/copmem/CopMEMMatcher.h"
+
+extern "C" {
+
+// The raw vector matchTexts leaves in resMatches, in push order: out[3 i .. 3 i + 2] = {posSrcText, length, posDestText}.
+// `dest` is the text exactly as the matcher is handed it (SimplePgMatcher::exactMatchPg reverse-complements it first
+// when revComplMatching).  seconds[0] = index build (constructor), seconds[1] = matchTexts.  Returns 0; -1 bad
+// arguments (the reference would exit()); -3 capacity too small (*count is still set).
+int pgref_match_texts(const char* src, uint64_t n, const char* dest, uint64_t n2, int dest_is_src, int rev_compl,
+                      uint32_t target_len, uint32_t min_len, int threads, uint64_t* out, uint64_t cap, uint64_t* count,
+                      double* seconds) {
+    uint32_t mml = min_len > target_len ? target_len : min_len;
+    if (!src || !dest || mml < 24 || n < target_len) return -1;
+    CoutSilencer quiet;
+    if (threads > 0) { omp_set_num_threads(threads); PgHelpers::numberOfThreads = threads; }
+    auto t0 = std::chrono::steady_clock::now();
+    CopMEMMatcher m(src, n, target_len, min_len);
+    auto t1 = std::chrono::steady_clock::now();
+    std::vector<TextMatch> res;
+    std::string d(dest, n2);
+    auto t2 = std::chrono::steady_clock::now();
+    m.matchTexts(res, d, dest_is_src != 0, rev_compl != 0, mml);
+    auto t3 = std::chrono::steady_clock::now();
+    if (seconds) {
+        seconds[0] = std::chrono::duration<double>(t1 - t0).count();
+        seconds[1] = std::chrono::duration<double>(t3 - t2).count();
+    }
+    *count = res.size();
+    if (res.size() > cap) return -3;
+    for (size_t i = 0; i < res.size(); i++) {
+        out[3 * i] = res[i].posSrcText; out[3 * i + 1] = res[i].length; out[3 * i + 2] = res[i].posDestText;
+    }
+    return 0;
+}
+
+// The whole of SimplePgMatcher::markAndRemoveExactMatches for one destination pseudogenome: `dest` (n2 bytes, not
+// reverse-complemented: the class does that itself) is replaced by the mapped sequence (matches cut out, one '%' each),
+// *mapped_len = its new length; map_off / map_len = the two side streams (resPgMapOff, resPgMapLen).  dest_is_src: the
+// destination IS the source text (`dest` is ignored on input and receives the mapped source).
+int pgref_mark_matches(const char* src, uint64_t n, char* dest, uint64_t n2, int dest_is_src, int rev_compl,
+                       uint32_t target_len, uint32_t min_len, int threads, uint64_t* mapped_len,
+                       uint8_t* map_off, uint64_t off_cap, uint64_t* off_len, uint8_t* map_len, uint64_t len_cap, uint64_t* len_len,
+                       double* seconds) {
+    uint32_t mml = min_len > target_len ? target_len : min_len;
+    if (!src || !dest || mml < 24) return -1;
+    CoutSilencer quiet;
+    if (threads > 0) { omp_set_num_threads(threads); PgHelpers::numberOfThreads = threads; }
+    std::string s(src, n);
+    std::string d = dest_is_src ? std::string() : std::string(dest, n2);
+    std::string off, len;
+    auto t0 = std::chrono::steady_clock::now();
+    SimplePgMatcher matcher(s, target_len, min_len);
+    matcher.markAndRemoveExactMatches(dest_is_src != 0, dest_is_src ? s : d, off, len, rev_compl != 0, min_len);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const std::string& mapped = dest_is_src ? s : d;
+    *mapped_len = mapped.size(); *off_len = off.size(); *len_len = len.size();
+    if (mapped.size() > (dest_is_src ? n : n2) || off.size() > off_cap || len.size() > len_cap) return -3;
+    memcpy(dest, mapped.data(), mapped.size());
+    memcpy(map_off, off.data(), off.size());
+    memcpy(map_len, len.data(), len.size());
+    return 0;
+}
+
+}  // extern "C"

@@ -230,6 +230,47 @@ CONFIGS = {
 }
 
 
+# ---------------------------------------------------------------------------------------------
+# Stage 7 (exact matches between pseudogenomes): a source text and a destination text that
+# shares stretches with it.
+def pg_texts(seed: int, n: int, n2: int, max_copy: int = 3000, n_frac: float = 0.0, self_rc: int = 0,
+             adversarial: bool = True):
+    """(src, dest) ASCII uint8.  src: random ACGT with internal repeats (buckets of the text index with several
+    entries), tandem repeats and homopolymers (buckets cut at 13 entries), `self_rc` reverse-complement repeats (what the
+    HQ-vs-its-own-reverse-complement call finds); dest: random ACGT with copies of stretches of src of 20..max_copy
+    characters, forward and reverse-complemented, 0-2 substitutions each, copies that touch both ends of the texts, and
+    `n_frac` N symbols."""
+    rng = np.random.default_rng(seed)
+    src = random_genome(n, rng)
+    if adversarial:
+        for _ in range(n // 400):
+            l = int(rng.integers(40, 600)); a = int(rng.integers(0, n - l)); b = int(rng.integers(0, n - l))
+            src[b:b + l] = src[a:a + l].copy()
+        for _ in range(n // 3000 + 1):
+            l = int(rng.integers(60, 400)); b = int(rng.integers(0, n - l))
+            src[b:b + l] = np.resize(random_genome(int(rng.integers(1, 7)), rng), l)
+    for _ in range(self_rc):
+        l = int(rng.integers(30, 400)); a = int(rng.integers(0, n - l)); b = int(rng.integers(0, n - l))
+        src[b:b + l] = revcomp(src[a:a + l].copy())
+    dest = random_genome(n2, rng)
+    for _ in range(n2 // 250 + 2):
+        l = int(rng.integers(20, max(21, min(max_copy, n2)))); a = int(rng.integers(0, max(1, n - l))); l = min(l, n - a)
+        b = int(rng.integers(0, n2))
+        seg = src[a:a + l].copy()
+        if rng.random() < 0.5:
+            seg = revcomp(seg)
+        for _ in range(int(rng.integers(0, 3))):
+            seg[int(rng.integers(0, l))] = _CODE2ASCII[int(rng.integers(0, 4))]
+        m = min(l, n2 - b)
+        dest[b:b + m] = seg[:m]
+    l = min(200, n2, n)
+    dest[:l] = src[:l]
+    dest[n2 - l:] = src[n - l:]
+    if n_frac > 0:
+        dest[rng.random(n2) < n_frac] = _N
+    return src, dest
+
+
 def scaled_config(name: str, scale: float = 1.0) -> dict:
     c = dict(CONFIGS[name])
     c["genome_len"] = max(2000, int(c["genome_len"] * scale))
