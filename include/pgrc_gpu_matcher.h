@@ -304,6 +304,36 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
                   uint32_t min_chars_per_mismatch, char pre_mode, char mode, int rev_compl,
                   uint64_t *out_pos, uint8_t *out_rc, uint8_t *out_mm, pgm_stats *stats);
 
+/* ---- stage 7: exact matches between pseudogenomes ------------------------------------
+ * Replaces CopMEMMatcher as SimplePgMatcher uses it (matching/SimplePgMatcher.cpp:11-55; the TextMatcher interface,
+ * matching/TextMatchers.h:54-61).  The source text is the context's text (pgm_set_text; whole text, alphabet ACGT).
+ *   pgm_mem_index  = the constructor CopMEMMatcher(srcText, srcLength, targetMatchLength, minMatchLength)
+ *                    (copmem/CopMEMMatcher.cpp:571-593): parameters K, k1, k2, hash size (initParams / calcCoprimes,
+ *                    :69-137) and the index of every k1-th source position (processRef, :176-231 — the SERIAL build,
+ *                    i.e. the reference at -t 1; its multithreaded build orders the buckets differently and races).
+ *                    PGM_ERR_UNSUPPORTED where the reference exits (minimal matching length below 24, K outside its
+ *                    hash-function table).  params (optional): K, k1, k2, hash size.
+ *   pgm_mem_match  = matchTexts(resMatches, destText, destIsSrc, revComplMatching, minMatchLength) (:605-624 ->
+ *                    processExactMatchQueryTight, :332-481).  `dest` is the text as the matcher receives it — already
+ *                    reverse-complemented by the caller when rev_compl (SimplePgMatcher::exactMatchPg, :33-43) — host
+ *                    or device memory, any byte values (symbols outside ACGT match nothing).  dest = NULL with
+ *                    dest_is_src: the library takes the source text itself (rev_compl = 0) or its reverse complement
+ *                    (rev_compl != 0) from the planes it already holds.  *count = resMatches.size().
+ *   pgm_mem_get_matches = resMatches in the reference's push order, `capacity` >= count elements, host or device.
+ * min_match_length is clamped to target_match_length as in the reference (:574-575; PgRC passes UINT32_MAX).  A minimal
+ * length BELOW the target is PGM_ERR_UNSUPPORTED: the reference's 4-byte guards (:396-398) then reject candidates
+ * depending on values left over from earlier candidates, which only a sequential replay reproduces; it is unreachable
+ * from pgrc-encoder.cpp:240-245. */
+typedef struct pgm_text_match {      /* = PgTools::TextMatch, matching/TextMatchers.h:11-14 */
+    uint64_t pos_src_text;
+    uint64_t length;
+    uint64_t pos_dest_text;
+} pgm_text_match;
+int pgm_mem_index(pgm_ctx *ctx, uint32_t target_match_length, uint32_t min_match_length, uint32_t *params /*[4] or NULL*/);
+int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
+                  uint32_t min_match_length, uint64_t *count);
+int pgm_mem_get_matches(pgm_ctx *ctx, pgm_text_match *out, uint64_t capacity);
+
 /* ---- introspection (bench / tests) -------------------------------------------------------*/
 /* Number of kernels this context has launched so far. */
 uint64_t pgm_kernel_launches(const pgm_ctx *ctx);
@@ -316,6 +346,7 @@ enum { PGM_K_PACK_TEXT = 0, PGM_K_RC_TEXT, PGM_K_UNPACK_READS, PGM_K_INIT_STATE,
        PGM_K_SCAN_FILTER, PGM_K_SCAN_PROBE, PGM_K_SCAN_VERIFY, /* the three stages of the L2-blocked scan pipeline */
        PGM_K_MISMATCHES, PGM_K_COPMEM_INDEX, PGM_K_COPMEM_QUERY,
        PGM_K_ROUTE_BUILD, PGM_K_ROUTE_SCAN, PGM_K_ROUTE_PROBE, PGM_K_ROUTE_VERIFY, /* the routed multi-GPU scheme */
+       PGM_K_MEM_PACK, PGM_K_MEM_QUERY, PGM_K_MEM_EMIT,                            /* stage 7 (the index is PGM_K_COPMEM_INDEX) */
        PGM_K_COUNT };
 typedef struct pgm_timings {
     double ms[PGM_K_COUNT];

@@ -27,11 +27,12 @@ EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pg
            "pgm_route_verify",
            "pgm_group_create", "pgm_group_destroy", "pgm_group_last_error", "pgm_group_size", "pgm_group_set_text", "pgm_group_set_reads",
            "pgm_group_upload", "pgm_group_match_begin", "pgm_group_pass", "pgm_group_copmem_begin", "pgm_group_copmem_pass",
-           "pgm_group_get_results", "pgm_group_get_mismatches"]
+           "pgm_group_get_results", "pgm_group_get_mismatches",
+           "pgm_mem_index", "pgm_mem_match", "pgm_mem_get_matches"]
 
 KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators",
                 "scan_filter", "scan_probe", "scan_verify", "mismatches", "copmem_index", "copmem_query",
-                "route_build", "route_scan", "route_probe", "route_verify"]
+                "route_build", "route_scan", "route_probe", "route_verify", "mem_pack", "mem_query", "mem_emit"]
 PGM_ROUTE_MAX_WORLD = 16
 PGM_ROUTE_PATTERNS, PGM_ROUTE_WINDOWS, PGM_ROUTE_CANDIDATES = 0, 1, 2
 
@@ -139,5 +140,8 @@ def load() -> ctypes.CDLL:
     lib.pgm_group_copmem_pass.restype = ci; lib.pgm_group_copmem_pass.argtypes = [vp, ci]
     lib.pgm_group_get_results.restype = ci; lib.pgm_group_get_results.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PgmStats)]
     lib.pgm_group_get_mismatches.restype = ci; lib.pgm_group_get_mismatches.argtypes = [vp, vp, vp, vp, u64, ctypes.POINTER(u64)]
+    lib.pgm_mem_index.restype = ci; lib.pgm_mem_index.argtypes = [vp, u32, u32, ctypes.POINTER(u32)]
+    lib.pgm_mem_match.restype = ci; lib.pgm_mem_match.argtypes = [vp, vp, u64, ci, ci, u32, ctypes.POINTER(u64)]
+    lib.pgm_mem_get_matches.restype = ci; lib.pgm_mem_get_matches.argtypes = [vp, vp, u64]
     _lib = lib
     return lib

@@ -5,6 +5,7 @@
 #include "pgm_kernels.cuh"
 #include "pgm_blocked.cuh"
 #include "pgm_copmem.cuh"
+#include "pgm_mem.cuh"
 #include "pgm_routed.cuh"
 
 #include <algorithm>
@@ -90,6 +91,12 @@ struct pgm_ctx {
     DevBuf cm_count, cm_start, cm_cumm, cm_fill, cm_hash, cm_all, cm_entries, cm_sums;
     uint32_t cm_K = 0, cm_k1 = 0, cm_k2 = 0, cm_hash_size = 0;
     bool copmem_active = false;
+    // stage 7 (pgm_mem.cuh): index of the context's text in the cm_* buffers + the destination text and the match lists
+    DevBuf mem_dlo, mem_dhi, mem_dinv, mem_stage, mem_fv, mem_has, mem_emit, mem_gcount, mem_gstart, mem_raw, mem_rawq, mem_keep, mem_kstart, mem_out;
+    bool mem_index_valid = false;
+    uint32_t mem_L = 0, mem_K = 0, mem_k1 = 0, mem_k2 = 0, mem_hash_size = 0;
+    uint64_t mem_count = 0;
+    bool mem_result_valid = false;
     uint32_t bq_cap = 0, bq_region_bits = 0;
     bool bq_pending = false;    // region queues hold patterns that build_insert_kernel has not inserted yet
     uint64_t n_slots = 0;
@@ -585,6 +592,8 @@ void pgm_destroy(pgm_ctx *ctx) {
                       &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->mis_sums, &ctx->mis_offsets, &ctx->mis_pos, &ctx->mis_syms,
                       &ctx->rt_win_send2[0], &ctx->rt_win_send2[1], &ctx->rt_win_recv2[0], &ctx->rt_win_recv2[1], &ctx->rt_cand_send2[0],
                       &ctx->rt_cand_send2[1], &ctx->rt_cand_recv2[0], &ctx->rt_cand_recv2[1], &ctx->rt_pat_recv, &ctx->rt_counters, &ctx->rt_live, &ctx->rt_live_count,
+                      &ctx->mem_dlo, &ctx->mem_dhi, &ctx->mem_dinv, &ctx->mem_stage, &ctx->mem_fv, &ctx->mem_has, &ctx->mem_emit, &ctx->mem_gcount,
+                      &ctx->mem_gstart, &ctx->mem_raw, &ctx->mem_rawq, &ctx->mem_keep, &ctx->mem_kstart, &ctx->mem_out,
                       &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
@@ -705,6 +714,7 @@ int pgm_set_text_shard(pgm_ctx *ctx, const char *slice, uint64_t slice_begin, ui
     ctx->pg_len = pg_len; ctx->slice_begin = slice_begin; ctx->slice_len = slice_len;
     ctx->own_begin = own_begin; ctx->own_end = own_end;
     ctx->has_text = true;
+    ctx->mem_index_valid = false; ctx->mem_result_valid = false;
     ctx->text_pending = false; ctx->text_copies_enqueued = false; ctx->h_text = nullptr;
     CU(cudaMemsetAsync(ctx->err_flag.p, 0, sizeof(int), ctx->stream));   // a new text: the symbol check starts over
     if (!slice_len) return PGM_OK;
@@ -1230,6 +1240,7 @@ int pgm_copmem_pass(pgm_ctx *ctx, int rev_mode) {
     cp.entries = ctx->cm_entries.as<uint32_t>();
     cp.reads = reads_view(ctx); cp.n_reads = n; cp.max_mm = ctx->max_mm; cp.min_mm = ctx->min_mm; cp.rev_mode = rev_mode ? 1 : 0;
     // the index of this pass's text: new CopMEMMatcher(pgPtr, pgLength, partLength) (ReadsMatchers.cpp:424)
+    ctx->mem_index_valid = false;      // (stage 7 keeps its index in the same buffers)
     CU(cudaMemsetAsync(cp.count, 0, (hs + 1) * 4, ctx->stream));
     if (cp.n_sampled)
         KLAUNCH(PGM_K_COPMEM_INDEX, "cm_hash_kernel", pgm::cm_hash_kernel<<<grid_for(cp.n_sampled, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
@@ -1832,3 +1843,193 @@ int pgm_map_reads(pgm_ctx *ctx, uint32_t match_prefix_length, uint32_t pre_seed,
 } // extern "C"
 
 #include "pgm_group.inl"
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stage 7: exact matches between pseudogenomes (pgm_mem.cuh)
+namespace {
+
+// initParams + calcCoprimes (copmem/CopMEMMatcher.cpp:69-137) for targetMatchLength = L and a minimal matching length;
+// false where the reference exits or would call a null entry of its hash-function table (:54-63)
+bool mem_derive(uint32_t L, uint32_t min_len, uint64_t N, uint32_t &K, uint32_t &k1, uint32_t &k2, uint32_t &hash_size) {
+    if (min_len > L) min_len = L;                            // constructor, :574-575
+    if (min_len < 24 || L > 0xFFFF) return false;
+    int k;
+    if (L > 110) k = 56; else if (L > 62) k = 44; else if (L > 53) k = 40; else if (L > 46) k = 36;
+    else if (L > 42) k = 32; else if (L > 32) k = 28; else k = ((int)L / 4 - 1) * 4;
+    k = std::min(k, ((int)min_len / 4 - 1) * 4);
+    if (!(k == 20 || k == 24 || k == 28 || k == 32 || k == 36 || k == 40 || k == 44 || k == 56)) return false;
+    const int t = (int)L - k + 1;
+    if (t <= 0) return false;
+    int a, b;
+    if (t >= 20) {
+        a = 1; while ((a + 1) * (a + 1) <= t) a++;
+        a += 1; b = a - 1;
+        if (a * b > t) { --b; --a; }
+    } else if (t >= 15) { a = 5; b = 3; } else if (t >= 12) { a = 4; b = 3; } else if (t >= 10) { a = 5; b = 2; }
+    else if (t >= 6) { a = 3; b = 2; } else { a = t; b = 1; }
+    K = (uint32_t)k; k1 = (uint32_t)a; k2 = (uint32_t)b;
+    int i = 24;
+    do { hash_size = 1u << (i++); } while (i <= 31 && hash_size < N / (uint64_t)a);
+    return true;
+}
+
+} // namespace
+
+extern "C" {
+
+int pgm_mem_index(pgm_ctx *ctx, uint32_t target_match_length, uint32_t min_match_length, uint32_t *params) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->has_text) return fail(ctx, PGM_ERR_STATE, "pgm_mem_index: set the text first");
+    if (ctx->slice_begin != 0 || ctx->slice_len != ctx->pg_len)
+        return fail(ctx, PGM_ERR_STATE, "pgm_mem_index: needs the whole text on this GPU (not a text shard)");
+    const uint64_t N = ctx->pg_len;
+    uint32_t K, k1, k2, hs;
+    if (!mem_derive(target_match_length, min_match_length, N, K, k1, k2, hs))
+        return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_mem_index: the reference exits for these lengths (minimal matching length below 24, "
+                                              "L and K mismatch, or no hash function for K)");
+    // With minMatchLength < targetMatchLength the reference's 4-byte guards (l1/l2/r1/r2, CopMEMMatcher.cpp:396-398) can reject
+    // candidates that would extend far enough, and near the text ends they hold values left over from earlier candidates:
+    // sequential state the order-free kernels do not carry.  PgRC never asks for it (pgrc-encoder.cpp:240-245 passes the target only).
+    if (min_match_length < target_match_length)
+        return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_mem_index: minimal matching length below the target match length is not covered "
+                                              "(unreachable from pgrc-encoder.cpp:240-245)");
+    if (N < target_match_length) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_mem_index: source text shorter than the target match length "
+                                                                        "(SimplePgMatcher creates no matcher then, SimplePgMatcher.cpp:15)");
+    if (N / k1 >= 0xFFFFFFF0ull) return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_mem_index: text too long for 32-bit sample indices");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = finish_text_upload(ctx))) return rc;
+    pgm::CopmemParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.tlo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS;
+    cp.thi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
+    cp.pg_len = N;
+    cp.K = K; cp.k1 = k1; cp.k2 = k2; cp.hash_mask = hs - 1;
+    cp.n_sampled = (uint32_t)((N - K) / k1 + 1);
+    const size_t hsz = hs;
+    if ((rc = ensure(ctx, ctx->cm_count, (hsz + 1) * 4)) || (rc = ensure(ctx, ctx->cm_start, (hsz + 1) * 4)) ||
+        (rc = ensure(ctx, ctx->cm_cumm, (hsz + 2) * 4)) || (rc = ensure(ctx, ctx->cm_fill, (size_t)cp.n_sampled * 4)) ||
+        (rc = ensure(ctx, ctx->cm_hash, (size_t)cp.n_sampled * 4)) || (rc = ensure(ctx, ctx->cm_all, (size_t)cp.n_sampled * 4)) ||
+        (rc = ensure(ctx, ctx->cm_entries, (size_t)cp.n_sampled * 4))) return rc;
+    cp.count = ctx->cm_count.as<uint32_t>(); cp.start_all = ctx->cm_start.as<uint32_t>(); cp.cumm = ctx->cm_cumm.as<uint32_t>();
+    cp.sample_rank = ctx->cm_fill.as<uint32_t>(); cp.sample_hash = ctx->cm_hash.as<uint32_t>(); cp.all_entries = ctx->cm_all.as<uint32_t>();
+    cp.entries = ctx->cm_entries.as<uint32_t>();
+    ctx->copmem_active = false;
+    CU(cudaMemsetAsync(cp.count, 0, (hsz + 1) * 4, ctx->stream));
+    KLAUNCH(PGM_K_COPMEM_INDEX, "cm_hash_kernel", pgm::cm_hash_kernel<<<grid_for(cp.n_sampled, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
+    if ((rc = device_scan<0>(ctx, cp.count, (uint32_t)hsz, cp.start_all)) ||
+        (rc = device_scan<PGM_CM_COLLISIONS_LIMIT + 1>(ctx, cp.count, (uint32_t)hsz, cp.cumm))) return rc;
+    KLAUNCH(PGM_K_COPMEM_INDEX, "cm_scatter_kernel", pgm::cm_scatter_kernel<<<grid_for(cp.n_sampled, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
+    KLAUNCH(PGM_K_COPMEM_INDEX, "cm_select_kernel", pgm::cm_select_kernel<<<grid_for(hsz, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, ctx->err_flag.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (bad) return fail(ctx, PGM_ERR_BAD_SYMBOL, "pgm_mem_index: the source text contains a symbol outside ACGT");
+    ctx->mem_L = target_match_length; ctx->mem_K = K; ctx->mem_k1 = k1; ctx->mem_k2 = k2; ctx->mem_hash_size = hs;
+    ctx->mem_index_valid = true;
+    ctx->mem_result_valid = false;
+    if (params) { params[0] = K; params[1] = k1; params[2] = k2; params[3] = hs; }
+    return PGM_OK;
+}
+
+int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
+                  uint32_t min_match_length, uint64_t *count) {
+    if (!ctx || !count) return PGM_ERR_INVALID_ARG;
+    if (!ctx->mem_index_valid) return fail(ctx, PGM_ERR_STATE, "pgm_mem_match: pgm_mem_index has not been called for the current text");
+    if (!dest && !dest_is_src) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_mem_match: destination text is null");
+    const uint64_t N = ctx->pg_len;
+    if (!dest) dest_len = N;
+    if (dest_is_src && dest_len != N) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_mem_match: dest_is_src with a destination of another length");
+    if (min_match_length > ctx->mem_L) min_match_length = ctx->mem_L;
+    if (min_match_length < ctx->mem_L)
+        return fail(ctx, PGM_ERR_UNSUPPORTED, "pgm_mem_match: minimal matching length below the target match length is not covered (see pgm_mem_index)");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    ctx->mem_result_valid = false;
+    pgm::MemParams mp;
+    memset(&mp, 0, sizeof mp);
+    mp.slo = ctx->f_lo.as<uint32_t>() + PGM_PAD_WORDS; mp.shi = ctx->f_hi.as<uint32_t>() + PGM_PAD_WORDS;
+    mp.N = N; mp.N2 = dest_len;
+    mp.K = ctx->mem_K; mp.k1 = ctx->mem_k1; mp.k2 = ctx->mem_k2; mp.hash_mask = ctx->mem_hash_size - 1;
+    mp.min_len = min_match_length; mp.skip = mp.K / mp.k1 - 1;
+    mp.dest_is_src = dest_is_src ? 1 : 0; mp.rev_compl = rev_compl ? 1 : 0;
+    mp.cumm = ctx->cm_cumm.as<uint32_t>(); mp.entries = ctx->cm_entries.as<uint32_t>();
+    if (!dest) {
+        mp.dlo = (rev_compl ? ctx->r_lo : ctx->f_lo).as<uint32_t>() + PGM_PAD_WORDS;
+        mp.dhi = (rev_compl ? ctx->r_hi : ctx->f_hi).as<uint32_t>() + PGM_PAD_WORDS;
+        mp.dinv = nullptr;
+    } else {
+        const size_t pb = plane_bytes(dest_len);
+        if ((rc = ensure(ctx, ctx->mem_dlo, pb)) || (rc = ensure(ctx, ctx->mem_dhi, pb)) || (rc = ensure(ctx, ctx->mem_dinv, pb))) return rc;
+        CU(cudaMemsetAsync(ctx->mem_dlo.p, 0, pb, ctx->stream));
+        CU(cudaMemsetAsync(ctx->mem_dhi.p, 0, pb, ctx->stream));
+        CU(cudaMemsetAsync(ctx->mem_dinv.p, 0, pb, ctx->stream));
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(dest);
+        if (dest_len && !is_device_ptr(dest)) {
+            if ((rc = ensure(ctx, ctx->mem_stage, dest_len))) return rc;
+            CU(cudaMemcpyAsync(ctx->mem_stage.p, dest, dest_len, cudaMemcpyHostToDevice, ctx->stream));
+            src = ctx->mem_stage.as<uint8_t>();
+        }
+        uint32_t *dlo = ctx->mem_dlo.as<uint32_t>() + PGM_PAD_WORDS, *dhi = ctx->mem_dhi.as<uint32_t>() + PGM_PAD_WORDS,
+                 *dinv = ctx->mem_dinv.as<uint32_t>() + PGM_PAD_WORDS;
+        if (dest_len)
+            KLAUNCH(PGM_K_MEM_PACK, "mem_pack_kernel", pgm::mem_pack_kernel<<<grid_for((dest_len + 31) / 32, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(
+                src, dest_len, dlo, dhi, dinv));
+        mp.dlo = dlo; mp.dhi = dhi; mp.dinv = dinv;
+    }
+    ctx->mem_count = 0;
+    *count = 0;
+    if (dest_len < mp.K) { ctx->mem_result_valid = true; return PGM_OK; }
+    mp.nq = (dest_len - mp.K) / mp.k2 + 1;
+    // groups of the main loop: i1 = g * k2 * 256 while i1 + K + k2 * 256 < N2 + 1 (CopMEMMatcher.cpp:364)
+    const uint64_t span = (uint64_t)mp.k2 * PGM_MEM_GROUP;
+    mp.n_groups = dest_len + 1 > mp.K + span ? (dest_len - mp.K - span) / span + 1 : 0;
+    const size_t mask_words = (size_t)((mp.nq + 31) / 32 + 8);
+    if ((rc = ensure(ctx, ctx->mem_fv, (size_t)mp.nq * 4)) || (rc = ensure(ctx, ctx->mem_has, mask_words * 4)) ||
+        (rc = ensure(ctx, ctx->mem_emit, mask_words * 4)) || (rc = ensure(ctx, ctx->mem_gcount, (size_t)(mp.n_groups + 2) * 4)) ||
+        (rc = ensure(ctx, ctx->mem_gstart, (size_t)(mp.n_groups + 2) * 4))) return rc;
+    mp.fv = ctx->mem_fv.as<uint32_t>(); mp.has_fv = ctx->mem_has.as<uint32_t>(); mp.emit = ctx->mem_emit.as<uint32_t>();
+    mp.group_count = ctx->mem_gcount.as<uint32_t>(); mp.group_start = ctx->mem_gstart.as<uint32_t>();
+    CU(cudaMemsetAsync(mp.has_fv, 0, mask_words * 4, ctx->stream));
+    CU(cudaMemsetAsync(mp.emit, 0, mask_words * 4, ctx->stream));
+    KLAUNCH(PGM_K_MEM_QUERY, "mem_query_kernel", pgm::mem_query_kernel<<<grid_for(mp.nq, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(mp));
+    KLAUNCH(PGM_K_MEM_EMIT, "mem_walk_kernel", pgm::mem_walk_kernel<<<grid_for(mp.n_groups + 1, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(mp));
+    if ((rc = device_scan<0>(ctx, mp.group_count, (uint32_t)(mp.n_groups + 1), ctx->mem_gstart.as<uint32_t>()))) return rc;
+    uint32_t n_raw = 0;
+    CU(cudaMemcpyAsync(&n_raw, ctx->mem_gstart.as<uint32_t>() + mp.n_groups + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    mp.n_raw = n_raw;
+    if (n_raw) {
+        if ((rc = ensure(ctx, ctx->mem_raw, (size_t)n_raw * sizeof(pgm::MemMatch))) || (rc = ensure(ctx, ctx->mem_rawq, (size_t)n_raw * 8)) ||
+            (rc = ensure(ctx, ctx->mem_keep, (size_t)n_raw * 4)) || (rc = ensure(ctx, ctx->mem_kstart, ((size_t)n_raw + 1) * 4)) ||
+            (rc = ensure(ctx, ctx->mem_out, (size_t)n_raw * sizeof(pgm::MemMatch)))) return rc;
+        mp.raw = ctx->mem_raw.as<pgm::MemMatch>(); mp.raw_q = ctx->mem_rawq.as<uint64_t>(); mp.keep = ctx->mem_keep.as<uint32_t>();
+        mp.keep_start = ctx->mem_kstart.as<uint32_t>(); mp.out = ctx->mem_out.as<pgm::MemMatch>();
+        KLAUNCH(PGM_K_MEM_EMIT, "mem_extend_kernel", pgm::mem_extend_kernel<<<grid_for((mp.nq + 31) / 32, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(mp));
+        KLAUNCH(PGM_K_MEM_EMIT, "mem_flag_kernel", pgm::mem_flag_kernel<<<grid_for(n_raw, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(mp));
+        if ((rc = device_scan<0>(ctx, mp.keep, n_raw, ctx->mem_kstart.as<uint32_t>()))) return rc;
+        KLAUNCH(PGM_K_MEM_EMIT, "mem_compact_kernel", pgm::mem_compact_kernel<<<grid_for(n_raw, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(mp));
+        uint32_t n_out = 0;
+        CU(cudaMemcpyAsync(&n_out, ctx->mem_kstart.as<uint32_t>() + n_raw, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->mem_count = n_out;
+    }
+    *count = ctx->mem_count;
+    ctx->mem_result_valid = true;
+    return PGM_OK;
+}
+
+int pgm_mem_get_matches(pgm_ctx *ctx, pgm_text_match *out, uint64_t capacity) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->mem_result_valid) return fail(ctx, PGM_ERR_STATE, "pgm_mem_get_matches: no result (call pgm_mem_match)");
+    if (capacity < ctx->mem_count || (ctx->mem_count && !out)) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_mem_get_matches: capacity below the match count");
+    if (!ctx->mem_count) return PGM_OK;
+    CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(pgm_text_match) == sizeof(pgm::MemMatch), "layout");
+    CU(cudaMemcpyAsync(out, ctx->mem_out.p, (size_t)ctx->mem_count * sizeof(pgm_text_match), cudaMemcpyDefault, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PGM_OK;
+}
+
+} // extern "C"

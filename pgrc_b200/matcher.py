@@ -334,6 +334,49 @@ class GpuReadsMatcher:
         return self._result(out, st)
 
 
+class GpuTextMatcher:
+    """Stage 7: the reference's TextMatcher interface (matching/TextMatchers.h:54-61) as
+    CopMEMMatcher implements it for SimplePgMatcher (copmem/CopMEMMatcher.cpp:571-624), on the GPU.
+
+        GpuTextMatcher(src_text, target_match_length[, min_match_length])   <->  CopMEMMatcher(srcText, srcLength, ...)
+        .match_texts(dest_text, dest_is_src, rev_compl_matching, min_match_length)  <->  matchTexts(resMatches, ...)
+
+    match_texts returns resMatches as an (n, 3) uint64 array {posSrcText, length, posDestText} in the reference's push
+    order.  `dest_text` is what the matcher is handed (SimplePgMatcher::exactMatchPg reverse-complements it beforehand when
+    rev_compl_matching); dest_text=None with dest_is_src takes the source (or its reverse complement) already on the GPU."""
+
+    def __init__(self, src_text, target_match_length: int, min_match_length: int = 0xFFFFFFFF, device: int = 0, matcher=None):
+        self._own = matcher is None
+        self.m = matcher if matcher is not None else GpuReadsMatcher(device)
+        if src_text is not None:
+            self.m.set_text(src_text)
+        par = (ctypes.c_uint32 * 4)()
+        self.m._check(self.m._lib.pgm_mem_index(self.m._h, target_match_length, min(min_match_length, 0xFFFFFFFF), par))
+        self.K, self.k1, self.k2, self.hash_size = (int(x) for x in par)
+        self.target_match_length = target_match_length
+
+    def match_texts(self, dest_text, dest_is_src: bool = False, rev_compl_matching: bool = True,
+                    min_match_length: int = 0xFFFFFFFF) -> np.ndarray:
+        n2 = 0 if dest_text is None else (dest_text.numel() if hasattr(dest_text, "numel") else dest_text.size)
+        cnt = ctypes.c_uint64(0)
+        self.m._check(self.m._lib.pgm_mem_match(self.m._h, _ptr(dest_text), n2, int(dest_is_src), int(rev_compl_matching),
+                                                min(min_match_length, 0xFFFFFFFF), ctypes.byref(cnt)))
+        out = np.empty((int(cnt.value), 3), np.uint64)
+        self.m._check(self.m._lib.pgm_mem_get_matches(self.m._h, out.ctypes.data if out.size else None, int(cnt.value)))
+        return out
+
+    def close(self):
+        if self._own and self.m is not None:
+            self.m.close()
+        self.m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 class GpuMatcherGroup:
     """Several GPUs behind one handle, inside one process (wraps ``pgm_group``; what the C++ host side of PgRC uses:
     pgrc_b200/host/GpuReadsMatchers.cpp).  Modes 'd'/'D' run the routed scheme with peer-to-peer copies over NVLink,

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Stage 7 (exact matches between pseudogenomes) on a bench-workload text: the HQ pseudogenome against its own reverse
+complement (SimplePgMatcher::markAndRemoveExactMatches(true, hqPg, ..., revComplMatching = true), SimplePgMatcher.cpp:196)
+and a destination text built from it (stretches of the source, reverse-complemented blockwise, with substitutions), GPU
+(pgm_mem_*) and — on a bounded sample — the reference's CopMEMMatcher on the host cores.  Prints one JSON line.
+
+    python tools/pgmatch_bench.py [--workload c2] [--scale 1.0] [--ref-scale 0.1] [--check]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--ref-scale", type=float, default=0.1, help="fraction of the text the CPU reference is timed on (0 = skip)")
+    ap.add_argument("--target", type=int, default=45, help="targetPgMatchLength (PgRC default 45)")
+    ap.add_argument("--check", action="store_true", help="compare the GPU result with the sequential oracle (small scales only)")
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    from pgrc_b200 import matcher, synth
+    dev = torch.device("cuda", 0)
+    cfg = synth.scaled_config(args.workload, args.scale)
+    gp = synth.hashed_params(**cfg, seed=20261017)
+    src_d = synth.hashed_text(gp, 0, int(gp.text_len), dev)
+    n = int(src_d.numel())
+    # destination: a third of the source length, blocks of 2000 characters taken from the source at a stride of three
+    # blocks, every other one reverse-complemented, 0.3 % substitutions
+    comp = torch.arange(256, dtype=torch.uint8, device=dev)
+    for a, b in ("AT", "CG", "GC", "TA"):
+        comp[ord(a)] = ord(b)
+    blk = 2000
+    nb = n // (3 * blk)
+    d = src_d[: nb * 3 * blk].view(nb, 3, blk)[:, 0, :].clone()
+    d[1::2] = comp[d[1::2].long()].flip(1)
+    dest_d = d.reshape(-1)
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    sub = torch.rand(dest_d.numel(), device=dev, generator=g) < 0.003
+    acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    dest_d[sub] = acgt[torch.randint(0, 4, (int(sub.sum()),), device=dev, generator=g)]
+    dest_rc_d = comp[dest_d.long()].flip(0).contiguous()          # what exactMatchPg hands to the matcher (:39-41)
+    torch.cuda.synchronize()
+
+    m = matcher.GpuReadsMatcher(0)
+    out = {"workload": args.workload, "scale": args.scale, "src_bases": n, "dest_bases": int(dest_d.numel()), "target_len": args.target}
+    m.set_text(src_d)
+    m.synchronize()
+    def timed(fn):
+        best = None
+        for _ in range(args.reps):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best, r
+    t_index, tm = timed(lambda: matcher.GpuTextMatcher(None, args.target, matcher=m))
+    out["params"] = {"K": tm.K, "k1": tm.k1, "k2": tm.k2, "hash_size": tm.hash_size}
+    out["index_ms"] = round(t_index * 1e3, 3)
+    t_self, r_self = timed(lambda: tm.match_texts(None, True, True))
+    t_lq, r_lq = timed(lambda: tm.match_texts(dest_rc_d, False, True))
+    out["self_rc"] = {"ms": round(t_self * 1e3, 3), "matches": int(len(r_self)), "gbases_per_s": round(n / t_self / 1e9, 3)}
+    out["lq"] = {"ms": round(t_lq * 1e3, 3), "matches": int(len(r_lq)), "gbases_per_s": round(int(dest_d.numel()) / t_lq / 1e9, 3)}
+    # host inputs (what the C++ shim passes): the upload of the destination is inside
+    dest_rc_h = dest_rc_d.cpu().numpy()
+    t_lq_h, r_lq_h = timed(lambda: tm.match_texts(dest_rc_h, False, True))
+    assert np.array_equal(r_lq_h, r_lq)
+    out["lq_host_input"] = {"ms": round(t_lq_h * 1e3, 3)}
+    m.set_profiling(True); m.timings()
+    matcher.GpuTextMatcher(None, args.target, matcher=m); tm.match_texts(None, True, True); tm.match_texts(dest_rc_d, False, True)
+    out["kernel_ms"] = {k: round(v[0], 3) for k, v in m.timings().items() if v[1]}
+    m.set_profiling(False)
+    if args.check:
+        import oracle
+        src_h = src_d.cpu().numpy()
+        w_self = oracle.oracle_match_texts(src_h, oracle.reverse_complement(src_h), True, True, args.target)
+        w_lq = oracle.oracle_match_texts(src_h, dest_rc_h, False, True, args.target)
+        out["check"] = {"self_equal": bool(np.array_equal(w_self, r_self)), "lq_equal": bool(np.array_equal(w_lq, r_lq))}
+    if args.ref_scale > 0:
+        import oracle
+        if oracle.have_ref():
+            k = max(100000, int(n * args.ref_scale))
+            src_h = src_d[:k].cpu().numpy()
+            dst_h = dest_rc_d[: max(30000, int(dest_d.numel() * args.ref_scale))].cpu().numpy()
+            ref = {}
+            for threads in (1, os.cpu_count() or 1):
+                secs = [0, 0]
+                r = oracle.ref_match_texts(src_h, oracle.reverse_complement(src_h), True, True, args.target, threads=threads, seconds=secs)
+                secs2 = [0, 0]
+                r2 = oracle.ref_match_texts(src_h, dst_h, False, True, args.target, threads=threads, seconds=secs2)
+                ref[f"t{threads}"] = {"src_bases": int(k), "dest_bases": int(dst_h.size), "index_s": round(secs[0], 3), "self_rc_s": round(secs[1], 3),
+                                      "lq_s": round(secs2[1], 3), "self_matches": int(len(r)), "lq_matches": int(len(r2)),
+                                      "self_gbases_per_s": round(k / secs[1] / 1e9, 4), "lq_gbases_per_s": round(dst_h.size / secs2[1] / 1e9, 4)}
+            out["reference_cpu"] = ref
+    tm.close(); m.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
