@@ -28,12 +28,13 @@ def _fastq(tmp, name, pair=False, **kw):
     return out, out2
 
 
-def _compress(tmp, tag, gpu, fastq, fastq2, flags, devices=None, env_matcher="1"):
+def _compress(tmp, tag, gpu, fastq, fastq2, flags, devices=None, env_matcher="1", env_extra=None):
     d = os.path.join(tmp, tag)
     os.makedirs(d)
     env = dict(os.environ)
-    for k in ("PGRC_GPU_MATCHER", "PGRC_GPU_DEVICES", "PGRC_GPU_DEVICE"):
+    for k in ("PGRC_GPU_MATCHER", "PGRC_GPU_DEVICES", "PGRC_GPU_DEVICE", "PGRC_GPU_PGMATCH"):
         env.pop(k, None)
+    env.update(env_extra or {})
     if gpu and env_matcher is not None:
         env["PGRC_GPU_MATCHER"] = env_matcher
     if devices:
@@ -77,7 +78,22 @@ def test_archive_bytes_identical_to_reference_cli(tmp_path, name):
     got, got_out = _compress(str(tmp_path), "gpu", True, f1, f2, c["flags"])
     assert len(ref) > 1000
     assert "Matched" in ref_out and "Matched" in got_out
+    # stage 7 ran on the GPU as well (GpuTextMatcher behind SimplePgMatcher) and pushed the same number of matches per call
+    assert "Pseudogenome text index on the GPU" in got_out and "Pseudogenome text index on the GPU" not in ref_out
+    found = lambda out: [l.split(" exact matches")[0] for l in out.splitlines() if l.startswith("... found ")]
+    assert len(found(ref_out)) == 3 and found(got_out) == found(ref_out)
     assert got == ref, f"{name}: archives differ ({len(got)} vs {len(ref)} bytes)"
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="oracle/_ref/PgRC-dev-gpu not built (needs /root/reference at build time)")
+def test_stage7_can_stay_on_the_cpu(tmp_path):
+    """PGRC_GPU_PGMATCH=0: stage 4 on the GPU, stage 7 (SimplePgMatcher's text matcher) the reference's CopMEMMatcher."""
+    c = CASES["PE_ORD_150bp"]
+    f1, f2 = _fastq(str(tmp_path), "p", c["pair"], **c["gen"])
+    ref, _ = _compress(str(tmp_path), "cpu", False, f1, f2, c["flags"])
+    got, out = _compress(str(tmp_path), "gpu4", True, f1, f2, c["flags"], env_extra=dict(PGRC_GPU_PGMATCH="0"))
+    assert "Pseudogenome text index on the GPU" not in out and "(GPU)" in out
+    assert got == ref
 
 
 MULTI = ["SE_100bp", "SE_ORD_150bp", "PE_ORD_150bp", "SE_two_phase", "SE_exact_prephase", "SE_ilv_100bp", "SE_default_cli"]

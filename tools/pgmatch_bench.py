@@ -30,25 +30,30 @@ def main():
     import torch
     from pgrc_b200 import matcher, synth
     dev = torch.device("cuda", 0)
-    cfg = synth.scaled_config(args.workload, args.scale)
-    gp = synth.hashed_params(**cfg, seed=20261017)
-    src_d = synth.hashed_text(gp, 0, int(gp.text_len), dev)
-    n = int(src_d.numel())
-    # destination: a third of the source length, blocks of 2000 characters taken from the source at a stride of three
-    # blocks, every other one reverse-complemented, 0.3 % substitutions
     comp = torch.arange(256, dtype=torch.uint8, device=dev)
     for a, b in ("AT", "CG", "GC", "TA"):
         comp[ord(a)] = ord(b)
-    blk = 2000
-    nb = n // (3 * blk)
-    d = src_d[: nb * 3 * blk].view(nb, 3, blk)[:, 0, :].clone()
-    d[1::2] = comp[d[1::2].long()].flip(1)
-    dest_d = d.reshape(-1)
-    g = torch.Generator(device=dev); g.manual_seed(7)
-    sub = torch.rand(dest_d.numel(), device=dev, generator=g) < 0.003
-    acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
-    dest_d[sub] = acgt[torch.randint(0, 4, (int(sub.sum()),), device=dev, generator=g)]
-    dest_rc_d = comp[dest_d.long()].flip(0).contiguous()          # what exactMatchPg hands to the matcher (:39-41)
+
+    def make_texts(scale):
+        """(source, destination as exactMatchPg hands it to the matcher, :39-41) of the workload at `scale`: the source is the
+        bench text; the destination has a third of its length — blocks of 2000 characters taken from the source at a stride
+        of three blocks, every other one reverse-complemented, 0.3 % substitutions — reverse-complemented as a whole."""
+        cfg = synth.scaled_config(args.workload, scale)
+        gp = synth.hashed_params(**cfg, seed=20261017)
+        src = synth.hashed_text(gp, 0, int(gp.text_len), dev)
+        blk = 2000
+        nb = int(src.numel()) // (3 * blk)
+        d = src[: nb * 3 * blk].view(nb, 3, blk)[:, 0, :].clone()
+        d[1::2] = comp[d[1::2].long()].flip(1)
+        dest = d.reshape(-1)
+        g = torch.Generator(device=dev); g.manual_seed(7)
+        sub = torch.rand(dest.numel(), device=dev, generator=g) < 0.003
+        acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+        dest[sub] = acgt[torch.randint(0, 4, (int(sub.sum()),), device=dev, generator=g)]
+        return src, dest, comp[dest.long()].flip(0).contiguous()
+
+    src_d, dest_d, dest_rc_d = make_texts(args.scale)
+    n = int(src_d.numel())
     torch.cuda.synchronize()
 
     m = matcher.GpuReadsMatcher(0)
@@ -87,9 +92,9 @@ def main():
     if args.ref_scale > 0:
         import oracle
         if oracle.have_ref():
-            k = max(100000, int(n * args.ref_scale))
-            src_h = src_d[:k].cpu().numpy()
-            dst_h = dest_rc_d[: max(30000, int(dest_d.numel() * args.ref_scale))].cpu().numpy()
+            rs, _, rd = make_texts(args.scale * args.ref_scale)      # the same workload shape, scaled
+            src_h, dst_h = rs.cpu().numpy(), rd.cpu().numpy()
+            k = int(src_h.size)
             ref = {}
             for threads in (1, os.cpu_count() or 1):
                 secs = [0, 0]
