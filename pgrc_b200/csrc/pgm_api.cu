@@ -4,6 +4,7 @@
 #include "../../include/pgrc_gpu_matcher.h"
 #include "pgm_kernels.cuh"
 #include "pgm_blocked.cuh"
+#include "pgm_part.cuh"
 #include "pgm_copmem.cuh"
 #include "pgm_mem.cuh"
 #include "pgm_routed.cuh"
@@ -55,6 +56,8 @@ struct pgm_ctx {
     int insert_prefetch = 1;    // build_insert_kernel prefetches the next region's buckets into the L2 (PGM_INSERT_PREFETCH)
     int blocked_scan = 0;       // L2-blocked scan pipeline: 0 off, 1 auto (by size), 2 always, 3 always with tiny queues (PGM_BLOCKED_SCAN; tests)
     int region_mb = 12, range_mb = 16;   // target sizes of a table region / a read range of the pipeline (PGM_REGION_MB, PGM_RANGE_MB)
+    int part_scan = 0;          // partitioned exact pre-filter (pgm_part.cuh), opt-in (measured slower at config 5): 0 off, 1 auto (pattern sets beyond the Bloom filter), 2 always, 3 always with tiny queues (PGM_PART_SCAN; tests)
+    int part_mb = 48;           // target size of a table partition (PGM_PART_MB)
     size_t persist_max = 0, window_max = 0, persist_set = 0;
 
     // text
@@ -86,9 +89,10 @@ struct pgm_ctx {
     // table
     DevBuf buckets, next, filter, bq_entries, bq_counters;
     DevBuf sq_pos, sq_cand, sq_counters;   // queues of the L2-blocked scan pipeline (pgm_blocked.cuh)
+    DevBuf pq_entries, pq_counters, pq_bits;   // partition queues and hit bitmap of the partitioned pre-filter (pgm_part.cuh)
     DevBuf mis_sums, mis_offsets, mis_pos, mis_syms;   // mismatch lists (pgm_get_mismatches)
     // mode 'c' (pgm_copmem.cuh): per-pass text index + parameters of the current CopMEM phase
-    DevBuf cm_count, cm_start, cm_cumm, cm_fill, cm_hash, cm_all, cm_entries, cm_sums;
+    DevBuf cm_count, cm_start, cm_cumm, cm_fill, cm_hash, cm_all, cm_entries, cm_sums, cm_nib, cm_coarse;
     uint32_t cm_K = 0, cm_k1 = 0, cm_k2 = 0, cm_hash_size = 0;
     bool copmem_active = false;
     // stage 7 (pgm_mem.cuh): index of the context's text in the cm_* buffers + the destination text and the match lists
@@ -450,13 +454,16 @@ int filter_window(pgm_ctx *ctx, bool on, bool force = false) {
 }
 
 template <int NCH>
-void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, bool filter_stage) {
+void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, int mode) {
     // FAST: only ACGT reads, records of exactly 64 bytes (read length <= 192)
     const bool fast = sp.reads.n_n == 0 && sp.reads.lq_stride16 == 4;
     const bool pair = sp.tab.pair != 0;          // (never set together with ilv)
-    if (filter_stage) {
+    if (mode == 1) {                             // filter stage of the L2-blocked pipeline
         if (pair) pgm::scan_kernel<NCH, false, 1, false, true><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
         else pgm::scan_kernel<NCH, false, 1, false, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+    } else if (mode == 2) {                      // behind the partitioned pre-filter: stage A1 reads the hit bitmap
+        if (fast) pgm::scan_kernel<NCH, true, 2, false, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
+        else pgm::scan_kernel<NCH, false, 2, false, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
     } else if (sp.ilv) {
         if (fast) pgm::scan_kernel<NCH, true, 0, true, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
         else pgm::scan_kernel<NCH, false, 0, true, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
@@ -467,17 +474,60 @@ void launch_scan(const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, b
     else pgm::scan_kernel<NCH, false, 0, false, false><<<grid, PGM_SCAN_THREADS, 0, s>>>(sp);
 }
 
-void launch_scan_nch(int nch, const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, bool filter_stage) {
+void launch_scan_nch(int nch, const pgm::ScanParams &sp, unsigned int grid, cudaStream_t s, int mode) {
     switch (nch) {
-        case 1: launch_scan<1>(sp, grid, s, filter_stage); break;
-        case 2: launch_scan<2>(sp, grid, s, filter_stage); break;
-        case 3: launch_scan<3>(sp, grid, s, filter_stage); break;
-        case 4: launch_scan<4>(sp, grid, s, filter_stage); break;
-        case 5: launch_scan<5>(sp, grid, s, filter_stage); break;
-        case 6: launch_scan<6>(sp, grid, s, filter_stage); break;
-        case 7: launch_scan<7>(sp, grid, s, filter_stage); break;
-        default: launch_scan<8>(sp, grid, s, filter_stage); break;
+        case 1: launch_scan<1>(sp, grid, s, mode); break;
+        case 2: launch_scan<2>(sp, grid, s, mode); break;
+        case 3: launch_scan<3>(sp, grid, s, mode); break;
+        case 4: launch_scan<4>(sp, grid, s, mode); break;
+        case 5: launch_scan<5>(sp, grid, s, mode); break;
+        case 6: launch_scan<6>(sp, grid, s, mode); break;
+        case 7: launch_scan<7>(sp, grid, s, mode); break;
+        default: launch_scan<8>(sp, grid, s, mode); break;
     }
+}
+
+template <int NCH>
+cudaError_t launch_part_scan(const pgm::PartScanParams &ps, unsigned int grid, cudaStream_t s) {
+    const size_t smem = sizeof(pgm::PartScanShared);
+    cudaError_t e = cudaFuncSetAttribute(pgm::part_scan_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pgm::part_scan_kernel<NCH><<<grid, PGM_PART_THREADS, smem, s>>>(ps);
+    return cudaSuccess;
+}
+
+cudaError_t launch_part_scan_nch(int nch, const pgm::PartScanParams &ps, unsigned int grid, cudaStream_t s) {
+    switch (nch) {
+        case 1: return launch_part_scan<1>(ps, grid, s);
+        case 2: return launch_part_scan<2>(ps, grid, s);
+        case 3: return launch_part_scan<3>(ps, grid, s);
+        case 4: return launch_part_scan<4>(ps, grid, s);
+        case 5: return launch_part_scan<5>(ps, grid, s);
+        case 6: return launch_part_scan<6>(ps, grid, s);
+        case 7: return launch_part_scan<7>(ps, grid, s);
+        default: return launch_part_scan<8>(ps, grid, s);
+    }
+}
+
+// The partitioned pre-filter (pgm_part.cuh) for one scan launch: window starts per round, partitions, queue capacity.
+// Auto mode: the pattern set is beyond what the Bloom filter tells apart (match_begin gave it more than one slice) and the
+// launch is long enough to pay for streaming the bucket array once.
+constexpr uint64_t PART_ROUND_MAX = (1ull << 31) - (1ull << 20);     // launch-relative positions are 32 bits; queues of a round <= 26 GB
+bool part_wanted(const pgm_ctx *ctx) {
+    if (ctx->part_scan <= 0 || ctx->n_reads() == 0 || ctx->interleaved) return false;
+    return ctx->part_scan >= 2 || ctx->filter_slice_bits > 0;
+}
+bool plan_part(const pgm_ctx *ctx, uint64_t n_pos, pgm::PartQueues &q) {
+    memset(&q, 0, sizeof q);
+    if (!part_wanted(ctx) || n_pos > PART_ROUND_MAX) return false;
+    const uint64_t table_bytes = (uint64_t)ctx->n_buckets * 32;
+    if (ctx->part_scan == 1 && n_pos * 12 < table_bytes / 8) return false;
+    int pb = ceil_log2((table_bytes + ((uint64_t)ctx->part_mb << 20) - 1) / ((uint64_t)ctx->part_mb << 20));
+    pb = std::min(10, std::max(ctx->part_scan >= 2 ? 3 : 1, pb));
+    q.part_bits = (uint32_t)pb;
+    const uint64_t cap = ctx->part_scan == 3 ? 64 : (n_pos >> pb) + (n_pos >> (pb + 6)) + 8192;       // mean + 1.5 % + slack
+    q.cap = (uint32_t)std::min<uint64_t>(cap, 0xFFFFFFF0ull);
+    return true;
 }
 
 int floor_log2(uint64_t v) { int b = 0; while ((2ull << b) <= v) b++; return b; }
@@ -549,6 +599,8 @@ int pgm_create(int device, pgm_ctx **out) {
     if (const char *t = getenv("PGM_FILTER_SLICES")) ctx->filter_slices_force = std::min(3, std::max(0, atoi(t)));
     if (const char *t = getenv("PGM_INSERT_PREFETCH")) ctx->insert_prefetch = atoi(t);
     if (const char *t = getenv("PGM_BLOCKED_SCAN")) ctx->blocked_scan = atoi(t);
+    if (const char *t = getenv("PGM_PART_SCAN")) ctx->part_scan = atoi(t);
+    if (const char *t = getenv("PGM_PART_MB")) ctx->part_mb = std::max(1, atoi(t));
     if (const char *t = getenv("PGM_REGION_MB")) ctx->region_mb = std::max(1, atoi(t));
     if (const char *t = getenv("PGM_RANGE_MB")) ctx->range_mb = std::max(1, atoi(t));
     if (const char *g = getenv("PGM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob
@@ -589,12 +641,12 @@ void pgm_destroy(pgm_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->f_lo, &ctx->f_hi, &ctx->r_lo, &ctx->r_hi, &ctx->ascii_stage, &ctx->packed_stage,
                       &ctx->lq_recs, &ctx->n_recs, &ctx->keys, &ctx->first_order,
                       &ctx->same_mask, &ctx->same_mm, &ctx->touched, &ctx->buckets, &ctx->next, &ctx->filter, &ctx->bq_entries, &ctx->bq_counters,
-                      &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->mis_sums, &ctx->mis_offsets, &ctx->mis_pos, &ctx->mis_syms,
+                      &ctx->sq_pos, &ctx->sq_cand, &ctx->sq_counters, &ctx->pq_entries, &ctx->pq_counters, &ctx->pq_bits, &ctx->mis_sums, &ctx->mis_offsets, &ctx->mis_pos, &ctx->mis_syms,
                       &ctx->rt_win_send2[0], &ctx->rt_win_send2[1], &ctx->rt_win_recv2[0], &ctx->rt_win_recv2[1], &ctx->rt_cand_send2[0],
                       &ctx->rt_cand_send2[1], &ctx->rt_cand_recv2[0], &ctx->rt_cand_recv2[1], &ctx->rt_pat_recv, &ctx->rt_counters, &ctx->rt_live, &ctx->rt_live_count,
                       &ctx->mem_dlo, &ctx->mem_dhi, &ctx->mem_dinv, &ctx->mem_stage, &ctx->mem_fv, &ctx->mem_has, &ctx->mem_emit, &ctx->mem_gcount,
                       &ctx->mem_gstart, &ctx->mem_raw, &ctx->mem_rawq, &ctx->mem_keep, &ctx->mem_kstart, &ctx->mem_out,
-                      &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums,
+                      &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums, &ctx->cm_nib, &ctx->cm_coarse,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
     for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -913,6 +965,16 @@ int match_begin_impl(pgm_ctx *ctx, uint32_t seed_len, uint32_t parts, uint32_t m
 // One scan launch over the seed-window starts [fb, fe) (FORWARD global coordinates) of the pass.
 int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
     if (fb >= fe) return PGM_OK;
+    if (part_wanted(ctx) && fe - fb > PART_ROUND_MAX) {
+        // the partitioned pre-filter works in rounds of at most 2^31 window starts (equal rounds, tile-aligned)
+        const uint64_t k = (fe - fb + PART_ROUND_MAX - 1) / PART_ROUND_MAX;
+        const uint64_t per = (((fe - fb + k - 1) / k) + PGM_TILE_POS - 1) / PGM_TILE_POS * PGM_TILE_POS;
+        for (uint64_t b = fb; b < fe; b += per) {
+            const int rc = scan_range(ctx, rev_mode, b, std::min(fe, b + per));
+            if (rc) return rc;
+        }
+        return PGM_OK;
+    }
     const uint64_t n = ctx->seed_span(), pg = ctx->pg_len;     // n: text bases a seed window covers
     pgm::ScanParams sp;
     memset(&sp, 0, sizeof sp);
@@ -947,6 +1009,37 @@ int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
     ctx->state_fresh = false;
     ctx->aux_clean = false;
     ctx->outputs_valid = false;
+    pgm::PartQueues pq;
+    if (plan_part(ctx, le - lb, pq)) {
+        // partitioned pre-filter: every window -> queue of its table partition -> probed partition by partition (L2) -> bitmap
+        // of the windows with a table hit; then the fused kernel with the bitmap in place of its hash + filter stage
+        int rc;
+        const size_t bit_words = (size_t)sp.n_tiles * PGM_TILE_WORDS + 32;
+        if ((rc = ensure(ctx, ctx->pq_entries, ((size_t)pq.cap << pq.part_bits) * 12)) ||
+            (rc = ensure(ctx, ctx->pq_counters, 2 * PGM_PART_MAX * sizeof(unsigned int))) ||
+            (rc = ensure(ctx, ctx->pq_bits, bit_words * 4))) return rc;
+        pq.entries = ctx->pq_entries.as<uint32_t>();
+        pq.count = ctx->pq_counters.as<unsigned int>(); pq.cursor = pq.count + PGM_PART_MAX;
+        pq.hit_bits = ctx->pq_bits.as<uint32_t>();
+        CU(cudaMemsetAsync(pq.count, 0, 2 * PGM_PART_MAX * sizeof(unsigned int), ctx->stream));
+        CU(cudaMemsetAsync(pq.hit_bits, 0, bit_words * 4, ctx->stream));
+        pgm::PartScanParams ps;
+        memset(&ps, 0, sizeof ps);
+        ps.tlo = sp.tlo; ps.thi = sp.thi; ps.slice_origin = sp.slice_origin; ps.own_begin = sp.own_begin; ps.own_end = sp.own_end;
+        ps.first_word = sp.first_word; ps.n_tiles = sp.n_tiles; ps.tail_mask = sp.tail_mask; ps.tile_counter = sp.tile_counter;
+        ps.q = pq;
+        KLAUNCH(PGM_K_SCAN_FILTER, "part_scan_kernel", {
+            cudaError_t le_ = launch_part_scan_nch(nch, ps, (unsigned int)std::min<uint64_t>(sp.n_tiles, (uint64_t)ctx->sm_count * 3), ctx->stream);
+            if (le_ != cudaSuccess) return cuda_fail(ctx, le_, "part_scan_kernel (attributes)"); });
+        pgm::PartProbeParams pp;
+        memset(&pp, 0, sizeof pp);
+        pp.q = pq; pp.tab = sp.tab;
+        KLAUNCH(PGM_K_SCAN_PROBE, "part_probe_kernel", pgm::part_probe_kernel<<<ctx->sm_count * 6, PGM_PART_THREADS, 0, ctx->stream>>>(pp));
+        CU(cudaMemsetAsync(sp.tile_counter, 0, sizeof(unsigned int), ctx->stream));
+        sp.hit_bits = pq.hit_bits;
+        KLAUNCH(PGM_K_SCAN, "scan_kernel (behind the partitioned pre-filter)", launch_scan_nch(nch, sp, grid, ctx->stream, 2));
+        return PGM_OK;
+    }
     { int wrc = filter_window(ctx, true); if (wrc) return wrc; }
     if (plan_blocked(ctx, le - lb, sp.n_tiles, sp.sq)) {
         // L2-blocked pipeline: filter stage (text order) -> probe stage (table-region order) -> verify stage (read-range
@@ -962,7 +1055,7 @@ int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
         q.overflow = cbase + 4 * PGM_SQ_MAX;
         q.counters = reinterpret_cast<unsigned long long *>(cbase + 4 * PGM_SQ_MAX + 2);
         CU(cudaMemsetAsync(cbase, 0, (4 * PGM_SQ_MAX + 2 + 8) * sizeof(unsigned int), ctx->stream));
-        KLAUNCH(PGM_K_SCAN_FILTER, "scan_kernel (filter stage)", launch_scan_nch(nch, sp, grid, ctx->stream, true));
+        KLAUNCH(PGM_K_SCAN_FILTER, "scan_kernel (filter stage)", launch_scan_nch(nch, sp, grid, ctx->stream, 1));
         pgm::VerifyParams vp;
         memset(&vp, 0, sizeof vp);
         vp.tlo = sp.tlo; vp.thi = sp.thi;
@@ -984,7 +1077,7 @@ int scan_range(pgm_ctx *ctx, int rev_mode, uint64_t fb, uint64_t fe) {
     for (uint32_t h = 0; h < n_slices; h++) {
         sp.slice = h;
         if (h) CU(cudaMemsetAsync(sp.tile_counter, 0, sizeof(unsigned int), ctx->stream));
-        KLAUNCH(PGM_K_SCAN, "scan_kernel", launch_scan_nch(nch, sp, grid, ctx->stream, false));
+        KLAUNCH(PGM_K_SCAN, "scan_kernel", launch_scan_nch(nch, sp, grid, ctx->stream, 0));
     }
     return filter_window(ctx, false);
 }
@@ -1016,6 +1109,8 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
         if ((rc = pack_text_chunk(ctx, ctx->ascii_stage.as<uint8_t>(), c))) return rc;
         const uint64_t have = ctx->slice_begin + std::min<uint64_t>(ctx->slice_len, (c + 1) * TEXT_CHUNK_BASES);   // bases [slice_begin, have) are packed
         uint64_t upto = c + 1 == nchunks ? fe : (have > 2 * 256 ? std::min<uint64_t>(fe, have - 2 * 256) : 0);
+        // (the partitioned pre-filter streams the whole bucket array once per launch: launches of a quarter of the text)
+        if (c + 1 != nchunks && part_wanted(ctx) && ctx->part_scan == 1 && (upto <= done || upto - done < std::max<uint64_t>((fe - fb) / 4, 256ull << 20))) continue;
         if (upto > done) {
             if ((rc = scan_range(ctx, 0, done, upto))) return rc;
             done = upto;
@@ -1911,7 +2006,9 @@ int pgm_mem_index(pgm_ctx *ctx, uint32_t target_match_length, uint32_t min_match
     if ((rc = ensure(ctx, ctx->cm_count, (hsz + 1) * 4)) || (rc = ensure(ctx, ctx->cm_start, (hsz + 1) * 4)) ||
         (rc = ensure(ctx, ctx->cm_cumm, (hsz + 2) * 4)) || (rc = ensure(ctx, ctx->cm_fill, (size_t)cp.n_sampled * 4)) ||
         (rc = ensure(ctx, ctx->cm_hash, (size_t)cp.n_sampled * 4)) || (rc = ensure(ctx, ctx->cm_all, (size_t)cp.n_sampled * 4)) ||
-        (rc = ensure(ctx, ctx->cm_entries, (size_t)cp.n_sampled * 4))) return rc;
+        (rc = ensure(ctx, ctx->cm_entries, (size_t)cp.n_sampled * 4)) ||
+        (rc = ensure(ctx, ctx->cm_nib, hsz / 8 * 4 + 64)) || (rc = ensure(ctx, ctx->cm_coarse, hsz / 64 * 4 + 64))) return rc;
+    cp.nib = ctx->cm_nib.as<uint32_t>(); cp.coarse = ctx->cm_coarse.as<uint32_t>();
     cp.count = ctx->cm_count.as<uint32_t>(); cp.start_all = ctx->cm_start.as<uint32_t>(); cp.cumm = ctx->cm_cumm.as<uint32_t>();
     cp.sample_rank = ctx->cm_fill.as<uint32_t>(); cp.sample_hash = ctx->cm_hash.as<uint32_t>(); cp.all_entries = ctx->cm_all.as<uint32_t>();
     cp.entries = ctx->cm_entries.as<uint32_t>();
@@ -1920,6 +2017,7 @@ int pgm_mem_index(pgm_ctx *ctx, uint32_t target_match_length, uint32_t min_match
     KLAUNCH(PGM_K_COPMEM_INDEX, "cm_hash_kernel", pgm::cm_hash_kernel<<<grid_for(cp.n_sampled, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
     if ((rc = device_scan<0>(ctx, cp.count, (uint32_t)hsz, cp.start_all)) ||
         (rc = device_scan<PGM_CM_COLLISIONS_LIMIT + 1>(ctx, cp.count, (uint32_t)hsz, cp.cumm))) return rc;
+    KLAUNCH(PGM_K_COPMEM_INDEX, "cm_compact_kernel", pgm::cm_compact_kernel<<<grid_for(hsz / 8, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
     KLAUNCH(PGM_K_COPMEM_INDEX, "cm_scatter_kernel", pgm::cm_scatter_kernel<<<grid_for(cp.n_sampled, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
     KLAUNCH(PGM_K_COPMEM_INDEX, "cm_select_kernel", pgm::cm_select_kernel<<<grid_for(hsz, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
     int bad = 0;
@@ -1954,7 +2052,7 @@ int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is
     mp.K = ctx->mem_K; mp.k1 = ctx->mem_k1; mp.k2 = ctx->mem_k2; mp.hash_mask = ctx->mem_hash_size - 1;
     mp.min_len = min_match_length; mp.skip = mp.K / mp.k1 - 1;
     mp.dest_is_src = dest_is_src ? 1 : 0; mp.rev_compl = rev_compl ? 1 : 0;
-    mp.cumm = ctx->cm_cumm.as<uint32_t>(); mp.entries = ctx->cm_entries.as<uint32_t>();
+    mp.nib = ctx->cm_nib.as<uint32_t>(); mp.coarse = ctx->cm_coarse.as<uint32_t>(); mp.entries = ctx->cm_entries.as<uint32_t>();
     if (!dest) {
         mp.dlo = (rev_compl ? ctx->r_lo : ctx->f_lo).as<uint32_t>() + PGM_PAD_WORDS;
         mp.dhi = (rev_compl ? ctx->r_hi : ctx->f_hi).as<uint32_t>() + PGM_PAD_WORDS;

@@ -35,6 +35,11 @@ struct CopmemParams {
     uint32_t *sample_hash;          // [n_sampled]
     uint32_t *all_entries;          // [n_sampled] sample indices, full buckets, unordered
     uint32_t *entries;              // kept sample indices (position = index * k1), ascending inside a bucket
+    // compact bucket directory for stage 7's queries (cm_bucket, pgm_mem.cuh): cumm[] is 4 bytes per hash value (256 MB for the
+    // config-2 text: every lookup a random DRAM line); kept entries per hash value fit a nibble (<= 13), so 4 bits per hash
+    // value + one 32-bit prefix per 64 hash values (36 MB) can stay in the L2: a lookup is one 256-bit load + nibble sums
+    uint32_t *nib;                  // [hash_size / 8] nibble h & 7 of word h >> 3 = min(count[h], 13)
+    uint32_t *coarse;               // [hash_size / 64] cumm[64 g]
     // query
     ReadsView reads;
     uint32_t n_reads, max_mm, min_mm;
@@ -176,6 +181,40 @@ __global__ void __launch_bounds__(PGM_CM_THREADS) cm_select_kernel(const __grid_
         if ((uint32_t)t < keep) dst[t] = best[t];
 }
 
+// the compact directory from count[] and cumm[] (see CopmemParams): thread per 8 hash values
+__global__ void __launch_bounds__(PGM_CM_THREADS) cm_compact_kernel(const __grid_constant__ CopmemParams p) {
+    const uint32_t w = blockIdx.x * PGM_CM_THREADS + threadIdx.x;
+    if (w > (p.hash_mask >> 3)) return;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v |= min(p.count[8 * w + k], (uint32_t)PGM_CM_COLLISIONS_LIMIT + 1u) << (4 * k);
+    p.nib[w] = v;
+    if ((w & 7u) == 0) p.coarse[w >> 3] = p.cumm[8 * w];
+}
+
+// sum of the eight nibbles of a word (each <= 13)
+__device__ __forceinline__ uint32_t cm_nibsum(uint32_t w) {
+    return (((w & 0x0F0F0F0Fu) + ((w >> 4) & 0x0F0F0F0Fu)) * 0x01010101u) >> 24;
+}
+
+// bucket [b0, b1) of hash value h from the compact directory (= [cumm[h], cumm[h + 1])); the directory's lines carry an L2
+// evict_last policy: it is the one structure of a query that can stay in the L2 next to the entries and the text windows
+__device__ __forceinline__ void cm_bucket(const uint32_t *nib, const uint32_t *coarse, uint32_t h, uint64_t pol_keep, uint32_t &b0, uint32_t &b1) {
+    const uint32_t g = h >> 6, i = h & 63u, wi = i >> 3;
+    const u32x8 w = ld256_stream_hint(nib + 8 * (size_t)g, pol_keep);
+    uint32_t before = ld_u32_hint(coarse + g, pol_keep), mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if ((uint32_t)k < wi) before += cm_nibsum(w.v[k]);
+        else if ((uint32_t)k == wi) {
+            const uint32_t sh = 4u * (i & 7u);
+            before += cm_nibsum(w.v[k] & ((1u << sh) - 1u));
+            mine = (w.v[k] >> sh) & 15u;
+        }
+    }
+    b0 = before; b1 = before + mine;
+}
+
 // processApproxMatchQueryTight (CopMEMMatcher.cpp:483-566) + the per-read part of CopMEMReadsApproxMatcher::executeMatching
 // (ReadsMatchers.cpp:427-448), one thread per read; the read's state in its record is updated in place.
 __global__ void __launch_bounds__(PGM_CM_THREADS, 4) cm_query_kernel(const __grid_constant__ CopmemParams p, unsigned long long *counters) {
@@ -217,6 +256,8 @@ __global__ void __launch_bounds__(PGM_CM_THREADS, 4) cm_query_kernel(const __gri
             const uint64_t hi = (uint64_t)__funnelshift_r(rh[w], rh[w + 1], s) | ((uint64_t)__funnelshift_r(rh[w + 1], rh[w + 2], s) << 32);
             const uint64_t nn = is_n ? (uint64_t)__funnelshift_r(rn[w], rn[w + 1], s) | ((uint64_t)__funnelshift_r(rn[w + 1], rn[w + 2], s) << 32) : 0ull;
             const uint32_t h = cm_hash(K, lo, hi, nn, p.hash_mask, lut);
+            // (the compact directory of cm_bucket was measured here too: 98 - 111 ms instead of 70 ms per config-2 step — this
+            // kernel is bound by its 135 candidate verifications per read, not by the directory lines; it serves stage 7 only)
             const uint32_t b0 = __ldg(p.cumm + h);
             uint32_t b1 = __ldg(p.cumm + h + 1);
             if (b0 == b1) continue;

@@ -190,6 +190,7 @@ struct ScanParams {
     unsigned long long *counters;   // [0] candidates [1] verified [2] accepted [3] filter positives
     StageQueues sq;                 // MODE 1 (filter stage of the L2-blocked pipeline) only
     const unsigned int *only_if;    // fused kernel as the pipeline's fallback: runs only when *only_if != 0, else commits sq.counters
+    const uint32_t *hit_bits;       // MODE 2 (behind the partitioned pre-filter, pgm_part.cuh): bit per launch-relative position
 };
 
 // ------------------------------------------------------------------------------------------ small helpers
@@ -890,6 +891,27 @@ __global__ void __launch_bounds__(PGM_SCAN_THREADS, PGM_SCAN_MIN_CTAS) scan_kern
                     base = __shfl_sync(PGM_FULL, base, 0);
                     if (hit) sm.q1[base + __popc(bal & lt_mask)] = (uint16_t)pos;
                     if (lane == 0) n_pos += __popc(bal);
+                }
+            }
+        } else if constexpr (MODE == 2) {
+            // the windows with a table hit are already known (pgm_part.cuh): A1 is a read of this warp's 16 words of the bitmap
+            const uint32_t w_first = warp * PGM_WORDS_PER_WARP;
+            const uint32_t mine = lane < PGM_WORDS_PER_WARP ? __ldg(p.hit_bits + (size_t)tile * PGM_TILE_WORDS + w_first + lane) : 0u;
+            if (__ballot_sync(PGM_FULL, mine != 0u)) {
+#pragma unroll 1
+                for (uint32_t it = 0; it < PGM_WORDS_PER_WARP; it++) {
+                    const uint32_t bits = __shfl_sync(PGM_FULL, mine, it);
+                    if (!bits) continue;                                        // (warp-uniform)
+                    const uint32_t pos = (w_first + it) * 32 + lane;
+                    const bool hit = pos >= vb && pos < ve && ((bits >> lane) & 1u);
+                    const uint32_t bal = __ballot_sync(PGM_FULL, hit);
+                    if (bal) {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&sm.q1_count[buf], __popc(bal));
+                        base = __shfl_sync(PGM_FULL, base, 0);
+                        if (hit) sm.q1[base + __popc(bal & lt_mask)] = (uint16_t)pos;
+                        if (lane == 0) n_pos += __popc(bal);
+                    }
                 }
             }
         } else {

@@ -36,7 +36,7 @@ struct MemParams {
     uint64_t N, N2;
     uint32_t K, k1, k2, hash_mask, min_len, skip;
     int dest_is_src, rev_compl;
-    const uint32_t *cumm, *entries; // the index (pgm_copmem.cuh)
+    const uint32_t *nib, *coarse, *entries; // the index (pgm_copmem.cuh: compact bucket directory + kept sample indices)
     uint64_t nq;                    // query positions 0, k2, 2 k2, ... <= N2 - K
     uint64_t n_groups;              // full groups of the main loop; group n_groups is the tail
     uint32_t *fv;                   // [nq] sample index of fv(q), 0xFFFFFFFF = none
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(PGM_MEM_THREADS) mem_query_kernel(const __grid
     __shared__ uint32_t lut[256];
     cm_build_lut(lut);
     const uint64_t i = (uint64_t)blockIdx.x * PGM_MEM_THREADS + threadIdx.x;
+    const uint64_t pol_keep = policy_evict_last();
     uint32_t found = 0xFFFFFFFFu;
     if (i < p.nq) {
         const uint64_t q = i * p.k2;
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(PGM_MEM_THREADS) mem_query_kernel(const __grid
         const uint64_t bad = p.dinv ? (mem_bits64(p.dinv, (long long)q) & maskK) : 0ull;
         if (!bad) {                                                         // a K-mer with an N equals no source K-mer
             const uint32_t h = cm_hash(p.K, lo, hi, 0ull, p.hash_mask, lut);
-            const uint32_t b0 = __ldg(p.cumm + h), b1 = __ldg(p.cumm + h + 1);
+            uint32_t b0, b1;
+            cm_bucket(p.nib, p.coarse, h, pol_keep, b0, b1);
             const uint64_t need = p.min_len - p.K;                          // extra characters a match needs (min_len >= K)
             for (uint32_t j = b0; j < b1; j++) {
                 const uint32_t e = __ldg(p.entries + j);

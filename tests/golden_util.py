@@ -6,8 +6,9 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-# (sample_*.npz are the full-size fixtures of tests/golden/make_fullsize.py: another format, used by tests/test_gpu_fullsize.py and bench.py --verify)
-NAMES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith("sample_"))
+# (pgmatch_*.npz are the stage-7 vectors of tests/golden/make_golden_pgmatch.py: tests/test_pgmatch_oracle.py, tests/test_gpu_pgmatch.py;
+# sample_*.npz are the full-size fixtures of tests/golden/make_fullsize.py: another format, used by tests/test_gpu_fullsize.py and bench.py --verify)
+NAMES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith(("sample_", "pgmatch_")))
 
 
 def load(name):

@@ -309,6 +309,49 @@ def test_blocked_scan_pipeline_hot_seeds_and_shards(monkeypatch):
         assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)
 
 
+@pytest.mark.parametrize("mode", ["2", "3"])
+def test_partitioned_prefilter_forced(monkeypatch, mode):
+    """The partitioned exact pre-filter (pgm_part.cuh: every window queued by table partition, partitions probed in the L2,
+    hit bitmap in place of the fused kernel's hash + filter stage; used for pattern sets beyond the Bloom filter) forced onto
+    small inputs.  Mode 3 shrinks the partition queues to 64 entries: the windows that do not fit are marked without a probe
+    and the fused kernel's own probe stage sorts them out — both routes must give the oracle's result."""
+    monkeypatch.setenv("PGM_PART_SCAN", mode)
+    for inp in (synth.adversarial(151, 100), synth.adversarial(152, 150), synth.adversarial(153, 255), synth.adversarial(154, 64),
+                synth.workload(200_000, 50_000, 150, 0.005, seed=155, n_frac=0.02, name="c2 shape"),
+                synth.workload(300_000, 40_000, 100, 0.01, seed=156, name="c4 shape")):
+        got, _ = _check(inp)
+        assert got.stats["candidates"] > 0 and got.stats["filter_positives"] > 0
+        _check(inp, pre_reads_exact_matching_chars=inp.read_len)
+        _check(inp, matching_mode="D")
+    for kw in (dict(reads_exact_matching_chars=30), dict(reads_exact_matching_chars=45), dict(reads_exact_matching_chars=100),
+               dict(min_chars_per_mismatch=2), dict(rev_compl_pg=False), dict(pre_reads_exact_matching_chars=50)):
+        _check(synth.adversarial(157, 100), **kw)
+
+
+def test_partitioned_prefilter_hot_seeds_shards_and_host_text(monkeypatch):
+    """Hot seeds (chains behind a slot, one partition far above the average), text shards, the group API and a host text
+    that arrives in chunks through the partitioned pre-filter."""
+    monkeypatch.setenv("PGM_PART_SCAN", "2")
+    rng = np.random.default_rng(158)
+    g = synth.random_genome(30_000, rng)
+    text = np.concatenate([g[:10_000], np.full(400, ord("A"), np.uint8), g[10_000:20_000], np.full(300, ord("T"), np.uint8), g[20_000:]])
+    base = synth.sample_reads(g, 40, 100, 0.02, rng)
+    polya = np.full((300, 100), ord("A"), np.uint8)
+    polya[np.arange(300), rng.integers(0, 100, 300)] = ord("C")
+    reads = np.concatenate([np.repeat(base, 60, axis=0), polya, synth.sample_reads(g, 500, 100, 0.01, rng)])
+    reads = reads[rng.permutation(len(reads))]
+    nn = synth.inject_n(np.repeat(base[:5], 40, axis=0), rng)
+    inp = synth.MatcherInputs(np.ascontiguousarray(text), np.ascontiguousarray(reads), nn, 100, "hot seeds")
+    _check(inp)
+    inp = synth.adversarial(159, 100, n_reads=2000, text_len=30000)
+    want = oracle.oracle_map_reads(inp.text, inp.lq_packed, inp.n_packed, inp.read_len)
+    for got in _run_sharded_on_one_gpu(inp, 3):
+        assert np.array_equal(got.pos, want.pos) and np.array_equal(got.rc, want.rc) and np.array_equal(got.mm, want.mm)
+    # a text of several upload chunks (16 M bases each), host inputs: the forward pass scans while the text arrives
+    big = synth.workload(14_000_000, 60_000, 100, 0.01, seed=160, name="40 Mbp host text")
+    _check(big)
+
+
 @pytest.mark.parametrize("seed,L", [(71, 100), (72, 150), (73, 120), (74, 64), (75, 255)])
 def test_interleaved_mode_adversarial(seed, L):
     """Mode 'i' (InterleavedReadsApproxMatcher, ReadsMatchers.cpp:343-409): strided seeds, alignment = hit - j."""
