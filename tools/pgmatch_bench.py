@@ -18,6 +18,40 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def stage7_texts(workload, scale, dev):
+    """(source, destination, destination as SimplePgMatcher::exactMatchPg hands it to the matcher, SimplePgMatcher.cpp:39-41) for
+    the bench workload at `scale`: the source is the bench text (counter-based generator); the destination has a third of its
+    length — blocks of 2000 characters taken from the source at a stride of three blocks, every other one reverse-complemented,
+    one substitution per 333 characters at counter-derived positions — and is then reverse-complemented as a whole.  Pure
+    integer arithmetic in torch: the same bytes on any device."""
+    import torch
+    from pgrc_b200 import synth
+    cfg = synth.scaled_config(workload, scale)
+    gp = synth.hashed_params(**cfg, seed=20261017)
+    src = synth.hashed_text(gp, 0, int(gp.text_len), dev)
+    comp = torch.arange(256, dtype=torch.uint8, device=dev)
+    for a, b in ("AT", "CG", "GC", "TA"):
+        comp[ord(a)] = ord(b)
+    blk = 2000
+    nb = int(src.numel()) // (3 * blk)
+    d = src[: nb * 3 * blk].view(nb, 3, blk)[:, 0, :].clone()
+    d[1::2] = comp[d[1::2].long()].flip(1)
+    dest = d.reshape(-1)
+    idx = torch.arange(dest.numel(), device=dev, dtype=torch.int64)
+    sub = ((idx * 2654435761) >> 7) % 333 == 0
+    nxt = torch.zeros(256, dtype=torch.uint8, device=dev)
+    for a, b in ("AC", "CG", "GT", "TA"):
+        nxt[ord(a)] = ord(b)
+    dest[sub] = nxt[dest[sub].long()]
+    return src, dest, comp[dest.long()].flip(0).contiguous()
+
+
+def result_digest(matches):
+    import hashlib
+    import numpy as np
+    return {"count": int(len(matches)), "sha256": hashlib.sha256(np.ascontiguousarray(matches, dtype=np.uint64).tobytes()).hexdigest()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c2")
@@ -26,31 +60,13 @@ def main():
     ap.add_argument("--target", type=int, default=45, help="targetPgMatchLength (PgRC default 45)")
     ap.add_argument("--check", action="store_true", help="compare the GPU result with the sequential oracle (small scales only)")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--fixture", default="", help="JSON made by tests/golden/make_fullsize_pgmatch.py (the REFERENCE's own run of this "
+                    "workload at one thread): compare count and sha256 of both result vectors")
     args = ap.parse_args()
     import torch
     from pgrc_b200 import matcher, synth
     dev = torch.device("cuda", 0)
-    comp = torch.arange(256, dtype=torch.uint8, device=dev)
-    for a, b in ("AT", "CG", "GC", "TA"):
-        comp[ord(a)] = ord(b)
-
-    def make_texts(scale):
-        """(source, destination as exactMatchPg hands it to the matcher, :39-41) of the workload at `scale`: the source is the
-        bench text; the destination has a third of its length — blocks of 2000 characters taken from the source at a stride
-        of three blocks, every other one reverse-complemented, 0.3 % substitutions — reverse-complemented as a whole."""
-        cfg = synth.scaled_config(args.workload, scale)
-        gp = synth.hashed_params(**cfg, seed=20261017)
-        src = synth.hashed_text(gp, 0, int(gp.text_len), dev)
-        blk = 2000
-        nb = int(src.numel()) // (3 * blk)
-        d = src[: nb * 3 * blk].view(nb, 3, blk)[:, 0, :].clone()
-        d[1::2] = comp[d[1::2].long()].flip(1)
-        dest = d.reshape(-1)
-        g = torch.Generator(device=dev); g.manual_seed(7)
-        sub = torch.rand(dest.numel(), device=dev, generator=g) < 0.003
-        acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
-        dest[sub] = acgt[torch.randint(0, 4, (int(sub.sum()),), device=dev, generator=g)]
-        return src, dest, comp[dest.long()].flip(0).contiguous()
+    make_texts = lambda scale: stage7_texts(args.workload, scale, dev)
 
     src_d, dest_d, dest_rc_d = make_texts(args.scale)
     n = int(src_d.numel())
@@ -83,6 +99,11 @@ def main():
     matcher.GpuTextMatcher(None, args.target, matcher=m); tm.match_texts(None, True, True); tm.match_texts(dest_rc_d, False, True)
     out["kernel_ms"] = {k: round(v[0], 3) for k, v in m.timings().items() if v[1]}
     m.set_profiling(False)
+    if args.fixture:
+        want = json.load(open(args.fixture))
+        assert want["workload"] == args.workload and want["scale"] == args.scale and want["target_len"] == args.target
+        out["reference_full_run"] = {"fixture": os.path.relpath(args.fixture, ROOT),
+                                     "self_equal": result_digest(r_self) == want["self_rc"], "lq_equal": result_digest(r_lq) == want["lq"]}
     if args.check:
         import oracle
         src_h = src_d.cpu().numpy()
