@@ -334,6 +334,14 @@ int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is
                   uint32_t min_match_length, uint64_t *count);
 int pgm_mem_get_matches(pgm_ctx *ctx, pgm_text_match *out, uint64_t capacity);
 
+/* The same on a group of contexts (pgm_group_set_text gave every GPU the source text): every GPU builds the index; the groups
+ * of 256 query positions of a destination text are independent, GPU r takes the r-th share of them, and the shares are
+ * concatenated (the "covered by the previous match" test, :388-393, runs across the seams).  Same results as one context. */
+int pgm_group_mem_index(pgm_group *g, uint32_t target_match_length, uint32_t min_match_length, uint32_t *params /*[4] or NULL*/);
+int pgm_group_mem_match(pgm_group *g, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
+                        uint32_t min_match_length, uint64_t *count);
+int pgm_group_mem_get_matches(pgm_group *g, pgm_text_match *out, uint64_t capacity);
+
 /* ---- introspection (bench / tests) -------------------------------------------------------*/
 /* Number of kernels this context has launched so far. */
 uint64_t pgm_kernel_launches(const pgm_ctx *ctx);

@@ -28,7 +28,8 @@ EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pg
            "pgm_group_create", "pgm_group_destroy", "pgm_group_last_error", "pgm_group_size", "pgm_group_set_text", "pgm_group_set_reads",
            "pgm_group_upload", "pgm_group_match_begin", "pgm_group_pass", "pgm_group_copmem_begin", "pgm_group_copmem_pass",
            "pgm_group_get_results", "pgm_group_get_mismatches",
-           "pgm_mem_index", "pgm_mem_match", "pgm_mem_get_matches"]
+           "pgm_mem_index", "pgm_mem_match", "pgm_mem_get_matches",
+           "pgm_group_mem_index", "pgm_group_mem_match", "pgm_group_mem_get_matches"]
 
 KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators",
                 "scan_filter", "scan_probe", "scan_verify", "mismatches", "copmem_index", "copmem_query",
@@ -143,5 +144,8 @@ def load() -> ctypes.CDLL:
     lib.pgm_mem_index.restype = ci; lib.pgm_mem_index.argtypes = [vp, u32, u32, ctypes.POINTER(u32)]
     lib.pgm_mem_match.restype = ci; lib.pgm_mem_match.argtypes = [vp, vp, u64, ci, ci, u32, ctypes.POINTER(u64)]
     lib.pgm_mem_get_matches.restype = ci; lib.pgm_mem_get_matches.argtypes = [vp, vp, u64]
+    lib.pgm_group_mem_index.restype = ci; lib.pgm_group_mem_index.argtypes = [vp, u32, u32, ctypes.POINTER(u32)]
+    lib.pgm_group_mem_match.restype = ci; lib.pgm_group_mem_match.argtypes = [vp, vp, u64, ci, ci, u32, ctypes.POINTER(u64)]
+    lib.pgm_group_mem_get_matches.restype = ci; lib.pgm_group_mem_get_matches.argtypes = [vp, vp, u64]
     _lib = lib
     return lib

@@ -10,6 +10,7 @@
 #include "pgm_routed.cuh"
 
 #include <algorithm>
+#include <array>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -2031,8 +2032,14 @@ int pgm_mem_index(pgm_ctx *ctx, uint32_t target_match_length, uint32_t min_match
     return PGM_OK;
 }
 
-int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
-                  uint32_t min_match_length, uint64_t *count) {
+} // extern "C"
+
+namespace {
+// pgm_mem_match for the groups of 256 query positions [G * part / n_parts, G * (part + 1) / n_parts) of the G groups; raw: stop
+// before the "covered by the previous match" test (a context of several: the caller applies it across the seams) and leave
+// ctx->mem_raw / mem_rawq with ctx->mem_count entries
+int mem_match_impl(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
+                   uint32_t min_match_length, uint64_t *count, int part, int n_parts, bool raw) {
     if (!ctx || !count) return PGM_ERR_INVALID_ARG;
     if (!ctx->mem_index_valid) return fail(ctx, PGM_ERR_STATE, "pgm_mem_match: pgm_mem_index has not been called for the current text");
     if (!dest && !dest_is_src) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_mem_match: destination text is null");
@@ -2079,10 +2086,16 @@ int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is
     ctx->mem_count = 0;
     *count = 0;
     if (dest_len < mp.K) { ctx->mem_result_valid = true; return PGM_OK; }
-    mp.nq = (dest_len - mp.K) / mp.k2 + 1;
-    // groups of the main loop: i1 = g * k2 * 256 while i1 + K + k2 * 256 < N2 + 1 (CopMEMMatcher.cpp:364)
-    const uint64_t span = (uint64_t)mp.k2 * PGM_MEM_GROUP;
-    mp.n_groups = dest_len + 1 > mp.K + span ? (dest_len - mp.K - span) / span + 1 : 0;
+    {
+        // groups of 256 query positions: the main loop's (i1 = g * k2 * 256 while i1 + K + k2 * 256 < N2 + 1, CopMEMMatcher.cpp:364)
+        // and the tail with the 1 .. 256 positions left
+        const uint64_t nq_total = (dest_len - mp.K) / mp.k2 + 1, groups = (nq_total + PGM_MEM_GROUP - 1) / PGM_MEM_GROUP;
+        const uint64_t g0 = groups * (uint64_t)part / (uint64_t)n_parts, g1 = groups * (uint64_t)(part + 1) / (uint64_t)n_parts;
+        mp.q0 = g0 * PGM_MEM_GROUP;
+        mp.nq = std::min(nq_total, g1 * PGM_MEM_GROUP) - mp.q0;
+        if (g1 == g0) { ctx->mem_result_valid = true; return PGM_OK; }
+        mp.n_groups = g1 - g0 - 1;
+    }
     const size_t mask_words = (size_t)((mp.nq + 31) / 32 + 8);
     if ((rc = ensure(ctx, ctx->mem_fv, (size_t)mp.nq * 4)) || (rc = ensure(ctx, ctx->mem_has, mask_words * 4)) ||
         (rc = ensure(ctx, ctx->mem_emit, mask_words * 4)) || (rc = ensure(ctx, ctx->mem_gcount, (size_t)(mp.n_groups + 2) * 4)) ||
@@ -2105,6 +2118,13 @@ int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is
         mp.raw = ctx->mem_raw.as<pgm::MemMatch>(); mp.raw_q = ctx->mem_rawq.as<uint64_t>(); mp.keep = ctx->mem_keep.as<uint32_t>();
         mp.keep_start = ctx->mem_kstart.as<uint32_t>(); mp.out = ctx->mem_out.as<pgm::MemMatch>();
         KLAUNCH(PGM_K_MEM_EMIT, "mem_extend_kernel", pgm::mem_extend_kernel<<<grid_for((mp.nq + 31) / 32, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(mp));
+        if (raw) {
+            CU(cudaStreamSynchronize(ctx->stream));
+            ctx->mem_count = n_raw;
+            *count = n_raw;
+            ctx->mem_result_valid = true;
+            return PGM_OK;
+        }
         KLAUNCH(PGM_K_MEM_EMIT, "mem_flag_kernel", pgm::mem_flag_kernel<<<grid_for(n_raw, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(mp));
         if ((rc = device_scan<0>(ctx, mp.keep, n_raw, ctx->mem_kstart.as<uint32_t>()))) return rc;
         KLAUNCH(PGM_K_MEM_EMIT, "mem_compact_kernel", pgm::mem_compact_kernel<<<grid_for(n_raw, PGM_MEM_THREADS), PGM_MEM_THREADS, 0, ctx->stream>>>(mp));
@@ -2117,6 +2137,14 @@ int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is
     ctx->mem_result_valid = true;
     return PGM_OK;
 }
+} // namespace
+
+extern "C" {
+
+int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
+                  uint32_t min_match_length, uint64_t *count) {
+    return mem_match_impl(ctx, dest, dest_len, dest_is_src, rev_compl, min_match_length, count, 0, 1, false);
+}
 
 int pgm_mem_get_matches(pgm_ctx *ctx, pgm_text_match *out, uint64_t capacity) {
     if (!ctx) return PGM_ERR_INVALID_ARG;
@@ -2127,6 +2155,82 @@ int pgm_mem_get_matches(pgm_ctx *ctx, pgm_text_match *out, uint64_t capacity) {
     static_assert(sizeof(pgm_text_match) == sizeof(pgm::MemMatch), "layout");
     CU(cudaMemcpyAsync(out, ctx->mem_out.p, (size_t)ctx->mem_count * sizeof(pgm_text_match), cudaMemcpyDefault, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return PGM_OK;
+}
+
+} // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stage 7 on a group of contexts: every GPU holds the source text and its index; the groups of 256 query positions of a
+// destination text are independent (pgm_mem.cuh), so GPU r takes the r-th share of them and the shares are concatenated; the
+// "covered by the previous match" test (CopMEMMatcher.cpp:388-393) runs over the concatenation, across the seams, on the host.
+extern "C" {
+
+int pgm_group_mem_index(pgm_group *g, uint32_t target_match_length, uint32_t min_match_length, uint32_t *params) {
+    if (!g) return PGM_ERR_INVALID_ARG;
+    g->err.clear();
+    g->mem_valid = false;
+    std::vector<std::array<uint32_t, 4>> par(g->size());
+    const int rc = group_run(g, [&](int r) -> int { return pgm_mem_index(g->ctx[r], target_match_length, min_match_length, par[r].data()); });
+    if (rc == PGM_OK && params) for (int k = 0; k < 4; k++) params[k] = par[0][k];
+    return rc;
+}
+
+int pgm_group_mem_match(pgm_group *g, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
+                        uint32_t min_match_length, uint64_t *count) {
+    if (!g || !count) return PGM_ERR_INVALID_ARG;
+    g->err.clear();
+    g->mem_valid = false;
+    const int n = g->size();
+    if (n == 1) {
+        const int rc = pgm_mem_match(g->ctx[0], dest, dest_len, dest_is_src, rev_compl, min_match_length, count);
+        if (rc != PGM_OK) return gfail(g, rc, pgm_last_error(g->ctx[0]));
+        g->mem_out.assign(*count, pgm_text_match{0, 0, 0});
+        const int rc2 = pgm_mem_get_matches(g->ctx[0], g->mem_out.data(), *count);
+        if (rc2 != PGM_OK) return gfail(g, rc2, pgm_last_error(g->ctx[0]));
+        g->mem_valid = true;
+        return PGM_OK;
+    }
+    std::vector<uint64_t> cnt(n, 0);
+    std::vector<std::vector<pgm::MemMatch>> raw(n);
+    std::vector<std::vector<uint64_t>> raw_q(n);
+    const int rc = group_run(g, [&](int r) -> int {
+        pgm_ctx *c = g->ctx[r];
+        int rr = mem_match_impl(c, dest, dest_len, dest_is_src, rev_compl, min_match_length, &cnt[r], r, n, true);
+        if (rr != PGM_OK || !cnt[r]) return rr;
+        raw[r].resize(cnt[r]); raw_q[r].resize(cnt[r]);
+        cudaSetDevice(c->device);
+        cudaError_t e = cudaMemcpyAsync(raw[r].data(), c->mem_raw.p, cnt[r] * sizeof(pgm::MemMatch), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(raw_q[r].data(), c->mem_rawq.p, cnt[r] * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        return e == cudaSuccess ? PGM_OK : cuda_fail(c, e, "pgm_group_mem_match (copy of the raw matches)");
+    });
+    if (rc != PGM_OK) return rc;
+    // the shares in query order; a position is pushed unless its match is the previous visited position's match
+    g->mem_out.clear();
+    const uint32_t K = g->ctx[0]->mem_K;
+    bool have_prev = false;
+    pgm::MemMatch prev{0, 0, 0};
+    for (int r = 0; r < n; r++)
+        for (uint64_t i = 0; i < cnt[r]; i++) {
+            const pgm::MemMatch &m = raw[r][i];
+            if (!(have_prev && m.dest - m.src == prev.dest - prev.src && raw_q[r][i] + K < prev.dest + prev.len))
+                g->mem_out.push_back(pgm_text_match{m.src, m.len, m.dest});
+            prev = m; have_prev = true;
+        }
+    *count = g->mem_out.size();
+    g->mem_valid = true;
+    return PGM_OK;
+}
+
+int pgm_group_mem_get_matches(pgm_group *g, pgm_text_match *out, uint64_t capacity) {
+    if (!g) return PGM_ERR_INVALID_ARG;
+    if (!g->mem_valid) return gfail(g, PGM_ERR_STATE, "pgm_group_mem_get_matches: no result (call pgm_group_mem_match)");
+    if (capacity < g->mem_out.size() || (!g->mem_out.empty() && !out)) return gfail(g, PGM_ERR_INVALID_ARG, "pgm_group_mem_get_matches: capacity below the match count");
+    if (g->mem_out.empty()) return PGM_OK;
+    const cudaError_t e = cudaMemcpy(out, g->mem_out.data(), g->mem_out.size() * sizeof(pgm_text_match), cudaMemcpyDefault);
+    if (e != cudaSuccess) return gfail(g, PGM_ERR_CUDA, std::string("pgm_group_mem_get_matches: ") + cudaGetErrorString(e));
     return PGM_OK;
 }
 

@@ -26,6 +26,9 @@ struct pgm_group {
     uint64_t generation = 0;
     bool failed = false;
     std::vector<pgm_route_buffer> send;         // per rank: the buffer of the exchange in flight
+    // stage 7 (pgm_group_mem_*): the matches of the last pgm_group_mem_match, in the reference's push order
+    std::vector<pgm_text_match> mem_out;
+    bool mem_valid = false;
 
     int size() const { return (int)ctx.size(); }
 };

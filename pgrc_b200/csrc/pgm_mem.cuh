@@ -37,8 +37,10 @@ struct MemParams {
     uint32_t K, k1, k2, hash_mask, min_len, skip;
     int dest_is_src, rev_compl;
     const uint32_t *nib, *coarse, *entries; // the index (pgm_copmem.cuh: compact bucket directory + kept sample indices)
-    uint64_t nq;                    // query positions 0, k2, 2 k2, ... <= N2 - K
-    uint64_t n_groups;              // full groups of the main loop; group n_groups is the tail
+    uint64_t q0, nq;                // this launch's query positions: indices q0 .. q0 + nq - 1 of 0, k2, 2 k2, ... <= N2 - K (q0: a multiple
+                                    // of 256; a context of several takes a range of groups, pgm_group_mem_match)
+    uint64_t n_groups;              // groups of 256 query positions in that range, minus one: the main loop's full groups (:364) and the
+                                    // tail (:422), which has 1 .. 256 positions — ceil(nq / 256) groups, all walked alike
     uint32_t *fv;                   // [nq] sample index of fv(q), 0xFFFFFFFF = none
     uint32_t *has_fv;               // [ceil(nq / 32) + 8] bit per query position
     uint32_t *emit;                 // same shape: visited & fv
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(PGM_MEM_THREADS) mem_query_kernel(const __grid
     const uint64_t pol_keep = policy_evict_last();
     uint32_t found = 0xFFFFFFFFu;
     if (i < p.nq) {
-        const uint64_t q = i * p.k2;
+        const uint64_t q = (p.q0 + i) * p.k2;
         const uint64_t maskK = p.K >= 64 ? ~0ull : ((1ull << p.K) - 1ull);
         const uint64_t lo = mem_bits64(p.dlo, (long long)q), hi = mem_bits64(p.dhi, (long long)q);
         const uint64_t bad = p.dinv ? (mem_bits64(p.dinv, (long long)q) & maskK) : 0ull;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(PGM_MEM_THREADS) mem_extend_kernel(const __gri
     while (m) {
         const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
         m &= m - 1;
-        const uint64_t i = wi * 32 + bit, q = i * p.k2;
+        const uint64_t i = wi * 32 + bit, q = (p.q0 + i) * p.k2;
         const uint64_t s = (uint64_t)p.fv[i] * p.k1;
         const uint64_t b = mem_right(p, s + p.K, q + p.K, min(p.N - s - p.K, p.N2 - q - p.K));
         const uint64_t amax = min(s, q);

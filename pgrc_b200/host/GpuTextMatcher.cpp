@@ -9,27 +9,29 @@
 
 namespace PgTools {
 
-    void GpuTextMatcher::check(int rc, pgm_ctx *ctx, const char *what) {
+    void GpuTextMatcher::check(int rc, pgm_group *g, const char *what) {
         if (rc == PGM_OK) return;
-        fprintf(stderr, "GPU text matcher: %s failed: %s\n", what, pgm_last_error(ctx));
+        fprintf(stderr, "GPU text matcher: %s failed: %s\n", what, pgm_group_last_error(g));
         exit(EXIT_FAILURE);
     }
 
     GpuTextMatcher::GpuTextMatcher(const char *srcText, const size_t srcLength, const uint32_t targetMatchLength, uint32_t minMatchLength)
             : srcLength(srcLength), targetMatchLength(targetMatchLength) {
-        const int device = GpuMatcherSession::devicesFromEnvironment()[0];
-        check(pgm_create(device, &ctx), nullptr, "pgm_create");
-        check(pgm_set_text(ctx, srcText, srcLength), ctx, "pgm_set_text");
+        const vector<int> devices = GpuMatcherSession::devicesFromEnvironment();
+        check(pgm_group_create((int) devices.size(), devices.data(), &grp), nullptr, "pgm_group_create");
+        check(pgm_group_set_text(grp, srcText, srcLength), grp, "pgm_group_set_text");
         uint32_t par[4];
-        check(pgm_mem_index(ctx, targetMatchLength, minMatchLength, par), ctx, "pgm_mem_index");
+        check(pgm_group_mem_index(grp, targetMatchLength, minMatchLength, par), grp, "pgm_group_mem_index");
         // CopMEMMatcher::displayParams (copmem/CopMEMMatcher.cpp:98-108)
         cout << "copMEM PARAMETERS: l = " << targetMatchLength << "; K = " << par[0] << "; HASH_SIZE = " << par[3] << "; k1 = " << par[1]
              << "; k2 = " << par[2] << std::endl;
-        cout << "Pseudogenome text index on the GPU (device " << device << ")" << endl;
+        cout << "Pseudogenome text index on the GPU";
+        if (devices.size() > 1) cout << ", queries shared out over " << devices.size() << " device contexts";
+        cout << endl;
     }
 
     GpuTextMatcher::~GpuTextMatcher() {
-        pgm_destroy(ctx);
+        pgm_group_destroy(grp);
     }
 
     void GpuTextMatcher::matchTexts(vector<TextMatch> &resMatches, const string &destText, bool destIsSrc, bool revComplMatching,
@@ -40,13 +42,13 @@ namespace PgTools {
             exit(EXIT_FAILURE);
         }
         // destIsSrc: the destination is the source (or its reverse complement, SimplePgMatcher.cpp:35-36), which the
-        // device already holds in both orientations — nothing to upload
+        // devices already hold in both orientations — nothing to upload
         uint64_t count = 0;
-        check(pgm_mem_match(ctx, destIsSrc ? nullptr : destText.data(), destText.length(), destIsSrc, revComplMatching, minMatchLength, &count),
-              ctx, "pgm_mem_match");
+        check(pgm_group_mem_match(grp, destIsSrc ? nullptr : destText.data(), destText.length(), destIsSrc, revComplMatching, minMatchLength, &count),
+              grp, "pgm_group_mem_match");
         static_assert(sizeof(TextMatch) == sizeof(pgm_text_match), "TextMatch is three uint64 (matching/TextMatchers.h:11-14)");
         resMatches.resize(count, TextMatch(0, 0, 0));
-        check(pgm_mem_get_matches(ctx, reinterpret_cast<pgm_text_match *>(resMatches.data()), count), ctx, "pgm_mem_get_matches");
+        check(pgm_group_mem_get_matches(grp, reinterpret_cast<pgm_text_match *>(resMatches.data()), count), grp, "pgm_group_mem_get_matches");
         *logout << "Exact matches on the GPU: " << count << endl;
     }
 

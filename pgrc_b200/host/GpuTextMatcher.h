@@ -16,10 +16,10 @@
 namespace PgTools {
 
     class GpuTextMatcher : public TextMatcher {
-        pgm_ctx *ctx = nullptr;
+        pgm_group *grp = nullptr;     // one device context by default; PGRC_GPU_DEVICES=0,1,... shares the query out over several GPUs
         size_t srcLength;
         uint32_t targetMatchLength;
-        static void check(int rc, pgm_ctx *ctx, const char *what);   // message on stderr + exit, the reference's convention
+        static void check(int rc, pgm_group *g, const char *what);   // message on stderr + exit, the reference's convention
     public:
         // = CopMEMMatcher(srcText, srcLength, targetMatchLength, minMatchLength): uploads the source text and builds its index
         GpuTextMatcher(const char *srcText, const size_t srcLength, const uint32_t targetMatchLength, uint32_t minMatchLength = UINT32_MAX);

@@ -424,6 +424,22 @@ class GpuMatcherGroup:
         self._check(self._lib.pgm_group_set_reads(self._h, _ptr(lq_packed) if n_lq else None, n_lq, _ptr(n_packed) if n_n else None, n_n, read_len))
         self.n_reads, self.read_len = n_lq + n_n, read_len
 
+    # -- stage 7 (pgm_group_mem_*): the text set with set_text is the source; every GPU indexes it, the query groups are shared out
+    def mem_index(self, target_match_length: int, min_match_length: int = 0xFFFFFFFF):
+        par = (ctypes.c_uint32 * 4)()
+        self._check(self._lib.pgm_group_mem_index(self._h, target_match_length, min(min_match_length, 0xFFFFFFFF), par))
+        return tuple(int(x) for x in par)
+
+    def match_texts(self, dest_text, dest_is_src: bool = False, rev_compl_matching: bool = True,
+                    min_match_length: int = 0xFFFFFFFF) -> np.ndarray:
+        n2 = 0 if dest_text is None else (dest_text.numel() if hasattr(dest_text, "numel") else dest_text.size)
+        cnt = ctypes.c_uint64(0)
+        self._check(self._lib.pgm_group_mem_match(self._h, _ptr(dest_text), n2, int(dest_is_src), int(rev_compl_matching),
+                                                  min(min_match_length, 0xFFFFFFFF), ctypes.byref(cnt)))
+        out = np.empty((int(cnt.value), 3), np.uint64)
+        self._check(self._lib.pgm_group_mem_get_matches(self._h, out.ctypes.data if out.size else None, int(cnt.value)))
+        return out
+
     def run_plan(self, plan: "MatchPlan", rev_compl_pg: bool = True):
         """The phases of mapReadsIntoPg through the step-wise group calls (as the C++ matcher classes issue them)."""
         for seed_len, parts, max_mm, min_mm, cont, ilv in plan.phases:

@@ -111,6 +111,7 @@ def test_archive_identical_with_the_stage_sharded_over_several_device_contexts(t
     devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
     got, out = _compress(str(tmp_path), "gpu2", True, f1, f2, c["flags"], devices=devs)
     assert "sharded over 2 device contexts" in out
+    assert "queries shared out over 2 device contexts" in out          # stage 7 (GpuTextMatcher) over the same device list
     assert got == ref, f"{name}: archives differ with PGRC_GPU_DEVICES={devs}"
     got3, _ = _compress(str(tmp_path), "gpu3", True, f1, f2, c["flags"], devices="0,0,0")
     assert got3 == ref

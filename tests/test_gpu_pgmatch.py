@@ -94,6 +94,28 @@ def test_medium_size_shape_of_a_pseudogenome():
         assert _check(src, dest, True, True, 45, tm=tm, null_dest=True) > 500
 
 
+@pytest.mark.parametrize("n_ctx", [1, 2, 3, 5])
+def test_group_of_contexts_shares_the_query_groups(n_ctx):
+    """pgm_group_mem_*: every context indexes the source, context r takes the r-th share of the groups of 256 query positions,
+    the shares are concatenated and the "covered by the previous match" test runs across the seams.  Real GPUs when the box has
+    them, else several contexts on GPU 0.  Long matches that span the seams, short destinations (fewer groups than contexts)."""
+    import torch
+    have = torch.cuda.device_count()
+    devs = [k % have for k in range(n_ctx)]
+    src, dest = synth.pg_texts(950 + n_ctx, 60000, 20000, max_copy=6000, self_rc=60)
+    with matcher.GpuMatcherGroup(devs) as g:
+        g.set_text(src)
+        assert g.mem_index(45)[:3] == (32, 4, 3)
+        total = 0
+        for d, dis, rc in ((dest, False, True), (dest, False, False), (src, True, True), (dest[:700], False, True), (dest[:40], False, False)):
+            q = oracle.reverse_complement(d) if rc else np.ascontiguousarray(d)
+            want = oracle.oracle_match_texts(src, q, dis, rc, 45)
+            got = g.match_texts(None if dis else q, dis, rc)
+            assert got.shape == want.shape and np.array_equal(got, want), (n_ctx, dis, rc, got.shape, want.shape)
+            total += len(want)
+        assert total > 100
+
+
 @pytest.mark.skipif(not GOLDEN, reason="no pgmatch golden vectors")
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_reference_golden_vectors(path):
