@@ -62,7 +62,9 @@ def hashes(text, starts, K, hash_size):
     return (h & np.uint64(0xFFFFFFFF) & np.uint64(hash_size - 1)).astype(np.int64)
 
 
-def match_texts(src, dest, dest_is_src, rev_compl, target_len, min_len=0xFFFFFFFF):
+def match_texts(src, dest, dest_is_src, rev_compl, target_len, min_len=0xFFFFFFFF, n_parts=1):
+    """n_parts > 1: the groups of 256 query positions shared out over that many contexts as pgm_group_mem_match does it
+    (context r: groups [G r / n, G (r + 1) / n)), the shares concatenated and the suppression test run across the seams."""
     src = np.asarray(src, np.uint8); dest = np.asarray(dest, np.uint8)
     N, N2 = len(src), len(dest)
     K, k1, k2, hs = derive(target_len, min_len, N)
@@ -106,14 +108,17 @@ def match_texts(src, dest, dest_is_src, rev_compl, target_len, min_len=0xFFFFFFF
     n_groups = 0
     while n_groups * MULTI * k2 + K + MULTI * k2 < N2 + 1:
         n_groups += 1
+    assert nq == 0 or n_groups + 1 == (nq + MULTI - 1) // MULTI      # the tail (:422-473) has 1 .. 256 positions: ceil(nq / 256) groups in all
+    groups = (nq + MULTI - 1) // MULTI
     visited = []
-    for g in range(n_groups + 1):
-        t, end = g * MULTI, ((g + 1) * MULTI if g < n_groups else nq)
-        while t < end:
-            if fvm[t] is not None:
-                visited.append(t); t += skip + 1
-            else:
-                t += 1
+    for r in range(n_parts):                                           # (a context's share; the walk of a group never looks outside it)
+        for g in range(groups * r // n_parts, groups * (r + 1) // n_parts):
+            t, end = g * MULTI, min((g + 1) * MULTI, nq)
+            while t < end:
+                if fvm[t] is not None:
+                    visited.append(t); t += skip + 1
+                else:
+                    t += 1
     out, prev = [], None
     for t in visited:
         m, q = fvm[t], t * k2

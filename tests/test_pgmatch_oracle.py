@@ -84,3 +84,15 @@ def test_oracle_against_the_reference_live(seed):
         want = oracle.ref_match_texts(src, q, dis, rc, L, min_len, threads=1)
         got = oracle.oracle_match_texts(src, q, dis, rc, L, min_len)
         assert got.shape == want.shape and np.array_equal(got, want), (tag, got.shape, want.shape)
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 7])
+def test_query_groups_shared_out_over_several_contexts(n_parts):
+    """The host logic of pgm_group_mem_match (ranges of groups per context, concatenation, suppression across the seams) in the
+    CPU model against the sequential oracle; long copies so that matches span the seams."""
+    src, dest = synth.pg_texts(640 + n_parts, 30000, 9000, max_copy=5000, self_rc=40)
+    for tag, dis, rc in CALLS:
+        q = _query(src, dest, dis, rc)
+        want = oracle.oracle_match_texts(src, q, dis, rc, 45)
+        got = cpu_mem_model.match_texts(src, q, dis, rc, 45, n_parts=n_parts)
+        assert got.shape == want.shape and np.array_equal(got, want), (tag, n_parts)
