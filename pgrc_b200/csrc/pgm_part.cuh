@@ -17,6 +17,12 @@
 //   scan_kernel<MODE 2> the fused kernel with that bitmap in place of stage A1 (hash + filter gather): the set bits ARE the
 //                       windows with a table hit — 1.4 % of the positions at config 5 instead of 63 % — and stages A2 (probe)
 //                       and B (verification against the staged text, accept test, atomicMin) run unchanged on them.
+// STATUS: opt-in (PGM_PART_SCAN=1 auto / 2 always / 3 always with tiny queues), off by default.  Measured at config 5 on B200
+// (profiles/bench_c5_n1_part_r02x.json): bit-exact, but 1312 ms per step against 450 for the sliced Bloom filter — emit 917 ms
+// (a lane per window and 512 queues: every warp store touches 32 sectors), probe 177 ms (each partition sweep walks the round's
+// whole 234 MB bitmap), fused kernel on the bitmap 107 ms.  It also showed that 11.6 % of config 5's windows are TRUE table
+// hits: even a perfect pre-filter leaves 53 ms per pass of bucket + record lines, so a well-engineered version of this pipeline
+// would gain about 20 % per pass at best.
 // The bitmap may be conservative (a window whose queue was full is marked without probing; stage A2 probes it again) but
 // never misses a hit: part_probe_kernel walks the same probe sequence with the same stop rule as stage A2.  The result is the
 // fused kernel's, bit for bit (tests: PGM_PART_SCAN=2 / 3 force the pipeline, 3 with tiny queues).
