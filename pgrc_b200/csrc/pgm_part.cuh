@@ -15,7 +15,7 @@
 //                       the partition stays in the L2), the fused kernel's probe sequence; a tag hit sets the window's bit in
 //                       a bitmap over the round's text positions.
 //   scan_kernel<MODE 2> the fused kernel with that bitmap in place of stage A1 (hash + filter gather): the set bits ARE the
-//                       windows with a table hit — 1.4 % of the positions at config 5 instead of 63 % — and stages A2 (probe)
+//                       windows with a table hit — 11.6 % of the positions at config 5 instead of the 63 % a Bloom filter passes — and stages A2 (probe)
 //                       and B (verification against the staged text, accept test, atomicMin) run unchanged on them.
 // STATUS: opt-in (PGM_PART_SCAN=1 auto / 2 always / 3 always with tiny queues), off by default.  Measured at config 5 on B200
 // (profiles/bench_c5_n1_part_r02x.json): bit-exact, but 1312 ms per step against 450 for the sliced Bloom filter — emit 917 ms
