@@ -17,6 +17,7 @@
 #include <cstring>
 #include <unistd.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -75,6 +76,13 @@ struct pgm_ctx {
     bool text_pending = false, text_copies_enqueued = false;
     const uint8_t *h_lq = nullptr, *h_n = nullptr;
     bool reads_pending = false;
+    // PAGEABLE host inputs (what PgRC's std::string / std::vector are): cudaMemcpyAsync would stage them inside the driver on
+    // one thread at 8 - 10 GB/s and block the caller meanwhile.  Instead each chunk is copied by several host threads into one
+    // of four pinned slots and sent from there, while the kernels of the chunks before it run (h2d_chunk).
+    struct HostStage { void *buf[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+                       bool busy[4] = {false, false, false, false}; size_t bytes = 0; int next = 0; } hstage;
+    bool text_pageable = false;         // the pending host text is pageable: its chunks are staged one by one as the scan asks for them
+    uint64_t text_chunks_sent = 0;
 
     // reads: one record per read (header {state, key} + bit planes), see pgm_kernels.cuh
     DevBuf packed_stage, lq_recs, n_recs;
@@ -284,6 +292,92 @@ cudaEvent_t chunk_event(std::vector<cudaEvent_t> &pool, size_t i) {
     return pool[i];
 }
 
+bool is_pageable_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+void parallel_memcpy(void *dst, const void *src, size_t n) {
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t per_min = 2u << 20;
+    const unsigned want = (unsigned)std::min<size_t>(std::min<unsigned>(8u, std::max(1u, hw / 2)), std::max<size_t>(1, n / per_min));
+    if (want <= 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((n + want - 1) / want + 63) & ~(size_t)63;
+    for (unsigned k = 1; k < want; k++) {
+        const size_t b = std::min(n, k * per), e = std::min(n, (k + 1) * per);
+        if (e > b) th.emplace_back([=] { memcpy(static_cast<char *>(dst) + b, static_cast<const char *>(src) + b, e - b); });
+    }
+    memcpy(dst, src, std::min(n, per));
+    for (auto &t : th) t.join();
+}
+
+// four pinned slots of at least `bytes` each
+int ensure_hstage(pgm_ctx *ctx, size_t bytes) {
+    pgm_ctx::HostStage &hs = ctx->hstage;
+    if (hs.bytes >= bytes) return PGM_OK;
+    for (int k = 0; k < 4; k++) {
+        if (hs.busy[k]) { CU(cudaEventSynchronize(hs.ev[k])); hs.busy[k] = false; }
+        if (hs.buf[k]) { CU(cudaFreeHost(hs.buf[k])); hs.buf[k] = nullptr; }
+    }
+    hs.bytes = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+    for (int k = 0; k < 4; k++) {
+        CU(cudaHostAlloc(&hs.buf[k], hs.bytes, cudaHostAllocDefault));
+        if (!hs.ev[k]) CU(cudaEventCreateWithFlags(&hs.ev[k], cudaEventDisableTiming));
+    }
+    return PGM_OK;
+}
+
+// A result array to the caller, stream-ordered behind the kernels that produce it.  Device and pinned destinations: one
+// asynchronous copy.  Pageable destinations: the copy engine fills the pinned slots (up to four copies in flight) and host
+// threads move each slot on into the caller's memory — the driver's own staging does this on one thread.
+int d2h_out(pgm_ctx *ctx, void *dst, const void *src, size_t n) {
+    if (n < (4u << 20) || is_device_ptr(dst) || !is_pageable_host(dst)) {
+        CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, ctx->stream));
+        return PGM_OK;
+    }
+    pgm_ctx::HostStage &hs = ctx->hstage;
+    { int rc = ensure_hstage(ctx, std::min<size_t>(n, 32u << 20)); if (rc) return rc; }
+    for (int k = 0; k < 4; k++) if (hs.busy[k]) { CU(cudaEventSynchronize(hs.ev[k])); hs.busy[k] = false; }
+    const size_t chunk = hs.bytes, n_chunks = (n + chunk - 1) / chunk;
+    size_t issued = 0, done = 0;
+    while (done < n_chunks) {
+        while (issued < n_chunks && issued - done < 4) {
+            const size_t off = issued * chunk, len = std::min(chunk, n - off);
+            CU(cudaMemcpyAsync(hs.buf[issued & 3], static_cast<const char *>(src) + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaEventRecord(hs.ev[issued & 3], ctx->stream));
+            issued++;
+        }
+        const size_t off = done * chunk, len = std::min(chunk, n - off);
+        CU(cudaEventSynchronize(hs.ev[done & 3]));
+        parallel_memcpy(static_cast<char *>(dst) + off, hs.buf[done & 3], len);
+        done++;
+    }
+    return PGM_OK;
+}
+
+// One chunk of a host input to the device on the copy stream; `done` is recorded behind it.  Pinned / registered memory goes
+// straight to the copy engine; pageable memory through the context's pinned slots (see pgm_ctx::hstage).
+int h2d_chunk(pgm_ctx *ctx, void *dst, const void *src, size_t n, cudaEvent_t done, bool pageable) {
+    if (!pageable || n < (1u << 20)) {                 // (small pageable copies: the driver's own staging is as good)
+        CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(done, ctx->copy_stream));
+        return PGM_OK;
+    }
+    pgm_ctx::HostStage &hs = ctx->hstage;
+    { int rc = ensure_hstage(ctx, n); if (rc) return rc; }
+    const int k = hs.next;
+    hs.next = (hs.next + 1) & 3;
+    if (hs.busy[k]) { CU(cudaEventSynchronize(hs.ev[k])); hs.busy[k] = false; }      // the DMA that last read this slot
+    parallel_memcpy(hs.buf[k], src, n);
+    CU(cudaMemcpyAsync(dst, hs.buf[k], n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(hs.ev[k], ctx->copy_stream));
+    hs.busy[k] = true;
+    CU(cudaEventRecord(done, ctx->copy_stream));
+    return PGM_OK;
+}
+
 // The copy stream may overwrite the staging buffers only after everything queued so far on the main stream
 // (the kernels of the previous call that read them) has finished.
 int fence_copy_stream(pgm_ctx *ctx) {
@@ -298,12 +392,29 @@ uint64_t text_chunks(const pgm_ctx *ctx) { return (ctx->slice_len + TEXT_CHUNK_B
 int enqueue_text_copies(pgm_ctx *ctx, bool fence) {
     if (!ctx->text_pending || ctx->text_copies_enqueued) return PGM_OK;
     if (fence) { int rc = fence_copy_stream(ctx); if (rc) return rc; }
+    ctx->text_pageable = ctx->slice_len != 0 && is_pageable_host(ctx->h_text);
+    ctx->text_chunks_sent = 0;
+    ctx->text_copies_enqueued = true;
+    if (ctx->text_pageable) return PGM_OK;               // staged chunk by chunk when the consumer asks (text_chunk_ready)
     for (uint64_t c = 0, off = 0; off < ctx->slice_len; c++, off += TEXT_CHUNK_BASES) {
         const uint64_t n = std::min<uint64_t>(TEXT_CHUNK_BASES, ctx->slice_len - off);
-        CU(cudaMemcpyAsync(ctx->ascii_stage.as<uint8_t>() + off, ctx->h_text + off, n, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CU(cudaEventRecord(chunk_event(ctx->text_ev, c), ctx->copy_stream));
+        int rc = h2d_chunk(ctx, ctx->ascii_stage.as<uint8_t>() + off, ctx->h_text + off, n, chunk_event(ctx->text_ev, c), false);
+        if (rc) return rc;
     }
-    ctx->text_copies_enqueued = true;
+    ctx->text_chunks_sent = text_chunks(ctx);
+    return PGM_OK;
+}
+
+// Chunk c of a pending host text is on its way (its event recorded): a pageable text is staged here, in order, so that the
+// host copies of chunk c + 1 run while the kernels of chunk c do.
+int text_chunk_ready(pgm_ctx *ctx, uint64_t c) {
+    while (ctx->text_chunks_sent <= c) {
+        const uint64_t k = ctx->text_chunks_sent, off = k * TEXT_CHUNK_BASES;
+        const uint64_t n = std::min<uint64_t>(TEXT_CHUNK_BASES, ctx->slice_len - off);
+        int rc = h2d_chunk(ctx, ctx->ascii_stage.as<uint8_t>() + off, ctx->h_text + off, n, chunk_event(ctx->text_ev, k), true);
+        if (rc) return rc;
+        ctx->text_chunks_sent++;
+    }
     return PGM_OK;
 }
 
@@ -332,6 +443,7 @@ int finish_text_upload(pgm_ctx *ctx) {
     int rc = enqueue_text_copies(ctx, true);
     if (rc) return rc;
     for (uint64_t c = 0; c < text_chunks(ctx); c++) {
+        if ((rc = text_chunk_ready(ctx, c))) return rc;
         CU(cudaStreamWaitEvent(ctx->stream, ctx->text_ev[c], 0));
         if ((rc = pack_text_chunk(ctx, ctx->ascii_stage.as<uint8_t>(), c))) return rc;
     }
@@ -403,33 +515,31 @@ int upload_reads(pgm_ctx *ctx, bool build) {
     reads_parts(ctx, ctx->h_lq, ctx->h_n, parts);
     int rc = fence_copy_stream(ctx);
     if (rc) return rc;
+    // chunk by chunk: the copy of chunk c is queued (pageable memory: staged by host threads first), then its unpack and table
+    // inserts behind the copy's event — they run while the host stages / the copy engine moves chunk c + 1
     size_t ev = 0;
-    struct Chunk { int part; uint32_t first, cnt; size_t ev; };
-    std::vector<Chunk> chunks;
+    const bool pageable[2] = {parts[0].host && is_pageable_host(parts[0].src), parts[1].host && is_pageable_host(parts[1].src)};
+    bool text_queued = false;
     for (int k = 0; k < 2; k++) {
         const ReadsPart &pt = parts[k];
-        for (uint32_t first = 0; first < pt.cnt; first += READS_CHUNK) {
+        for (uint32_t first = 0; first < pt.cnt; first += READS_CHUNK, ev++) {
             const uint32_t cnt = std::min<uint32_t>(READS_CHUNK, pt.cnt - first);
+            const uint8_t *src = pt.src;
             if (pt.host) {
-                CU(cudaMemcpyAsync(ctx->packed_stage.as<uint8_t>() + pt.stage_off + (size_t)first * pt.plen, pt.src + (size_t)first * pt.plen,
-                                   (size_t)cnt * pt.plen, cudaMemcpyHostToDevice, ctx->copy_stream));
-                CU(cudaEventRecord(chunk_event(ctx->reads_ev, ev), ctx->copy_stream));
+                if ((rc = h2d_chunk(ctx, ctx->packed_stage.as<uint8_t>() + pt.stage_off + (size_t)first * pt.plen, pt.src + (size_t)first * pt.plen,
+                                    (size_t)cnt * pt.plen, chunk_event(ctx->reads_ev, ev), pageable[k]))) return rc;
+                CU(cudaStreamWaitEvent(ctx->stream, ctx->reads_ev[ev], 0));
+                src = ctx->packed_stage.as<uint8_t>() + pt.stage_off;
             }
-            chunks.push_back({k, first, cnt, ev});
-            ev++;
+            // (pinned inputs: the copies are asynchronous, so the text's copies are queued behind the LAST read chunk's copy
+            // before that chunk's kernels are launched — the copy engine never waits for the host)
+            const bool last = (k == 1 || parts[1].cnt == 0) && first + READS_CHUNK >= pt.cnt;
+            if (last && !text_queued) { if ((rc = enqueue_text_copies(ctx, false))) return rc; text_queued = true; }
+            if ((rc = unpack_range(ctx, pt, src, first, cnt))) return rc;
+            if (build && (rc = build_range(ctx, pt.first_read + first, pt.first_read + first + cnt, 0))) return rc;
         }
     }
-    if ((rc = enqueue_text_copies(ctx, false))) return rc;
-    for (const Chunk &c : chunks) {
-        const ReadsPart &pt = parts[c.part];
-        const uint8_t *src = pt.src;
-        if (pt.host) {
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->reads_ev[c.ev], 0));
-            src = ctx->packed_stage.as<uint8_t>() + pt.stage_off;
-        }
-        if ((rc = unpack_range(ctx, pt, src, c.first, c.cnt))) return rc;
-        if (build && (rc = build_range(ctx, pt.first_read + c.first, pt.first_read + c.first + c.cnt, 0))) return rc;
-    }
+    if (!text_queued && (rc = enqueue_text_copies(ctx, false))) return rc;
     ctx->reads_pending = false;
     ctx->state_fresh = true;
     return PGM_OK;
@@ -656,6 +766,10 @@ void pgm_destroy(pgm_ctx *ctx) {
     for (cudaEvent_t e : ctx->reads_ev) cudaEventDestroy(e);
     for (auto &kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
     if (ctx->rt_counts_host) cudaFreeHost(ctx->rt_counts_host);
+    for (int k = 0; k < 4; k++) {
+        if (ctx->hstage.buf[k]) cudaFreeHost(ctx->hstage.buf[k]);
+        if (ctx->hstage.ev[k]) cudaEventDestroy(ctx->hstage.ev[k]);
+    }
     for (int k = 0; k < 3; k++) for (int sl = 0; sl < 2; sl++) if (ctx->counts_ev[k][sl]) cudaEventDestroy(ctx->counts_ev[k][sl]);
     for (int k = 0; k < 3; k++) for (int sl = 0; sl < 2; sl++) if (ctx->consumed_ev[k][sl]) cudaEventDestroy(ctx->consumed_ev[k][sl]);
     for (int k = 0; k < 3; k++) for (int sl = 0; sl < 2; sl++) if (ctx->pull_ev[k][sl]) cudaEventDestroy(ctx->pull_ev[k][sl]);
@@ -1106,6 +1220,7 @@ int pgm_scan_pass(pgm_ctx *ctx, int rev_mode) {
     uint64_t done = fb;
     const uint64_t nchunks = text_chunks(ctx);
     for (uint64_t c = 0; c < nchunks; c++) {
+        if ((rc = text_chunk_ready(ctx, c))) return rc;
         CU(cudaStreamWaitEvent(ctx->stream, ctx->text_ev[c], 0));
         if ((rc = pack_text_chunk(ctx, ctx->ascii_stage.as<uint8_t>(), c))) return rc;
         const uint64_t have = ctx->slice_begin + std::min<uint64_t>(ctx->slice_len, (c + 1) * TEXT_CHUNK_BASES);   // bases [slice_begin, have) are packed
@@ -1210,9 +1325,10 @@ int pgm_get_results(pgm_ctx *ctx, uint64_t *out_pos, uint8_t *out_rc, uint8_t *o
                 ctx->hist.as<unsigned long long>()));
             ctx->outputs_valid = true;
         }
-        if (out_pos) CU(cudaMemcpyAsync(out_pos, ctx->out_pos.p, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
-        if (out_rc) CU(cudaMemcpyAsync(out_rc, ctx->out_rc.p, n, cudaMemcpyDefault, ctx->stream));
-        if (out_mm) CU(cudaMemcpyAsync(out_mm, ctx->out_mm.p, n, cudaMemcpyDefault, ctx->stream));
+        int rc2;
+        if (out_pos && (rc2 = d2h_out(ctx, out_pos, ctx->out_pos.p, (size_t)n * 8))) return rc2;
+        if (out_rc && (rc2 = d2h_out(ctx, out_rc, ctx->out_rc.p, n))) return rc2;
+        if (out_mm && (rc2 = d2h_out(ctx, out_mm, ctx->out_mm.p, n))) return rc2;
     } else {
         CU(cudaMemsetAsync(ctx->hist.p, 0, 257 * sizeof(unsigned long long), ctx->stream));
     }
