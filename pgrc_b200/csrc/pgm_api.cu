@@ -71,7 +71,7 @@ struct pgm_ctx {
     // table-build / forward-scan kernels of the chunks that have already arrived (pgm_match_begin, pgm_scan_pass)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t fence_ev = nullptr;
-    std::vector<cudaEvent_t> text_ev, reads_ev;
+    std::vector<cudaEvent_t> text_ev, reads_ev, mem_ev;
     const uint8_t *h_text = nullptr;
     bool text_pending = false, text_copies_enqueued = false;
     const uint8_t *h_lq = nullptr, *h_n = nullptr;
@@ -764,6 +764,7 @@ void pgm_destroy(pgm_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_free) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->text_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->reads_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->mem_ev) cudaEventDestroy(e);
     for (auto &kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
     if (ctx->rt_counts_host) cudaFreeHost(ctx->rt_counts_host);
     for (int k = 0; k < 4; k++) {
@@ -2189,7 +2190,17 @@ int mem_match_impl(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_i
         const uint8_t *src = reinterpret_cast<const uint8_t *>(dest);
         if (dest_len && !is_device_ptr(dest)) {
             if ((rc = ensure(ctx, ctx->mem_stage, dest_len))) return rc;
-            CU(cudaMemcpyAsync(ctx->mem_stage.p, dest, dest_len, cudaMemcpyHostToDevice, ctx->stream));
+            if (dest_len < (8u << 20) || !is_pageable_host(dest)) {
+                CU(cudaMemcpyAsync(ctx->mem_stage.p, dest, dest_len, cudaMemcpyHostToDevice, ctx->stream));
+            } else {
+                // a pageable destination text (PgRC's std::string): staged by host threads through the pinned slots (h2d_chunk)
+                if ((rc = fence_copy_stream(ctx))) return rc;
+                uint64_t c = 0;
+                for (uint64_t off = 0; off < dest_len; off += TEXT_CHUNK_BASES, c++)
+                    if ((rc = h2d_chunk(ctx, ctx->mem_stage.as<uint8_t>() + off, dest + off, std::min<uint64_t>(TEXT_CHUNK_BASES, dest_len - off),
+                                        chunk_event(ctx->mem_ev, c), true))) return rc;
+                CU(cudaStreamWaitEvent(ctx->stream, ctx->mem_ev[c - 1], 0));
+            }
             src = ctx->mem_stage.as<uint8_t>();
         }
         uint32_t *dlo = ctx->mem_dlo.as<uint32_t>() + PGM_PAD_WORDS, *dhi = ctx->mem_dhi.as<uint32_t>() + PGM_PAD_WORDS,
