@@ -2,7 +2,9 @@
 (oracle.oracle_match_texts, pinned against the reference's CopMEMMatcher) and the committed golden vectors of the
 reference.  Bit-exact: the raw resMatches vector in push order."""
 import glob
+import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -128,6 +130,32 @@ def test_reference_golden_vectors(path):
             q = oracle.reverse_complement(d) if rc else d
             got = tm.match_texts(q, dis, rc, int(z["min_len"]))
             assert np.array_equal(got, z["matches_" + tag]), tag
+
+
+FULLSIZE = [("c2", 0.05, "pgmatch_fullsize_c2_x0.05.json"), ("c2", 1.0, "pgmatch_fullsize_c2.json"), ("c3", 1.0, "pgmatch_fullsize_c3.json")]
+
+
+@pytest.mark.parametrize("workload,scale,fixture", FULLSIZE, ids=[f[2][:-5] for f in FULLSIZE])
+def test_full_size_texts_against_the_reference_run(workload, scale, fixture):
+    """The pseudogenome of a BASELINE config (counter-based generator: the same bytes here and in the build container) against
+    its own reverse complement and against a derived destination: count and sha256 of both raw resMatches vectors equal the
+    REFERENCE's own one-thread run (tests/golden/make_fullsize_pgmatch.py: 140.6 Mbp and 250 Mbp texts, where the sequential
+    oracle agreed with the reference too).  Also through a group of three contexts."""
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import pgmatch_bench
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fixture)))
+    src, dest, dest_rc = pgmatch_bench.stage7_texts(workload, scale, torch.device("cuda", 0))
+    assert int(src.numel()) == want["src_bases"] and int(dest_rc.numel()) == want["dest_bases"]
+    with matcher.GpuTextMatcher(src, want["target_len"]) as tm:
+        assert pgmatch_bench.result_digest(tm.match_texts(None, True, True)) == want["self_rc"]
+        assert pgmatch_bench.result_digest(tm.match_texts(dest_rc, False, True)) == want["lq"]
+    if scale < 1.0 or workload == "c2":
+        with matcher.GpuMatcherGroup([0, 0, 0]) as g:
+            g.set_text(src)
+            g.mem_index(want["target_len"])
+            assert pgmatch_bench.result_digest(g.match_texts(None, True, True)) == want["self_rc"]
+            assert pgmatch_bench.result_digest(g.match_texts(dest_rc, False, True)) == want["lq"]
 
 
 def test_errors_are_loud():
