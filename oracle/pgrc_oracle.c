@@ -540,6 +540,83 @@ static uint64_t copmem_query(const copmem_index *x, const char *read, uint32_t N
     return match_pos;
 }
 
+/* The STAGED form of copmem_query that the warp-per-read CUDA kernels use (pgrc_b200/csrc/pgm_copmem_warp.cuh), as a CPU model
+ * (pgo_set_copmem_staged(1) makes mode 'c' run through it; tests compare it with the sequential transcription above):
+ *   stage 1  every read offset: hash, bucket; every bucket entry: its alignment start a = sp - i1, or "skipped" (:512, :514);
+ *            the DISTINCT alignments of the read are verified once each, with both mismatch counts in full (first trim8
+ *            characters / tail) and kept in a table of CMS_VT entries; a candidate becomes a one-byte index into it;
+ *   stage 2  the sequential loop replayed over those bytes: bucket truncation by the false-match budget, strict improvement,
+ *            the +1 / +2 false-match accounting, the early stop at min_mm.
+ * Exact because a verification's outcome under any limit follows from the two full counts: blocks > limit -> +1 false match;
+ * else blocks + tail > limit -> +2; else accept.  More than CMS_VT distinct alignments: the read takes the sequential path. */
+#ifndef CMS_VT
+#define CMS_VT 32
+#endif
+static int g_copmem_staged = 0;
+void pgo_set_copmem_staged(int on) { g_copmem_staged = on; }
+
+static uint64_t copmem_query_staged(const copmem_index *x, const char *read, uint32_t N2, uint8_t max_mm, uint8_t min_mm,
+                                    uint8_t *mismatches, uint64_t *better, uint64_t *false_matches) {
+    const uint32_t n_off = N2 >= x->K ? (N2 - x->K) / x->k2 + 1 : 0;
+    const uint32_t n2trim8 = (N2 / 8) * 8;
+    uint8_t *lens = (uint8_t *)malloc(n_off + 1), *cand = (uint8_t *)malloc((size_t)n_off * (CM_COLLISIONS_LIMIT + 1) + 1);
+    uint64_t vt_a[CMS_VT];
+    uint8_t vt_db[CMS_VT], vt_dt[CMS_VT];
+    uint32_t n_vt = 0, n_cand = 0;
+    int overflow = 0;
+    for (uint32_t o = 0; o < n_off && !overflow; o++) {                        /* stage 1 */
+        const uint32_t i1 = o * x->k2;
+        const uint32_t h = copmem_hash(x, read + i1);
+        const uint32_t b0 = x->cumm[h], b1 = x->cumm[h + 1];
+        lens[o] = (uint8_t)(b1 - b0);
+        for (uint32_t j = b0; j < b1 && !overflow; j++) {
+            const uint64_t sp = x->pos[j];
+            uint8_t v = 0xFF;
+            if (i1 <= sp && sp - i1 + N2 <= x->N) {
+                const uint64_t a = sp - i1;
+                uint32_t k = 0;
+                while (k < n_vt && vt_a[k] != a) k++;
+                if (k == n_vt) {
+                    if (n_vt == CMS_VT) { overflow = 1; break; }
+                    const char *txt = x->text + a;
+                    uint32_t db = 0, dt = 0;
+                    for (uint32_t p = 0; p < N2; p++) if (read[p] != txt[p]) { if (p < n2trim8) db++; else dt++; }
+                    vt_a[k] = a; vt_db[k] = (uint8_t)db; vt_dt[k] = (uint8_t)dt; n_vt++;
+                }
+                v = (uint8_t)k;
+            }
+            cand[n_cand++] = v;
+        }
+    }
+    if (overflow) { free(lens); free(cand); return copmem_query(x, read, N2, max_mm, min_mm, mismatches, better, false_matches); }
+    if (*mismatches < max_mm) max_mm = (uint8_t)(*mismatches - 1);              /* stage 2 */
+    const uint64_t limit = (uint64_t)((N2 + 1 - x->K) / x->k2) * CM_AVG_COLLISIONS_LIMIT;
+    uint64_t cur_false = 0, match_pos = PGO_NOT_MATCHED_POSITION;
+    uint32_t base = 0;
+    int done = 0;
+    for (uint32_t o = 0; o < n_off && !done; o++) {
+        const uint32_t len = lens[o];
+        uint32_t lim = len;
+        if (limit < cur_false && len > CM_TRUNCATED_BUCKET) lim = CM_TRUNCATED_BUCKET;
+        for (uint32_t t = 0; t < lim; t++) {
+            const uint8_t v = cand[base + t];
+            if (v == 0xFF) continue;
+            const uint32_t db = vt_db[v], dt = vt_dt[v];
+            if (db > max_mm) { cur_false++; continue; }
+            if (db + dt > max_mm) { cur_false += 2; continue; }
+            if (*mismatches != 255) (*better)++;
+            *mismatches = (uint8_t)(db + dt);
+            match_pos = vt_a[v];
+            if (db + dt <= min_mm) { done = 1; break; }
+            max_mm = (uint8_t)(db + dt - 1);
+        }
+        base += len;
+    }
+    *false_matches += cur_false;
+    free(lens); free(cand);
+    return match_pos;
+}
+
 /* CopMEMReadsApproxMatcher::executeMatching (ReadsMatchers.cpp:421-451), one thread */
 static int copmem_pass(matcher *m, const char *txt, int rev_mode) {
     copmem_index x;
@@ -551,8 +628,8 @@ static int copmem_pass(matcher *m, const char *txt, int rev_mode) {
         if (m->mm[r] <= m->min_mm) continue;
         get_read(m->rs, r, m->cur_read);
         uint8_t c = m->mm[r];
-        const uint64_t p = copmem_query(&x, m->cur_read, m->matching_len, m->max_mm, m->min_mm, &c, &m->st->better,
-                                        &m->st->false_matches);
+        const uint64_t p = (g_copmem_staged ? copmem_query_staged : copmem_query)(&x, m->cur_read, m->matching_len, m->max_mm, m->min_mm, &c,
+                                                                                   &m->st->better, &m->st->false_matches);
         if (p == PGO_NOT_MATCHED_POSITION) continue;
         if (c < m->mm[r]) {
             if (m->mm[r] == PGO_NOT_MATCHED_COUNT) m->st->matched++;
