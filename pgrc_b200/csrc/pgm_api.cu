@@ -6,6 +6,7 @@
 #include "pgm_blocked.cuh"
 #include "pgm_part.cuh"
 #include "pgm_copmem.cuh"
+#include "pgm_copmem_warp.cuh"
 #include "pgm_mem.cuh"
 #include "pgm_routed.cuh"
 
@@ -60,6 +61,7 @@ struct pgm_ctx {
     int region_mb = 12, range_mb = 16;   // target sizes of a table region / a read range of the pipeline (PGM_REGION_MB, PGM_RANGE_MB)
     int part_scan = 0;          // partitioned exact pre-filter (pgm_part.cuh), opt-in (measured slower at config 5): 0 off, 1 auto (pattern sets beyond the Bloom filter), 2 always, 3 always with tiny queues (PGM_PART_SCAN; tests)
     int part_mb = 48;           // target size of a table partition (PGM_PART_MB)
+    int cm_warp = 0;            // mode 'c': the staged warp-per-read query (pgm_copmem_warp.cuh) instead of the thread-per-read kernel (PGM_CM_WARP)
     size_t persist_max = 0, window_max = 0, persist_set = 0;
 
     // text
@@ -102,6 +104,7 @@ struct pgm_ctx {
     DevBuf mis_sums, mis_offsets, mis_pos, mis_syms;   // mismatch lists (pgm_get_mismatches)
     // mode 'c' (pgm_copmem.cuh): per-pass text index + parameters of the current CopMEM phase
     DevBuf cm_count, cm_start, cm_cumm, cm_fill, cm_hash, cm_all, cm_entries, cm_sums, cm_nib, cm_coarse;
+    DevBuf cmw_lens, cmw_cand, cmw_vt, cmw_nvt;     // per-read candidate streams of the staged query (pgm_copmem_warp.cuh)
     uint32_t cm_K = 0, cm_k1 = 0, cm_k2 = 0, cm_hash_size = 0;
     bool copmem_active = false;
     // stage 7 (pgm_mem.cuh): index of the context's text in the cm_* buffers + the destination text and the match lists
@@ -712,6 +715,7 @@ int pgm_create(int device, pgm_ctx **out) {
     if (const char *t = getenv("PGM_BLOCKED_SCAN")) ctx->blocked_scan = atoi(t);
     if (const char *t = getenv("PGM_PART_SCAN")) ctx->part_scan = atoi(t);
     if (const char *t = getenv("PGM_PART_MB")) ctx->part_mb = std::max(1, atoi(t));
+    if (const char *t = getenv("PGM_CM_WARP")) ctx->cm_warp = atoi(t);
     if (const char *t = getenv("PGM_REGION_MB")) ctx->region_mb = std::max(1, atoi(t));
     if (const char *t = getenv("PGM_RANGE_MB")) ctx->range_mb = std::max(1, atoi(t));
     if (const char *g = getenv("PGM_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));   // experiment knob
@@ -757,7 +761,7 @@ void pgm_destroy(pgm_ctx *ctx) {
                       &ctx->rt_cand_send2[1], &ctx->rt_cand_recv2[0], &ctx->rt_cand_recv2[1], &ctx->rt_pat_recv, &ctx->rt_counters, &ctx->rt_live, &ctx->rt_live_count,
                       &ctx->mem_dlo, &ctx->mem_dhi, &ctx->mem_dinv, &ctx->mem_stage, &ctx->mem_fv, &ctx->mem_has, &ctx->mem_emit, &ctx->mem_gcount,
                       &ctx->mem_gstart, &ctx->mem_raw, &ctx->mem_rawq, &ctx->mem_keep, &ctx->mem_kstart, &ctx->mem_out,
-                      &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums, &ctx->cm_nib, &ctx->cm_coarse,
+                      &ctx->cm_count, &ctx->cm_start, &ctx->cm_cumm, &ctx->cm_fill, &ctx->cm_hash, &ctx->cm_all, &ctx->cm_entries, &ctx->cm_sums, &ctx->cm_nib, &ctx->cm_coarse, &ctx->cmw_lens, &ctx->cmw_cand, &ctx->cmw_vt, &ctx->cmw_nvt,
                       &ctx->counters, &ctx->hist, &ctx->err_flag, &ctx->out_pos, &ctx->out_rc, &ctx->out_mm};
     for (DevBuf *b : bufs) release(*b);
     for (const pgm_ctx::EvPair &e : ctx->ev_used) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -1466,6 +1470,34 @@ int pgm_copmem_pass(pgm_ctx *ctx, int rev_mode) {
     // every read on its own (ReadsMatchers.cpp:425-448)
     ctx->state_fresh = false;
     ctx->outputs_valid = false;
+    const uint32_t n_off = ctx->read_len >= cp.K ? (ctx->read_len - cp.K) / cp.k2 + 1 : 0;
+    if (ctx->cm_warp && n_off) {
+        // staged query (pgm_copmem_warp.cuh): compact bucket directory, then per batch of reads: stage 1 (warp per read), stage 2
+        // (replay, thread per read), and the thread-per-read kernel for the reads whose table overflowed
+        if ((rc = ensure(ctx, ctx->cm_nib, hs / 8 * 4 + 64)) || (rc = ensure(ctx, ctx->cm_coarse, hs / 64 * 4 + 64))) return rc;
+        cp.nib = ctx->cm_nib.as<uint32_t>(); cp.coarse = ctx->cm_coarse.as<uint32_t>();
+        KLAUNCH(PGM_K_COPMEM_INDEX, "cm_compact_kernel", pgm::cm_compact_kernel<<<grid_for(hs / 8, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(cp));
+        const uint32_t cap = n_off * (PGM_CM_COLLISIONS_LIMIT + 1);
+        const size_t per_read = (size_t)n_off + cap + PGM_CMW_VT * 8 + 1;
+        const uint32_t batch = (uint32_t)std::min<uint64_t>(n, std::max<uint64_t>(1024, (6ull << 30) / per_read));
+        if ((rc = ensure(ctx, ctx->cmw_lens, (size_t)batch * n_off)) || (rc = ensure(ctx, ctx->cmw_cand, (size_t)batch * cap)) ||
+            (rc = ensure(ctx, ctx->cmw_vt, (size_t)batch * PGM_CMW_VT * 8)) || (rc = ensure(ctx, ctx->cmw_nvt, batch))) return rc;
+        for (uint32_t rb = 0; rb < n; rb += batch) {
+            pgm::CmwParams q;
+            memset(&q, 0, sizeof q);
+            q.c = cp; q.n_off = n_off; q.cap = cap; q.r_begin = rb; q.r_count = std::min(batch, n - rb);
+            q.lens = ctx->cmw_lens.as<uint8_t>(); q.cand = ctx->cmw_cand.as<uint8_t>();
+            q.vt = ctx->cmw_vt.as<unsigned long long>(); q.n_vt = ctx->cmw_nvt.as<uint8_t>();
+            KLAUNCH(PGM_K_COPMEM_QUERY, "cmw_stage1_kernel", pgm::cmw_stage1_kernel<<<grid_for(q.r_count, PGM_CMW_WARPS), PGM_CMW_WARPS * 32, 0, ctx->stream>>>(q));
+            KLAUNCH(PGM_K_COPMEM_QUERY, "cmw_stage2_kernel", pgm::cmw_stage2_kernel<<<grid_for(q.r_count, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(
+                q, ctx->counters.as<unsigned long long>()));
+            pgm::CopmemParams cf = cp;
+            cf.only_marked = q.n_vt; cf.marked_base = rb; cf.marked_count = q.r_count;
+            KLAUNCH(PGM_K_COPMEM_QUERY, "cm_query_kernel (table overflow)", pgm::cm_query_kernel<<<grid_for(n, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(
+                cf, ctx->counters.as<unsigned long long>()));
+        }
+        return PGM_OK;
+    }
     KLAUNCH(PGM_K_COPMEM_QUERY, "cm_query_kernel", pgm::cm_query_kernel<<<grid_for(n, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(
         cp, ctx->counters.as<unsigned long long>()));
     return PGM_OK;

@@ -44,6 +44,9 @@ struct CopmemParams {
     ReadsView reads;
     uint32_t n_reads, max_mm, min_mm;
     int rev_mode;
+    // (pgm_copmem_warp.cuh) cm_query_kernel for the marked reads only: only_marked[r - marked_base] == 0xFF; nullptr = every read
+    const uint8_t *only_marked;
+    uint32_t marked_base, marked_count;
 };
 
 // four ASCII characters of four 2-bit codes: index = lo nibble | hi nibble << 4 (character t at bits t / t + 4)
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(PGM_CM_THREADS, 4) cm_query_kernel(const __gri
     cm_build_lut(lut);
     const uint32_t r = blockIdx.x * PGM_CM_THREADS + threadIdx.x;
     if (r >= p.n_reads) return;
+    if (p.only_marked && (r < p.marked_base || r - p.marked_base >= p.marked_count || p.only_marked[r - p.marked_base] != 0xFFu)) return;
     uint32_t stride16; bool is_n;
     uint4 *rec = record_of(p.reads, r, stride16, is_n);
     const uint4 hd = __ldcg(rec);

@@ -490,6 +490,23 @@ def test_copmem_mode_workloads_and_edges():
     _check(inp, matching_mode="c")
 
 
+def test_copmem_staged_query_forced(monkeypatch):
+    """PGM_CM_WARP=1: mode 'c' through the staged per-read query (pgm_copmem_warp.cuh: a warp per read gathers the candidates of
+    all offsets and verifies each distinct alignment once, a thread per read replays the reference's sequential loop over the
+    table indices; reads with more than 32 distinct alignments go to the thread-per-read kernel) — same results as the oracle
+    on the adversarial inputs, the parameter matrix, N reads, texts around K, hot seeds (table overflow) and a workload."""
+    monkeypatch.setenv("PGM_CM_WARP", "1")
+    for seed, L in ((121, 100), (122, 150), (123, 120), (124, 64), (125, 255)):
+        _check(synth.adversarial(seed, L), matching_mode="c")
+    for kw in (dict(matching_mode="c", reads_exact_matching_chars=30), dict(matching_mode="c", reads_exact_matching_chars=64),
+               dict(matching_mode="c", reads_exact_matching_chars=24), dict(matching_mode="c", reads_exact_matching_chars=100),
+               dict(matching_mode="C"), dict(matching_mode="c", pre_reads_exact_matching_chars=50, pre_matching_mode="c"),
+               dict(matching_mode="c", pre_reads_exact_matching_chars=100, pre_matching_mode="d"),
+               dict(matching_mode="c", min_chars_per_mismatch=2), dict(matching_mode="c", rev_compl_pg=False)):
+        _check(synth.adversarial(126, 100), **kw)
+    test_copmem_mode_workloads_and_edges()
+
+
 @pytest.mark.parametrize("chunk", range(4))
 def test_randomized_sweep_over_modes_and_parameters(chunk):
     """40 random (input, parameter) combinations — read lengths 40..255, seeds from 12 (24 for CopMEM) to beyond the read length,
