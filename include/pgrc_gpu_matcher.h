@@ -355,6 +355,7 @@ enum { PGM_K_PACK_TEXT = 0, PGM_K_RC_TEXT, PGM_K_UNPACK_READS, PGM_K_INIT_STATE,
        PGM_K_MISMATCHES, PGM_K_COPMEM_INDEX, PGM_K_COPMEM_QUERY,
        PGM_K_ROUTE_BUILD, PGM_K_ROUTE_SCAN, PGM_K_ROUTE_PROBE, PGM_K_ROUTE_VERIFY, /* the routed multi-GPU scheme */
        PGM_K_MEM_PACK, PGM_K_MEM_QUERY, PGM_K_MEM_EMIT,                            /* stage 7 (the index is PGM_K_COPMEM_INDEX) */
+       PGM_K_COPMEM_STAGE1, PGM_K_COPMEM_STAGE2,                                   /* the staged mode-c query (PGM_CM_WARP=1) */
        PGM_K_COUNT };
 typedef struct pgm_timings {
     double ms[PGM_K_COUNT];

@@ -33,7 +33,8 @@ EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pg
 
 KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators",
                 "scan_filter", "scan_probe", "scan_verify", "mismatches", "copmem_index", "copmem_query",
-                "route_build", "route_scan", "route_probe", "route_verify", "mem_pack", "mem_query", "mem_emit"]
+                "route_build", "route_scan", "route_probe", "route_verify", "mem_pack", "mem_query", "mem_emit",
+                "copmem_stage1", "copmem_stage2"]
 PGM_ROUTE_MAX_WORLD = 16
 PGM_ROUTE_PATTERNS, PGM_ROUTE_WINDOWS, PGM_ROUTE_CANDIDATES = 0, 1, 2
 

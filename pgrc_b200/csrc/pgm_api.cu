@@ -1488,8 +1488,8 @@ int pgm_copmem_pass(pgm_ctx *ctx, int rev_mode) {
             q.c = cp; q.n_off = n_off; q.cap = cap; q.r_begin = rb; q.r_count = std::min(batch, n - rb);
             q.lens = ctx->cmw_lens.as<uint8_t>(); q.cand = ctx->cmw_cand.as<uint8_t>();
             q.vt = ctx->cmw_vt.as<unsigned long long>(); q.n_vt = ctx->cmw_nvt.as<uint8_t>();
-            KLAUNCH(PGM_K_COPMEM_QUERY, "cmw_stage1_kernel", pgm::cmw_stage1_kernel<<<grid_for(q.r_count, PGM_CMW_WARPS), PGM_CMW_WARPS * 32, 0, ctx->stream>>>(q));
-            KLAUNCH(PGM_K_COPMEM_QUERY, "cmw_stage2_kernel", pgm::cmw_stage2_kernel<<<grid_for(q.r_count, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(
+            KLAUNCH(PGM_K_COPMEM_STAGE1, "cmw_stage1_kernel", pgm::cmw_stage1_kernel<<<grid_for(q.r_count, PGM_CMW_WARPS), PGM_CMW_WARPS * 32, 0, ctx->stream>>>(q));
+            KLAUNCH(PGM_K_COPMEM_STAGE2, "cmw_stage2_kernel", pgm::cmw_stage2_kernel<<<grid_for(q.r_count, PGM_CM_THREADS), PGM_CM_THREADS, 0, ctx->stream>>>(
                 q, ctx->counters.as<unsigned long long>()));
             pgm::CopmemParams cf = cp;
             cf.only_marked = q.n_vt; cf.marked_base = rb; cf.marked_count = q.r_count;

@@ -4,8 +4,8 @@
 // cm_query_kernel replays processApproxMatchQueryTight (CopMEMMatcher.cpp:483-566) with one thread per read: about 62 read
 // offsets x 2.2 bucket entries = 135 candidate verifications per read at config 2, strictly one after the other, and a warp
 // whose 32 reads are at different points of that chain runs with 11.7 of 32 lanes active (profiles/cm_query_full_r01y.json).
-// The staged form (oracle/pgrc_oracle.c: copmem_query_staged is its CPU model, equal to the sequential transcription incl. the
-// log-only counters):
+// The staged form (the test oracle carries a CPU model of it, copmem_query_staged, equal to its sequential transcription of the
+// reference incl. the log-only counters):
 //   cmw_stage1_kernel  a WARP per read.  Lane <-> read offset: hash, bucket bounds (compact L2 directory, cm_bucket), then the
 //                      bucket entries of all 32 offsets side by side; an entry becomes its alignment start a = sp - i1 or
 //                      "skipped" (:512, :514).  The DISTINCT alignments of a read (3 - 4 at config 2: the same ones come back at
