@@ -21,7 +21,7 @@ def kernels_sha():
     h = hashlib.sha256()
     d = os.path.join(ROOT, "pgrc_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.startswith("pgm_") and f.endswith(".cuh"):      # the kernels; pgm_api.cu / pgm_group.inl are host plumbing
+        if f == "pgm_kernels.cuh":      # the file scan_kernel (and the other stage-4 kernels) is compiled from
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -61,7 +61,7 @@ def main():
         h = hashlib.sha256()
         csrc = os.path.join(ROOT, "pgrc_b200", "csrc")
         for f in sorted(os.listdir(csrc)):
-            if f.startswith("pgm_") and f.endswith(".cuh"):      # the kernels; pgm_api.cu / pgm_group.inl are host plumbing
+            if f == "pgm_kernels.cuh":      # the file scan_kernel (and the other stage-4 kernels) is compiled from
                 h.update(open(os.path.join(csrc, f), "rb").read())
         t[workload] = {"dram_bytes_per_launch": int(sum(traffic) / len(traffic)),
                        "kernels_sha": sys.argv[5] if len(sys.argv) > 5 else h.hexdigest()[:16],
