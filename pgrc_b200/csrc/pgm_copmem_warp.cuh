@@ -8,8 +8,8 @@
 // reference incl. the log-only counters):
 //   cmw_stage1_kernel  a WARP per read.  Lane <-> read offset: hash, bucket bounds (compact L2 directory, cm_bucket), then the
 //                      bucket entries of all 32 offsets side by side; an entry becomes its alignment start a = sp - i1 or
-//                      "skipped" (:512, :514).  The DISTINCT alignments of a read (3 - 4 at config 2: the same ones come back at
-//                      most offsets) are verified ONCE each, by one lane, with both mismatch counts in full, and kept in a
+//                      "skipped" (:512, :514).  The DISTINCT alignments of a read (the true ones come back at most offsets) are
+//                      verified ONCE each, by one lane, with both mismatch counts in full, and kept in a
 //                      32-entry table; every candidate is written out as a one-byte index into that table.
 //   cmw_stage2_kernel  a thread per read replays the sequential loop over those bytes: bucket truncation by the false-match
 //                      budget (:505-509), +1 / +2 false matches (:528-543), strict improvement, stop at min_mm — 135 table
@@ -17,6 +17,14 @@
 //   cm_query_kernel    once more, for the reads with more than 32 distinct alignments only (CopmemParams::only_marked).
 // Exact because a verification's outcome under ANY limit follows from the two full counts (blocks > limit: +1 false match;
 // else blocks + tail > limit: +2; else accept).
+// STATUS: opt-in, bit-exact (tests/test_gpu_parity.py::test_copmem_staged_query_forced, config 2 at full size against the
+// sampled oracle), and SLOWER than the default as built: 165 ms per config-2 step against 77 (profiles/bench_c2_mode_c_warp_r02am.json).
+// Two measured reasons.  (1) A looked-up bucket holds 0.84 unrelated text positions on average (28 M samples in 2^25 hash
+// values) next to the true ones, so a config-2 read has about 55 DISTINCT alignments, not 3 - 4: the 32-entry table overflows
+// for most reads and the thread-per-read kernel redoes them (68 ms).  (2) Stage 1 walks the buckets entry by entry, one
+// dependent load and several warp-wide exchanges per step: 89 ms although it stops at the overflow.  What it needs next: a
+// 128-entry hashed table, the bucket entries of a batch loaded in bulk before they are looked at, and early rejection of the
+// chance hits (one 32-base group decides almost all of them) before the full counts.
 #pragma once
 #include "pgm_copmem.cuh"
 
