@@ -79,6 +79,8 @@ def _oracle():
         lib.pgo_mismatch_lists.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
                                            ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.pgo_set_copmem_staged.restype = None
+        lib.pgo_set_copmem_staged.argtypes = [ctypes.c_int]
         lib.pgo_match_texts.restype = ctypes.c_int
         lib.pgo_match_texts.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
@@ -142,6 +144,12 @@ def pack_reads(reads_ascii: np.ndarray, read_len: int, with_n: bool, use_ref: bo
         if r != packed_len:
             raise ValueError(f"pack_reads failed ({r})")
     return out
+
+
+def set_copmem_staged(on: bool) -> None:
+    """Mode 'c' of oracle_map_reads through the STAGED form of the per-read query (copmem_query_staged: the CPU model of the
+    warp-per-read CUDA kernels of pgm_copmem_warp.cuh) instead of the sequential transcription."""
+    _oracle().pgo_set_copmem_staged(int(on))
 
 
 def _mode(c: str) -> bytes:
