@@ -334,6 +334,15 @@ int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is
                   uint32_t min_match_length, uint64_t *count);
 int pgm_mem_get_matches(pgm_ctx *ctx, pgm_text_match *out, uint64_t capacity);
 
+/* One rank of several (one process per GPU, the source text and its index on every GPU): the matches of the part-th of
+ * n_parts shares of the groups of 256 query positions, in push order but BEFORE the "covered by the previous match" test
+ * (:388-393), with the query position of each — the caller concatenates the shares in rank order and drops an element whose
+ * diagonal (pos_dest - pos_src) equals its predecessor's and whose query position + K lies below the predecessor's
+ * pos_dest + length (pgrc_b200/matcher.py: merge_text_match_shares; pgm_group_mem_match does the same inside one process). */
+int pgm_mem_match_share(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
+                        uint32_t min_match_length, int part, int n_parts, uint64_t *count);
+int pgm_mem_get_share(pgm_ctx *ctx, pgm_text_match *out_matches, uint64_t *out_query_pos, uint64_t capacity);
+
 /* The same on a group of contexts (pgm_group_set_text gave every GPU the source text): every GPU builds the index; the groups
  * of 256 query positions of a destination text are independent, GPU r takes the r-th share of them, and the shares are
  * concatenated (the "covered by the previous match" test, :388-393, runs across the seams).  Same results as one context. */

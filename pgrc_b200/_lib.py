@@ -29,7 +29,7 @@ EXPORTS = ["pgm_abi_version", "pgm_create", "pgm_destroy", "pgm_last_error", "pg
            "pgm_group_upload", "pgm_group_match_begin", "pgm_group_pass", "pgm_group_copmem_begin", "pgm_group_copmem_pass",
            "pgm_group_get_results", "pgm_group_get_mismatches",
            "pgm_mem_index", "pgm_mem_match", "pgm_mem_get_matches",
-           "pgm_group_mem_index", "pgm_group_mem_match", "pgm_group_mem_get_matches"]
+           "pgm_group_mem_index", "pgm_group_mem_match", "pgm_group_mem_get_matches", "pgm_mem_match_share", "pgm_mem_get_share"]
 
 KERNEL_NAMES = ["pack_text", "rc_text", "unpack_reads", "init_state", "build_table", "scan", "resolve", "finalize", "accumulators",
                 "scan_filter", "scan_probe", "scan_verify", "mismatches", "copmem_index", "copmem_query",
@@ -145,6 +145,8 @@ def load() -> ctypes.CDLL:
     lib.pgm_mem_index.restype = ci; lib.pgm_mem_index.argtypes = [vp, u32, u32, ctypes.POINTER(u32)]
     lib.pgm_mem_match.restype = ci; lib.pgm_mem_match.argtypes = [vp, vp, u64, ci, ci, u32, ctypes.POINTER(u64)]
     lib.pgm_mem_get_matches.restype = ci; lib.pgm_mem_get_matches.argtypes = [vp, vp, u64]
+    lib.pgm_mem_match_share.restype = ci; lib.pgm_mem_match_share.argtypes = [vp, vp, u64, ci, ci, u32, ci, ci, ctypes.POINTER(u64)]
+    lib.pgm_mem_get_share.restype = ci; lib.pgm_mem_get_share.argtypes = [vp, vp, vp, u64]
     lib.pgm_group_mem_index.restype = ci; lib.pgm_group_mem_index.argtypes = [vp, u32, u32, ctypes.POINTER(u32)]
     lib.pgm_group_mem_match.restype = ci; lib.pgm_group_mem_match.argtypes = [vp, vp, u64, ci, ci, u32, ctypes.POINTER(u64)]
     lib.pgm_group_mem_get_matches.restype = ci; lib.pgm_group_mem_get_matches.argtypes = [vp, vp, u64]

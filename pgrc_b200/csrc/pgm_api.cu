@@ -112,7 +112,7 @@ struct pgm_ctx {
     bool mem_index_valid = false;
     uint32_t mem_L = 0, mem_K = 0, mem_k1 = 0, mem_k2 = 0, mem_hash_size = 0;
     uint64_t mem_count = 0;
-    bool mem_result_valid = false;
+    bool mem_result_valid = false, mem_share_valid = false;
     uint32_t bq_cap = 0, bq_region_bits = 0;
     bool bq_pending = false;    // region queues hold patterns that build_insert_kernel has not inserted yet
     uint64_t n_slots = 0;
@@ -2302,7 +2302,31 @@ extern "C" {
 
 int pgm_mem_match(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
                   uint32_t min_match_length, uint64_t *count) {
+    if (ctx) ctx->mem_share_valid = false;
     return mem_match_impl(ctx, dest, dest_len, dest_is_src, rev_compl, min_match_length, count, 0, 1, false);
+}
+
+int pgm_mem_match_share(pgm_ctx *ctx, const char *dest, uint64_t dest_len, int dest_is_src, int rev_compl,
+                        uint32_t min_match_length, int part, int n_parts, uint64_t *count) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (n_parts < 1 || part < 0 || part >= n_parts) return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_mem_match_share: need 0 <= part < n_parts");
+    ctx->mem_share_valid = false;
+    const int rc = mem_match_impl(ctx, dest, dest_len, dest_is_src, rev_compl, min_match_length, count, part, n_parts, true);
+    if (rc == PGM_OK) { ctx->mem_share_valid = true; ctx->mem_result_valid = false; }
+    return rc;
+}
+
+int pgm_mem_get_share(pgm_ctx *ctx, pgm_text_match *out_matches, uint64_t *out_query_pos, uint64_t capacity) {
+    if (!ctx) return PGM_ERR_INVALID_ARG;
+    if (!ctx->mem_share_valid) return fail(ctx, PGM_ERR_STATE, "pgm_mem_get_share: no result (call pgm_mem_match_share)");
+    if (capacity < ctx->mem_count || (ctx->mem_count && (!out_matches || !out_query_pos)))
+        return fail(ctx, PGM_ERR_INVALID_ARG, "pgm_mem_get_share: capacity below the share's size");
+    if (!ctx->mem_count) return PGM_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(out_matches, ctx->mem_raw.p, (size_t)ctx->mem_count * sizeof(pgm_text_match), cudaMemcpyDefault, ctx->stream));
+    CU(cudaMemcpyAsync(out_query_pos, ctx->mem_rawq.p, (size_t)ctx->mem_count * 8, cudaMemcpyDefault, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PGM_OK;
 }
 
 int pgm_mem_get_matches(pgm_ctx *ctx, pgm_text_match *out, uint64_t capacity) {

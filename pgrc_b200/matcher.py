@@ -365,6 +365,20 @@ class GpuTextMatcher:
         self.m._check(self.m._lib.pgm_mem_get_matches(self.m._h, out.ctypes.data if out.size else None, int(cnt.value)))
         return out
 
+    def match_texts_share(self, dest_text, dest_is_src: bool, rev_compl_matching: bool, part: int, n_parts: int,
+                          min_match_length: int = 0xFFFFFFFF):
+        """One rank of several (one process per GPU): the part-th share of the groups of 256 query positions — (matches (n, 3),
+        query positions (n,)) in push order before the "covered by the previous match" test; merge_text_match_shares joins
+        the shares."""
+        n2 = 0 if dest_text is None else (dest_text.numel() if hasattr(dest_text, "numel") else dest_text.size)
+        cnt = ctypes.c_uint64(0)
+        self.m._check(self.m._lib.pgm_mem_match_share(self.m._h, _ptr(dest_text), n2, int(dest_is_src), int(rev_compl_matching),
+                                                      min(min_match_length, 0xFFFFFFFF), part, n_parts, ctypes.byref(cnt)))
+        n = int(cnt.value)
+        out, qpos = np.empty((n, 3), np.uint64), np.empty(n, np.uint64)
+        self.m._check(self.m._lib.pgm_mem_get_share(self.m._h, out.ctypes.data if n else None, qpos.ctypes.data if n else None, n))
+        return out, qpos
+
     def close(self):
         if self._own and self.m is not None:
             self.m.close()
@@ -375,6 +389,29 @@ class GpuTextMatcher:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def merge_text_match_shares(shares, K: int) -> np.ndarray:
+    """resMatches from the shares of all ranks, in rank order: an element is dropped when it is its predecessor's match —
+    same diagonal, and its K-mer ends inside the predecessor (CopMEMMatcher.cpp:388-393).  shares: [(matches (n, 3), query
+    positions (n,)), ...] as GpuTextMatcher.match_texts_share returns them."""
+    m = np.concatenate([np.asarray(s[0], np.uint64).reshape(-1, 3) for s in shares]) if shares else np.zeros((0, 3), np.uint64)
+    q = np.concatenate([np.asarray(s[1], np.uint64).reshape(-1) for s in shares]) if shares else np.zeros(0, np.uint64)
+    if len(m) < 2:
+        return m
+    diag = m[:, 2] - m[:, 0]                                    # (unsigned wrap-around on both sides, as in the reference)
+    same = (diag[1:] == diag[:-1]) & (q[1:] + np.uint64(K) < m[:-1, 2] + m[:-1, 1])
+    return m[np.concatenate([[True], ~same])]
+
+
+def match_texts_distributed(tm, comm_world: int, rank: int, all_gather_arrays, dest_text, dest_is_src: bool = False,
+                            rev_compl_matching: bool = True, min_match_length: int = 0xFFFFFFFF) -> np.ndarray:
+    """Stage 7 with one process per GPU: this rank's share of the query groups, an all-gather of the (small) shares, the merge.
+    tm: a text matcher with match_texts_share and K (GpuTextMatcher); all_gather_arrays(list of numpy arrays) -> per rank
+    lists (TorchComm.all_gather_arrays).  Every rank returns the whole resMatches vector."""
+    mine = tm.match_texts_share(dest_text, dest_is_src, rev_compl_matching, rank, comm_world, min_match_length)
+    shares = all_gather_arrays([mine[0].reshape(-1), mine[1]])
+    return merge_text_match_shares([(s[0].reshape(-1, 3), s[1]) for s in shares], tm.K)
 
 
 class GpuMatcherGroup:
@@ -611,6 +648,25 @@ class TorchComm:
         dist.all_gather_into_tensor(allb, mine, group=self.group)
         raw = allb.cpu().numpy().tobytes()
         return [raw[r * len(blob):(r + 1) * len(blob)] for r in range(self.world)]
+
+    def all_gather_arrays(self, arrays, device="cpu"):
+        """Every rank's list of 1-D uint64 numpy arrays (sizes differ between ranks), in rank order: [[a0, a1, ...] of rank 0, ...]."""
+        import torch
+        import torch.distributed as dist
+        sizes = torch.tensor([len(a) for a in arrays], dtype=torch.int64, device=device)
+        all_sizes = [torch.zeros_like(sizes) for _ in range(self.world)]
+        dist.all_gather(all_sizes, sizes, group=self.group)
+        out = [[] for _ in range(self.world)]
+        for k, a in enumerate(arrays):
+            mx = max(int(sz[k].item()) for sz in all_sizes)
+            mine = torch.zeros(max(mx, 1), dtype=torch.int64, device=device)
+            if len(a):
+                mine[:len(a)] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).to(device)
+            bufs = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(bufs, mine, group=self.group)
+            for r in range(self.world):
+                out[r].append(bufs[r][:int(all_sizes[r][k].item())].cpu().numpy().view(np.uint64).copy())
+        return out
 
     def all_to_all_async(self, recv, send):
         """send[d] -> rank d, recv[s] <- rank s (uint8 tensors or None for empty segments): NCCL send/recv pairs on the

@@ -62,7 +62,18 @@ def hashes(text, starts, K, hash_size):
     return (h & np.uint64(0xFFFFFFFF) & np.uint64(hash_size - 1)).astype(np.int64)
 
 
-def match_texts(src, dest, dest_is_src, rev_compl, target_len, min_len=0xFFFFFFFF, n_parts=1):
+class CpuTextMatcher:
+    """Same interface as pgrc_b200.matcher.GpuTextMatcher's share call (for the world_size > 1 gloo tests of the host logic)."""
+
+    def __init__(self, src, target_len):
+        self.src, self.target_len = np.asarray(src, np.uint8), target_len
+        self.K, self.k1, self.k2, self.hash_size = derive(target_len, 0xFFFFFFFF, len(self.src))
+
+    def match_texts_share(self, dest, dest_is_src, rev_compl, part, n_parts, min_len=0xFFFFFFFF):
+        return match_texts(self.src, dest, dest_is_src, rev_compl, self.target_len, min_len, share=(part, n_parts))
+
+
+def match_texts(src, dest, dest_is_src, rev_compl, target_len, min_len=0xFFFFFFFF, n_parts=1, share=None):
     """n_parts > 1: the groups of 256 query positions shared out over that many contexts as pgm_group_mem_match does it
     (context r: groups [G r / n, G (r + 1) / n)), the shares concatenated and the suppression test run across the seams."""
     src = np.asarray(src, np.uint8); dest = np.asarray(dest, np.uint8)
@@ -111,7 +122,10 @@ def match_texts(src, dest, dest_is_src, rev_compl, target_len, min_len=0xFFFFFFF
     assert nq == 0 or n_groups + 1 == (nq + MULTI - 1) // MULTI      # the tail (:422-473) has 1 .. 256 positions: ceil(nq / 256) groups in all
     groups = (nq + MULTI - 1) // MULTI
     visited = []
-    for r in range(n_parts):                                           # (a context's share; the walk of a group never looks outside it)
+    parts = [share[0]] if share is not None else range(n_parts)
+    if share is not None:
+        n_parts = share[1]
+    for r in parts:                                                    # (a context's share; the walk of a group never looks outside it)
         for g in range(groups * r // n_parts, groups * (r + 1) // n_parts):
             t, end = g * MULTI, min((g + 1) * MULTI, nq)
             while t < end:
@@ -119,6 +133,8 @@ def match_texts(src, dest, dest_is_src, rev_compl, target_len, min_len=0xFFFFFFF
                     visited.append(t); t += skip + 1
                 else:
                     t += 1
+    if share is not None:                                              # one rank's share: raw matches + their query positions
+        return (np.array([fvm[t] for t in visited], np.uint64).reshape(-1, 3), np.array([t * k2 for t in visited], np.uint64))
     out, prev = [], None
     for t in visited:
         m, q = fvm[t], t * k2

@@ -118,6 +118,21 @@ def test_group_of_contexts_shares_the_query_groups(n_ctx):
         assert total > 100
 
 
+@pytest.mark.parametrize("n_parts", [1, 2, 4])
+def test_shares_of_one_rank_each_merge_to_the_oracle_result(n_parts):
+    """pgm_mem_match_share / pgm_mem_get_share (one process per GPU: rank r computes the r-th share) + the product's merge
+    (matcher.merge_text_match_shares), all shares computed here on one GPU one after the other."""
+    src, dest = synth.pg_texts(990 + n_parts, 50000, 16000, max_copy=5000, self_rc=50)
+    with matcher.GpuTextMatcher(src, 45) as tm:
+        for d, dis, rc in ((dest, False, True), (src, True, True), (dest[:500], False, False)):
+            q = oracle.reverse_complement(d) if rc else np.ascontiguousarray(d)
+            want = oracle.oracle_match_texts(src, q, dis, rc, 45)
+            shares = [tm.match_texts_share(None if dis else q, dis, rc, r, n_parts) for r in range(n_parts)]
+            got = matcher.merge_text_match_shares(shares, tm.K)
+            assert got.shape == want.shape and np.array_equal(got, want), (n_parts, dis, rc)
+            assert np.array_equal(tm.match_texts(None if dis else q, dis, rc), want)      # (a plain call after the shares)
+
+
 @pytest.mark.skipif(not GOLDEN, reason="no pgmatch golden vectors")
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_reference_golden_vectors(path):

@@ -193,3 +193,45 @@ def test_routed_ranks_gloo(tmp_path, world, round_windows, kw):
         assert np.array_equal(got["pos"], want.pos[lo:hi]), f"rank {rank}"
         assert np.array_equal(got["rc"], want.rc[lo:hi]) and np.array_equal(got["mm"], want.mm[lo:hi])
         assert (int(got["rounds"]) > 1) == bool(round_windows)
+
+
+def _worker_pgmatch(rank, world, port, seed, ret_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    import oracle
+    from cpu_mem_model import CpuTextMatcher
+    from pgrc_b200 import matcher, synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = matcher.TorchComm()
+    src, dest = synth.pg_texts(seed, 20000, 7000, max_copy=4000, self_rc=30)
+    tm = CpuTextMatcher(src, 45)
+    out = {}
+    for tag, dis, rc in (("lq", False, True), ("fw", False, False), ("self", True, True)):
+        d = src if dis else dest
+        q = oracle.reverse_complement(d) if rc else d
+        out[tag] = matcher.match_texts_distributed(tm, world, rank, comm.all_gather_arrays, q, dis, rc)
+    np.savez(os.path.join(ret_dir, f"pgmatch_rank{rank}.npz"), **out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_stage7_shares_merged_over_gloo(tmp_path, world):
+    """Stage 7 with one process per GPU (matcher.match_texts_distributed): every rank takes its share of the groups of 256 query
+    positions, the shares are all-gathered over torch.distributed and merged (merge_text_match_shares: the "covered by the previous
+    match" test across the seams) — the per-rank kernels replaced by tests/cpu_mem_model.py, the host logic the product's own."""
+    import oracle
+    from pgrc_b200 import synth
+    mp.spawn(_worker_pgmatch, args=(world, _free_port(), 970 + world, str(tmp_path)), nprocs=world, join=True)
+    src, dest = synth.pg_texts(970 + world, 20000, 7000, max_copy=4000, self_rc=30)
+    total = 0
+    for tag, dis, rc in (("lq", False, True), ("fw", False, False), ("self", True, True)):
+        d = src if dis else dest
+        q = oracle.reverse_complement(d) if rc else d
+        want = oracle.oracle_match_texts(src, q, dis, rc, 45)
+        total += len(want)
+        for rank in range(world):
+            got = np.load(tmp_path / f"pgmatch_rank{rank}.npz")[tag]
+            assert got.shape == want.shape and np.array_equal(got, want), (tag, rank)
+    assert total > 20
